@@ -1,0 +1,204 @@
+/*
+ * orc_b200.h — C ABI of the B200-native ORC stripe decoder (drop-in boundary for orc-rust's decode path).
+ *
+ * This is exactly what a Rust `orc-rust-cuda` crate's `extern "C"` block would bind.
+ * Plain pointers and sizes only; Arrow data crosses as the Arrow C Data / C Device Data interface.
+ * Reference citations are file:line in datafusion-contrib/orc-rust v0.8.0.
+ *
+ * Threading: handles are not thread-safe; distinct handles may be used from distinct threads.
+ * Errors: every call returns 0 (ORCB_OK) or an OrcbStatus; details via orcb_last_error().  Nothing
+ * panics or aborts across this boundary (reference panics are reported as ORCB_OUT_OF_SPEC).
+ */
+#ifndef ORC_B200_H
+#define ORC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Status = orc-rust `OrcError` variant ordinal + 1 (src/error.rs:31-174), then device-path additions. */
+typedef enum OrcbStatus {
+    ORCB_OK = 0,
+    ORCB_IO_ERROR = 1,
+    ORCB_EMPTY_FILE = 2,
+    ORCB_OUT_OF_SPEC = 3,
+    ORCB_DECODE_FLOAT = 4,
+    ORCB_DECODE_TIMESTAMP = 5,
+    ORCB_OFFSET_OVERFLOW = 6,
+    ORCB_DECODE_PROTO = 7,
+    ORCB_NO_TYPES = 8,
+    ORCB_UNSUPPORTED_TYPE_VARIANT = 9,
+    ORCB_MISMATCHED_SCHEMA = 10,
+    ORCB_CONVERT_RECORD_BATCH = 11,
+    ORCB_VARINT_TOO_LARGE = 12,
+    ORCB_UNEXPECTED = 13,
+    ORCB_BUILD_ZSTD_DECODER = 14,
+    ORCB_BUILD_SNAPPY_DECODER = 15,
+    ORCB_BUILD_LZO_DECODER = 16,
+    ORCB_BUILD_LZ4_DECODER = 17,
+    ORCB_ARROW = 18,
+    /* new on the device path (BASELINE north_star): Zlib / Zstd / LZO are rejected, never CPU-decoded */
+    ORCB_UNSUPPORTED_DEVICE_CODEC = 19,
+    ORCB_CUDA = 20,
+    ORCB_INVALID_ARGUMENT = 21,
+    ORCB_NOT_IMPLEMENTED = 22,
+    ORCB_DEVICE_HEAP_OVERFLOW = 23
+} OrcbStatus;
+
+/* ---- Arrow C Data Interface (ABI-stable structs from the Arrow specification) ---- */
+#ifndef ARROW_C_DATA_INTERFACE
+#define ARROW_C_DATA_INTERFACE
+struct ArrowSchema {
+    const char* format;
+    const char* name;
+    const char* metadata;
+    int64_t flags;
+    int64_t n_children;
+    struct ArrowSchema** children;
+    struct ArrowSchema* dictionary;
+    void (*release)(struct ArrowSchema*);
+    void* private_data;
+};
+struct ArrowArray {
+    int64_t length;
+    int64_t null_count;
+    int64_t offset;
+    int64_t n_buffers;
+    int64_t n_children;
+    const void** buffers;
+    struct ArrowArray** children;
+    struct ArrowArray* dictionary;
+    void (*release)(struct ArrowArray*);
+    void* private_data;
+};
+#endif
+#ifndef ARROW_C_DEVICE_DATA_INTERFACE
+#define ARROW_C_DEVICE_DATA_INTERFACE
+typedef int32_t ArrowDeviceType;
+#define ARROW_DEVICE_CPU 1
+#define ARROW_DEVICE_CUDA 2
+struct ArrowDeviceArray {
+    struct ArrowArray array;
+    int64_t device_id;
+    ArrowDeviceType device_type;
+    void* sync_event; /* cudaEvent_t* or NULL */
+    int64_t reserved[3];
+};
+#endif
+
+typedef struct OrcbFile OrcbFile;     /* parsed file tail (FileMetadata, src/reader/metadata.rs:63-178) */
+typedef struct OrcbReader OrcbReader; /* ArrowReader (src/arrow_reader.rs:233-347) with a device */
+typedef struct OrcbJob OrcbJob;       /* one device launch plan over many stripes (new; no reference twin) */
+
+/* ---- file open: replaces ArrowReaderBuilder::try_new -> read_metadata
+ *      (src/arrow_reader.rs:202-205, src/reader/metadata.rs:180-263) ---- */
+/* The library borrows `data` for the life of the OrcbFile (the ChunkReader for Bytes, src/reader/mod.rs:64-76). */
+int orcb_open_memory(const uint8_t* data, size_t len, OrcbFile** out);
+/* Reads the whole file into (pinned, if a device is present) host memory owned by the handle
+ * (ChunkReader for File, src/reader/mod.rs:48-62). */
+int orcb_open_path(const char* path, OrcbFile** out);
+void orcb_file_free(OrcbFile* f);
+
+/* FileMetadata accessors (src/reader/metadata.rs:141-178) */
+uint64_t orcb_file_num_rows(const OrcbFile* f);
+uint32_t orcb_file_num_stripes(const OrcbFile* f);
+int32_t orcb_file_compression(const OrcbFile* f);          /* proto CompressionKind */
+uint64_t orcb_file_compression_block_size(const OrcbFile* f);
+int64_t orcb_file_row_index_stride(const OrcbFile* f);     /* -1 when absent */
+uint32_t orcb_file_num_root_columns(const OrcbFile* f);
+const char* orcb_file_root_column_name(const OrcbFile* f, uint32_t i);
+/* StripeMetadata (src/stripe.rs:38-81): out[0..5) = offset, index_length, data_length, footer_length, rows */
+int orcb_file_stripe_info(const OrcbFile* f, uint32_t stripe, uint64_t out[5]);
+
+/* ---- reader options: the ArrowReaderBuilder setters (src/arrow_reader.rs:39-198) + `device` ---- */
+typedef struct OrcbReadOptions {
+    int32_t device;            /* CUDA ordinal (with_device; new) */
+    uint32_t batch_size;       /* with_batch_size; 0 = default 8192 (src/arrow_reader.rs:37) */
+    const char* const* projection_names; /* with_projection(ProjectionMask::named_roots) or NULL = all */
+    uint32_t n_projection;
+    uint64_t range_start;      /* with_file_byte_range: stripes whose offset is in [start, end) */
+    uint64_t range_end;        /* 0,0 = no range */
+    int32_t timestamp_unit;    /* with_timestamp_precision: 0 = nanosecond (default), 1 = microsecond;
+                                  2 = millisecond, 3 = second (with_schema overrides) */
+    int32_t use_row_index;     /* 1 (default when 0 passed with flags==0): split streams at row-index positions */
+    int32_t device_resident;   /* 0: batches come back in host memory; 1: ArrowDeviceArray in HBM */
+    uint32_t max_stripes_per_launch; /* 0 = library default */
+    void* cuda_stream;         /* cudaStream_t to enqueue on, or NULL for the reader's own stream */
+    uint32_t flags;            /* bit0: no_row_index */
+    uint32_t stripe_shard_index;  /* multi-GPU stripe sharding: keep stripes with */
+    uint32_t stripe_shard_count;  /*   (ordinal % count) == index; count 0 or 1 = all */
+} OrcbReadOptions;
+
+/* ArrowReaderBuilder::schema (src/arrow_reader.rs:182-198) for the given options */
+int orcb_schema(const OrcbFile* f, const OrcbReadOptions* opt, struct ArrowSchema* out);
+
+/* ArrowReaderBuilder::build (src/arrow_reader.rs:207-230) */
+int orcb_reader_new(OrcbFile* f, const OrcbReadOptions* opt, OrcbReader** out);
+void orcb_reader_free(OrcbReader* r);
+/* ArrowReader::total_row_count (src/arrow_reader.rs:243-247) */
+uint64_t orcb_reader_total_row_count(const OrcbReader* r);
+/* Iterator::next (src/arrow_reader.rs:333-346): one RecordBatch as a struct ArrowArray in host memory.
+ * *eos = 1 and `out` untouched at end of stream. */
+int orcb_reader_next(OrcbReader* r, struct ArrowArray* out, int* eos);
+/* Same, batch buffers stay in HBM (device_type = ARROW_DEVICE_CUDA).  Requires device_resident = 1. */
+int orcb_reader_next_device(OrcbReader* r, struct ArrowDeviceArray* out, int* eos);
+
+/* ---- bulk job API: NaiveStripeDecoder::new_with_selection + drain (src/array_decoder/mod.rs:570-594,
+ *      371-387) for many stripes in one launch plan.  Used by the reader internally and by bench.py. ---- */
+int orcb_job_new(OrcbFile* const* files, uint32_t n_files, const OrcbReadOptions* opt, OrcbJob** out);
+void orcb_job_free(OrcbJob* j);
+/* Host planning only (no CUDA calls): builds every descriptor table. */
+int orcb_job_plan(OrcbJob* j);
+/* Allocates device arenas and copies compressed stripe bytes + descriptor tables H2D (async on the stream). */
+int orcb_job_stage(OrcbJob* j);
+/* Enqueues every decode kernel on the stream; returns without synchronising. */
+int orcb_job_launch(OrcbJob* j);
+/* Copies per-batch metadata + error words D2H, synchronises, maps device error words to OrcbStatus. */
+int orcb_job_finish(OrcbJob* j);
+/* Plan statistics: see OrcbJobStats. */
+typedef struct OrcbJobStats {
+    uint64_t n_stripes, n_rows, n_columns;
+    uint64_t input_bytes;       /* Σ stored bytes of projected non-index streams */
+    uint64_t staged_bytes;      /* bytes copied H2D per stage() */
+    uint64_t output_bytes;      /* Σ logical Arrow buffer bytes (valid after finish()) */
+    uint64_t device_bytes;      /* arena capacity allocated in HBM */
+    uint64_t n_segments;        /* (stream, row-group) work units */
+    uint64_t n_kernel_launches; /* kernels enqueued by one launch() */
+    uint64_t n_batches;
+    uint64_t d2h_meta_bytes;    /* per-batch metadata + error words read back in finish() */
+} OrcbJobStats;
+int orcb_job_stats(const OrcbJob* j, OrcbJobStats* out);
+uint64_t orcb_job_num_batches(const OrcbJob* j);
+/* Export batch `i` (stripe-major order, reference batch boundaries).  Host copy happens lazily, per job. */
+int orcb_job_export_batch(OrcbJob* j, uint64_t i, struct ArrowArray* out);
+int orcb_job_export_batch_device(OrcbJob* j, uint64_t i, struct ArrowDeviceArray* out);
+
+/* ---- stream-level entry points (one kernel each; used by the parity tests against the reference's
+ *      unit-test vectors, src/encoding/ ** /tests) ---- */
+/* kind: 0 RLEv1, 1 RLEv2 (src/encoding/integer); is_signed per EncodingSign; nbytes 2/4/8 = N. */
+int orcb_decode_int_rle(int device, const uint8_t* in, size_t in_len, int version, int is_signed, int nbytes,
+                        int64_t* out, size_t n_values);
+int orcb_decode_byte_rle(int device, const uint8_t* in, size_t in_len, uint8_t* out, size_t n_values);
+/* boolean RLE -> LSB-first Arrow bitmap of n_values bits (src/encoding/boolean.rs:101-113) */
+int orcb_decode_bool_rle(int device, const uint8_t* in, size_t in_len, uint8_t* out_bitmap, size_t n_values);
+/* decimal DATA: zigzag varint -> i128 little-endian, 16 bytes each (src/encoding/decimal.rs:46-51) */
+int orcb_decode_varint128(int device, const uint8_t* in, size_t in_len, uint8_t* out16, size_t n_values);
+/* chunk framing + block decompression of one whole stream (src/compression.rs:244-347);
+ * *out_len receives the decompressed size; out_cap must be >= chunks * block_size. */
+int orcb_decompress_stream(int device, int compression_kind, const uint8_t* in, size_t in_len, size_t block_size,
+                           uint8_t* out, size_t out_cap, size_t* out_len);
+
+/* Error detail of the last failing call on this thread. */
+const char* orcb_last_error(void);
+/* Build identification: "sm_100a" etc. */
+const char* orcb_build_info(void);
+/* 1 if a CUDA device is usable in this process. */
+int orcb_device_available(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORC_B200_H */

@@ -1,0 +1,467 @@
+"""orc_rust_b200 — B200-native ORC stripe decoder behind orc-rust's reader API.
+
+Host-side mirror of the reference's public interface for the decode path
+(`ArrowReaderBuilder` / `ArrowReader`, src/arrow_reader.rs:39-347 of datafusion-contrib/orc-rust),
+bound over the C ABI in include/orc_b200.h.  Every decode goes through the CUDA library
+(`liborc_b200.so`, built in-tree by `orc_rust_b200.build`); there is no CPU fallback: if the
+library or a CUDA device is missing, calls fail loudly.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Iterator, List, Optional, Sequence
+
+from . import build as _build
+
+__all__ = ["ArrowReaderBuilder", "ArrowReader", "DecodeJob", "OrcError", "lib", "device_available",
+           "TimestampPrecision", "decode_int_rle", "decode_byte_rle", "decode_bool_rle", "decode_varint128",
+           "decompress_stream"]
+
+STATUS_NAMES = {
+    1: "IoError", 2: "EmptyFile", 3: "OutOfSpec", 4: "DecodeFloat", 5: "DecodeTimestamp", 6: "OffsetOverflow",
+    7: "DecodeProto", 8: "NoTypes", 9: "UnsupportedTypeVariant", 10: "MismatchedSchema", 11: "ConvertRecordBatch",
+    12: "VarintTooLarge", 13: "Unexpected", 14: "BuildZstdDecoder", 15: "BuildSnappyDecoder", 16: "BuildLzoDecoder",
+    17: "BuildLz4Decoder", 18: "Arrow", 19: "UnsupportedDeviceCodec", 20: "Cuda", 21: "InvalidArgument",
+    22: "NotImplemented", 23: "DeviceHeapOverflow",
+}
+
+
+class OrcError(Exception):
+    """Mirror of `OrcError` (src/error.rs:31-174) + the device-path variants."""
+
+    def __init__(self, code: int, msg: str):
+        self.code = code
+        self.variant = STATUS_NAMES.get(code, f"status{code}")
+        super().__init__(f"{self.variant}: {msg}")
+
+
+class TimestampPrecision:
+    """src/schema.rs:31-39"""
+    Nanosecond = 0
+    Microsecond = 1
+    Millisecond = 2  # reachable in the reference through with_schema
+    Second = 3
+
+
+class _ReadOptions(ctypes.Structure):
+    _fields_ = [
+        ("device", ctypes.c_int32), ("batch_size", ctypes.c_uint32),
+        ("projection_names", ctypes.POINTER(ctypes.c_char_p)), ("n_projection", ctypes.c_uint32),
+        ("range_start", ctypes.c_uint64), ("range_end", ctypes.c_uint64),
+        ("timestamp_unit", ctypes.c_int32), ("use_row_index", ctypes.c_int32), ("device_resident", ctypes.c_int32),
+        ("max_stripes_per_launch", ctypes.c_uint32), ("cuda_stream", ctypes.c_void_p), ("flags", ctypes.c_uint32),
+        ("stripe_shard_index", ctypes.c_uint32), ("stripe_shard_count", ctypes.c_uint32),
+    ]
+
+
+class JobStats(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint64) for n in (
+        "n_stripes", "n_rows", "n_columns", "input_bytes", "staged_bytes", "output_bytes", "device_bytes",
+        "n_segments", "n_kernel_launches", "n_batches", "d2h_meta_bytes")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+class _ArrowArray(ctypes.Structure):
+    pass
+
+
+_ArrowArray._fields_ = [
+    ("length", ctypes.c_int64), ("null_count", ctypes.c_int64), ("offset", ctypes.c_int64),
+    ("n_buffers", ctypes.c_int64), ("n_children", ctypes.c_int64), ("buffers", ctypes.POINTER(ctypes.c_void_p)),
+    ("children", ctypes.POINTER(ctypes.POINTER(_ArrowArray))), ("dictionary", ctypes.POINTER(_ArrowArray)),
+    ("release", ctypes.c_void_p), ("private_data", ctypes.c_void_p),
+]
+
+
+class _ArrowSchema(ctypes.Structure):
+    pass
+
+
+_ArrowSchema._fields_ = [
+    ("format", ctypes.c_char_p), ("name", ctypes.c_char_p), ("metadata", ctypes.c_void_p),
+    ("flags", ctypes.c_int64), ("n_children", ctypes.c_int64),
+    ("children", ctypes.POINTER(ctypes.POINTER(_ArrowSchema))), ("dictionary", ctypes.POINTER(_ArrowSchema)),
+    ("release", ctypes.c_void_p), ("private_data", ctypes.c_void_p),
+]
+
+
+class _ArrowDeviceArray(ctypes.Structure):
+    _fields_ = [("array", _ArrowArray), ("device_id", ctypes.c_int64), ("device_type", ctypes.c_int32),
+                ("sync_event", ctypes.c_void_p), ("reserved", ctypes.c_int64 * 3)]
+
+
+_lib = None
+
+EXPORTED_SYMBOLS = [
+    "orcb_open_memory", "orcb_open_path", "orcb_file_free", "orcb_file_num_rows", "orcb_file_num_stripes",
+    "orcb_file_compression", "orcb_file_compression_block_size", "orcb_file_row_index_stride",
+    "orcb_file_num_root_columns", "orcb_file_root_column_name", "orcb_file_stripe_info", "orcb_schema",
+    "orcb_reader_new", "orcb_reader_free", "orcb_reader_total_row_count", "orcb_reader_next",
+    "orcb_reader_next_device", "orcb_job_new", "orcb_job_free", "orcb_job_plan", "orcb_job_stage",
+    "orcb_job_launch", "orcb_job_finish", "orcb_job_stats", "orcb_job_num_batches", "orcb_job_export_batch",
+    "orcb_job_export_batch_device", "orcb_decode_int_rle", "orcb_decode_byte_rle", "orcb_decode_bool_rle",
+    "orcb_decode_varint128", "orcb_decompress_stream", "orcb_last_error", "orcb_build_info",
+    "orcb_device_available",
+]
+
+
+def lib() -> ctypes.CDLL:
+    """Loads (building if stale) the CUDA library.  Raises if it cannot be built or loaded."""
+    global _lib
+    if _lib is None:
+        path = _build.build()
+        L = ctypes.CDLL(path)
+        L.orcb_last_error.restype = ctypes.c_char_p
+        L.orcb_build_info.restype = ctypes.c_char_p
+        L.orcb_file_num_rows.restype = ctypes.c_uint64
+        L.orcb_file_compression_block_size.restype = ctypes.c_uint64
+        L.orcb_file_row_index_stride.restype = ctypes.c_int64
+        L.orcb_file_root_column_name.restype = ctypes.c_char_p
+        L.orcb_reader_total_row_count.restype = ctypes.c_uint64
+        L.orcb_job_num_batches.restype = ctypes.c_uint64
+        for name in ("orcb_file_num_rows", "orcb_file_num_stripes", "orcb_file_compression",
+                     "orcb_file_compression_block_size", "orcb_file_row_index_stride",
+                     "orcb_file_num_root_columns", "orcb_file_free", "orcb_reader_free", "orcb_job_free",
+                     "orcb_reader_total_row_count", "orcb_job_num_batches"):
+            getattr(L, name).argtypes = [ctypes.c_void_p]
+        L.orcb_file_root_column_name.argtypes = [ctypes.c_void_p, ctypes.c_uint32]
+        L.orcb_file_stripe_info.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint64)]
+        L.orcb_open_memory.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]
+        L.orcb_open_path.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]
+        L.orcb_schema.argtypes = [ctypes.c_void_p, ctypes.POINTER(_ReadOptions), ctypes.c_void_p]
+        L.orcb_reader_new.argtypes = [ctypes.c_void_p, ctypes.POINTER(_ReadOptions), ctypes.POINTER(ctypes.c_void_p)]
+        L.orcb_reader_next.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]
+        L.orcb_reader_next_device.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]
+        L.orcb_job_new.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_uint32, ctypes.POINTER(_ReadOptions),
+                                   ctypes.POINTER(ctypes.c_void_p)]
+        for name in ("orcb_job_plan", "orcb_job_stage", "orcb_job_launch", "orcb_job_finish"):
+            getattr(L, name).argtypes = [ctypes.c_void_p]
+        L.orcb_job_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(JobStats)]
+        L.orcb_job_export_batch.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p]
+        L.orcb_job_export_batch_device.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p]
+        L.orcb_decode_int_rle.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t]
+        L.orcb_decode_byte_rle.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t]
+        L.orcb_decode_bool_rle.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t]
+        L.orcb_decode_varint128.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t]
+        L.orcb_decompress_stream.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t,
+                                             ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
+        _lib = L
+    return _lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise OrcError(rc, lib().orcb_last_error().decode("utf-8", "replace"))
+
+
+def device_available() -> bool:
+    return bool(lib().orcb_device_available())
+
+
+class _File:
+    """FileMetadata handle (src/reader/metadata.rs:63-178)."""
+
+    def __init__(self, source):
+        self._h = ctypes.c_void_p()
+        self._keep = None
+        if isinstance(source, (str, os.PathLike)):
+            _check(lib().orcb_open_path(os.fspath(source).encode(), ctypes.byref(self._h)))
+        else:
+            data = bytes(source) if not isinstance(source, bytes) else source
+            self._keep = data  # borrowed by the library for the life of the handle
+            buf = ctypes.cast(ctypes.c_char_p(data), ctypes.c_void_p)
+            _check(lib().orcb_open_memory(buf, len(data), ctypes.byref(self._h)))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value and _lib is not None:
+            _lib.orcb_file_free(self._h)
+            self._h = ctypes.c_void_p()
+
+    @property
+    def number_of_rows(self) -> int:
+        return lib().orcb_file_num_rows(self._h)
+
+    @property
+    def num_stripes(self) -> int:
+        return lib().orcb_file_num_stripes(self._h)
+
+    @property
+    def compression(self) -> int:
+        return lib().orcb_file_compression(self._h)
+
+    @property
+    def compression_block_size(self) -> int:
+        return lib().orcb_file_compression_block_size(self._h)
+
+    @property
+    def row_index_stride(self) -> Optional[int]:
+        v = lib().orcb_file_row_index_stride(self._h)
+        return None if v < 0 else v
+
+    @property
+    def column_names(self) -> List[str]:
+        n = lib().orcb_file_num_root_columns(self._h)
+        return [lib().orcb_file_root_column_name(self._h, i).decode() for i in range(n)]
+
+    def stripe_info(self, i: int):
+        out = (ctypes.c_uint64 * 5)()
+        _check(lib().orcb_file_stripe_info(self._h, i, out))
+        return dict(zip(("offset", "index_length", "data_length", "footer_length", "number_of_rows"), list(out)))
+
+
+def _make_options(device=0, batch_size=8192, projection=None, byte_range=None, timestamp_precision=0,
+                  use_row_index=True, device_resident=False, max_stripes_per_launch=0, cuda_stream=None,
+                  shard=None):
+    o = _ReadOptions()
+    o.device = device
+    o.batch_size = batch_size
+    keep = None
+    if projection is not None:
+        arr = (ctypes.c_char_p * max(len(projection), 1))(*[p.encode() for p in projection])
+        o.projection_names = arr
+        o.n_projection = len(projection)
+        keep = arr
+    if byte_range is not None:
+        o.range_start, o.range_end = byte_range
+    o.timestamp_unit = timestamp_precision
+    o.flags = 0 if use_row_index else 1
+    o.device_resident = 1 if device_resident else 0
+    o.max_stripes_per_launch = max_stripes_per_launch
+    o.cuda_stream = cuda_stream
+    if shard is not None:
+        o.stripe_shard_index, o.stripe_shard_count = shard
+    return o, keep
+
+
+def _import_schema(fh, opts):
+    import pyarrow as pa
+    cs = _ArrowSchema()
+    _check(lib().orcb_schema(fh, ctypes.byref(opts), ctypes.byref(cs)))
+    return pa.Schema._import_from_c(ctypes.addressof(cs))
+
+
+class ArrowReaderBuilder:
+    """Mirror of `ArrowReaderBuilder` (src/arrow_reader.rs:39-231) with one extra option, `with_device`."""
+
+    def __init__(self, file: _File):
+        self._file = file
+        self._batch_size = 8192  # DEFAULT_BATCH_SIZE, src/arrow_reader.rs:37
+        self._projection: Optional[List[str]] = None
+        self._byte_range = None
+        self._ts = TimestampPrecision.Nanosecond
+        self._device = 0
+        self._use_row_index = True
+        self._device_resident = False
+        self._max_stripes = 0
+
+    @classmethod
+    def try_new(cls, source) -> "ArrowReaderBuilder":
+        """`source`: path or bytes-like (the two `ChunkReader` impls, src/reader/mod.rs:48-76)."""
+        return cls(_File(source))
+
+    def file_metadata(self) -> _File:
+        return self._file
+
+    def with_batch_size(self, batch_size: int) -> "ArrowReaderBuilder":
+        self._batch_size = batch_size
+        return self
+
+    def with_projection(self, names: Sequence[str]) -> "ArrowReaderBuilder":
+        """ProjectionMask::named_roots (src/projection.rs:58-73)."""
+        self._projection = list(names)
+        return self
+
+    def with_file_byte_range(self, start: int, end: int) -> "ArrowReaderBuilder":
+        self._byte_range = (start, end)
+        return self
+
+    def with_timestamp_precision(self, precision: int) -> "ArrowReaderBuilder":
+        self._ts = precision
+        return self
+
+    def with_device(self, ordinal: int, resident: bool = False) -> "ArrowReaderBuilder":
+        self._device = ordinal
+        self._device_resident = resident
+        return self
+
+    def with_row_index(self, enabled: bool) -> "ArrowReaderBuilder":
+        self._use_row_index = enabled
+        return self
+
+    def with_max_stripes_per_launch(self, n: int) -> "ArrowReaderBuilder":
+        self._max_stripes = n
+        return self
+
+    def with_row_selection(self, *_a, **_k):
+        raise OrcError(22, "row selection is not on the device path yet (SURVEY §8(f) rank 1)")
+
+    def with_predicate(self, *_a, **_k):
+        raise OrcError(22, "predicate pushdown is not on the device path yet (SURVEY §8(f) rank 1)")
+
+    def _options(self):
+        return _make_options(self._device, self._batch_size, self._projection, self._byte_range, self._ts,
+                             self._use_row_index, self._device_resident, self._max_stripes)
+
+    def schema(self):
+        o, keep = self._options()
+        return _import_schema(self._file._h, o)
+
+    def build(self) -> "ArrowReader":
+        return ArrowReader(self)
+
+
+class ArrowReader:
+    """Mirror of `ArrowReader` (src/arrow_reader.rs:233-347): an iterator of RecordBatches."""
+
+    def __init__(self, b: ArrowReaderBuilder):
+        self._file = b._file
+        self._opts, self._keep = b._options()
+        self._schema = _import_schema(self._file._h, self._opts)
+        self._h = ctypes.c_void_p()
+        _check(lib().orcb_reader_new(self._file._h, ctypes.byref(self._opts), ctypes.byref(self._h)))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value and _lib is not None:
+            _lib.orcb_reader_free(self._h)
+            self._h = ctypes.c_void_p()
+
+    def schema(self):
+        return self._schema
+
+    def total_row_count(self) -> int:
+        return lib().orcb_reader_total_row_count(self._h)
+
+    def __iter__(self) -> Iterator:
+        return self
+
+    def __next__(self):
+        import pyarrow as pa
+        arr = _ArrowArray()
+        eos = ctypes.c_int(0)
+        _check(lib().orcb_reader_next(self._h, ctypes.byref(arr), ctypes.byref(eos)))
+        if eos.value:
+            raise StopIteration
+        return pa.RecordBatch._import_from_c(ctypes.addressof(arr), self._schema)
+
+    def read_all(self):
+        import pyarrow as pa
+        batches = list(self)
+        return pa.Table.from_batches(batches, schema=self._schema)
+
+
+class DecodeJob:
+    """One device launch plan over many stripes of many files (bulk API used by bench.py)."""
+
+    def __init__(self, sources, *, device=0, batch_size=8192, projection=None, use_row_index=True,
+                 cuda_stream=None, shard=None, timestamp_precision=0):
+        self._files = [s if isinstance(s, _File) else _File(s) for s in sources]
+        self._opts, self._keep = _make_options(device, batch_size, projection, None, timestamp_precision,
+                                               use_row_index, True, 0, cuda_stream, shard)
+        arr = (ctypes.c_void_p * len(self._files))(*[f._h for f in self._files])
+        self._h = ctypes.c_void_p()
+        _check(lib().orcb_job_new(arr, len(self._files), ctypes.byref(self._opts), ctypes.byref(self._h)))
+        self._schema = None
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value and _lib is not None:
+            _lib.orcb_job_free(self._h)
+            self._h = ctypes.c_void_p()
+
+    def plan(self):
+        _check(lib().orcb_job_plan(self._h))
+        return self
+
+    def stage(self):
+        _check(lib().orcb_job_stage(self._h))
+        return self
+
+    def launch(self):
+        _check(lib().orcb_job_launch(self._h))
+        return self
+
+    def finish(self):
+        _check(lib().orcb_job_finish(self._h))
+        return self
+
+    def stats(self) -> dict:
+        s = JobStats()
+        _check(lib().orcb_job_stats(self._h, ctypes.byref(s)))
+        return s.as_dict()
+
+    @property
+    def num_batches(self) -> int:
+        return lib().orcb_job_num_batches(self._h)
+
+    def schema(self):
+        if self._schema is None:
+            self._schema = _import_schema(self._files[0]._h, self._opts)
+        return self._schema
+
+    def batch(self, i: int):
+        import pyarrow as pa
+        arr = _ArrowArray()
+        _check(lib().orcb_job_export_batch(self._h, i, ctypes.byref(arr)))
+        return pa.RecordBatch._import_from_c(ctypes.addressof(arr), self.schema())
+
+    def batches(self):
+        return [self.batch(i) for i in range(self.num_batches)]
+
+
+# ---- stream-level entry points (parity tests against the reference's unit-test vectors) -------------
+def decode_int_rle(data: bytes, n: int, *, version: int = 2, signed: bool = True, nbytes: int = 8, device: int = 0):
+    import numpy as np
+    out = np.empty(n, dtype=np.int64)
+    buf = ctypes.cast(ctypes.c_char_p(bytes(data)), ctypes.c_void_p)
+    _check(lib().orcb_decode_int_rle(device, buf, len(data), 1 if version == 2 else 0, int(signed), nbytes,
+                                     out.ctypes.data_as(ctypes.c_void_p), n))
+    return out
+
+
+def decode_byte_rle(data: bytes, n: int, device: int = 0):
+    import numpy as np
+    out = np.empty(n, dtype=np.uint8)
+    buf = ctypes.cast(ctypes.c_char_p(bytes(data)), ctypes.c_void_p)
+    _check(lib().orcb_decode_byte_rle(device, buf, len(data), out.ctypes.data_as(ctypes.c_void_p), n))
+    return out
+
+
+def decode_bool_rle(data: bytes, n: int, device: int = 0):
+    """Returns the LSB-first Arrow bitmap unpacked to one uint8 per value."""
+    import numpy as np
+    bm = np.zeros((n + 7) // 8 + 8, dtype=np.uint8)
+    buf = ctypes.cast(ctypes.c_char_p(bytes(data)), ctypes.c_void_p)
+    _check(lib().orcb_decode_bool_rle(device, buf, len(data), bm.ctypes.data_as(ctypes.c_void_p), n))
+    return np.unpackbits(bm, bitorder="little")[:n]
+
+
+def decode_varint128(data: bytes, n: int, device: int = 0):
+    """Returns an (n, 2) uint64 array of little-endian (lo, hi) halves."""
+    import numpy as np
+    out = np.empty((n, 2), dtype=np.uint64)
+    buf = ctypes.cast(ctypes.c_char_p(bytes(data)), ctypes.c_void_p)
+    _check(lib().orcb_decode_varint128(device, buf, len(data), out.ctypes.data_as(ctypes.c_void_p), n))
+    return out
+
+
+def decompress_stream(kind: int, data: bytes, block_size: int, device: int = 0) -> bytes:
+    import numpy as np
+    n_chunks_max = len(data) // 3 + 1
+    cap = min(n_chunks_max, max(1, len(data))) * block_size + 64
+    # exact chunk count: walk the headers (framing only)
+    p = 0
+    chunks = 0
+    while p + 3 <= len(data):
+        h = data[p] | (data[p + 1] << 8) | (data[p + 2] << 16)
+        p += 3 + (h >> 1)
+        chunks += 1
+    cap = chunks * block_size + 64
+    out = np.empty(cap, dtype=np.uint8)
+    out_len = ctypes.c_size_t(0)
+    buf = ctypes.cast(ctypes.c_char_p(bytes(data)), ctypes.c_void_p)
+    _check(lib().orcb_decompress_stream(device, kind, buf, len(data), block_size,
+                                        out.ctypes.data_as(ctypes.c_void_p), cap, ctypes.byref(out_len)))
+    return out[: out_len.value].tobytes()

@@ -1,0 +1,456 @@
+// extern "C" boundary (include/orc_b200.h).  No exception, panic or abort crosses it.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <memory>
+
+#include "job.h"
+#include "kernels.h"
+#include "meta.h"
+
+using namespace orcb;
+
+#define ORCB_STR2(x) #x
+#define ORCB_STR(x) ORCB_STR2(x)
+
+static thread_local std::string g_last_error;
+
+struct OrcbFile {
+    FileMeta meta;
+};
+
+struct OrcbJob {
+    std::unique_ptr<Job> job;
+};
+
+// ArrowReader: walks the selected stripes in groups, one Job per group (src/arrow_reader.rs:233-347)
+struct OrcbReader {
+    OrcbFile* file;
+    ReadOptions opt;
+    std::vector<uint32_t> stripes;  // after byte-range / shard filtering (Cursor::get_stripe_metadatas :358-372)
+    size_t next_stripe = 0;
+    std::unique_ptr<Job> job;
+    uint64_t next_batch = 0;
+    bool failed = false;
+};
+
+template <typename F>
+static int guarded(F&& f) {
+    try {
+        f();
+        return ORCB_OK;
+    } catch (const OrcException& e) {
+        g_last_error = e.msg;
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        g_last_error = "out of host memory";
+        return ORCB_UNEXPECTED;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return ORCB_UNEXPECTED;
+    } catch (...) {
+        g_last_error = "unknown error";
+        return ORCB_UNEXPECTED;
+    }
+}
+
+extern "C" {
+
+const char* orcb_last_error(void) { return g_last_error.c_str(); }
+const char* orcb_build_info(void) { return "orc_b200 " __DATE__ " sm_100a cuda " ORCB_STR(CUDART_VERSION); }
+
+int orcb_device_available(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n > 0;
+}
+
+int orcb_open_memory(const uint8_t* data, size_t len, OrcbFile** out) {
+    return guarded([&] {
+        if (!out) fail(ORCB_INVALID_ARGUMENT, "out is NULL");
+        auto f = std::make_unique<OrcbFile>();
+        f->meta.data = data;
+        f->meta.len = len;
+        parse_file_tail(f->meta);
+        *out = f.release();
+    });
+}
+
+int orcb_open_path(const char* path, OrcbFile** out) {
+    return guarded([&] {
+        if (!out || !path) fail(ORCB_INVALID_ARGUMENT, "NULL argument");
+        FILE* fp = fopen(path, "rb");
+        if (!fp) fail(ORCB_IO_ERROR, std::string("cannot open ") + path);
+        fseek(fp, 0, SEEK_END);
+        long n = ftell(fp);
+        fseek(fp, 0, SEEK_SET);
+        auto f = std::make_unique<OrcbFile>();
+        uint8_t* buf = nullptr;
+        if (n > 0 && orcb_device_available() && cudaHostAlloc((void**)&buf, (size_t)n, cudaHostAllocDefault) == cudaSuccess) {
+            f->meta.pinned = buf;
+        } else {
+            cudaGetLastError();
+            f->meta.owned.resize((size_t)std::max<long>(n, 0));
+            buf = f->meta.owned.data();
+        }
+        size_t got = n > 0 ? fread(buf, 1, (size_t)n, fp) : 0;
+        fclose(fp);
+        if ((long)got != n) {
+            if (f->meta.pinned) cudaFreeHost(f->meta.pinned);
+            fail(ORCB_IO_ERROR, std::string("short read on ") + path);
+        }
+        f->meta.data = buf;
+        f->meta.len = (size_t)std::max<long>(n, 0);
+        try {
+            parse_file_tail(f->meta);
+        } catch (...) {
+            if (f->meta.pinned) cudaFreeHost(f->meta.pinned);
+            throw;
+        }
+        *out = f.release();
+    });
+}
+
+void orcb_file_free(OrcbFile* f) {
+    if (!f) return;
+    if (f->meta.pinned) cudaFreeHost(f->meta.pinned);
+    delete f;
+}
+
+uint64_t orcb_file_num_rows(const OrcbFile* f) { return f->meta.num_rows; }
+uint32_t orcb_file_num_stripes(const OrcbFile* f) { return (uint32_t)f->meta.stripes.size(); }
+int32_t orcb_file_compression(const OrcbFile* f) { return f->meta.compression; }
+uint64_t orcb_file_compression_block_size(const OrcbFile* f) { return f->meta.block_size; }
+int64_t orcb_file_row_index_stride(const OrcbFile* f) { return f->meta.row_index_stride; }
+uint32_t orcb_file_num_root_columns(const OrcbFile* f) { return (uint32_t)f->meta.root_columns.size(); }
+const char* orcb_file_root_column_name(const OrcbFile* f, uint32_t i) {
+    return i < f->meta.root_columns.size() ? f->meta.root_columns[i].first.c_str() : nullptr;
+}
+int orcb_file_stripe_info(const OrcbFile* f, uint32_t stripe, uint64_t out[5]) {
+    return guarded([&] {
+        if (stripe >= f->meta.stripes.size()) fail(ORCB_INVALID_ARGUMENT, "stripe index out of range");
+        const StripeInfo& s = f->meta.stripes[stripe];
+        out[0] = s.offset;
+        out[1] = s.index_length;
+        out[2] = s.data_length;
+        out[3] = s.footer_length;
+        out[4] = s.rows;
+    });
+}
+
+int orcb_schema(const OrcbFile* f, const OrcbReadOptions* opt, struct ArrowSchema* out) {
+    return guarded([&] {
+        ReadOptions o = ReadOptions::from_c(opt);
+        auto cols = project_columns(f->meta, o);
+        export_schema(f->meta, cols, out);
+    });
+}
+
+static std::vector<uint32_t> select_stripes(const FileMeta& fm, const ReadOptions& o) {
+    std::vector<uint32_t> out;
+    uint32_t ordinal = 0;
+    for (uint32_t i = 0; i < fm.stripes.size(); i++) {
+        if (o.range_start || o.range_end) {
+            const uint64_t off = fm.stripes[i].offset;
+            if (off < o.range_start || off >= o.range_end) continue;
+        }
+        if (o.shard_count > 1 && (ordinal % o.shard_count) != o.shard_index) {
+            ordinal++;
+            continue;
+        }
+        ordinal++;
+        out.push_back(i);
+    }
+    return out;
+}
+
+int orcb_reader_new(OrcbFile* f, const OrcbReadOptions* opt, OrcbReader** out) {
+    return guarded([&] {
+        if (!f || !out) fail(ORCB_INVALID_ARGUMENT, "NULL argument");
+        auto r = std::make_unique<OrcbReader>();
+        r->file = f;
+        r->opt = ReadOptions::from_c(opt);
+        (void)project_columns(f->meta, r->opt);  // surfaces schema errors at build time
+        r->stripes = select_stripes(f->meta, r->opt);
+        *out = r.release();
+    });
+}
+
+void orcb_reader_free(OrcbReader* r) { delete r; }
+
+uint64_t orcb_reader_total_row_count(const OrcbReader* r) { return r->file->meta.num_rows; }
+
+static bool reader_advance(OrcbReader* r) {
+    // returns false at end of stream
+    while (!r->job || r->next_batch >= r->job->num_batches()) {
+        r->job.reset();
+        if (r->next_stripe >= r->stripes.size()) return false;
+        const uint32_t group = r->opt.max_stripes_per_launch ? r->opt.max_stripes_per_launch : 16;
+        std::vector<StripeTask> tasks;
+        uint64_t bytes = 0;
+        while (r->next_stripe < r->stripes.size() && tasks.size() < group) {
+            const StripeInfo& si = r->file->meta.stripes[r->stripes[r->next_stripe]];
+            if (!tasks.empty() && bytes + si.data_length > (1ull << 30)) break;  // bound one launch plan to ~1 GiB in
+            bytes += si.data_length;
+            tasks.push_back({&r->file->meta, r->stripes[r->next_stripe]});
+            r->next_stripe++;
+        }
+        r->job = std::make_unique<Job>(std::move(tasks), r->opt);
+        r->next_batch = 0;
+        r->job->plan();
+        r->job->stage();
+        r->job->launch();
+        r->job->finish();
+    }
+    return true;
+}
+
+int orcb_reader_next(OrcbReader* r, struct ArrowArray* out, int* eos) {
+    return guarded([&] {
+        if (!r || !out || !eos) fail(ORCB_INVALID_ARGUMENT, "NULL argument");
+        *eos = 0;
+        if (r->failed) fail(ORCB_UNEXPECTED, "reader is in the error state");
+        try {
+            if (!reader_advance(r)) {
+                *eos = 1;
+                return;
+            }
+            r->job->export_batch(r->next_batch++, out);
+        } catch (...) {
+            r->failed = true;  // StreamState::Error analogue (src/async_arrow_reader.rs:262-277)
+            throw;
+        }
+    });
+}
+
+int orcb_reader_next_device(OrcbReader* r, struct ArrowDeviceArray* out, int* eos) {
+    return guarded([&] {
+        if (!r || !out || !eos) fail(ORCB_INVALID_ARGUMENT, "NULL argument");
+        *eos = 0;
+        if (r->failed) fail(ORCB_UNEXPECTED, "reader is in the error state");
+        try {
+            if (!reader_advance(r)) {
+                *eos = 1;
+                return;
+            }
+            r->job->export_batch_device(r->next_batch++, out);
+        } catch (...) {
+            r->failed = true;
+            throw;
+        }
+    });
+}
+
+int orcb_job_new(OrcbFile* const* files, uint32_t n_files, const OrcbReadOptions* opt, OrcbJob** out) {
+    return guarded([&] {
+        if (!files || !n_files || !out) fail(ORCB_INVALID_ARGUMENT, "NULL argument");
+        ReadOptions o = ReadOptions::from_c(opt);
+        std::vector<StripeTask> tasks;
+        for (uint32_t i = 0; i < n_files; i++)
+            for (uint32_t s : select_stripes(files[i]->meta, o)) tasks.push_back({&files[i]->meta, s});
+        auto j = std::make_unique<OrcbJob>();
+        j->job = std::make_unique<Job>(std::move(tasks), o);
+        *out = j.release();
+    });
+}
+void orcb_job_free(OrcbJob* j) { delete j; }
+int orcb_job_plan(OrcbJob* j) { return guarded([&] { j->job->plan(); }); }
+int orcb_job_stage(OrcbJob* j) { return guarded([&] { j->job->stage(); }); }
+int orcb_job_launch(OrcbJob* j) { return guarded([&] { j->job->launch(); }); }
+int orcb_job_finish(OrcbJob* j) { return guarded([&] { j->job->finish(); }); }
+int orcb_job_stats(const OrcbJob* j, OrcbJobStats* out) { return guarded([&] { j->job->stats(out); }); }
+uint64_t orcb_job_num_batches(const OrcbJob* j) { return j->job->num_batches(); }
+int orcb_job_export_batch(OrcbJob* j, uint64_t i, struct ArrowArray* out) {
+    return guarded([&] { j->job->export_batch(i, out); });
+}
+int orcb_job_export_batch_device(OrcbJob* j, uint64_t i, struct ArrowDeviceArray* out) {
+    return guarded([&] { j->job->export_batch_device(i, out); });
+}
+
+// ---------------------------------------------------------------------------------------------
+// stream-level entry points: one segment, one kernel
+// ---------------------------------------------------------------------------------------------
+#define CU(expr)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) fail(ORCB_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+namespace {
+struct DevBuf {
+    void* p = nullptr;
+    explicit DevBuf(size_t n) { CU(cudaMalloc(&p, n ? n : 16)); }
+    ~DevBuf() { cudaFree(p); }
+    DevBuf(const DevBuf&) = delete;
+};
+struct StreamRun {
+    DevBuf in, err;
+    size_t in_len;
+    StreamRun(int device, const uint8_t* src, size_t n) : in(((cudaSetDevice(device)), n + 256)), err(16), in_len(n) {
+        CU(cudaMemset(in.p, 0, n + 256));
+        if (n) CU(cudaMemcpy(in.p, src, n, cudaMemcpyHostToDevice));
+        CU(cudaMemset(err.p, 0, 16));
+    }
+    void check() {
+        CU(cudaDeviceSynchronize());
+        uint32_t e[2] = {0, 0};
+        CU(cudaMemcpy(e, err.p, 8, cudaMemcpyDeviceToHost));
+        if (e[0]) fail((int)e[0], "device decode error");
+    }
+};
+}  // namespace
+
+int orcb_decode_int_rle(int device, const uint8_t* in, size_t in_len, int version, int is_signed, int nbytes,
+                        int64_t* out, size_t n_values) {
+    return guarded([&] {
+        if (nbytes != 2 && nbytes != 4 && nbytes != 8) fail(ORCB_INVALID_ARGUMENT, "nbytes must be 2, 4 or 8");
+        StreamRun sr(device, in, in_len);
+        DevBuf dout(n_values * 8 + 16), dseg(sizeof(Seg)), mis(16);
+        CU(cudaMemset(mis.p, 0, 16));
+        Seg s{};
+        s.in = (uint64_t)(uintptr_t)sr.in.p;
+        s.out = (uint64_t)(uintptr_t)dout.p;
+        s.in_len = (uint32_t)in_len;
+        s.n_values = (uint32_t)n_values;
+        s.cnt_idx = -1;
+        s.start_idx = -1;
+        s.flags = (is_signed ? SEG_SIGNED : 0) | (version == 1 ? SEG_RLE_V2 : 0);
+        s.nbytes = (uint8_t)nbytes;
+        s.out_kind = OUT_I64;
+        s.end_byte = 0xffffffffu;
+        CU(cudaMemcpy(dseg.p, &s, sizeof(s), cudaMemcpyHostToDevice));
+        int rc = launch_int_rle((Seg*)dseg.p, 1, nullptr, nullptr, (uint32_t*)sr.err.p, (uint32_t*)mis.p, 0);
+        if (rc) fail(ORCB_CUDA, cudaGetErrorString((cudaError_t)rc));
+        sr.check();
+        if (n_values) CU(cudaMemcpy(out, dout.p, n_values * 8, cudaMemcpyDeviceToHost));
+    });
+}
+
+int orcb_decode_byte_rle(int device, const uint8_t* in, size_t in_len, uint8_t* out, size_t n_values) {
+    return guarded([&] {
+        StreamRun sr(device, in, in_len);
+        DevBuf dout(n_values + 16), dseg(sizeof(Seg));
+        Seg s{};
+        s.in = (uint64_t)(uintptr_t)sr.in.p;
+        s.out = (uint64_t)(uintptr_t)dout.p;
+        s.in_len = (uint32_t)in_len;
+        s.n_values = (uint32_t)n_values;
+        s.cnt_idx = -1;
+        s.start_idx = -1;
+        s.out_kind = OUT_I8;
+        CU(cudaMemcpy(dseg.p, &s, sizeof(s), cudaMemcpyHostToDevice));
+        int rc = launch_byte_rle((Seg*)dseg.p, 1, nullptr, nullptr, (uint32_t*)sr.err.p, 0);
+        if (rc) fail(ORCB_CUDA, cudaGetErrorString((cudaError_t)rc));
+        sr.check();
+        if (n_values) CU(cudaMemcpy(out, dout.p, n_values, cudaMemcpyDeviceToHost));
+    });
+}
+
+int orcb_decode_bool_rle(int device, const uint8_t* in, size_t in_len, uint8_t* out_bitmap, size_t n_values) {
+    return guarded([&] {
+        StreamRun sr(device, in, in_len);
+        const size_t raw_bytes = (n_values + 7) / 8;
+        const size_t bm_bytes = (n_values + 31) / 32 * 4 + 16;
+        DevBuf raw(raw_bytes + 32), bm(bm_bytes), dseg(sizeof(Seg)), dbit(sizeof(BitSeg)), cnt(64);
+        CU(cudaMemset(bm.p, 0, bm_bytes));
+        CU(cudaMemset(raw.p, 0, raw_bytes + 32));
+        Seg s{};
+        s.in = (uint64_t)(uintptr_t)sr.in.p;
+        s.out = (uint64_t)(uintptr_t)raw.p;
+        s.in_len = (uint32_t)in_len;
+        s.n_values = (uint32_t)n_values;
+        s.cnt_idx = -1;
+        s.start_idx = -1;
+        s.out_kind = OUT_I8;
+        s.aux = 1;  // bit mode, bit_skip 0
+        CU(cudaMemcpy(dseg.p, &s, sizeof(s), cudaMemcpyHostToDevice));
+        BitSeg b{};
+        b.src = (uint64_t)(uintptr_t)raw.p;
+        b.dst = (uint64_t)(uintptr_t)bm.p;
+        b.n_bits = (uint32_t)n_values;
+        b.cnt_idx = -1;
+        b.start_idx = -1;
+        b.popc_out = 0;
+        CU(cudaMemcpy(dbit.p, &b, sizeof(b), cudaMemcpyHostToDevice));
+        int rc = launch_byte_rle((Seg*)dseg.p, 1, nullptr, nullptr, (uint32_t*)sr.err.p, 0);
+        if (rc) fail(ORCB_CUDA, cudaGetErrorString((cudaError_t)rc));
+        rc = launch_bits((BitSeg*)dbit.p, 1, (uint32_t*)cnt.p, nullptr, 0);
+        if (rc) fail(ORCB_CUDA, cudaGetErrorString((cudaError_t)rc));
+        sr.check();
+        if (n_values) CU(cudaMemcpy(out_bitmap, bm.p, raw_bytes, cudaMemcpyDeviceToHost));
+    });
+}
+
+int orcb_decode_varint128(int device, const uint8_t* in, size_t in_len, uint8_t* out16, size_t n_values) {
+    return guarded([&] {
+        StreamRun sr(device, in, in_len);
+        DevBuf dout(n_values * 16 + 16), dseg(sizeof(Seg));
+        Seg s{};
+        s.in = (uint64_t)(uintptr_t)sr.in.p;
+        s.out = (uint64_t)(uintptr_t)dout.p;
+        s.in_len = (uint32_t)in_len;
+        s.n_values = (uint32_t)n_values;
+        s.cnt_idx = -1;
+        s.start_idx = -1;
+        CU(cudaMemcpy(dseg.p, &s, sizeof(s), cudaMemcpyHostToDevice));
+        int rc = launch_varint128((Seg*)dseg.p, 1, nullptr, nullptr, (uint32_t*)sr.err.p, 0);
+        if (rc) fail(ORCB_CUDA, cudaGetErrorString((cudaError_t)rc));
+        sr.check();
+        if (n_values) CU(cudaMemcpy(out16, dout.p, n_values * 16, cudaMemcpyDeviceToHost));
+    });
+}
+
+int orcb_decompress_stream(int device, int compression_kind, const uint8_t* in, size_t in_len, size_t block_size,
+                           uint8_t* out, size_t out_cap, size_t* out_len) {
+    return guarded([&] {
+        if (compression_kind != C_NONE && compression_kind != C_SNAPPY && compression_kind != C_LZ4)
+            fail(ORCB_UNSUPPORTED_DEVICE_CODEC, "Zlib/Zstd/LZO are not supported on the device path");
+        if (compression_kind == C_NONE) {
+            if (in_len > out_cap) fail(ORCB_INVALID_ARGUMENT, "output too small");
+            memcpy(out, in, in_len);
+            *out_len = in_len;
+            return;
+        }
+        FileMeta fm;
+        fm.data = in;
+        fm.len = in_len;
+        fm.compression = compression_kind;
+        fm.block_size = block_size;
+        std::vector<ChunkInfo> chunks = fm.chunk_table(0, in_len);
+        StreamRun sr(device, in, in_len);
+        const size_t cap = chunks.size() * block_size + 256;
+        if (chunks.size() * block_size > out_cap) fail(ORCB_INVALID_ARGUMENT, "out_cap must be >= chunks * block_size");
+        DevBuf dout(cap), ddesc(chunks.size() * sizeof(ChunkDesc) + 16), dlens(chunks.size() * 4 + 16);
+        std::vector<ChunkDesc> descs(chunks.size());
+        for (size_t i = 0; i < chunks.size(); i++) {
+            ChunkDesc& d = descs[i];
+            memset(&d, 0, sizeof(d));
+            d.src = (uint64_t)(uintptr_t)sr.in.p + chunks[i].src_off;
+            d.dst = (uint64_t)(uintptr_t)dout.p + i * block_size;
+            d.src_len = chunks[i].src_len;
+            d.dst_cap = (uint32_t)block_size;
+            d.expect_len = -1;
+            d.codec = chunks[i].original ? 0 : (uint8_t)compression_kind;
+        }
+        if (!chunks.empty()) CU(cudaMemcpy(ddesc.p, descs.data(), descs.size() * sizeof(ChunkDesc), cudaMemcpyHostToDevice));
+        int rc = launch_decompress((ChunkDesc*)ddesc.p, (uint32_t)chunks.size(), (uint32_t*)sr.err.p, (uint32_t*)dlens.p, 0);
+        if (rc) fail(ORCB_CUDA, cudaGetErrorString((cudaError_t)rc));
+        sr.check();
+        std::vector<uint32_t> lens(chunks.size());
+        if (!chunks.empty()) CU(cudaMemcpy(lens.data(), dlens.p, chunks.size() * 4, cudaMemcpyDeviceToHost));
+        size_t o = 0;
+        for (size_t i = 0; i < chunks.size(); i++) {
+            if (lens[i]) CU(cudaMemcpy(out + o, (uint8_t*)dout.p + i * block_size, lens[i], cudaMemcpyDeviceToHost));
+            o += lens[i];
+        }
+        *out_len = o;
+    });
+}
+
+}  // extern "C"

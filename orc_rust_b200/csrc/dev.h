@@ -1,0 +1,169 @@
+// POD descriptor tables shared by the host planner (plan.cc) and the CUDA kernels (kernels.cu).
+// One decode job = flat arrays of these, uploaded once; every kernel indexes them by warp.
+//
+// Pointer-typed fields (uint64_t) hold an arena-tagged offset while planning on the host
+// (top 4 bits = arena id, low 60 bits = byte offset) and a device address after relocation.
+#pragma once
+#include <cstdint>
+
+namespace orcb {
+
+// AR_ZERO: temporaries that must be zero before every launch (atomicOr targets)
+enum Arena : uint64_t { AR_NULL = 0, AR_IN = 1, AR_DEC = 2, AR_OUT = 3, AR_TMP = 4, AR_HEAP = 5, AR_ZERO = 6 };
+static inline uint64_t aref(Arena a, uint64_t off) { return ((uint64_t)a << 60) | off; }
+
+// how an integer-RLE segment stores its values
+enum OutKind : uint8_t {
+    OUT_I16 = 0,
+    OUT_I32 = 1,
+    OUT_I64 = 2,
+    OUT_LEN31 = 3,   // i32, error `aux` if value outside [0, 2^31)  (string lengths, dictionary keys)
+    OUT_SCALE = 4,   // i32, raises the colstripe's scale-mismatch flag when value != aux (decimal SECONDARY)
+    OUT_I8 = 5       // byte RLE payload
+};
+
+enum SegFlags : uint8_t { SEG_SIGNED = 1, SEG_RLE_V2 = 2 };
+
+// One (stream, row-group) unit for k_int_rle / k_byte_rle / k_varint128.
+struct Seg {
+    uint64_t in;         // stream base
+    uint64_t out;        // element 0 of the destination buffer
+    uint32_t in_len;     // stream bytes
+    uint32_t start_byte; // entry point (row-index position or 0)
+    uint32_t run_skip;   // values already consumed from the run at start_byte
+    uint32_t n_values;   // used when cnt_idx < 0
+    int32_t cnt_idx;     // >= 0: n_values = cnt[cnt_idx]
+    int32_t start_idx;   // >= 0: out_start = dstart[start_idx]
+    uint32_t out_start;  // element offset when start_idx < 0
+    uint32_t colstripe;  // error word index
+    uint8_t flags;
+    uint8_t nbytes;      // N of the reference's NInt (2/4/8)
+    uint8_t out_kind;
+    uint8_t pad0;
+    uint32_t aux;
+    // consistency probe: where the next segment's row-index entry says this one must end (0xffffffff = none)
+    uint32_t end_byte;
+    uint32_t end_skip;
+};
+
+// MSB-first boolean bytes -> LSB-first bitmap (+ popcount)
+struct BitSeg {
+    uint64_t src;        // decoded byte-RLE bytes of this segment
+    uint64_t dst;        // bitmap base (32-bit words), zero-initialised
+    uint32_t bit_skip;   // bits to skip in src
+    uint32_t n_bits;     // when cnt_idx < 0
+    int32_t cnt_idx;
+    int32_t start_idx;   // >= 0: dst_bit0 = dstart[start_idx]
+    uint32_t dst_bit0;
+    int32_t popc_out;    // >= 0: cnt[popc_out] = number of set bits
+};
+
+// exclusive scan of per-group non-null counts of one column-stripe
+struct ScanDesc {
+    uint32_t base;       // first index in cnt[] / dstart[]; entry base + n_groups receives the total
+    uint32_t n_groups;
+};
+
+struct CopyDesc {
+    uint64_t src;
+    uint64_t dst;
+    uint64_t n_bytes;    // when cnt_idx < 0
+    int32_t cnt_idx;     // >= 0: n_bytes = cnt[cnt_idx] * width
+    uint32_t width;
+    uint32_t src_len;    // available source bytes (bound; IoError if short)
+    uint32_t colstripe;
+};
+
+// dense values -> row slots of one row group (decode_spaced)
+struct SpacedDesc {
+    uint64_t src;        // dense buffer (element 0 of the colstripe)
+    uint64_t dst;        // row-domain buffer
+    uint64_t valid;      // stripe-level LSB-first validity bitmap
+    uint32_t row0;
+    uint32_t n_rows;
+    int32_t start_idx;   // dense start of this group = dstart[start_idx]
+    uint32_t width;      // bytes per element; 0 = bit mode (boolean values)
+};
+
+// elementwise epilogues over the dense domain of one column-stripe
+struct DecFixDesc {
+    uint64_t vals;       // i128 dense
+    uint64_t scales;     // i32 dense
+    uint32_t n;          // when cnt_idx < 0
+    int32_t cnt_idx;
+    uint32_t fixed_scale;
+    uint32_t colstripe;  // flag word index (scale mismatch) == error word index
+};
+
+struct TsDesc {
+    uint64_t secs;       // i64 dense
+    uint64_t nanos;      // i64 dense
+    uint64_t out;        // i64 (or i128 when as_i128)
+    int64_t base;
+    int64_t unit_ns;
+    uint32_t n;
+    int32_t cnt_idx;
+    uint32_t colstripe;
+    uint32_t as_i128;
+};
+
+// string column of one stripe
+struct StrCol {
+    uint64_t lens;       // i32 row-domain lengths (direct) or keys (dictionary)
+    uint64_t valid;      // stripe-level validity bitmap or 0
+    uint64_t dict_len;   // i32[dict_size]      (dictionary mode)
+    uint64_t dict_off;   // i32[dict_size + 1]  (dictionary mode; written by k_dict_prepare)
+    uint64_t dict_data;  // dictionary bytes
+    uint64_t offsets;    // out: i32, batch b at b * (batch_size + 1)
+    uint64_t tile_base;  // tmp: i64[n_tiles + 1]
+    uint64_t batch_base; // meta: i64[n_batches + 1] absolute byte offset of each batch start
+    uint64_t data;       // out: string bytes (direct: static; dictionary: bump-allocated by k_tile_scan)
+    uint64_t data_cap;   // capacity behind `data` (direct) / unused
+    uint32_t n_rows;
+    uint32_t batch_size;
+    uint32_t n_batches;
+    uint32_t tiles_per_batch;
+    uint32_t n_tiles;
+    uint32_t dict_size;
+    uint32_t dict_data_len;
+    uint32_t mode;       // 0 direct, 1 dictionary
+    uint32_t colstripe;
+    uint32_t tile0;      // first global tile index of this column (for the tile -> column map)
+    uint32_t data_len;   // direct: bytes available in the DATA stream
+    uint32_t meta_slot;  // index of this column's data pointer in the per-job pointer table
+};
+
+// stripe-level bitmap -> per-batch bitmaps (+ null counts)
+struct RepackDesc {
+    uint64_t src;
+    uint64_t dst;        // batch b at dst + b * dst_stride
+    uint32_t dst_stride; // bytes
+    uint32_t n_rows;
+    uint32_t batch_size;
+    uint32_t n_batches;
+    int32_t null_out;    // >= 0: nulls[null_out + b] = rows_in_batch - popcount
+    uint32_t batch0;     // first global (desc, batch) work index
+};
+
+// one compression chunk (src/compression.rs framing, resolved on the host)
+struct ChunkDesc {
+    uint64_t src;
+    uint64_t dst;
+    uint32_t src_len;
+    uint32_t dst_cap;    // bytes this chunk may produce (exact when known, else block size)
+    int32_t expect_len;  // >= 0: decompressed size must equal this (layout was planned on it)
+    uint8_t codec;       // 0 original (copy), 2 snappy, 4 lz4
+    uint8_t pad[3];
+    uint32_t colstripe;
+};
+
+// job-wide mutable device state
+struct JobState {
+    unsigned long long heap_top;
+    unsigned long long reserved;
+};
+
+// tile size (rows) of the string offset scan
+constexpr uint32_t STR_TILE = 1024;
+
+}  // namespace orcb

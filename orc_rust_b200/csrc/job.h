@@ -1,0 +1,151 @@
+// Decode job: host planner + device execution for a list of (file, stripe) tasks.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "common.h"
+#include "dev.h"
+#include "meta.h"
+
+namespace orcb {
+
+struct ReadOptions {
+    int device = 0;
+    uint32_t batch_size = 8192;
+    bool project_all = true;
+    std::vector<std::string> projection;
+    uint64_t range_start = 0, range_end = 0;
+    int timestamp_unit = 0;  // 0 ns, 1 us, 2 ms, 3 s
+    bool use_row_index = true;
+    bool device_resident = false;
+    uint32_t max_stripes_per_launch = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    uint32_t shard_index = 0, shard_count = 1;
+    static ReadOptions from_c(const OrcbReadOptions* o);
+};
+
+// projected root column after schema mapping (src/schema.rs:503-577)
+struct OutColumn {
+    std::string name;
+    uint32_t col_id;
+    int kind;            // ORC TypeKind
+    uint32_t precision = 0, scale = 0;
+    std::string format;  // Arrow C format string
+    uint32_t width = 0;  // bytes per value (0 for bool / strings)
+};
+
+std::vector<OutColumn> project_columns(const FileMeta& fm, const ReadOptions& opt);
+void export_schema(const FileMeta& fm, const std::vector<OutColumn>& cols, ArrowSchema* out);
+
+struct StripeTask {
+    const FileMeta* file;
+    uint32_t stripe;
+};
+
+// where one column of one stripe lands
+struct ColStripePlan {
+    uint32_t task = 0, col = 0;       // indices into tasks / out columns
+    uint32_t n_rows = 0, n_batches = 0;
+    bool has_present = false;
+    uint32_t nulls_idx = 0;           // first entry in nulls[] (has_present)
+    uint64_t validity = 0;            // AR_OUT offset, batch b at + b * validity_stride
+    uint32_t validity_stride = 0;
+    uint64_t values = 0;              // AR_OUT offset (prims: n_rows*width; bool: per-batch bitmaps)
+    uint32_t values_stride = 0;       // bool only
+    uint64_t offsets = 0;             // AR_OUT offset, strings
+    uint64_t str_data = 0;            // AR_OUT offset (direct) — dictionary: from ptr_table
+    int32_t str_slot = -1;            // index into StrCol table / ptr_table
+    uint64_t batch_base_off = 0;      // byte offset inside the meta blob of i64[n_batches+1]
+};
+
+struct HostOutput;  // D2H copy of the output arenas, shared by exported batches
+
+class Job {
+  public:
+    Job(std::vector<StripeTask> tasks, const ReadOptions& opt);
+    ~Job();
+    void plan();
+    void stage();
+    void launch();
+    void finish();
+    void stats(OrcbJobStats* out) const;
+    uint64_t num_batches() const { return batch_task_.size(); }
+    void export_batch(uint64_t i, ArrowArray* out);
+    void export_batch_device(uint64_t i, ArrowDeviceArray* out);
+    const std::vector<OutColumn>& columns() const { return cols_; }
+
+  private:
+    uint64_t alloc(Arena a, uint64_t bytes, uint64_t align = 256);
+    uint64_t reloc(uint64_t tagged) const;
+    void plan_stripe(uint32_t task_idx);
+    void ensure_host_output();
+
+    std::vector<StripeTask> tasks_;
+    ReadOptions opt_;
+    std::vector<OutColumn> cols_;
+    bool planned_ = false, staged_ = false, launched_ = false, finished_ = false;
+
+    // arena sizes (bytes) and device bases
+    uint64_t size_[8] = {0};
+    uint8_t* base_[8] = {nullptr};
+
+    // descriptor tables (host copies; pointer fields relocated at stage())
+    std::vector<Seg> present_byte_segs_, data_byte_segs_, int_segs_, var_segs_;
+    std::vector<BitSeg> present_bit_segs_, data_bit_segs_;
+    std::vector<ScanDesc> scans_;
+    std::vector<CopyDesc> copies_;
+    std::vector<uint2> copy_tiles_;
+    std::vector<SpacedDesc> spaced_, spaced_late_;
+    std::vector<DecFixDesc> decfix_;
+    std::vector<TsDesc> ts_;
+    std::vector<StrCol> strcols_;
+    std::vector<RepackDesc> repacks_;
+    std::vector<ChunkDesc> chunks_;
+    uint32_t str_tiles_ = 0, repack_work_ = 0;
+
+    // stage copies: (file ptr, file offset, AR_IN offset, bytes)
+    struct StageCopy {
+        const uint8_t* src;
+        uint64_t dst_off, bytes;
+    };
+    std::vector<StageCopy> stage_copies_;
+
+    // device blobs
+    uint8_t* d_desc_ = nullptr;
+    uint64_t desc_bytes_ = 0;
+    // offsets of each table inside the descriptor blob
+    uint64_t o_pbyte_ = 0, o_dbyte_ = 0, o_int_ = 0, o_var_ = 0, o_pbit_ = 0, o_dbit_ = 0, o_scan_ = 0, o_copy_ = 0,
+             o_ctile_ = 0, o_sp_ = 0, o_sp2_ = 0, o_dec_ = 0, o_ts_ = 0, o_str_ = 0, o_rep_ = 0, o_chunk_ = 0;
+    std::vector<uint8_t> desc_blob_;
+
+    // state blob (device only, zeroed per launch): cnt[], dstart[], mis[], JobState
+    uint32_t n_cnt_ = 0, n_colstripes_ = 0;
+    uint8_t* d_state_ = nullptr;
+    uint64_t state_bytes_ = 0, o_cnt_ = 0, o_dstart_ = 0, o_mis_ = 0, o_jobstate_ = 0;
+    // meta blob (device, zeroed per launch, copied to host at finish): err[], nulls[], ptr_table[], batch_base[]
+    uint8_t* d_meta_ = nullptr;
+    uint8_t* h_meta_ = nullptr;  // pinned
+    uint64_t meta_bytes_ = 0, o_err_ = 0, o_nulls_ = 0, o_ptrs_ = 0, o_bbase_ = 0;
+    uint32_t n_nulls_ = 0;
+
+    std::vector<ColStripePlan> colstripes_;
+    // batch i -> (task, batch-in-stripe)
+    std::vector<uint32_t> batch_task_, batch_idx_;
+    std::vector<uint32_t> task_first_cs_;
+
+    // stats
+    uint64_t input_bytes_ = 0, n_rows_ = 0, n_segments_ = 0, n_launches_ = 0, output_bytes_ = 0;
+
+    cudaStream_t stream_ = nullptr;
+    bool own_stream_ = false;
+    cudaEvent_t done_ = nullptr;
+    std::shared_ptr<HostOutput> host_out_;
+    std::shared_ptr<void> dev_keepalive_;
+    friend struct DeviceArenas;
+};
+
+}  // namespace orcb

@@ -1,0 +1,1222 @@
+// CUDA kernels of the B200 ORC stripe decoder (sm_100a).  All integer / byte work, HBM-bound:
+// no tensor cores.  One warp owns one (stream, row-group) segment; lanes cooperate inside a run.
+//
+// Semantics follow the reference (datafusion-contrib/orc-rust v0.8.0) bit for bit; each kernel cites
+// the functions it replaces.  Error words: first error per column-stripe wins (atomicCAS), value =
+// OrcbStatus.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "dev.h"
+#include "kernels.h"
+
+namespace orcb {
+
+#define FULL 0xffffffffu
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void set_err(uint32_t* err, uint32_t cs, uint32_t code) { atomicCAS(&err[cs], 0u, code); }
+
+__device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+
+// w (1..64) bits, MSB-first big-endian, starting `bitpos` bits after p (read_ints, integer/util.rs:44-218).
+// Reads aligned 32-bit words; may touch up to 11 bytes past the last needed byte (arenas are padded).
+__device__ __forceinline__ uint64_t load_be_bits(const uint8_t* p, uint32_t bitpos, int w) {
+    const uint8_t* a = p + (bitpos >> 3);
+    const uintptr_t ai = (uintptr_t)a;
+    const uint32_t* q = (const uint32_t*)(ai & ~(uintptr_t)3);
+    const uint32_t sh = ((uint32_t)(ai & 3) << 3) + (bitpos & 7);  // 0..31
+    const uint32_t w0 = bswap32(__ldg(q));
+    const uint32_t w1 = bswap32(__ldg(q + 1));
+    const uint32_t w2 = (sh + (uint32_t)w > 64u) ? bswap32(__ldg(q + 2)) : 0u;
+    const uint32_t hi = __funnelshift_l(w1, w0, sh);
+    const uint32_t lo = __funnelshift_l(w2, w1, sh);
+    const uint64_t t = ((uint64_t)hi << 32) | lo;
+    return t >> (64 - w);
+}
+
+// 32 bits of an LSB-first bitmap starting at an arbitrary bit position
+__device__ __forceinline__ uint32_t load_bits32(const uint32_t* bm, uint64_t bitpos) {
+    const uint64_t wi = bitpos >> 5;
+    const uint32_t sh = (uint32_t)(bitpos & 31);
+    const uint32_t a = bm[wi];
+    const uint32_t b = sh ? bm[wi + 1] : 0u;
+    return __funnelshift_r(a, b, sh);
+}
+
+__device__ __forceinline__ int64_t trunc_n(int64_t v, int nbytes) {
+    if (nbytes >= 8) return v;
+    const int sh = 64 - 8 * nbytes;
+    return (int64_t)((uint64_t)v << sh) >> sh;
+}
+// signed_zigzag_decode in width N (integer/util.rs:536-546)
+__device__ __forceinline__ int64_t zigzag_n(int64_t v, int nbytes) {
+    const uint64_t mask = nbytes >= 8 ? ~0ull : ((1ull << (8 * nbytes)) - 1);
+    const uint64_t u = (uint64_t)v & mask;
+    const uint64_t r = (u >> 1) ^ (0ull - (u & 1));
+    return trunc_n((int64_t)(r & mask), nbytes);
+}
+__device__ __forceinline__ bool in_range_n(__int128 v, int nbytes) {
+    const __int128 lim = (__int128)1 << (8 * nbytes - 1);
+    return v >= -lim && v < lim;
+}
+// rle_v2_decode_bit_width (integer/util.rs:370-384)
+__device__ __forceinline__ int width_of(uint32_t code) {
+    return code <= 23 ? (int)code + 1 : (code == 24 ? 26 : code == 25 ? 28 : code == 26 ? 30 : code == 27 ? 32 : (int)(code - 23) * 8);
+}
+// get_closest_fixed_bits (integer/util.rs:407-421)
+__device__ __forceinline__ int closest_fixed_bits(int n) {
+    if (n == 0) return 1;
+    if (n <= 24) return n;
+    if (n <= 26) return 26;
+    if (n <= 28) return 28;
+    if (n <= 30) return 30;
+    if (n <= 32) return 32;
+    return (n + 7) & ~7;
+}
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(FULL, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+__device__ __forceinline__ uint64_t warp_incl_scan64(uint64_t v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint64_t t = __shfl_up_sync(FULL, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+__device__ __forceinline__ uint64_t warp_sum64(uint64_t v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+    return v;
+}
+
+struct SegCtx {
+    const Seg* s;
+    uint32_t* err;
+    uint32_t* mis;
+    uint64_t obase;  // element index of the first value this segment writes
+};
+
+__device__ __forceinline__ void store_val(const SegCtx& c, uint64_t idx, int64_t v) {
+    const Seg& s = *c.s;
+    switch (s.out_kind) {
+        case OUT_I16: ((int16_t*)s.out)[idx] = (int16_t)v; break;
+        case OUT_I32: ((int32_t*)s.out)[idx] = (int32_t)v; break;
+        case OUT_I64: ((int64_t*)s.out)[idx] = v; break;
+        case OUT_LEN31:
+            if ((uint64_t)v > 0x7fffffffull) set_err(c.err, s.colstripe, s.aux);
+            ((int32_t*)s.out)[idx] = (int32_t)v;
+            break;
+        case OUT_SCALE:
+            if ((uint32_t)(int32_t)v != s.aux) atomicOr(&c.mis[s.colstripe], 1u);
+            ((int32_t*)s.out)[idx] = (int32_t)v;
+            break;
+        default: break;
+    }
+}
+
+// value i of the current run -> output, clipped to [skip, skip + take)
+#define EMIT(i, val)                                                            \
+    do {                                                                        \
+        uint32_t _i = (i);                                                      \
+        if (_i >= skip && _i - skip < take) store_val(c, c.obase + produced + (_i - skip), (val)); \
+    } while (0)
+
+// read_varint::<N> (integer/util.rs:475-498); uniform across the warp. returns 0 ok / status
+__device__ __forceinline__ uint32_t parse_varint(const uint8_t* in, uint32_t& p, uint32_t len, int nbits, uint64_t& out) {
+    uint64_t num = 0;
+    uint32_t off = 0;
+    for (;;) {
+        if (p >= len) return ORCB_IO_ERROR;
+        const uint32_t b = in[p++];
+        if (off >= (uint32_t)nbits) return ORCB_VARINT_TOO_LARGE;
+        num |= (uint64_t)(b & 0x7f) << off;
+        off += 7;
+        if (!(b & 0x80)) break;
+    }
+    out = num;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// RLE v2 (integer/rle_v2/{mod,short_repeat,direct,patched_base,delta}.rs)
+// ------------------------------------------------------------------------------------------------
+__device__ void rle2_segment(SegCtx& c, uint32_t n, uint32_t* patchmap, uint32_t& end_cur, uint32_t& end_skip) {
+    const Seg& s = *c.s;
+    const uint8_t* in = (const uint8_t*)s.in;
+    const uint32_t len = s.in_len;
+    const int lane = threadIdx.x & 31;
+    const int nb = s.nbytes;
+    const bool sg = (s.flags & SEG_SIGNED) != 0;
+    uint32_t cur = s.start_byte, skip = s.run_skip, produced = 0;
+    uint32_t last_rl = 0, last_cur = cur;
+
+    while (produced < n) {
+        if (cur >= len) { set_err(c.err, s.colstripe, ORCB_OUT_OF_SPEC); return; }
+        const uint32_t hdr = (uint32_t)load_be_bits(in + cur, 0, 32);
+        const uint32_t h0 = hdr >> 24;
+        const uint32_t kind = h0 >> 6;
+        uint32_t rl, run_bytes;
+        // `take` is resolved once the run length is known
+        uint32_t take;
+        if (kind == 0) {
+            // SHORT_REPEAT short_repeat.rs:29-63
+            const int bw = (int)((h0 >> 3) & 7) + 1;
+            if (nb < bw) { set_err(c.err, s.colstripe, ORCB_OUT_OF_SPEC); return; }
+            rl = (h0 & 7) + 3;
+            run_bytes = 1 + bw;
+            if (cur + run_bytes > len) { set_err(c.err, s.colstripe, ORCB_IO_ERROR); return; }
+            int64_t v = trunc_n((int64_t)load_be_bits(in + cur + 1, 0, bw * 8), nb);
+            if (sg) v = zigzag_n(v, nb);
+            const uint32_t avail = rl > skip ? rl - skip : 0;
+            take = min(avail, n - produced);
+            EMIT(lane, v);
+        } else if (kind == 1) {
+            // DIRECT direct.rs:39-65
+            const int w = width_of((h0 >> 1) & 31);
+            if (nb * 8 < w) { set_err(c.err, s.colstripe, ORCB_OUT_OF_SPEC); return; }
+            if (cur + 2 > len) { set_err(c.err, s.colstripe, ORCB_IO_ERROR); return; }
+            rl = (((h0 & 1) << 8) | ((hdr >> 16) & 255)) + 1;
+            run_bytes = 2 + (rl * (uint32_t)w + 7) / 8;
+            if (cur + run_bytes > len) { set_err(c.err, s.colstripe, ORCB_IO_ERROR); return; }
+            const uint32_t avail = rl > skip ? rl - skip : 0;
+            take = min(avail, n - produced);
+            const uint8_t* data = in + cur + 2;
+            const uint32_t i_end = min(rl, skip + take);
+            for (uint32_t i = skip + lane; i < i_end; i += 32) {
+                int64_t v = trunc_n((int64_t)load_be_bits(data, i * (uint32_t)w, w), nb);
+                if (sg) v = zigzag_n(v, nb);
+                store_val(c, c.obase + produced + (i - skip), v);
+            }
+        } else if (kind == 3) {
+            // DELTA delta.rs:44-116
+            if (cur + 2 > len) { set_err(c.err, s.colstripe, ORCB_IO_ERROR); return; }
+            const uint32_t code = (h0 >> 1) & 31;
+            const int w = code == 0 ? 0 : width_of(code);
+            rl = (((h0 & 1) << 8) | ((hdr >> 16) & 255)) + 1;
+            uint32_t p = cur + 2;
+            uint64_t ub, ud;
+            uint32_t e = parse_varint(in, p, len, nb * 8, ub);
+            if (e) { set_err(c.err, s.colstripe, e); return; }
+            int64_t base = trunc_n((int64_t)ub, nb);
+            if (sg) base = zigzag_n(base, nb);
+            e = parse_varint(in, p, len, 64, ud);
+            if (e) { set_err(c.err, s.colstripe, e); return; }
+            const int64_t d0 = zigzag_n((int64_t)ud, 8);
+            // op = add when d0 > 0, else subtract |d0| (is_positive() is false for 0), delta.rs:77-82
+            // d0 <= 0: base - |d0| == base + d0; |i64::MIN| wraps to i64::MIN in the reference, so the
+            // subtraction of it moves by +2^63
+            const __int128 step = d0 == INT64_MIN ? ((__int128)1 << 63) : (__int128)d0;
+            const bool positive = d0 > 0;
+            if (w == 0) {
+                run_bytes = p - cur;
+                const __int128 last = (__int128)base + (__int128)(rl - 1) * step;
+                if (!in_range_n(last, nb)) { set_err(c.err, s.colstripe, ORCB_OUT_OF_SPEC); return; }
+                const uint32_t avail = rl > skip ? rl - skip : 0;
+                take = min(avail, n - produced);
+                const uint32_t i_end = min(rl, skip + take);
+                const uint64_t ustep = (uint64_t)(int64_t)step;
+                for (uint32_t i = skip + lane; i < i_end; i += 32)
+                    store_val(c, c.obase + produced + (i - skip), (int64_t)((uint64_t)base + (uint64_t)i * ustep));
+            } else {
+                if (rl < 2) { set_err(c.err, s.colstripe, ORCB_IO_ERROR); return; }
+                const uint32_t nd = rl - 2;
+                run_bytes = (p - cur) + (nd * (uint32_t)w + 7) / 8;
+                if (cur + run_bytes > len) { set_err(c.err, s.colstripe, ORCB_IO_ERROR); return; }
+                const __int128 second = (__int128)base + step;
+                if (!in_range_n(second, nb)) { set_err(c.err, s.colstripe, ORCB_OUT_OF_SPEC); return; }
+                const uint32_t avail = rl > skip ? rl - skip : 0;
+                take = min(avail, n - produced);
+                EMIT(lane == 0 ? 0u : 0xffffffffu, base);
+                EMIT(lane == 1 ? 1u : 0xffffffffu, (int64_t)second);
+                const uint8_t* data = in + p;
+                if (w == 64) {
+                    // deltas are i64 here and may be negative: exact sequential semantics
+                    __int128 acc = second;
+                    for (uint32_t i = 0; i < nd; i++) {
+                        const int64_t d = (int64_t)load_be_bits(data, i * 64u, 64);
+                        acc = positive ? acc + (__int128)d : acc - (__int128)d;
+                        if (!in_range_n(acc, nb)) { set_err(c.err, s.colstripe, ORCB_OUT_OF_SPEC); return; }
+                        EMIT((i & 31) == (uint32_t)lane ? i + 2 : 0xffffffffu, (int64_t)acc);
+                    }
+                } else {
+                    // monotone run: wrapping prefix sums are exact iff the final value is in range
+                    uint64_t carry = 0, tot_lo = 0, tot_hi = 0;
+                    const uint64_t sec = (uint64_t)(int64_t)second;
+                    for (uint32_t i0 = 0; i0 < nd; i0 += 32) {
+                        const uint32_t i = i0 + lane;
+                        const uint64_t d = i < nd ? load_be_bits(data, i * (uint32_t)w, w) : 0ull;
+                        tot_lo += d & 0xffffffffull;
+                        tot_hi += d >> 32;
+                        const uint64_t pre = warp_incl_scan64(d, lane) + carry;
+                        if (i < nd) {
+                            const uint64_t v = positive ? sec + pre : sec - pre;
+                            EMIT(i + 2, (int64_t)v);
+                        }
+                        carry = __shfl_sync(FULL, pre, 31);
+                    }
+                    tot_lo = warp_sum64(tot_lo);
+                    tot_hi = warp_sum64(tot_hi);
+                    const __int128 total = ((__int128)tot_hi << 32) + (__int128)tot_lo;
+                    const __int128 fin = positive ? second + total : second - total;
+                    if (!in_range_n(fin, nb)) { set_err(c.err, s.colstripe, ORCB_OUT_OF_SPEC); return; }
+                }
+            }
+        } else {
+            // PATCHED_BASE patched_base.rs:38-151
+            if (cur + 4 > len) { set_err(c.err, s.colstripe, ORCB_IO_ERROR); return; }
+            const int w = width_of((h0 >> 1) & 31);
+            rl = (((h0 & 1) << 8) | ((hdr >> 16) & 255)) + 1;
+            const uint32_t b3 = (hdr >> 8) & 255, b4 = hdr & 255;
+            const int base_bw = (int)((b3 >> 5) & 7) + 1;
+            const int pw = width_of(b3 & 31);
+            const int pgw = (int)((b4 >> 5) & 7) + 1;
+            if (pw + pgw > 64) { set_err(c.err, s.colstripe, ORCB_OUT_OF_SPEC); return; }
+            const uint32_t pll = b4 & 31;
+            const int cfb = closest_fixed_bits(pw + pgw);
+            const uint32_t data_off = cur + 4 + base_bw;
+            const uint32_t data_bytes = (rl * (uint32_t)w + 7) / 8;
+            run_bytes = 4 + base_bw + data_bytes + (pll * (uint32_t)cfb + 7) / 8;
+            if (cur + run_bytes > len) { set_err(c.err, s.colstripe, ORCB_IO_ERROR); return; }
+            // value width wider than N: the reference panics or silently truncates; reported as OutOfSpec
+            if (nb * 8 < w || pll == 0) { set_err(c.err, s.colstripe, ORCB_OUT_OF_SPEC); return; }
+            const uint64_t ubase = load_be_bits(in + cur + 4, 0, base_bw * 8);
+            int64_t base = (int64_t)ubase;
+            if (sg) {  // signed_msb_decode util.rs:559-569
+                const uint64_t msb = 1ull << (base_bw * 8 - 1);
+                base = (ubase & msb) ? (int64_t)(0ull - (ubase & ~msb)) : (int64_t)(ubase & ~msb);
+            }
+            base = trunc_n(base, nb);
+            const uint8_t* data = in + data_off;
+            const uint8_t* pdata = data + data_bytes;
+            // one lane per patch-list entry
+            uint64_t pe = 0;
+            if ((uint32_t)lane < pll) pe = load_be_bits(pdata, (uint32_t)lane * (uint32_t)cfb, cfb);
+            const uint64_t pmask = (1ull << pw) - 1;  // pw <= 63 here
+            const uint64_t gap = pe >> pw;
+            const uint64_t patch = pe & pmask;
+            const bool live = (uint32_t)lane < pll;
+            const bool ext = live && gap == 255 && patch == 0;
+            const uint32_t pos = warp_incl_scan(live ? (uint32_t)gap : 0u, lane);
+            const uint32_t extmask = __ballot_sync(FULL, ext);
+            const bool prev_nonext = lane > 0 && !((extmask >> (lane - 1)) & 1);
+            const bool bad = live && !ext && gap == 0 && lane > 0 && prev_nonext;
+            const uint32_t badmask = __ballot_sync(FULL, bad);
+            const uint32_t first_bad = badmask ? (uint32_t)__ffs(badmask) - 1 : 32u;
+            const bool applied = live && !ext && (uint32_t)lane < first_bad && pos < rl;
+            const uint32_t appmask = __ballot_sync(FULL, applied);
+            // trailing gap-extension entries index past the patch list in the reference (panic)
+            if ((extmask >> (pll - 1)) & 1) {
+                const uint32_t nonext = ~extmask & (pll >= 32 ? FULL : ((1u << pll) - 1));
+                const bool reached = nonext == 0 || ((appmask >> (31 - __clz(nonext))) & 1);
+                if (reached) { set_err(c.err, s.colstripe, ORCB_OUT_OF_SPEC); return; }
+            }
+            if (lane < 16) patchmap[lane] = 0;
+            __syncwarp();
+            if (applied) atomicOr(&patchmap[pos >> 5], 1u << (pos & 31));
+            __syncwarp();
+            const uint32_t avail = rl > skip ? rl - skip : 0;
+            take = min(avail, n - produced);
+            bool ovf = false;
+            for (uint32_t i = lane; i < rl; i += 32) {
+                if ((patchmap[i >> 5] >> (i & 31)) & 1) continue;
+                const int64_t raw = trunc_n((int64_t)load_be_bits(data, i * (uint32_t)w, w), nb);
+                const __int128 sum = (__int128)raw + (__int128)base;
+                if (!in_range_n(sum, nb)) ovf = true;  // checked_add :144-146
+                EMIT(i, (int64_t)sum);
+            }
+            if (applied && w >= 64) ovf = true;  // checked_shl(64) -> None :112-117
+            if (__any_sync(FULL, ovf)) { set_err(c.err, s.colstripe, ORCB_OUT_OF_SPEC); return; }
+            if (applied) {
+                const int64_t raw = trunc_n((int64_t)load_be_bits(data, pos * (uint32_t)w, w), nb);
+                const int64_t pbits = trunc_n((int64_t)(patch << w), nb);
+                const int64_t v = trunc_n((int64_t)((uint64_t)(raw | pbits) + (uint64_t)base), nb);  // wrapping_add :122-124
+                EMIT(pos, v);
+            }
+            __syncwarp();
+        }
+        last_rl = rl;
+        last_cur = cur;
+        if (skip >= rl) {
+            skip -= rl;
+        } else {
+            produced += take;
+            // position after this run for the consistency probe
+            if (produced >= n && skip + take < rl) {
+                end_cur = cur;
+                end_skip = skip + take;
+                return;
+            }
+            skip = 0;
+        }
+        cur += run_bytes;
+    }
+    (void)last_rl;
+    (void)last_cur;
+    end_cur = cur;
+    end_skip = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// RLE v1 (integer/rle_v1.rs:54-68, 90-159).  Legacy format: decoded with warp-uniform control flow.
+// ------------------------------------------------------------------------------------------------
+__device__ void rle1_segment(SegCtx& c, uint32_t n, uint32_t& end_cur, uint32_t& end_skip) {
+    const Seg& s = *c.s;
+    const uint8_t* in = (const uint8_t*)s.in;
+    const uint32_t len = s.in_len;
+    const int lane = threadIdx.x & 31;
+    const int nb = s.nbytes;
+    const bool sg = (s.flags & SEG_SIGNED) != 0;
+    uint32_t cur = s.start_byte, skip = s.run_skip, produced = 0;
+    while (produced < n) {
+        if (cur >= len) { set_err(c.err, s.colstripe, ORCB_OUT_OF_SPEC); return; }
+        const int8_t h = (int8_t)in[cur];
+        uint32_t p = cur + 1;
+        uint32_t rl, take;
+        if (h < 0) {
+            rl = (uint32_t)(-(int)h);
+            const uint32_t avail = rl > skip ? rl - skip : 0;
+            take = min(avail, n - produced);
+            for (uint32_t i = 0; i < rl; i++) {
+                uint64_t u;
+                const uint32_t e = parse_varint(in, p, len, nb * 8, u);
+                if (e) { set_err(c.err, s.colstripe, e); return; }
+                int64_t v = trunc_n((int64_t)u, nb);
+                if (sg) v = zigzag_n(v, nb);
+                EMIT((i & 31) == (uint32_t)lane ? i : 0xffffffffu, v);
+            }
+        } else {
+            rl = (uint32_t)(uint8_t)h + 3;
+            if (p >= len) { set_err(c.err, s.colstripe, ORCB_IO_ERROR); return; }
+            const int delta = (int)(int8_t)in[p++];
+            uint64_t u;
+            const uint32_t e = parse_varint(in, p, len, nb * 8, u);
+            if (e) { set_err(c.err, s.colstripe, e); return; }
+            int64_t base = trunc_n((int64_t)u, nb);
+            if (sg) base = zigzag_n(base, nb);
+            const __int128 last = (__int128)base + (__int128)(rl - 1) * (__int128)delta;
+            if (!in_range_n(last, nb)) { set_err(c.err, s.colstripe, ORCB_OUT_OF_SPEC); return; }
+            const uint32_t avail = rl > skip ? rl - skip : 0;
+            take = min(avail, n - produced);
+            for (uint32_t i = lane; i < rl; i += 32) EMIT(i, base + (int64_t)i * delta);
+        }
+        if (skip >= rl) {
+            skip -= rl;
+        } else {
+            produced += take;
+            if (produced >= n && skip + take < rl) {
+                end_cur = cur;
+                end_skip = skip + take;
+                return;
+            }
+            skip = 0;
+        }
+        cur = p;
+    }
+    end_cur = cur;
+    end_skip = 0;
+}
+
+constexpr int RLE_WARPS = 4;
+
+__global__ void __launch_bounds__(RLE_WARPS * 32) k_int_rle(const Seg* __restrict__ segs, uint32_t nseg,
+                                                            const uint32_t* __restrict__ cnt,
+                                                            const uint32_t* __restrict__ dstart, uint32_t* err,
+                                                            uint32_t* mis) {
+    __shared__ uint32_t patchmap[RLE_WARPS][16];
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= nseg) return;
+    const Seg* s = &segs[warp];
+    SegCtx c;
+    c.s = s;
+    c.err = err;
+    c.mis = mis;
+    const uint32_t n = s->cnt_idx >= 0 ? cnt[s->cnt_idx] : s->n_values;
+    c.obase = s->start_idx >= 0 ? dstart[s->start_idx] : s->out_start;
+    uint32_t end_cur = 0, end_skip = 0;
+    if (s->flags & SEG_RLE_V2) rle2_segment(c, n, patchmap[(threadIdx.x >> 5)], end_cur, end_skip);
+    else rle1_segment(c, n, end_cur, end_skip);
+    (void)end_cur;
+    (void)end_skip;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Byte RLE (encoding/byte.rs:228-247): TINYINT data and the byte layer under boolean RLE.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RLE_WARPS * 32) k_byte_rle(const Seg* __restrict__ segs, uint32_t nseg,
+                                                             const uint32_t* __restrict__ cnt,
+                                                             const uint32_t* __restrict__ dstart, uint32_t* err) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= nseg) return;
+    const Seg& s = segs[warp];
+    const int lane = threadIdx.x & 31;
+    const uint8_t* in = (const uint8_t*)s.in;
+    const uint32_t len = s.in_len;
+    // for boolean streams n_values counts BITS; aux = 1 marks "bits": convert to bytes incl. the bit offset
+    uint32_t n = s.cnt_idx >= 0 ? cnt[s.cnt_idx] : s.n_values;
+    if (s.aux & 1) n = (n + (s.aux >> 1) + 7) / 8;  // aux>>1 = bit_skip
+    uint8_t* out = (uint8_t*)s.out + (s.start_idx >= 0 ? dstart[s.start_idx] : s.out_start);
+    uint32_t cur = s.start_byte, skip = s.run_skip, produced = 0;
+    while (produced < n) {
+        if (cur >= len) { set_err(err, s.colstripe, ORCB_IO_ERROR); return; }
+        const uint32_t h = in[cur];
+        uint32_t rl, run_bytes;
+        if (h < 0x80) {
+            rl = h + 3;
+            run_bytes = 2;
+            if (cur + 2 > len) { set_err(err, s.colstripe, ORCB_IO_ERROR); return; }
+            const uint8_t v = in[cur + 1];
+            const uint32_t avail = rl > skip ? rl - skip : 0;
+            const uint32_t take = min(avail, n - produced);
+            for (uint32_t i = lane; i < take; i += 32) out[produced + i] = v;
+            if (skip >= rl) skip -= rl;
+            else { produced += take; skip = 0; }
+        } else {
+            rl = 0x100 - h;
+            run_bytes = 1 + rl;
+            if (cur + run_bytes > len) { set_err(err, s.colstripe, ORCB_IO_ERROR); return; }
+            const uint32_t avail = rl > skip ? rl - skip : 0;
+            const uint32_t take = min(avail, n - produced);
+            for (uint32_t i = lane; i < take; i += 32) out[produced + i] = in[cur + 1 + skip + i];
+            if (skip >= rl) skip -= rl;
+            else { produced += take; skip = 0; }
+        }
+        cur += run_bytes;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Boolean bits (encoding/boolean.rs:101-113 + NullBuffer::from, array_decoder/mod.rs:209-213):
+// MSB-first bytes -> LSB-first Arrow bitmap at an arbitrary bit position, plus popcount.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t load_msb_bits32(const uint8_t* src, uint32_t sbit) {
+    // 32 stream bits starting at MSB-first bit index sbit, returned LSB-first
+    const uint8_t* a = src + (sbit >> 3);
+    const uintptr_t ai = (uintptr_t)a;
+    const uint32_t* q = (const uint32_t*)(ai & ~(uintptr_t)3);
+    const uint32_t sh = ((uint32_t)(ai & 3) << 3) + (sbit & 7);
+    // per-byte bit reversal keeps byte order: brev reverses everything, bswap restores byte order
+    const uint32_t w0 = bswap32(__brev(q[0]));
+    const uint32_t w1 = bswap32(__brev(q[1]));
+    return __funnelshift_r(w0, w1, sh);
+}
+
+__global__ void __launch_bounds__(128) k_bits(const BitSeg* __restrict__ segs, uint32_t nseg, uint32_t* cnt,
+                                               const uint32_t* __restrict__ dstart) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= nseg) return;
+    const BitSeg& s = segs[warp];
+    const int lane = threadIdx.x & 31;
+    const uint32_t n = s.cnt_idx >= 0 ? cnt[s.cnt_idx] : s.n_bits;
+    const uint64_t d0 = s.start_idx >= 0 ? (uint64_t)dstart[s.start_idx] : (uint64_t)s.dst_bit0;
+    const uint8_t* src = (const uint8_t*)s.src;
+    uint32_t* dst = (uint32_t*)s.dst;
+    uint32_t pc = 0;
+    if (n > 0) {
+        const uint64_t wfirst = d0 >> 5, wlast = (d0 + n - 1) >> 5;
+        for (uint64_t wi = wfirst + lane; wi <= wlast; wi += 32) {
+            const uint64_t lo = max(wi << 5, d0), hi = min((wi << 5) + 32, d0 + (uint64_t)n);
+            const uint32_t nbits = (uint32_t)(hi - lo);
+            const uint32_t sbit = (uint32_t)(lo - d0) + s.bit_skip;
+            uint32_t v = load_msb_bits32(src, sbit);
+            if (nbits < 32) v &= (1u << nbits) - 1;
+            pc += __popc(v);
+            const uint32_t word = v << (uint32_t)(lo - (wi << 5));
+            if (nbits == 32) dst[wi] = word;
+            else if (word) atomicOr(&dst[wi], word);
+        }
+    }
+    if (s.popc_out >= 0) {
+        pc = (uint32_t)warp_sum64(pc);
+        if (lane == 0) cnt[s.popc_out] = pc;
+    }
+}
+
+// exclusive scan of per-group non-null counts (value-stream entry index of each row group)
+__global__ void k_seg_scan(const ScanDesc* __restrict__ descs, uint32_t ndesc, uint32_t* cnt, uint32_t* dstart) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= ndesc) return;
+    const ScanDesc d = descs[warp];
+    const int lane = threadIdx.x & 31;
+    uint32_t carry = 0;
+    for (uint32_t g0 = 0; g0 < d.n_groups; g0 += 32) {
+        const uint32_t g = g0 + lane;
+        const uint32_t v = g < d.n_groups ? cnt[d.base + g] : 0;
+        const uint32_t inc = warp_incl_scan(v, lane);
+        if (g < d.n_groups) dstart[d.base + g] = carry + inc - v;
+        carry += __shfl_sync(FULL, inc, 31);
+    }
+    if (lane == 0) {
+        cnt[d.base + d.n_groups] = carry;
+        dstart[d.base + d.n_groups] = carry;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Decimal DATA: unbounded zigzag varints -> i128 (encoding/decimal.rs:46-51, integer/util.rs:475-527).
+// Terminator bytes found with ballot; the lane owning a terminator assembles its value.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_varint128(const Seg* __restrict__ segs, uint32_t nseg,
+                                                   const uint32_t* __restrict__ cnt,
+                                                   const uint32_t* __restrict__ dstart, uint32_t* err) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= nseg) return;
+    const Seg& s = segs[warp];
+    const int lane = threadIdx.x & 31;
+    const uint8_t* in = (const uint8_t*)s.in;
+    const uint32_t len = s.in_len;
+    const uint32_t n = s.cnt_idx >= 0 ? cnt[s.cnt_idx] : s.n_values;
+    const uint64_t obase = s.start_idx >= 0 ? dstart[s.start_idx] : s.out_start;
+    uint4* out = (uint4*)s.out;
+    uint32_t produced = 0;
+    uint32_t cur = s.start_byte;      // first byte of this 32-byte window
+    uint32_t open_start = cur;        // first byte of the value that is still open
+    while (produced < n) {
+        if (cur >= len) { set_err(err, s.colstripe, ORCB_IO_ERROR); return; }
+        const uint32_t p = cur + lane;
+        const bool inb = p < len;
+        const uint32_t b = inb ? in[p] : 0x80u;
+        const uint32_t term = __ballot_sync(FULL, inb && !(b & 0x80));
+        const bool is_term = (term >> lane) & 1;
+        const uint32_t below = term & ((1u << lane) - 1);
+        const uint32_t vi = produced + __popc(below);
+        if (is_term && vi < n) {
+            const uint32_t start = below ? cur + (32 - __clz(below)) : open_start;
+            const uint32_t nbv = p - start + 1;
+            if (nbv > 19) {
+                set_err(err, s.colstripe, ORCB_VARINT_TOO_LARGE);  // shift >= 128
+            }
+            uint64_t lo = 0, hi = 0;
+            for (uint32_t k = 0; k < nbv && k < 19; k++) {
+                const uint64_t x = in[start + k] & 0x7f;
+                const uint32_t sh = 7 * k;
+                if (sh < 64) {
+                    lo |= x << sh;
+                    if (sh > 57) hi |= x >> (64 - sh);
+                } else {
+                    hi |= x << (sh - 64);
+                }
+            }
+            // zigzag: (v >>> 1) ^ -(v & 1) on 128 bits
+            const uint64_t sgn = 0ull - (lo & 1);
+            const uint64_t rlo = ((lo >> 1) | (hi << 63)) ^ sgn;
+            const uint64_t rhi = (hi >> 1) ^ sgn;
+            out[obase + vi] = make_uint4((uint32_t)rlo, (uint32_t)(rlo >> 32), (uint32_t)rhi, (uint32_t)(rhi >> 32));
+        }
+        produced += __popc(term);
+        if (term) open_start = cur + (32 - __clz(term));
+        else if (min(cur + 32, len) - open_start >= 20 && produced < n) {
+            // 20 continuation bytes in a row: checked_shl fails at shift >= 128
+            set_err(err, s.colstripe, ORCB_VARINT_TOO_LARGE);
+            return;
+        }
+        cur += 32;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Raw byte copies: FLOAT/DOUBLE streams (encoding/float.rs:70-74), string DATA (string.rs:135-140).
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t COPY_TILE = 16384;  // bytes per CTA
+
+__global__ void __launch_bounds__(256) k_copy(const CopyDesc* __restrict__ descs, const uint2* __restrict__ tiles,
+                                              uint32_t ntiles, const uint32_t* __restrict__ cnt, uint32_t* err) {
+    if (blockIdx.x >= ntiles) return;
+    const uint2 t = tiles[blockIdx.x];  // (desc index, tile index)
+    const CopyDesc& d = descs[t.x];
+    const uint64_t total = d.cnt_idx >= 0 ? (uint64_t)cnt[d.cnt_idx] * d.width : d.n_bytes;
+    if (total > d.src_len) {
+        if (t.y == 0 && threadIdx.x == 0) set_err(err, d.colstripe, ORCB_IO_ERROR);
+        return;
+    }
+    const uint64_t off = (uint64_t)t.y * COPY_TILE;
+    if (off >= total) return;
+    const uint32_t nbytes = (uint32_t)min((uint64_t)COPY_TILE, total - off);
+    const uint8_t* src = (const uint8_t*)d.src + off;
+    uint8_t* dst = (uint8_t*)d.dst + off;  // dst tiles are 16-byte aligned (dst base is 256-byte aligned)
+    const uint32_t mis = (uint32_t)((uintptr_t)src & 3);
+    if (mis == 0 && (((uintptr_t)src & 15) == 0)) {
+        const uint32_t n16 = nbytes >> 4;
+        for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) ((uint4*)dst)[i] = __ldg((const uint4*)src + i);
+        for (uint32_t i = (n16 << 4) + threadIdx.x; i < nbytes; i += blockDim.x) dst[i] = src[i];
+    } else {
+        // unaligned source: aligned 32-bit loads + byte funnel, 16-byte aligned stores
+        const uint32_t* q = (const uint32_t*)((uintptr_t)src & ~(uintptr_t)3);
+        const uint32_t sh = mis * 8;
+        const uint32_t n16 = nbytes >> 4;
+        for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) {
+            const uint32_t* w = q + i * 4;
+            const uint32_t a = __ldg(w), b = __ldg(w + 1), c2 = __ldg(w + 2), d2 = __ldg(w + 3);
+            const uint32_t e = sh ? __ldg(w + 4) : 0u;
+            uint4 v;
+            v.x = __funnelshift_r(a, b, sh);
+            v.y = __funnelshift_r(b, c2, sh);
+            v.z = __funnelshift_r(c2, d2, sh);
+            v.w = __funnelshift_r(d2, e, sh);
+            ((uint4*)dst)[i] = v;
+        }
+        for (uint32_t i = (n16 << 4) + threadIdx.x; i < nbytes; i += blockDim.x) dst[i] = src[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// decode_spaced (encoding/mod.rs:64-91): dense values -> row slots, null slots zero.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_spaced(const SpacedDesc* __restrict__ descs, uint32_t ndesc,
+                                                const uint32_t* __restrict__ dstart) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= ndesc) return;
+    const SpacedDesc& d = descs[warp];
+    const int lane = threadIdx.x & 31;
+    const uint32_t* valid = (const uint32_t*)d.valid;
+    uint64_t rank0 = dstart[d.start_idx];
+    for (uint32_t t = 0; t < d.n_rows; t += 32) {
+        const uint32_t nbits = min(32u, d.n_rows - t);
+        uint32_t word = load_bits32(valid, (uint64_t)d.row0 + t);
+        if (nbits < 32) word &= (1u << nbits) - 1;
+        const bool v = (word >> lane) & 1;
+        const uint64_t rank = rank0 + __popc(word & ((1u << lane) - 1));
+        const uint64_t row = (uint64_t)d.row0 + t + lane;
+        const bool inr = (uint32_t)lane < nbits;
+        switch (d.width) {
+            case 1: if (inr) ((uint8_t*)d.dst)[row] = v ? ((const uint8_t*)d.src)[rank] : (uint8_t)0; break;
+            case 2: if (inr) ((uint16_t*)d.dst)[row] = v ? ((const uint16_t*)d.src)[rank] : (uint16_t)0; break;
+            case 4: if (inr) ((uint32_t*)d.dst)[row] = v ? ((const uint32_t*)d.src)[rank] : 0u; break;
+            case 8: if (inr) ((uint64_t*)d.dst)[row] = v ? ((const uint64_t*)d.src)[rank] : 0ull; break;
+            case 16: if (inr) ((uint4*)d.dst)[row] = v ? ((const uint4*)d.src)[rank] : make_uint4(0, 0, 0, 0); break;
+            default: {
+                // bit mode (boolean values): dst is a zero-initialised stripe-level bitmap
+                const uint32_t* sb = (const uint32_t*)d.src;
+                const bool bit = v && ((sb[rank >> 5] >> (rank & 31)) & 1);
+                const uint32_t bal = __ballot_sync(FULL, bit);
+                if (lane == 0 && bal) {
+                    const uint64_t bp = (uint64_t)d.row0 + t;
+                    const uint32_t sh = (uint32_t)(bp & 31);
+                    atomicOr(&((uint32_t*)d.dst)[bp >> 5], bal << sh);
+                    if (sh && (bal >> (32 - sh))) atomicOr(&((uint32_t*)d.dst)[(bp >> 5) + 1], bal >> (32 - sh));
+                }
+            }
+        }
+        rank0 += __popc(word);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Decimal scale repair (array_decoder/decimal.rs:138-166) — only does work when a SECONDARY value
+// differed from the type scale (flag raised by k_int_rle OUT_SCALE).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_decimal_fix(const DecFixDesc* __restrict__ descs,
+                                                     const uint32_t* __restrict__ cnt,
+                                                     const uint32_t* __restrict__ mis) {
+    const DecFixDesc& d = descs[blockIdx.y];
+    if (!mis[d.colstripe]) return;
+    const uint32_t n = d.cnt_idx >= 0 ? cnt[d.cnt_idx] : d.n;
+    __int128* vals = (__int128*)d.vals;
+    const int32_t* scales = (const int32_t*)d.scales;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t vs = (uint32_t)scales[i];
+        if (vs == d.fixed_scale) continue;
+        __int128 v = vals[i];
+        if (d.fixed_scale < vs) {
+            uint32_t k = vs - d.fixed_scale;
+            // 10^k overflows i128 for k >= 39 (the reference panics in pow); quotient is then 0
+            if (k >= 39) v = 0;
+            else {
+                __int128 f = 1;
+                for (uint32_t j = 0; j < k; j++) f *= 10;
+                v = v / f;
+            }
+        } else {
+            uint32_t k = d.fixed_scale - vs;
+            unsigned __int128 f = 1;
+            for (uint32_t j = 0; j < k && j < 64; j++) f *= 10;
+            v = (__int128)((unsigned __int128)v * f);
+        }
+        vals[i] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Timestamp recombination (encoding/timestamp.rs:121-196)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_timestamp(const TsDesc* __restrict__ descs, const uint32_t* __restrict__ cnt,
+                                                   uint32_t* err) {
+    const TsDesc& d = descs[blockIdx.y];
+    const uint32_t n = d.cnt_idx >= 0 ? cnt[d.cnt_idx] : d.n;
+    const int64_t* secs = (const int64_t*)d.secs;
+    const int64_t* nanos = (const int64_t*)d.nanos;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint64_t ns = (uint64_t)nanos[i];
+        const uint32_t zeros = (uint32_t)(ns & 7);
+        ns >>= 3;
+        if (zeros) {
+            uint64_t p = 100;
+            for (uint32_t j = 1; j < zeros; j++) p *= 10;
+            ns *= p;  // wrapping, as the release-mode reference
+        }
+        int64_t sec = (int64_t)((uint64_t)secs[i] + (uint64_t)d.base);
+        if (sec < 0 && ns > 999999ull) sec -= 1;
+        const __int128 t = (__int128)sec * 1000000000 + (__int128)ns;
+        if (d.as_i128) {
+            ((__int128*)d.out)[i] = t;
+        } else {
+            const __int128 u = (__int128)d.unit_ns;
+            const __int128 q = t / u;
+            if (t % u != 0 || q > (__int128)INT64_MAX || q < (__int128)INT64_MIN) set_err(err, d.colstripe, ORCB_DECODE_TIMESTAMP);
+            ((int64_t*)d.out)[i] = (int64_t)q;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Strings (array_decoder/string.rs:111-153, 205-224): lengths -> per-batch i32 offsets, dictionary gather.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ const StrCol& find_strcol(const StrCol* cols, uint32_t ncols, uint32_t tile) {
+    uint32_t lo = 0, hi = ncols;  // last col with tile0 <= tile
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (cols[mid].tile0 <= tile) lo = mid;
+        else hi = mid;
+    }
+    return cols[lo];
+}
+
+// length of row r (0 for null rows; dictionary keys are bounds-checked for valid rows)
+__device__ __forceinline__ uint32_t str_row_len(const StrCol& c, uint32_t r, uint32_t* err, int32_t* key_out) {
+    const int32_t x = ((const int32_t*)c.lens)[r];
+    if (c.mode == 0) return (uint32_t)x;
+    bool valid = true;
+    if (c.valid) valid = (((const uint32_t*)c.valid)[r >> 5] >> (r & 31)) & 1;
+    if (!valid) { *key_out = -1; return 0; }
+    if ((uint32_t)x >= c.dict_size) {  // DictionaryArray::try_new rejects out-of-range valid keys
+        set_err(err, c.colstripe, ORCB_ARROW);
+        *key_out = -1;
+        return 0;
+    }
+    *key_out = x;
+    return (uint32_t)((const int32_t*)c.dict_len)[x];
+}
+
+// dictionary LENGTH -> offsets (one warp per dictionary)
+__global__ void k_dict_prepare(StrCol* cols, uint32_t ncols, uint32_t* err) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= ncols) return;
+    const StrCol& c = cols[warp];
+    if (c.mode != 1) return;
+    const int lane = threadIdx.x & 31;
+    const int32_t* dl = (const int32_t*)c.dict_len;
+    int32_t* doff = (int32_t*)c.dict_off;
+    uint64_t carry = 0;
+    for (uint32_t i0 = 0; i0 < c.dict_size; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const uint64_t v = i < c.dict_size ? (uint64_t)(uint32_t)dl[i] : 0;
+        const uint64_t inc = warp_incl_scan64(v, lane);
+        if (i < c.dict_size) doff[i] = (int32_t)(carry + inc - v);
+        carry += __shfl_sync(FULL, inc, 31);
+    }
+    if (lane == 0) {
+        doff[c.dict_size] = (int32_t)carry;
+        // the dictionary itself is a string batch: offsets must fit i32 and its bytes must exist
+        if (carry > 0x7fffffffull) set_err(err, c.colstripe, ORCB_OFFSET_OVERFLOW);
+        else if (carry > c.dict_data_len) set_err(err, c.colstripe, ORCB_ARROW);
+    }
+}
+
+__device__ __forceinline__ void tile_rows(const StrCol& c, uint32_t tile, uint32_t& b, uint32_t& r0, uint32_t& nr) {
+    b = tile / c.tiles_per_batch;
+    const uint32_t k = tile - b * c.tiles_per_batch;
+    const uint32_t brow0 = b * c.batch_size;
+    const uint32_t brows = min(c.batch_size, c.n_rows - brow0);
+    r0 = brow0 + k * STR_TILE;
+    const uint32_t off = k * STR_TILE;
+    nr = off >= brows ? 0 : min(STR_TILE, brows - off);
+}
+
+__global__ void __launch_bounds__(128) k_str_tile_sum(const StrCol* __restrict__ cols, uint32_t ncols, uint32_t ntiles,
+                                                      uint32_t* err) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= ntiles) return;
+    const StrCol& c = find_strcol(cols, ncols, warp);
+    const uint32_t tile = warp - c.tile0;
+    const int lane = threadIdx.x & 31;
+    uint32_t b, r0, nr;
+    tile_rows(c, tile, b, r0, nr);
+    uint64_t sum = 0;
+    for (uint32_t i = lane; i < nr; i += 32) {
+        int32_t key;
+        sum += str_row_len(c, r0 + i, err, &key);
+    }
+    sum = warp_sum64(sum);
+    if (lane == 0) ((uint64_t*)c.tile_base)[tile] = sum;
+}
+
+// per column: exclusive scan of tile sums, batch bases, overflow checks, dictionary data allocation
+__global__ void k_str_tile_scan(StrCol* cols, uint32_t ncols, uint32_t* err, JobState* st, uint64_t heap_base,
+                                uint64_t heap_cap, uint64_t* ptr_table) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= ncols) return;
+    StrCol& c = cols[warp];
+    const int lane = threadIdx.x & 31;
+    uint64_t* tb = (uint64_t*)c.tile_base;
+    uint64_t* bb = (uint64_t*)c.batch_base;
+    uint64_t carry = 0;
+    for (uint32_t t0 = 0; t0 < c.n_tiles; t0 += 32) {
+        const uint32_t t = t0 + lane;
+        const uint64_t v = t < c.n_tiles ? tb[t] : 0;
+        const uint64_t inc = warp_incl_scan64(v, lane);
+        if (t < c.n_tiles) {
+            const uint64_t ex = carry + inc - v;
+            tb[t] = ex;
+            if (t % c.tiles_per_batch == 0) bb[t / c.tiles_per_batch] = ex;
+        }
+        carry += __shfl_sync(FULL, inc, 31);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        tb[c.n_tiles] = carry;
+        bb[c.n_batches] = carry;
+    }
+    __syncwarp();
+    // OffsetOverflow: a batch whose bytes exceed i32::MAX (string.rs:125-133)
+    for (uint32_t b = lane; b < c.n_batches; b += 32) {
+        if (bb[b + 1] - bb[b] > 0x7fffffffull) set_err(err, c.colstripe, c.mode == 0 ? ORCB_OFFSET_OVERFLOW : ORCB_ARROW);
+    }
+    if (lane == 0) {
+        if (c.mode == 1) {
+            const unsigned long long need = (carry + 255ull) & ~255ull;
+            const unsigned long long at = atomicAdd(&st->heap_top, need);
+            if (at + need > heap_cap) {
+                set_err(err, c.colstripe, ORCB_DEVICE_HEAP_OVERFLOW);
+                c.data = 0;
+            } else {
+                c.data = heap_base + at;
+            }
+        } else if (carry > c.data_len) {
+            // fewer DATA bytes than the lengths claim: GenericByteArray::try_new fails (Arrow error)
+            set_err(err, c.colstripe, ORCB_ARROW);
+        }
+        ptr_table[c.meta_slot] = c.data;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_str_offsets(const StrCol* __restrict__ cols, uint32_t ncols, uint32_t ntiles,
+                                                     uint32_t* err) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= ntiles) return;
+    const StrCol& c = find_strcol(cols, ncols, warp);
+    const uint32_t tile = warp - c.tile0;
+    const int lane = threadIdx.x & 31;
+    uint32_t b, r0, nr;
+    tile_rows(c, tile, b, r0, nr);
+    const uint64_t* tb = (const uint64_t*)c.tile_base;
+    const uint64_t* bb = (const uint64_t*)c.batch_base;
+    const uint64_t bbase = bb[b];
+    uint64_t run = tb[tile];  // absolute byte offset of the first row of this tile
+    int32_t* offs = (int32_t*)c.offsets + (uint64_t)b * (c.batch_size + 1) + (r0 - b * c.batch_size);
+    const uint8_t* dict = (const uint8_t*)c.dict_data;
+    const int32_t* doff = (const int32_t*)c.dict_off;
+    uint8_t* data = (uint8_t*)c.data;
+    for (uint32_t i0 = 0; i0 < nr; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        int32_t key = -1;
+        const uint32_t l = i < nr ? str_row_len(c, r0 + i, err, &key) : 0;
+        const uint64_t inc = warp_incl_scan64(l, lane);
+        const uint64_t abs0 = run + inc - l;
+        if (i < nr) offs[i] = (int32_t)(abs0 - bbase);
+        if (c.mode == 1 && key >= 0 && data) {
+            const uint8_t* sp = dict + doff[key];
+            uint8_t* dp = data + abs0;
+            for (uint32_t k = 0; k < l; k++) dp[k] = sp[k];
+        }
+        run += __shfl_sync(FULL, inc, 31);
+    }
+    // closing offset of the batch
+    const uint32_t brow0 = b * c.batch_size;
+    const uint32_t brows = min(c.batch_size, c.n_rows - brow0);
+    if (lane == 0 && r0 + nr == brow0 + brows) ((int32_t*)c.offsets)[(uint64_t)b * (c.batch_size + 1) + brows] = (int32_t)(bb[b + 1] - bbase);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stripe-level bitmaps -> per-batch bitmaps + null counts (derive_present_vec, array_decoder/mod.rs:231-252)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_repack(const RepackDesc* __restrict__ descs, uint32_t ndesc, uint32_t nwork,
+                                                uint32_t* nulls) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= nwork) return;
+    uint32_t lo = 0, hi = ndesc;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (descs[mid].batch0 <= warp) lo = mid;
+        else hi = mid;
+    }
+    const RepackDesc& d = descs[lo];
+    const uint32_t b = warp - d.batch0;
+    const int lane = threadIdx.x & 31;
+    const uint32_t row0 = b * d.batch_size;
+    const uint32_t rows = min(d.batch_size, d.n_rows - row0);
+    const uint32_t* src = (const uint32_t*)d.src;
+    uint32_t* dst = (uint32_t*)((uint8_t*)d.dst + (uint64_t)b * d.dst_stride);
+    const uint32_t nwords = (rows + 31) >> 5;
+    uint32_t pc = 0;
+    for (uint32_t w = lane; w < nwords; w += 32) {
+        uint32_t v = load_bits32(src, (uint64_t)row0 + (uint64_t)w * 32);
+        const uint32_t rem = rows - w * 32;
+        if (rem < 32) v &= (1u << rem) - 1;
+        dst[w] = v;
+        pc += __popc(v);
+    }
+    if (d.null_out >= 0) {
+        pc = (uint32_t)warp_sum64(pc);
+        if (lane == 0) nulls[d.null_out + b] = rows - pc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Compression chunks (src/compression.rs:113-123, 244-275): original chunks are copied, Snappy and LZ4
+// blocks are decoded by one warp per chunk: lane 0 walks the tags, all lanes move the bytes.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_copy_fwd(uint8_t* dst, const uint8_t* src, uint32_t n, int lane) {
+    for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
+}
+// overlapping back-reference: dst[i] = dst[i - dist]; bytes further than `dist` ahead depend on bytes
+// written earlier in this same copy, so copy in rounds of `dist` bytes when dist < 32
+__device__ __forceinline__ void warp_copy_match(uint8_t* out, uint32_t o, uint32_t dist, uint32_t n, int lane) {
+    if (dist >= 32) {
+        for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            uint8_t v = 0;
+            if (i < n) v = out[o + i - dist];
+            __syncwarp();
+            if (i < n) out[o + i] = v;
+            __syncwarp();
+        }
+    } else {
+        // period replication: byte i equals pattern byte (i mod dist)
+        for (uint32_t i = lane; i < n; i += 32) out[o + i] = out[o - dist + (i % dist)];
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(128) k_decompress(const ChunkDesc* __restrict__ chunks, uint32_t nchunks, uint32_t* err,
+                                                    uint32_t* out_lens) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= nchunks) return;
+    const ChunkDesc& c = chunks[warp];
+    const int lane = threadIdx.x & 31;
+    const uint8_t* s = (const uint8_t*)c.src;
+    uint8_t* d = (uint8_t*)c.dst;
+    const uint32_t n = c.src_len;
+    uint32_t o = 0;
+    uint32_t fail = 0;
+    if (c.codec == 0) {
+        if (n > c.dst_cap) fail = ORCB_UNEXPECTED;
+        else warp_copy_fwd(d, s, n, lane);
+        o = n;
+    } else if (c.codec == 2) {
+        // Snappy raw block (snap::raw::Decoder, compression.rs:161-172)
+        uint32_t p = 0;
+        uint64_t ulen = 0;
+        for (uint32_t sh = 0;; sh += 7) {
+            if (p >= n || sh > 35) { fail = ORCB_BUILD_SNAPPY_DECODER; break; }
+            const uint32_t b = s[p++];
+            ulen |= (uint64_t)(b & 0x7f) << sh;
+            if (b < 0x80) break;
+        }
+        if (!fail && ulen > c.dst_cap) fail = ORCB_BUILD_SNAPPY_DECODER;
+        while (!fail && p < n) {
+            const uint32_t tag = s[p++];
+            const uint32_t t = tag & 3;
+            if (t == 0) {
+                uint32_t l = tag >> 2;
+                if (l >= 60) {
+                    const uint32_t extra = l - 59;
+                    if (p + extra > n) { fail = ORCB_BUILD_SNAPPY_DECODER; break; }
+                    l = 0;
+                    for (uint32_t k = 0; k < extra; k++) l |= (uint32_t)s[p + k] << (8 * k);
+                    p += extra;
+                }
+                l += 1;
+                if (p + l > n || (uint64_t)o + l > ulen) { fail = ORCB_BUILD_SNAPPY_DECODER; break; }
+                warp_copy_fwd(d + o, s + p, l, lane);
+                __syncwarp();
+                p += l;
+                o += l;
+            } else {
+                uint32_t l, dist;
+                if (t == 1) {
+                    if (p + 1 > n) { fail = ORCB_BUILD_SNAPPY_DECODER; break; }
+                    l = 4 + ((tag >> 2) & 7);
+                    dist = ((tag >> 5) << 8) | s[p];
+                    p += 1;
+                } else if (t == 2) {
+                    if (p + 2 > n) { fail = ORCB_BUILD_SNAPPY_DECODER; break; }
+                    l = 1 + (tag >> 2);
+                    dist = s[p] | ((uint32_t)s[p + 1] << 8);
+                    p += 2;
+                } else {
+                    if (p + 4 > n) { fail = ORCB_BUILD_SNAPPY_DECODER; break; }
+                    l = 1 + (tag >> 2);
+                    dist = s[p] | ((uint32_t)s[p + 1] << 8) | ((uint32_t)s[p + 2] << 16) | ((uint32_t)s[p + 3] << 24);
+                    p += 4;
+                }
+                if (dist == 0 || dist > o || (uint64_t)o + l > ulen) { fail = ORCB_BUILD_SNAPPY_DECODER; break; }
+                warp_copy_match(d, o, dist, l, lane);
+                o += l;
+            }
+        }
+        if (!fail && o != ulen) fail = ORCB_BUILD_SNAPPY_DECODER;
+    } else {
+        // LZ4 block (lz4_flex::block::decompress(src, max), compression.rs:185-195)
+        uint32_t p = 0;
+        while (!fail && p < n) {
+            const uint32_t tok = s[p++];
+            uint32_t ll = tok >> 4;
+            if (ll == 15) {
+                for (;;) {
+                    if (p >= n) { fail = ORCB_BUILD_LZ4_DECODER; break; }
+                    const uint32_t b = s[p++];
+                    ll += b;
+                    if (b != 255) break;
+                }
+                if (fail) break;
+            }
+            if (p + ll > n || o + ll > c.dst_cap) { fail = ORCB_BUILD_LZ4_DECODER; break; }
+            warp_copy_fwd(d + o, s + p, ll, lane);
+            __syncwarp();
+            p += ll;
+            o += ll;
+            if (p >= n) break;
+            if (p + 2 > n) { fail = ORCB_BUILD_LZ4_DECODER; break; }
+            const uint32_t dist = s[p] | ((uint32_t)s[p + 1] << 8);
+            p += 2;
+            uint32_t ml = tok & 15;
+            if (ml == 15) {
+                for (;;) {
+                    if (p >= n) { fail = ORCB_BUILD_LZ4_DECODER; break; }
+                    const uint32_t b = s[p++];
+                    ml += b;
+                    if (b != 255) break;
+                }
+                if (fail) break;
+            }
+            ml += 4;
+            if (dist == 0 || dist > o || o + ml > c.dst_cap) { fail = ORCB_BUILD_LZ4_DECODER; break; }
+            warp_copy_match(d, o, dist, ml, lane);
+            o += ml;
+        }
+    }
+    if (!fail && c.expect_len >= 0 && o != (uint32_t)c.expect_len) fail = ORCB_UNEXPECTED;
+    if (lane == 0) {
+        if (fail) set_err(err, c.colstripe, fail);
+        if (out_lens) out_lens[warp] = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side launch wrappers
+// ------------------------------------------------------------------------------------------------
+static inline uint32_t blocks_for_warps(uint32_t nwarps, uint32_t warps_per_block) {
+    return (nwarps + warps_per_block - 1) / warps_per_block;
+}
+
+#define LAUNCH_CHECK()                           \
+    do {                                         \
+        cudaError_t _e = cudaGetLastError();     \
+        if (_e != cudaSuccess) return (int)_e;   \
+    } while (0)
+
+int launch_int_rle(const Seg* segs, uint32_t n, const uint32_t* cnt, const uint32_t* dstart, uint32_t* err, uint32_t* mis,
+                   cudaStream_t st) {
+    if (!n) return 0;
+    k_int_rle<<<blocks_for_warps(n, RLE_WARPS), RLE_WARPS * 32, 0, st>>>(segs, n, cnt, dstart, err, mis);
+    LAUNCH_CHECK();
+    return 0;
+}
+int launch_byte_rle(const Seg* segs, uint32_t n, const uint32_t* cnt, const uint32_t* dstart, uint32_t* err,
+                    cudaStream_t st) {
+    if (!n) return 0;
+    k_byte_rle<<<blocks_for_warps(n, RLE_WARPS), RLE_WARPS * 32, 0, st>>>(segs, n, cnt, dstart, err);
+    LAUNCH_CHECK();
+    return 0;
+}
+int launch_bits(const BitSeg* segs, uint32_t n, uint32_t* cnt, const uint32_t* dstart, cudaStream_t st) {
+    if (!n) return 0;
+    k_bits<<<blocks_for_warps(n, 4), 128, 0, st>>>(segs, n, cnt, dstart);
+    LAUNCH_CHECK();
+    return 0;
+}
+int launch_seg_scan(const ScanDesc* d, uint32_t n, uint32_t* cnt, uint32_t* dstart, cudaStream_t st) {
+    if (!n) return 0;
+    k_seg_scan<<<blocks_for_warps(n, 4), 128, 0, st>>>(d, n, cnt, dstart);
+    LAUNCH_CHECK();
+    return 0;
+}
+int launch_varint128(const Seg* segs, uint32_t n, const uint32_t* cnt, const uint32_t* dstart, uint32_t* err,
+                     cudaStream_t st) {
+    if (!n) return 0;
+    k_varint128<<<blocks_for_warps(n, 4), 128, 0, st>>>(segs, n, cnt, dstart, err);
+    LAUNCH_CHECK();
+    return 0;
+}
+int launch_copy(const CopyDesc* d, const uint2* tiles, uint32_t ntiles, const uint32_t* cnt, uint32_t* err,
+                cudaStream_t st) {
+    if (!ntiles) return 0;
+    k_copy<<<ntiles, 256, 0, st>>>(d, tiles, ntiles, cnt, err);
+    LAUNCH_CHECK();
+    return 0;
+}
+int launch_spaced(const SpacedDesc* d, uint32_t n, const uint32_t* dstart, cudaStream_t st) {
+    if (!n) return 0;
+    k_spaced<<<blocks_for_warps(n, 4), 128, 0, st>>>(d, n, dstart);
+    LAUNCH_CHECK();
+    return 0;
+}
+int launch_decimal_fix(const DecFixDesc* d, uint32_t n, const uint32_t* cnt, const uint32_t* mis, cudaStream_t st) {
+    if (!n) return 0;
+    k_decimal_fix<<<dim3(64, n), 256, 0, st>>>(d, cnt, mis);
+    LAUNCH_CHECK();
+    return 0;
+}
+int launch_timestamp(const TsDesc* d, uint32_t n, const uint32_t* cnt, uint32_t* err, cudaStream_t st) {
+    if (!n) return 0;
+    k_timestamp<<<dim3(64, n), 256, 0, st>>>(d, cnt, err);
+    LAUNCH_CHECK();
+    return 0;
+}
+int launch_strings(StrCol* cols, uint32_t ncols, uint32_t ntiles, uint32_t* err, JobState* state, uint64_t heap_base,
+                   uint64_t heap_cap, uint64_t* ptr_table, cudaStream_t st) {
+    if (!ncols) return 0;
+    k_dict_prepare<<<blocks_for_warps(ncols, 4), 128, 0, st>>>(cols, ncols, err);
+    LAUNCH_CHECK();
+    k_str_tile_sum<<<blocks_for_warps(ntiles, 4), 128, 0, st>>>(cols, ncols, ntiles, err);
+    LAUNCH_CHECK();
+    k_str_tile_scan<<<blocks_for_warps(ncols, 4), 128, 0, st>>>(cols, ncols, err, state, heap_base, heap_cap, ptr_table);
+    LAUNCH_CHECK();
+    k_str_offsets<<<blocks_for_warps(ntiles, 4), 128, 0, st>>>(cols, ncols, ntiles, err);
+    LAUNCH_CHECK();
+    return 0;
+}
+int launch_repack(const RepackDesc* d, uint32_t ndesc, uint32_t nwork, uint32_t* nulls, cudaStream_t st) {
+    if (!nwork) return 0;
+    k_repack<<<blocks_for_warps(nwork, 4), 128, 0, st>>>(d, ndesc, nwork, nulls);
+    LAUNCH_CHECK();
+    return 0;
+}
+int launch_decompress(const ChunkDesc* c, uint32_t n, uint32_t* err, uint32_t* out_lens, cudaStream_t st) {
+    if (!n) return 0;
+    k_decompress<<<blocks_for_warps(n, 4), 128, 0, st>>>(c, n, err, out_lens);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace orcb

@@ -1,0 +1,332 @@
+#include "meta.h"
+
+#include <cstring>
+
+#include "pb.h"
+
+namespace orcb {
+
+// ---------------------------------------------------------------------------------------------
+// Host block decoders for metadata sections (file footer, stripe footers, ROW_INDEX streams).
+// Data streams never pass through these: they are decompressed by the CUDA kernels.
+// ---------------------------------------------------------------------------------------------
+static void host_snappy_block(const uint8_t* s, size_t n, std::vector<uint8_t>& out) {
+    size_t ip = 0;
+    uint64_t want = 0;
+    for (int shift = 0;; shift += 7) {
+        if (ip >= n || shift > 35) fail(ORCB_BUILD_SNAPPY_DECODER, "bad snappy preamble");
+        uint8_t b = s[ip++];
+        want |= (uint64_t)(b & 0x7f) << shift;
+        if (b < 0x80) break;
+    }
+    size_t base = out.size();
+    out.reserve(base + want);
+    while (ip < n) {
+        const uint8_t tag = s[ip++];
+        size_t len, dist = 0;
+        switch (tag & 3) {
+            case 0: {
+                len = tag >> 2;
+                if (len >= 60) {
+                    size_t extra = len - 59;
+                    if (ip + extra > n) fail(ORCB_BUILD_SNAPPY_DECODER, "truncated literal length");
+                    len = 0;
+                    for (size_t k = 0; k < extra; k++) len |= (size_t)s[ip + k] << (8 * k);
+                    ip += extra;
+                }
+                len++;
+                if (ip + len > n) fail(ORCB_BUILD_SNAPPY_DECODER, "truncated literal");
+                out.insert(out.end(), s + ip, s + ip + len);
+                ip += len;
+                continue;
+            }
+            case 1:
+                if (ip + 1 > n) fail(ORCB_BUILD_SNAPPY_DECODER, "truncated copy");
+                len = 4 + ((tag >> 2) & 7);
+                dist = ((size_t)(tag >> 5) << 8) | s[ip];
+                ip += 1;
+                break;
+            case 2:
+                if (ip + 2 > n) fail(ORCB_BUILD_SNAPPY_DECODER, "truncated copy");
+                len = 1 + (tag >> 2);
+                dist = s[ip] | ((size_t)s[ip + 1] << 8);
+                ip += 2;
+                break;
+            default:
+                if (ip + 4 > n) fail(ORCB_BUILD_SNAPPY_DECODER, "truncated copy");
+                len = 1 + (tag >> 2);
+                dist = s[ip] | ((size_t)s[ip + 1] << 8) | ((size_t)s[ip + 2] << 16) | ((size_t)s[ip + 3] << 24);
+                ip += 4;
+                break;
+        }
+        size_t produced = out.size() - base;
+        if (dist == 0 || dist > produced) fail(ORCB_BUILD_SNAPPY_DECODER, "copy offset out of range");
+        for (size_t k = 0; k < len; k++) out.push_back(out[out.size() - dist]);
+    }
+    if (out.size() - base != want) fail(ORCB_BUILD_SNAPPY_DECODER, "snappy length mismatch");
+}
+
+static void host_lz4_block(const uint8_t* s, size_t n, size_t max_out, std::vector<uint8_t>& out) {
+    size_t ip = 0;
+    const size_t base = out.size();
+    auto ext = [&](size_t v) {
+        if (v == 15) {
+            uint8_t b;
+            do {
+                if (ip >= n) fail(ORCB_BUILD_LZ4_DECODER, "truncated length");
+                b = s[ip++];
+                v += b;
+            } while (b == 255);
+        }
+        return v;
+    };
+    while (ip < n) {
+        const uint8_t token = s[ip++];
+        size_t lit = ext(token >> 4);
+        if (ip + lit > n || out.size() - base + lit > max_out) fail(ORCB_BUILD_LZ4_DECODER, "literal overrun");
+        out.insert(out.end(), s + ip, s + ip + lit);
+        ip += lit;
+        if (ip >= n) break;
+        if (ip + 2 > n) fail(ORCB_BUILD_LZ4_DECODER, "truncated offset");
+        size_t dist = s[ip] | ((size_t)s[ip + 1] << 8);
+        ip += 2;
+        size_t mlen = ext(token & 15) + 4;
+        if (dist == 0 || dist > out.size() - base || out.size() - base + mlen > max_out)
+            fail(ORCB_BUILD_LZ4_DECODER, "match out of range");
+        for (size_t k = 0; k < mlen; k++) out.push_back(out[out.size() - dist]);
+    }
+}
+
+std::vector<uint8_t> host_decompress_section(int compression, uint64_t block_size, const uint8_t* in, size_t len) {
+    std::vector<uint8_t> out;
+    if (compression == C_NONE) {
+        out.assign(in, in + len);
+        return out;
+    }
+    size_t p = 0;
+    while (p < len) {
+        if (p + 3 > len) fail(ORCB_OUT_OF_SPEC, "truncated compression chunk header");
+        uint32_t h = in[p] | ((uint32_t)in[p + 1] << 8) | ((uint32_t)in[p + 2] << 16);
+        p += 3;
+        uint32_t clen = h >> 1;
+        if (p + clen > len) fail(ORCB_OUT_OF_SPEC, "compression chunk exceeds section");
+        if (h & 1) {
+            out.insert(out.end(), in + p, in + p + clen);
+        } else if (compression == C_SNAPPY) {
+            host_snappy_block(in + p, clen, out);
+        } else if (compression == C_LZ4) {
+            host_lz4_block(in + p, clen, block_size, out);
+        } else {
+            fail(ORCB_UNSUPPORTED_DEVICE_CODEC, "Zlib/Zstd/LZO are not supported on the device path");
+        }
+        p += clen;
+    }
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// File tail (src/reader/metadata.rs:180-263)
+// ---------------------------------------------------------------------------------------------
+static OrcType parse_type(const uint8_t* p, size_t n) {
+    OrcType t;
+    PbCursor c(p, n);
+    PbField f;
+    while (c.next(f)) {
+        switch (f.number) {
+            case 1: t.kind = (int)f.value; break;
+            case 2: {
+                std::vector<uint64_t> v;
+                PbCursor::packed_u64(f, v);
+                for (auto x : v) t.subtypes.push_back((uint32_t)x);
+                break;
+            }
+            case 3: t.field_names.emplace_back((const char*)f.data, f.len); break;
+            case 4: t.max_length = (uint32_t)f.value; break;
+            case 5: t.precision = (uint32_t)f.value; break;
+            case 6: t.scale = (uint32_t)f.value; break;
+            default: break;
+        }
+    }
+    return t;
+}
+
+void parse_file_tail(FileMeta& fm) {
+    const uint8_t* d = fm.data;
+    const size_t n = fm.len;
+    if (n == 0) fail(ORCB_EMPTY_FILE, "Empty file");
+    size_t ps_len = d[n - 1];
+    if (n - 1 < ps_len) fail(ORCB_OUT_OF_SPEC, "File too small for given postscript length");
+    bool have_footer = false, have_meta = false;
+    uint64_t footer_len = 0, meta_len = 0;
+    {
+        PbCursor c(d + n - 1 - ps_len, ps_len);
+        PbField f;
+        while (c.next(f)) {
+            switch (f.number) {
+                case 1: footer_len = f.value; have_footer = true; break;
+                case 2: fm.compression = (int)f.value; break;
+                case 3: fm.block_size = f.value; break;
+                case 5: meta_len = f.value; have_meta = true; break;
+                default: break;
+            }
+        }
+    }
+    if (!have_footer) fail(ORCB_OUT_OF_SPEC, "Footer length is empty");
+    if (!have_meta) fail(ORCB_OUT_OF_SPEC, "Metadata length is empty");
+    if (fm.compression == C_ZLIB || fm.compression == C_ZSTD || fm.compression == C_LZO)
+        fail(ORCB_UNSUPPORTED_DEVICE_CODEC,
+             "file is compressed with Zlib/Zstd/LZO: not decodable on the device path (no CPU fallback)");
+    if (fm.compression < 0 || fm.compression > C_ZSTD) fail(ORCB_DECODE_PROTO, "unknown compression kind");
+    if (footer_len + meta_len + ps_len + 1 > n) fail(ORCB_OUT_OF_SPEC, "footer exceeds file");
+    size_t fend = n - 1 - ps_len;
+    std::vector<uint8_t> footer = host_decompress_section(fm.compression, fm.block_size, d + fend - footer_len, footer_len);
+    PbCursor c(footer.data(), footer.size());
+    PbField f;
+    while (c.next(f)) {
+        switch (f.number) {
+            case 3: {
+                StripeInfo s;
+                PbCursor sc(f.data, f.len);
+                PbField g;
+                while (sc.next(g)) {
+                    if (g.number == 1) s.offset = g.value;
+                    else if (g.number == 2) s.index_length = g.value;
+                    else if (g.number == 3) s.data_length = g.value;
+                    else if (g.number == 4) s.footer_length = g.value;
+                    else if (g.number == 5) s.rows = g.value;
+                }
+                fm.stripes.push_back(s);
+                break;
+            }
+            case 4: fm.types.push_back(parse_type(f.data, f.len)); break;
+            case 5: {
+                std::string k, v;
+                PbCursor mc(f.data, f.len);
+                PbField g;
+                while (mc.next(g)) {
+                    if (g.number == 1) k.assign((const char*)g.data, g.len);
+                    else if (g.number == 2) v.assign((const char*)g.data, g.len);
+                }
+                fm.user_metadata.emplace_back(k, v);
+                break;
+            }
+            case 6: fm.num_rows = f.value; break;
+            case 8: fm.row_index_stride = (int64_t)f.value; break;
+            default: break;
+        }
+    }
+    if (fm.types.empty()) fail(ORCB_NO_TYPES, "No types found");
+    const OrcType& root = fm.types[0];
+    if (root.kind != T_STRUCT) fail(ORCB_UNEXPECTED, "non-struct root type is not supported");
+    if (root.subtypes.size() != root.field_names.size())
+        fail(ORCB_UNEXPECTED, "Struct type for column index 0 must have matching lengths for subtypes and field names lists");
+    for (size_t i = 0; i < root.subtypes.size(); i++) {
+        if (root.subtypes[i] >= fm.types.size()) fail(ORCB_UNEXPECTED, "Column index out of bounds");
+        fm.root_columns.emplace_back(root.field_names[i], root.subtypes[i]);
+    }
+    for (auto& s : fm.stripes) {
+        if (s.offset + s.index_length + s.data_length + s.footer_length > n)
+            fail(ORCB_IO_ERROR, "stripe exceeds file length");
+    }
+}
+
+// src/stripe.rs:128-182 (footer decode + running stream offsets)
+StripeFooter FileMeta::read_stripe_footer(uint32_t stripe) const {
+    const StripeInfo& si = stripes.at(stripe);
+    uint64_t off = si.offset + si.index_length + si.data_length;
+    std::vector<uint8_t> raw = host_decompress_section(compression, block_size, data + off, si.footer_length);
+    StripeFooter sf;
+    PbCursor c(raw.data(), raw.size());
+    PbField f;
+    uint64_t pos = si.offset;
+    while (c.next(f)) {
+        if (f.number == 1) {
+            StreamInfo s;
+            PbCursor sc(f.data, f.len);
+            PbField g;
+            while (sc.next(g)) {
+                if (g.number == 1) s.kind = (int)g.value;
+                else if (g.number == 2) s.column = (uint32_t)g.value;
+                else if (g.number == 3) s.length = g.value;
+            }
+            s.offset = pos;
+            pos += s.length;
+            if (pos > len) fail(ORCB_IO_ERROR, "stream exceeds file length");
+            sf.streams.push_back(s);
+        } else if (f.number == 2) {
+            ColumnEncoding e;
+            PbCursor ec(f.data, f.len);
+            PbField g;
+            while (ec.next(g)) {
+                if (g.number == 1) e.kind = (int)g.value;
+                else if (g.number == 2) e.dict_size = (uint32_t)g.value;
+            }
+            sf.encodings.push_back(e);
+        } else if (f.number == 3) {
+            sf.has_tz = true;
+            sf.tz.assign((const char*)f.data, f.len);
+        }
+    }
+    return sf;
+}
+
+// src/row_index.rs:204-289 — only the positions (the reference parses but never uses them, :35-51)
+std::vector<std::vector<uint64_t>> FileMeta::read_row_index(const StripeInfo& si, const StripeFooter& sf,
+                                                            uint32_t column) const {
+    (void)si;
+    std::vector<std::vector<uint64_t>> out;
+    const StreamInfo* st = sf.find(column, S_ROW_INDEX);
+    if (!st || st->length == 0) return out;
+    std::vector<uint8_t> raw = host_decompress_section(compression, block_size, data + st->offset, st->length);
+    PbCursor c(raw.data(), raw.size());
+    PbField f;
+    while (c.next(f)) {
+        if (f.number != 1) continue;
+        std::vector<uint64_t> pos;
+        PbCursor ec(f.data, f.len);
+        PbField g;
+        while (ec.next(g)) {
+            if (g.number == 1) PbCursor::packed_u64(g, pos);
+        }
+        out.push_back(std::move(pos));
+    }
+    return out;
+}
+
+// src/compression.rs:244-275 — header walk only
+std::vector<ChunkInfo> FileMeta::chunk_table(uint64_t stream_off, uint64_t stream_len) const {
+    std::vector<ChunkInfo> out;
+    const uint8_t* s = data + stream_off;
+    uint64_t p = 0;
+    while (p < stream_len) {
+        if (p + 3 > stream_len) fail(ORCB_OUT_OF_SPEC, "truncated compression chunk header");
+        uint32_t h = s[p] | ((uint32_t)s[p + 1] << 8) | ((uint32_t)s[p + 2] << 16);
+        ChunkInfo ci;
+        ci.hdr_off = (uint32_t)p;
+        ci.src_off = p + 3;
+        ci.src_len = h >> 1;
+        ci.original = h & 1;
+        if (ci.src_off + ci.src_len > stream_len) fail(ORCB_OUT_OF_SPEC, "compression chunk exceeds stream");
+        ci.dst_len = -1;
+        if (ci.original) {
+            ci.dst_len = ci.src_len;
+        } else if (compression == C_SNAPPY) {
+            // uncompressed length preamble (snap::raw::decompress_len, src/compression.rs:163-165)
+            uint64_t v = 0;
+            uint64_t q = ci.src_off;
+            bool ok = false;
+            for (int shift = 0; shift <= 35 && q < ci.src_off + ci.src_len; shift += 7) {
+                uint8_t b = s[q++];
+                v |= (uint64_t)(b & 0x7f) << shift;
+                if (b < 0x80) { ok = true; break; }
+            }
+            if (!ok) fail(ORCB_BUILD_SNAPPY_DECODER, "bad snappy preamble");
+            ci.dst_len = (int64_t)v;
+        }
+        out.push_back(ci);
+        p = ci.src_off + ci.src_len;
+    }
+    return out;
+}
+
+}  // namespace orcb

@@ -1,0 +1,228 @@
+"""GPU parity: CUDA decode through the C ABI vs the CPU oracle, byte-identical Arrow buffers per batch.
+Covers the reference's fixture files the device path accepts (NONE / Snappy / LZ4, flat schemas), the
+stream-level known-answer vectors of the reference's unit tests, and seeded synthetic files of the
+BASELINE configs at sizes the oracle finishes in seconds."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import kat_vectors as kv
+from conftest import GOLDEN
+from parity_util import assert_batches_identical
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ob():
+    import orc_rust_b200 as m
+    assert m.device_available(), "no CUDA device: the product path has no CPU fallback"
+    return m
+
+
+def _device_ok_files():
+    from oracle import orc_oracle as oo
+    out = []
+    for f in sorted(glob.glob(os.path.join(GOLDEN, "ref_*", "*.orc"))):
+        try:
+            of = oo.OracleFile(open(f, "rb").read())
+        except oo.OracleError:
+            continue
+        if of.is_flat() and of.compression in (0, 2, 4) and os.path.basename(f) != "orc_split_elim.orc":
+            out.append(f)
+    return out
+
+
+FILES = _device_ok_files()
+
+
+@pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f) for f in FILES])
+@pytest.mark.parametrize("use_index", [True, False], ids=["index", "noindex"])
+def test_fixture_files(ob, path, use_index):
+    from oracle import orc_oracle as oo
+    data = open(path, "rb").read()
+    of = oo.OracleFile(data)
+    try:
+        exp = of.read()
+    except oo.OracleError as e:
+        with pytest.raises(ob.OrcError):
+            ob.ArrowReaderBuilder.try_new(data).with_row_index(use_index).build().read_all()
+        return
+    got = list(ob.ArrowReaderBuilder.try_new(data).with_row_index(use_index).build())
+    assert_batches_identical(got, exp, os.path.basename(path))
+
+
+@pytest.mark.parametrize("batch_size", [1000, 8192, 100000])
+def test_batch_sizes(ob, batch_size):
+    from oracle import orc_oracle as oo
+    path = os.path.join(GOLDEN, "ref_integration", "nulls-at-end-snappy.orc")
+    data = open(path, "rb").read()
+    exp = oo.OracleFile(data).read(batch_size=batch_size)
+    got = list(ob.ArrowReaderBuilder.try_new(data).with_batch_size(batch_size).build())
+    assert_batches_identical(got, exp, f"bs={batch_size}")
+
+
+# ---- stream-level KATs through the C ABI -------------------------------------------------------------
+@pytest.mark.parametrize("name,data,signed,expected", kv.RLE_V2, ids=[k[0] for k in kv.RLE_V2])
+def test_rle_v2_kat(ob, name, data, signed, expected):
+    out = ob.decode_int_rle(bytes(data), len(expected), version=2, signed=signed, nbytes=8)
+    assert out.tolist() == expected
+
+
+@pytest.mark.parametrize("name,data,signed,expected", kv.RLE_V1, ids=[k[0] for k in kv.RLE_V1])
+def test_rle_v1_kat(ob, name, data, signed, expected):
+    out = ob.decode_int_rle(bytes(data), len(expected), version=1, signed=signed, nbytes=8)
+    assert out.tolist() == expected
+
+
+@pytest.mark.parametrize("name,data,expected", kv.BYTE_RLE, ids=[k[0] for k in kv.BYTE_RLE])
+def test_byte_rle_kat(ob, name, data, expected):
+    assert ob.decode_byte_rle(bytes(data), len(expected)).tolist() == expected
+
+
+@pytest.mark.parametrize("name,data,expected", kv.BOOL_RLE, ids=[k[0] for k in kv.BOOL_RLE])
+def test_bool_rle_kat(ob, name, data, expected):
+    assert ob.decode_bool_rle(bytes(data), len(expected)).tolist() == expected
+
+
+def test_varint_kat(ob):
+    for data, expected in kv.VARINT_U64:
+        assert ob.decode_int_rle(bytes([0xFF] + data), 1, version=1, signed=False).tolist() == [expected]
+    with pytest.raises(ob.OrcError) as e:
+        ob.decode_int_rle(bytes([0xFF] + kv.VARINT_TOO_LARGE), 1, version=1, signed=False)
+    assert e.value.variant == "VarintTooLarge"
+    with pytest.raises(ob.OrcError) as e:
+        ob.decode_int_rle(bytes([0xFF] + kv.VARINT_TRUNCATED), 1, version=1, signed=False)
+    assert e.value.variant == "IoError"
+
+
+def test_decimal_varint_kat(ob):
+    for data, expected in kv.DECIMAL_VARINT:
+        out = ob.decode_varint128(bytes(data), len(expected))
+        got = [int(lo) | (int(hi) << 64) for lo, hi in out.tolist()]
+        got = [g - (1 << 128) if g >> 127 else g for g in got]
+        assert got == expected
+    with pytest.raises(ob.OrcError):
+        ob.decode_varint128(bytes([0x00, 0x02, 0x01]), 4)
+
+
+# ---- seeded random streams: CUDA vs oracle ------------------------------------------------------------
+def _rand_rle2_stream(rng, n_runs, nbytes, signed):
+    """Random *encoded* RLEv2 runs (valid headers, random payload bits)."""
+    out = bytearray()
+    widths = [w for w in list(range(1, 25)) + [26, 28, 30, 32, 40, 48, 56, 64] if w <= nbytes * 8]
+    codes = {w: (w - 1 if w <= 24 else {26: 24, 28: 25, 30: 26, 32: 27, 40: 28, 48: 29, 56: 30, 64: 31}[w]) for w in widths}
+    for _ in range(n_runs):
+        kind = rng.integers(0, 4)
+        if kind == 0:
+            bw = int(rng.integers(1, nbytes + 1))
+            cnt = int(rng.integers(3, 11))
+            out.append(((bw - 1) << 3) | (cnt - 3))
+            out += bytes(rng.integers(0, 256, bw, dtype=np.uint8))
+        elif kind == 1:
+            w = int(rng.choice(widths))
+            ln = int(rng.integers(1, 513))
+            out.append(0x40 | (codes[w] << 1) | ((ln - 1) >> 8))
+            out.append((ln - 1) & 255)
+            out += bytes(rng.integers(0, 256, (ln * w + 7) // 8, dtype=np.uint8))
+        elif kind == 3:
+            w = int(rng.choice([0] + [x for x in widths if x <= 16]))
+            ln = int(rng.integers(2, 513))
+            code = 0 if w == 0 else codes[w]
+            out.append(0xC0 | (code << 1) | ((ln - 1) >> 8))
+            out.append((ln - 1) & 255)
+            base = int(rng.integers(0, 1 << 20))
+            d0 = int(rng.integers(-50, 50))
+            for v in (base << 1 if signed else base, (d0 << 1) ^ (d0 >> 63)):
+                v &= (1 << 64) - 1
+                while True:
+                    b = v & 0x7F
+                    v >>= 7
+                    if v:
+                        out.append(b | 0x80)
+                    else:
+                        out.append(b)
+                        break
+            if w:
+                out += bytes(rng.integers(0, 256, ((ln - 2) * w + 7) // 8, dtype=np.uint8))
+        else:
+            w = int(rng.choice([x for x in widths if x <= 32]))
+            ln = int(rng.integers(1, 513))
+            bw = int(rng.integers(1, min(nbytes, 7) + 1))
+            pw = int(rng.choice([x for x in widths if x <= 16]))
+            pgw = int(rng.integers(1, 9))
+            pll = int(rng.integers(1, 32))
+            out.append(0x80 | (codes[w] << 1) | ((ln - 1) >> 8))
+            out.append((ln - 1) & 255)
+            out.append(((bw - 1) << 5) | codes[pw])
+            out.append(((pgw - 1) << 5) | pll)
+            basebytes = bytearray(rng.integers(0, 256, bw, dtype=np.uint8))
+            basebytes[0] &= 0x3F  # keep bases small so unpatched adds rarely overflow
+            out += basebytes
+            out += bytes(rng.integers(0, 256, (ln * w + 7) // 8, dtype=np.uint8))
+            tot = pw + pgw
+            cfb = tot if tot <= 24 else (26 if tot <= 26 else 28 if tot <= 28 else 30 if tot <= 30 else 32 if tot <= 32 else (tot + 7) // 8 * 8)
+            out += bytes(rng.integers(0, 256, (pll * cfb + 7) // 8, dtype=np.uint8))
+    return bytes(out)
+
+
+@pytest.mark.parametrize("nbytes", [2, 4, 8])
+@pytest.mark.parametrize("signed", [False, True])
+def test_rle_v2_random_streams_vs_oracle(ob, nbytes, signed):
+    from oracle import orc_oracle as oo
+    rng = np.random.default_rng(1234 + nbytes + int(signed))
+    agree_ok = agree_err = 0
+    for it in range(60):
+        data = _rand_rle2_stream(rng, int(rng.integers(1, 12)), nbytes, signed)
+        # count how many values the stream holds by decoding progressively with the oracle
+        n = 0
+        err = None
+        for n_try in (1, 5, 50, 500, 3000):
+            try:
+                oo.rle_v2(data, n_try, signed, nbytes)
+                n = n_try
+            except oo.OracleError as e:
+                err = e
+                break
+        n_req = n if err is None else n_try
+        try:
+            exp = oo.rle_v2(data, n_req, signed, nbytes)
+            exp_err = None
+        except oo.OracleError as e:
+            exp, exp_err = None, e
+        try:
+            got = ob.decode_int_rle(data, n_req, version=2, signed=signed, nbytes=nbytes)
+            got_err = None
+        except ob.OrcError as e:
+            got, got_err = None, e
+        assert (exp_err is None) == (got_err is None), f"iter {it}: oracle {exp_err} vs cuda {got_err} ({data.hex()})"
+        if exp_err is None:
+            assert np.array_equal(exp, got), f"iter {it}: values differ ({data.hex()})"
+            agree_ok += 1
+        else:
+            agree_err += 1
+    assert agree_ok > 5
+
+
+def test_synthetic_configs(ob, tmp_path):
+    """Seeded synthetic files of the BASELINE configs (reduced sizes), all codecs the writer offers."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tools"))
+    import gen_orc
+    from oracle import orc_oracle as oo
+    cases = [
+        ("config1", gen_orc.config1_table(100_000, 0), dict(stripe_size=1 << 30)),
+        ("lineitem", gen_orc.lineitem_table(30_000, 0), dict()),
+        ("nullheavy", gen_orc.nullheavy_table(60_000, 1), dict()),
+    ]
+    for name, table, kw in cases:
+        for comp in ("uncompressed", "snappy", "lz4"):
+            p = str(tmp_path / f"{name}_{comp}.orc")
+            gen_orc.write(table, p, compression=comp, block_size=64 << 10, **kw)
+            data = open(p, "rb").read()
+            exp = oo.OracleFile(data).read()
+            for use_index in (True, False):
+                got = list(ob.ArrowReaderBuilder.try_new(data).with_row_index(use_index).build())
+                assert_batches_identical(got, exp, f"{name}/{comp}/index={use_index}")
