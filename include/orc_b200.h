@@ -171,6 +171,18 @@ typedef struct OrcbJobStats {
     uint64_t d2h_meta_bytes;    /* per-batch metadata + error words read back in finish() */
 } OrcbJobStats;
 int orcb_job_stats(const OrcbJob* j, OrcbJobStats* out);
+/* Re-copies the compressed stripe bytes H2D into the already allocated arenas (end-to-end timing loops). */
+int orcb_job_restage(OrcbJob* j);
+/* Per-kernel device time of the last launch() (CUDA events recorded on the job's stream around every
+ * kernel) and the algorithmic bytes each kernel has to move: stream bytes it consumes + buffer bytes it
+ * produces.  Valid after finish(). */
+typedef struct OrcbKernelStat {
+    char name[32];
+    double ms;
+    uint64_t alg_bytes;
+    uint64_t work_items; /* warps / CTAs launched */
+} OrcbKernelStat;
+int orcb_job_kernel_stats(const OrcbJob* j, OrcbKernelStat* out, uint32_t cap, uint32_t* n);
 uint64_t orcb_job_num_batches(const OrcbJob* j);
 /* Export batch `i` (stripe-major order, reference batch boundaries).  Host copy happens lazily, per job. */
 int orcb_job_export_batch(OrcbJob* j, uint64_t i, struct ArrowArray* out);

@@ -64,6 +64,11 @@ class JobStats(ctypes.Structure):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
+class KernelStat(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char * 32), ("ms", ctypes.c_double), ("alg_bytes", ctypes.c_uint64),
+                ("work_items", ctypes.c_uint64)]
+
+
 class _ArrowArray(ctypes.Structure):
     pass
 
@@ -101,7 +106,7 @@ EXPORTED_SYMBOLS = [
     "orcb_file_num_root_columns", "orcb_file_root_column_name", "orcb_file_stripe_info", "orcb_schema",
     "orcb_reader_new", "orcb_reader_free", "orcb_reader_total_row_count", "orcb_reader_next",
     "orcb_reader_next_device", "orcb_job_new", "orcb_job_free", "orcb_job_plan", "orcb_job_stage",
-    "orcb_job_launch", "orcb_job_finish", "orcb_job_stats", "orcb_job_num_batches", "orcb_job_export_batch",
+    "orcb_job_launch", "orcb_job_finish", "orcb_job_stats", "orcb_job_restage", "orcb_job_kernel_stats", "orcb_job_num_batches", "orcb_job_export_batch",
     "orcb_job_export_batch_device", "orcb_decode_int_rle", "orcb_decode_byte_rle", "orcb_decode_bool_rle",
     "orcb_decode_varint128", "orcb_decompress_stream", "orcb_last_error", "orcb_build_info",
     "orcb_device_available",
@@ -137,7 +142,9 @@ def lib() -> ctypes.CDLL:
         L.orcb_reader_next_device.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]
         L.orcb_job_new.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_uint32, ctypes.POINTER(_ReadOptions),
                                    ctypes.POINTER(ctypes.c_void_p)]
-        for name in ("orcb_job_plan", "orcb_job_stage", "orcb_job_launch", "orcb_job_finish"):
+        L.orcb_job_kernel_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(KernelStat), ctypes.c_uint32,
+                                            ctypes.POINTER(ctypes.c_uint32)]
+        for name in ("orcb_job_plan", "orcb_job_stage", "orcb_job_launch", "orcb_job_finish", "orcb_job_restage"):
             getattr(L, name).argtypes = [ctypes.c_void_p]
         L.orcb_job_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(JobStats)]
         L.orcb_job_export_batch.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p]
@@ -386,6 +393,17 @@ class DecodeJob:
     def finish(self):
         _check(lib().orcb_job_finish(self._h))
         return self
+
+    def restage(self):
+        _check(lib().orcb_job_restage(self._h))
+        return self
+
+    def kernel_stats(self):
+        arr = (KernelStat * 32)()
+        n = ctypes.c_uint32(0)
+        _check(lib().orcb_job_kernel_stats(self._h, arr, 32, ctypes.byref(n)))
+        return [dict(name=arr[i].name.decode(), ms=arr[i].ms, alg_bytes=int(arr[i].alg_bytes),
+                     work_items=int(arr[i].work_items)) for i in range(n.value)]
 
     def stats(self) -> dict:
         s = JobStats()

@@ -265,6 +265,10 @@ int orcb_job_stage(OrcbJob* j) { return guarded([&] { j->job->stage(); }); }
 int orcb_job_launch(OrcbJob* j) { return guarded([&] { j->job->launch(); }); }
 int orcb_job_finish(OrcbJob* j) { return guarded([&] { j->job->finish(); }); }
 int orcb_job_stats(const OrcbJob* j, OrcbJobStats* out) { return guarded([&] { j->job->stats(out); }); }
+int orcb_job_restage(OrcbJob* j) { return guarded([&] { j->job->restage(); }); }
+int orcb_job_kernel_stats(const OrcbJob* j, OrcbKernelStat* out, uint32_t cap, uint32_t* n) {
+    return guarded([&] { *n = j->job->kernel_stats(out, cap); });
+}
 uint64_t orcb_job_num_batches(const OrcbJob* j) { return j->job->num_batches(); }
 int orcb_job_export_batch(OrcbJob* j, uint64_t i, struct ArrowArray* out) {
     return guarded([&] { j->job->export_batch(i, out); });

@@ -172,7 +172,44 @@ Job::Job(std::vector<StripeTask> tasks, const ReadOptions& opt) : tasks_(std::mo
     if (!tasks_.empty()) cols_ = project_columns(*tasks_[0].file, opt_);
 }
 
+Job::KStat& Job::kstat(const char* name) {
+    for (auto& k : kstats_)
+        if (k.name == name) return k;
+    kstats_.emplace_back();
+    KStat& k = kstats_.back();
+    k.name = name;
+    cudaEventCreate(&k.e0);
+    cudaEventCreate(&k.e1);
+    return k;
+}
+
+uint32_t Job::kernel_stats(OrcbKernelStat* out, uint32_t cap) const {
+    uint32_t n = 0;
+    for (auto& k : kstats_) {
+        if (!k.ran || n >= cap) continue;
+        memset(&out[n], 0, sizeof(out[n]));
+        strncpy(out[n].name, k.name.c_str(), sizeof(out[n].name) - 1);
+        out[n].ms = k.ms;
+        out[n].alg_bytes = k.alg_bytes;
+        out[n].work_items = k.work;
+        n++;
+    }
+    return n;
+}
+
+void Job::restage() {
+    if (!staged_) { stage(); return; }
+    CUDA_OK(cudaSetDevice(opt_.device));
+    CUDA_OK(cudaMemcpyAsync(d_desc_, desc_blob_.data(), desc_blob_.size(), cudaMemcpyHostToDevice, stream_));
+    for (auto& sc : stage_copies_)
+        CUDA_OK(cudaMemcpyAsync(base_[AR_IN] + sc.dst_off, sc.src, sc.bytes, cudaMemcpyHostToDevice, stream_));
+}
+
 Job::~Job() {
+    for (auto& k : kstats_) {
+        if (k.e0) cudaEventDestroy(k.e0);
+        if (k.e1) cudaEventDestroy(k.e1);
+    }
     if (h_meta_) cudaFreeHost(h_meta_);
     if (done_) cudaEventDestroy(done_);
     if (own_stream_ && stream_) cudaStreamDestroy(stream_);
@@ -383,6 +420,7 @@ void Job::plan_stripe(uint32_t task_idx) {
                     d.expect_len = i + 1 < r.chunks.size() ? (int32_t)fm.block_size : -1;
                 }
                 chunks_.push_back(d);
+                ab_decomp_ += c.src_len + (uint64_t)d.dst_cap;
             }
             return r;
         };
@@ -551,6 +589,8 @@ void Job::plan_stripe(uint32_t task_idx) {
             repack_work_ += n_batches;
             repacks_.push_back(rp);
             n_segments_ += n_groups;
+            ab_present_ += s_present.len + (uint64_t)n_rows / 8;
+            ab_repack_ += (uint64_t)n_rows / 4;
         }
         const int32_t total_idx = has_present ? (int32_t)(cnt_base + n_groups) : -1;
 
@@ -584,6 +624,8 @@ void Job::plan_stripe(uint32_t task_idx) {
                 int_segs_.push_back(sg);
             }
             n_segments_ += ng;
+            static const uint32_t ow[6] = {2, 4, 8, 4, 4, 1};
+            ab_int_ += sr.len + (uint64_t)n_rows * ow[okind];
         };
         // helper: dense -> rows
         auto add_spaced = [&](uint64_t src, uint64_t dst, uint32_t width, bool late) {
@@ -598,6 +640,7 @@ void Job::plan_stripe(uint32_t task_idx) {
                 d.width = width;
                 (late ? spaced_late_ : spaced_).push_back(d);
             }
+            ab_spaced_ += (uint64_t)n_rows * (2 * std::max(width, 1u)) + n_rows / 8;
         };
         auto add_copy = [&](uint64_t src, uint32_t src_len, uint64_t dst, uint64_t nbytes, int32_t cnt_idx, uint32_t width,
                             uint64_t max_bytes) {
@@ -611,6 +654,7 @@ void Job::plan_stripe(uint32_t task_idx) {
             d.colstripe = cs;
             const uint32_t di = (uint32_t)copies_.size();
             copies_.push_back(d);
+            ab_copy_ += 2 * max_bytes;
             const uint32_t nt = (uint32_t)((max_bytes + COPY_TILE_BYTES - 1) / COPY_TILE_BYTES);
             for (uint32_t t = 0; t < std::max(nt, 1u); t++) copy_tiles_.push_back(make_uint2(di, t));
         };
@@ -790,6 +834,8 @@ void Job::plan_stripe(uint32_t task_idx) {
                     n_segments_ += 1;
                 }
                 if (has_present) add_spaced(dense_i32, rows_i32, 4, false);
+                // lengths/keys read twice (tile sums, offsets) + offsets written; gathered bytes added in finish()
+                ab_str_ += (uint64_t)n_rows * 12;
                 strcols_.push_back(sc);
                 break;
             }
@@ -820,6 +866,7 @@ void Job::plan_stripe(uint32_t task_idx) {
                     var_segs_.push_back(sg);
                 }
                 n_segments_ += ng;
+                ab_var_ += s_data.len + (uint64_t)n_rows * 16;
                 add_int_segs(s_secondary, scales, true, 4, OUT_SCALE, oc.scale, true);
                 DecFixDesc df{};
                 df.vals = dst;
@@ -856,6 +903,7 @@ void Job::plan_stripe(uint32_t task_idx) {
                 td.colstripe = cs;
                 td.as_i128 = 0;
                 ts_.push_back(td);
+                ab_ts_ += (uint64_t)n_rows * 24;
                 if (has_present) add_spaced(dst, cp.values, 8, true);
                 break;
             }
@@ -978,27 +1026,46 @@ void Job::launch() {
         if (rc) fail(ORCB_CUDA, std::string("launch ") + what + ": " + cudaGetErrorString((cudaError_t)rc));
     };
 #define N(v) ((uint32_t)(v).size())
-    if (N(chunks_)) { chk(launch_decompress((ChunkDesc*)(d_desc_ + o_chunk_), N(chunks_), err, nullptr, st), "decompress"); launches++; }
+    for (auto& k : kstats_) k.ran = false;
+    auto run = [&](const char* name, uint64_t alg_bytes, uint64_t work, int nk, auto&& fn) {
+        KStat& k = kstat(name);
+        k.alg_bytes = alg_bytes;
+        k.work = work;
+        k.ran = true;
+        CUDA_OK(cudaEventRecord(k.e0, st));
+        chk(fn(), name);
+        CUDA_OK(cudaEventRecord(k.e1, st));
+        launches += nk;
+    };
+    if (N(chunks_))
+        run("k_decompress", ab_decomp_, N(chunks_), 1, [&] { return launch_decompress((ChunkDesc*)(d_desc_ + o_chunk_), N(chunks_), err, nullptr, st); });
     if (N(present_byte_segs_)) {
-        chk(launch_byte_rle((Seg*)(d_desc_ + o_pbyte_), N(present_byte_segs_), cnt, dstart, err, st), "present byte rle");
-        chk(launch_bits((BitSeg*)(d_desc_ + o_pbit_), N(present_bit_segs_), cnt, dstart, st), "present bits");
-        chk(launch_seg_scan((ScanDesc*)(d_desc_ + o_scan_), N(scans_), cnt, dstart, st), "seg scan");
-        launches += 3;
+        run("k_byte_rle(present)", ab_present_, N(present_byte_segs_), 1, [&] { return launch_byte_rle((Seg*)(d_desc_ + o_pbyte_), N(present_byte_segs_), cnt, dstart, err, st); });
+        run("k_bits(present)", ab_present_, N(present_bit_segs_), 1, [&] { return launch_bits((BitSeg*)(d_desc_ + o_pbit_), N(present_bit_segs_), cnt, dstart, st); });
+        run("k_seg_scan", 0, N(scans_), 1, [&] { return launch_seg_scan((ScanDesc*)(d_desc_ + o_scan_), N(scans_), cnt, dstart, st); });
     }
-    if (N(data_byte_segs_)) { chk(launch_byte_rle((Seg*)(d_desc_ + o_dbyte_), N(data_byte_segs_), cnt, dstart, err, st), "byte rle"); launches++; }
-    if (N(data_bit_segs_)) { chk(launch_bits((BitSeg*)(d_desc_ + o_dbit_), N(data_bit_segs_), cnt, dstart, st), "bool bits"); launches++; }
-    if (N(int_segs_)) { chk(launch_int_rle((Seg*)(d_desc_ + o_int_), N(int_segs_), cnt, dstart, err, mis, st), "int rle"); launches++; }
-    if (N(var_segs_)) { chk(launch_varint128((Seg*)(d_desc_ + o_var_), N(var_segs_), cnt, dstart, err, st), "varint128"); launches++; }
-    if (N(copy_tiles_)) { chk(launch_copy((CopyDesc*)(d_desc_ + o_copy_), (uint2*)(d_desc_ + o_ctile_), N(copy_tiles_), cnt, err, st), "copy"); launches++; }
-    if (N(decfix_)) { chk(launch_decimal_fix((DecFixDesc*)(d_desc_ + o_dec_), N(decfix_), cnt, mis, st), "decimal fix"); launches++; }
-    if (N(ts_)) { chk(launch_timestamp((TsDesc*)(d_desc_ + o_ts_), N(ts_), cnt, err, st), "timestamp"); launches++; }
-    if (N(spaced_)) { chk(launch_spaced((SpacedDesc*)(d_desc_ + o_sp_), N(spaced_), dstart, st), "spaced"); launches++; }
-    if (N(spaced_late_)) { chk(launch_spaced((SpacedDesc*)(d_desc_ + o_sp2_), N(spaced_late_), dstart, st), "spaced late"); launches++; }
-    if (N(strcols_)) {
-        chk(launch_strings((StrCol*)(d_desc_ + o_str_), N(strcols_), str_tiles_, err, dstate, (uint64_t)(uintptr_t)base_[AR_HEAP], heap_cap, ptrs, st), "strings");
-        launches += 4;
-    }
-    if (repack_work_) { chk(launch_repack((RepackDesc*)(d_desc_ + o_rep_), N(repacks_), repack_work_, nulls, st), "repack"); launches++; }
+    if (N(data_byte_segs_))
+        run("k_byte_rle", ab_byte_, N(data_byte_segs_), 1, [&] { return launch_byte_rle((Seg*)(d_desc_ + o_dbyte_), N(data_byte_segs_), cnt, dstart, err, st); });
+    if (N(data_bit_segs_))
+        run("k_bits", ab_bits_, N(data_bit_segs_), 1, [&] { return launch_bits((BitSeg*)(d_desc_ + o_dbit_), N(data_bit_segs_), cnt, dstart, st); });
+    if (N(int_segs_))
+        run("k_int_rle", ab_int_, N(int_segs_), 1, [&] { return launch_int_rle((Seg*)(d_desc_ + o_int_), N(int_segs_), cnt, dstart, err, mis, st); });
+    if (N(var_segs_))
+        run("k_varint128", ab_var_, N(var_segs_), 1, [&] { return launch_varint128((Seg*)(d_desc_ + o_var_), N(var_segs_), cnt, dstart, err, st); });
+    if (N(copy_tiles_))
+        run("k_copy", ab_copy_, N(copy_tiles_), 1, [&] { return launch_copy((CopyDesc*)(d_desc_ + o_copy_), (uint2*)(d_desc_ + o_ctile_), N(copy_tiles_), cnt, err, st); });
+    if (N(decfix_))
+        run("k_decimal_fix", ab_dec_, N(decfix_), 1, [&] { return launch_decimal_fix((DecFixDesc*)(d_desc_ + o_dec_), N(decfix_), cnt, mis, st); });
+    if (N(ts_))
+        run("k_timestamp", ab_ts_, N(ts_), 1, [&] { return launch_timestamp((TsDesc*)(d_desc_ + o_ts_), N(ts_), cnt, err, st); });
+    if (N(spaced_))
+        run("k_spaced", ab_spaced_, N(spaced_), 1, [&] { return launch_spaced((SpacedDesc*)(d_desc_ + o_sp_), N(spaced_), dstart, st); });
+    if (N(spaced_late_))
+        run("k_spaced(late)", ab_spaced_, N(spaced_late_), 1, [&] { return launch_spaced((SpacedDesc*)(d_desc_ + o_sp2_), N(spaced_late_), dstart, st); });
+    if (N(strcols_))
+        run("k_strings(4 kernels)", ab_str_, str_tiles_, 4, [&] { return launch_strings((StrCol*)(d_desc_ + o_str_), N(strcols_), str_tiles_, err, dstate, (uint64_t)(uintptr_t)base_[AR_HEAP], heap_cap, ptrs, st); });
+    if (repack_work_)
+        run("k_repack", ab_repack_, repack_work_, 1, [&] { return launch_repack((RepackDesc*)(d_desc_ + o_rep_), N(repacks_), repack_work_, nulls, st); });
 #undef N
     n_launches_ = launches;
     launched_ = true;
@@ -1013,6 +1080,12 @@ void Job::finish() {
     CUDA_OK(cudaMemcpyAsync(h_meta_, d_meta_, meta_bytes_, cudaMemcpyDeviceToHost, stream_));
     CUDA_OK(cudaEventRecord(done_, stream_));
     CUDA_OK(cudaStreamSynchronize(stream_));
+    for (auto& k : kstats_) {
+        if (!k.ran) continue;
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, k.e0, k.e1) == cudaSuccess) k.ms = ms;
+        else cudaGetLastError();
+    }
     const uint32_t* err = (const uint32_t*)(h_meta_ + o_err_);
     for (uint32_t i = 0; i < n_colstripes_; i++) {
         if (err[i]) {

@@ -72,7 +72,9 @@ class Job {
     void stage();
     void launch();
     void finish();
+    void restage();
     void stats(OrcbJobStats* out) const;
+    uint32_t kernel_stats(OrcbKernelStat* out, uint32_t cap) const;
     uint64_t num_batches() const { return batch_task_.size(); }
     void export_batch(uint64_t i, ArrowArray* out);
     void export_batch_device(uint64_t i, ArrowDeviceArray* out);
@@ -139,6 +141,19 @@ class Job {
 
     // stats
     uint64_t input_bytes_ = 0, n_rows_ = 0, n_segments_ = 0, n_launches_ = 0, output_bytes_ = 0;
+
+    struct KStat {
+        std::string name;
+        uint64_t alg_bytes = 0, work = 0;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        double ms = 0;
+        bool ran = false;
+    };
+    std::vector<KStat> kstats_;
+    KStat& kstat(const char* name);
+    // algorithmic byte counters accumulated by the planner (per kernel)
+    uint64_t ab_decomp_ = 0, ab_present_ = 0, ab_byte_ = 0, ab_bits_ = 0, ab_int_ = 0, ab_var_ = 0, ab_copy_ = 0,
+             ab_spaced_ = 0, ab_dec_ = 0, ab_ts_ = 0, ab_str_ = 0, ab_repack_ = 0;
 
     cudaStream_t stream_ = nullptr;
     bool own_stream_ = false;

@@ -176,34 +176,34 @@ def test_rle_v2_random_streams_vs_oracle(ob, nbytes, signed):
     agree_ok = agree_err = 0
     for it in range(60):
         data = _rand_rle2_stream(rng, int(rng.integers(1, 12)), nbytes, signed)
-        # count how many values the stream holds by decoding progressively with the oracle
-        n = 0
-        err = None
-        for n_try in (1, 5, 50, 500, 3000):
+        # largest prefix the oracle decodes cleanly, plus one request past the end (error agreement)
+        n_ok = 0
+        for n_try in (3000, 1000, 300, 100, 30, 10, 3, 1):
             try:
                 oo.rle_v2(data, n_try, signed, nbytes)
-                n = n_try
-            except oo.OracleError as e:
-                err = e
+                n_ok = n_try
                 break
-        n_req = n if err is None else n_try
-        try:
-            exp = oo.rle_v2(data, n_req, signed, nbytes)
-            exp_err = None
-        except oo.OracleError as e:
-            exp, exp_err = None, e
-        try:
-            got = ob.decode_int_rle(data, n_req, version=2, signed=signed, nbytes=nbytes)
-            got_err = None
-        except ob.OrcError as e:
-            got, got_err = None, e
-        assert (exp_err is None) == (got_err is None), f"iter {it}: oracle {exp_err} vs cuda {got_err} ({data.hex()})"
-        if exp_err is None:
-            assert np.array_equal(exp, got), f"iter {it}: values differ ({data.hex()})"
-            agree_ok += 1
-        else:
-            agree_err += 1
-    assert agree_ok > 5
+            except oo.OracleError:
+                continue
+        for n_req in ([n_ok] if n_ok else []) + [n_ok + 4000]:
+            try:
+                exp = oo.rle_v2(data, n_req, signed, nbytes)
+                exp_err = None
+            except oo.OracleError as e:
+                exp, exp_err = None, e
+            try:
+                got = ob.decode_int_rle(data, n_req, version=2, signed=signed, nbytes=nbytes)
+                got_err = None
+            except ob.OrcError as e:
+                got, got_err = None, e
+            assert (exp_err is None) == (got_err is None), \
+                f"iter {it} n={n_req}: oracle {exp_err} vs cuda {got_err} ({data.hex()})"
+            if exp_err is None:
+                assert np.array_equal(exp, got), f"iter {it} n={n_req}: values differ ({data.hex()})"
+                agree_ok += 1
+            else:
+                agree_err += 1
+    assert agree_ok > 20 and agree_err > 20
 
 
 def test_synthetic_configs(ob, tmp_path):

@@ -60,26 +60,39 @@ def lineitem_table(n_orders: int, seed: int = 0, sf: float = 10.0) -> pa.Table:
     commitdate = (orderdate + rng.integers(30, 91, n)).astype(np.int32)
     receiptdate = (shipdate + rng.integers(1, 31, n)).astype(np.int32)
     cur = 9298  # 1995-06-17
-    rf = np.where(receiptdate <= cur, np.where(rng.random(n) < 0.5, "R", "A"), "N")
-    ls = np.where(shipdate > cur, "O", "F")
-    instr = np.array(["DELIVER IN PERSON", "COLLECT COD", "NONE", "TAKE BACK RETURN"])[rng.integers(0, 4, n)]
-    mode = np.array(["REG AIR", "AIR", "RAIL", "SHIP", "TRUCK", "MAIL", "FOB"])[rng.integers(0, 7, n)]
-    # comments: 2-6 words from a 40-word vocabulary, built vectorised through a padded word matrix
+    def take(vocab, idx):
+        return pa.array(vocab, pa.utf8()).take(pa.array(idx.astype(np.int32)))
+
+    rf = take(["R", "A", "N"], np.where(receiptdate <= cur, (rng.random(n) < 0.5).astype(np.int32), 2))
+    ls = take(["O", "F"], (shipdate <= cur).astype(np.int32))
+    instr = take(["DELIVER IN PERSON", "COLLECT COD", "NONE", "TAKE BACK RETURN"], rng.integers(0, 4, n))
+    mode = take(["REG AIR", "AIR", "RAIL", "SHIP", "TRUCK", "MAIL", "FOB"], rng.integers(0, 7, n))
+    # comments: 2-6 words from a 40-word vocabulary, assembled directly as Arrow offsets + bytes
     nw = rng.integers(2, 7, n)
-    wid = rng.integers(0, len(_WORDS), (n, 6))
-    words = np.array(_WORDS)
-    parts = words[wid]
-    comment = parts[:, 0]
-    for j in range(1, 6):
-        comment = np.where(nw > j, np.char.add(np.char.add(comment, " "), parts[:, j]), comment)
+    table = (" ".join(_WORDS) + " ").encode()
+    wl = np.array([len(x) for x in _WORDS], dtype=np.int64)
+    wstart = np.concatenate([[0], np.cumsum(wl + 1)[:-1]])
+    total_words = int(nw.sum())
+    wid = rng.integers(0, len(_WORDS), total_words)
+    last = np.zeros(total_words, dtype=bool)
+    last[np.cumsum(nw) - 1] = True
+    plen = wl[wid] + 1 - last  # word + trailing space, no space after the last word of a row
+    pstart = np.cumsum(plen) - plen
+    nchar = int(plen.sum())
+    src = np.repeat(wstart[wid] - pstart, plen) + np.arange(nchar, dtype=np.int64)
+    cdata = np.frombuffer(table, dtype=np.uint8)[src]
+    row_len = np.add.reduceat(plen, np.cumsum(nw) - nw)
+    coffs = np.zeros(n + 1, dtype=np.int32)
+    np.cumsum(row_len, out=coffs[1:])
+    comment = pa.Array.from_buffers(pa.utf8(), n, [None, pa.py_buffer(coffs.tobytes()), pa.py_buffer(cdata.tobytes())])
     return pa.table({
         "l_orderkey": orderkey, "l_partkey": partkey, "l_suppkey": suppkey, "l_linenumber": linenumber,
         "l_quantity": quantity, "l_extendedprice": extendedprice, "l_discount": discount, "l_tax": tax,
-        "l_returnflag": pa.array(rf, pa.utf8()), "l_linestatus": pa.array(ls, pa.utf8()),
+        "l_returnflag": rf, "l_linestatus": ls,
         "l_shipdate": pa.array(shipdate, pa.date32()), "l_commitdate": pa.array(commitdate, pa.date32()),
         "l_receiptdate": pa.array(receiptdate, pa.date32()),
-        "l_shipinstruct": pa.array(instr, pa.utf8()), "l_shipmode": pa.array(mode, pa.utf8()),
-        "l_comment": pa.array(comment, pa.utf8()),
+        "l_shipinstruct": instr, "l_shipmode": mode,
+        "l_comment": comment,
     })
 
 
@@ -127,6 +140,33 @@ def write(table: pa.Table, path: str, compression: str = "uncompressed", stripe_
                    compression_block_size=block_size, dictionary_key_size_threshold=dict_threshold,
                    row_index_stride=row_index_stride)
     return path
+
+
+def _lineitem_file(args):
+    path, n_orders, seed, compression, block_size = args
+    if not os.path.exists(path):
+        t = lineitem_table(n_orders, seed)
+        tmp = path + ".tmp%d" % os.getpid()
+        write(t, tmp, compression=compression, block_size=block_size)
+        os.replace(tmp, path)
+    return path
+
+
+def lineitem_dataset(out_dir: str, total_rows: int, n_files: int, compression: str = "uncompressed",
+                     block_size: int = 256 << 10, procs: int = 0):
+    """Writes `n_files` lineitem ORC files (seeds 0..n_files-1, ~total_rows rows in all) in parallel.
+    Existing files are reused, so back-to-back bench arms share one generation."""
+    import concurrent.futures as cf
+    import multiprocessing as mp
+    os.makedirs(out_dir, exist_ok=True)
+    n_orders = max(1, total_rows // n_files // 4)
+    jobs = [(os.path.join(out_dir, f"lineitem_{compression}_{n_orders}_{i:03d}.orc"), n_orders, i, compression,
+             block_size) for i in range(n_files)]
+    procs = procs or min(n_files, os.cpu_count() or 1)
+    if procs <= 1 or all(os.path.exists(j[0]) for j in jobs):
+        return [_lineitem_file(j) for j in jobs]
+    with cf.ProcessPoolExecutor(procs, mp_context=mp.get_context("fork")) as ex:
+        return list(ex.map(_lineitem_file, jobs))
 
 
 if __name__ == "__main__":
