@@ -194,7 +194,9 @@ def main():
     if rank != 0:
         files, gen_s = _dataset(args.rows, args.files, args.compression)
 
-    stream = torch.cuda.current_stream()
+    # a real (non-null) torch stream: the library enqueues on it, torch.cuda.Event times it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     job = ob.DecodeJob(files, device=local_rank, cuda_stream=stream.cuda_stream, use_row_index=not args.no_row_index)
     job.plan()
     job.stage()     # allocates arenas, H2D of every stripe (untimed for `value`)
