@@ -327,9 +327,15 @@ int orcb_decode_int_rle(int device, const uint8_t* in, size_t in_len, int versio
         s.flags = (is_signed ? SEG_SIGNED : 0) | (version == 1 ? SEG_RLE_V2 : 0);
         s.nbytes = (uint8_t)nbytes;
         s.out_kind = OUT_I64;
-        s.end_byte = 0xffffffffu;
+        // exercise both code paths: with the sub-segment pre-pass when the request is large enough
+        const uint32_t nslots = (uint32_t)(n_values / SUB_VALUES + 2);
+        DevBuf dsub((size_t)nslots * sizeof(SubSeg));
+        CU(cudaMemset(dsub.p, 0, (size_t)nslots * sizeof(SubSeg)));
+        s.sub_base = 0;
+        s.sub_cap = nslots;
         CU(cudaMemcpy(dseg.p, &s, sizeof(s), cudaMemcpyHostToDevice));
-        int rc = launch_int_rle((Seg*)dseg.p, 1, nullptr, nullptr, (uint32_t*)sr.err.p, (uint32_t*)mis.p, 0);
+        int rc = launch_int_rle((Seg*)dseg.p, 1, n_values > 2 * SUB_VALUES ? (SubSeg*)dsub.p : nullptr, nslots, nullptr, nullptr,
+                                (uint32_t*)sr.err.p, (uint32_t*)mis.p, 0);
         if (rc) fail(ORCB_CUDA, cudaGetErrorString((cudaError_t)rc));
         sr.check();
         if (n_values) CU(cudaMemcpy(out, dout.p, n_values * 8, cudaMemcpyDeviceToHost));

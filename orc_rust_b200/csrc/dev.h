@@ -41,10 +41,24 @@ struct Seg {
     uint8_t out_kind;
     uint8_t pad0;
     uint32_t aux;
-    // consistency probe: where the next segment's row-index entry says this one must end (0xffffffff = none)
-    uint32_t end_byte;
-    uint32_t end_skip;
+    // sub-segment slots of this segment in the SubSeg table (filled by k_rle_index)
+    uint32_t sub_base;
+    uint32_t sub_cap;
 };
+
+// A slice of a segment that starts at a run boundary found by the k_rle_index pre-pass: the unit of work
+// of one lane of k_int_rle.  Unused slots stay zero (n_values == 0).
+struct SubSeg {
+    uint32_t seg;
+    uint32_t start_byte;
+    uint32_t run_skip;
+    uint32_t n_values;
+    uint32_t out_off;    // element offset from the segment's first output element
+    uint32_t pad[3];
+};
+
+// values per sub-segment (checkpoint spacing of the pre-pass)
+constexpr uint32_t SUB_VALUES = 256;
 
 // MSB-first boolean bytes -> LSB-first bitmap (+ popcount)
 struct BitSeg {

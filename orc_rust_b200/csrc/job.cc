@@ -265,6 +265,8 @@ void Job::plan() {
     task_first_cs_.clear();
     for (uint32_t t = 0; t < tasks_.size(); t++) plan_stripe(t);
 
+    if (n_sub_slots_) sub_table_ = alloc(AR_ZERO, (uint64_t)n_sub_slots_ * sizeof(SubSeg));
+
     // ---- descriptor blob layout
     auto place = [&](uint64_t& off, size_t bytes) {
         off = align_up(desc_bytes_, 256);
@@ -273,6 +275,7 @@ void Job::plan() {
     place(o_pbyte_, present_byte_segs_.size() * sizeof(Seg));
     place(o_dbyte_, data_byte_segs_.size() * sizeof(Seg));
     place(o_int_, int_segs_.size() * sizeof(Seg));
+    place(o_intbig_, int_big_segs_.size() * sizeof(Seg));
     place(o_var_, var_segs_.size() * sizeof(Seg));
     place(o_pbit_, present_bit_segs_.size() * sizeof(BitSeg));
     place(o_dbit_, data_bit_segs_.size() * sizeof(BitSeg));
@@ -559,8 +562,7 @@ void Job::plan_stripe(uint32_t task_idx) {
                 sg.colstripe = cs;
                 sg.out_kind = OUT_I8;
                 sg.aux = 1u | (pe[g].bit << 1);
-                sg.end_byte = 0xffffffffu;
-                present_byte_segs_.push_back(sg);
+                                present_byte_segs_.push_back(sg);
                 BitSeg b{};
                 b.src = raw + (uint64_t)g * slot;
                 b.dst = valid_raw;
@@ -611,8 +613,7 @@ void Job::plan_stripe(uint32_t task_idx) {
                 sg.nbytes = (uint8_t)nbytes;
                 sg.out_kind = okind;
                 sg.aux = aux;
-                sg.end_byte = 0xffffffffu;
-                if (has_present && per_group_counts) {
+                                if (has_present && per_group_counts) {
                     sg.cnt_idx = (int32_t)(cnt_base + g);
                     sg.start_idx = (int32_t)(cnt_base + g);
                 } else {
@@ -621,11 +622,27 @@ void Job::plan_stripe(uint32_t task_idx) {
                     sg.n_values = rows_in_group(g);
                     sg.out_start = g * gstride;
                 }
-                int_segs_.push_back(sg);
+                // Peek at the run header at the entry point (host has the bytes when the file is not
+                // compressed): segments that open with a long run go to the warp-per-segment kernel,
+                // everything else to the lane-per-segment kernel.  Purely a scheduling hint.
+                bool long_runs = false;
+                if (!compressed && v2 && sr.present && sg.start_byte + 2 <= sr.len) {
+                    const uint8_t* hp = fm.data + (sf.find(cid, &sr == &s_data ? S_DATA : (&sr == &s_length ? S_LENGTH : S_SECONDARY))->offset) + sg.start_byte;
+                    const uint32_t kind = hp[0] >> 6;
+                    const uint32_t rl = (((uint32_t)hp[0] & 1) << 8 | hp[1]) + 1;
+                    long_runs = kind != 0 && rl > 64;
+                }
+                if (!long_runs) {
+                    const uint32_t bound = (has_present && per_group_counts) ? rows_in_group(g) : sg.n_values;
+                    sg.sub_base = n_sub_slots_;
+                    sg.sub_cap = bound / SUB_VALUES + 2;
+                    n_sub_slots_ += sg.sub_cap;
+                }
+                (long_runs ? int_big_segs_ : int_segs_).push_back(sg);
+                static const uint32_t ow1[6] = {2, 4, 8, 4, 4, 1};
+                (long_runs ? ab_intbig_ : ab_int_) += (uint64_t)(sr.len / ng) + (uint64_t)rows_in_group(g) * ow1[okind];
             }
             n_segments_ += ng;
-            static const uint32_t ow[6] = {2, 4, 8, 4, 4, 1};
-            ab_int_ += sr.len + (uint64_t)n_rows * ow[okind];
         };
         // helper: dense -> rows
         auto add_spaced = [&](uint64_t src, uint64_t dst, uint32_t width, bool late) {
@@ -685,8 +702,7 @@ void Job::plan_stripe(uint32_t task_idx) {
                     sg.run_skip = en[g].skip;
                     sg.colstripe = cs;
                     sg.out_kind = OUT_I8;
-                    sg.end_byte = 0xffffffffu;
-                    if (has_present) {
+                                        if (has_present) {
                         sg.cnt_idx = (int32_t)(cnt_base + g);
                         sg.start_idx = (int32_t)(cnt_base + g);
                     } else {
@@ -721,8 +737,7 @@ void Job::plan_stripe(uint32_t task_idx) {
                     sg.colstripe = cs;
                     sg.out_kind = OUT_I8;
                     sg.aux = 1u | (en[g].bit << 1);
-                    sg.end_byte = 0xffffffffu;
-                    BitSeg b{};
+                                        BitSeg b{};
                     b.src = raw + (uint64_t)g * slot;
                     b.dst = dense_bits;
                     b.bit_skip = en[g].bit;
@@ -815,7 +830,9 @@ void Job::plan_stripe(uint32_t task_idx) {
                         sg.nbytes = 8;
                         sg.out_kind = OUT_LEN31;
                         sg.aux = ORCB_OFFSET_OVERFLOW;
-                        sg.end_byte = 0xffffffffu;
+                        sg.sub_base = n_sub_slots_;
+                        sg.sub_cap = enc.dict_size / SUB_VALUES + 2;
+                        n_sub_slots_ += sg.sub_cap;
                         int_segs_.push_back(sg);
                         n_segments_ += 1;
                     }
@@ -853,8 +870,7 @@ void Job::plan_stripe(uint32_t task_idx) {
                     sg.out = dst;
                     sg.start_byte = en[g].byte;
                     sg.colstripe = cs;
-                    sg.end_byte = 0xffffffffu;
-                    if (has_present) {
+                                        if (has_present) {
                         sg.cnt_idx = (int32_t)(cnt_base + g);
                         sg.start_idx = (int32_t)(cnt_base + g);
                     } else {
@@ -957,6 +973,7 @@ void Job::stage() {
     rseg(present_byte_segs_);
     rseg(data_byte_segs_);
     rseg(int_segs_);
+    rseg(int_big_segs_);
     rseg(var_segs_);
     for (auto* v : {&present_bit_segs_, &data_bit_segs_})
         for (auto& b : *v) { R(b.src); R(b.dst); }
@@ -979,6 +996,7 @@ void Job::stage() {
     put(o_pbyte_, present_byte_segs_.data(), present_byte_segs_.size() * sizeof(Seg));
     put(o_dbyte_, data_byte_segs_.data(), data_byte_segs_.size() * sizeof(Seg));
     put(o_int_, int_segs_.data(), int_segs_.size() * sizeof(Seg));
+    put(o_intbig_, int_big_segs_.data(), int_big_segs_.size() * sizeof(Seg));
     put(o_var_, var_segs_.data(), var_segs_.size() * sizeof(Seg));
     put(o_pbit_, present_bit_segs_.data(), present_bit_segs_.size() * sizeof(BitSeg));
     put(o_dbit_, data_bit_segs_.data(), data_bit_segs_.size() * sizeof(BitSeg));
@@ -1048,8 +1066,10 @@ void Job::launch() {
         run("k_byte_rle", ab_byte_, N(data_byte_segs_), 1, [&] { return launch_byte_rle((Seg*)(d_desc_ + o_dbyte_), N(data_byte_segs_), cnt, dstart, err, st); });
     if (N(data_bit_segs_))
         run("k_bits", ab_bits_, N(data_bit_segs_), 1, [&] { return launch_bits((BitSeg*)(d_desc_ + o_dbit_), N(data_bit_segs_), cnt, dstart, st); });
+    if (N(int_big_segs_))
+        run("k_int_rle_coop", ab_intbig_, N(int_big_segs_), 1, [&] { return launch_int_rle_coop((Seg*)(d_desc_ + o_intbig_), N(int_big_segs_), cnt, dstart, err, mis, st); });
     if (N(int_segs_))
-        run("k_int_rle", ab_int_, N(int_segs_), 1, [&] { return launch_int_rle((Seg*)(d_desc_ + o_int_), N(int_segs_), cnt, dstart, err, mis, st); });
+        run("k_rle_index+k_int_rle", ab_int_, N(int_segs_), 2, [&] { return launch_int_rle((Seg*)(d_desc_ + o_int_), N(int_segs_), (SubSeg*)(uintptr_t)reloc(sub_table_), n_sub_slots_, cnt, dstart, err, mis, st); });
     if (N(var_segs_))
         run("k_varint128", ab_var_, N(var_segs_), 1, [&] { return launch_varint128((Seg*)(d_desc_ + o_var_), N(var_segs_), cnt, dstart, err, st); });
     if (N(copy_tiles_))

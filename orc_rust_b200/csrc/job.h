@@ -96,7 +96,7 @@ class Job {
     uint8_t* base_[8] = {nullptr};
 
     // descriptor tables (host copies; pointer fields relocated at stage())
-    std::vector<Seg> present_byte_segs_, data_byte_segs_, int_segs_, var_segs_;
+    std::vector<Seg> present_byte_segs_, data_byte_segs_, int_segs_, int_big_segs_, var_segs_;
     std::vector<BitSeg> present_bit_segs_, data_bit_segs_;
     std::vector<ScanDesc> scans_;
     std::vector<CopyDesc> copies_;
@@ -107,7 +107,8 @@ class Job {
     std::vector<StrCol> strcols_;
     std::vector<RepackDesc> repacks_;
     std::vector<ChunkDesc> chunks_;
-    uint32_t str_tiles_ = 0, repack_work_ = 0;
+    uint32_t str_tiles_ = 0, repack_work_ = 0, n_sub_slots_ = 0;
+    uint64_t sub_table_ = 0;  // AR_ZERO offset of the SubSeg table
 
     // stage copies: (file ptr, file offset, AR_IN offset, bytes)
     struct StageCopy {
@@ -120,7 +121,7 @@ class Job {
     uint8_t* d_desc_ = nullptr;
     uint64_t desc_bytes_ = 0;
     // offsets of each table inside the descriptor blob
-    uint64_t o_pbyte_ = 0, o_dbyte_ = 0, o_int_ = 0, o_var_ = 0, o_pbit_ = 0, o_dbit_ = 0, o_scan_ = 0, o_copy_ = 0,
+    uint64_t o_pbyte_ = 0, o_dbyte_ = 0, o_int_ = 0, o_intbig_ = 0, o_var_ = 0, o_pbit_ = 0, o_dbit_ = 0, o_scan_ = 0, o_copy_ = 0,
              o_ctile_ = 0, o_sp_ = 0, o_sp2_ = 0, o_dec_ = 0, o_ts_ = 0, o_str_ = 0, o_rep_ = 0, o_chunk_ = 0;
     std::vector<uint8_t> desc_blob_;
 
@@ -152,7 +153,7 @@ class Job {
     std::vector<KStat> kstats_;
     KStat& kstat(const char* name);
     // algorithmic byte counters accumulated by the planner (per kernel)
-    uint64_t ab_decomp_ = 0, ab_present_ = 0, ab_byte_ = 0, ab_bits_ = 0, ab_int_ = 0, ab_var_ = 0, ab_copy_ = 0,
+    uint64_t ab_decomp_ = 0, ab_present_ = 0, ab_byte_ = 0, ab_bits_ = 0, ab_int_ = 0, ab_intbig_ = 0, ab_var_ = 0, ab_copy_ = 0,
              ab_spaced_ = 0, ab_dec_ = 0, ab_ts_ = 0, ab_str_ = 0, ab_repack_ = 0;
 
     cudaStream_t stream_ = nullptr;

@@ -104,7 +104,6 @@ struct SegCtx {
     const Seg* s;
     uint32_t* err;
     uint32_t* mis;
-    uint64_t obase;  // element index of the first value this segment writes
 };
 
 __device__ __forceinline__ void store_val(const SegCtx& c, uint64_t idx, int64_t v) {
@@ -126,13 +125,13 @@ __device__ __forceinline__ void store_val(const SegCtx& c, uint64_t idx, int64_t
 }
 
 // value i of the current run -> output, clipped to [skip, skip + take)
-#define EMIT(i, val)                                                            \
-    do {                                                                        \
-        uint32_t _i = (i);                                                      \
-        if (_i >= skip && _i - skip < take) store_val(c, c.obase + produced + (_i - skip), (val)); \
+#define EMIT(i, val)                                                                      \
+    do {                                                                                  \
+        uint32_t _i = (i);                                                                \
+        if (_i >= skip && _i - skip < take) store_val(c, out_pos + (_i - skip), (val));   \
     } while (0)
 
-// read_varint::<N> (integer/util.rs:475-498); uniform across the warp. returns 0 ok / status
+// read_varint::<N> (integer/util.rs:475-498). returns 0 ok / status
 __device__ __forceinline__ uint32_t parse_varint(const uint8_t* in, uint32_t& p, uint32_t len, int nbits, uint64_t& out) {
     uint64_t num = 0;
     uint32_t off = 0;
@@ -148,306 +147,651 @@ __device__ __forceinline__ uint32_t parse_varint(const uint8_t* in, uint32_t& p,
     return 0;
 }
 
+
 // ------------------------------------------------------------------------------------------------
-// RLE v2 (integer/rle_v2/{mod,short_repeat,direct,patched_base,delta}.rs)
+// RLE v2, ONE run decoded by all 32 lanes (integer/rle_v2/{direct,patched_base,delta}.rs).
+// All arguments are warp-uniform.  Values i in [skip, skip+take) go to out_pos + (i - skip).
 // ------------------------------------------------------------------------------------------------
-__device__ void rle2_segment(SegCtx& c, uint32_t n, uint32_t* patchmap, uint32_t& end_cur, uint32_t& end_skip) {
+__device__ uint32_t coop_run2(const SegCtx& c, uint32_t cur, uint32_t skip, uint32_t room, uint64_t out_pos,
+                              uint32_t* patchmap, uint32_t& rl_out, uint32_t& bytes_out, uint32_t& take_out) {
     const Seg& s = *c.s;
     const uint8_t* in = (const uint8_t*)s.in;
     const uint32_t len = s.in_len;
     const int lane = threadIdx.x & 31;
     const int nb = s.nbytes;
     const bool sg = (s.flags & SEG_SIGNED) != 0;
-    uint32_t cur = s.start_byte, skip = s.run_skip, produced = 0;
-    uint32_t last_rl = 0, last_cur = cur;
-
-    while (produced < n) {
-        if (cur >= len) { set_err(c.err, s.colstripe, ORCB_OUT_OF_SPEC); return; }
-        const uint32_t hdr = (uint32_t)load_be_bits(in + cur, 0, 32);
-        const uint32_t h0 = hdr >> 24;
-        const uint32_t kind = h0 >> 6;
-        uint32_t rl, run_bytes;
-        // `take` is resolved once the run length is known
-        uint32_t take;
-        if (kind == 0) {
-            // SHORT_REPEAT short_repeat.rs:29-63
-            const int bw = (int)((h0 >> 3) & 7) + 1;
-            if (nb < bw) { set_err(c.err, s.colstripe, ORCB_OUT_OF_SPEC); return; }
-            rl = (h0 & 7) + 3;
-            run_bytes = 1 + bw;
-            if (cur + run_bytes > len) { set_err(c.err, s.colstripe, ORCB_IO_ERROR); return; }
-            int64_t v = trunc_n((int64_t)load_be_bits(in + cur + 1, 0, bw * 8), nb);
-            if (sg) v = zigzag_n(v, nb);
-            const uint32_t avail = rl > skip ? rl - skip : 0;
-            take = min(avail, n - produced);
-            EMIT(lane, v);
-        } else if (kind == 1) {
-            // DIRECT direct.rs:39-65
-            const int w = width_of((h0 >> 1) & 31);
-            if (nb * 8 < w) { set_err(c.err, s.colstripe, ORCB_OUT_OF_SPEC); return; }
-            if (cur + 2 > len) { set_err(c.err, s.colstripe, ORCB_IO_ERROR); return; }
-            rl = (((h0 & 1) << 8) | ((hdr >> 16) & 255)) + 1;
-            run_bytes = 2 + (rl * (uint32_t)w + 7) / 8;
-            if (cur + run_bytes > len) { set_err(c.err, s.colstripe, ORCB_IO_ERROR); return; }
-            const uint32_t avail = rl > skip ? rl - skip : 0;
-            take = min(avail, n - produced);
-            const uint8_t* data = in + cur + 2;
-            const uint32_t i_end = min(rl, skip + take);
-            for (uint32_t i = skip + lane; i < i_end; i += 32) {
-                int64_t v = trunc_n((int64_t)load_be_bits(data, i * (uint32_t)w, w), nb);
-                if (sg) v = zigzag_n(v, nb);
-                store_val(c, c.obase + produced + (i - skip), v);
+    const uint32_t hdr = (uint32_t)load_be_bits(in + cur, 0, 32);
+    const uint32_t h0 = hdr >> 24;
+    const uint32_t kind = h0 >> 6;
+    uint32_t rl, run_bytes, take;
+    if (kind == 0) {
+        // SHORT_REPEAT short_repeat.rs:29-63 (normally taken by the owning lane; kept for completeness)
+        const int bw = (int)((h0 >> 3) & 7) + 1;
+        if (nb < bw) return ORCB_OUT_OF_SPEC;
+        rl = (h0 & 7) + 3;
+        run_bytes = 1 + bw;
+        if (cur + run_bytes > len) return ORCB_IO_ERROR;
+        int64_t v = trunc_n((int64_t)load_be_bits(in + cur + 1, 0, bw * 8), nb);
+        if (sg) v = zigzag_n(v, nb);
+        take = min(rl > skip ? rl - skip : 0u, room);
+        EMIT(lane, v);
+    } else if (kind == 1) {
+        // DIRECT direct.rs:39-65
+        const int w = width_of((h0 >> 1) & 31);
+        if (nb * 8 < w) return ORCB_OUT_OF_SPEC;
+        if (cur + 2 > len) return ORCB_IO_ERROR;
+        rl = (((h0 & 1) << 8) | ((hdr >> 16) & 255)) + 1;
+        run_bytes = 2 + (rl * (uint32_t)w + 7) / 8;
+        if (cur + run_bytes > len) return ORCB_IO_ERROR;
+        take = min(rl > skip ? rl - skip : 0u, room);
+        const uint8_t* data = in + cur + 2;
+        const uint32_t i_end = min(rl, skip + take);
+        // four values per lane per step, all loads issued before the first store (memory-level parallelism)
+        for (uint32_t i0 = skip + lane; i0 < i_end; i0 += 128) {
+            uint64_t raw[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t i = i0 + 32u * u;
+                raw[u] = i < i_end ? load_be_bits(data, i * (uint32_t)w, w) : 0ull;
             }
-        } else if (kind == 3) {
-            // DELTA delta.rs:44-116
-            if (cur + 2 > len) { set_err(c.err, s.colstripe, ORCB_IO_ERROR); return; }
-            const uint32_t code = (h0 >> 1) & 31;
-            const int w = code == 0 ? 0 : width_of(code);
-            rl = (((h0 & 1) << 8) | ((hdr >> 16) & 255)) + 1;
-            uint32_t p = cur + 2;
-            uint64_t ub, ud;
-            uint32_t e = parse_varint(in, p, len, nb * 8, ub);
-            if (e) { set_err(c.err, s.colstripe, e); return; }
-            int64_t base = trunc_n((int64_t)ub, nb);
-            if (sg) base = zigzag_n(base, nb);
-            e = parse_varint(in, p, len, 64, ud);
-            if (e) { set_err(c.err, s.colstripe, e); return; }
-            const int64_t d0 = zigzag_n((int64_t)ud, 8);
-            // op = add when d0 > 0, else subtract |d0| (is_positive() is false for 0), delta.rs:77-82
-            // d0 <= 0: base - |d0| == base + d0; |i64::MIN| wraps to i64::MIN in the reference, so the
-            // subtraction of it moves by +2^63
-            const __int128 step = d0 == INT64_MIN ? ((__int128)1 << 63) : (__int128)d0;
-            const bool positive = d0 > 0;
-            if (w == 0) {
-                run_bytes = p - cur;
-                const __int128 last = (__int128)base + (__int128)(rl - 1) * step;
-                if (!in_range_n(last, nb)) { set_err(c.err, s.colstripe, ORCB_OUT_OF_SPEC); return; }
-                const uint32_t avail = rl > skip ? rl - skip : 0;
-                take = min(avail, n - produced);
-                const uint32_t i_end = min(rl, skip + take);
-                const uint64_t ustep = (uint64_t)(int64_t)step;
-                for (uint32_t i = skip + lane; i < i_end; i += 32)
-                    store_val(c, c.obase + produced + (i - skip), (int64_t)((uint64_t)base + (uint64_t)i * ustep));
-            } else {
-                if (rl < 2) { set_err(c.err, s.colstripe, ORCB_IO_ERROR); return; }
-                const uint32_t nd = rl - 2;
-                run_bytes = (p - cur) + (nd * (uint32_t)w + 7) / 8;
-                if (cur + run_bytes > len) { set_err(c.err, s.colstripe, ORCB_IO_ERROR); return; }
-                const __int128 second = (__int128)base + step;
-                if (!in_range_n(second, nb)) { set_err(c.err, s.colstripe, ORCB_OUT_OF_SPEC); return; }
-                const uint32_t avail = rl > skip ? rl - skip : 0;
-                take = min(avail, n - produced);
-                EMIT(lane == 0 ? 0u : 0xffffffffu, base);
-                EMIT(lane == 1 ? 1u : 0xffffffffu, (int64_t)second);
-                const uint8_t* data = in + p;
-                if (w == 64) {
-                    // deltas are i64 here and may be negative: exact sequential semantics
-                    __int128 acc = second;
-                    for (uint32_t i = 0; i < nd; i++) {
-                        const int64_t d = (int64_t)load_be_bits(data, i * 64u, 64);
-                        acc = positive ? acc + (__int128)d : acc - (__int128)d;
-                        if (!in_range_n(acc, nb)) { set_err(c.err, s.colstripe, ORCB_OUT_OF_SPEC); return; }
-                        EMIT((i & 31) == (uint32_t)lane ? i + 2 : 0xffffffffu, (int64_t)acc);
-                    }
-                } else {
-                    // monotone run: wrapping prefix sums are exact iff the final value is in range
-                    uint64_t carry = 0, tot_lo = 0, tot_hi = 0;
-                    const uint64_t sec = (uint64_t)(int64_t)second;
-                    for (uint32_t i0 = 0; i0 < nd; i0 += 32) {
-                        const uint32_t i = i0 + lane;
-                        const uint64_t d = i < nd ? load_be_bits(data, i * (uint32_t)w, w) : 0ull;
-                        tot_lo += d & 0xffffffffull;
-                        tot_hi += d >> 32;
-                        const uint64_t pre = warp_incl_scan64(d, lane) + carry;
-                        if (i < nd) {
-                            const uint64_t v = positive ? sec + pre : sec - pre;
-                            EMIT(i + 2, (int64_t)v);
-                        }
-                        carry = __shfl_sync(FULL, pre, 31);
-                    }
-                    tot_lo = warp_sum64(tot_lo);
-                    tot_hi = warp_sum64(tot_hi);
-                    const __int128 total = ((__int128)tot_hi << 32) + (__int128)tot_lo;
-                    const __int128 fin = positive ? second + total : second - total;
-                    if (!in_range_n(fin, nb)) { set_err(c.err, s.colstripe, ORCB_OUT_OF_SPEC); return; }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t i = i0 + 32u * u;
+                if (i < i_end) {
+                    int64_t v = trunc_n((int64_t)raw[u], nb);
+                    if (sg) v = zigzag_n(v, nb);
+                    store_val(c, out_pos + (i - skip), v);
                 }
             }
-        } else {
-            // PATCHED_BASE patched_base.rs:38-151
-            if (cur + 4 > len) { set_err(c.err, s.colstripe, ORCB_IO_ERROR); return; }
-            const int w = width_of((h0 >> 1) & 31);
-            rl = (((h0 & 1) << 8) | ((hdr >> 16) & 255)) + 1;
-            const uint32_t b3 = (hdr >> 8) & 255, b4 = hdr & 255;
-            const int base_bw = (int)((b3 >> 5) & 7) + 1;
-            const int pw = width_of(b3 & 31);
-            const int pgw = (int)((b4 >> 5) & 7) + 1;
-            if (pw + pgw > 64) { set_err(c.err, s.colstripe, ORCB_OUT_OF_SPEC); return; }
-            const uint32_t pll = b4 & 31;
-            const int cfb = closest_fixed_bits(pw + pgw);
-            const uint32_t data_off = cur + 4 + base_bw;
-            const uint32_t data_bytes = (rl * (uint32_t)w + 7) / 8;
-            run_bytes = 4 + base_bw + data_bytes + (pll * (uint32_t)cfb + 7) / 8;
-            if (cur + run_bytes > len) { set_err(c.err, s.colstripe, ORCB_IO_ERROR); return; }
-            // value width wider than N: the reference panics or silently truncates; reported as OutOfSpec
-            if (nb * 8 < w || pll == 0) { set_err(c.err, s.colstripe, ORCB_OUT_OF_SPEC); return; }
-            const uint64_t ubase = load_be_bits(in + cur + 4, 0, base_bw * 8);
-            int64_t base = (int64_t)ubase;
-            if (sg) {  // signed_msb_decode util.rs:559-569
-                const uint64_t msb = 1ull << (base_bw * 8 - 1);
-                base = (ubase & msb) ? (int64_t)(0ull - (ubase & ~msb)) : (int64_t)(ubase & ~msb);
-            }
-            base = trunc_n(base, nb);
-            const uint8_t* data = in + data_off;
-            const uint8_t* pdata = data + data_bytes;
-            // one lane per patch-list entry
-            uint64_t pe = 0;
-            if ((uint32_t)lane < pll) pe = load_be_bits(pdata, (uint32_t)lane * (uint32_t)cfb, cfb);
-            const uint64_t pmask = (1ull << pw) - 1;  // pw <= 63 here
-            const uint64_t gap = pe >> pw;
-            const uint64_t patch = pe & pmask;
-            const bool live = (uint32_t)lane < pll;
-            const bool ext = live && gap == 255 && patch == 0;
-            const uint32_t pos = warp_incl_scan(live ? (uint32_t)gap : 0u, lane);
-            const uint32_t extmask = __ballot_sync(FULL, ext);
-            const bool prev_nonext = lane > 0 && !((extmask >> (lane - 1)) & 1);
-            const bool bad = live && !ext && gap == 0 && lane > 0 && prev_nonext;
-            const uint32_t badmask = __ballot_sync(FULL, bad);
-            const uint32_t first_bad = badmask ? (uint32_t)__ffs(badmask) - 1 : 32u;
-            const bool applied = live && !ext && (uint32_t)lane < first_bad && pos < rl;
-            const uint32_t appmask = __ballot_sync(FULL, applied);
-            // trailing gap-extension entries index past the patch list in the reference (panic)
-            if ((extmask >> (pll - 1)) & 1) {
-                const uint32_t nonext = ~extmask & (pll >= 32 ? FULL : ((1u << pll) - 1));
-                const bool reached = nonext == 0 || ((appmask >> (31 - __clz(nonext))) & 1);
-                if (reached) { set_err(c.err, s.colstripe, ORCB_OUT_OF_SPEC); return; }
-            }
-            if (lane < 16) patchmap[lane] = 0;
-            __syncwarp();
-            if (applied) atomicOr(&patchmap[pos >> 5], 1u << (pos & 31));
-            __syncwarp();
-            const uint32_t avail = rl > skip ? rl - skip : 0;
-            take = min(avail, n - produced);
-            bool ovf = false;
-            for (uint32_t i = lane; i < rl; i += 32) {
-                if ((patchmap[i >> 5] >> (i & 31)) & 1) continue;
-                const int64_t raw = trunc_n((int64_t)load_be_bits(data, i * (uint32_t)w, w), nb);
-                const __int128 sum = (__int128)raw + (__int128)base;
-                if (!in_range_n(sum, nb)) ovf = true;  // checked_add :144-146
-                EMIT(i, (int64_t)sum);
-            }
-            if (applied && w >= 64) ovf = true;  // checked_shl(64) -> None :112-117
-            if (__any_sync(FULL, ovf)) { set_err(c.err, s.colstripe, ORCB_OUT_OF_SPEC); return; }
-            if (applied) {
-                const int64_t raw = trunc_n((int64_t)load_be_bits(data, pos * (uint32_t)w, w), nb);
-                const int64_t pbits = trunc_n((int64_t)(patch << w), nb);
-                const int64_t v = trunc_n((int64_t)((uint64_t)(raw | pbits) + (uint64_t)base), nb);  // wrapping_add :122-124
-                EMIT(pos, v);
-            }
-            __syncwarp();
         }
-        last_rl = rl;
-        last_cur = cur;
-        if (skip >= rl) {
-            skip -= rl;
+    } else if (kind == 3) {
+        // DELTA delta.rs:44-116
+        if (cur + 2 > len) return ORCB_IO_ERROR;
+        const uint32_t code = (h0 >> 1) & 31;
+        const int w = code == 0 ? 0 : width_of(code);
+        rl = (((h0 & 1) << 8) | ((hdr >> 16) & 255)) + 1;
+        uint32_t p = cur + 2;
+        uint64_t ub, ud;
+        uint32_t e = parse_varint(in, p, len, nb * 8, ub);
+        if (e) return e;
+        int64_t base = trunc_n((int64_t)ub, nb);
+        if (sg) base = zigzag_n(base, nb);
+        e = parse_varint(in, p, len, 64, ud);
+        if (e) return e;
+        const int64_t d0 = zigzag_n((int64_t)ud, 8);
+        // d0 <= 0: base - |d0| == base + d0 (is_positive() is false for 0, delta.rs:77-82);
+        // |i64::MIN| wraps to i64::MIN in the reference, so subtracting it moves by +2^63
+        const __int128 step = d0 == INT64_MIN ? ((__int128)1 << 63) : (__int128)d0;
+        const bool positive = d0 > 0;
+        if (w == 0) {
+            run_bytes = p - cur;
+            const __int128 last = (__int128)base + (__int128)(rl - 1) * step;
+            if (!in_range_n(last, nb)) return ORCB_OUT_OF_SPEC;
+            take = min(rl > skip ? rl - skip : 0u, room);
+            const uint32_t i_end = min(rl, skip + take);
+            const uint64_t ustep = (uint64_t)(int64_t)step;
+            for (uint32_t i = skip + lane; i < i_end; i += 32)
+                store_val(c, out_pos + (i - skip), (int64_t)((uint64_t)base + (uint64_t)i * ustep));
         } else {
-            produced += take;
-            // position after this run for the consistency probe
-            if (produced >= n && skip + take < rl) {
-                end_cur = cur;
-                end_skip = skip + take;
-                return;
+            if (rl < 2) return ORCB_IO_ERROR;
+            const uint32_t nd = rl - 2;
+            run_bytes = (p - cur) + (nd * (uint32_t)w + 7) / 8;
+            if (cur + run_bytes > len) return ORCB_IO_ERROR;
+            const __int128 second = (__int128)base + step;
+            if (!in_range_n(second, nb)) return ORCB_OUT_OF_SPEC;
+            take = min(rl > skip ? rl - skip : 0u, room);
+            EMIT(lane == 0 ? 0u : 0xffffffffu, base);
+            EMIT(lane == 1 ? 1u : 0xffffffffu, (int64_t)second);
+            const uint8_t* data = in + p;
+            if (w == 64) {
+                // deltas are i64 here and may be negative: exact sequential semantics
+                __int128 acc = second;
+                for (uint32_t i = 0; i < nd; i++) {
+                    const int64_t d = (int64_t)load_be_bits(data, i * 64u, 64);
+                    acc = positive ? acc + (__int128)d : acc - (__int128)d;
+                    if (!in_range_n(acc, nb)) return ORCB_OUT_OF_SPEC;
+                    EMIT((i & 31) == (uint32_t)lane ? i + 2 : 0xffffffffu, (int64_t)acc);
+                }
+            } else {
+                // monotone run: wrapping prefix sums are exact iff the final value is in range
+                uint64_t carry = 0, tot_lo = 0, tot_hi = 0;
+                const uint64_t sec = (uint64_t)(int64_t)second;
+                for (uint32_t i0 = 0; i0 < nd; i0 += 32) {
+                    const uint32_t i = i0 + lane;
+                    const uint64_t d = i < nd ? load_be_bits(data, i * (uint32_t)w, w) : 0ull;
+                    tot_lo += d & 0xffffffffull;
+                    tot_hi += d >> 32;
+                    const uint64_t pre = warp_incl_scan64(d, lane) + carry;
+                    if (i < nd) {
+                        const uint64_t v = positive ? sec + pre : sec - pre;
+                        EMIT(i + 2, (int64_t)v);
+                    }
+                    carry = __shfl_sync(FULL, pre, 31);
+                }
+                tot_lo = warp_sum64(tot_lo);
+                tot_hi = warp_sum64(tot_hi);
+                const __int128 total = ((__int128)tot_hi << 32) + (__int128)tot_lo;
+                const __int128 fin = positive ? second + total : second - total;
+                if (!in_range_n(fin, nb)) return ORCB_OUT_OF_SPEC;
             }
-            skip = 0;
         }
-        cur += run_bytes;
+    } else {
+        // PATCHED_BASE patched_base.rs:38-151
+        if (cur + 4 > len) return ORCB_IO_ERROR;
+        const int w = width_of((h0 >> 1) & 31);
+        rl = (((h0 & 1) << 8) | ((hdr >> 16) & 255)) + 1;
+        const uint32_t b3 = (hdr >> 8) & 255, b4 = hdr & 255;
+        const int base_bw = (int)((b3 >> 5) & 7) + 1;
+        const int pw = width_of(b3 & 31);
+        const int pgw = (int)((b4 >> 5) & 7) + 1;
+        if (pw + pgw > 64) return ORCB_OUT_OF_SPEC;
+        const uint32_t pll = b4 & 31;
+        const int cfb = closest_fixed_bits(pw + pgw);
+        const uint32_t data_off = cur + 4 + base_bw;
+        const uint32_t data_bytes = (rl * (uint32_t)w + 7) / 8;
+        run_bytes = 4 + base_bw + data_bytes + (pll * (uint32_t)cfb + 7) / 8;
+        if (cur + run_bytes > len) return ORCB_IO_ERROR;
+        // value width wider than N: the reference panics or silently truncates; reported as OutOfSpec
+        if (nb * 8 < w || pll == 0) return ORCB_OUT_OF_SPEC;
+        const uint64_t ubase = load_be_bits(in + cur + 4, 0, base_bw * 8);
+        int64_t base = (int64_t)ubase;
+        if (sg) {  // signed_msb_decode util.rs:559-569
+            const uint64_t msb = 1ull << (base_bw * 8 - 1);
+            base = (ubase & msb) ? (int64_t)(0ull - (ubase & ~msb)) : (int64_t)(ubase & ~msb);
+        }
+        base = trunc_n(base, nb);
+        const uint8_t* data = in + data_off;
+        const uint8_t* pdata = data + data_bytes;
+        // one lane per patch-list entry
+        uint64_t pe = 0;
+        if ((uint32_t)lane < pll) pe = load_be_bits(pdata, (uint32_t)lane * (uint32_t)cfb, cfb);
+        const uint64_t pmask = (1ull << pw) - 1;  // pw <= 63 here
+        const uint64_t gap = pe >> pw;
+        const uint64_t patch = pe & pmask;
+        const bool live = (uint32_t)lane < pll;
+        const bool ext = live && gap == 255 && patch == 0;
+        const uint32_t pos = warp_incl_scan(live ? (uint32_t)gap : 0u, lane);
+        const uint32_t extmask = __ballot_sync(FULL, ext);
+        const bool prev_nonext = lane > 0 && !((extmask >> (lane - 1)) & 1);
+        const bool bad = live && !ext && gap == 0 && lane > 0 && prev_nonext;
+        const uint32_t badmask = __ballot_sync(FULL, bad);
+        const uint32_t first_bad = badmask ? (uint32_t)__ffs(badmask) - 1 : 32u;
+        const bool applied = live && !ext && (uint32_t)lane < first_bad && pos < rl;
+        const uint32_t appmask = __ballot_sync(FULL, applied);
+        // trailing gap-extension entries index past the patch list in the reference (panic)
+        if ((extmask >> (pll - 1)) & 1) {
+            const uint32_t nonext = ~extmask & (pll >= 32 ? FULL : ((1u << pll) - 1));
+            const bool reached = nonext == 0 || ((appmask >> (31 - __clz(nonext))) & 1);
+            if (reached) return ORCB_OUT_OF_SPEC;
+        }
+        if (lane < 16) patchmap[lane] = 0;
+        __syncwarp();
+        if (applied) atomicOr(&patchmap[pos >> 5], 1u << (pos & 31));
+        __syncwarp();
+        take = min(rl > skip ? rl - skip : 0u, room);
+        bool ovf = false;
+        for (uint32_t i = lane; i < rl; i += 32) {
+            if ((patchmap[i >> 5] >> (i & 31)) & 1) continue;
+            const int64_t raw = trunc_n((int64_t)load_be_bits(data, i * (uint32_t)w, w), nb);
+            const __int128 sum = (__int128)raw + (__int128)base;
+            if (!in_range_n(sum, nb)) ovf = true;  // checked_add :144-146
+            EMIT(i, (int64_t)sum);
+        }
+        if (applied && w >= 64) ovf = true;  // checked_shl(64) -> None :112-117
+        if (__any_sync(FULL, ovf)) return ORCB_OUT_OF_SPEC;
+        if (applied) {
+            const int64_t raw = trunc_n((int64_t)load_be_bits(data, pos * (uint32_t)w, w), nb);
+            const int64_t pbits = trunc_n((int64_t)(patch << w), nb);
+            const int64_t v = trunc_n((int64_t)((uint64_t)(raw | pbits) + (uint64_t)base), nb);  // wrapping_add :122-124
+            EMIT(pos, v);
+        }
+        __syncwarp();
     }
-    (void)last_rl;
-    (void)last_cur;
-    end_cur = cur;
-    end_skip = 0;
+    rl_out = rl;
+    bytes_out = run_bytes;
+    take_out = take;
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
-// RLE v1 (integer/rle_v1.rs:54-68, 90-159).  Legacy format: decoded with warp-uniform control flow.
+// Integer RLE, third design: every lane of a warp owns one (stream, row-group) segment and only PARSES
+// its next run header (scalar code, constant cost per run); the values of the parsed runs are then
+// produced by all 32 lanes together, one value per lane per step, whichever run they belong to.
+// Runs that need a scan or a patch list (DELTA with packed deltas, PATCHED_BASE) are decoded one at a
+// time by the whole warp (coop_run2).
 // ------------------------------------------------------------------------------------------------
-__device__ void rle1_segment(SegCtx& c, uint32_t n, uint32_t& end_cur, uint32_t& end_skip) {
+enum RunClass : uint32_t { RC_NONE = 0, RC_CONST = 1, RC_DIRECT = 2, RC_COOP = 3 };
+
+struct RunSlot {       // one per lane, in shared memory
+    uint64_t base;     // RC_CONST: value at k = 0
+    uint64_t step;     // RC_CONST: value(k) = base + k * step
+    uint64_t data;     // RC_DIRECT: packed values
+    uint64_t out;      // destination buffer
+    uint64_t out_idx;  // element index of the first emitted value
+    uint32_t skip;     // first k emitted
+    uint32_t meta;     // w | cls << 8 | out_kind << 12 | nbytes << 16 | signed << 24
+    uint32_t prefix;   // inclusive prefix sum of emitted counts over the lanes
+    uint32_t colstripe;
+    uint32_t aux;
+    uint32_t pad;
+};
+
+// Parse the run at `cur` of the lane's own segment.  No values are produced here (except RLE v1 literals).
+__device__ __forceinline__ uint32_t parse_run2(const Seg& s, uint32_t cur, RunSlot& d, uint32_t& cls, uint32_t& rl_out,
+                                               uint32_t& bytes_out) {
+    const uint8_t* in = (const uint8_t*)s.in;
+    const uint32_t len = s.in_len;
+    const int nb = s.nbytes;
+    const bool sg = (s.flags & SEG_SIGNED) != 0;
+    const uint32_t hdr = (uint32_t)load_be_bits(in + cur, 0, 32);
+    const uint32_t h0 = hdr >> 24;
+    const uint32_t kind = h0 >> 6;
+    if (kind == 0) {
+        // SHORT_REPEAT short_repeat.rs:29-63
+        const int bw = (int)((h0 >> 3) & 7) + 1;
+        if (nb < bw) return ORCB_OUT_OF_SPEC;
+        rl_out = (h0 & 7) + 3;
+        bytes_out = 1 + bw;
+        if (cur + bytes_out > len) return ORCB_IO_ERROR;
+        const uint64_t raw = bw <= 3 ? (uint64_t)((hdr & 0xffffffu) >> (8 * (3 - bw))) : load_be_bits(in + cur + 1, 0, bw * 8);
+        int64_t v = trunc_n((int64_t)raw, nb);
+        if (sg) v = zigzag_n(v, nb);
+        d.base = (uint64_t)v;
+        d.step = 0;
+        cls = RC_CONST;
+        return 0;
+    }
+    if (kind == 2) {
+        cls = RC_COOP;
+        return 0;
+    }
+    if (cur + 2 > len) return ORCB_IO_ERROR;
+    const uint32_t rl = (((h0 & 1) << 8) | ((hdr >> 16) & 255)) + 1;
+    const uint32_t code = (h0 >> 1) & 31;
+    rl_out = rl;
+    if (kind == 1) {
+        // DIRECT direct.rs:39-65
+        const int w = width_of(code);
+        if (nb * 8 < w) return ORCB_OUT_OF_SPEC;
+        bytes_out = 2 + (rl * (uint32_t)w + 7) / 8;
+        if (cur + bytes_out > len) return ORCB_IO_ERROR;
+        d.data = (uint64_t)(uintptr_t)(in + cur + 2);
+        d.meta = (uint32_t)w;
+        cls = RC_DIRECT;
+        return 0;
+    }
+    // DELTA delta.rs:44-116
+    if (code != 0) {
+        cls = RC_COOP;  // packed deltas need a prefix sum
+        return 0;
+    }
+    uint32_t p = cur + 2;
+    uint64_t ub, ud;
+    uint32_t e = parse_varint(in, p, len, nb * 8, ub);
+    if (e) return e;
+    int64_t base = trunc_n((int64_t)ub, nb);
+    if (sg) base = zigzag_n(base, nb);
+    e = parse_varint(in, p, len, 64, ud);
+    if (e) return e;
+    const int64_t d0 = zigzag_n((int64_t)ud, 8);
+    // d0 <= 0: base - |d0| == base + d0 (is_positive() is false for 0, delta.rs:77-82);
+    // |i64::MIN| wraps to i64::MIN in the reference, so subtracting it moves by +2^63
+    const __int128 step = d0 == INT64_MIN ? ((__int128)1 << 63) : (__int128)d0;
+    const __int128 last = (__int128)base + (__int128)(rl - 1) * step;
+    if (!in_range_n(last, nb)) return ORCB_OUT_OF_SPEC;
+    bytes_out = p - cur;
+    d.base = (uint64_t)base;
+    d.step = (uint64_t)(int64_t)step;
+    cls = RC_CONST;
+    return 0;
+}
+
+// RLE v1 (integer/rle_v1.rs:54-68, 90-159).  Runs become RC_CONST; literal groups are decoded right here
+// by the owning lane (legacy format, not worth a cooperative path).
+__device__ __forceinline__ uint32_t parse_run1(const SegCtx& c, uint32_t cur, uint32_t skip, uint32_t room, uint64_t out_pos,
+                                               RunSlot& d, uint32_t& cls, uint32_t& rl_out, uint32_t& bytes_out,
+                                               uint32_t& take_out) {
     const Seg& s = *c.s;
     const uint8_t* in = (const uint8_t*)s.in;
     const uint32_t len = s.in_len;
-    const int lane = threadIdx.x & 31;
     const int nb = s.nbytes;
     const bool sg = (s.flags & SEG_SIGNED) != 0;
-    uint32_t cur = s.start_byte, skip = s.run_skip, produced = 0;
-    while (produced < n) {
-        if (cur >= len) { set_err(c.err, s.colstripe, ORCB_OUT_OF_SPEC); return; }
-        const int8_t h = (int8_t)in[cur];
-        uint32_t p = cur + 1;
-        uint32_t rl, take;
-        if (h < 0) {
-            rl = (uint32_t)(-(int)h);
-            const uint32_t avail = rl > skip ? rl - skip : 0;
-            take = min(avail, n - produced);
-            for (uint32_t i = 0; i < rl; i++) {
-                uint64_t u;
-                const uint32_t e = parse_varint(in, p, len, nb * 8, u);
-                if (e) { set_err(c.err, s.colstripe, e); return; }
-                int64_t v = trunc_n((int64_t)u, nb);
-                if (sg) v = zigzag_n(v, nb);
-                EMIT((i & 31) == (uint32_t)lane ? i : 0xffffffffu, v);
-            }
-        } else {
-            rl = (uint32_t)(uint8_t)h + 3;
-            if (p >= len) { set_err(c.err, s.colstripe, ORCB_IO_ERROR); return; }
-            const int delta = (int)(int8_t)in[p++];
+    const int8_t h = (int8_t)in[cur];
+    uint32_t p = cur + 1;
+    if (h < 0) {
+        const uint32_t rl = (uint32_t)(-(int)h);
+        const uint32_t take = min(rl > skip ? rl - skip : 0u, room);
+        for (uint32_t i = 0; i < rl; i++) {
             uint64_t u;
             const uint32_t e = parse_varint(in, p, len, nb * 8, u);
-            if (e) { set_err(c.err, s.colstripe, e); return; }
-            int64_t base = trunc_n((int64_t)u, nb);
-            if (sg) base = zigzag_n(base, nb);
-            const __int128 last = (__int128)base + (__int128)(rl - 1) * (__int128)delta;
-            if (!in_range_n(last, nb)) { set_err(c.err, s.colstripe, ORCB_OUT_OF_SPEC); return; }
-            const uint32_t avail = rl > skip ? rl - skip : 0;
-            take = min(avail, n - produced);
-            for (uint32_t i = lane; i < rl; i += 32) EMIT(i, base + (int64_t)i * delta);
+            if (e) return e;
+            int64_t v = trunc_n((int64_t)u, nb);
+            if (sg) v = zigzag_n(v, nb);
+            EMIT(i, v);
         }
+        rl_out = rl;
+        bytes_out = p - cur;
+        take_out = take;
+        cls = RC_NONE;  // already emitted
+        return 0;
+    }
+    const uint32_t rl = (uint32_t)(uint8_t)h + 3;
+    if (p >= len) return ORCB_IO_ERROR;
+    const int delta = (int)(int8_t)in[p++];
+    uint64_t u;
+    const uint32_t e = parse_varint(in, p, len, nb * 8, u);
+    if (e) return e;
+    int64_t base = trunc_n((int64_t)u, nb);
+    if (sg) base = zigzag_n(base, nb);
+    const __int128 last = (__int128)base + (__int128)(rl - 1) * (__int128)delta;
+    if (!in_range_n(last, nb)) return ORCB_OUT_OF_SPEC;
+    d.base = (uint64_t)base;
+    d.step = (uint64_t)(int64_t)delta;
+    rl_out = rl;
+    bytes_out = p - cur;
+    cls = RC_CONST;
+    return 0;
+}
+
+// Header-only walk: length in values and bytes of the run at `cur` (no values produced).
+__device__ __forceinline__ uint32_t measure_run(const Seg& s, uint32_t cur, uint32_t& rl_out, uint32_t& bytes_out) {
+    const uint8_t* in = (const uint8_t*)s.in;
+    const uint32_t len = s.in_len;
+    if (!(s.flags & SEG_RLE_V2)) {
+        // RLE v1 (integer/rle_v1.rs:54-68)
+        const int8_t h = (int8_t)in[cur];
+        uint32_t p = cur + 1;
+        uint32_t nvar;
+        if (h < 0) {
+            rl_out = (uint32_t)(-(int)h);
+            nvar = rl_out;
+        } else {
+            rl_out = (uint32_t)(uint8_t)h + 3;
+            p += 1;  // delta byte
+            nvar = 1;
+        }
+        for (uint32_t i = 0; i < nvar; i++) {
+            for (;;) {
+                if (p >= len) return ORCB_IO_ERROR;
+                if (!(in[p++] & 0x80)) break;
+            }
+        }
+        bytes_out = p - cur;
+        return 0;
+    }
+    const uint32_t hdr = (uint32_t)load_be_bits(in + cur, 0, 32);
+    const uint32_t h0 = hdr >> 24;
+    const uint32_t kind = h0 >> 6;
+    if (kind == 0) {
+        rl_out = (h0 & 7) + 3;
+        bytes_out = 2 + ((h0 >> 3) & 7);
+    } else {
+        const uint32_t rl = (((h0 & 1) << 8) | ((hdr >> 16) & 255)) + 1;
+        const uint32_t code = (h0 >> 1) & 31;
+        rl_out = rl;
+        if (kind == 1) {
+            bytes_out = 2 + (rl * (uint32_t)width_of(code) + 7) / 8;
+        } else if (kind == 2) {
+            const uint32_t b3 = (hdr >> 8) & 255, b4 = hdr & 255;
+            const int pw = width_of(b3 & 31), pgw = (int)((b4 >> 5) & 7) + 1;
+            if (pw + pgw > 64) return ORCB_OUT_OF_SPEC;
+            bytes_out = 4 + ((b3 >> 5) & 7) + 1 + (rl * (uint32_t)width_of(code) + 7) / 8 +
+                        ((b4 & 31) * (uint32_t)closest_fixed_bits(pw + pgw) + 7) / 8;
+        } else {
+            uint32_t p = cur + 2;
+            for (int i = 0; i < 2; i++) {
+                for (;;) {
+                    if (p >= len) return ORCB_IO_ERROR;
+                    if (!(in[p++] & 0x80)) break;
+                }
+            }
+            if (code != 0) {
+                if (rl < 2) return ORCB_IO_ERROR;
+                p += ((rl - 2) * (uint32_t)width_of(code) + 7) / 8;
+            }
+            bytes_out = p - cur;
+        }
+    }
+    if (cur + bytes_out > len) return ORCB_IO_ERROR;
+    return 0;
+}
+
+// Pre-pass ("device-built row index"): one lane per segment walks the run headers only and drops a
+// checkpoint at the first run boundary after every SUB_VALUES values.  Gives k_int_rle short, independent
+// units even for streams of very short runs, and for files written without a row index.
+__global__ void __launch_bounds__(128) k_rle_index(const Seg* __restrict__ segs, uint32_t nseg,
+                                                   const uint32_t* __restrict__ cnt, SubSeg* subs, uint32_t* err) {
+    const uint32_t segi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (segi >= nseg) return;
+    const Seg& s = segs[segi];
+    const uint32_t n = s.cnt_idx >= 0 ? cnt[s.cnt_idx] : s.n_values;
+    if (n == 0 || s.sub_cap == 0) return;
+    SubSeg* out = subs + s.sub_base;
+    uint32_t cur = s.start_byte, skip = s.run_skip, produced = 0;
+    uint32_t slot = 0, sub_start = cur, sub_skip = skip, sub_first = 0;
+    while (produced < n) {
+        if (cur >= s.in_len) break;  // reported by k_int_rle when it reaches this point
+        uint32_t rl, nbytes;
+        if (measure_run(s, cur, rl, nbytes)) break;
         if (skip >= rl) {
             skip -= rl;
         } else {
-            produced += take;
-            if (produced >= n && skip + take < rl) {
-                end_cur = cur;
-                end_skip = skip + take;
-                return;
-            }
+            produced += min(rl - skip, n - produced);
             skip = 0;
         }
-        cur = p;
+        cur += nbytes;
+        if (produced - sub_first >= SUB_VALUES && produced < n && slot + 1 < s.sub_cap) {
+            SubSeg r;
+            r.seg = segi; r.start_byte = sub_start; r.run_skip = sub_skip; r.n_values = produced - sub_first;
+            r.out_off = sub_first; r.pad[0] = r.pad[1] = r.pad[2] = 0;
+            out[slot++] = r;
+            sub_start = cur;
+            sub_skip = 0;
+            sub_first = produced;
+        }
     }
-    end_cur = cur;
-    end_skip = 0;
+    // last slice: everything that is left (k_int_rle re-walks it and reports any error)
+    SubSeg r;
+    r.seg = segi; r.start_byte = sub_start; r.run_skip = sub_skip; r.n_values = n - sub_first;
+    r.out_off = sub_first; r.pad[0] = r.pad[1] = r.pad[2] = 0;
+    out[slot] = r;
 }
 
 constexpr int RLE_WARPS = 4;
+constexpr int SEGS_PER_WARP = 32;
 
-__global__ void __launch_bounds__(RLE_WARPS * 32) k_int_rle(const Seg* __restrict__ segs, uint32_t nseg,
+__global__ void __launch_bounds__(RLE_WARPS * 32) k_int_rle(const Seg* __restrict__ segs, uint32_t nunits,
+                                                            const SubSeg* __restrict__ subs,
                                                             const uint32_t* __restrict__ cnt,
                                                             const uint32_t* __restrict__ dstart, uint32_t* err,
                                                             uint32_t* mis) {
-    __shared__ uint32_t patchmap[RLE_WARPS][16];
+    __shared__ uint32_t patchmap_all[RLE_WARPS][16];
+    __shared__ RunSlot slots_all[RLE_WARPS][32];
+    uint32_t* patchmap = patchmap_all[threadIdx.x >> 5];
+    RunSlot* slots = slots_all[threadIdx.x >> 5];
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (warp >= nseg) return;
-    const Seg* s = &segs[warp];
+    const int lane = threadIdx.x & 31;
+    // unit = a whole segment (subs == nullptr) or one sub-segment slot written by k_rle_index
+    const uint32_t unit = warp * SEGS_PER_WARP + lane;
+    const bool have = lane < SEGS_PER_WARP && unit < nunits;
+    SubSeg sub;
+    sub.seg = have ? unit : 0;
+    sub.n_values = 0xffffffffu;
+    sub.out_off = 0;
+    if (subs && have) sub = subs[unit];
+    const uint32_t segi = sub.seg;
     SegCtx c;
-    c.s = s;
+    c.s = &segs[segi];
     c.err = err;
     c.mis = mis;
-    const uint32_t n = s->cnt_idx >= 0 ? cnt[s->cnt_idx] : s->n_values;
-    c.obase = s->start_idx >= 0 ? dstart[s->start_idx] : s->out_start;
-    uint32_t end_cur = 0, end_skip = 0;
-    if (s->flags & SEG_RLE_V2) rle2_segment(c, n, patchmap[(threadIdx.x >> 5)], end_cur, end_skip);
-    else rle1_segment(c, n, end_cur, end_skip);
-    (void)end_cur;
-    (void)end_skip;
+    const Seg& s = *c.s;
+    uint32_t n = 0;
+    uint64_t obase = 0;
+    uint32_t cur = s.start_byte, skip = s.run_skip, produced = 0;
+    if (have) {
+        if (subs) {
+            n = sub.n_values;
+            cur = sub.start_byte;
+            skip = sub.run_skip;
+        } else {
+            n = s.cnt_idx >= 0 ? cnt[s.cnt_idx] : s.n_values;
+        }
+        obase = (uint64_t)(s.start_idx >= 0 ? dstart[s.start_idx] : s.out_start) + sub.out_off;
+    }
+    const bool v2 = (s.flags & SEG_RLE_V2) != 0;
+    bool active = have && n > 0;
+    RunSlot& my = slots[lane];
+    my.out = s.out;
+    my.colstripe = s.colstripe;
+    my.aux = s.aux;
+    const uint32_t meta_hi = ((uint32_t)s.out_kind << 12) | ((uint32_t)s.nbytes << 16) | ((s.flags & SEG_SIGNED) ? (1u << 24) : 0u);
+
+    while (__any_sync(FULL, active)) {
+        uint32_t cls = RC_NONE, rl = 0, nbytes = 0, take = 0;
+        bool parsed = false;
+        if (active) {
+            uint32_t st;
+            my.meta = 0;
+            if (cur >= s.in_len) st = ORCB_OUT_OF_SPEC;  // "not enough values to decode" rle_v2/mod.rs:115-122
+            else if (v2) st = parse_run2(s, cur, my, cls, rl, nbytes);
+            else st = parse_run1(c, cur, skip, n - produced, obase + produced, my, cls, rl, nbytes, take);
+            if (st) {
+                set_err(err, s.colstripe, st);
+                active = false;
+                cls = RC_NONE;
+            } else {
+                parsed = true;
+            }
+            if (cls == RC_CONST || cls == RC_DIRECT) {
+                take = min(rl > skip ? rl - skip : 0u, n - produced);
+                my.out_idx = obase + produced;
+                my.skip = skip;
+                my.meta = (my.meta & 0xffu) | (cls << 8) | meta_hi;
+            }
+        }
+        const uint32_t emit = (cls == RC_CONST || cls == RC_DIRECT) ? take : 0u;
+        const uint32_t incl = warp_incl_scan(emit, lane);
+        my.prefix = incl;
+        const uint32_t total = __shfl_sync(FULL, incl, 31);
+        __syncwarp();
+        // ---- all lanes produce the values of all parsed runs: 4 values per lane per step, every load
+        //      issued before the first store
+        for (uint32_t v0 = lane; v0 < total; v0 += 128) {
+            uint32_t li[4], jj[4];
+            uint64_t raw[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t v = v0 + 32u * u;
+                uint32_t l = 0;
+                if (v < total) {
+#pragma unroll
+                    for (int stp = 16; stp > 0; stp >>= 1)
+                        if (slots[l + stp - 1].prefix <= v) l += stp;
+                }
+                li[u] = l;
+                const RunSlot& d = slots[l];
+                jj[u] = v - (l ? slots[l - 1].prefix : 0u);
+                const uint32_t meta = d.meta;
+                raw[u] = 0;
+                if (v < total && ((meta >> 8) & 0xf) == RC_DIRECT) {
+                    const int w = (int)(meta & 0xff);
+                    raw[u] = load_be_bits((const uint8_t*)(uintptr_t)d.data, (d.skip + jj[u]) * (uint32_t)w, w);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t v = v0 + 32u * u;
+                if (v >= total) continue;
+                const RunSlot& d = slots[li[u]];
+                const uint32_t meta = d.meta;
+                const int nb = (int)((meta >> 16) & 0xff);
+                int64_t val;
+                if (((meta >> 8) & 0xf) == RC_CONST) {
+                    val = (int64_t)(d.base + (uint64_t)(d.skip + jj[u]) * d.step);
+                } else {
+                    val = trunc_n((int64_t)raw[u], nb);
+                    if (meta & (1u << 24)) val = zigzag_n(val, nb);
+                }
+                const uint64_t idx = d.out_idx + jj[u];
+                switch ((meta >> 12) & 0xf) {
+                    case OUT_I16: ((int16_t*)d.out)[idx] = (int16_t)val; break;
+                    case OUT_I32: ((int32_t*)d.out)[idx] = (int32_t)val; break;
+                    case OUT_I64: ((int64_t*)d.out)[idx] = val; break;
+                    case OUT_LEN31:
+                        if ((uint64_t)val > 0x7fffffffull) set_err(err, d.colstripe, d.aux);
+                        ((int32_t*)d.out)[idx] = (int32_t)val;
+                        break;
+                    case OUT_SCALE:
+                        if ((uint32_t)(int32_t)val != d.aux) atomicOr(&mis[d.colstripe], 1u);
+                        ((int32_t*)d.out)[idx] = (int32_t)val;
+                        break;
+                    default: break;
+                }
+            }
+        }
+        __syncwarp();
+        // ---- runs that need the whole warp
+        uint32_t bigmask = __ballot_sync(FULL, active && cls == RC_COOP);
+        while (bigmask) {
+            const int leader = __ffs(bigmask) - 1;
+            bigmask &= bigmask - 1;
+            const uint32_t lseg = __shfl_sync(FULL, segi, leader);
+            const uint32_t lcur = __shfl_sync(FULL, cur, leader);
+            const uint32_t lskip = __shfl_sync(FULL, skip, leader);
+            const uint32_t lroom = __shfl_sync(FULL, n - produced, leader);
+            const uint64_t lout = __shfl_sync(FULL, obase + produced, leader);
+            SegCtx lc;
+            lc.s = &segs[lseg];
+            lc.err = err;
+            lc.mis = mis;
+            uint32_t crl = 0, cbytes = 0, ctake = 0;
+            const uint32_t st = coop_run2(lc, lcur, lskip, lroom, lout, patchmap, crl, cbytes, ctake);
+            if (lane == leader) {
+                if (st) {
+                    set_err(err, s.colstripe, st);
+                    active = false;
+                    parsed = false;
+                }
+                rl = crl;
+                nbytes = cbytes;
+                take = ctake;
+            }
+        }
+        if (active && parsed) {
+            if (skip >= rl) skip -= rl;
+            else { produced += take; skip = 0; }
+            cur += nbytes;
+        }
+        active = active && produced < n;
+    }
+}
+
+// Warp-per-segment variant for segments made of long runs (every run decoded by all 32 lanes).
+__global__ void __launch_bounds__(RLE_WARPS * 32) k_int_rle_coop(const Seg* __restrict__ segs, uint32_t nseg,
+                                                                 const uint32_t* __restrict__ cnt,
+                                                                 const uint32_t* __restrict__ dstart, uint32_t* err,
+                                                                 uint32_t* mis) {
+    __shared__ uint32_t patchmap_all[RLE_WARPS][16];
+    uint32_t* patchmap = patchmap_all[threadIdx.x >> 5];
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= nseg) return;
+    SegCtx c;
+    c.s = &segs[warp];
+    c.err = err;
+    c.mis = mis;
+    const Seg& s = *c.s;
+    const uint32_t n = s.cnt_idx >= 0 ? cnt[s.cnt_idx] : s.n_values;
+    const uint64_t obase = s.start_idx >= 0 ? dstart[s.start_idx] : s.out_start;
+    uint32_t cur = s.start_byte, skip = s.run_skip, produced = 0;
+    while (produced < n) {
+        if (cur >= s.in_len) { set_err(err, s.colstripe, ORCB_OUT_OF_SPEC); return; }
+        uint32_t rl = 0, nbytes = 0, take = 0;
+        const uint32_t st = coop_run2(c, cur, skip, n - produced, obase + produced, patchmap, rl, nbytes, take);
+        if (st) { set_err(err, s.colstripe, st); return; }
+        if (skip >= rl) skip -= rl;
+        else { produced += take; skip = 0; }
+        cur += nbytes;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -569,58 +913,97 @@ __global__ void k_seg_scan(const ScanDesc* __restrict__ descs, uint32_t ndesc, u
 __global__ void __launch_bounds__(128) k_varint128(const Seg* __restrict__ segs, uint32_t nseg,
                                                    const uint32_t* __restrict__ cnt,
                                                    const uint32_t* __restrict__ dstart, uint32_t* err) {
+    // 128-byte windows: lane l owns bytes [4l, 4l+4).  Every window starts at the first byte of a value;
+    // all values that terminate inside the window are emitted, the next window restarts right after the
+    // last terminator (so a value cut by the window edge is simply read again).
+    __shared__ uint32_t win_all[4][32 + 2];
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (warp >= nseg) return;
     const Seg& s = segs[warp];
     const int lane = threadIdx.x & 31;
+    uint32_t* win = win_all[threadIdx.x >> 5];
+    const uint8_t* winb = (const uint8_t*)win;
     const uint8_t* in = (const uint8_t*)s.in;
     const uint32_t len = s.in_len;
     const uint32_t n = s.cnt_idx >= 0 ? cnt[s.cnt_idx] : s.n_values;
     const uint64_t obase = s.start_idx >= 0 ? dstart[s.start_idx] : s.out_start;
     uint4* out = (uint4*)s.out;
     uint32_t produced = 0;
-    uint32_t cur = s.start_byte;      // first byte of this 32-byte window
-    uint32_t open_start = cur;        // first byte of the value that is still open
+    uint32_t cur = s.start_byte;
+    const uint32_t lt = (1u << lane) - 1;
     while (produced < n) {
         if (cur >= len) { set_err(err, s.colstripe, ORCB_IO_ERROR); return; }
-        const uint32_t p = cur + lane;
-        const bool inb = p < len;
-        const uint32_t b = inb ? in[p] : 0x80u;
-        const uint32_t term = __ballot_sync(FULL, inb && !(b & 0x80));
-        const bool is_term = (term >> lane) & 1;
-        const uint32_t below = term & ((1u << lane) - 1);
-        const uint32_t vi = produced + __popc(below);
-        if (is_term && vi < n) {
-            const uint32_t start = below ? cur + (32 - __clz(below)) : open_start;
-            const uint32_t nbv = p - start + 1;
-            if (nbv > 19) {
-                set_err(err, s.colstripe, ORCB_VARINT_TOO_LARGE);  // shift >= 128
-            }
-            uint64_t lo = 0, hi = 0;
-            for (uint32_t k = 0; k < nbv && k < 19; k++) {
-                const uint64_t x = in[start + k] & 0x7f;
-                const uint32_t sh = 7 * k;
-                if (sh < 64) {
-                    lo |= x << sh;
-                    if (sh > 57) hi |= x >> (64 - sh);
-                } else {
-                    hi |= x << (sh - 64);
-                }
-            }
-            // zigzag: (v >>> 1) ^ -(v & 1) on 128 bits
-            const uint64_t sgn = 0ull - (lo & 1);
-            const uint64_t rlo = ((lo >> 1) | (hi << 63)) ^ sgn;
-            const uint64_t rhi = (hi >> 1) ^ sgn;
-            out[obase + vi] = make_uint4((uint32_t)rlo, (uint32_t)(rlo >> 32), (uint32_t)rhi, (uint32_t)(rhi >> 32));
-        }
-        produced += __popc(term);
-        if (term) open_start = cur + (32 - __clz(term));
-        else if (min(cur + 32, len) - open_start >= 20 && produced < n) {
-            // 20 continuation bytes in a row: checked_shl fails at shift >= 128
-            set_err(err, s.colstripe, ORCB_VARINT_TOO_LARGE);
+        // unaligned 4-byte little-endian load of bytes cur + 4*lane .. +3
+        const uint32_t p = cur + 4u * lane;
+        const uintptr_t ai = (uintptr_t)(in + p);
+        const uint32_t* q = (const uint32_t*)(ai & ~(uintptr_t)3);
+        const uint32_t sh = (uint32_t)(ai & 3) * 8;
+        const uint32_t w0 = __ldg(q);
+        const uint32_t w1 = sh ? __ldg(q + 1) : 0u;
+        uint32_t word = __funnelshift_r(w0, w1, sh);
+        // bytes past the end of the stream count as continuation bytes
+        const uint32_t valid = p >= len ? 0u : min(4u, len - p);
+        uint32_t cont = word & 0x80808080u;
+        if (valid < 4) cont |= 0x80808080u << (8 * valid);
+        const uint32_t tb = ~cont & 0x80808080u;  // bit 7 of byte j set <=> byte j terminates a value
+        win[lane] = word;
+        const uint32_t T0 = __ballot_sync(FULL, tb & 0x00000080u);
+        const uint32_t T1 = __ballot_sync(FULL, tb & 0x00008000u);
+        const uint32_t T2 = __ballot_sync(FULL, tb & 0x00800000u);
+        const uint32_t T3 = __ballot_sync(FULL, tb & 0x80000000u);
+        __syncwarp();
+        const uint32_t all = T0 | T1 | T2 | T3;
+        if (all == 0) {
+            // no terminator in 128 bytes: either >= 20 continuation bytes (shift >= 128) or end of stream
+            set_err(err, s.colstripe, (len - cur >= 20) ? ORCB_VARINT_TOO_LARGE : ORCB_IO_ERROR);
             return;
         }
-        cur += 32;
+        // terminators strictly before my word, and the byte position just after the last of them
+        const uint32_t before = __popc(T0 & lt) + __popc(T1 & lt) + __popc(T2 & lt) + __popc(T3 & lt);
+        int prev_end = -1;  // window byte index of the last terminator before my word
+        if (T0 & lt) prev_end = max(prev_end, 4 * (31 - __clz(T0 & lt)) + 0);
+        if (T1 & lt) prev_end = max(prev_end, 4 * (31 - __clz(T1 & lt)) + 1);
+        if (T2 & lt) prev_end = max(prev_end, 4 * (31 - __clz(T2 & lt)) + 2);
+        if (T3 & lt) prev_end = max(prev_end, 4 * (31 - __clz(T3 & lt)) + 3);
+        uint32_t vi = produced + before;
+        int start = prev_end + 1;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (tb & (0x80u << (8 * j))) {
+                const int end = 4 * lane + j;
+                const int nbv = end - start + 1;
+                if (vi < n) {
+                    if (nbv > 19) set_err(err, s.colstripe, ORCB_VARINT_TOO_LARGE);
+                    uint64_t lo = 0, hi = 0;
+                    for (int k = 0; k < nbv && k < 19; k++) {
+                        const uint64_t x = winb[start + k] & 0x7f;
+                        const int sft = 7 * k;
+                        if (sft < 64) {
+                            lo |= x << sft;
+                            if (sft > 57) hi |= x >> (64 - sft);
+                        } else {
+                            hi |= x << (sft - 64);
+                        }
+                    }
+                    // zigzag: (v >>> 1) ^ -(v & 1) on 128 bits
+                    const uint64_t sgn = 0ull - (lo & 1);
+                    const uint64_t rlo = ((lo >> 1) | (hi << 63)) ^ sgn;
+                    const uint64_t rhi = (hi >> 1) ^ sgn;
+                    out[obase + vi] = make_uint4((uint32_t)rlo, (uint32_t)(rlo >> 32), (uint32_t)rhi, (uint32_t)(rhi >> 32));
+                }
+                vi++;
+                start = end + 1;
+            }
+        }
+        produced += __popc(T0) + __popc(T1) + __popc(T2) + __popc(T3);
+        // restart right after the last terminator of the window
+        int last = 0;
+        if (T0) last = max(last, 4 * (31 - __clz(T0)) + 0);
+        if (T1) last = max(last, 4 * (31 - __clz(T1)) + 1);
+        if (T2) last = max(last, 4 * (31 - __clz(T2)) + 2);
+        if (T3) last = max(last, 4 * (31 - __clz(T3)) + 3);
+        cur += (uint32_t)last + 1;
+        __syncwarp();
     }
 }
 
@@ -1135,10 +1518,24 @@ static inline uint32_t blocks_for_warps(uint32_t nwarps, uint32_t warps_per_bloc
         if (_e != cudaSuccess) return (int)_e;   \
     } while (0)
 
-int launch_int_rle(const Seg* segs, uint32_t n, const uint32_t* cnt, const uint32_t* dstart, uint32_t* err, uint32_t* mis,
-                   cudaStream_t st) {
+int launch_int_rle(const Seg* segs, uint32_t n, SubSeg* subs, uint32_t nslots, const uint32_t* cnt, const uint32_t* dstart,
+                   uint32_t* err, uint32_t* mis, cudaStream_t st) {
     if (!n) return 0;
-    k_int_rle<<<blocks_for_warps(n, RLE_WARPS), RLE_WARPS * 32, 0, st>>>(segs, n, cnt, dstart, err, mis);
+    uint32_t units = n;
+    if (subs) {
+        k_rle_index<<<(n + 127) / 128, 128, 0, st>>>(segs, n, cnt, subs, err);
+        LAUNCH_CHECK();
+        units = nslots;
+    }
+    const uint32_t nwarps = (units + SEGS_PER_WARP - 1) / SEGS_PER_WARP;
+    k_int_rle<<<blocks_for_warps(nwarps, RLE_WARPS), RLE_WARPS * 32, 0, st>>>(segs, units, subs, cnt, dstart, err, mis);
+    LAUNCH_CHECK();
+    return 0;
+}
+int launch_int_rle_coop(const Seg* segs, uint32_t n, const uint32_t* cnt, const uint32_t* dstart, uint32_t* err,
+                        uint32_t* mis, cudaStream_t st) {
+    if (!n) return 0;
+    k_int_rle_coop<<<blocks_for_warps(n, RLE_WARPS), RLE_WARPS * 32, 0, st>>>(segs, n, cnt, dstart, err, mis);
     LAUNCH_CHECK();
     return 0;
 }

@@ -7,8 +7,11 @@
 
 namespace orcb {
 
-int launch_int_rle(const Seg* segs, uint32_t n, const uint32_t* cnt, const uint32_t* dstart, uint32_t* err, uint32_t* mis,
-                   cudaStream_t st);
+// subs != nullptr: run the k_rle_index pre-pass into `subs` (nslots zeroed entries) and decode per sub-segment
+int launch_int_rle(const Seg* segs, uint32_t n, SubSeg* subs, uint32_t nslots, const uint32_t* cnt, const uint32_t* dstart,
+                   uint32_t* err, uint32_t* mis, cudaStream_t st);
+int launch_int_rle_coop(const Seg* segs, uint32_t n, const uint32_t* cnt, const uint32_t* dstart, uint32_t* err,
+                        uint32_t* mis, cudaStream_t st);
 int launch_byte_rle(const Seg* segs, uint32_t n, const uint32_t* cnt, const uint32_t* dstart, uint32_t* err,
                     cudaStream_t st);
 int launch_bits(const BitSeg* segs, uint32_t n, uint32_t* cnt, const uint32_t* dstart, cudaStream_t st);
