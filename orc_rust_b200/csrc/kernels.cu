@@ -38,6 +38,24 @@ __device__ __forceinline__ uint64_t load_be_bits(const uint8_t* p, uint32_t bitp
     return t >> (64 - w);
 }
 
+// same for w <= 32: two aligned words, 32-bit arithmetic only
+__device__ __forceinline__ uint32_t load_be_bits32(const uint8_t* p, uint32_t bitpos, int w) {
+    const uint8_t* a = p + (bitpos >> 3);
+    const uintptr_t ai = (uintptr_t)a;
+    const uint32_t* q = (const uint32_t*)(ai & ~(uintptr_t)3);
+    const uint32_t sh = ((uint32_t)(ai & 3) << 3) + (bitpos & 7);  // 0..31
+    const uint32_t w0 = bswap32(__ldg(q));
+    const uint32_t w1 = bswap32(__ldg(q + 1));
+    return __funnelshift_l(w1, w0, sh) >> (32 - w);
+}
+// packed value of width <= 32 -> i64 with the reference's N-width zigzag semantics (see trunc_n / zigzag_n):
+// for w <= 8*nbytes the 32-bit zigzag followed by sign extension gives the same bits
+__device__ __forceinline__ int64_t finish32(uint32_t x, bool sg, int nb) {
+    const uint32_t z = (x >> 1) ^ (0u - (x & 1));
+    if (sg) return (int64_t)(int32_t)z;
+    return nb >= 8 ? (int64_t)(uint64_t)x : (nb == 4 ? (int64_t)(int32_t)x : (int64_t)(int16_t)x);
+}
+
 // 32 bits of an LSB-first bitmap starting at an arbitrary bit position
 __device__ __forceinline__ uint32_t load_bits32(const uint32_t* bm, uint64_t bitpos) {
     const uint64_t wi = bitpos >> 5;
@@ -187,20 +205,36 @@ __device__ uint32_t coop_run2(const SegCtx& c, uint32_t cur, uint32_t skip, uint
         const uint8_t* data = in + cur + 2;
         const uint32_t i_end = min(rl, skip + take);
         // four values per lane per step, all loads issued before the first store (memory-level parallelism)
-        for (uint32_t i0 = skip + lane; i0 < i_end; i0 += 128) {
-            uint64_t raw[4];
+        if (w <= 32 && (nb > 2 || w <= 16)) {
+            for (uint32_t i0 = skip + lane; i0 < i_end; i0 += 128) {
+                uint32_t raw[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const uint32_t i = i0 + 32u * u;
-                raw[u] = i < i_end ? load_be_bits(data, i * (uint32_t)w, w) : 0ull;
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t i = i0 + 32u * u;
+                    raw[u] = i < i_end ? load_be_bits32(data, i * (uint32_t)w, w) : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t i = i0 + 32u * u;
+                    if (i < i_end) store_val(c, out_pos + (i - skip), finish32(raw[u], sg, nb));
+                }
             }
+        } else {
+            for (uint32_t i0 = skip + lane; i0 < i_end; i0 += 128) {
+                uint64_t raw[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const uint32_t i = i0 + 32u * u;
-                if (i < i_end) {
-                    int64_t v = trunc_n((int64_t)raw[u], nb);
-                    if (sg) v = zigzag_n(v, nb);
-                    store_val(c, out_pos + (i - skip), v);
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t i = i0 + 32u * u;
+                    raw[u] = i < i_end ? load_be_bits(data, i * (uint32_t)w, w) : 0ull;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t i = i0 + 32u * u;
+                    if (i < i_end) {
+                        int64_t v = trunc_n((int64_t)raw[u], nb);
+                        if (sg) v = zigzag_n(v, nb);
+                        store_val(c, out_pos + (i - skip), v);
+                    }
                 }
             }
         }
@@ -599,6 +633,7 @@ __global__ void __launch_bounds__(128) k_rle_index(const Seg* __restrict__ segs,
 
 constexpr int RLE_WARPS = 4;
 constexpr int SEGS_PER_WARP = 32;
+constexpr uint32_t SELF_MAX = 0;   // runs up to this long would be emitted by their own lane (measured slower: scattered stores)
 
 __global__ void __launch_bounds__(RLE_WARPS * 32) k_int_rle(const Seg* __restrict__ segs, uint32_t nunits,
                                                             const SubSeg* __restrict__ subs,
@@ -669,7 +704,31 @@ __global__ void __launch_bounds__(RLE_WARPS * 32) k_int_rle(const Seg* __restric
                 my.meta = (my.meta & 0xffu) | (cls << 8) | meta_hi;
             }
         }
-        const uint32_t emit = (cls == RC_CONST || cls == RC_DIRECT) ? take : 0u;
+        // short runs are written by their own lane; longer ones by the whole warp below
+        bool self = false;
+        if (SELF_MAX > 0 && (cls == RC_CONST || cls == RC_DIRECT) && take <= SELF_MAX) {
+            self = true;
+            const uint64_t o0 = obase + produced;
+            if (cls == RC_CONST) {
+                for (uint32_t j = 0; j < take; j++) store_val(c, o0 + j, (int64_t)(my.base + (uint64_t)(skip + j) * my.step));
+            } else {
+                const int w = (int)(my.meta & 0xff);
+                const int nb = s.nbytes;
+                const bool sg = (s.flags & SEG_SIGNED) != 0;
+                const uint8_t* data = (const uint8_t*)(uintptr_t)my.data;
+                if (w <= 32 && (nb > 2 || w <= 16)) {
+                    for (uint32_t j = 0; j < take; j++)
+                        store_val(c, o0 + j, finish32(load_be_bits32(data, (skip + j) * (uint32_t)w, w), sg, nb));
+                } else {
+                    for (uint32_t j = 0; j < take; j++) {
+                        int64_t v = trunc_n((int64_t)load_be_bits(data, (skip + j) * (uint32_t)w, w), nb);
+                        if (sg) v = zigzag_n(v, nb);
+                        store_val(c, o0 + j, v);
+                    }
+                }
+            }
+        }
+        const uint32_t emit = (!self && (cls == RC_CONST || cls == RC_DIRECT)) ? take : 0u;
         const uint32_t incl = warp_incl_scan(emit, lane);
         my.prefix = incl;
         const uint32_t total = __shfl_sync(FULL, incl, 31);
@@ -695,7 +754,11 @@ __global__ void __launch_bounds__(RLE_WARPS * 32) k_int_rle(const Seg* __restric
                 raw[u] = 0;
                 if (v < total && ((meta >> 8) & 0xf) == RC_DIRECT) {
                     const int w = (int)(meta & 0xff);
-                    raw[u] = load_be_bits((const uint8_t*)(uintptr_t)d.data, (d.skip + jj[u]) * (uint32_t)w, w);
+                    const int nbx = (int)((meta >> 16) & 0xff);
+                    if (w <= 32 && (nbx > 2 || w <= 16))
+                        raw[u] = load_be_bits32((const uint8_t*)(uintptr_t)d.data, (d.skip + jj[u]) * (uint32_t)w, w);
+                    else
+                        raw[u] = load_be_bits((const uint8_t*)(uintptr_t)d.data, (d.skip + jj[u]) * (uint32_t)w, w);
                 }
             }
 #pragma unroll
@@ -709,8 +772,13 @@ __global__ void __launch_bounds__(RLE_WARPS * 32) k_int_rle(const Seg* __restric
                 if (((meta >> 8) & 0xf) == RC_CONST) {
                     val = (int64_t)(d.base + (uint64_t)(d.skip + jj[u]) * d.step);
                 } else {
-                    val = trunc_n((int64_t)raw[u], nb);
-                    if (meta & (1u << 24)) val = zigzag_n(val, nb);
+                    const int w = (int)(meta & 0xff);
+                    if (w <= 32 && (nb > 2 || w <= 16)) {
+                        val = finish32((uint32_t)raw[u], (meta & (1u << 24)) != 0, nb);
+                    } else {
+                        val = trunc_n((int64_t)raw[u], nb);
+                        if (meta & (1u << 24)) val = zigzag_n(val, nb);
+                    }
                 }
                 const uint64_t idx = d.out_idx + jj[u];
                 switch ((meta >> 12) & 0xf) {
@@ -913,16 +981,19 @@ __global__ void k_seg_scan(const ScanDesc* __restrict__ descs, uint32_t ndesc, u
 __global__ void __launch_bounds__(128) k_varint128(const Seg* __restrict__ segs, uint32_t nseg,
                                                    const uint32_t* __restrict__ cnt,
                                                    const uint32_t* __restrict__ dstart, uint32_t* err) {
-    // 128-byte windows: lane l owns bytes [4l, 4l+4).  Every window starts at the first byte of a value;
-    // all values that terminate inside the window are emitted, the next window restarts right after the
-    // last terminator (so a value cut by the window edge is simply read again).
-    __shared__ uint32_t win_all[4][32 + 2];
+    // 128-byte windows.  Lane l looks at bytes l, l+32, l+64, l+96 so that each ballot is a terminator
+    // bitmap in byte order.  Every window starts at the first byte of a value; terminator lanes publish the
+    // end position of "their" value in shared memory, then the values are assembled one per lane per round.
+    // The next window restarts right after the last terminator (a value cut by the edge is read again).
+    __shared__ uint32_t win_all[4][32 + 4];
+    __shared__ uint8_t ends_all[4][128];
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (warp >= nseg) return;
     const Seg& s = segs[warp];
     const int lane = threadIdx.x & 31;
     uint32_t* win = win_all[threadIdx.x >> 5];
-    const uint8_t* winb = (const uint8_t*)win;
+    uint8_t* winb = (uint8_t*)win;
+    uint8_t* ends = ends_all[threadIdx.x >> 5];
     const uint8_t* in = (const uint8_t*)s.in;
     const uint32_t len = s.in_len;
     const uint32_t n = s.cnt_idx >= 0 ? cnt[s.cnt_idx] : s.n_values;
@@ -931,78 +1002,69 @@ __global__ void __launch_bounds__(128) k_varint128(const Seg* __restrict__ segs,
     uint32_t produced = 0;
     uint32_t cur = s.start_byte;
     const uint32_t lt = (1u << lane) - 1;
+    if (lane < 4) win[32 + lane] = 0;
     while (produced < n) {
         if (cur >= len) { set_err(err, s.colstripe, ORCB_IO_ERROR); return; }
-        // unaligned 4-byte little-endian load of bytes cur + 4*lane .. +3
-        const uint32_t p = cur + 4u * lane;
-        const uintptr_t ai = (uintptr_t)(in + p);
-        const uint32_t* q = (const uint32_t*)(ai & ~(uintptr_t)3);
-        const uint32_t sh = (uint32_t)(ai & 3) * 8;
-        const uint32_t w0 = __ldg(q);
-        const uint32_t w1 = sh ? __ldg(q + 1) : 0u;
-        uint32_t word = __funnelshift_r(w0, w1, sh);
-        // bytes past the end of the stream count as continuation bytes
-        const uint32_t valid = p >= len ? 0u : min(4u, len - p);
-        uint32_t cont = word & 0x80808080u;
-        if (valid < 4) cont |= 0x80808080u << (8 * valid);
-        const uint32_t tb = ~cont & 0x80808080u;  // bit 7 of byte j set <=> byte j terminates a value
-        win[lane] = word;
-        const uint32_t T0 = __ballot_sync(FULL, tb & 0x00000080u);
-        const uint32_t T1 = __ballot_sync(FULL, tb & 0x00008000u);
-        const uint32_t T2 = __ballot_sync(FULL, tb & 0x00800000u);
-        const uint32_t T3 = __ballot_sync(FULL, tb & 0x80000000u);
-        __syncwarp();
-        const uint32_t all = T0 | T1 | T2 | T3;
-        if (all == 0) {
+        uint32_t T[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t p = cur + 32u * j + lane;
+            // bytes past the end of the stream count as continuation bytes
+            const uint32_t b = p < len ? (uint32_t)__ldg(in + p) : 0x80u;
+            winb[32 * j + lane] = (uint8_t)b;
+            T[j] = __ballot_sync(FULL, !(b & 0x80));
+        }
+        const uint32_t c0 = __popc(T[0]), c1 = __popc(T[1]), c2 = __popc(T[2]), c3 = __popc(T[3]);
+        const uint32_t total = c0 + c1 + c2 + c3;
+        if (total == 0) {
             // no terminator in 128 bytes: either >= 20 continuation bytes (shift >= 128) or end of stream
             set_err(err, s.colstripe, (len - cur >= 20) ? ORCB_VARINT_TOO_LARGE : ORCB_IO_ERROR);
             return;
         }
-        // terminators strictly before my word, and the byte position just after the last of them
-        const uint32_t before = __popc(T0 & lt) + __popc(T1 & lt) + __popc(T2 & lt) + __popc(T3 & lt);
-        int prev_end = -1;  // window byte index of the last terminator before my word
-        if (T0 & lt) prev_end = max(prev_end, 4 * (31 - __clz(T0 & lt)) + 0);
-        if (T1 & lt) prev_end = max(prev_end, 4 * (31 - __clz(T1 & lt)) + 1);
-        if (T2 & lt) prev_end = max(prev_end, 4 * (31 - __clz(T2 & lt)) + 2);
-        if (T3 & lt) prev_end = max(prev_end, 4 * (31 - __clz(T3 & lt)) + 3);
-        uint32_t vi = produced + before;
-        int start = prev_end + 1;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            if (tb & (0x80u << (8 * j))) {
-                const int end = 4 * lane + j;
-                const int nbv = end - start + 1;
-                if (vi < n) {
-                    if (nbv > 19) set_err(err, s.colstripe, ORCB_VARINT_TOO_LARGE);
-                    uint64_t lo = 0, hi = 0;
-                    for (int k = 0; k < nbv && k < 19; k++) {
-                        const uint64_t x = winb[start + k] & 0x7f;
-                        const int sft = 7 * k;
-                        if (sft < 64) {
-                            lo |= x << sft;
-                            if (sft > 57) hi |= x >> (64 - sft);
-                        } else {
-                            hi |= x << (sft - 64);
-                        }
+        if ((T[0] >> lane) & 1) ends[__popc(T[0] & lt)] = (uint8_t)lane;
+        if ((T[1] >> lane) & 1) ends[c0 + __popc(T[1] & lt)] = (uint8_t)(32 + lane);
+        if ((T[2] >> lane) & 1) ends[c0 + c1 + __popc(T[2] & lt)] = (uint8_t)(64 + lane);
+        if ((T[3] >> lane) & 1) ends[c0 + c1 + c2 + __popc(T[3] & lt)] = (uint8_t)(96 + lane);
+        __syncwarp();
+        const uint32_t room = n - produced;
+        for (uint32_t k = lane; k < total && k < room; k += 32) {
+            const uint32_t end = ends[k];
+            const uint32_t start = k ? (uint32_t)ends[k - 1] + 1 : 0u;
+            const uint32_t nbv = end - start + 1;
+            uint64_t lo, hi = 0;
+            if (nbv <= 8) {
+                // 8 little-endian bytes starting at `start` (window is padded), 7-bit groups squeezed together
+                const uint32_t a = start >> 2, shb = (start & 3) * 8;
+                const uint32_t w0 = win[a], w1 = win[a + 1], w2 = win[a + 2];
+                uint32_t x0 = __funnelshift_r(w0, w1, shb), x1 = __funnelshift_r(w1, w2, shb);
+                if (nbv < 4) x0 &= (1u << (8 * nbv)) - 1;
+                if (nbv <= 4) x1 = 0;
+                else if (nbv < 8) x1 &= (1u << (8 * (nbv - 4))) - 1;
+                const uint32_t g0 = (x0 & 0x7fu) | ((x0 & 0x7f00u) >> 1) | ((x0 & 0x7f0000u) >> 2) | ((x0 & 0x7f000000u) >> 3);
+                const uint32_t g1 = (x1 & 0x7fu) | ((x1 & 0x7f00u) >> 1) | ((x1 & 0x7f0000u) >> 2) | ((x1 & 0x7f000000u) >> 3);
+                lo = (uint64_t)g0 | ((uint64_t)g1 << 28);
+            } else {
+                if (nbv > 19) set_err(err, s.colstripe, ORCB_VARINT_TOO_LARGE);  // shift >= 128
+                lo = 0;
+                for (uint32_t q = 0; q < nbv && q < 19; q++) {
+                    const uint64_t x = winb[start + q] & 0x7f;
+                    const uint32_t sft = 7 * q;
+                    if (sft < 64) {
+                        lo |= x << sft;
+                        if (sft > 57) hi |= x >> (64 - sft);
+                    } else {
+                        hi |= x << (sft - 64);
                     }
-                    // zigzag: (v >>> 1) ^ -(v & 1) on 128 bits
-                    const uint64_t sgn = 0ull - (lo & 1);
-                    const uint64_t rlo = ((lo >> 1) | (hi << 63)) ^ sgn;
-                    const uint64_t rhi = (hi >> 1) ^ sgn;
-                    out[obase + vi] = make_uint4((uint32_t)rlo, (uint32_t)(rlo >> 32), (uint32_t)rhi, (uint32_t)(rhi >> 32));
                 }
-                vi++;
-                start = end + 1;
             }
+            // zigzag: (v >>> 1) ^ -(v & 1) on 128 bits
+            const uint64_t sgn = 0ull - (lo & 1);
+            const uint64_t rlo = ((lo >> 1) | (hi << 63)) ^ sgn;
+            const uint64_t rhi = (hi >> 1) ^ sgn;
+            out[obase + produced + k] = make_uint4((uint32_t)rlo, (uint32_t)(rlo >> 32), (uint32_t)rhi, (uint32_t)(rhi >> 32));
         }
-        produced += __popc(T0) + __popc(T1) + __popc(T2) + __popc(T3);
-        // restart right after the last terminator of the window
-        int last = 0;
-        if (T0) last = max(last, 4 * (31 - __clz(T0)) + 0);
-        if (T1) last = max(last, 4 * (31 - __clz(T1)) + 1);
-        if (T2) last = max(last, 4 * (31 - __clz(T2)) + 2);
-        if (T3) last = max(last, 4 * (31 - __clz(T3)) + 3);
-        cur += (uint32_t)last + 1;
+        produced += total;
+        cur += (uint32_t)ends[total - 1] + 1;
         __syncwarp();
     }
 }
@@ -1292,13 +1354,23 @@ __global__ void k_str_tile_scan(StrCol* cols, uint32_t ncols, uint32_t* err, Job
     }
 }
 
+constexpr uint32_t SD_ENTRIES = 256;   // dictionaries up to this many entries / bytes are staged in shared memory
+constexpr uint32_t SD_BYTES = 2048;
+constexpr uint32_t STAGE_BYTES = 1024; // bytes of 32 rows gathered in shared memory before one coalesced write
+
 __global__ void __launch_bounds__(128) k_str_offsets(const StrCol* __restrict__ cols, uint32_t ncols, uint32_t ntiles,
                                                      uint32_t* err) {
+    __shared__ uint16_t s_doff_all[4][SD_ENTRIES + 2];
+    __shared__ uint8_t s_ddata_all[4][SD_BYTES];
+    __shared__ uint8_t s_stage_all[4][STAGE_BYTES];
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (warp >= ntiles) return;
     const StrCol& c = find_strcol(cols, ncols, warp);
     const uint32_t tile = warp - c.tile0;
     const int lane = threadIdx.x & 31;
+    uint16_t* s_doff = s_doff_all[threadIdx.x >> 5];
+    uint8_t* s_ddata = s_ddata_all[threadIdx.x >> 5];
+    uint8_t* s_stage = s_stage_all[threadIdx.x >> 5];
     uint32_t b, r0, nr;
     tile_rows(c, tile, b, r0, nr);
     const uint64_t* tb = (const uint64_t*)c.tile_base;
@@ -1309,6 +1381,17 @@ __global__ void __launch_bounds__(128) k_str_offsets(const StrCol* __restrict__ 
     const uint8_t* dict = (const uint8_t*)c.dict_data;
     const int32_t* doff = (const int32_t*)c.dict_off;
     uint8_t* data = (uint8_t*)c.data;
+    // small dictionaries live in shared memory for the whole tile
+    bool sdict = false;
+    if (c.mode == 1 && nr > 0 && c.dict_size <= SD_ENTRIES) {
+        const uint32_t dbytes = (uint32_t)doff[c.dict_size];
+        if (dbytes <= SD_BYTES) {
+            sdict = true;
+            for (uint32_t i = lane; i <= c.dict_size; i += 32) s_doff[i] = (uint16_t)doff[i];
+            for (uint32_t i = lane; i < dbytes; i += 32) s_ddata[i] = dict[i];
+            __syncwarp();
+        }
+    }
     for (uint32_t i0 = 0; i0 < nr; i0 += 32) {
         const uint32_t i = i0 + lane;
         int32_t key = -1;
@@ -1316,12 +1399,25 @@ __global__ void __launch_bounds__(128) k_str_offsets(const StrCol* __restrict__ 
         const uint64_t inc = warp_incl_scan64(l, lane);
         const uint64_t abs0 = run + inc - l;
         if (i < nr) offs[i] = (int32_t)(abs0 - bbase);
-        if (c.mode == 1 && key >= 0 && data) {
-            const uint8_t* sp = dict + doff[key];
-            uint8_t* dp = data + abs0;
-            for (uint32_t k = 0; k < l; k++) dp[k] = sp[k];
+        const uint32_t B = (uint32_t)__shfl_sync(FULL, inc, 31);
+        if (c.mode == 1 && data) {
+            if (sdict && B <= STAGE_BYTES) {
+                if (key >= 0) {
+                    const uint32_t so = s_doff[key];
+                    const uint32_t ro = (uint32_t)(inc - l);
+                    for (uint32_t k = 0; k < l; k++) s_stage[ro + k] = s_ddata[so + k];
+                }
+                __syncwarp();
+                uint8_t* dp = data + run;
+                for (uint32_t k = lane; k < B; k += 32) dp[k] = s_stage[k];
+                __syncwarp();
+            } else if (key >= 0) {
+                const uint8_t* sp = dict + doff[key];
+                uint8_t* dp = data + abs0;
+                for (uint32_t k = 0; k < l; k++) dp[k] = sp[k];
+            }
         }
-        run += __shfl_sync(FULL, inc, 31);
+        run += B;
     }
     // closing offset of the batch
     const uint32_t brow0 = b * c.batch_size;
