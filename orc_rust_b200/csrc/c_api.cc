@@ -1,6 +1,7 @@
 // extern "C" boundary (include/orc_b200.h).  No exception, panic or abort crosses it.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -327,15 +328,18 @@ int orcb_decode_int_rle(int device, const uint8_t* in, size_t in_len, int versio
         s.flags = (is_signed ? SEG_SIGNED : 0) | (version == 1 ? SEG_RLE_V2 : 0);
         s.nbytes = (uint8_t)nbytes;
         s.out_kind = OUT_I64;
-        // exercise both code paths: with the sub-segment pre-pass when the request is large enough
-        const uint32_t nslots = (uint32_t)(n_values / SUB_VALUES + 2);
-        DevBuf dsub((size_t)nslots * sizeof(SubSeg));
-        CU(cudaMemset(dsub.p, 0, (size_t)nslots * sizeof(SubSeg)));
-        s.sub_base = 0;
-        s.sub_cap = nslots;
+        // same two kernels as the job path: header-walk pre-pass, then one warp per 32 runs
+        const uint32_t cap = (uint32_t)std::min<size_t>(in_len / 2 + 3, n_values + 2);
+        const uint32_t pool = (cap + 31) / 32 + 1;
+        DevBuf dtab((size_t)pool * 32 * sizeof(RunRec)), dblk((size_t)pool * sizeof(BlockRec)), dcnt(16);
+        CU(cudaMemset(dcnt.p, 0, 16));
+        s.run_cap = cap;
         CU(cudaMemcpy(dseg.p, &s, sizeof(s), cudaMemcpyHostToDevice));
-        int rc = launch_int_rle((Seg*)dseg.p, 1, n_values > 2 * SUB_VALUES ? (SubSeg*)dsub.p : nullptr, nslots, nullptr, nullptr,
-                                (uint32_t*)sr.err.p, (uint32_t*)mis.p, 0);
+        int rc = launch_rle_index((Seg*)dseg.p, 1, nullptr, (RunRec*)dtab.p, (BlockRec*)dblk.p, (uint32_t*)dcnt.p, pool,
+                                  (uint32_t*)sr.err.p, 0);
+        if (rc) fail(ORCB_CUDA, cudaGetErrorString((cudaError_t)rc));
+        rc = launch_int_rle((Seg*)dseg.p, (BlockRec*)dblk.p, (uint32_t*)dcnt.p, pool, (RunRec*)dtab.p, nullptr, nullptr,
+                            (uint32_t*)sr.err.p, (uint32_t*)mis.p, 0);
         if (rc) fail(ORCB_CUDA, cudaGetErrorString((cudaError_t)rc));
         sr.check();
         if (n_values) CU(cudaMemcpy(out, dout.p, n_values * 8, cudaMemcpyDeviceToHost));

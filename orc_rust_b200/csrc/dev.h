@@ -41,24 +41,25 @@ struct Seg {
     uint8_t out_kind;
     uint8_t pad0;
     uint32_t aux;
-    // sub-segment slots of this segment in the SubSeg table (filled by k_rle_index)
-    uint32_t sub_base;
-    uint32_t sub_cap;
+    uint32_t run_base;   // unused (run blocks are allocated dynamically by k_rle_index)
+    uint32_t run_cap;
 };
 
-// A slice of a segment that starts at a run boundary found by the k_rle_index pre-pass: the unit of work
-// of one lane of k_int_rle.  Unused slots stay zero (n_values == 0).
-struct SubSeg {
-    uint32_t seg;
-    uint32_t start_byte;
-    uint32_t run_skip;
-    uint32_t n_values;
+// 32 consecutive runs of one segment: the unit of work of one warp of k_int_rle.  Allocated from a pool by
+// the k_rle_index pre-pass (one atomicAdd per 32 runs).
+struct BlockRec {
+    uint32_t seg;        // index into the short-run segment table
+    uint32_t n_runs;     // 1..32
+    uint32_t skip;       // values to skip in the block's first run (only the first block of a segment)
+    uint32_t pad;
+};
+
+// One run found by the k_rle_index header walk: where it starts and where its first emitted value goes.
+// The unit of work of one lane of k_int_rle.
+struct RunRec {
+    uint32_t byte_off;   // offset of the run header inside the stream
     uint32_t out_off;    // element offset from the segment's first output element
-    uint32_t pad[3];
 };
-
-// values per sub-segment (checkpoint spacing of the pre-pass)
-constexpr uint32_t SUB_VALUES = 256;
 
 // MSB-first boolean bytes -> LSB-first bitmap (+ popcount)
 struct BitSeg {

@@ -212,6 +212,9 @@ Job::~Job() {
     }
     if (h_meta_) cudaFreeHost(h_meta_);
     if (done_) cudaEventDestroy(done_);
+    if (ev_fork_) cudaEventDestroy(ev_fork_);
+    if (ev_join_) cudaEventDestroy(ev_join_);
+    if (aux_stream_) cudaStreamDestroy(aux_stream_);
     if (own_stream_ && stream_) cudaStreamDestroy(stream_);
     // device arenas are released by dev_keepalive_ (shared with exported device batches)
 }
@@ -257,6 +260,38 @@ bool is_utc_zone(const std::string& z) {
     return false;
 }
 
+// Scheduling hint only: do the first few RLE v2 runs at `pos` all hold more than 64 values?  (Header walk,
+// no values decoded.)  Such segments go to the warp-per-segment kernel.
+bool rle2_opens_with_long_runs(const uint8_t* s, uint32_t len, uint32_t pos) {
+    static const int W[32] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 26, 28, 30, 32, 40, 48, 56, 64};
+    for (int r = 0; r < 8; r++) {
+        if (pos + 4 > len) return r > 0;
+        const uint32_t h = s[pos], kind = h >> 6;
+        if (kind == 0) return false;
+        const uint32_t rl = (((h & 1) << 8) | s[pos + 1]) + 1;
+        if (rl <= 64) return false;
+        const uint32_t code = (h >> 1) & 31;
+        if (kind == 1) {
+            pos += 2 + (rl * W[code] + 7) / 8;
+        } else if (kind == 2) {
+            const uint32_t b3 = s[pos + 2], b4 = s[pos + 3];
+            const int pw = W[b3 & 31], pgw = ((b4 >> 5) & 7) + 1;
+            const int t = pw + pgw;
+            const int cfb = t <= 24 ? t : t <= 26 ? 26 : t <= 28 ? 28 : t <= 30 ? 30 : t <= 32 ? 32 : (t + 7) / 8 * 8;
+            pos += 4 + ((b3 >> 5) & 7) + 1 + (rl * W[code] + 7) / 8 + ((b4 & 31) * cfb + 7) / 8;
+        } else {
+            uint32_t p = pos + 2;
+            for (int v = 0; v < 2; v++) {
+                while (p < len && (s[p] & 0x80)) p++;
+                p++;
+            }
+            if (code) p += ((rl - 2) * W[code] + 7) / 8;
+            pos = p;
+        }
+    }
+    return true;
+}
+
 }  // namespace
 
 void Job::plan() {
@@ -265,7 +300,10 @@ void Job::plan() {
     task_first_cs_.clear();
     for (uint32_t t = 0; t < tasks_.size(); t++) plan_stripe(t);
 
-    if (n_sub_slots_) sub_table_ = alloc(AR_ZERO, (uint64_t)n_sub_slots_ * sizeof(SubSeg));
+    if (pool_blocks_) {
+        run_table_ = alloc(AR_TMP, (uint64_t)pool_blocks_ * 32 * sizeof(RunRec));
+        block_recs_ = alloc(AR_TMP, (uint64_t)pool_blocks_ * sizeof(BlockRec));
+    }
 
     // ---- descriptor blob layout
     auto place = [&](uint64_t& off, size_t bytes) {
@@ -302,6 +340,7 @@ void Job::plan() {
     splace(o_dstart_, (size_t)(n_cnt_ + 1) * 4);
     splace(o_mis_, (size_t)(n_colstripes_ + 1) * 4);
     splace(o_jobstate_, sizeof(JobState));
+    splace(o_nblocks_, 16);
     state_bytes_ = align_up(state_bytes_, 256);
 
     // ---- meta blob: err | nulls | ptr table | batch bases (batch_base_off were assigned relative to o_bbase_)
@@ -596,6 +635,13 @@ void Job::plan_stripe(uint32_t task_idx) {
         }
         const int32_t total_idx = has_present ? (int32_t)(cnt_base + n_groups) : -1;
 
+        // run-table slots of a short-run segment: every run is at least two bytes long and (bar corrupt
+        // row-index entries) emits at least one value
+        auto assign_run_slots = [&](Seg& sg, uint32_t n_bound, uint32_t span_bytes) {
+            const uint32_t cap = std::min(span_bytes / 2 + 3, n_bound + 2);
+            sg.run_cap = cap;
+            pool_blocks_ += (cap + 31) / 32;
+        };
         // helper: integer-RLE segments of one stream into `dst` (dense domain if has_present)
         auto add_int_segs = [&](StreamRef& sr, uint64_t dst, bool is_signed, int nbytes, OutKind okind, uint32_t aux,
                                 bool per_group_counts) {
@@ -626,17 +672,14 @@ void Job::plan_stripe(uint32_t task_idx) {
                 // compressed): segments that open with a long run go to the warp-per-segment kernel,
                 // everything else to the lane-per-segment kernel.  Purely a scheduling hint.
                 bool long_runs = false;
-                if (!compressed && v2 && sr.present && sg.start_byte + 2 <= sr.len) {
-                    const uint8_t* hp = fm.data + (sf.find(cid, &sr == &s_data ? S_DATA : (&sr == &s_length ? S_LENGTH : S_SECONDARY))->offset) + sg.start_byte;
-                    const uint32_t kind = hp[0] >> 6;
-                    const uint32_t rl = (((uint32_t)hp[0] & 1) << 8 | hp[1]) + 1;
-                    long_runs = kind != 0 && rl > 64;
+                if (!compressed && v2 && sr.present) {
+                    const uint8_t* sp = fm.data + (sf.find(cid, &sr == &s_data ? S_DATA : (&sr == &s_length ? S_LENGTH : S_SECONDARY))->offset);
+                    long_runs = rle2_opens_with_long_runs(sp, sr.len, sg.start_byte);
                 }
                 if (!long_runs) {
                     const uint32_t bound = (has_present && per_group_counts) ? rows_in_group(g) : sg.n_values;
-                    sg.sub_base = n_sub_slots_;
-                    sg.sub_cap = bound / SUB_VALUES + 2;
-                    n_sub_slots_ += sg.sub_cap;
+                    const uint32_t span = (g + 1 < ng ? en[g + 1].byte : sr.len) - std::min(en[g].byte, sr.len);
+                    assign_run_slots(sg, bound, span);
                 }
                 (long_runs ? int_big_segs_ : int_segs_).push_back(sg);
                 static const uint32_t ow1[6] = {2, 4, 8, 4, 4, 1};
@@ -830,9 +873,7 @@ void Job::plan_stripe(uint32_t task_idx) {
                         sg.nbytes = 8;
                         sg.out_kind = OUT_LEN31;
                         sg.aux = ORCB_OFFSET_OVERFLOW;
-                        sg.sub_base = n_sub_slots_;
-                        sg.sub_cap = enc.dict_size / SUB_VALUES + 2;
-                        n_sub_slots_ += sg.sub_cap;
+                        assign_run_slots(sg, enc.dict_size, s_length.len);
                         int_segs_.push_back(sg);
                         n_segments_ += 1;
                     }
@@ -943,6 +984,9 @@ void Job::stage() {
         stream_ = opt_.stream;
     }
     CUDA_OK(cudaEventCreateWithFlags(&done_, cudaEventDisableTiming));
+    CUDA_OK(cudaStreamCreateWithFlags(&aux_stream_, cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming));
     auto arenas = std::make_shared<DeviceArenas>();
     arenas->device = opt_.device;
     for (int a = 1; a < 8; a++) {
@@ -1045,14 +1089,15 @@ void Job::launch() {
     };
 #define N(v) ((uint32_t)(v).size())
     for (auto& k : kstats_) k.ran = false;
+    cudaStream_t cur_st = st;
     auto run = [&](const char* name, uint64_t alg_bytes, uint64_t work, int nk, auto&& fn) {
         KStat& k = kstat(name);
         k.alg_bytes = alg_bytes;
         k.work = work;
         k.ran = true;
-        CUDA_OK(cudaEventRecord(k.e0, st));
+        CUDA_OK(cudaEventRecord(k.e0, cur_st));
         chk(fn(), name);
-        CUDA_OK(cudaEventRecord(k.e1, st));
+        CUDA_OK(cudaEventRecord(k.e1, cur_st));
         launches += nk;
     };
     if (N(chunks_))
@@ -1066,14 +1111,28 @@ void Job::launch() {
         run("k_byte_rle", ab_byte_, N(data_byte_segs_), 1, [&] { return launch_byte_rle((Seg*)(d_desc_ + o_dbyte_), N(data_byte_segs_), cnt, dstart, err, st); });
     if (N(data_bit_segs_))
         run("k_bits", ab_bits_, N(data_bit_segs_), 1, [&] { return launch_bits((BitSeg*)(d_desc_ + o_dbit_), N(data_bit_segs_), cnt, dstart, st); });
+    // fork: the header-walk pre-pass is a long dependent chain on few warps, so it runs beside the
+    // bandwidth-heavy kernels on a second stream and joins before the epilogues
+    const bool forked = N(int_segs_) > 0;
+    if (forked) {
+        CUDA_OK(cudaEventRecord(ev_fork_, st));
+        CUDA_OK(cudaStreamWaitEvent(aux_stream_, ev_fork_, 0));
+        cur_st = aux_stream_;
+        RunRec* rtab = (RunRec*)(uintptr_t)reloc(run_table_);
+        BlockRec* brec = (BlockRec*)(uintptr_t)reloc(block_recs_);
+        uint32_t* nblk = (uint32_t*)(d_state_ + o_nblocks_);
+        run("k_rle_index", 0, N(int_segs_), 1, [&] { return launch_rle_index((Seg*)(d_desc_ + o_int_), N(int_segs_), cnt, rtab, brec, nblk, pool_blocks_, err, aux_stream_); });
+        run("k_int_rle", ab_int_, pool_blocks_, 1, [&] { return launch_int_rle((Seg*)(d_desc_ + o_int_), brec, nblk, pool_blocks_, rtab, cnt, dstart, err, mis, aux_stream_); });
+        CUDA_OK(cudaEventRecord(ev_join_, aux_stream_));
+        cur_st = st;
+    }
     if (N(int_big_segs_))
         run("k_int_rle_coop", ab_intbig_, N(int_big_segs_), 1, [&] { return launch_int_rle_coop((Seg*)(d_desc_ + o_intbig_), N(int_big_segs_), cnt, dstart, err, mis, st); });
-    if (N(int_segs_))
-        run("k_rle_index+k_int_rle", ab_int_, N(int_segs_), 2, [&] { return launch_int_rle((Seg*)(d_desc_ + o_int_), N(int_segs_), (SubSeg*)(uintptr_t)reloc(sub_table_), n_sub_slots_, cnt, dstart, err, mis, st); });
     if (N(var_segs_))
         run("k_varint128", ab_var_, N(var_segs_), 1, [&] { return launch_varint128((Seg*)(d_desc_ + o_var_), N(var_segs_), cnt, dstart, err, st); });
     if (N(copy_tiles_))
         run("k_copy", ab_copy_, N(copy_tiles_), 1, [&] { return launch_copy((CopyDesc*)(d_desc_ + o_copy_), (uint2*)(d_desc_ + o_ctile_), N(copy_tiles_), cnt, err, st); });
+    if (forked) CUDA_OK(cudaStreamWaitEvent(st, ev_join_, 0));
     if (N(decfix_))
         run("k_decimal_fix", ab_dec_, N(decfix_), 1, [&] { return launch_decimal_fix((DecFixDesc*)(d_desc_ + o_dec_), N(decfix_), cnt, mis, st); });
     if (N(ts_))

@@ -107,8 +107,8 @@ class Job {
     std::vector<StrCol> strcols_;
     std::vector<RepackDesc> repacks_;
     std::vector<ChunkDesc> chunks_;
-    uint32_t str_tiles_ = 0, repack_work_ = 0, n_sub_slots_ = 0;
-    uint64_t sub_table_ = 0;  // AR_ZERO offset of the SubSeg table
+    uint32_t str_tiles_ = 0, repack_work_ = 0, pool_blocks_ = 0;  // capacity of the run-block pool
+    uint64_t run_table_ = 0, block_recs_ = 0;  // AR_TMP offsets: RunRec table (32 per block), BlockRec table
 
     // stage copies: (file ptr, file offset, AR_IN offset, bytes)
     struct StageCopy {
@@ -128,7 +128,7 @@ class Job {
     // state blob (device only, zeroed per launch): cnt[], dstart[], mis[], JobState
     uint32_t n_cnt_ = 0, n_colstripes_ = 0;
     uint8_t* d_state_ = nullptr;
-    uint64_t state_bytes_ = 0, o_cnt_ = 0, o_dstart_ = 0, o_mis_ = 0, o_jobstate_ = 0;
+    uint64_t state_bytes_ = 0, o_cnt_ = 0, o_dstart_ = 0, o_mis_ = 0, o_jobstate_ = 0, o_nblocks_ = 0;
     // meta blob (device, zeroed per launch, copied to host at finish): err[], nulls[], ptr_table[], batch_base[]
     uint8_t* d_meta_ = nullptr;
     uint8_t* h_meta_ = nullptr;  // pinned
@@ -156,6 +156,8 @@ class Job {
     uint64_t ab_decomp_ = 0, ab_present_ = 0, ab_byte_ = 0, ab_bits_ = 0, ab_int_ = 0, ab_intbig_ = 0, ab_var_ = 0, ab_copy_ = 0,
              ab_spaced_ = 0, ab_dec_ = 0, ab_ts_ = 0, ab_str_ = 0, ab_repack_ = 0;
 
+    cudaStream_t aux_stream_ = nullptr;  // latency-bound pre-pass + short-run integer decode overlap the rest
+    cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr;
     cudaStream_t stream_ = nullptr;
     bool own_stream_ = false;
     cudaEvent_t done_ = nullptr;

@@ -6,6 +6,7 @@
 // OrcbStatus.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 
 #include "dev.h"
@@ -166,6 +167,59 @@ __device__ __forceinline__ uint32_t parse_varint(const uint8_t* in, uint32_t& p,
 }
 
 
+// DIRECT run of width <= 32 spread over the warp: lane handles values first, first+32, ...  Because 32*w bits
+// is a whole number of 32-bit words, the bit phase of a lane never changes inside a run: per value this is
+// two word loads, one funnel shift, one shift, the zigzag and a store.
+template <typename OutT, bool SIGNED, bool CHECK31>
+__device__ __forceinline__ void direct32_lane_loop(const uint8_t* data, int w, uint32_t first, uint32_t i_end, OutT* outp,
+                                                   uint32_t* err, uint32_t colstripe, uint32_t aux) {
+    if (first >= i_end) return;
+    const uint32_t bit0 = first * (uint32_t)w;
+    const uintptr_t ai = (uintptr_t)(data + (bit0 >> 3));
+    const uint32_t* q = (const uint32_t*)(ai & ~(uintptr_t)3);
+    const uint32_t sh = ((uint32_t)(ai & 3) << 3) + (bit0 & 7);
+    const int rs = 32 - w;
+    bool bad = false;
+    auto conv = [&](uint32_t lo, uint32_t hi) -> OutT {
+        const uint32_t x = __funnelshift_l(bswap32(hi), bswap32(lo), sh) >> rs;
+        if (CHECK31 && x > 0x7fffffffu) bad = true;
+        if (SIGNED) return (OutT)(int32_t)((x >> 1) ^ (0u - (x & 1)));
+        return (OutT)x;
+    };
+    uint32_t i = first;
+    for (; i + 224 < i_end; i += 256) {
+        uint32_t lo[8], hi[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            lo[u] = __ldg(q + u * w);
+            hi[u] = __ldg(q + u * w + 1);
+        }
+        q += 8 * w;
+#pragma unroll
+        for (int u = 0; u < 8; u++) outp[32 * u] = conv(lo[u], hi[u]);
+        outp += 256;
+    }
+    for (; i + 96 < i_end; i += 128) {
+        const uint32_t a0 = __ldg(q), a1 = __ldg(q + 1);
+        const uint32_t b0 = __ldg(q + w), b1 = __ldg(q + w + 1);
+        const uint32_t c0 = __ldg(q + 2 * w), c1 = __ldg(q + 2 * w + 1);
+        const uint32_t d0 = __ldg(q + 3 * w), d1 = __ldg(q + 3 * w + 1);
+        q += 4 * w;
+        outp[0] = conv(a0, a1);
+        outp[32] = conv(b0, b1);
+        outp[64] = conv(c0, c1);
+        outp[96] = conv(d0, d1);
+        outp += 128;
+    }
+    for (; i < i_end; i += 32) {
+        const uint32_t a0 = __ldg(q), a1 = __ldg(q + 1);
+        q += w;
+        outp[0] = conv(a0, a1);
+        outp += 32;
+    }
+    if (CHECK31 && bad) set_err(err, colstripe, aux);
+}
+
 // ------------------------------------------------------------------------------------------------
 // RLE v2, ONE run decoded by all 32 lanes (integer/rle_v2/{direct,patched_base,delta}.rs).
 // All arguments are warp-uniform.  Values i in [skip, skip+take) go to out_pos + (i - skip).
@@ -205,19 +259,26 @@ __device__ uint32_t coop_run2(const SegCtx& c, uint32_t cur, uint32_t skip, uint
         const uint8_t* data = in + cur + 2;
         const uint32_t i_end = min(rl, skip + take);
         // four values per lane per step, all loads issued before the first store (memory-level parallelism)
-        if (w <= 32 && (nb > 2 || w <= 16)) {
-            for (uint32_t i0 = skip + lane; i0 < i_end; i0 += 128) {
-                uint32_t raw[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const uint32_t i = i0 + 32u * u;
-                    raw[u] = i < i_end ? load_be_bits32(data, i * (uint32_t)w, w) : 0u;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const uint32_t i = i0 + 32u * u;
-                    if (i < i_end) store_val(c, out_pos + (i - skip), finish32(raw[u], sg, nb));
-                }
+        if (w <= 32 && (sg || nb == 8) && s.out_kind <= OUT_LEN31 && !(sg && s.out_kind == OUT_LEN31)) {
+            const uint32_t first = skip + lane;
+            const uint64_t o = out_pos + lane;
+            switch (s.out_kind) {
+                case OUT_I16:
+                    if (sg) direct32_lane_loop<int16_t, true, false>(data, w, first, i_end, (int16_t*)s.out + o, c.err, s.colstripe, s.aux);
+                    else direct32_lane_loop<int16_t, false, false>(data, w, first, i_end, (int16_t*)s.out + o, c.err, s.colstripe, s.aux);
+                    break;
+                case OUT_I32:
+                    if (sg) direct32_lane_loop<int32_t, true, false>(data, w, first, i_end, (int32_t*)s.out + o, c.err, s.colstripe, s.aux);
+                    else direct32_lane_loop<int32_t, false, false>(data, w, first, i_end, (int32_t*)s.out + o, c.err, s.colstripe, s.aux);
+                    break;
+                case OUT_I64:
+                    if (sg) direct32_lane_loop<int64_t, true, false>(data, w, first, i_end, (int64_t*)s.out + o, c.err, s.colstripe, s.aux);
+                    else direct32_lane_loop<int64_t, false, false>(data, w, first, i_end, (int64_t*)s.out + o, c.err, s.colstripe, s.aux);
+                    break;
+                default:  // OUT_LEN31: unsigned lengths / keys
+                    if (sg) direct32_lane_loop<int32_t, true, true>(data, w, first, i_end, (int32_t*)s.out + o, c.err, s.colstripe, s.aux);
+                    else direct32_lane_loop<int32_t, false, true>(data, w, first, i_end, (int32_t*)s.out + o, c.err, s.colstripe, s.aux);
+                    break;
             }
         } else {
             for (uint32_t i0 = skip + lane; i0 < i_end; i0 += 128) {
@@ -395,6 +456,8 @@ __device__ uint32_t coop_run2(const SegCtx& c, uint32_t cur, uint32_t skip, uint
 // time by the whole warp (coop_run2).
 // ------------------------------------------------------------------------------------------------
 enum RunClass : uint32_t { RC_NONE = 0, RC_CONST = 1, RC_DIRECT = 2, RC_COOP = 3 };
+constexpr uint32_t TILE_VALUES = 512;   // values of one 32-run block staged in shared memory (fast block path)
+constexpr uint32_t COOP_MIN_RUN = 96;  // DIRECT runs at least this long are decoded by the whole warp
 
 struct RunSlot {       // one per lane, in shared memory
     uint64_t base;     // RC_CONST: value at k = 0
@@ -449,6 +512,10 @@ __device__ __forceinline__ uint32_t parse_run2(const Seg& s, uint32_t cur, RunSl
         if (nb * 8 < w) return ORCB_OUT_OF_SPEC;
         bytes_out = 2 + (rl * (uint32_t)w + 7) / 8;
         if (cur + bytes_out > len) return ORCB_IO_ERROR;
+        if (rl >= COOP_MIN_RUN) {
+            cls = RC_COOP;  // long run: the constant-phase warp loop of coop_run2 is cheaper per value
+            return 0;
+        }
         d.data = (uint64_t)(uintptr_t)(in + cur + 2);
         d.meta = (uint32_t)w;
         cls = RC_DIRECT;
@@ -553,35 +620,49 @@ __device__ __forceinline__ uint32_t measure_run(const Seg& s, uint32_t cur, uint
         bytes_out = p - cur;
         return 0;
     }
-    const uint32_t hdr = (uint32_t)load_be_bits(in + cur, 0, 32);
-    const uint32_t h0 = hdr >> 24;
+    // One 8-byte window serves every common header: SHORT_REPEAT / DIRECT need 2 bytes, DELTA needs the
+    // two varints that follow (found with a continuation-bit mask instead of a byte loop).
+    const uintptr_t ai = (uintptr_t)(in + cur);
+    const uint32_t* q = (const uint32_t*)(ai & ~(uintptr_t)3);
+    const uint32_t shb = (uint32_t)(ai & 3) * 8;
+    const uint32_t q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+    const uint32_t lo = __funnelshift_r(q0, q1, shb);  // stream bytes 0..3 (little-endian lanes)
+    const uint32_t hi = __funnelshift_r(q1, q2, shb);  // stream bytes 4..7
+    const uint32_t h0 = lo & 255, b1 = (lo >> 8) & 255;
     const uint32_t kind = h0 >> 6;
-    if (kind == 0) {
-        rl_out = (h0 & 7) + 3;
-        bytes_out = 2 + ((h0 >> 3) & 7);
-    } else {
-        const uint32_t rl = (((h0 & 1) << 8) | ((hdr >> 16) & 255)) + 1;
-        const uint32_t code = (h0 >> 1) & 31;
-        rl_out = rl;
-        if (kind == 1) {
-            bytes_out = 2 + (rl * (uint32_t)width_of(code) + 7) / 8;
-        } else if (kind == 2) {
-            const uint32_t b3 = (hdr >> 8) & 255, b4 = hdr & 255;
+    const uint32_t code = (h0 >> 1) & 31;
+    const uint32_t rl = (((h0 & 1) << 8) | b1) + 1;
+    const uint32_t w = code < 24 ? code + 1 : (uint32_t)(0x40383028201E1C1Aull >> ((code - 24) * 8)) & 0xffu;
+    rl_out = kind == 0 ? (h0 & 7) + 3 : rl;
+    bytes_out = kind == 0 ? 2 + ((h0 >> 3) & 7) : 2 + (rl * w + 7) / 8;
+    if (kind >= 2) {
+        if (kind == 2) {
+            const uint32_t b3 = (lo >> 16) & 255, b4 = lo >> 24;
             const int pw = width_of(b3 & 31), pgw = (int)((b4 >> 5) & 7) + 1;
             if (pw + pgw > 64) return ORCB_OUT_OF_SPEC;
-            bytes_out = 4 + ((b3 >> 5) & 7) + 1 + (rl * (uint32_t)width_of(code) + 7) / 8 +
-                        ((b4 & 31) * (uint32_t)closest_fixed_bits(pw + pgw) + 7) / 8;
+            bytes_out = 4 + ((b3 >> 5) & 7) + 1 + (rl * w + 7) / 8 + ((b4 & 31) * (uint32_t)closest_fixed_bits(pw + pgw) + 7) / 8;
         } else {
-            uint32_t p = cur + 2;
-            for (int i = 0; i < 2; i++) {
-                for (;;) {
-                    if (p >= len) return ORCB_IO_ERROR;
-                    if (!(in[p++] & 0x80)) break;
+            // terminator bytes (bit 7 clear) among stream bytes 2..7
+            const uint64_t win = ((uint64_t)hi << 32) | lo;
+            uint64_t term = ~win & 0x8080808080800000ull;
+            uint32_t p;
+            const int t1 = __ffsll((long long)term);  // 1-based bit index of the first terminator's bit 7
+            term &= term - 1;
+            const int t2 = __ffsll((long long)term);
+            if (t1 && t2) {
+                p = cur + (uint32_t)(t2 >> 3);  // byte after the second varint
+            } else {
+                p = cur + 2;
+                for (int i = 0; i < 2; i++) {
+                    for (;;) {
+                        if (p >= len) return ORCB_IO_ERROR;
+                        if (!(in[p++] & 0x80)) break;
+                    }
                 }
             }
             if (code != 0) {
                 if (rl < 2) return ORCB_IO_ERROR;
-                p += ((rl - 2) * (uint32_t)width_of(code) + 7) / 8;
+                p += ((rl - 2) * w + 7) / 8;
             }
             bytes_out = p - cur;
         }
@@ -590,248 +671,272 @@ __device__ __forceinline__ uint32_t measure_run(const Seg& s, uint32_t cur, uint
     return 0;
 }
 
-// Pre-pass ("device-built row index"): one lane per segment walks the run headers only and drops a
-// checkpoint at the first run boundary after every SUB_VALUES values.  Gives k_int_rle short, independent
-// units even for streams of very short runs, and for files written without a row index.
+constexpr uint32_t IDX_LANES = 4;
+
+// Pre-pass ("device-built run index"): one lane per segment walks the run headers only and records where
+// every run starts and where its values go.  This is the only serial chain of the integer path (a run's
+// position depends on all runs before it); it is a few dozen instructions per run and produces no values,
+// so the decode proper (k_int_rle) runs as one fully parallel step of one run per lane.
 __global__ void __launch_bounds__(128) k_rle_index(const Seg* __restrict__ segs, uint32_t nseg,
-                                                   const uint32_t* __restrict__ cnt, SubSeg* subs, uint32_t* err) {
-    const uint32_t segi = blockIdx.x * blockDim.x + threadIdx.x;
+                                                   const uint32_t* __restrict__ cnt, RunRec* __restrict__ table,
+                                                   BlockRec* __restrict__ blocks, uint32_t* __restrict__ nblocks,
+                                                   uint32_t pool_blocks, uint32_t* err) {
+    // only IDX_LANES lanes of each warp own a segment: a warp advances at the pace of its slowest lane
+    // (the one that misses L1 this step), so fewer streams per warp and more warps hide more latency
+    const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((gt & 31) >= IDX_LANES) return;
+    const uint32_t segi = (gt >> 5) * IDX_LANES + (gt & 31);
     if (segi >= nseg) return;
     const Seg& s = segs[segi];
     const uint32_t n = s.cnt_idx >= 0 ? cnt[s.cnt_idx] : s.n_values;
-    if (n == 0 || s.sub_cap == 0) return;
-    SubSeg* out = subs + s.sub_base;
     uint32_t cur = s.start_byte, skip = s.run_skip, produced = 0;
-    uint32_t slot = 0, sub_start = cur, sub_skip = skip, sub_first = 0;
-    while (produced < n) {
-        if (cur >= s.in_len) break;  // reported by k_int_rle when it reaches this point
+    // a row-index position may skip more values than its first run holds (writers record positions while
+    // values are still buffered): step over the runs that are skipped entirely
+    while (skip > 0 && cur < s.in_len) {
         uint32_t rl, nbytes;
-        if (measure_run(s, cur, rl, nbytes)) break;
-        if (skip >= rl) {
-            skip -= rl;
-        } else {
-            produced += min(rl - skip, n - produced);
-            skip = 0;
-        }
+        if (measure_run(s, cur, rl, nbytes) || skip < rl) break;
+        skip -= rl;
         cur += nbytes;
-        if (produced - sub_first >= SUB_VALUES && produced < n && slot + 1 < s.sub_cap) {
-            SubSeg r;
-            r.seg = segi; r.start_byte = sub_start; r.run_skip = sub_skip; r.n_values = produced - sub_first;
-            r.out_off = sub_first; r.pad[0] = r.pad[1] = r.pad[2] = 0;
-            out[slot++] = r;
-            sub_start = cur;
-            sub_skip = 0;
-            sub_first = produced;
+    }
+    uint32_t blk = 0xffffffffu, in_blk = 0, blk_skip = skip;
+    uint32_t pf_next = cur & ~127u;
+    while (produced < n) {
+        if (cur + 256 >= pf_next) {
+            if (pf_next < s.in_len) asm volatile("prefetch.global.L1 [%0];" ::"l"((const uint8_t*)s.in + pf_next));
+            pf_next += 128;
+        }
+        if (in_blk == 0) {
+            blk = atomicAdd(nblocks, 1u);
+            if (blk >= pool_blocks) { set_err(err, s.colstripe, ORCB_UNEXPECTED); blk = 0xffffffffu; break; }
+        }
+        RunRec r;
+        r.byte_off = cur;
+        r.out_off = produced;
+        table[(uint64_t)blk * 32 + in_blk] = r;
+        in_blk++;
+        bool stop = cur >= s.in_len;  // k_int_rle reports "not enough values" for this record
+        uint32_t rl = 0, nbytes = 0;
+        if (!stop) stop = measure_run(s, cur, rl, nbytes) != 0;  // k_int_rle re-parses the run and reports the error
+        if (!stop) {
+            produced += min(rl > skip ? rl - skip : 0u, n - produced);
+            skip = 0;
+            cur += nbytes;
+        }
+        if (in_blk == 32 || stop || produced >= n) {
+            BlockRec br;
+            br.seg = segi;
+            br.n_runs = in_blk;
+            br.skip = blk_skip;
+            br.pad = 0;
+            blocks[blk] = br;
+            in_blk = 0;
+            blk_skip = 0;
+            if (stop) break;
         }
     }
-    // last slice: everything that is left (k_int_rle re-walks it and reports any error)
-    SubSeg r;
-    r.seg = segi; r.start_byte = sub_start; r.run_skip = sub_skip; r.n_values = n - sub_first;
-    r.out_off = sub_first; r.pad[0] = r.pad[1] = r.pad[2] = 0;
-    out[slot] = r;
 }
 
 constexpr int RLE_WARPS = 4;
-constexpr int SEGS_PER_WARP = 32;
-constexpr uint32_t SELF_MAX = 0;   // runs up to this long would be emitted by their own lane (measured slower: scattered stores)
 
-__global__ void __launch_bounds__(RLE_WARPS * 32) k_int_rle(const Seg* __restrict__ segs, uint32_t nunits,
-                                                            const SubSeg* __restrict__ subs,
+// Integer RLE decode proper: one warp per 32 consecutive runs of one segment (run table from k_rle_index).
+// One block of up to 32 consecutive runs of one segment, one run per lane.
+__device__ __forceinline__ void int_rle_block(const Seg* __restrict__ segs, const BlockRec br, const RunRec* __restrict__ recs,
+                                              const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ dstart,
+                                              uint32_t* err, uint32_t* mis, uint32_t* patchmap, RunSlot* slots,
+                                              int64_t* tile, const int lane) {
+    SegCtx c;
+    c.s = &segs[br.seg];
+    c.err = err;
+    c.mis = mis;
+    const Seg& s = *c.s;
+    bool active = (uint32_t)lane < br.n_runs;
+    const uint32_t n = s.cnt_idx >= 0 ? cnt[s.cnt_idx] : s.n_values;
+    const uint64_t obase = s.start_idx >= 0 ? dstart[s.start_idx] : s.out_start;
+    const bool v2 = (s.flags & SEG_RLE_V2) != 0;
+    RunRec rec;
+    rec.byte_off = 0;
+    rec.out_off = 0;
+    if (active) rec = recs[lane];
+    const uint32_t cur = rec.byte_off;
+    const uint32_t skip = lane == 0 ? br.skip : 0u;
+    const uint32_t room = n - rec.out_off;
+    const uint64_t out_pos = obase + rec.out_off;
+    __syncwarp();
+    RunSlot& my = slots[lane];
+    uint32_t cls = RC_NONE, rl = 0, nbytes = 0, take = 0;
+    if (active) {
+        uint32_t st;
+        my.meta = 0;
+        if (cur >= s.in_len) st = ORCB_OUT_OF_SPEC;  // "not enough values to decode" rle_v2/mod.rs:115-122
+        else if (v2) st = parse_run2(s, cur, my, cls, rl, nbytes);
+        else st = parse_run1(c, cur, skip, room, out_pos, my, cls, rl, nbytes, take);
+        if (st) {
+            set_err(err, s.colstripe, st);
+            active = false;
+            cls = RC_NONE;
+        }
+        if (cls == RC_CONST || cls == RC_DIRECT) {
+            take = min(rl > skip ? rl - skip : 0u, room);
+            my.out_idx = out_pos;
+            my.skip = skip;
+            my.meta = (my.meta & 0xffu) | (cls << 8);
+        }
+    }
+    const uint32_t emit = (cls == RC_CONST || cls == RC_DIRECT) ? take : 0u;
+    const uint32_t incl = warp_incl_scan(emit, lane);
+    my.prefix = incl;
+    const uint32_t total = __shfl_sync(FULL, incl, 31);
+    const int nb = s.nbytes;
+    const bool sg = (s.flags & SEG_SIGNED) != 0;
+    const uint32_t okind = s.out_kind;
+    // ---- fast block: every run of the block is a short constant / direct run.  The 32 runs are consecutive
+    //      runs of one segment, so their values are contiguous in the output: each lane expands its own run
+    //      into a shared-memory tile, then the warp writes the tile with coalesced stores.
+    if (total <= TILE_VALUES && __all_sync(FULL, !active || cls == RC_CONST || cls == RC_DIRECT)) {
+        const uint32_t pe = incl - emit;
+        if (cls == RC_CONST) {
+            uint64_t v = my.base + (uint64_t)skip * my.step;
+            for (uint32_t j = 0; j < take; j++, v += my.step) tile[pe + j] = (int64_t)v;
+        } else if (cls == RC_DIRECT) {
+            const int w = (int)(my.meta & 0xff);
+            const uint8_t* data = (const uint8_t*)(uintptr_t)my.data;
+            if (w <= 32 && (nb > 2 || w <= 16)) {
+                for (uint32_t j = 0; j < take; j++)
+                    tile[pe + j] = finish32(load_be_bits32(data, (skip + j) * (uint32_t)w, w), sg, nb);
+            } else {
+                for (uint32_t j = 0; j < take; j++) {
+                    int64_t v = trunc_n((int64_t)load_be_bits(data, (skip + j) * (uint32_t)w, w), nb);
+                    if (sg) v = zigzag_n(v, nb);
+                    tile[pe + j] = v;
+                }
+            }
+        }
+        __syncwarp();
+        // first emitted value of the block = first active lane's position (lane 0 is always active here)
+        const uint64_t o0 = __shfl_sync(FULL, out_pos, 0);
+        bool bad = false;
+        switch (okind) {
+            case OUT_I16: for (uint32_t p = lane; p < total; p += 32) ((int16_t*)s.out)[o0 + p] = (int16_t)tile[p]; break;
+            case OUT_I32: for (uint32_t p = lane; p < total; p += 32) ((int32_t*)s.out)[o0 + p] = (int32_t)tile[p]; break;
+            case OUT_I64: for (uint32_t p = lane; p < total; p += 32) ((int64_t*)s.out)[o0 + p] = tile[p]; break;
+            case OUT_LEN31:
+                for (uint32_t p = lane; p < total; p += 32) {
+                    const int64_t v = tile[p];
+                    if ((uint64_t)v > 0x7fffffffull) bad = true;
+                    ((int32_t*)s.out)[o0 + p] = (int32_t)v;
+                }
+                if (bad) set_err(err, s.colstripe, s.aux);
+                break;
+            case OUT_SCALE:
+                for (uint32_t p = lane; p < total; p += 32) {
+                    const int64_t v = tile[p];
+                    if ((uint32_t)(int32_t)v != s.aux) bad = true;
+                    ((int32_t*)s.out)[o0 + p] = (int32_t)v;
+                }
+                if (bad) atomicOr(&mis[s.colstripe], 1u);
+                break;
+            default: break;
+        }
+        return;
+    }
+    __syncwarp();
+    // ---- general block: all lanes produce the values of all parsed runs, 4 values per lane per step, every
+    //      load issued before the first store.  out kind / N / signedness are per segment, hence warp-uniform.
+    for (uint32_t v0 = lane; v0 < total; v0 += 128) {
+        uint32_t li[4], jj[4];
+        uint64_t raw[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t v = v0 + 32u * u;
+            uint32_t l = 0;
+            if (v < total) {
+#pragma unroll
+                for (int stp = 16; stp > 0; stp >>= 1)
+                    if (slots[l + stp - 1].prefix <= v) l += stp;
+            }
+            li[u] = l;
+            const RunSlot& d = slots[l];
+            jj[u] = v - (l ? slots[l - 1].prefix : 0u);
+            const uint32_t meta = d.meta;
+            raw[u] = 0;
+            if (v < total && (meta >> 8) == RC_DIRECT) {
+                const int w = (int)(meta & 0xff);
+                if (w <= 32 && (nb > 2 || w <= 16))
+                    raw[u] = load_be_bits32((const uint8_t*)(uintptr_t)d.data, (d.skip + jj[u]) * (uint32_t)w, w);
+                else
+                    raw[u] = load_be_bits((const uint8_t*)(uintptr_t)d.data, (d.skip + jj[u]) * (uint32_t)w, w);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t v = v0 + 32u * u;
+            if (v >= total) continue;
+            const RunSlot& d = slots[li[u]];
+            const uint32_t meta = d.meta;
+            int64_t val;
+            if ((meta >> 8) == RC_CONST) {
+                val = (int64_t)(d.base + (uint64_t)(d.skip + jj[u]) * d.step);
+            } else {
+                const int w = (int)(meta & 0xff);
+                if (w <= 32 && (nb > 2 || w <= 16)) {
+                    val = finish32((uint32_t)raw[u], sg, nb);
+                } else {
+                    val = trunc_n((int64_t)raw[u], nb);
+                    if (sg) val = zigzag_n(val, nb);
+                }
+            }
+            const uint64_t idx = d.out_idx + jj[u];
+            switch (okind) {
+                case OUT_I16: ((int16_t*)s.out)[idx] = (int16_t)val; break;
+                case OUT_I32: ((int32_t*)s.out)[idx] = (int32_t)val; break;
+                case OUT_I64: ((int64_t*)s.out)[idx] = val; break;
+                case OUT_LEN31:
+                    if ((uint64_t)val > 0x7fffffffull) set_err(err, s.colstripe, s.aux);
+                    ((int32_t*)s.out)[idx] = (int32_t)val;
+                    break;
+                case OUT_SCALE:
+                    if ((uint32_t)(int32_t)val != s.aux) atomicOr(&mis[s.colstripe], 1u);
+                    ((int32_t*)s.out)[idx] = (int32_t)val;
+                    break;
+                default: break;
+            }
+        }
+    }
+    __syncwarp();
+    // ---- runs that need the whole warp (long DIRECT, DELTA with packed deltas, PATCHED_BASE)
+    uint32_t bigmask = __ballot_sync(FULL, active && cls == RC_COOP);
+    while (bigmask) {
+        const int leader = __ffs(bigmask) - 1;
+        bigmask &= bigmask - 1;
+        const uint32_t lcur = __shfl_sync(FULL, cur, leader);
+        const uint32_t lskip = __shfl_sync(FULL, skip, leader);
+        const uint32_t lroom = __shfl_sync(FULL, room, leader);
+        const uint64_t lout = __shfl_sync(FULL, out_pos, leader);
+        uint32_t crl = 0, cbytes = 0, ctake = 0;
+        const uint32_t st = coop_run2(c, lcur, lskip, lroom, lout, patchmap, crl, cbytes, ctake);
+        if (st && lane == leader) set_err(err, s.colstripe, st);
+    }
+}
+
+__global__ void __launch_bounds__(RLE_WARPS * 32) k_int_rle(const Seg* __restrict__ segs,
+                                                            const BlockRec* __restrict__ blocks,
+                                                            const uint32_t* __restrict__ nblocks_ptr,
+                                                            const RunRec* __restrict__ table,
                                                             const uint32_t* __restrict__ cnt,
                                                             const uint32_t* __restrict__ dstart, uint32_t* err,
                                                             uint32_t* mis) {
     __shared__ uint32_t patchmap_all[RLE_WARPS][16];
     __shared__ RunSlot slots_all[RLE_WARPS][32];
+    __shared__ int64_t tile_all[RLE_WARPS][TILE_VALUES];
+    const uint32_t nblocks = *nblocks_ptr;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
     uint32_t* patchmap = patchmap_all[threadIdx.x >> 5];
     RunSlot* slots = slots_all[threadIdx.x >> 5];
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    // unit = a whole segment (subs == nullptr) or one sub-segment slot written by k_rle_index
-    const uint32_t unit = warp * SEGS_PER_WARP + lane;
-    const bool have = lane < SEGS_PER_WARP && unit < nunits;
-    SubSeg sub;
-    sub.seg = have ? unit : 0;
-    sub.n_values = 0xffffffffu;
-    sub.out_off = 0;
-    if (subs && have) sub = subs[unit];
-    const uint32_t segi = sub.seg;
-    SegCtx c;
-    c.s = &segs[segi];
-    c.err = err;
-    c.mis = mis;
-    const Seg& s = *c.s;
-    uint32_t n = 0;
-    uint64_t obase = 0;
-    uint32_t cur = s.start_byte, skip = s.run_skip, produced = 0;
-    if (have) {
-        if (subs) {
-            n = sub.n_values;
-            cur = sub.start_byte;
-            skip = sub.run_skip;
-        } else {
-            n = s.cnt_idx >= 0 ? cnt[s.cnt_idx] : s.n_values;
-        }
-        obase = (uint64_t)(s.start_idx >= 0 ? dstart[s.start_idx] : s.out_start) + sub.out_off;
-    }
-    const bool v2 = (s.flags & SEG_RLE_V2) != 0;
-    bool active = have && n > 0;
-    RunSlot& my = slots[lane];
-    my.out = s.out;
-    my.colstripe = s.colstripe;
-    my.aux = s.aux;
-    const uint32_t meta_hi = ((uint32_t)s.out_kind << 12) | ((uint32_t)s.nbytes << 16) | ((s.flags & SEG_SIGNED) ? (1u << 24) : 0u);
-
-    while (__any_sync(FULL, active)) {
-        uint32_t cls = RC_NONE, rl = 0, nbytes = 0, take = 0;
-        bool parsed = false;
-        if (active) {
-            uint32_t st;
-            my.meta = 0;
-            if (cur >= s.in_len) st = ORCB_OUT_OF_SPEC;  // "not enough values to decode" rle_v2/mod.rs:115-122
-            else if (v2) st = parse_run2(s, cur, my, cls, rl, nbytes);
-            else st = parse_run1(c, cur, skip, n - produced, obase + produced, my, cls, rl, nbytes, take);
-            if (st) {
-                set_err(err, s.colstripe, st);
-                active = false;
-                cls = RC_NONE;
-            } else {
-                parsed = true;
-            }
-            if (cls == RC_CONST || cls == RC_DIRECT) {
-                take = min(rl > skip ? rl - skip : 0u, n - produced);
-                my.out_idx = obase + produced;
-                my.skip = skip;
-                my.meta = (my.meta & 0xffu) | (cls << 8) | meta_hi;
-            }
-        }
-        // short runs are written by their own lane; longer ones by the whole warp below
-        bool self = false;
-        if (SELF_MAX > 0 && (cls == RC_CONST || cls == RC_DIRECT) && take <= SELF_MAX) {
-            self = true;
-            const uint64_t o0 = obase + produced;
-            if (cls == RC_CONST) {
-                for (uint32_t j = 0; j < take; j++) store_val(c, o0 + j, (int64_t)(my.base + (uint64_t)(skip + j) * my.step));
-            } else {
-                const int w = (int)(my.meta & 0xff);
-                const int nb = s.nbytes;
-                const bool sg = (s.flags & SEG_SIGNED) != 0;
-                const uint8_t* data = (const uint8_t*)(uintptr_t)my.data;
-                if (w <= 32 && (nb > 2 || w <= 16)) {
-                    for (uint32_t j = 0; j < take; j++)
-                        store_val(c, o0 + j, finish32(load_be_bits32(data, (skip + j) * (uint32_t)w, w), sg, nb));
-                } else {
-                    for (uint32_t j = 0; j < take; j++) {
-                        int64_t v = trunc_n((int64_t)load_be_bits(data, (skip + j) * (uint32_t)w, w), nb);
-                        if (sg) v = zigzag_n(v, nb);
-                        store_val(c, o0 + j, v);
-                    }
-                }
-            }
-        }
-        const uint32_t emit = (!self && (cls == RC_CONST || cls == RC_DIRECT)) ? take : 0u;
-        const uint32_t incl = warp_incl_scan(emit, lane);
-        my.prefix = incl;
-        const uint32_t total = __shfl_sync(FULL, incl, 31);
-        __syncwarp();
-        // ---- all lanes produce the values of all parsed runs: 4 values per lane per step, every load
-        //      issued before the first store
-        for (uint32_t v0 = lane; v0 < total; v0 += 128) {
-            uint32_t li[4], jj[4];
-            uint64_t raw[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const uint32_t v = v0 + 32u * u;
-                uint32_t l = 0;
-                if (v < total) {
-#pragma unroll
-                    for (int stp = 16; stp > 0; stp >>= 1)
-                        if (slots[l + stp - 1].prefix <= v) l += stp;
-                }
-                li[u] = l;
-                const RunSlot& d = slots[l];
-                jj[u] = v - (l ? slots[l - 1].prefix : 0u);
-                const uint32_t meta = d.meta;
-                raw[u] = 0;
-                if (v < total && ((meta >> 8) & 0xf) == RC_DIRECT) {
-                    const int w = (int)(meta & 0xff);
-                    const int nbx = (int)((meta >> 16) & 0xff);
-                    if (w <= 32 && (nbx > 2 || w <= 16))
-                        raw[u] = load_be_bits32((const uint8_t*)(uintptr_t)d.data, (d.skip + jj[u]) * (uint32_t)w, w);
-                    else
-                        raw[u] = load_be_bits((const uint8_t*)(uintptr_t)d.data, (d.skip + jj[u]) * (uint32_t)w, w);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const uint32_t v = v0 + 32u * u;
-                if (v >= total) continue;
-                const RunSlot& d = slots[li[u]];
-                const uint32_t meta = d.meta;
-                const int nb = (int)((meta >> 16) & 0xff);
-                int64_t val;
-                if (((meta >> 8) & 0xf) == RC_CONST) {
-                    val = (int64_t)(d.base + (uint64_t)(d.skip + jj[u]) * d.step);
-                } else {
-                    const int w = (int)(meta & 0xff);
-                    if (w <= 32 && (nb > 2 || w <= 16)) {
-                        val = finish32((uint32_t)raw[u], (meta & (1u << 24)) != 0, nb);
-                    } else {
-                        val = trunc_n((int64_t)raw[u], nb);
-                        if (meta & (1u << 24)) val = zigzag_n(val, nb);
-                    }
-                }
-                const uint64_t idx = d.out_idx + jj[u];
-                switch ((meta >> 12) & 0xf) {
-                    case OUT_I16: ((int16_t*)d.out)[idx] = (int16_t)val; break;
-                    case OUT_I32: ((int32_t*)d.out)[idx] = (int32_t)val; break;
-                    case OUT_I64: ((int64_t*)d.out)[idx] = val; break;
-                    case OUT_LEN31:
-                        if ((uint64_t)val > 0x7fffffffull) set_err(err, d.colstripe, d.aux);
-                        ((int32_t*)d.out)[idx] = (int32_t)val;
-                        break;
-                    case OUT_SCALE:
-                        if ((uint32_t)(int32_t)val != d.aux) atomicOr(&mis[d.colstripe], 1u);
-                        ((int32_t*)d.out)[idx] = (int32_t)val;
-                        break;
-                    default: break;
-                }
-            }
-        }
-        __syncwarp();
-        // ---- runs that need the whole warp
-        uint32_t bigmask = __ballot_sync(FULL, active && cls == RC_COOP);
-        while (bigmask) {
-            const int leader = __ffs(bigmask) - 1;
-            bigmask &= bigmask - 1;
-            const uint32_t lseg = __shfl_sync(FULL, segi, leader);
-            const uint32_t lcur = __shfl_sync(FULL, cur, leader);
-            const uint32_t lskip = __shfl_sync(FULL, skip, leader);
-            const uint32_t lroom = __shfl_sync(FULL, n - produced, leader);
-            const uint64_t lout = __shfl_sync(FULL, obase + produced, leader);
-            SegCtx lc;
-            lc.s = &segs[lseg];
-            lc.err = err;
-            lc.mis = mis;
-            uint32_t crl = 0, cbytes = 0, ctake = 0;
-            const uint32_t st = coop_run2(lc, lcur, lskip, lroom, lout, patchmap, crl, cbytes, ctake);
-            if (lane == leader) {
-                if (st) {
-                    set_err(err, s.colstripe, st);
-                    active = false;
-                    parsed = false;
-                }
-                rl = crl;
-                nbytes = cbytes;
-                take = ctake;
-            }
-        }
-        if (active && parsed) {
-            if (skip >= rl) skip -= rl;
-            else { produced += take; skip = 0; }
-            cur += nbytes;
-        }
-        active = active && produced < n;
-    }
+    // persistent warps: the number of run blocks is only known on the device
+    for (uint32_t blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; blk < nblocks; blk += nwarps)
+        int_rle_block(segs, blocks[blk], table + (uint64_t)blk * 32, cnt, dstart, err, mis, patchmap, slots,
+                      tile_all[threadIdx.x >> 5], lane);
 }
 
 // Warp-per-segment variant for segments made of long runs (every run decoded by all 32 lanes).
@@ -853,6 +958,11 @@ __global__ void __launch_bounds__(RLE_WARPS * 32) k_int_rle_coop(const Seg* __re
     uint32_t cur = s.start_byte, skip = s.run_skip, produced = 0;
     while (produced < n) {
         if (cur >= s.in_len) { set_err(err, s.colstripe, ORCB_OUT_OF_SPEC); return; }
+        // pull the bytes of the following runs into L2 while this run is decoded (one line per lane, 4 KiB)
+        {
+            const uint32_t pf = cur + 2048u + 128u * (threadIdx.x & 31);
+            if (pf < s.in_len) asm volatile("prefetch.global.L2 [%0];" ::"l"((const uint8_t*)s.in + pf));
+        }
         uint32_t rl = 0, nbytes = 0, take = 0;
         const uint32_t st = coop_run2(c, cur, skip, n - produced, obase + produced, patchmap, rl, nbytes, take);
         if (st) { set_err(err, s.colstripe, st); return; }
@@ -1614,17 +1724,28 @@ static inline uint32_t blocks_for_warps(uint32_t nwarps, uint32_t warps_per_bloc
         if (_e != cudaSuccess) return (int)_e;   \
     } while (0)
 
-int launch_int_rle(const Seg* segs, uint32_t n, SubSeg* subs, uint32_t nslots, const uint32_t* cnt, const uint32_t* dstart,
-                   uint32_t* err, uint32_t* mis, cudaStream_t st) {
+int launch_rle_index(const Seg* segs, uint32_t n, const uint32_t* cnt, RunRec* table, BlockRec* blocks, uint32_t* nblocks,
+                     uint32_t pool_blocks, uint32_t* err, cudaStream_t st) {
     if (!n) return 0;
-    uint32_t units = n;
-    if (subs) {
-        k_rle_index<<<(n + 127) / 128, 128, 0, st>>>(segs, n, cnt, subs, err);
-        LAUNCH_CHECK();
-        units = nslots;
+    const uint32_t nwarps = (n + IDX_LANES - 1) / IDX_LANES;
+    k_rle_index<<<(nwarps + 3) / 4, 128, 0, st>>>(segs, n, cnt, table, blocks, nblocks, pool_blocks, err);
+    LAUNCH_CHECK();
+    return 0;
+}
+int launch_int_rle(const Seg* segs, const BlockRec* blocks, const uint32_t* nblocks, uint32_t pool_blocks, const RunRec* table,
+                   const uint32_t* cnt, const uint32_t* dstart, uint32_t* err, uint32_t* mis, cudaStream_t st) {
+    if (!pool_blocks) return 0;
+    // persistent grid: enough CTAs to fill every SM, never more warps than blocks could exist
+    static int ctas = 0;
+    if (!ctas) {
+        int dev = 0, sms = 148, per_sm = 8;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_int_rle, RLE_WARPS * 32, 0);
+        ctas = sms * (per_sm > 0 ? per_sm : 1);
     }
-    const uint32_t nwarps = (units + SEGS_PER_WARP - 1) / SEGS_PER_WARP;
-    k_int_rle<<<blocks_for_warps(nwarps, RLE_WARPS), RLE_WARPS * 32, 0, st>>>(segs, units, subs, cnt, dstart, err, mis);
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)ctas, ((uint64_t)pool_blocks + RLE_WARPS - 1) / RLE_WARPS);
+    k_int_rle<<<grid, RLE_WARPS * 32, 0, st>>>(segs, blocks, nblocks, table, cnt, dstart, err, mis);
     LAUNCH_CHECK();
     return 0;
 }

@@ -7,9 +7,11 @@
 
 namespace orcb {
 
-// subs != nullptr: run the k_rle_index pre-pass into `subs` (nslots zeroed entries) and decode per sub-segment
-int launch_int_rle(const Seg* segs, uint32_t n, SubSeg* subs, uint32_t nslots, const uint32_t* cnt, const uint32_t* dstart,
-                   uint32_t* err, uint32_t* mis, cudaStream_t st);
+// short-run integer path: header-walk pre-pass into the run table, then one warp per 32 runs
+int launch_rle_index(const Seg* segs, uint32_t n, const uint32_t* cnt, RunRec* table, BlockRec* blocks, uint32_t* nblocks,
+                     uint32_t pool_blocks, uint32_t* err, cudaStream_t st);
+int launch_int_rle(const Seg* segs, const BlockRec* blocks, const uint32_t* nblocks, uint32_t pool_blocks, const RunRec* table,
+                   const uint32_t* cnt, const uint32_t* dstart, uint32_t* err, uint32_t* mis, cudaStream_t st);
 int launch_int_rle_coop(const Seg* segs, uint32_t n, const uint32_t* cnt, const uint32_t* dstart, uint32_t* err,
                         uint32_t* mis, cudaStream_t st);
 int launch_byte_rle(const Seg* segs, uint32_t n, const uint32_t* cnt, const uint32_t* dstart, uint32_t* err,
