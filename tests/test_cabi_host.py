@@ -1,0 +1,150 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads, exports every symbol include/orc_b200.h
+declares, and the host half (file tail, schema mapping, stripe selection, launch planning, error mapping)
+behaves like the reference's builder.  No kernels are launched here."""
+import glob
+import os
+import re
+
+import pyarrow as pa
+import pytest
+
+from conftest import GOLDEN
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def ob():
+    import orc_rust_b200 as m
+    m.lib()
+    return m
+
+
+def test_library_exports_every_declared_symbol(ob):
+    hdr = open(os.path.join(ROOT, "include", "orc_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(orcb_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 30
+    L = ob.lib()
+    missing = [s for s in declared if not hasattr(L, s)]
+    assert not missing, f"library lacks {missing}"
+    assert set(declared) == set(ob.EXPORTED_SYMBOLS)
+    assert b"sm_100a" in L.orcb_build_info()
+
+
+def test_no_cpu_decode_fallback(ob):
+    """Without a CUDA device the decode entry points must fail loudly (status Cuda), never decode on the host."""
+    if ob.device_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(ob.OrcError) as e:
+        ob.decode_int_rle(bytes([0x0A, 0x27, 0x10]), 5, version=2, signed=False)
+    assert e.value.variant == "Cuda"
+    path = os.path.join(GOLDEN, "ref_basic", "test.orc")
+    with pytest.raises(ob.OrcError) as e:
+        next(iter(ob.ArrowReaderBuilder.try_new(path).build()))
+    assert e.value.variant == "Cuda"
+
+
+def test_file_metadata_matches_oracle_and_pyarrow(ob):
+    import pyarrow.orc as po
+    from oracle import orc_oracle as oo
+    for f in sorted(glob.glob(os.path.join(GOLDEN, "ref_*", "*.orc"))):
+        data = open(f, "rb").read()
+        try:
+            of = oo.OracleFile(data)
+        except oo.OracleError:
+            continue
+        if of.compression in (1, 3, 5) or not of.is_flat() or os.path.basename(f) == "orc_split_elim.orc":
+            continue
+        b = ob.ArrowReaderBuilder.try_new(data)
+        fm = b.file_metadata()
+        assert fm.number_of_rows == of.number_of_rows
+        assert fm.num_stripes == len(of.stripes)
+        assert fm.compression == of.compression
+        assert fm.column_names == [n for n, _ in of.columns]
+        for i, s in enumerate(of.stripes):
+            si = fm.stripe_info(i)
+            assert (si["offset"], si["index_length"], si["data_length"], si["footer_length"], si["number_of_rows"]) == \
+                (s.offset, s.index_length, s.data_length, s.footer_length, s.number_of_rows)
+        sch = b.schema()
+        assert sch.equals(of.schema(), check_metadata=False), f
+        ref = po.ORCFile(f).schema
+        for name in sch.names:  # same ORC -> Arrow mapping as the Apache reader for flat types
+            assert sch.field(name).type == ref.field(name).type or pa.types.is_timestamp(sch.field(name).type)
+            assert sch.field(name).nullable
+
+
+def test_schema_options(ob):
+    path = os.path.join(GOLDEN, "ref_basic", "pyarrow_timestamps.orc")
+    b = ob.ArrowReaderBuilder.try_new(path)
+    assert b.schema().field("timestamp_notz").type == pa.timestamp("ns")
+    assert b.schema().field("timestamp_utc").type == pa.timestamp("ns", tz="UTC")
+    b.with_timestamp_precision(ob.TimestampPrecision.Microsecond)
+    assert b.schema().field("timestamp_notz").type == pa.timestamp("us")
+    b = ob.ArrowReaderBuilder.try_new(os.path.join(GOLDEN, "ref_basic", "test.orc")).with_projection(["a", "d"])
+    assert b.schema().names == ["a", "d"]
+
+
+def test_error_mapping(ob):
+    with pytest.raises(ob.OrcError) as e:
+        ob.ArrowReaderBuilder.try_new(b"")
+    assert e.value.variant == "EmptyFile"
+    for name in ("alltypes.zlib.orc", "alltypes.zstd.orc", "alltypes.lzo.orc"):
+        with pytest.raises(ob.OrcError) as e:
+            ob.ArrowReaderBuilder.try_new(os.path.join(GOLDEN, "ref_basic", name))
+        assert e.value.variant == "UnsupportedDeviceCodec", name
+    with pytest.raises(ob.OrcError) as e:
+        ob.ArrowReaderBuilder.try_new(os.path.join(GOLDEN, "ref_basic", "nested_struct.orc")).schema()
+    assert e.value.variant == "NotImplemented"
+    with pytest.raises(ob.OrcError) as e:
+        ob.ArrowReaderBuilder.try_new(os.path.join(GOLDEN, "ref_integration", "orc_no_format.orc"))
+    assert e.value.variant == "OutOfSpec"
+    with pytest.raises(ob.OrcError) as e:
+        ob.ArrowReaderBuilder.try_new(b"not an orc file at all, just bytes")
+    assert e.value.variant in ("OutOfSpec", "DecodeProto")
+    with pytest.raises(ob.OrcError) as e:
+        ob.ArrowReaderBuilder.try_new("/nonexistent/file.orc")
+    assert e.value.variant == "IoError"
+
+
+def test_launch_plan_statistics(ob, tmp_path):
+    """The host planner batches every stream of every projected column of every stripe into one plan."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_orc
+    p = str(tmp_path / "li.orc")
+    gen_orc.write(gen_orc.lineitem_table(30_000, 0), p, stripe_size=16 << 20, row_index_stride=1000)
+    from oracle import orc_oracle as oo
+    of = oo.OracleFile(open(p, "rb").read())
+    job = ob.DecodeJob([p]).plan()
+    st = job.stats()
+    assert st["n_stripes"] == len(of.stripes) and st["n_rows"] == of.number_of_rows and st["n_columns"] == 16
+    assert st["n_batches"] == sum((s.number_of_rows + 8191) // 8192 for s in of.stripes)
+    # algorithmic input bytes = stored bytes of the projected non-index streams
+    exp = 0
+    for s in of.stripes:
+        streams, _, _ = of._stripe_footer(s)
+        exp += sum(x.length for x in streams if x.kind in (0, 1, 2, 3, 5) and x.column != 0)
+    assert st["input_bytes"] == exp
+    # one (stream, row group) segment per row-proportional stream and row group when the row index is used
+    groups = sum((s.number_of_rows + 999) // 1000 for s in of.stripes)
+    assert st["n_segments"] >= 20 * groups
+    no_idx = ob.DecodeJob([p], use_row_index=False).plan().stats()
+    assert no_idx["n_segments"] < st["n_segments"] and no_idx["n_segments"] >= 20 * len(of.stripes)
+    proj = ob.DecodeJob([p], projection=["l_orderkey", "l_comment"]).plan().stats()
+    assert proj["n_columns"] == 2 and proj["input_bytes"] < st["input_bytes"]
+
+
+def test_stripe_sharding_partitions_stripes(ob, tmp_path):
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_orc
+    p = str(tmp_path / "li.orc")
+    gen_orc.write(gen_orc.lineitem_table(40_000, 1), p, stripe_size=2 << 20)
+    total = ob.DecodeJob([p]).plan().stats()
+    assert total["n_stripes"] >= 4
+    for n in (2, 3, 8):
+        parts = [ob.DecodeJob([p], shard=(r, n)).plan().stats() for r in range(n)]
+        assert sum(x["n_stripes"] for x in parts) == total["n_stripes"]
+        assert sum(x["n_rows"] for x in parts) == total["n_rows"]
+        assert max(x["n_stripes"] for x in parts) - min(x["n_stripes"] for x in parts) <= 1  # round robin
