@@ -226,15 +226,31 @@ def main():
     kstats = job.kernel_stats()
     st = job.stats()
 
-    # ---- end-to-end through the C ABI: H2D + decode + metadata D2H every step
+    # ---- end-to-end through the C ABI: H2D + decode + metadata D2H every step.  The file set is split into a
+    #      few jobs, each on its own library stream, so the pinned H2D copy of group g+1 overlaps the decode of g.
+    del job
+    torch.cuda.synchronize()
+    n_groups = min(4, len(files))
+    groups = [files[i::n_groups] for i in range(n_groups)]
+    jobs = [ob.DecodeJob(g, device=local_rank, use_row_index=not args.no_row_index) for g in groups]
+    for j in jobs:
+        j.plan(); j.stage(); j.launch(); j.finish()
+    e2e_staged = sum(j.stats()["staged_bytes"] for j in jobs)
+    e2e_meta = sum(j.stats()["d2h_meta_bytes"] for j in jobs)
+
+    def e2e_step():
+        for j in jobs:
+            j.restage()
+            j.launch()
+        for j in jobs:
+            j.finish()
+
     for _ in range(2):
-        job.restage(); job.launch(); job.finish()
+        e2e_step()
     sync_all()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        job.restage()
-        job.launch()
-        job.finish()
+        e2e_step()
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
 
@@ -275,9 +291,10 @@ def main():
                    "segments_per_gpu": st["n_segments"], "input_bytes_per_gpu": in_bytes,
                    "arrow_bytes_per_gpu": out_bytes, "l2_policy": "inputs+outputs per step (>=13 GB) far exceed the 126 MB L2",
                    "row_index": not args.no_row_index, "dataset_gen_s": round(gen_s, 1)},
-        "e2e": {"value": e2e, "unit": "GB/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": st["staged_bytes"],
-                "d2h_bytes_per_step": st["d2h_meta_bytes"],
-                "note": "pinned H2D of all stripes + decode + D2H of per-batch metadata; Arrow buffers stay in HBM"},
+        "e2e": {"value": e2e, "unit": "GB/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": e2e_staged,
+                "d2h_bytes_per_step": e2e_meta,
+                "note": "pinned H2D of all stripes + decode + D2H of per-batch metadata (4 pipelined jobs); "
+                        "decoded Arrow stays in HBM"},
         "gpu_launches": st["n_kernel_launches"] * args.steps,
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clk.summary(),
     }
