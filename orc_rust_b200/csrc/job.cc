@@ -10,6 +10,7 @@
 #include "job.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "kernels.h"
@@ -303,6 +304,7 @@ void Job::plan() {
     if (pool_blocks_) {
         run_table_ = alloc(AR_TMP, (uint64_t)pool_blocks_ * 32 * sizeof(RunRec));
         block_recs_ = alloc(AR_TMP, (uint64_t)pool_blocks_ * sizeof(BlockRec));
+        slow_list_ = alloc(AR_TMP, (uint64_t)pool_blocks_ * 4 + 16);
     }
 
     // ---- descriptor blob layout
@@ -1113,17 +1115,22 @@ void Job::launch() {
         run("k_bits", ab_bits_, N(data_bit_segs_), 1, [&] { return launch_bits((BitSeg*)(d_desc_ + o_dbit_), N(data_bit_segs_), cnt, dstart, st); });
     // fork: the header-walk pre-pass is a long dependent chain on few warps, so it runs beside the
     // bandwidth-heavy kernels on a second stream and joins before the epilogues
+    // ORCB_SERIAL=1 keeps everything on one stream (clean per-kernel timings when profiling)
+    static const bool serial_env = getenv("ORCB_SERIAL") != nullptr;
     const bool forked = N(int_segs_) > 0;
+    cudaStream_t aux = serial_env ? st : aux_stream_;
     if (forked) {
-        CUDA_OK(cudaEventRecord(ev_fork_, st));
-        CUDA_OK(cudaStreamWaitEvent(aux_stream_, ev_fork_, 0));
-        cur_st = aux_stream_;
+        if (!serial_env) {
+            CUDA_OK(cudaEventRecord(ev_fork_, st));
+            CUDA_OK(cudaStreamWaitEvent(aux, ev_fork_, 0));
+        }
+        cur_st = aux;
         RunRec* rtab = (RunRec*)(uintptr_t)reloc(run_table_);
         BlockRec* brec = (BlockRec*)(uintptr_t)reloc(block_recs_);
         uint32_t* nblk = (uint32_t*)(d_state_ + o_nblocks_);
-        run("k_rle_index", 0, N(int_segs_), 1, [&] { return launch_rle_index((Seg*)(d_desc_ + o_int_), N(int_segs_), cnt, rtab, brec, nblk, pool_blocks_, err, aux_stream_); });
-        run("k_int_rle", ab_int_, pool_blocks_, 1, [&] { return launch_int_rle((Seg*)(d_desc_ + o_int_), brec, nblk, pool_blocks_, rtab, cnt, dstart, err, mis, aux_stream_); });
-        CUDA_OK(cudaEventRecord(ev_join_, aux_stream_));
+        run("k_rle_index", 0, N(int_segs_), 1, [&] { return launch_rle_index((Seg*)(d_desc_ + o_int_), N(int_segs_), cnt, rtab, brec, nblk, pool_blocks_, err, aux); });
+        run("k_int_rle(+general)", ab_int_, pool_blocks_, 2, [&] { return launch_int_rle((Seg*)(d_desc_ + o_int_), brec, nblk, pool_blocks_, rtab, cnt, dstart, err, mis, (uint32_t*)(uintptr_t)reloc(slow_list_), nblk + 1, aux); });
+        if (!serial_env) CUDA_OK(cudaEventRecord(ev_join_, aux));
         cur_st = st;
     }
     if (N(int_big_segs_))
@@ -1132,7 +1139,7 @@ void Job::launch() {
         run("k_varint128", ab_var_, N(var_segs_), 1, [&] { return launch_varint128((Seg*)(d_desc_ + o_var_), N(var_segs_), cnt, dstart, err, st); });
     if (N(copy_tiles_))
         run("k_copy", ab_copy_, N(copy_tiles_), 1, [&] { return launch_copy((CopyDesc*)(d_desc_ + o_copy_), (uint2*)(d_desc_ + o_ctile_), N(copy_tiles_), cnt, err, st); });
-    if (forked) CUDA_OK(cudaStreamWaitEvent(st, ev_join_, 0));
+    if (forked && !serial_env) CUDA_OK(cudaStreamWaitEvent(st, ev_join_, 0));
     if (N(decfix_))
         run("k_decimal_fix", ab_dec_, N(decfix_), 1, [&] { return launch_decimal_fix((DecFixDesc*)(d_desc_ + o_dec_), N(decfix_), cnt, mis, st); });
     if (N(ts_))

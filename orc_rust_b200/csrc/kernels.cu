@@ -457,6 +457,7 @@ __device__ uint32_t coop_run2(const SegCtx& c, uint32_t cur, uint32_t skip, uint
 // ------------------------------------------------------------------------------------------------
 enum RunClass : uint32_t { RC_NONE = 0, RC_CONST = 1, RC_DIRECT = 2, RC_COOP = 3 };
 constexpr uint32_t TILE_VALUES = 512;   // values of one 32-run block staged in shared memory (fast block path)
+constexpr uint32_t SELF_FILL = 10;      // runs up to this long (every SHORT_REPEAT) are expanded by their own lane
 constexpr uint32_t COOP_MIN_RUN = 96;  // DIRECT runs at least this long are decoded by the whole warp
 
 struct RunSlot {       // one per lane, in shared memory
@@ -473,15 +474,31 @@ struct RunSlot {       // one per lane, in shared memory
     uint32_t pad;
 };
 
+// up to 8 varint bytes (little-endian in x, continuation bits ignored) -> the 7-bit groups squeezed together
+__device__ __forceinline__ uint64_t squeeze7(uint64_t x) {
+    x &= 0x7f7f7f7f7f7f7f7full;
+    x = (x & 0x007f007f007f007full) | ((x & 0x7f007f007f007f00ull) >> 1);
+    x = (x & 0x00003fff00003fffull) | ((x & 0x3fff00003fff0000ull) >> 2);
+    x = (x & 0x000000000fffffffull) | ((x & 0x0fffffff00000000ull) >> 4);
+    return x;
+}
+
 // Parse the run at `cur` of the lane's own segment.  No values are produced here (except RLE v1 literals).
+// One 8-byte window of the stream serves the common headers without byte loops.
 __device__ __forceinline__ uint32_t parse_run2(const Seg& s, uint32_t cur, RunSlot& d, uint32_t& cls, uint32_t& rl_out,
                                                uint32_t& bytes_out) {
     const uint8_t* in = (const uint8_t*)s.in;
     const uint32_t len = s.in_len;
     const int nb = s.nbytes;
     const bool sg = (s.flags & SEG_SIGNED) != 0;
-    const uint32_t hdr = (uint32_t)load_be_bits(in + cur, 0, 32);
-    const uint32_t h0 = hdr >> 24;
+    const uintptr_t ai = (uintptr_t)(in + cur);
+    const uint32_t* q = (const uint32_t*)(ai & ~(uintptr_t)3);
+    const uint32_t shb = (uint32_t)(ai & 3) * 8;
+    const uint32_t q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+    const uint32_t lo = __funnelshift_r(q0, q1, shb);  // stream bytes 0..3, byte 0 in the low bits
+    const uint32_t hi = __funnelshift_r(q1, q2, shb);  // stream bytes 4..7
+    const uint64_t win = ((uint64_t)hi << 32) | lo;
+    const uint32_t h0 = lo & 255;
     const uint32_t kind = h0 >> 6;
     if (kind == 0) {
         // SHORT_REPEAT short_repeat.rs:29-63
@@ -490,7 +507,15 @@ __device__ __forceinline__ uint32_t parse_run2(const Seg& s, uint32_t cur, RunSl
         rl_out = (h0 & 7) + 3;
         bytes_out = 1 + bw;
         if (cur + bytes_out > len) return ORCB_IO_ERROR;
-        const uint64_t raw = bw <= 3 ? (uint64_t)((hdr & 0xffffffu) >> (8 * (3 - bw))) : load_be_bits(in + cur + 1, 0, bw * 8);
+        uint64_t raw;
+        if (bw <= 7) {
+            // big-endian value of stream bytes 1..bw: byte-reverse the window past the header
+            const uint64_t t = win >> 8;
+            const uint64_t rev = ((uint64_t)bswap32((uint32_t)t) << 32) | bswap32((uint32_t)(t >> 32));
+            raw = rev >> (64 - 8 * bw);
+        } else {
+            raw = load_be_bits(in + cur + 1, 0, 64);
+        }
         int64_t v = trunc_n((int64_t)raw, nb);
         if (sg) v = zigzag_n(v, nb);
         d.base = (uint64_t)v;
@@ -503,7 +528,7 @@ __device__ __forceinline__ uint32_t parse_run2(const Seg& s, uint32_t cur, RunSl
         return 0;
     }
     if (cur + 2 > len) return ORCB_IO_ERROR;
-    const uint32_t rl = (((h0 & 1) << 8) | ((hdr >> 16) & 255)) + 1;
+    const uint32_t rl = (((h0 & 1) << 8) | ((lo >> 8) & 255)) + 1;
     const uint32_t code = (h0 >> 1) & 31;
     rl_out = rl;
     if (kind == 1) {
@@ -526,23 +551,50 @@ __device__ __forceinline__ uint32_t parse_run2(const Seg& s, uint32_t cur, RunSl
         cls = RC_COOP;  // packed deltas need a prefix sum
         return 0;
     }
-    uint32_t p = cur + 2;
     uint64_t ub, ud;
-    uint32_t e = parse_varint(in, p, len, nb * 8, ub);
-    if (e) return e;
+    uint32_t p;
+    {
+        // both varints inside the window (terminators among stream bytes 2..7)?
+        uint64_t term = ~win & 0x8080808080800000ull;
+        const int t1 = __ffsll((long long)term);
+        term &= term - 1;
+        const int t2 = __ffsll((long long)term);
+        const uint32_t e1 = (uint32_t)(t1 >> 3), e2 = (uint32_t)(t2 >> 3);  // byte index after each varint
+        if (t1 && t2) {
+            const uint64_t x = win >> 16;                                   // bytes 2..7
+            const uint32_t n1 = e1 - 2, n2 = e2 - e1;
+            // read_varint::<N>: a byte at shift >= bit-width(N) is an error even when zero (util.rs:486-489)
+            if ((n1 - 1) * 7 >= (uint32_t)nb * 8) return ORCB_VARINT_TOO_LARGE;
+            ub = squeeze7(x & ((1ull << (8 * n1)) - 1));
+            ud = squeeze7((x >> (8 * n1)) & ((1ull << (8 * n2)) - 1));
+            p = cur + e2;
+            if (p > len) return ORCB_IO_ERROR;
+        } else {
+            p = cur + 2;
+            uint32_t e = parse_varint(in, p, len, nb * 8, ub);
+            if (e) return e;
+            e = parse_varint(in, p, len, 64, ud);
+            if (e) return e;
+        }
+    }
     int64_t base = trunc_n((int64_t)ub, nb);
     if (sg) base = zigzag_n(base, nb);
-    e = parse_varint(in, p, len, 64, ud);
-    if (e) return e;
     const int64_t d0 = zigzag_n((int64_t)ud, 8);
     // d0 <= 0: base - |d0| == base + d0 (is_positive() is false for 0, delta.rs:77-82);
     // |i64::MIN| wraps to i64::MIN in the reference, so subtracting it moves by +2^63
-    const __int128 step = d0 == INT64_MIN ? ((__int128)1 << 63) : (__int128)d0;
-    const __int128 last = (__int128)base + (__int128)(rl - 1) * step;
-    if (!in_range_n(last, nb)) return ORCB_OUT_OF_SPEC;
+    if (d0 > -(1ll << 40) && d0 < (1ll << 40) && base > -(1ll << 62) && base < (1ll << 62)) {
+        // no i64 overflow possible (run length <= 512): plain 64-bit arithmetic
+        const int64_t last = base + (int64_t)(rl - 1) * d0;
+        if (trunc_n(last, nb) != last) return ORCB_OUT_OF_SPEC;
+        d.step = (uint64_t)d0;
+    } else {
+        const __int128 step = d0 == INT64_MIN ? ((__int128)1 << 63) : (__int128)d0;
+        const __int128 last = (__int128)base + (__int128)(rl - 1) * step;
+        if (!in_range_n(last, nb)) return ORCB_OUT_OF_SPEC;
+        d.step = (uint64_t)(int64_t)step;
+    }
     bytes_out = p - cur;
     d.base = (uint64_t)base;
-    d.step = (uint64_t)(int64_t)step;
     cls = RC_CONST;
     return 0;
 }
@@ -740,7 +792,12 @@ constexpr int RLE_WARPS = 4;
 
 // Integer RLE decode proper: one warp per 32 consecutive runs of one segment (run table from k_rle_index).
 // One block of up to 32 consecutive runs of one segment, one run per lane.
-__device__ __forceinline__ void int_rle_block(const Seg* __restrict__ segs, const BlockRec br, const RunRec* __restrict__ recs,
+// FAST = true: only blocks made of constant / short direct runs are decoded (shared-memory tile, coalesced
+// flush); anything else returns false and is queued for the FAST = false instantiation (general blocks:
+// scan + per-value search, whole-warp runs, RLE v1, error reporting).  Two kernels keep the hot one small
+// enough for the instruction cache.
+template <bool FAST>
+__device__ __forceinline__ bool int_rle_block(const Seg* __restrict__ segs, const BlockRec br, const RunRec* __restrict__ recs,
                                               const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ dstart,
                                               uint32_t* err, uint32_t* mis, uint32_t* patchmap, RunSlot* slots,
                                               int64_t* tile, const int lane) {
@@ -753,6 +810,7 @@ __device__ __forceinline__ void int_rle_block(const Seg* __restrict__ segs, cons
     const uint32_t n = s.cnt_idx >= 0 ? cnt[s.cnt_idx] : s.n_values;
     const uint64_t obase = s.start_idx >= 0 ? dstart[s.start_idx] : s.out_start;
     const bool v2 = (s.flags & SEG_RLE_V2) != 0;
+    if (FAST && !v2) return false;
     RunRec rec;
     rec.byte_off = 0;
     rec.out_off = 0;
@@ -764,14 +822,16 @@ __device__ __forceinline__ void int_rle_block(const Seg* __restrict__ segs, cons
     __syncwarp();
     RunSlot& my = slots[lane];
     uint32_t cls = RC_NONE, rl = 0, nbytes = 0, take = 0;
+    bool failed = false;
     if (active) {
         uint32_t st;
         my.meta = 0;
         if (cur >= s.in_len) st = ORCB_OUT_OF_SPEC;  // "not enough values to decode" rle_v2/mod.rs:115-122
-        else if (v2) st = parse_run2(s, cur, my, cls, rl, nbytes);
+        else if (FAST || v2) st = parse_run2(s, cur, my, cls, rl, nbytes);
         else st = parse_run1(c, cur, skip, room, out_pos, my, cls, rl, nbytes, take);
         if (st) {
-            set_err(err, s.colstripe, st);
+            if (FAST) failed = true;  // the general kernel re-parses the block and reports the error
+            else set_err(err, s.colstripe, st);
             active = false;
             cls = RC_NONE;
         }
@@ -792,22 +852,126 @@ __device__ __forceinline__ void int_rle_block(const Seg* __restrict__ segs, cons
     // ---- fast block: every run of the block is a short constant / direct run.  The 32 runs are consecutive
     //      runs of one segment, so their values are contiguous in the output: each lane expands its own run
     //      into a shared-memory tile, then the warp writes the tile with coalesced stores.
-    if (total <= TILE_VALUES && __all_sync(FULL, !active || cls == RC_CONST || cls == RC_DIRECT)) {
+    if (FAST) {
+      if (__any_sync(FULL, failed)) return false;
+      if (!(total <= TILE_VALUES && __all_sync(FULL, !active || cls == RC_CONST || cls == RC_DIRECT))) return false;
+      {
         const uint32_t pe = incl - emit;
-        if (cls == RC_CONST) {
-            uint64_t v = my.base + (uint64_t)skip * my.step;
-            for (uint32_t j = 0; j < take; j++, v += my.step) tile[pe + j] = (int64_t)v;
-        } else if (cls == RC_DIRECT) {
-            const int w = (int)(my.meta & 0xff);
-            const uint8_t* data = (const uint8_t*)(uintptr_t)my.data;
-            if (w <= 32 && (nb > 2 || w <= 16)) {
-                for (uint32_t j = 0; j < take; j++)
-                    tile[pe + j] = finish32(load_be_bits32(data, (skip + j) * (uint32_t)w, w), sg, nb);
+        const int w = (int)(my.meta & 0xff);
+        const uint8_t* data = (const uint8_t*)(uintptr_t)my.data;
+        const bool narrow = w <= 32 && (nb > 2 || w <= 16);
+        // ---- outputs of at most 32 bits (dictionary keys, lengths, INT / DATE / SHORT, decimal scales): the same
+        //      block in 32-bit arithmetic with a 32-bit tile; range checks are done once per constant run
+        if (okind != OUT_I64 && __all_sync(FULL, cls != RC_DIRECT || w <= 32)) {
+            uint32_t* tile32 = (uint32_t*)tile;
+            bool bad = false;
+            if (cls == RC_CONST) {
+                const uint64_t first = my.base + (uint64_t)skip * my.step;
+                const uint64_t last = first + (uint64_t)(take ? take - 1 : 0) * my.step;
+                if (okind == OUT_LEN31) bad = take && (first > 0x7fffffffull || last > 0x7fffffffull);
+                else if (okind == OUT_SCALE) bad = take && ((uint32_t)first != s.aux || (take > 1 && my.step != 0));
+            }
+            if (take <= SELF_FILL) {
+                if (cls == RC_CONST) {
+                    uint32_t v = (uint32_t)my.base + skip * (uint32_t)my.step;
+                    for (uint32_t j = 0; j < take; j++, v += (uint32_t)my.step) tile32[pe + j] = v;
+                } else if (cls == RC_DIRECT) {
+                    for (uint32_t j = 0; j < take; j++) {
+                        uint32_t x = load_be_bits32(data, (skip + j) * (uint32_t)w, w);
+                        if (sg) x = (x >> 1) ^ (0u - (x & 1));
+                        tile32[pe + j] = x;
+                    }
+                }
+            }
+            uint32_t longmask = __ballot_sync(FULL, (cls == RC_CONST || cls == RC_DIRECT) && take > SELF_FILL);
+            while (longmask) {
+                const int leader = __ffs(longmask) - 1;
+                longmask &= longmask - 1;
+                const uint32_t lcls = __shfl_sync(FULL, cls, leader);
+                const uint32_t ltake = __shfl_sync(FULL, take, leader);
+                const uint32_t lpe = __shfl_sync(FULL, pe, leader);
+                const uint32_t lskip = __shfl_sync(FULL, skip, leader);
+                if (lcls == RC_CONST) {
+                    const uint32_t lbase = __shfl_sync(FULL, (uint32_t)my.base, leader);
+                    const uint32_t lstep = __shfl_sync(FULL, (uint32_t)my.step, leader);
+                    for (uint32_t j = lane; j < ltake; j += 32) tile32[lpe + j] = lbase + (lskip + j) * lstep;
+                } else {
+                    const int lw = __shfl_sync(FULL, w, leader);
+                    const uint8_t* ldata = (const uint8_t*)(uintptr_t)__shfl_sync(FULL, (uint64_t)(uintptr_t)data, leader);
+                    for (uint32_t j = lane; j < ltake; j += 32) {
+                        uint32_t x = load_be_bits32(ldata, (lskip + j) * (uint32_t)lw, lw);
+                        if (sg) x = (x >> 1) ^ (0u - (x & 1));
+                        tile32[lpe + j] = x;
+                    }
+                }
+            }
+            __syncwarp();
+            const uint64_t o0 = __shfl_sync(FULL, out_pos, 0);
+            if (okind == OUT_I16) {
+                for (uint32_t p = lane; p < total; p += 32) ((int16_t*)s.out)[o0 + p] = (int16_t)tile32[p];
             } else {
-                for (uint32_t j = 0; j < take; j++) {
-                    int64_t v = trunc_n((int64_t)load_be_bits(data, (skip + j) * (uint32_t)w, w), nb);
-                    if (sg) v = zigzag_n(v, nb);
-                    tile[pe + j] = v;
+                // DIRECT values of LEN31 / SCALE streams are checked on the way out (constant runs were checked above);
+                // a value with bit 31 set is outside [0, 2^31) whether the stream is signed (negative) or not
+                const uint32_t dmask = __ballot_sync(FULL, cls == RC_DIRECT && take > 0);
+                for (uint32_t p = lane; p < total; p += 32) {
+                    const uint32_t v = tile32[p];
+                    if (dmask) {
+                        if (okind == OUT_LEN31) bad |= (v >> 31) != 0;
+                        else if (okind == OUT_SCALE) bad |= v != s.aux;
+                    }
+                    ((int32_t*)s.out)[o0 + p] = (int32_t)v;
+                }
+            }
+            if (bad) {
+                if (okind == OUT_LEN31) set_err(err, s.colstripe, s.aux);
+                else if (okind == OUT_SCALE) atomicOr(&mis[s.colstripe], 1u);
+            }
+            return true;
+        }
+        // runs of up to SELF_FILL values are expanded by their own lane ...
+        if (take <= SELF_FILL) {
+            if (cls == RC_CONST) {
+                uint64_t v = my.base + (uint64_t)skip * my.step;
+                for (uint32_t j = 0; j < take; j++, v += my.step) tile[pe + j] = (int64_t)v;
+            } else if (cls == RC_DIRECT) {
+                if (narrow) {
+                    for (uint32_t j = 0; j < take; j++)
+                        tile[pe + j] = finish32(load_be_bits32(data, (skip + j) * (uint32_t)w, w), sg, nb);
+                } else {
+                    for (uint32_t j = 0; j < take; j++) {
+                        int64_t v = trunc_n((int64_t)load_be_bits(data, (skip + j) * (uint32_t)w, w), nb);
+                        if (sg) v = zigzag_n(v, nb);
+                        tile[pe + j] = v;
+                    }
+                }
+            }
+        }
+        // ... longer ones by the whole warp, one run after the other
+        uint32_t longmask = __ballot_sync(FULL, (cls == RC_CONST || cls == RC_DIRECT) && take > SELF_FILL);
+        while (longmask) {
+            const int leader = __ffs(longmask) - 1;
+            longmask &= longmask - 1;
+            const uint32_t lcls = __shfl_sync(FULL, cls, leader);
+            const uint32_t ltake = __shfl_sync(FULL, take, leader);
+            const uint32_t lpe = __shfl_sync(FULL, pe, leader);
+            const uint32_t lskip = __shfl_sync(FULL, skip, leader);
+            if (lcls == RC_CONST) {
+                const uint64_t lbase = __shfl_sync(FULL, my.base, leader);
+                const uint64_t lstep = __shfl_sync(FULL, my.step, leader);
+                for (uint32_t j = lane; j < ltake; j += 32) tile[lpe + j] = (int64_t)(lbase + (uint64_t)(lskip + j) * lstep);
+            } else {
+                const int lw = __shfl_sync(FULL, w, leader);
+                const uint8_t* ldata = (const uint8_t*)(uintptr_t)__shfl_sync(FULL, (uint64_t)(uintptr_t)data, leader);
+                const bool lnarrow = lw <= 32 && (nb > 2 || lw <= 16);
+                for (uint32_t j = lane; j < ltake; j += 32) {
+                    int64_t v;
+                    if (lnarrow) {
+                        v = finish32(load_be_bits32(ldata, (lskip + j) * (uint32_t)lw, lw), sg, nb);
+                    } else {
+                        v = trunc_n((int64_t)load_be_bits(ldata, (lskip + j) * (uint32_t)lw, lw), nb);
+                        if (sg) v = zigzag_n(v, nb);
+                    }
+                    tile[lpe + j] = v;
                 }
             }
         }
@@ -837,7 +1001,8 @@ __device__ __forceinline__ void int_rle_block(const Seg* __restrict__ segs, cons
                 break;
             default: break;
         }
-        return;
+        return true;
+      }
     }
     __syncwarp();
     // ---- general block: all lanes produce the values of all parsed runs, 4 values per lane per step, every
@@ -916,27 +1081,50 @@ __device__ __forceinline__ void int_rle_block(const Seg* __restrict__ segs, cons
         const uint32_t st = coop_run2(c, lcur, lskip, lroom, lout, patchmap, crl, cbytes, ctake);
         if (st && lane == leader) set_err(err, s.colstripe, st);
     }
+    return true;
 }
 
+// Hot kernel: persistent warps over the run blocks; blocks it cannot take are appended to `slow_list`.
 __global__ void __launch_bounds__(RLE_WARPS * 32) k_int_rle(const Seg* __restrict__ segs,
                                                             const BlockRec* __restrict__ blocks,
                                                             const uint32_t* __restrict__ nblocks_ptr,
                                                             const RunRec* __restrict__ table,
                                                             const uint32_t* __restrict__ cnt,
                                                             const uint32_t* __restrict__ dstart, uint32_t* err,
-                                                            uint32_t* mis) {
-    __shared__ uint32_t patchmap_all[RLE_WARPS][16];
+                                                            uint32_t* mis, uint32_t* slow_list, uint32_t* slow_count) {
     __shared__ RunSlot slots_all[RLE_WARPS][32];
     __shared__ int64_t tile_all[RLE_WARPS][TILE_VALUES];
     const uint32_t nblocks = *nblocks_ptr;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
     const int lane = threadIdx.x & 31;
-    uint32_t* patchmap = patchmap_all[threadIdx.x >> 5];
     RunSlot* slots = slots_all[threadIdx.x >> 5];
     // persistent warps: the number of run blocks is only known on the device
-    for (uint32_t blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; blk < nblocks; blk += nwarps)
-        int_rle_block(segs, blocks[blk], table + (uint64_t)blk * 32, cnt, dstart, err, mis, patchmap, slots,
-                      tile_all[threadIdx.x >> 5], lane);
+    for (uint32_t blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; blk < nblocks; blk += nwarps) {
+        const bool done = int_rle_block<true>(segs, blocks[blk], table + (uint64_t)blk * 32, cnt, dstart, err, mis, nullptr,
+                                              slots, tile_all[threadIdx.x >> 5], lane);
+        if (!done && lane == 0) slow_list[atomicAdd(slow_count, 1u)] = blk;
+    }
+}
+
+// General blocks queued by k_int_rle.
+__global__ void __launch_bounds__(RLE_WARPS * 32) k_int_rle_general(const Seg* __restrict__ segs,
+                                                                    const BlockRec* __restrict__ blocks,
+                                                                    const uint32_t* __restrict__ slow_list,
+                                                                    const uint32_t* __restrict__ slow_count,
+                                                                    const RunRec* __restrict__ table,
+                                                                    const uint32_t* __restrict__ cnt,
+                                                                    const uint32_t* __restrict__ dstart, uint32_t* err,
+                                                                    uint32_t* mis) {
+    __shared__ uint32_t patchmap_all[RLE_WARPS][16];
+    __shared__ RunSlot slots_all[RLE_WARPS][32];
+    const uint32_t nslow = *slow_count;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nslow; i += nwarps) {
+        const uint32_t blk = slow_list[i];
+        int_rle_block<false>(segs, blocks[blk], table + (uint64_t)blk * 32, cnt, dstart, err, mis,
+                             patchmap_all[threadIdx.x >> 5], slots_all[threadIdx.x >> 5], nullptr, lane);
+    }
 }
 
 // Warp-per-segment variant for segments made of long runs (every run decoded by all 32 lanes).
@@ -1733,19 +1921,26 @@ int launch_rle_index(const Seg* segs, uint32_t n, const uint32_t* cnt, RunRec* t
     return 0;
 }
 int launch_int_rle(const Seg* segs, const BlockRec* blocks, const uint32_t* nblocks, uint32_t pool_blocks, const RunRec* table,
-                   const uint32_t* cnt, const uint32_t* dstart, uint32_t* err, uint32_t* mis, cudaStream_t st) {
+                   const uint32_t* cnt, const uint32_t* dstart, uint32_t* err, uint32_t* mis, uint32_t* slow_list,
+                   uint32_t* slow_count, cudaStream_t st) {
     if (!pool_blocks) return 0;
-    // persistent grid: enough CTAs to fill every SM, never more warps than blocks could exist
-    static int ctas = 0;
-    if (!ctas) {
+    // persistent grids: enough CTAs to fill every SM, never more warps than blocks could exist
+    static int ctas_fast = 0, ctas_gen = 0;
+    if (!ctas_fast) {
         int dev = 0, sms = 148, per_sm = 8;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_int_rle, RLE_WARPS * 32, 0);
-        ctas = sms * (per_sm > 0 ? per_sm : 1);
+        ctas_fast = sms * (per_sm > 0 ? per_sm : 1);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_int_rle_general, RLE_WARPS * 32, 0);
+        ctas_gen = sms * (per_sm > 0 ? per_sm : 1);
     }
-    const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)ctas, ((uint64_t)pool_blocks + RLE_WARPS - 1) / RLE_WARPS);
-    k_int_rle<<<grid, RLE_WARPS * 32, 0, st>>>(segs, blocks, nblocks, table, cnt, dstart, err, mis);
+    const uint64_t need = ((uint64_t)pool_blocks + RLE_WARPS - 1) / RLE_WARPS;
+    k_int_rle<<<(uint32_t)std::min<uint64_t>(ctas_fast, need), RLE_WARPS * 32, 0, st>>>(segs, blocks, nblocks, table, cnt, dstart,
+                                                                                         err, mis, slow_list, slow_count);
+    LAUNCH_CHECK();
+    k_int_rle_general<<<(uint32_t)std::min<uint64_t>(ctas_gen, need), RLE_WARPS * 32, 0, st>>>(segs, blocks, slow_list, slow_count,
+                                                                                                table, cnt, dstart, err, mis);
     LAUNCH_CHECK();
     return 0;
 }

@@ -11,7 +11,8 @@ namespace orcb {
 int launch_rle_index(const Seg* segs, uint32_t n, const uint32_t* cnt, RunRec* table, BlockRec* blocks, uint32_t* nblocks,
                      uint32_t pool_blocks, uint32_t* err, cudaStream_t st);
 int launch_int_rle(const Seg* segs, const BlockRec* blocks, const uint32_t* nblocks, uint32_t pool_blocks, const RunRec* table,
-                   const uint32_t* cnt, const uint32_t* dstart, uint32_t* err, uint32_t* mis, cudaStream_t st);
+                   const uint32_t* cnt, const uint32_t* dstart, uint32_t* err, uint32_t* mis, uint32_t* slow_list,
+                   uint32_t* slow_count, cudaStream_t st);
 int launch_int_rle_coop(const Seg* segs, uint32_t n, const uint32_t* cnt, const uint32_t* dstart, uint32_t* err,
                         uint32_t* mis, cudaStream_t st);
 int launch_byte_rle(const Seg* segs, uint32_t n, const uint32_t* cnt, const uint32_t* dstart, uint32_t* err,
