@@ -483,6 +483,30 @@ __device__ __forceinline__ uint64_t squeeze7(uint64_t x) {
     return x;
 }
 
+// Rare DELTA headers (varints longer than the 8-byte window, or arithmetic that needs 128 bits): kept out of line
+// so the hot kernel stays small.
+__device__ __noinline__ uint32_t parse_delta_slow(const uint8_t* in, uint32_t len, uint32_t cur, int nb, bool sg, uint32_t rl,
+                                                  uint64_t* base_out, uint64_t* step_out, uint32_t* bytes_out) {
+    uint32_t p = cur + 2;
+    uint64_t ub, ud;
+    uint32_t e = parse_varint(in, p, len, nb * 8, ub);
+    if (e) return e;
+    e = parse_varint(in, p, len, 64, ud);
+    if (e) return e;
+    int64_t base = trunc_n((int64_t)ub, nb);
+    if (sg) base = zigzag_n(base, nb);
+    const int64_t d0 = zigzag_n((int64_t)ud, 8);
+    // d0 <= 0: base - |d0| == base + d0 (is_positive() is false for 0, delta.rs:77-82);
+    // |i64::MIN| wraps to i64::MIN in the reference, so subtracting it moves by +2^63
+    const __int128 step = d0 == INT64_MIN ? ((__int128)1 << 63) : (__int128)d0;
+    const __int128 last = (__int128)base + (__int128)(rl - 1) * step;
+    if (!in_range_n(last, nb)) return ORCB_OUT_OF_SPEC;
+    *base_out = (uint64_t)base;
+    *step_out = (uint64_t)(int64_t)step;
+    *bytes_out = p - cur;
+    return 0;
+}
+
 // Parse the run at `cur` of the lane's own segment.  No values are produced here (except RLE v1 literals).
 // One 8-byte window of the stream serves the common headers without byte loops.
 __device__ __forceinline__ uint32_t parse_run2(const Seg& s, uint32_t cur, RunSlot& d, uint32_t& cls, uint32_t& rl_out,
@@ -551,48 +575,34 @@ __device__ __forceinline__ uint32_t parse_run2(const Seg& s, uint32_t cur, RunSl
         cls = RC_COOP;  // packed deltas need a prefix sum
         return 0;
     }
-    uint64_t ub, ud;
-    uint32_t p;
-    {
-        // both varints inside the window (terminators among stream bytes 2..7)?
-        uint64_t term = ~win & 0x8080808080800000ull;
-        const int t1 = __ffsll((long long)term);
-        term &= term - 1;
-        const int t2 = __ffsll((long long)term);
-        const uint32_t e1 = (uint32_t)(t1 >> 3), e2 = (uint32_t)(t2 >> 3);  // byte index after each varint
-        if (t1 && t2) {
-            const uint64_t x = win >> 16;                                   // bytes 2..7
-            const uint32_t n1 = e1 - 2, n2 = e2 - e1;
-            // read_varint::<N>: a byte at shift >= bit-width(N) is an error even when zero (util.rs:486-489)
-            if ((n1 - 1) * 7 >= (uint32_t)nb * 8) return ORCB_VARINT_TOO_LARGE;
-            ub = squeeze7(x & ((1ull << (8 * n1)) - 1));
-            ud = squeeze7((x >> (8 * n1)) & ((1ull << (8 * n2)) - 1));
-            p = cur + e2;
-            if (p > len) return ORCB_IO_ERROR;
-        } else {
-            p = cur + 2;
-            uint32_t e = parse_varint(in, p, len, nb * 8, ub);
-            if (e) return e;
-            e = parse_varint(in, p, len, 64, ud);
-            if (e) return e;
-        }
+    // both varints inside the window (terminators among stream bytes 2..7)?
+    uint64_t term = ~win & 0x8080808080800000ull;
+    const int t1 = __ffsll((long long)term);
+    term &= term - 1;
+    const int t2 = __ffsll((long long)term);
+    const uint32_t e1 = (uint32_t)(t1 >> 3), e2 = (uint32_t)(t2 >> 3);  // byte index after each varint
+    bool slow = !(t1 && t2);
+    int64_t base = 0, d0 = 0;
+    uint32_t p = cur + e2;
+    if (!slow) {
+        const uint64_t x = win >> 16;  // bytes 2..7
+        const uint32_t n1 = e1 - 2, n2 = e2 - e1;
+        // read_varint::<N>: a byte at shift >= bit-width(N) is an error even when zero (util.rs:486-489)
+        if ((n1 - 1) * 7 >= (uint32_t)nb * 8) return ORCB_VARINT_TOO_LARGE;
+        if (p > len) return ORCB_IO_ERROR;
+        base = trunc_n((int64_t)squeeze7(x & ((1ull << (8 * n1)) - 1)), nb);
+        if (sg) base = zigzag_n(base, nb);
+        d0 = zigzag_n((int64_t)squeeze7((x >> (8 * n1)) & ((1ull << (8 * n2)) - 1)), 8);
+        // no i64 overflow possible below these bounds (run length <= 512): plain 64-bit arithmetic
+        slow = !(d0 > -(1ll << 40) && d0 < (1ll << 40) && base > -(1ll << 62) && base < (1ll << 62));
     }
-    int64_t base = trunc_n((int64_t)ub, nb);
-    if (sg) base = zigzag_n(base, nb);
-    const int64_t d0 = zigzag_n((int64_t)ud, 8);
-    // d0 <= 0: base - |d0| == base + d0 (is_positive() is false for 0, delta.rs:77-82);
-    // |i64::MIN| wraps to i64::MIN in the reference, so subtracting it moves by +2^63
-    if (d0 > -(1ll << 40) && d0 < (1ll << 40) && base > -(1ll << 62) && base < (1ll << 62)) {
-        // no i64 overflow possible (run length <= 512): plain 64-bit arithmetic
-        const int64_t last = base + (int64_t)(rl - 1) * d0;
-        if (trunc_n(last, nb) != last) return ORCB_OUT_OF_SPEC;
-        d.step = (uint64_t)d0;
-    } else {
-        const __int128 step = d0 == INT64_MIN ? ((__int128)1 << 63) : (__int128)d0;
-        const __int128 last = (__int128)base + (__int128)(rl - 1) * step;
-        if (!in_range_n(last, nb)) return ORCB_OUT_OF_SPEC;
-        d.step = (uint64_t)(int64_t)step;
+    if (slow) {
+        cls = RC_CONST;
+        return parse_delta_slow(in, len, cur, nb, sg, rl, &d.base, &d.step, &bytes_out);
     }
+    const int64_t last = base + (int64_t)(rl - 1) * d0;
+    if (trunc_n(last, nb) != last) return ORCB_OUT_OF_SPEC;
+    d.step = (uint64_t)d0;
     bytes_out = p - cur;
     d.base = (uint64_t)base;
     cls = RC_CONST;
@@ -723,7 +733,7 @@ __device__ __forceinline__ uint32_t measure_run(const Seg& s, uint32_t cur, uint
     return 0;
 }
 
-constexpr uint32_t IDX_LANES = 4;
+constexpr uint32_t IDX_LANES = 8;
 
 // Pre-pass ("device-built run index"): one lane per segment walks the run headers only and records where
 // every run starts and where its values go.  This is the only serial chain of the integer path (a run's
@@ -1567,7 +1577,13 @@ __global__ void k_dict_prepare(StrCol* cols, uint32_t ncols, uint32_t* err) {
         if (i < c.dict_size) doff[i] = (int32_t)(carry + inc - v);
         carry += __shfl_sync(FULL, inc, 31);
     }
+    // dictionaries whose entries all have the same length (flags, codes) get a scan-free fast path
+    uint32_t first_len = c.dict_size ? (uint32_t)dl[0] : 0u;
+    bool same = true;
+    for (uint32_t i = lane; i < c.dict_size; i += 32) same &= (uint32_t)dl[i] == first_len;
+    same = __all_sync(FULL, same);
     if (lane == 0) {
+        cols[warp].data_cap = (same && c.dict_size && first_len >= 1 && first_len <= 4 && !c.valid) ? first_len : 0;
         doff[c.dict_size] = (int32_t)carry;
         // the dictionary itself is a string batch: offsets must fit i32 and its bytes must exist
         if (carry > 0x7fffffffull) set_err(err, c.colstripe, ORCB_OFFSET_OVERFLOW);
@@ -1595,6 +1611,14 @@ __global__ void __launch_bounds__(128) k_str_tile_sum(const StrCol* __restrict__
     uint32_t b, r0, nr;
     tile_rows(c, tile, b, r0, nr);
     uint64_t sum = 0;
+    if (c.mode == 1 && c.data_cap) {
+        // uniform entry length, no nulls: only the key bounds need checking
+        bool bad = false;
+        for (uint32_t i = lane; i < nr; i += 32) bad |= (uint32_t)((const int32_t*)c.lens)[r0 + i] >= c.dict_size;
+        if (bad) set_err(err, c.colstripe, ORCB_ARROW);
+        if (lane == 0) ((uint64_t*)c.tile_base)[tile] = (uint64_t)nr * c.data_cap;
+        return;
+    }
     for (uint32_t i = lane; i < nr; i += 32) {
         int32_t key;
         sum += str_row_len(c, r0 + i, err, &key);
@@ -1690,10 +1714,27 @@ __global__ void __launch_bounds__(128) k_str_offsets(const StrCol* __restrict__ 
             __syncwarp();
         }
     }
+    if (c.mode == 1 && c.data_cap && data) {
+        // uniform entry length L (1..4), no nulls: offsets are an arithmetic progression and every row copies L bytes
+        const uint32_t L = (uint32_t)c.data_cap;
+        const int32_t* keys = (const int32_t*)c.lens;
+        const uint32_t rel0 = (uint32_t)(run - bbase);
+        uint8_t* dp = data + run;
+        for (uint32_t i = lane; i < nr; i += 32) {
+            offs[i] = (int32_t)(rel0 + i * L);
+            const uint32_t key = (uint32_t)keys[r0 + i];
+            if (key < c.dict_size) {
+                const uint8_t* sp = sdict ? s_ddata + key * L : dict + key * L;
+                for (uint32_t k = 0; k < L; k++) dp[i * L + k] = sp[k];
+            }
+        }
+    } else
     for (uint32_t i0 = 0; i0 < nr; i0 += 32) {
         const uint32_t i = i0 + lane;
         int32_t key = -1;
         const uint32_t l = i < nr ? str_row_len(c, r0 + i, err, &key) : 0;
+        // a single length is below 2^31, 32 of them fit 64 bits easily; the prefix inside the step is done on
+        // 32-bit halves only when it cannot overflow
         const uint64_t inc = warp_incl_scan64(l, lane);
         const uint64_t abs0 = run + inc - l;
         if (i < nr) offs[i] = (int32_t)(abs0 - bbase);
