@@ -263,12 +263,19 @@ def main():
     value = out_bytes * world / (dev_ms / 1e3) / 1e9
     e2e = out_bytes * world / (e2e_ms / 1e3) / 1e9
     peak, peak_src = _peaks()
-    top = max(kstats, key=lambda k: k["ms"]) if kstats else None
+    # dominant kernel = most device time among the kernels that move data (event pairs on the launching streams)
+    top = max((k for k in kstats if k["alg_bytes"]), key=lambda k: k["ms"]) if kstats else None
     roofline = None
     if top:
         ach = top["alg_bytes"] / (top["ms"] / 1e3) / 1e9
+        traffic = None
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu capture of this workload
+            with open(os.path.join(ROOT, "profiles", "r01_traffic_sf10.json")) as f:
+                traffic = json.load(f).get(top["name"])
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": top["name"], "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                     "kernel_ms": top["ms"], "kernel_alg_bytes": top["alg_bytes"],
                     "step_achieved": (in_bytes + out_bytes) / (dev_ms / 1e3) / 1e9,
                     "step_frac": (in_bytes + out_bytes) / (dev_ms / 1e3) / 1e9 / peak,

@@ -1335,14 +1335,28 @@ __global__ void __launch_bounds__(128) k_varint128(const Seg* __restrict__ segs,
         if ((T[3] >> lane) & 1) ends[c0 + c1 + c2 + __popc(T[3] & lt)] = (uint8_t)(96 + lane);
         __syncwarp();
         const uint32_t room = n - produced;
-        for (uint32_t k = lane; k < total && k < room; k += 32) {
-            const uint32_t end = ends[k];
-            const uint32_t start = k ? (uint32_t)ends[k - 1] + 1 : 0u;
+        for (uint32_t k0 = 0; k0 < total && k0 < room; k0 += 32) {
+            const uint32_t k = k0 + lane;
+            const bool live = k < total && k < room;
+            const uint32_t end = live ? ends[k] : 0u;
+            const uint32_t start = (live && k) ? (uint32_t)ends[k - 1] + 1 : 0u;
             const uint32_t nbv = end - start + 1;
+            const uint32_t a = start >> 2, shb = (start & 3) * 8;
+            if (__all_sync(FULL, !live || nbv <= 4)) {
+                // common case (values below 2^28): one 32-bit window per value, 32-bit squeeze, hi half = sign
+                if (live) {
+                    uint32_t x0 = __funnelshift_r(win[a], win[a + 1], shb);
+                    if (nbv < 4) x0 &= (1u << (8 * nbv)) - 1;
+                    const uint32_t g = (x0 & 0x7fu) | ((x0 & 0x7f00u) >> 1) | ((x0 & 0x7f0000u) >> 2) | ((x0 & 0x7f000000u) >> 3);
+                    const uint32_t sgn = 0u - (g & 1);
+                    out[obase + produced + k] = make_uint4((g >> 1) ^ sgn, sgn, sgn, sgn);
+                }
+                continue;
+            }
+            if (!live) continue;
             uint64_t lo, hi = 0;
             if (nbv <= 8) {
                 // 8 little-endian bytes starting at `start` (window is padded), 7-bit groups squeezed together
-                const uint32_t a = start >> 2, shb = (start & 3) * 8;
                 const uint32_t w0 = win[a], w1 = win[a + 1], w2 = win[a + 2];
                 uint32_t x0 = __funnelshift_r(w0, w1, shb), x1 = __funnelshift_r(w1, w2, shb);
                 if (nbv < 4) x0 &= (1u << (8 * nbv)) - 1;
