@@ -332,14 +332,17 @@ int orcb_decode_int_rle(int device, const uint8_t* in, size_t in_len, int versio
         const uint32_t cap = (uint32_t)std::min<size_t>(in_len / 2 + 3, n_values + 2);
         const uint32_t pool = (cap + 31) / 32 + 1;
         DevBuf dtab((size_t)pool * 32 * sizeof(RunRec)), dblk((size_t)pool * sizeof(BlockRec)), dcnt(16), dslow((size_t)pool * 4 + 16);
+        const uint32_t qcap = (uint32_t)(n_values / 64 + 1024);
+        DevBuf dq((size_t)qcap * sizeof(CoopRec));
         CU(cudaMemset(dcnt.p, 0, 16));
         s.run_cap = cap;
         CU(cudaMemcpy(dseg.p, &s, sizeof(s), cudaMemcpyHostToDevice));
         int rc = launch_rle_index((Seg*)dseg.p, 1, nullptr, (RunRec*)dtab.p, (BlockRec*)dblk.p, (uint32_t*)dcnt.p, pool,
-                                  (uint32_t*)sr.err.p, 0);
+                                  (CoopRec*)dq.p, (uint32_t*)dcnt.p + 2, qcap, (uint32_t*)sr.err.p, 0);
         if (rc) fail(ORCB_CUDA, cudaGetErrorString((cudaError_t)rc));
         rc = launch_int_rle((Seg*)dseg.p, (BlockRec*)dblk.p, (uint32_t*)dcnt.p, pool, (RunRec*)dtab.p, nullptr, nullptr,
-                            (uint32_t*)sr.err.p, (uint32_t*)mis.p, (uint32_t*)dslow.p, (uint32_t*)dcnt.p + 1, 0);
+                            (uint32_t*)sr.err.p, (uint32_t*)mis.p, (uint32_t*)dslow.p, (uint32_t*)dcnt.p + 1,
+                            (CoopRec*)dq.p, (uint32_t*)dcnt.p + 2, qcap, 0);
         if (rc) fail(ORCB_CUDA, cudaGetErrorString((cudaError_t)rc));
         sr.check();
         if (n_values) CU(cudaMemcpy(out, dout.p, n_values * 8, cudaMemcpyDeviceToHost));

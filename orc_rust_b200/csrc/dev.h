@@ -45,6 +45,16 @@ struct Seg {
     uint32_t run_cap;
 };
 
+// A run that needs the whole warp (long DIRECT, DELTA with packed deltas, PATCHED_BASE), queued by the pre-pass
+// for k_coop_runs.  Its RunRec in the block table carries RUN_QUEUED in out_off.
+struct CoopRec {
+    uint32_t seg;
+    uint32_t byte_off;
+    uint32_t out_off;
+    uint32_t skip;
+};
+constexpr uint32_t RUN_QUEUED = 0x80000000u;
+
 // 32 consecutive runs of one segment: the unit of work of one warp of k_int_rle.  Allocated from a pool by
 // the k_rle_index pre-pass (one atomicAdd per 32 runs).
 struct BlockRec {

@@ -305,6 +305,9 @@ void Job::plan() {
         run_table_ = alloc(AR_TMP, (uint64_t)pool_blocks_ * 32 * sizeof(RunRec));
         block_recs_ = alloc(AR_TMP, (uint64_t)pool_blocks_ * sizeof(BlockRec));
         slow_list_ = alloc(AR_TMP, (uint64_t)pool_blocks_ * 4 + 16);
+        // queue of whole-warp runs found by the pre-pass; on overflow the run simply stays in its block
+        coop_cap_ = (uint32_t)std::min<uint64_t>(small_values_ / 64 + 65536, 0x7fffffffu);
+        coop_q_ = alloc(AR_TMP, (uint64_t)coop_cap_ * sizeof(CoopRec));
     }
 
     // ---- descriptor blob layout
@@ -643,6 +646,7 @@ void Job::plan_stripe(uint32_t task_idx) {
             const uint32_t cap = std::min(span_bytes / 2 + 3, n_bound + 2);
             sg.run_cap = cap;
             pool_blocks_ += (cap + 31) / 32;
+            small_values_ += n_bound;
         };
         // helper: integer-RLE segments of one stream into `dst` (dense domain if has_present)
         auto add_int_segs = [&](StreamRef& sr, uint64_t dst, bool is_signed, int nbytes, OutKind okind, uint32_t aux,
@@ -1128,8 +1132,8 @@ void Job::launch() {
         RunRec* rtab = (RunRec*)(uintptr_t)reloc(run_table_);
         BlockRec* brec = (BlockRec*)(uintptr_t)reloc(block_recs_);
         uint32_t* nblk = (uint32_t*)(d_state_ + o_nblocks_);
-        run("k_rle_index", 0, N(int_segs_), 1, [&] { return launch_rle_index((Seg*)(d_desc_ + o_int_), N(int_segs_), cnt, rtab, brec, nblk, pool_blocks_, err, aux); });
-        run("k_int_rle(+general)", ab_int_, pool_blocks_, 2, [&] { return launch_int_rle((Seg*)(d_desc_ + o_int_), brec, nblk, pool_blocks_, rtab, cnt, dstart, err, mis, (uint32_t*)(uintptr_t)reloc(slow_list_), nblk + 1, aux); });
+        run("k_rle_index", 0, N(int_segs_), 1, [&] { return launch_rle_index((Seg*)(d_desc_ + o_int_), N(int_segs_), cnt, rtab, brec, nblk, pool_blocks_, (CoopRec*)(uintptr_t)reloc(coop_q_), nblk + 2, coop_cap_, err, aux); });
+        run("k_int_rle(+general,+coop_runs)", ab_int_, pool_blocks_, 3, [&] { return launch_int_rle((Seg*)(d_desc_ + o_int_), brec, nblk, pool_blocks_, rtab, cnt, dstart, err, mis, (uint32_t*)(uintptr_t)reloc(slow_list_), nblk + 1, (CoopRec*)(uintptr_t)reloc(coop_q_), nblk + 2, coop_cap_, aux); });
         if (!serial_env) CUDA_OK(cudaEventRecord(ev_join_, aux));
         cur_st = st;
     }

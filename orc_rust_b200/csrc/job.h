@@ -108,7 +108,9 @@ class Job {
     std::vector<RepackDesc> repacks_;
     std::vector<ChunkDesc> chunks_;
     uint32_t str_tiles_ = 0, repack_work_ = 0, pool_blocks_ = 0;  // capacity of the run-block pool
-    uint64_t run_table_ = 0, block_recs_ = 0, slow_list_ = 0;  // AR_TMP offsets: RunRec table (32 per block), BlockRec table
+    uint64_t run_table_ = 0, block_recs_ = 0, slow_list_ = 0, coop_q_ = 0;
+    uint32_t coop_cap_ = 0;
+    uint64_t small_values_ = 0;  // values decoded by the short-run path (sizes the whole-warp run queue)  // AR_TMP offsets: RunRec table (32 per block), BlockRec table
 
     // stage copies: (file ptr, file offset, AR_IN offset, bytes)
     struct StageCopy {

@@ -456,9 +456,9 @@ __device__ uint32_t coop_run2(const SegCtx& c, uint32_t cur, uint32_t skip, uint
 // time by the whole warp (coop_run2).
 // ------------------------------------------------------------------------------------------------
 enum RunClass : uint32_t { RC_NONE = 0, RC_CONST = 1, RC_DIRECT = 2, RC_COOP = 3 };
+constexpr uint32_t COOP_MIN_RUN = 96;  // DIRECT runs at least this long are decoded by the whole warp
 constexpr uint32_t TILE_VALUES = 512;   // values of one 32-run block staged in shared memory (fast block path)
 constexpr uint32_t SELF_FILL = 10;      // runs up to this long (every SHORT_REPEAT) are expanded by their own lane
-constexpr uint32_t COOP_MIN_RUN = 96;  // DIRECT runs at least this long are decoded by the whole warp
 
 struct RunSlot {       // one per lane, in shared memory
     uint64_t base;     // RC_CONST: value at k = 0
@@ -656,8 +656,11 @@ __device__ __forceinline__ uint32_t parse_run1(const SegCtx& c, uint32_t cur, ui
     return 0;
 }
 
+
 // Header-only walk: length in values and bytes of the run at `cur` (no values produced).
-__device__ __forceinline__ uint32_t measure_run(const Seg& s, uint32_t cur, uint32_t& rl_out, uint32_t& bytes_out) {
+__device__ __forceinline__ uint32_t measure_run(const Seg& s, uint32_t cur, uint32_t& rl_out, uint32_t& bytes_out,
+                                                bool& coop) {
+    coop = false;
     const uint8_t* in = (const uint8_t*)s.in;
     const uint32_t len = s.in_len;
     if (!(s.flags & SEG_RLE_V2)) {
@@ -697,6 +700,7 @@ __device__ __forceinline__ uint32_t measure_run(const Seg& s, uint32_t cur, uint
     const uint32_t w = code < 24 ? code + 1 : (uint32_t)(0x40383028201E1C1Aull >> ((code - 24) * 8)) & 0xffu;
     rl_out = kind == 0 ? (h0 & 7) + 3 : rl;
     bytes_out = kind == 0 ? 2 + ((h0 >> 3) & 7) : 2 + (rl * w + 7) / 8;
+    coop = kind == 2 || (kind == 1 && rl >= COOP_MIN_RUN) || (kind == 3 && code != 0);
     if (kind >= 2) {
         if (kind == 2) {
             const uint32_t b3 = (lo >> 16) & 255, b4 = lo >> 24;
@@ -742,7 +746,8 @@ constexpr uint32_t IDX_LANES = 8;
 __global__ void __launch_bounds__(128) k_rle_index(const Seg* __restrict__ segs, uint32_t nseg,
                                                    const uint32_t* __restrict__ cnt, RunRec* __restrict__ table,
                                                    BlockRec* __restrict__ blocks, uint32_t* __restrict__ nblocks,
-                                                   uint32_t pool_blocks, uint32_t* err) {
+                                                   uint32_t pool_blocks, CoopRec* __restrict__ coop_q,
+                                                   uint32_t* __restrict__ ncoop, uint32_t coop_cap, uint32_t* err) {
     // only IDX_LANES lanes of each warp own a segment: a warp advances at the pace of its slowest lane
     // (the one that misses L1 this step), so fewer streams per warp and more warps hide more latency
     const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
@@ -756,7 +761,8 @@ __global__ void __launch_bounds__(128) k_rle_index(const Seg* __restrict__ segs,
     // values are still buffered): step over the runs that are skipped entirely
     while (skip > 0 && cur < s.in_len) {
         uint32_t rl, nbytes;
-        if (measure_run(s, cur, rl, nbytes) || skip < rl) break;
+        bool cq;
+        if (measure_run(s, cur, rl, nbytes, cq) || skip < rl) break;
         skip -= rl;
         cur += nbytes;
     }
@@ -771,14 +777,28 @@ __global__ void __launch_bounds__(128) k_rle_index(const Seg* __restrict__ segs,
             blk = atomicAdd(nblocks, 1u);
             if (blk >= pool_blocks) { set_err(err, s.colstripe, ORCB_UNEXPECTED); blk = 0xffffffffu; break; }
         }
+        bool stop = cur >= s.in_len;  // k_int_rle reports "not enough values" for this record
+        uint32_t rl = 0, nbytes = 0;
+        bool cq = false;
+        if (!stop) stop = measure_run(s, cur, rl, nbytes, cq) != 0;  // k_int_rle re-parses the run and reports the error
         RunRec r;
         r.byte_off = cur;
         r.out_off = produced;
+        if (cq && !stop) {
+            // whole-warp runs go to their own queue; the block table keeps a placeholder so positions stay aligned
+            const uint32_t qi = atomicAdd(ncoop, 1u);
+            if (qi < coop_cap) {
+                CoopRec cr;
+                cr.seg = segi;
+                cr.byte_off = cur;
+                cr.out_off = produced;
+                cr.skip = skip;
+                coop_q[qi] = cr;
+                r.out_off |= RUN_QUEUED;
+            }
+        }
         table[(uint64_t)blk * 32 + in_blk] = r;
         in_blk++;
-        bool stop = cur >= s.in_len;  // k_int_rle reports "not enough values" for this record
-        uint32_t rl = 0, nbytes = 0;
-        if (!stop) stop = measure_run(s, cur, rl, nbytes) != 0;  // k_int_rle re-parses the run and reports the error
         if (!stop) {
             produced += min(rl > skip ? rl - skip : 0u, n - produced);
             skip = 0;
@@ -825,6 +845,9 @@ __device__ __forceinline__ bool int_rle_block(const Seg* __restrict__ segs, cons
     rec.byte_off = 0;
     rec.out_off = 0;
     if (active) rec = recs[lane];
+    const bool queued = (rec.out_off & RUN_QUEUED) != 0;  // decoded by k_coop_runs
+    rec.out_off &= ~RUN_QUEUED;
+    if (queued) active = false;
     const uint32_t cur = rec.byte_off;
     const uint32_t skip = lane == 0 ? br.skip : 0u;
     const uint32_t room = n - rec.out_off;
@@ -916,20 +939,31 @@ __device__ __forceinline__ bool int_rle_block(const Seg* __restrict__ segs, cons
                 }
             }
             __syncwarp();
-            const uint64_t o0 = __shfl_sync(FULL, out_pos, 0);
-            if (okind == OUT_I16) {
-                for (uint32_t p = lane; p < total; p += 32) ((int16_t*)s.out)[o0 + p] = (int16_t)tile32[p];
-            } else {
-                // DIRECT values of LEN31 / SCALE streams are checked on the way out (constant runs were checked above);
-                // a value with bit 31 set is outside [0, 2^31) whether the stream is signed (negative) or not
-                const uint32_t dmask = __ballot_sync(FULL, cls == RC_DIRECT && take > 0);
-                for (uint32_t p = lane; p < total; p += 32) {
-                    const uint32_t v = tile32[p];
-                    if (dmask) {
-                        if (okind == OUT_LEN31) bad |= (v >> 31) != 0;
-                        else if (okind == OUT_SCALE) bad |= v != s.aux;
+            // DIRECT values of LEN31 / SCALE streams are checked on the way out (constant runs were checked above);
+            // a value with bit 31 set is outside [0, 2^31) whether the stream is signed (negative) or not
+            const uint32_t dmask = __ballot_sync(FULL, cls == RC_DIRECT && take > 0);
+            // the block's values are contiguous in the output except where a queued whole-warp run sits:
+            // flush the lanes between two queued lanes as one coalesced range
+            const uint32_t qmask = __ballot_sync(FULL, queued);
+            uint32_t pending = __ballot_sync(FULL, emit > 0);
+            while (pending) {
+                const int a = __ffs(pending) - 1;
+                const uint32_t after = qmask & ~((2u << a) - 1u);
+                const int stop = after ? __ffs(after) - 1 : 32;
+                pending &= ~((stop >= 32 ? FULL : ((1u << stop) - 1u)) & ~((1u << a) - 1u));
+                const uint32_t t0 = __shfl_sync(FULL, pe, a), t1 = __shfl_sync(FULL, incl, stop - 1);
+                const uint64_t o0 = __shfl_sync(FULL, out_pos, a);
+                if (okind == OUT_I16) {
+                    for (uint32_t p = t0 + lane; p < t1; p += 32) ((int16_t*)s.out)[o0 + (p - t0)] = (int16_t)tile32[p];
+                } else {
+                    for (uint32_t p = t0 + lane; p < t1; p += 32) {
+                        const uint32_t v = tile32[p];
+                        if (dmask) {
+                            if (okind == OUT_LEN31) bad |= (v >> 31) != 0;
+                            else if (okind == OUT_SCALE) bad |= v != s.aux;
+                        }
+                        ((int32_t*)s.out)[o0 + (p - t0)] = (int32_t)v;
                     }
-                    ((int32_t*)s.out)[o0 + p] = (int32_t)v;
                 }
             }
             if (bad) {
@@ -986,30 +1020,40 @@ __device__ __forceinline__ bool int_rle_block(const Seg* __restrict__ segs, cons
             }
         }
         __syncwarp();
-        // first emitted value of the block = first active lane's position (lane 0 is always active here)
-        const uint64_t o0 = __shfl_sync(FULL, out_pos, 0);
         bool bad = false;
-        switch (okind) {
-            case OUT_I16: for (uint32_t p = lane; p < total; p += 32) ((int16_t*)s.out)[o0 + p] = (int16_t)tile[p]; break;
-            case OUT_I32: for (uint32_t p = lane; p < total; p += 32) ((int32_t*)s.out)[o0 + p] = (int32_t)tile[p]; break;
-            case OUT_I64: for (uint32_t p = lane; p < total; p += 32) ((int64_t*)s.out)[o0 + p] = tile[p]; break;
-            case OUT_LEN31:
-                for (uint32_t p = lane; p < total; p += 32) {
-                    const int64_t v = tile[p];
-                    if ((uint64_t)v > 0x7fffffffull) bad = true;
-                    ((int32_t*)s.out)[o0 + p] = (int32_t)v;
-                }
-                if (bad) set_err(err, s.colstripe, s.aux);
-                break;
-            case OUT_SCALE:
-                for (uint32_t p = lane; p < total; p += 32) {
-                    const int64_t v = tile[p];
-                    if ((uint32_t)(int32_t)v != s.aux) bad = true;
-                    ((int32_t*)s.out)[o0 + p] = (int32_t)v;
-                }
-                if (bad) atomicOr(&mis[s.colstripe], 1u);
-                break;
-            default: break;
+        const uint32_t qmask = __ballot_sync(FULL, queued);
+        uint32_t pending = __ballot_sync(FULL, emit > 0);
+        while (pending) {
+            const int a = __ffs(pending) - 1;
+            const uint32_t after = qmask & ~((2u << a) - 1u);
+            const int stop = after ? __ffs(after) - 1 : 32;
+            pending &= ~((stop >= 32 ? FULL : ((1u << stop) - 1u)) & ~((1u << a) - 1u));
+            const uint32_t t0 = __shfl_sync(FULL, pe, a), t1 = __shfl_sync(FULL, incl, stop - 1);
+            const uint64_t o0 = __shfl_sync(FULL, out_pos, a);
+            switch (okind) {
+                case OUT_I16: for (uint32_t p = t0 + lane; p < t1; p += 32) ((int16_t*)s.out)[o0 + (p - t0)] = (int16_t)tile[p]; break;
+                case OUT_I32: for (uint32_t p = t0 + lane; p < t1; p += 32) ((int32_t*)s.out)[o0 + (p - t0)] = (int32_t)tile[p]; break;
+                case OUT_I64: for (uint32_t p = t0 + lane; p < t1; p += 32) ((int64_t*)s.out)[o0 + (p - t0)] = tile[p]; break;
+                case OUT_LEN31:
+                    for (uint32_t p = t0 + lane; p < t1; p += 32) {
+                        const int64_t v = tile[p];
+                        if ((uint64_t)v > 0x7fffffffull) bad = true;
+                        ((int32_t*)s.out)[o0 + (p - t0)] = (int32_t)v;
+                    }
+                    break;
+                case OUT_SCALE:
+                    for (uint32_t p = t0 + lane; p < t1; p += 32) {
+                        const int64_t v = tile[p];
+                        if ((uint32_t)(int32_t)v != s.aux) bad = true;
+                        ((int32_t*)s.out)[o0 + (p - t0)] = (int32_t)v;
+                    }
+                    break;
+                default: break;
+            }
+        }
+        if (bad) {
+            if (okind == OUT_LEN31) set_err(err, s.colstripe, s.aux);
+            else if (okind == OUT_SCALE) atomicOr(&mis[s.colstripe], 1u);
         }
         return true;
       }
@@ -1134,6 +1178,32 @@ __global__ void __launch_bounds__(RLE_WARPS * 32) k_int_rle_general(const Seg* _
         const uint32_t blk = slow_list[i];
         int_rle_block<false>(segs, blocks[blk], table + (uint64_t)blk * 32, cnt, dstart, err, mis,
                              patchmap_all[threadIdx.x >> 5], slots_all[threadIdx.x >> 5], nullptr, lane);
+    }
+}
+
+// Whole-warp runs queued by the pre-pass: one warp per run.
+__global__ void __launch_bounds__(RLE_WARPS * 32) k_coop_runs(const Seg* __restrict__ segs, const CoopRec* __restrict__ q,
+                                                              const uint32_t* __restrict__ nq_ptr, uint32_t cap,
+                                                              const uint32_t* __restrict__ cnt,
+                                                              const uint32_t* __restrict__ dstart, uint32_t* err,
+                                                              uint32_t* mis) {
+    __shared__ uint32_t patchmap_all[RLE_WARPS][16];
+    const uint32_t nq = min(*nq_ptr, cap);
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nq; i += nwarps) {
+        const CoopRec r = q[i];
+        SegCtx c;
+        c.s = &segs[r.seg];
+        c.err = err;
+        c.mis = mis;
+        const Seg& s = *c.s;
+        const uint32_t n = s.cnt_idx >= 0 ? cnt[s.cnt_idx] : s.n_values;
+        const uint64_t obase = s.start_idx >= 0 ? dstart[s.start_idx] : s.out_start;
+        uint32_t rl = 0, nbytes = 0, take = 0;
+        const uint32_t st = coop_run2(c, r.byte_off, r.skip, n - r.out_off, obase + r.out_off, patchmap_all[threadIdx.x >> 5],
+                                      rl, nbytes, take);
+        if (st) set_err(err, s.colstripe, st);
+        __syncwarp();
     }
 }
 
@@ -1968,16 +2038,16 @@ static inline uint32_t blocks_for_warps(uint32_t nwarps, uint32_t warps_per_bloc
     } while (0)
 
 int launch_rle_index(const Seg* segs, uint32_t n, const uint32_t* cnt, RunRec* table, BlockRec* blocks, uint32_t* nblocks,
-                     uint32_t pool_blocks, uint32_t* err, cudaStream_t st) {
+                     uint32_t pool_blocks, CoopRec* coop_q, uint32_t* ncoop, uint32_t coop_cap, uint32_t* err, cudaStream_t st) {
     if (!n) return 0;
     const uint32_t nwarps = (n + IDX_LANES - 1) / IDX_LANES;
-    k_rle_index<<<(nwarps + 3) / 4, 128, 0, st>>>(segs, n, cnt, table, blocks, nblocks, pool_blocks, err);
+    k_rle_index<<<(nwarps + 3) / 4, 128, 0, st>>>(segs, n, cnt, table, blocks, nblocks, pool_blocks, coop_q, ncoop, coop_cap, err);
     LAUNCH_CHECK();
     return 0;
 }
 int launch_int_rle(const Seg* segs, const BlockRec* blocks, const uint32_t* nblocks, uint32_t pool_blocks, const RunRec* table,
                    const uint32_t* cnt, const uint32_t* dstart, uint32_t* err, uint32_t* mis, uint32_t* slow_list,
-                   uint32_t* slow_count, cudaStream_t st) {
+                   uint32_t* slow_count, const CoopRec* coop_q, const uint32_t* ncoop, uint32_t coop_cap, cudaStream_t st) {
     if (!pool_blocks) return 0;
     // persistent grids: enough CTAs to fill every SM, never more warps than blocks could exist
     static int ctas_fast = 0, ctas_gen = 0;
@@ -1997,6 +2067,12 @@ int launch_int_rle(const Seg* segs, const BlockRec* blocks, const uint32_t* nblo
     k_int_rle_general<<<(uint32_t)std::min<uint64_t>(ctas_gen, need), RLE_WARPS * 32, 0, st>>>(segs, blocks, slow_list, slow_count,
                                                                                                 table, cnt, dstart, err, mis);
     LAUNCH_CHECK();
+    if (coop_cap) {
+        const uint64_t needq = ((uint64_t)coop_cap + RLE_WARPS - 1) / RLE_WARPS;
+        k_coop_runs<<<(uint32_t)std::min<uint64_t>(ctas_gen, needq), RLE_WARPS * 32, 0, st>>>(segs, coop_q, ncoop, coop_cap, cnt, dstart,
+                                                                                               err, mis);
+        LAUNCH_CHECK();
+    }
     return 0;
 }
 int launch_int_rle_coop(const Seg* segs, uint32_t n, const uint32_t* cnt, const uint32_t* dstart, uint32_t* err,

@@ -9,10 +9,10 @@ namespace orcb {
 
 // short-run integer path: header-walk pre-pass into the run table, then one warp per 32 runs
 int launch_rle_index(const Seg* segs, uint32_t n, const uint32_t* cnt, RunRec* table, BlockRec* blocks, uint32_t* nblocks,
-                     uint32_t pool_blocks, uint32_t* err, cudaStream_t st);
+                     uint32_t pool_blocks, CoopRec* coop_q, uint32_t* ncoop, uint32_t coop_cap, uint32_t* err, cudaStream_t st);
 int launch_int_rle(const Seg* segs, const BlockRec* blocks, const uint32_t* nblocks, uint32_t pool_blocks, const RunRec* table,
                    const uint32_t* cnt, const uint32_t* dstart, uint32_t* err, uint32_t* mis, uint32_t* slow_list,
-                   uint32_t* slow_count, cudaStream_t st);
+                   uint32_t* slow_count, const CoopRec* coop_q, const uint32_t* ncoop, uint32_t coop_cap, cudaStream_t st);
 int launch_int_rle_coop(const Seg* segs, uint32_t n, const uint32_t* cnt, const uint32_t* dstart, uint32_t* err,
                         uint32_t* mis, cudaStream_t st);
 int launch_byte_rle(const Seg* segs, uint32_t n, const uint32_t* cnt, const uint32_t* dstart, uint32_t* err,
