@@ -1703,10 +1703,40 @@ __global__ void __launch_bounds__(128) k_str_tile_sum(const StrCol* __restrict__
         if (lane == 0) ((uint64_t*)c.tile_base)[tile] = (uint64_t)nr * c.data_cap;
         return;
     }
-    for (uint32_t i = lane; i < nr; i += 32) {
-        int32_t key;
-        sum += str_row_len(c, r0 + i, err, &key);
+    const int32_t* lens = (const int32_t*)c.lens + r0;
+    const uint32_t mode = c.mode, dict_size = c.dict_size;
+    const uint32_t* valid = (const uint32_t*)c.valid;
+    const int32_t* dl = (const int32_t*)c.dict_len;
+    bool bad = false;
+    for (uint32_t j = 0; j < nr; j += 256) {
+        // 8 independent loads per lane in flight, then the dependent dictionary lookups
+        int32_t x[8];
+#pragma unroll
+        for (uint32_t u = 0; u < 8; u++) {
+            const uint32_t i = j + u * 32 + lane;
+            x[u] = i < nr ? lens[i] : (mode == 0 ? 0 : -1);
+        }
+        if (mode == 0) {
+#pragma unroll
+            for (uint32_t u = 0; u < 8; u++) sum += (uint32_t)x[u];
+        } else {
+            uint32_t l[8];
+#pragma unroll
+            for (uint32_t u = 0; u < 8; u++) {
+                const uint32_t i = j + u * 32 + lane;
+                bool ok = i < nr;
+                if (ok && valid) ok = (valid[(r0 + i) >> 5] >> ((r0 + i) & 31)) & 1;
+                l[u] = 0;
+                if (ok) {
+                    if ((uint32_t)x[u] >= dict_size) bad = true;  // DictionaryArray::try_new rejects out-of-range valid keys
+                    else l[u] = (uint32_t)dl[x[u]];
+                }
+            }
+#pragma unroll
+            for (uint32_t u = 0; u < 8; u++) sum += l[u];
+        }
     }
+    if (bad) set_err(err, c.colstripe, ORCB_ARROW);
     sum = warp_sum64(sum);
     if (lane == 0) ((uint64_t*)c.tile_base)[tile] = sum;
 }
@@ -1762,13 +1792,14 @@ __global__ void k_str_tile_scan(StrCol* cols, uint32_t ncols, uint32_t* err, Job
 
 constexpr uint32_t SD_ENTRIES = 256;   // dictionaries up to this many entries / bytes are staged in shared memory
 constexpr uint32_t SD_BYTES = 2048;
-constexpr uint32_t STAGE_BYTES = 1024; // bytes of 32 rows gathered in shared memory before one coalesced write
+constexpr uint32_t STAGE_BYTES = 2048; // per-warp ring of gathered bytes, indexed by the low bits of the global address
 
 __global__ void __launch_bounds__(128) k_str_offsets(const StrCol* __restrict__ cols, uint32_t ncols, uint32_t ntiles,
                                                      uint32_t* err) {
     __shared__ uint16_t s_doff_all[4][SD_ENTRIES + 2];
-    __shared__ uint8_t s_ddata_all[4][SD_BYTES];
-    __shared__ uint8_t s_stage_all[4][STAGE_BYTES];
+    __shared__ __align__(16) uint8_t s_ddata_all[4][SD_BYTES + 16];
+    __shared__ __align__(16) uint8_t s_stage_all[4][STAGE_BYTES];
+    __shared__ int32_t s_keys_all[4][STR_TILE];
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (warp >= ntiles) return;
     const StrCol& c = find_strcol(cols, ncols, warp);
@@ -1783,69 +1814,148 @@ __global__ void __launch_bounds__(128) k_str_offsets(const StrCol* __restrict__ 
     const uint64_t* bb = (const uint64_t*)c.batch_base;
     const uint64_t bbase = bb[b];
     uint64_t run = tb[tile];  // absolute byte offset of the first row of this tile
-    int32_t* offs = (int32_t*)c.offsets + (uint64_t)b * (c.batch_size + 1) + (r0 - b * c.batch_size);
+    const uint32_t batch_size = c.batch_size, mode = c.mode, dict_size = c.dict_size, colstripe = c.colstripe;
+    int32_t* offs = (int32_t*)c.offsets + (uint64_t)b * (batch_size + 1) + (r0 - b * batch_size);
     const uint8_t* dict = (const uint8_t*)c.dict_data;
     const int32_t* doff = (const int32_t*)c.dict_off;
+    const int32_t* lens = (const int32_t*)c.lens + r0;
+    const uint32_t* valid = (const uint32_t*)c.valid;
     uint8_t* data = (uint8_t*)c.data;
+    // the tile's lengths / keys first: all loads in flight at once instead of one dependent load per 32 rows
+    int32_t* s_keys = s_keys_all[threadIdx.x >> 5];
+#pragma unroll
+    for (uint32_t j = 0; j < STR_TILE; j += 256) {
+        int32_t t[8];
+#pragma unroll
+        for (uint32_t u = 0; u < 8; u++) {
+            const uint32_t i = j + u * 32 + lane;
+            t[u] = i < nr ? lens[i] : 0;
+        }
+#pragma unroll
+        for (uint32_t u = 0; u < 8; u++) s_keys[j + u * 32 + lane] = t[u];
+    }
+    __syncwarp();
     // small dictionaries live in shared memory for the whole tile
     bool sdict = false;
-    if (c.mode == 1 && nr > 0 && c.dict_size <= SD_ENTRIES) {
-        const uint32_t dbytes = (uint32_t)doff[c.dict_size];
+    if (mode == 1 && nr > 0 && dict_size <= SD_ENTRIES) {
+        const uint32_t dbytes = (uint32_t)doff[dict_size];
         if (dbytes <= SD_BYTES) {
             sdict = true;
-            for (uint32_t i = lane; i <= c.dict_size; i += 32) s_doff[i] = (uint16_t)doff[i];
+            for (uint32_t i = lane; i <= dict_size; i += 32) s_doff[i] = (uint16_t)doff[i];
             for (uint32_t i = lane; i < dbytes; i += 32) s_ddata[i] = dict[i];
             __syncwarp();
         }
     }
-    if (c.mode == 1 && c.data_cap && data) {
+    if (mode == 1 && c.data_cap && data) {
         // uniform entry length L (1..4), no nulls: offsets are an arithmetic progression and every row copies L bytes
         const uint32_t L = (uint32_t)c.data_cap;
-        const int32_t* keys = (const int32_t*)c.lens;
         const uint32_t rel0 = (uint32_t)(run - bbase);
         uint8_t* dp = data + run;
         for (uint32_t i = lane; i < nr; i += 32) {
             offs[i] = (int32_t)(rel0 + i * L);
-            const uint32_t key = (uint32_t)keys[r0 + i];
-            if (key < c.dict_size) {
+            const uint32_t key = (uint32_t)s_keys[i];
+            if (key < dict_size) {
                 const uint8_t* sp = sdict ? s_ddata + key * L : dict + key * L;
                 for (uint32_t k = 0; k < L; k++) dp[i * L + k] = sp[k];
             }
         }
-    } else
-    for (uint32_t i0 = 0; i0 < nr; i0 += 32) {
-        const uint32_t i = i0 + lane;
-        int32_t key = -1;
-        const uint32_t l = i < nr ? str_row_len(c, r0 + i, err, &key) : 0;
-        // a single length is below 2^31, 32 of them fit 64 bits easily; the prefix inside the step is done on
-        // 32-bit halves only when it cannot overflow
-        const uint64_t inc = warp_incl_scan64(l, lane);
-        const uint64_t abs0 = run + inc - l;
-        if (i < nr) offs[i] = (int32_t)(abs0 - bbase);
-        const uint32_t B = (uint32_t)__shfl_sync(FULL, inc, 31);
-        if (c.mode == 1 && data) {
-            if (sdict && B <= STAGE_BYTES) {
-                if (key >= 0) {
-                    const uint32_t so = s_doff[key];
-                    const uint32_t ro = (uint32_t)(inc - l);
-                    for (uint32_t k = 0; k < l; k++) s_stage[ro + k] = s_ddata[so + k];
+    } else {
+        // `fl`: bytes below this absolute address are in global memory; [fl, data + run) waits in the ring
+        const uint64_t d0 = (uint64_t)(uintptr_t)data;
+        uint64_t fl = d0 + run;
+        constexpr uint32_t RING = STAGE_BYTES - 1;
+        for (uint32_t i0 = 0; i0 < nr; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            int32_t key = -1;
+            uint32_t l = 0, so = 0;
+            if (i < nr) {
+                const int32_t x = s_keys[i];
+                if (mode == 0) {
+                    l = (uint32_t)x;
+                } else {
+                    bool ok = true;
+                    if (valid) ok = (valid[(r0 + i) >> 5] >> ((r0 + i) & 31)) & 1;
+                    if (ok) {
+                        if ((uint32_t)x >= dict_size) {  // DictionaryArray::try_new rejects out-of-range valid keys
+                            set_err(err, colstripe, ORCB_ARROW);
+                        } else {
+                            key = x;
+                            if (sdict) {
+                                so = s_doff[x];
+                                l = (uint32_t)s_doff[x + 1] - so;
+                            } else {
+                                so = (uint32_t)doff[x];
+                                l = (uint32_t)doff[x + 1] - so;
+                            }
+                        }
+                    }
                 }
-                __syncwarp();
-                uint8_t* dp = data + run;
-                for (uint32_t k = lane; k < B; k += 32) dp[k] = s_stage[k];
-                __syncwarp();
-            } else if (key >= 0) {
-                const uint8_t* sp = dict + doff[key];
-                uint8_t* dp = data + abs0;
-                for (uint32_t k = 0; k < l; k++) dp[k] = sp[k];
             }
+            // a single length is below 2^31: the prefix of 32 of them fits 32 bits unless one is huge
+            uint64_t inc;
+            if (__any_sync(FULL, l >> 26)) inc = warp_incl_scan64(l, lane);
+            else inc = warp_incl_scan(l, lane);
+            const uint64_t abs0 = run + inc - l;
+            if (i < nr) offs[i] = (int32_t)(abs0 - bbase);
+            const uint64_t B64 = __shfl_sync(FULL, inc, 31);
+            if (mode == 1 && data) {
+                if (sdict && B64 <= STAGE_BYTES - 32) {
+                    if (l) {
+                        // own string -> ring, whole words where the destination is word aligned
+                        uint32_t d = (uint32_t)(d0 + abs0), sidx = so, rem = l;
+                        while ((d & 3) && rem) { s_stage[d & RING] = s_ddata[sidx]; d++; sidx++; rem--; }
+                        if (rem >= 4) {
+                            const uint32_t* sw = (const uint32_t*)s_ddata;
+                            uint32_t wi = sidx >> 2;
+                            const uint32_t sel = 0x3210u + 0x1111u * (sidx & 3);
+                            uint32_t w0 = sw[wi];
+                            do {
+                                const uint32_t w1 = sw[++wi];
+                                *(uint32_t*)(s_stage + (d & RING)) = __byte_perm(w0, w1, sel);
+                                w0 = w1;
+                                d += 4; sidx += 4; rem -= 4;
+                            } while (rem >= 4);
+                        }
+                        while (rem) { s_stage[d & RING] = s_ddata[sidx]; d++; sidx++; rem--; }
+                    }
+                    __syncwarp();
+                    // write what is complete: leading bytes up to a 16-byte boundary (first round only), then 16-byte groups
+                    const uint64_t end = d0 + run + B64;
+                    if (fl & 15) {
+                        uint64_t h = (fl + 15) & ~(uint64_t)15;
+                        if (h > end) h = end;
+                        if (fl + lane < h) *(uint8_t*)(uintptr_t)(fl + lane) = s_stage[(uint32_t)(fl + lane) & RING];
+                        fl = h;
+                    }
+                    const uint64_t e16 = end & ~(uint64_t)15;
+                    for (uint64_t g = fl + 16u * lane; g < e16; g += 512)
+                        *(uint4*)(uintptr_t)g = *(const uint4*)(s_stage + ((uint32_t)g & RING));
+                    if (e16 > fl) fl = e16;
+                    __syncwarp();
+                } else {
+                    // drain the ring, then every lane copies its own string
+                    const uint64_t cur_end = d0 + run;
+                    for (uint64_t g = fl + lane; g < cur_end; g += 32) *(uint8_t*)(uintptr_t)g = s_stage[(uint32_t)g & RING];
+                    __syncwarp();
+                    if (key >= 0) {
+                        const uint8_t* sp = dict + so;
+                        uint8_t* dp = data + abs0;
+                        for (uint32_t k = 0; k < l; k++) dp[k] = sp[k];
+                    }
+                    fl = cur_end + B64;
+                }
+            }
+            run += B64;
         }
-        run += B;
+        if (mode == 1 && data) {
+            const uint64_t cur_end = d0 + run;
+            for (uint64_t g = fl + lane; g < cur_end; g += 32) *(uint8_t*)(uintptr_t)g = s_stage[(uint32_t)g & RING];
+        }
     }
     // closing offset of the batch
-    const uint32_t brow0 = b * c.batch_size;
-    const uint32_t brows = min(c.batch_size, c.n_rows - brow0);
-    if (lane == 0 && r0 + nr == brow0 + brows) ((int32_t*)c.offsets)[(uint64_t)b * (c.batch_size + 1) + brows] = (int32_t)(bb[b + 1] - bbase);
+    const uint32_t brow0 = b * batch_size;
+    const uint32_t brows = min(batch_size, c.n_rows - brow0);
+    if (lane == 0 && r0 + nr == brow0 + brows) ((int32_t*)c.offsets)[(uint64_t)b * (batch_size + 1) + brows] = (int32_t)(bb[b + 1] - bbase);
 }
 
 // ------------------------------------------------------------------------------------------------
