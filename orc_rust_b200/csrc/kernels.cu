@@ -1363,40 +1363,64 @@ __global__ void __launch_bounds__(128) k_varint128(const Seg* __restrict__ segs,
     // bitmap in byte order.  Every window starts at the first byte of a value; terminator lanes publish the
     // end position of "their" value in shared memory, then the values are assembled one per lane per round.
     // The next window restarts right after the last terminator (a value cut by the edge is read again).
-    __shared__ uint32_t win_all[4][32 + 4];
+    // Stream bytes travel through a 512-byte ring per warp (4 aligned 128-byte chunks, indexed by the low bits
+    // of the global address): the chunk after the ones a window can touch is always in flight in a register,
+    // so the window never waits for memory.
+    __shared__ uint32_t ring_all[4][128];
     __shared__ uint8_t ends_all[4][128];
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (warp >= nseg) return;
     const Seg& s = segs[warp];
     const int lane = threadIdx.x & 31;
-    uint32_t* win = win_all[threadIdx.x >> 5];
-    uint8_t* winb = (uint8_t*)win;
+    uint32_t* ring = ring_all[threadIdx.x >> 5];
+    const uint8_t* ringb = (const uint8_t*)ring;
     uint8_t* ends = ends_all[threadIdx.x >> 5];
-    const uint8_t* in = (const uint8_t*)s.in;
     const uint32_t len = s.in_len;
     const uint32_t n = s.cnt_idx >= 0 ? cnt[s.cnt_idx] : s.n_values;
     const uint64_t obase = s.start_idx >= 0 ? dstart[s.start_idx] : s.out_start;
-    uint4* out = (uint4*)s.out;
+    const uint32_t colstripe = s.colstripe;
+    uint4* out = (uint4*)s.out + obase;
     uint32_t produced = 0;
     uint32_t cur = s.start_byte;
     const uint32_t lt = (1u << lane) - 1;
-    if (lane < 4) win[32 + lane] = 0;
+    if (n == 0) return;
+    const uint64_t a0 = (uint64_t)(uintptr_t)s.in;
+    const uint64_t a_lim = a0 + len + 128;  // chunks are fetched only below this address (inside the arena slack)
+    auto fetch = [&](uint64_t chunk) -> uint32_t {
+        const uint64_t a = chunk + 4u * lane;
+        return a < a_lim ? __ldg((const uint32_t*)(uintptr_t)a) : 0u;
+    };
+    uint64_t loaded_end = (a0 + cur) & ~(uint64_t)127;
+    {
+        const uint32_t w0 = fetch(loaded_end), w1 = fetch(loaded_end + 128), w2 = fetch(loaded_end + 256);
+        ring[((uint32_t)(loaded_end >> 2) + lane) & 127] = w0;
+        ring[((uint32_t)(loaded_end >> 2) + 32 + lane) & 127] = w1;
+        ring[((uint32_t)(loaded_end >> 2) + 64 + lane) & 127] = w2;
+        loaded_end += 384;
+    }
+    uint32_t pend = fetch(loaded_end);
     while (produced < n) {
-        if (cur >= len) { set_err(err, s.colstripe, ORCB_IO_ERROR); return; }
+        if (cur >= len) { set_err(err, colstripe, ORCB_IO_ERROR); return; }
+        const uint64_t ca = a0 + cur;
+        if (loaded_end < (ca & ~(uint64_t)127) + 384) {
+            ring[((uint32_t)(loaded_end >> 2) + lane) & 127] = pend;
+            loaded_end += 128;
+            pend = fetch(loaded_end);
+        }
+        __syncwarp();
+        const uint32_t cb = (uint32_t)ca;  // low address bits index the ring
         uint32_t T[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const uint32_t p = cur + 32u * j + lane;
             // bytes past the end of the stream count as continuation bytes
-            const uint32_t b = p < len ? (uint32_t)__ldg(in + p) : 0x80u;
-            winb[32 * j + lane] = (uint8_t)b;
-            T[j] = __ballot_sync(FULL, !(b & 0x80));
+            const uint32_t b = ringb[(cb + 32u * j + lane) & 511];
+            T[j] = __ballot_sync(FULL, !(b & 0x80) && cur + 32u * j + lane < len);
         }
         const uint32_t c0 = __popc(T[0]), c1 = __popc(T[1]), c2 = __popc(T[2]), c3 = __popc(T[3]);
         const uint32_t total = c0 + c1 + c2 + c3;
         if (total == 0) {
             // no terminator in 128 bytes: either >= 20 continuation bytes (shift >= 128) or end of stream
-            set_err(err, s.colstripe, (len - cur >= 20) ? ORCB_VARINT_TOO_LARGE : ORCB_IO_ERROR);
+            set_err(err, colstripe, (len - cur >= 20) ? ORCB_VARINT_TOO_LARGE : ORCB_IO_ERROR);
             return;
         }
         if ((T[0] >> lane) & 1) ends[__popc(T[0] & lt)] = (uint8_t)lane;
@@ -1405,29 +1429,31 @@ __global__ void __launch_bounds__(128) k_varint128(const Seg* __restrict__ segs,
         if ((T[3] >> lane) & 1) ends[c0 + c1 + c2 + __popc(T[3] & lt)] = (uint8_t)(96 + lane);
         __syncwarp();
         const uint32_t room = n - produced;
-        for (uint32_t k0 = 0; k0 < total && k0 < room; k0 += 32) {
+        const uint32_t todo = min(total, room);
+        for (uint32_t k0 = 0; k0 < todo; k0 += 32) {
             const uint32_t k = k0 + lane;
-            const bool live = k < total && k < room;
+            const bool live = k < todo;
             const uint32_t end = live ? ends[k] : 0u;
             const uint32_t start = (live && k) ? (uint32_t)ends[k - 1] + 1 : 0u;
             const uint32_t nbv = end - start + 1;
-            const uint32_t a = start >> 2, shb = (start & 3) * 8;
+            const uint32_t sa = cb + start;  // ring byte address of the value's first byte
+            const uint32_t a = sa >> 2, shb = (sa & 3) * 8;
             if (__all_sync(FULL, !live || nbv <= 4)) {
                 // common case (values below 2^28): one 32-bit window per value, 32-bit squeeze, hi half = sign
                 if (live) {
-                    uint32_t x0 = __funnelshift_r(win[a], win[a + 1], shb);
-                    if (nbv < 4) x0 &= (1u << (8 * nbv)) - 1;
+                    uint32_t x0 = __funnelshift_r(ring[a & 127], ring[(a + 1) & 127], shb);
+                    x0 &= 0xffffffffu >> (32 - 8 * nbv);
                     const uint32_t g = (x0 & 0x7fu) | ((x0 & 0x7f00u) >> 1) | ((x0 & 0x7f0000u) >> 2) | ((x0 & 0x7f000000u) >> 3);
                     const uint32_t sgn = 0u - (g & 1);
-                    out[obase + produced + k] = make_uint4((g >> 1) ^ sgn, sgn, sgn, sgn);
+                    out[produced + k] = make_uint4((g >> 1) ^ sgn, sgn, sgn, sgn);
                 }
                 continue;
             }
             if (!live) continue;
             uint64_t lo, hi = 0;
             if (nbv <= 8) {
-                // 8 little-endian bytes starting at `start` (window is padded), 7-bit groups squeezed together
-                const uint32_t w0 = win[a], w1 = win[a + 1], w2 = win[a + 2];
+                // 8 little-endian bytes starting at the value, 7-bit groups squeezed together
+                const uint32_t w0 = ring[a & 127], w1 = ring[(a + 1) & 127], w2 = ring[(a + 2) & 127];
                 uint32_t x0 = __funnelshift_r(w0, w1, shb), x1 = __funnelshift_r(w1, w2, shb);
                 if (nbv < 4) x0 &= (1u << (8 * nbv)) - 1;
                 if (nbv <= 4) x1 = 0;
@@ -1436,10 +1462,10 @@ __global__ void __launch_bounds__(128) k_varint128(const Seg* __restrict__ segs,
                 const uint32_t g1 = (x1 & 0x7fu) | ((x1 & 0x7f00u) >> 1) | ((x1 & 0x7f0000u) >> 2) | ((x1 & 0x7f000000u) >> 3);
                 lo = (uint64_t)g0 | ((uint64_t)g1 << 28);
             } else {
-                if (nbv > 19) set_err(err, s.colstripe, ORCB_VARINT_TOO_LARGE);  // shift >= 128
+                if (nbv > 19) set_err(err, colstripe, ORCB_VARINT_TOO_LARGE);  // shift >= 128
                 lo = 0;
                 for (uint32_t q = 0; q < nbv && q < 19; q++) {
-                    const uint64_t x = winb[start + q] & 0x7f;
+                    const uint64_t x = ringb[(sa + q) & 511] & 0x7f;
                     const uint32_t sft = 7 * q;
                     if (sft < 64) {
                         lo |= x << sft;
@@ -1453,7 +1479,7 @@ __global__ void __launch_bounds__(128) k_varint128(const Seg* __restrict__ segs,
             const uint64_t sgn = 0ull - (lo & 1);
             const uint64_t rlo = ((lo >> 1) | (hi << 63)) ^ sgn;
             const uint64_t rhi = (hi >> 1) ^ sgn;
-            out[obase + produced + k] = make_uint4((uint32_t)rlo, (uint32_t)(rlo >> 32), (uint32_t)rhi, (uint32_t)(rhi >> 32));
+            out[produced + k] = make_uint4((uint32_t)rlo, (uint32_t)(rlo >> 32), (uint32_t)rhi, (uint32_t)(rhi >> 32));
         }
         produced += total;
         cur += (uint32_t)ends[total - 1] + 1;
@@ -1901,22 +1927,35 @@ __global__ void __launch_bounds__(128) k_str_offsets(const StrCol* __restrict__ 
             if (mode == 1 && data) {
                 if (sdict && B64 <= STAGE_BYTES - 32) {
                     if (l) {
-                        // own string -> ring, whole words where the destination is word aligned
-                        uint32_t d = (uint32_t)(d0 + abs0), sidx = so, rem = l;
-                        while ((d & 3) && rem) { s_stage[d & RING] = s_ddata[sidx]; d++; sidx++; rem--; }
-                        if (rem >= 4) {
-                            const uint32_t* sw = (const uint32_t*)s_ddata;
-                            uint32_t wi = sidx >> 2;
-                            const uint32_t sel = 0x3210u + 0x1111u * (sidx & 3);
-                            uint32_t w0 = sw[wi];
-                            do {
-                                const uint32_t w1 = sw[++wi];
-                                *(uint32_t*)(s_stage + (d & RING)) = __byte_perm(w0, w1, sel);
-                                w0 = w1;
-                                d += 4; sidx += 4; rem -= 4;
-                            } while (rem >= 4);
+                        // own string -> ring: bytes up to a word boundary of the destination, whole words, trailing
+                        // bytes; source words are read unaligned (two aligned words + byte permute)
+                        const uint32_t* sw = (const uint32_t*)s_ddata;
+                        uint32_t d = (uint32_t)(d0 + abs0);
+                        const uint32_t nh = min((0u - d) & 3u, l);
+                        if (nh) {
+                            const uint32_t hw = __byte_perm(sw[so >> 2], sw[(so >> 2) + 1], 0x3210u + 0x1111u * (so & 3));
+                            s_stage[d & RING] = (uint8_t)hw;
+                            if (nh > 1) s_stage[(d + 1) & RING] = (uint8_t)(hw >> 8);
+                            if (nh > 2) s_stage[(d + 2) & RING] = (uint8_t)(hw >> 16);
                         }
-                        while (rem) { s_stage[d & RING] = s_ddata[sidx]; d++; sidx++; rem--; }
+                        d += nh;
+                        const uint32_t sidx = so + nh;
+                        uint32_t rem = l - nh, wi = sidx >> 2;
+                        const uint32_t sel = 0x3210u + 0x1111u * (sidx & 3);
+                        uint32_t w0 = sw[wi];
+                        while (rem >= 4) {
+                            const uint32_t w1 = sw[++wi];
+                            *(uint32_t*)(s_stage + (d & RING)) = __byte_perm(w0, w1, sel);
+                            w0 = w1;
+                            d += 4;
+                            rem -= 4;
+                        }
+                        if (rem) {
+                            const uint32_t tw = __byte_perm(w0, sw[wi + 1], sel);
+                            s_stage[d & RING] = (uint8_t)tw;
+                            if (rem > 1) s_stage[(d + 1) & RING] = (uint8_t)(tw >> 8);
+                            if (rem > 2) s_stage[(d + 2) & RING] = (uint8_t)(tw >> 16);
+                        }
                     }
                     __syncwarp();
                     // write what is complete: leading bytes up to a 16-byte boundary (first round only), then 16-byte groups
