@@ -598,7 +598,14 @@ __device__ __forceinline__ uint32_t parse_run2(const Seg& s, uint32_t cur, RunSl
     }
     if (slow) {
         cls = RC_CONST;
-        return parse_delta_slow(in, len, cur, nb, sg, rl, &d.base, &d.step, &bytes_out);
+        // results come back through locals so that the caller's RunSlot can stay in registers
+        uint64_t sb = 0, ss = 0;
+        uint32_t sbytes = 0;
+        const uint32_t st = parse_delta_slow(in, len, cur, nb, sg, rl, &sb, &ss, &sbytes);
+        d.base = sb;
+        d.step = ss;
+        bytes_out = sbytes;
+        return st;
     }
     const int64_t last = base + (int64_t)(rl - 1) * d0;
     if (trunc_n(last, nb) != last) return ORCB_OUT_OF_SPEC;
@@ -853,7 +860,9 @@ __device__ __forceinline__ bool int_rle_block(const Seg* __restrict__ segs, cons
     const uint32_t room = n - rec.out_off;
     const uint64_t out_pos = obase + rec.out_off;
     __syncwarp();
-    RunSlot& my = slots[lane];
+    // the fast kernel keeps its run in registers; general blocks publish theirs for the per-value search
+    RunSlot my_reg;
+    RunSlot& my = FAST ? my_reg : slots[lane];
     uint32_t cls = RC_NONE, rl = 0, nbytes = 0, take = 0;
     bool failed = false;
     if (active) {
@@ -877,7 +886,7 @@ __device__ __forceinline__ bool int_rle_block(const Seg* __restrict__ segs, cons
     }
     const uint32_t emit = (cls == RC_CONST || cls == RC_DIRECT) ? take : 0u;
     const uint32_t incl = warp_incl_scan(emit, lane);
-    my.prefix = incl;
+    if (!FAST) my.prefix = incl;
     const uint32_t total = __shfl_sync(FULL, incl, 31);
     const int nb = s.nbytes;
     const bool sg = (s.flags & SEG_SIGNED) != 0;
@@ -1146,12 +1155,11 @@ __global__ void __launch_bounds__(RLE_WARPS * 32) k_int_rle(const Seg* __restric
                                                             const uint32_t* __restrict__ cnt,
                                                             const uint32_t* __restrict__ dstart, uint32_t* err,
                                                             uint32_t* mis, uint32_t* slow_list, uint32_t* slow_count) {
-    __shared__ RunSlot slots_all[RLE_WARPS][32];
     __shared__ int64_t tile_all[RLE_WARPS][TILE_VALUES];
     const uint32_t nblocks = *nblocks_ptr;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
     const int lane = threadIdx.x & 31;
-    RunSlot* slots = slots_all[threadIdx.x >> 5];
+    RunSlot* slots = nullptr;
     // persistent warps: the number of run blocks is only known on the device
     for (uint32_t blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; blk < nblocks; blk += nwarps) {
         const bool done = int_rle_block<true>(segs, blocks[blk], table + (uint64_t)blk * 32, cnt, dstart, err, mis, nullptr,
@@ -1818,14 +1826,15 @@ __global__ void k_str_tile_scan(StrCol* cols, uint32_t ncols, uint32_t* err, Job
 
 constexpr uint32_t SD_ENTRIES = 256;   // dictionaries up to this many entries / bytes are staged in shared memory
 constexpr uint32_t SD_BYTES = 2048;
-constexpr uint32_t STAGE_BYTES = 2048; // per-warp ring of gathered bytes, indexed by the low bits of the global address
+constexpr uint32_t KEY_GROUP = 256;    // lengths / keys are fetched this many rows ahead (8 loads per lane in flight)
+constexpr uint32_t STAGE_BYTES = 1024; // per-warp ring of gathered bytes, indexed by the low bits of the global address
 
 __global__ void __launch_bounds__(128) k_str_offsets(const StrCol* __restrict__ cols, uint32_t ncols, uint32_t ntiles,
                                                      uint32_t* err) {
     __shared__ uint16_t s_doff_all[4][SD_ENTRIES + 2];
     __shared__ __align__(16) uint8_t s_ddata_all[4][SD_BYTES + 16];
     __shared__ __align__(16) uint8_t s_stage_all[4][STAGE_BYTES];
-    __shared__ int32_t s_keys_all[4][STR_TILE];
+    __shared__ int32_t s_keys_all[4][KEY_GROUP];
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (warp >= ntiles) return;
     const StrCol& c = find_strcol(cols, ncols, warp);
@@ -1847,20 +1856,7 @@ __global__ void __launch_bounds__(128) k_str_offsets(const StrCol* __restrict__ 
     const int32_t* lens = (const int32_t*)c.lens + r0;
     const uint32_t* valid = (const uint32_t*)c.valid;
     uint8_t* data = (uint8_t*)c.data;
-    // the tile's lengths / keys first: all loads in flight at once instead of one dependent load per 32 rows
     int32_t* s_keys = s_keys_all[threadIdx.x >> 5];
-#pragma unroll
-    for (uint32_t j = 0; j < STR_TILE; j += 256) {
-        int32_t t[8];
-#pragma unroll
-        for (uint32_t u = 0; u < 8; u++) {
-            const uint32_t i = j + u * 32 + lane;
-            t[u] = i < nr ? lens[i] : 0;
-        }
-#pragma unroll
-        for (uint32_t u = 0; u < 8; u++) s_keys[j + u * 32 + lane] = t[u];
-    }
-    __syncwarp();
     // small dictionaries live in shared memory for the whole tile
     bool sdict = false;
     if (mode == 1 && nr > 0 && dict_size <= SD_ENTRIES) {
@@ -1872,30 +1868,49 @@ __global__ void __launch_bounds__(128) k_str_offsets(const StrCol* __restrict__ 
             __syncwarp();
         }
     }
-    if (mode == 1 && c.data_cap && data) {
-        // uniform entry length L (1..4), no nulls: offsets are an arithmetic progression and every row copies L bytes
-        const uint32_t L = (uint32_t)c.data_cap;
-        const uint32_t rel0 = (uint32_t)(run - bbase);
-        uint8_t* dp = data + run;
-        for (uint32_t i = lane; i < nr; i += 32) {
+    const bool uniform = mode == 1 && c.data_cap && data;
+    const uint32_t L = (uint32_t)c.data_cap;  // uniform entry length (1..4), no nulls
+    const uint32_t rel0 = (uint32_t)(run - bbase);
+    uint8_t* const dp0 = data + run;
+    // `fl`: bytes below this absolute address are in global memory; [fl, data + run) waits in the ring
+    const uint64_t d0 = (uint64_t)(uintptr_t)data;
+    uint64_t fl = d0 + run;
+    constexpr uint32_t RING = STAGE_BYTES - 1;
+    // lengths / keys travel one group ahead of their use: 8 loads per lane in flight while a group is processed
+    int32_t tn[KEY_GROUP / 32];
+#pragma unroll
+    for (uint32_t u = 0; u < KEY_GROUP / 32; u++) {
+        const uint32_t i = u * 32 + lane;
+        tn[u] = i < nr ? lens[i] : 0;
+    }
+    for (uint32_t g0 = 0; g0 < nr; g0 += KEY_GROUP) {
+    __syncwarp();
+#pragma unroll
+    for (uint32_t u = 0; u < KEY_GROUP / 32; u++) s_keys[u * 32 + lane] = tn[u];
+    __syncwarp();
+#pragma unroll
+    for (uint32_t u = 0; u < KEY_GROUP / 32; u++) {
+        const uint32_t i = g0 + KEY_GROUP + u * 32 + lane;
+        tn[u] = i < nr ? lens[i] : 0;
+    }
+    const uint32_t gend = min(nr, g0 + KEY_GROUP);
+    if (uniform) {
+        // offsets are an arithmetic progression and every row copies L bytes
+        for (uint32_t i = g0 + lane; i < gend; i += 32) {
             offs[i] = (int32_t)(rel0 + i * L);
-            const uint32_t key = (uint32_t)s_keys[i];
+            const uint32_t key = (uint32_t)s_keys[i - g0];
             if (key < dict_size) {
                 const uint8_t* sp = sdict ? s_ddata + key * L : dict + key * L;
-                for (uint32_t k = 0; k < L; k++) dp[i * L + k] = sp[k];
+                for (uint32_t k = 0; k < L; k++) dp0[i * L + k] = sp[k];
             }
         }
     } else {
-        // `fl`: bytes below this absolute address are in global memory; [fl, data + run) waits in the ring
-        const uint64_t d0 = (uint64_t)(uintptr_t)data;
-        uint64_t fl = d0 + run;
-        constexpr uint32_t RING = STAGE_BYTES - 1;
-        for (uint32_t i0 = 0; i0 < nr; i0 += 32) {
+        for (uint32_t i0 = g0; i0 < gend; i0 += 32) {
             const uint32_t i = i0 + lane;
             int32_t key = -1;
             uint32_t l = 0, so = 0;
             if (i < nr) {
-                const int32_t x = s_keys[i];
+                const int32_t x = s_keys[i - g0];
                 if (mode == 0) {
                     l = (uint32_t)x;
                 } else {
@@ -1986,6 +2001,9 @@ __global__ void __launch_bounds__(128) k_str_offsets(const StrCol* __restrict__ 
             }
             run += B64;
         }
+    }
+    }
+    if (!uniform) {
         if (mode == 1 && data) {
             const uint64_t cur_end = d0 + run;
             for (uint64_t g = fl + lane; g < cur_end; g += 32) *(uint8_t*)(uintptr_t)g = s_stage[(uint32_t)g & RING];
