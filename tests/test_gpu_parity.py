@@ -228,6 +228,50 @@ def test_synthetic_configs(ob, tmp_path):
                 assert_batches_identical(got, exp, f"{name}/{comp}/index={use_index}")
 
 
+def test_string_dictionary_shapes(ob, tmp_path):
+    """Dictionary-string gather paths: tiny uniform entries, short mixed entries (shared-memory ring), long
+    entries of a small dictionary (ring bypass inside a tile), a dictionary too large for shared memory,
+    direct encoding, all with and without nulls, at batch sizes that are not multiples of the tile."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tools"))
+    import gen_orc
+    import numpy as np
+    import pyarrow as pa
+    from oracle import orc_oracle as oo
+    rng = np.random.default_rng(7)
+    n = 50_000
+
+    def col(words, null_frac):
+        idx = rng.integers(0, len(words), n)
+        vals = [words[i] for i in idx]
+        if null_frac:
+            mask = rng.random(n) < null_frac
+            vals = [None if m else v for v, m in zip(vals, mask)]
+        return pa.array(vals, type=pa.string())
+
+    flags = ["A", "N", "R"]
+    codes = ["AIR", "FOB", "MAIL", "RAIL", "SHIP", "TRUCK", "REG AIR", ""]
+    longish = ["x" * k for k in (1, 3, 40, 61, 75, 90, 2, 33)] + ["é" * 30]
+    big = ["w%05d-%s" % (i, "z" * (i % 23)) for i in range(900)]
+    uniq = ["row %d of the direct column %s" % (i, "q" * (i % 11)) for i in range(n)]
+    cols = {}
+    for nm, words in (("flags", flags), ("codes", codes), ("longish", longish), ("big", big)):
+        cols[nm] = col(words, 0.0)
+        cols[nm + "_n"] = col(words, 0.3)
+    cols["direct"] = pa.array(uniq, type=pa.string())
+    cols["direct_n"] = pa.array([None if i % 7 == 0 else u for i, u in enumerate(uniq)], type=pa.string())
+    table = pa.table(cols)
+    for comp in ("uncompressed", "snappy"):
+        p = str(tmp_path / f"strings_{comp}.orc")
+        gen_orc.write(table, p, compression=comp, block_size=64 << 10)
+        data = open(p, "rb").read()
+        for bs in (8192, 1000, 3333):
+            exp = oo.OracleFile(data).read(batch_size=bs)
+            for use_index in (True, False):
+                got = list(ob.ArrowReaderBuilder.try_new(data).with_batch_size(bs).with_row_index(use_index).build())
+                assert_batches_identical(got, exp, f"strings/{comp}/bs={bs}/index={use_index}")
+
+
 # ---- chunk framing + Snappy / LZ4 blocks with real back-references (src/compression.rs) ----------------
 @pytest.mark.parametrize("kind", ["snappy", "lz4"])
 def test_decompress_streams_vs_oracle(ob, kind):
