@@ -84,7 +84,8 @@ __device__ __forceinline__ bool in_range_n(__int128 v, int nbytes) {
 }
 // rle_v2_decode_bit_width (integer/util.rs:370-384)
 __device__ __forceinline__ int width_of(uint32_t code) {
-    return code <= 23 ? (int)code + 1 : (code == 24 ? 26 : code == 25 ? 28 : code == 26 ? 30 : code == 27 ? 32 : (int)(code - 23) * 8);
+    // codes 24..31 -> 26, 28, 30, 32, 40, 48, 56, 64: one byte select out of two constants
+    return code <= 23 ? (int)code + 1 : (int)(__byte_perm(0x201E1C1Au, 0x40383028u, code - 24) & 0xffu);
 }
 // get_closest_fixed_bits (integer/util.rs:407-421)
 __device__ __forceinline__ int closest_fixed_bits(int n) {
@@ -665,12 +666,14 @@ __device__ __forceinline__ uint32_t parse_run1(const SegCtx& c, uint32_t cur, ui
 
 
 // Header-only walk: length in values and bytes of the run at `cur` (no values produced).
+// KNOWN_V2: the caller has already checked the segment's RLE version (hot loop of the run index).
+template <bool KNOWN_V2 = false>
 __device__ __forceinline__ uint32_t measure_run(const Seg& s, uint32_t cur, uint32_t& rl_out, uint32_t& bytes_out,
                                                 bool& coop) {
     coop = false;
     const uint8_t* in = (const uint8_t*)s.in;
     const uint32_t len = s.in_len;
-    if (!(s.flags & SEG_RLE_V2)) {
+    if (!KNOWN_V2 && !(s.flags & SEG_RLE_V2)) {
         // RLE v1 (integer/rle_v1.rs:54-68)
         const int8_t h = (int8_t)in[cur];
         uint32_t p = cur + 1;
@@ -704,7 +707,7 @@ __device__ __forceinline__ uint32_t measure_run(const Seg& s, uint32_t cur, uint
     const uint32_t kind = h0 >> 6;
     const uint32_t code = (h0 >> 1) & 31;
     const uint32_t rl = (((h0 & 1) << 8) | b1) + 1;
-    const uint32_t w = code < 24 ? code + 1 : (uint32_t)(0x40383028201E1C1Aull >> ((code - 24) * 8)) & 0xffu;
+    const uint32_t w = (uint32_t)width_of(code);
     rl_out = kind == 0 ? (h0 & 7) + 3 : rl;
     bytes_out = kind == 0 ? 2 + ((h0 >> 3) & 7) : 2 + (rl * w + 7) / 8;
     coop = kind == 2 || (kind == 1 && rl >= COOP_MIN_RUN) || (kind == 3 && code != 0);
@@ -774,20 +777,24 @@ __global__ void __launch_bounds__(128) k_rle_index(const Seg* __restrict__ segs,
         cur += nbytes;
     }
     uint32_t blk = 0xffffffffu, in_blk = 0, blk_skip = skip;
-    uint32_t pf_next = cur & ~127u;
+    const bool v2 = (s.flags & SEG_RLE_V2) != 0;
+    const uint32_t len = s.in_len;
+    RunRec* slot = nullptr;
+    // every instruction of this loop sits on the segment's serial chain: keep it short
     while (produced < n) {
-        if (cur + 256 >= pf_next) {
-            if (pf_next < s.in_len) asm volatile("prefetch.global.L1 [%0];" ::"l"((const uint8_t*)s.in + pf_next));
-            pf_next += 128;
-        }
         if (in_blk == 0) {
             blk = atomicAdd(nblocks, 1u);
             if (blk >= pool_blocks) { set_err(err, s.colstripe, ORCB_UNEXPECTED); blk = 0xffffffffu; break; }
+            slot = table + (uint64_t)blk * 32;
         }
-        bool stop = cur >= s.in_len;  // k_int_rle reports "not enough values" for this record
+        bool stop = cur >= len;  // k_int_rle reports "not enough values" for this record
         uint32_t rl = 0, nbytes = 0;
         bool cq = false;
-        if (!stop) stop = measure_run(s, cur, rl, nbytes, cq) != 0;  // k_int_rle re-parses the run and reports the error
+        if (!stop) {
+            // k_int_rle re-parses a run that does not parse here and reports the error
+            if (v2) stop = measure_run<true>(s, cur, rl, nbytes, cq) != 0;
+            else stop = measure_run<false>(s, cur, rl, nbytes, cq) != 0;
+        }
         RunRec r;
         r.byte_off = cur;
         r.out_off = produced;
@@ -804,10 +811,10 @@ __global__ void __launch_bounds__(128) k_rle_index(const Seg* __restrict__ segs,
                 r.out_off |= RUN_QUEUED;
             }
         }
-        table[(uint64_t)blk * 32 + in_blk] = r;
+        *slot++ = r;
         in_blk++;
         if (!stop) {
-            produced += min(rl > skip ? rl - skip : 0u, n - produced);
+            produced += min(rl - min(skip, rl), n - produced);
             skip = 0;
             cur += nbytes;
         }
