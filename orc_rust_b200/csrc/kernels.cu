@@ -2062,7 +2062,23 @@ __global__ void __launch_bounds__(128) k_repack(const RepackDesc* __restrict__ d
 // blocks are decoded by one warp per chunk: lane 0 walks the tags, all lanes move the bytes.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void warp_copy_fwd(uint8_t* dst, const uint8_t* src, uint32_t n, int lane) {
-    for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
+    if (n < 256) {
+        for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
+        return;
+    }
+    // long copies (original chunks, incompressible literals): whole words where dst is word aligned, the source
+    // words funnel-shifted into place (reads up to 7 bytes past the source, inside the arena slack)
+    const uint32_t head = (uint32_t)(0u - (uint32_t)(uintptr_t)dst) & 3u;
+    if ((uint32_t)lane < head) dst[lane] = src[lane];
+    const uint32_t nw = (n - head) >> 2;
+    uint32_t* dw = (uint32_t*)(dst + head);
+    const uintptr_t sa = (uintptr_t)(src + head);
+    const uint32_t* sw = (const uint32_t*)(sa & ~(uintptr_t)3);
+    const uint32_t shb = (uint32_t)(sa & 3) * 8;
+#pragma unroll 4
+    for (uint32_t i = lane; i < nw; i += 32) dw[i] = __funnelshift_r(__ldg(sw + i), __ldg(sw + i + 1), shb);
+    const uint32_t done = head + nw * 4;
+    if (done + lane < n) dst[done + lane] = src[done + lane];
 }
 // overlapping back-reference: dst[i] = dst[i - dist]; bytes further than `dist` ahead depend on bytes
 // written earlier in this same copy, so copy in rounds of `dist` bytes when dist < 32
