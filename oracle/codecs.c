@@ -530,6 +530,9 @@ int orc_oracle_offsets(const int64_t *lengths, size_t n, int32_t *offsets) {
     int64_t acc = 0;
     offsets[0] = 0;
     for (size_t i = 0; i < n; i++) {
+        /* an unsigned length >= 2^63 arrives as a negative i64; `l as usize` then overflows
+         * OffsetBuffer::from_lengths (a panic in the reference, reported as OutOfSpec here) */
+        if (lengths[i] < 0) return ERR_OUT_OF_SPEC;
         acc += lengths[i];
         if (acc > INT32_MAX) return ERR_OFFSET_OVERFLOW;
         offsets[i + 1] = (int32_t)acc;

@@ -427,7 +427,10 @@ class OracleFile:
                     _check(lib().orc_oracle_offsets(_u8p(dl), ctypes.c_size_t(dict_size), _u8p(doff)), "dict offsets")
                     ddata = self._stream(smap, cid, S_DICTIONARY_DATA)
                     if ddata.size < int(doff[-1]):
-                        ddata = np.concatenate([ddata, np.zeros(int(doff[-1]) - ddata.size, np.uint8)])
+                        # the dictionary is built by the same next_byte_batch as direct strings (string.rs:65-74):
+                        # offsets past the bytes that could be read fail GenericByteArray::try_new
+                        raise OracleError(18, "dictionary data shorter than its lengths")
+                    _validate_utf8(ddata, doff)  # the dictionary is a StringArray of its own
                     keys = int_rle(self._stream(smap, cid, S_DATA), nn, False, 8, ver)
                     payload = ("dict", keys, doff, np.ascontiguousarray(ddata))
                 else:
@@ -588,7 +591,14 @@ def _slice_to_arrow(typ, present, payload, rows, a, b):
 
 
 def _validate_utf8(data: np.ndarray, offs: np.ndarray):
+    """GenericByteArray::<Utf8>::try_new (string.rs:150-151): the bytes the offsets cover are one valid UTF-8
+    string and every offset falls on a character boundary."""
+    used = data[:int(offs[-1])]
     try:
-        data.tobytes().decode("utf-8")
-    except UnicodeDecodeError as e:  # GenericByteArray::<Utf8>::try_new validation (string.rs:150-151)
+        used.tobytes().decode("utf-8")
+    except UnicodeDecodeError as e:
         raise OracleError(18, f"invalid utf-8: {e}")
+    inner = np.asarray(offs[:-1], dtype=np.int64)
+    inner = inner[inner < used.size]
+    if inner.size and np.any((used[inner] & 0xC0) == 0x80):
+        raise OracleError(18, "invalid utf-8: value starts inside a character")

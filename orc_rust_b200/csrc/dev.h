@@ -97,6 +97,8 @@ struct CopyDesc {
     uint32_t width;
     uint32_t src_len;    // available source bytes (bound; IoError if short)
     uint32_t colstripe;
+    int32_t u8_col;      // >= 0: string DATA, validated as UTF-8 on the way through (index of its StrCol)
+    uint32_t pad;
 };
 
 // dense values -> row slots of one row group (decode_spaced)
@@ -156,7 +158,15 @@ struct StrCol {
     uint32_t tile0;      // first global tile index of this column (for the tile -> column map)
     uint32_t data_len;   // direct: bytes available in the DATA stream
     uint32_t meta_slot;  // index of this column's data pointer in the per-job pointer table
+    // UTF-8 validation (GenericByteArray::<Utf8>::try_new, string.rs:150-151): the bytes every value is cut
+    // from (DATA stream / dictionary bytes) are checked tile by tile before their real length is known
+    uint64_t u8_src;     // bytes to validate, 0 = BINARY column
+    uint64_t u8_bad;     // u32[2] in the zeroed arena: [0] max over invalid characters of ~position (0 = none), [1] any non-ASCII byte
+    uint64_t u8_flags;   // u32 bitmap in the zeroed arena: U8_TILE-byte tiles that hold non-ASCII bytes
+    uint32_t u8_len;     // bytes behind u8_src
+    uint32_t u8_pad;
 };
+constexpr uint32_t U8_TILE = 16384;
 
 // stripe-level bitmap -> per-batch bitmaps (+ null counts)
 struct RepackDesc {

@@ -325,6 +325,7 @@ void Job::plan() {
     place(o_scan_, scans_.size() * sizeof(ScanDesc));
     place(o_copy_, copies_.size() * sizeof(CopyDesc));
     place(o_ctile_, copy_tiles_.size() * sizeof(uint2));
+    place(o_u8tile_, u8_tiles_.size() * sizeof(uint2));
     place(o_sp_, spaced_.size() * sizeof(SpacedDesc));
     place(o_sp2_, spaced_late_.size() * sizeof(SpacedDesc));
     place(o_dec_, decfix_.size() * sizeof(DecFixDesc));
@@ -718,6 +719,7 @@ void Job::plan_stripe(uint32_t task_idx) {
             d.width = width;
             d.src_len = src_len;
             d.colstripe = cs;
+            d.u8_col = -1;
             const uint32_t di = (uint32_t)copies_.size();
             copies_.push_back(d);
             ab_copy_ += 2 * max_bytes;
@@ -894,12 +896,31 @@ void Job::plan_stripe(uint32_t task_idx) {
                     cp.str_data = alloc(AR_OUT, (uint64_t)s_data.len + 16);
                     sc.data = cp.str_data;
                     sc.data_len = s_data.len;
-                    if (s_data.len) add_copy(s_data.ptr, s_data.len, cp.str_data, s_data.len, -1, 1, s_data.len);
+                    if (s_data.len) {
+                        add_copy(s_data.ptr, s_data.len, cp.str_data, s_data.len, -1, 1, s_data.len);
+                        if (k != T_BINARY) copies_.back().u8_col = (int32_t)strcols_.size();  // validated on the way through
+                    }
                     n_segments_ += 1;
                 }
                 if (has_present) add_spaced(dense_i32, rows_i32, 4, false);
                 // lengths/keys read twice (tile sums, offsets) + offsets written; gathered bytes added in finish()
                 ab_str_ += (uint64_t)n_rows * 12;
+                if (k != T_BINARY) {
+                    // Utf8 arrays are validated (string.rs:150-151): direct = the DATA stream, dictionary = its bytes
+                    const StreamRef& u8 = use_dict ? s_dict : s_data;
+                    if (u8.present && u8.len) {
+                        sc.u8_src = u8.ptr;
+                        sc.u8_len = u8.len;
+                        sc.u8_bad = alloc(AR_ZERO, 16);
+                        const uint32_t nt = (uint32_t)(((uint64_t)u8.len + 15) / U8_TILE + 1);  // tiles are cut at aligned addresses
+                        sc.u8_flags = alloc(AR_ZERO, ((uint64_t)nt + 32) / 32 * 4 + 16);
+                        if (use_dict) {
+                            // dictionary bytes get their own pass; direct DATA is checked by the copy kernel
+                            for (uint32_t t = 0; t < nt; t++) u8_tiles_.push_back(make_uint2((uint32_t)strcols_.size(), t));
+                            ab_utf8_ += u8.len;
+                        }
+                    }
+                }
                 strcols_.push_back(sc);
                 break;
             }
@@ -1034,6 +1055,7 @@ void Job::stage() {
     for (auto& d : ts_) { R(d.secs); R(d.nanos); R(d.out); }
     for (auto& c : strcols_) {
         R(c.lens); R(c.valid); R(c.dict_len); R(c.dict_off); R(c.dict_data); R(c.offsets); R(c.tile_base); R(c.data);
+        R(c.u8_src); R(c.u8_bad); R(c.u8_flags);
         c.batch_base = (uint64_t)(uintptr_t)(d_meta_ + o_bbase_ + c.batch_base);
     }
     for (auto& d : repacks_) { R(d.src); R(d.dst); }
@@ -1053,6 +1075,7 @@ void Job::stage() {
     put(o_scan_, scans_.data(), scans_.size() * sizeof(ScanDesc));
     put(o_copy_, copies_.data(), copies_.size() * sizeof(CopyDesc));
     put(o_ctile_, copy_tiles_.data(), copy_tiles_.size() * sizeof(uint2));
+    put(o_u8tile_, u8_tiles_.data(), u8_tiles_.size() * sizeof(uint2));
     put(o_sp_, spaced_.data(), spaced_.size() * sizeof(SpacedDesc));
     put(o_sp2_, spaced_late_.data(), spaced_late_.size() * sizeof(SpacedDesc));
     put(o_dec_, decfix_.data(), decfix_.size() * sizeof(DecFixDesc));
@@ -1139,6 +1162,8 @@ void Job::launch() {
     }
     // main-stream kernels that run beside the short-run integer path: the copy first (bandwidth-bound, it leaves
     // the issue slots to the latency-bound header walk), then the issue-bound decoders
+    if (N(u8_tiles_))
+        run("k_utf8", ab_utf8_, N(u8_tiles_), 1, [&] { return launch_utf8((StrCol*)(d_desc_ + o_str_), (uint2*)(d_desc_ + o_u8tile_), N(u8_tiles_), st); });
     static const char* order_env = getenv("ORCB_MAIN_ORDER");
     const char* order = order_env ? order_env : "kcv";
     for (const char* o = order; *o; o++) {
@@ -1147,7 +1172,7 @@ void Job::launch() {
         if (*o == 'v' && N(var_segs_))
             run("k_varint128", ab_var_, N(var_segs_), 1, [&] { return launch_varint128((Seg*)(d_desc_ + o_var_), N(var_segs_), cnt, dstart, err, st); });
         if (*o == 'k' && N(copy_tiles_))
-            run("k_copy", ab_copy_, N(copy_tiles_), 1, [&] { return launch_copy((CopyDesc*)(d_desc_ + o_copy_), (uint2*)(d_desc_ + o_ctile_), N(copy_tiles_), cnt, err, st); });
+            run("k_copy", ab_copy_, N(copy_tiles_), 1, [&] { return launch_copy((CopyDesc*)(d_desc_ + o_copy_), (uint2*)(d_desc_ + o_ctile_), N(copy_tiles_), cnt, err, (StrCol*)(d_desc_ + o_str_), st); });
     }
     if (forked && !serial_env) CUDA_OK(cudaStreamWaitEvent(st, ev_join_, 0));
     if (N(decfix_))
@@ -1159,7 +1184,7 @@ void Job::launch() {
     if (N(spaced_late_))
         run("k_spaced(late)", ab_spaced_, N(spaced_late_), 1, [&] { return launch_spaced((SpacedDesc*)(d_desc_ + o_sp2_), N(spaced_late_), dstart, st); });
     if (N(strcols_))
-        run("k_strings(4 kernels)", ab_str_, str_tiles_, 4, [&] { return launch_strings((StrCol*)(d_desc_ + o_str_), N(strcols_), str_tiles_, err, dstate, (uint64_t)(uintptr_t)base_[AR_HEAP], heap_cap, ptrs, st); });
+        run("k_strings(5 kernels)", ab_str_, str_tiles_, 5, [&] { return launch_strings((StrCol*)(d_desc_ + o_str_), N(strcols_), str_tiles_, err, dstate, (uint64_t)(uintptr_t)base_[AR_HEAP], heap_cap, ptrs, st); });
     if (repack_work_)
         run("k_repack", ab_repack_, repack_work_, 1, [&] { return launch_repack((RepackDesc*)(d_desc_ + o_rep_), N(repacks_), repack_work_, nulls, st); });
 #undef N

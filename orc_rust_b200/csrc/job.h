@@ -101,6 +101,7 @@ class Job {
     std::vector<ScanDesc> scans_;
     std::vector<CopyDesc> copies_;
     std::vector<uint2> copy_tiles_;
+    std::vector<uint2> u8_tiles_;   // (string column, U8_TILE-byte tile) units of the UTF-8 check
     std::vector<SpacedDesc> spaced_, spaced_late_;
     std::vector<DecFixDesc> decfix_;
     std::vector<TsDesc> ts_;
@@ -124,7 +125,7 @@ class Job {
     uint64_t desc_bytes_ = 0;
     // offsets of each table inside the descriptor blob
     uint64_t o_pbyte_ = 0, o_dbyte_ = 0, o_int_ = 0, o_intbig_ = 0, o_var_ = 0, o_pbit_ = 0, o_dbit_ = 0, o_scan_ = 0, o_copy_ = 0,
-             o_ctile_ = 0, o_sp_ = 0, o_sp2_ = 0, o_dec_ = 0, o_ts_ = 0, o_str_ = 0, o_rep_ = 0, o_chunk_ = 0;
+             o_ctile_ = 0, o_sp_ = 0, o_sp2_ = 0, o_dec_ = 0, o_ts_ = 0, o_str_ = 0, o_rep_ = 0, o_chunk_ = 0, o_u8tile_ = 0;
     std::vector<uint8_t> desc_blob_;
 
     // state blob (device only, zeroed per launch): cnt[], dstart[], mis[], JobState
@@ -155,7 +156,7 @@ class Job {
     std::vector<KStat> kstats_;
     KStat& kstat(const char* name);
     // algorithmic byte counters accumulated by the planner (per kernel)
-    uint64_t ab_decomp_ = 0, ab_present_ = 0, ab_byte_ = 0, ab_bits_ = 0, ab_int_ = 0, ab_intbig_ = 0, ab_var_ = 0, ab_copy_ = 0,
+    uint64_t ab_utf8_ = 0, ab_decomp_ = 0, ab_present_ = 0, ab_byte_ = 0, ab_bits_ = 0, ab_int_ = 0, ab_intbig_ = 0, ab_var_ = 0, ab_copy_ = 0,
              ab_spaced_ = 0, ab_dec_ = 0, ab_ts_ = 0, ab_str_ = 0, ab_repack_ = 0;
 
     cudaStream_t aux_stream_ = nullptr;  // latency-bound pre-pass + short-run integer decode overlap the rest

@@ -1502,13 +1502,59 @@ __global__ void __launch_bounds__(128) k_varint128(const Seg* __restrict__ segs,
     }
 }
 
+// ---- UTF-8 validation ------------------------------------------------------------------------------
+// length of the character a lead byte opens (0 = not a lead byte)
+__device__ __forceinline__ uint32_t utf8_len(uint32_t b) {
+    return b < 0x80u ? 1u : (b >= 0xC2u && b <= 0xDFu) ? 2u : (b >= 0xE0u && b <= 0xEFu) ? 3u : (b >= 0xF0u && b <= 0xF4u) ? 4u : 0u;
+}
+__device__ __forceinline__ bool utf8_cont(uint32_t b) { return (b & 0xC0u) == 0x80u; }
+// is the character starting at p well formed (str::from_utf8 rules: shortest form, no surrogates, <= U+10FFFF)?
+__device__ __forceinline__ bool utf8_char_ok(const uint8_t* d, uint32_t p, uint32_t len) {
+    const uint32_t b0 = d[p];
+    if (b0 < 0x80u) return true;
+    const uint32_t n = utf8_len(b0);
+    if (n == 0 || p + n > len) return false;
+    const uint32_t b1 = d[p + 1];
+    uint32_t lo = 0x80u, hi = 0xBFu;
+    if (b0 == 0xE0u) lo = 0xA0u;
+    else if (b0 == 0xEDu) hi = 0x9Fu;
+    else if (b0 == 0xF0u) lo = 0x90u;
+    else if (b0 == 0xF4u) hi = 0x8Fu;
+    if (b1 < lo || b1 > hi) return false;
+    if (n >= 3 && !utf8_cont(d[p + 2])) return false;
+    if (n == 4 && !utf8_cont(d[p + 3])) return false;
+    return true;
+}
+
+// smallest position in [p0, p1) where the text stops being valid UTF-8 (0xffffffff = none): a lead byte must open a
+// well-formed character, a continuation byte must be claimed by a lead byte at most three positions back
+__device__ __forceinline__ uint32_t utf8_first_bad(const uint8_t* d, uint32_t p0, uint32_t p1, uint32_t len) {
+    for (uint32_t p = p0; p < p1; p++) {
+        const uint32_t b = d[p];
+        if (b < 0x80u) continue;
+        bool ok;
+        if (utf8_cont(b)) {
+            ok = false;
+            for (uint32_t k = 1; k <= 3 && k <= p; k++) {
+                const uint32_t lead = d[p - k];
+                if (!utf8_cont(lead)) { ok = utf8_len(lead) > k; break; }
+            }
+        } else {
+            ok = utf8_char_ok(d, p, len);
+        }
+        if (!ok) return p;
+    }
+    return 0xffffffffu;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Raw byte copies: FLOAT/DOUBLE streams (encoding/float.rs:70-74), string DATA (string.rs:135-140).
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t COPY_TILE = 16384;  // bytes per CTA
 
 __global__ void __launch_bounds__(256) k_copy(const CopyDesc* __restrict__ descs, const uint2* __restrict__ tiles,
-                                              uint32_t ntiles, const uint32_t* __restrict__ cnt, uint32_t* err) {
+                                              uint32_t ntiles, const uint32_t* __restrict__ cnt, uint32_t* err,
+                                              const StrCol* __restrict__ strcols) {
     if (blockIdx.x >= ntiles) return;
     const uint2 t = tiles[blockIdx.x];  // (desc index, tile index)
     const CopyDesc& d = descs[t.x];
@@ -1523,15 +1569,26 @@ __global__ void __launch_bounds__(256) k_copy(const CopyDesc* __restrict__ descs
     const uint8_t* src = (const uint8_t*)d.src + off;
     uint8_t* dst = (uint8_t*)d.dst + off;  // dst tiles are 16-byte aligned (dst base is 256-byte aligned)
     const uint32_t mis = (uint32_t)((uintptr_t)src & 3);
+    // string DATA is validated as UTF-8 while it passes through (string.rs:150-151): 16-byte groups without a high
+    // bit are ASCII, the others are walked byte by byte; COPY_TILE == U8_TILE, so the tile is the flag unit
+    const bool u8 = d.u8_col >= 0;
+    const uint32_t u8_len = (uint32_t)total;
+    const uint8_t* u8_d = (const uint8_t*)d.src;
+    uint32_t hi_bits = 0, bad = 0xffffffffu;
+    const uint32_t n16 = nbytes >> 4;
     if (mis == 0 && (((uintptr_t)src & 15) == 0)) {
-        const uint32_t n16 = nbytes >> 4;
-        for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) ((uint4*)dst)[i] = __ldg((const uint4*)src + i);
-        for (uint32_t i = (n16 << 4) + threadIdx.x; i < nbytes; i += blockDim.x) dst[i] = src[i];
+        for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) {
+            const uint4 v = __ldg((const uint4*)src + i);
+            ((uint4*)dst)[i] = v;
+            if (u8 && ((v.x | v.y | v.z | v.w) & 0x80808080u)) {
+                hi_bits = 1;
+                bad = min(bad, utf8_first_bad(u8_d, (uint32_t)off + i * 16, (uint32_t)off + i * 16 + 16, u8_len));
+            }
+        }
     } else {
         // unaligned source: aligned 32-bit loads + byte funnel, 16-byte aligned stores
         const uint32_t* q = (const uint32_t*)((uintptr_t)src & ~(uintptr_t)3);
         const uint32_t sh = mis * 8;
-        const uint32_t n16 = nbytes >> 4;
         for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) {
             const uint32_t* w = q + i * 4;
             const uint32_t a = __ldg(w), b = __ldg(w + 1), c2 = __ldg(w + 2), d2 = __ldg(w + 3);
@@ -1542,8 +1599,27 @@ __global__ void __launch_bounds__(256) k_copy(const CopyDesc* __restrict__ descs
             v.z = __funnelshift_r(c2, d2, sh);
             v.w = __funnelshift_r(d2, e, sh);
             ((uint4*)dst)[i] = v;
+            if (u8 && ((v.x | v.y | v.z | v.w) & 0x80808080u)) {
+                hi_bits = 1;
+                bad = min(bad, utf8_first_bad(u8_d, (uint32_t)off + i * 16, (uint32_t)off + i * 16 + 16, u8_len));
+            }
         }
-        for (uint32_t i = (n16 << 4) + threadIdx.x; i < nbytes; i += blockDim.x) dst[i] = src[i];
+    }
+    for (uint32_t i = (n16 << 4) + threadIdx.x; i < nbytes; i += blockDim.x) {
+        const uint8_t b = src[i];
+        dst[i] = b;
+        if (u8 && b >= 0x80u) {
+            hi_bits = 1;
+            bad = min(bad, utf8_first_bad(u8_d, (uint32_t)off + i, (uint32_t)off + i + 1, u8_len));
+        }
+    }
+    if (u8) {
+        const StrCol& sc = strcols[d.u8_col];
+        if (__syncthreads_or(hi_bits) && threadIdx.x == 0) {
+            atomicOr((uint32_t*)sc.u8_flags + (t.y >> 5), 1u << (t.y & 31));
+            ((volatile uint32_t*)sc.u8_bad)[1] = 1u;  // the column has multi-byte characters at all
+        }
+        if (bad != 0xffffffffu) atomicMax((uint32_t*)sc.u8_bad, ~bad);
     }
 }
 
@@ -1685,6 +1761,70 @@ __device__ __forceinline__ uint32_t str_row_len(const StrCol& c, uint32_t r, uin
     return (uint32_t)((const int32_t*)c.dict_len)[x];
 }
 
+// One CTA per U8_TILE bytes, 16 bytes per thread.  Pure-ASCII groups (the common case) cost four loads and an OR;
+// other groups are walked byte by byte: a lead byte must open a well-formed character, a continuation byte must be
+// claimed by a lead byte at most three positions back.  Only the smallest offending position is kept: whether
+// it matters is decided once the number of bytes the values really use is known (k_str_tile_scan).
+__global__ void __launch_bounds__(256) k_utf8(const StrCol* __restrict__ cols, const uint2* __restrict__ tiles, uint32_t ntiles) {
+    if (blockIdx.x >= ntiles) return;
+    const uint2 t = tiles[blockIdx.x];  // (column, tile)
+    const StrCol& c = cols[t.x];
+    const uint8_t* d = (const uint8_t*)c.u8_src;
+    const uint32_t len = c.u8_len;
+    // threads take 16-byte groups that are aligned in memory (128-bit loads, four in flight per thread): tile k is
+    // groups [G k, G k + G), G = U8_TILE / 16, counted from the stream's first byte rounded down to 16; bytes outside
+    // the stream are masked
+    constexpr uint32_t G = U8_TILE / 16, PER_THREAD = G / 256;
+    const uintptr_t base = (uintptr_t)d;
+    const uintptr_t g0 = (base & ~(uintptr_t)15) + ((uintptr_t)t.y * G + threadIdx.x) * 16u;
+    uint4 v[PER_THREAD];
+#pragma unroll
+    for (uint32_t u = 0; u < PER_THREAD; u++) {
+        const uintptr_t g = g0 + (uintptr_t)u * 256u * 16u;
+        v[u] = (int64_t)g - (int64_t)base < (int64_t)len ? __ldg((const uint4*)g) : make_uint4(0, 0, 0, 0);
+    }
+    bool multi = false;
+    uint32_t bad = 0xffffffffu;
+#pragma unroll
+    for (uint32_t u = 0; u < PER_THREAD; u++) {
+        const int64_t rel = (int64_t)(g0 + (uintptr_t)u * 256u * 16u) - (int64_t)base;  // stream offset of the group (-15.. for the first)
+        if (rel >= (int64_t)len) continue;
+        const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+        const uint32_t lo = rel < 0 ? (uint32_t)(-rel) : 0u;                                   // first byte of the group inside the stream
+        const uint32_t hi = (int64_t)len - rel < 16 ? (uint32_t)((int64_t)len - rel) : 16u;   // one past the last
+        uint32_t any = 0;
+        if (lo == 0 && hi == 16) {
+            any = w[0] | w[1] | w[2] | w[3];
+        } else {
+#pragma unroll
+            for (uint32_t i = 0; i < 4; i++) {
+                uint32_t m = 0xffffffffu;
+                const uint32_t b0 = 4 * i;
+                if (lo > b0) m &= lo - b0 >= 4 ? 0u : 0xffffffffu << (8 * (lo - b0));
+                if (hi < b0 + 4) m &= hi <= b0 ? 0u : 0xffffffffu >> (8 * (b0 + 4 - hi));
+                any |= w[i] & m;
+            }
+        }
+        if (!(any & 0x80808080u)) continue;
+        multi = true;
+        bad = min(bad, utf8_first_bad(d, (uint32_t)(rel + lo), (uint32_t)(rel + hi), len));
+    }
+    if (__syncthreads_or(multi) && threadIdx.x == 0) {
+        atomicOr((uint32_t*)c.u8_flags + (t.y >> 5), 1u << (t.y & 31));
+        ((volatile uint32_t*)c.u8_bad)[1] = 1u;  // the column has multi-byte characters at all
+    }
+    if (bad != 0xffffffffu) atomicMax((uint32_t*)c.u8_bad, ~bad);
+}
+
+// values must be cut at character boundaries: does `pos` (< total) fall on a continuation byte?
+__device__ __forceinline__ bool utf8_mid_char(const StrCol& c, uint32_t pos) {
+    // k_copy cuts its tiles at stream offsets, k_utf8 at 16-byte aligned addresses: look at both candidates
+    const uint32_t ta = pos / U8_TILE, tb2 = (pos + ((uint32_t)c.u8_src & 15u)) / U8_TILE;
+    const uint32_t* fl = (const uint32_t*)c.u8_flags;
+    if (!(((fl[ta >> 5] >> (ta & 31)) | (fl[tb2 >> 5] >> (tb2 & 31))) & 1u)) return false;
+    return utf8_cont(((const uint8_t*)c.u8_src)[pos]);
+}
+
 // dictionary LENGTH -> offsets (one warp per dictionary)
 __global__ void k_dict_prepare(StrCol* cols, uint32_t ncols, uint32_t* err) {
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -1707,6 +1847,15 @@ __global__ void k_dict_prepare(StrCol* cols, uint32_t ncols, uint32_t* err) {
     bool same = true;
     for (uint32_t i = lane; i < c.dict_size; i += 32) same &= (uint32_t)dl[i] == first_len;
     same = __all_sync(FULL, same);
+    // every dictionary entry starts at a character boundary (the dictionary is a string array of its own)
+    if (c.u8_src && carry <= c.dict_data_len) {
+        bool mid = false;
+        for (uint32_t i = lane; i < c.dict_size; i += 32) {
+            const uint32_t o = (uint32_t)doff[i];
+            if (o < (uint32_t)carry) mid |= utf8_mid_char(c, o);
+        }
+        if (mid) set_err(err, c.colstripe, ORCB_ARROW);
+    }
     if (lane == 0) {
         cols[warp].data_cap = (same && c.dict_size && first_len >= 1 && first_len <= 4 && !c.valid) ? first_len : 0;
         doff[c.dict_size] = (int32_t)carry;
@@ -1826,6 +1975,17 @@ __global__ void k_str_tile_scan(StrCol* cols, uint32_t ncols, uint32_t* err, Job
         } else if (carry > c.data_len) {
             // fewer DATA bytes than the lengths claim: GenericByteArray::try_new fails (Arrow error)
             set_err(err, c.colstripe, ORCB_ARROW);
+        }
+        if (c.u8_src) {
+            // the bytes the values use: direct = sum of the lengths, dictionary = sum of the entry lengths
+            const uint64_t used = c.mode == 0 ? carry : (uint64_t)(uint32_t)((const int32_t*)c.dict_off)[c.dict_size];
+            if (used <= c.u8_len) {
+                const uint32_t word = *(const uint32_t*)c.u8_bad;
+                const uint32_t first_bad = ~word;  // 0xffffffff when nothing was found
+                const uint8_t* d = (const uint8_t*)c.u8_src;
+                // invalid character inside the used prefix, or a character that straddles its end
+                if ((word && first_bad < used) || (used && used < c.u8_len && utf8_cont(d[used]))) set_err(err, c.colstripe, ORCB_ARROW);
+            }
         }
         ptr_table[c.meta_slot] = c.data;
     }
@@ -2020,6 +2180,28 @@ __global__ void __launch_bounds__(128) k_str_offsets(const StrCol* __restrict__ 
     const uint32_t brow0 = b * batch_size;
     const uint32_t brows = min(batch_size, c.n_rows - brow0);
     if (lane == 0 && r0 + nr == brow0 + brows) ((int32_t*)c.offsets)[(uint64_t)b * (batch_size + 1) + brows] = (int32_t)(bb[b + 1] - bbase);
+}
+
+// Direct strings whose DATA stream has multi-byte characters: every value must start at a character boundary
+// (GenericByteArray::<Utf8>::try_new).  Pure-ASCII columns leave at once.
+__global__ void __launch_bounds__(128) k_utf8_bounds(const StrCol* __restrict__ cols, uint32_t ncols, uint32_t ntiles, uint32_t* err) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= ntiles) return;
+    const StrCol& c = find_strcol(cols, ncols, warp);
+    if (c.mode != 0 || !c.u8_src || ((const uint32_t*)c.u8_bad)[1] == 0) return;
+    const uint32_t tile = warp - c.tile0;
+    const int lane = threadIdx.x & 31;
+    uint32_t b, r0, nr;
+    tile_rows(c, tile, b, r0, nr);
+    const uint64_t* bb = (const uint64_t*)c.batch_base;
+    const uint64_t bbase = bb[b], total = min(bb[c.n_batches], (uint64_t)c.u8_len);
+    const int32_t* offs = (const int32_t*)c.offsets + (uint64_t)b * (c.batch_size + 1) + (r0 - b * c.batch_size);
+    bool mid = false;
+    for (uint32_t i = lane; i < nr; i += 32) {
+        const uint64_t a = bbase + (uint32_t)offs[i];
+        if (a < total) mid |= utf8_mid_char(c, (uint32_t)a);
+    }
+    if (mid) set_err(err, c.colstripe, ORCB_ARROW);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2299,9 +2481,10 @@ int launch_varint128(const Seg* segs, uint32_t n, const uint32_t* cnt, const uin
     return 0;
 }
 int launch_copy(const CopyDesc* d, const uint2* tiles, uint32_t ntiles, const uint32_t* cnt, uint32_t* err,
-                cudaStream_t st) {
+                const StrCol* strcols, cudaStream_t st) {
+    static_assert(COPY_TILE == U8_TILE, "k_copy sets one UTF-8 flag bit per tile");
     if (!ntiles) return 0;
-    k_copy<<<ntiles, 256, 0, st>>>(d, tiles, ntiles, cnt, err);
+    k_copy<<<ntiles, 256, 0, st>>>(d, tiles, ntiles, cnt, err, strcols);
     LAUNCH_CHECK();
     return 0;
 }
@@ -2323,6 +2506,12 @@ int launch_timestamp(const TsDesc* d, uint32_t n, const uint32_t* cnt, uint32_t*
     LAUNCH_CHECK();
     return 0;
 }
+int launch_utf8(const StrCol* cols, const uint2* tiles, uint32_t ntiles, cudaStream_t st) {
+    if (!ntiles) return 0;
+    k_utf8<<<ntiles, 256, 0, st>>>(cols, tiles, ntiles);
+    LAUNCH_CHECK();
+    return 0;
+}
 int launch_strings(StrCol* cols, uint32_t ncols, uint32_t ntiles, uint32_t* err, JobState* state, uint64_t heap_base,
                    uint64_t heap_cap, uint64_t* ptr_table, cudaStream_t st) {
     if (!ncols) return 0;
@@ -2333,6 +2522,8 @@ int launch_strings(StrCol* cols, uint32_t ncols, uint32_t ntiles, uint32_t* err,
     k_str_tile_scan<<<blocks_for_warps(ncols, 4), 128, 0, st>>>(cols, ncols, err, state, heap_base, heap_cap, ptr_table);
     LAUNCH_CHECK();
     k_str_offsets<<<blocks_for_warps(ntiles, 4), 128, 0, st>>>(cols, ncols, ntiles, err);
+    LAUNCH_CHECK();
+    k_utf8_bounds<<<blocks_for_warps(ntiles, 4), 128, 0, st>>>(cols, ncols, ntiles, err);
     LAUNCH_CHECK();
     return 0;
 }

@@ -22,10 +22,11 @@ int launch_seg_scan(const ScanDesc* d, uint32_t n, uint32_t* cnt, uint32_t* dsta
 int launch_varint128(const Seg* segs, uint32_t n, const uint32_t* cnt, const uint32_t* dstart, uint32_t* err,
                      cudaStream_t st);
 int launch_copy(const CopyDesc* d, const uint2* tiles, uint32_t ntiles, const uint32_t* cnt, uint32_t* err,
-                cudaStream_t st);
+                const StrCol* strcols, cudaStream_t st);
 int launch_spaced(const SpacedDesc* d, uint32_t n, const uint32_t* dstart, cudaStream_t st);
 int launch_decimal_fix(const DecFixDesc* d, uint32_t n, const uint32_t* cnt, const uint32_t* mis, cudaStream_t st);
 int launch_timestamp(const TsDesc* d, uint32_t n, const uint32_t* cnt, uint32_t* err, cudaStream_t st);
+int launch_utf8(const StrCol* cols, const uint2* tiles, uint32_t ntiles, cudaStream_t st);
 int launch_strings(StrCol* cols, uint32_t ncols, uint32_t ntiles, uint32_t* err, JobState* state, uint64_t heap_base,
                    uint64_t heap_cap, uint64_t* ptr_table, cudaStream_t st);
 int launch_repack(const RepackDesc* d, uint32_t ndesc, uint32_t nwork, uint32_t* nulls, cudaStream_t st);

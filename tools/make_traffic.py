@@ -15,10 +15,11 @@ GROUPS = {
     "k_int_rle": "k_int_rle(+general,+coop_runs)",
     "k_int_rle_general": "k_int_rle(+general,+coop_runs)",
     "k_coop_runs": "k_int_rle(+general,+coop_runs)",
-    "k_dict_prepare": "k_strings(4 kernels)",
-    "k_str_tile_sum": "k_strings(4 kernels)",
-    "k_str_tile_scan": "k_strings(4 kernels)",
-    "k_str_offsets": "k_strings(4 kernels)",
+    "k_dict_prepare": "k_strings(5 kernels)",
+    "k_str_tile_sum": "k_strings(5 kernels)",
+    "k_str_tile_scan": "k_strings(5 kernels)",
+    "k_str_offsets": "k_strings(5 kernels)",
+    "k_utf8_bounds": "k_strings(5 kernels)",
 }
 
 if __name__ == "__main__":
