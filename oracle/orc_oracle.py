@@ -489,22 +489,34 @@ class OracleFile:
         return out
 
 
+# old link names ("backward" file of the tz database) that minimal tzdata installs leave out; chrono-tz knows them
+_ZONE_LINKS = {"US/Pacific": "America/Los_Angeles", "US/Eastern": "America/New_York", "US/Central": "America/Chicago",
+               "US/Mountain": "America/Denver", "US/Alaska": "America/Anchorage", "US/Hawaii": "Pacific/Honolulu",
+               "US/Arizona": "America/Phoenix", "Asia/Calcutta": "Asia/Kolkata", "Japan": "Asia/Tokyo", "PRC": "Asia/Shanghai",
+               "GB": "Europe/London", "Eire": "Europe/Dublin", "NZ": "Pacific/Auckland", "Singapore": "Asia/Singapore"}
+
+
 def _zone(name: str):
     import zoneinfo
-    return zoneinfo.ZoneInfo(name)
+    try:
+        return zoneinfo.ZoneInfo(name)
+    except zoneinfo.ZoneInfoNotFoundError:
+        if name in _ZONE_LINKS:
+            return zoneinfo.ZoneInfo(_ZONE_LINKS[name])
+        raise
 
 
 def _tz_to_utc(vals: np.ndarray, zone, unit_ns: int) -> np.ndarray:
     """TimestampOffsetArrayDecoder (array_decoder/timestamp.rs:242-286): wall clock of the instant in the
     writer zone, re-read as UTC = instant + utcoffset(instant)."""
-    out = vals.copy()
     per_s = 1_000_000_000 // unit_ns
     epoch = _dt.datetime(1970, 1, 1, tzinfo=_dt.timezone.utc)
-    for i, v in enumerate(vals.tolist()):
-        secs = v // per_s
-        off = (epoch + _dt.timedelta(seconds=secs)).astimezone(zone).utcoffset()
-        out[i] = v + int(off.total_seconds()) * per_s
-    return out
+    secs = np.floor_divide(vals, per_s)
+    uniq, inv = np.unique(secs, return_inverse=True)  # one zone lookup per distinct second
+    offs = np.empty(uniq.size, dtype=np.int64)
+    for i, sv in enumerate(uniq.tolist()):
+        offs[i] = int((epoch + _dt.timedelta(seconds=sv)).astimezone(zone).utcoffset().total_seconds())
+    return vals + offs[inv] * per_s
 
 
 def _to_rows(present, payload, n):

@@ -132,6 +132,13 @@ struct TsDesc {
     int32_t cnt_idx;
     uint32_t colstripe;
     uint32_t as_i128;
+    // writer time zone (array_decoder/timestamp.rs:242-286): out = instant + UTC offset in force at the instant
+    uint64_t tz_at;      // i64[tz_n] transition instants (UTC seconds), ascending; 0 = no conversion
+    uint64_t tz_off;     // i32[tz_n] offset in force from tz_at[i] on
+    uint32_t tz_n;
+    int32_t tz_first;    // offset before the first transition
+    uint32_t tz_on;
+    uint32_t pad;
 };
 
 // string column of one stripe

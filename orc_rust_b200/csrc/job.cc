@@ -8,6 +8,7 @@
 // and adds what the reference never uses: row-index positions (src/row_index.rs:37-51) as parallel
 // entry points, one segment per (stream, row group).
 #include "job.h"
+#include "tz.h"
 
 #include <algorithm>
 #include <cstdlib>
@@ -333,6 +334,7 @@ void Job::plan() {
     place(o_str_, strcols_.size() * sizeof(StrCol));
     place(o_rep_, repacks_.size() * sizeof(RepackDesc));
     place(o_chunk_, chunks_.size() * sizeof(ChunkDesc));
+    place(o_tz_, tz_blob_.size());
     desc_bytes_ = align_up(desc_bytes_, 256);
 
     // ---- state blob
@@ -972,9 +974,35 @@ void Job::plan_stripe(uint32_t task_idx) {
                 add_int_segs(s_data, secs, true, 8, OUT_I64, 0, true);
                 add_int_segs(s_secondary, nanos, false, 8, OUT_I64, 0, true);
                 int64_t base = ORC_EPOCH_UTC;
-                if (k == T_TIMESTAMP && sf.has_tz && !is_utc_zone(sf.tz))
-                    fail(ORCB_NOT_IMPLEMENTED, "TIMESTAMP columns written in zone '" + sf.tz +
-                                                   "' need a time-zone transition table (only UTC/GMT writers are handled on the device path)");
+                bool tz_on = false;
+                std::array<uint64_t, 4> tzt{};
+                if (k == T_TIMESTAMP && sf.has_tz && !is_utc_zone(sf.tz)) {
+                    // the ORC epoch is 2015-01-01 00:00 on the writer's wall clock (timestamp.rs:128-147); values are
+                    // moved from the writer's zone to UTC after decoding (:242-286)
+                    auto it = tz_tables_.find(sf.tz);
+                    if (it == tz_tables_.end()) {
+                        ZoneTable z;
+                        std::string why;
+                        if (!load_zone_table(sf.tz, z, why)) fail(ORCB_NOT_IMPLEMENTED, "TIMESTAMP column written in a zone this host has no table for: " + why);
+                        int64_t b = 0;
+                        if (!zone_local_to_utc(z, ORC_EPOCH_UTC, b)) fail(ORCB_UNEXPECTED, "2015-01-01 00:00 is not a unique instant in zone " + sf.tz);
+                        auto append = [&](const void* p, size_t n) {
+                            tz_blob_.resize((tz_blob_.size() + 15) / 16 * 16);
+                            const uint64_t at = tz_blob_.size();
+                            tz_blob_.insert(tz_blob_.end(), (const uint8_t*)p, (const uint8_t*)p + n);
+                            return at;
+                        };
+                        std::array<uint64_t, 4> e{};
+                        e[0] = append(z.at.data(), z.at.size() * 8);
+                        e[1] = append(z.off.data(), z.off.size() * 4);
+                        e[2] = z.at.size();
+                        e[3] = ((uint64_t)(uint32_t)z.first_off << 32) | (uint64_t)(uint32_t)(int32_t)(b - ORC_EPOCH_UTC);
+                        it = tz_tables_.emplace(sf.tz, e).first;
+                    }
+                    tzt = it->second;
+                    base = ORC_EPOCH_UTC + (int64_t)(int32_t)(uint32_t)(tzt[3] & 0xffffffffu);
+                    tz_on = true;
+                }
                 static const int64_t unit_ns[4] = {1, 1000, 1000000, 1000000000};
                 TsDesc td{};
                 td.secs = secs;
@@ -986,6 +1014,13 @@ void Job::plan_stripe(uint32_t task_idx) {
                 td.cnt_idx = total_idx;
                 td.colstripe = cs;
                 td.as_i128 = 0;
+                if (tz_on) {
+                    td.tz_on = 1;
+                    td.tz_at = tzt[0];   // offsets inside the zone-table blob until stage()
+                    td.tz_off = tzt[1];
+                    td.tz_n = (uint32_t)tzt[2];
+                    td.tz_first = (int32_t)(uint32_t)(tzt[3] >> 32);
+                }
                 ts_.push_back(td);
                 ab_ts_ += (uint64_t)n_rows * 24;
                 if (has_present) add_spaced(dst, cp.values, 8, true);
@@ -1052,7 +1087,13 @@ void Job::stage() {
     for (auto* v : {&spaced_, &spaced_late_})
         for (auto& d : *v) { R(d.src); R(d.dst); R(d.valid); }
     for (auto& d : decfix_) { R(d.vals); R(d.scales); }
-    for (auto& d : ts_) { R(d.secs); R(d.nanos); R(d.out); }
+    for (auto& d : ts_) {
+        R(d.secs); R(d.nanos); R(d.out);
+        if (d.tz_on) {
+            d.tz_at = (uint64_t)(uintptr_t)(d_desc_ + o_tz_ + d.tz_at);
+            d.tz_off = (uint64_t)(uintptr_t)(d_desc_ + o_tz_ + d.tz_off);
+        }
+    }
     for (auto& c : strcols_) {
         R(c.lens); R(c.valid); R(c.dict_len); R(c.dict_off); R(c.dict_data); R(c.offsets); R(c.tile_base); R(c.data);
         R(c.u8_src); R(c.u8_bad); R(c.u8_flags);
@@ -1083,6 +1124,7 @@ void Job::stage() {
     put(o_str_, strcols_.data(), strcols_.size() * sizeof(StrCol));
     put(o_rep_, repacks_.data(), repacks_.size() * sizeof(RepackDesc));
     put(o_chunk_, chunks_.data(), chunks_.size() * sizeof(ChunkDesc));
+    put(o_tz_, tz_blob_.data(), tz_blob_.size());
     CUDA_OK(cudaMemcpyAsync(d_desc_, desc_blob_.data(), desc_blob_.size(), cudaMemcpyHostToDevice, stream_));
     for (auto& sc : stage_copies_)
         CUDA_OK(cudaMemcpyAsync(base_[AR_IN] + sc.dst_off, sc.src, sc.bytes, cudaMemcpyHostToDevice, stream_));

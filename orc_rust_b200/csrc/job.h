@@ -4,6 +4,8 @@
 
 #include <memory>
 #include <string>
+#include <array>
+#include <map>
 #include <vector>
 
 #include "common.h"
@@ -101,6 +103,8 @@ class Job {
     std::vector<ScanDesc> scans_;
     std::vector<CopyDesc> copies_;
     std::vector<uint2> copy_tiles_;
+    std::vector<uint8_t> tz_blob_;                  // zone tables: i64 instants then i32 offsets, 16-byte aligned pieces
+    std::map<std::string, std::array<uint64_t, 4>> tz_tables_;  // zone -> {offset of instants, offset of offsets, n, first}
     std::vector<uint2> u8_tiles_;   // (string column, U8_TILE-byte tile) units of the UTF-8 check
     std::vector<SpacedDesc> spaced_, spaced_late_;
     std::vector<DecFixDesc> decfix_;
@@ -125,7 +129,7 @@ class Job {
     uint64_t desc_bytes_ = 0;
     // offsets of each table inside the descriptor blob
     uint64_t o_pbyte_ = 0, o_dbyte_ = 0, o_int_ = 0, o_intbig_ = 0, o_var_ = 0, o_pbit_ = 0, o_dbit_ = 0, o_scan_ = 0, o_copy_ = 0,
-             o_ctile_ = 0, o_sp_ = 0, o_sp2_ = 0, o_dec_ = 0, o_ts_ = 0, o_str_ = 0, o_rep_ = 0, o_chunk_ = 0, o_u8tile_ = 0;
+             o_ctile_ = 0, o_sp_ = 0, o_sp2_ = 0, o_dec_ = 0, o_ts_ = 0, o_str_ = 0, o_rep_ = 0, o_chunk_ = 0, o_u8tile_ = 0, o_tz_ = 0;
     std::vector<uint8_t> desc_blob_;
 
     // state blob (device only, zeroed per launch): cnt[], dstart[], mis[], JobState

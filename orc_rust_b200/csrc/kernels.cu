@@ -1727,7 +1727,25 @@ __global__ void __launch_bounds__(256) k_timestamp(const TsDesc* __restrict__ de
             const __int128 u = (__int128)d.unit_ns;
             const __int128 q = t / u;
             if (t % u != 0 || q > (__int128)INT64_MAX || q < (__int128)INT64_MIN) set_err(err, d.colstripe, ORCB_DECODE_TIMESTAMP);
-            ((int64_t*)d.out)[i] = (int64_t)q;
+            int64_t v = (int64_t)q;
+            if (d.tz_on) {
+                // the value is an instant; the reference re-reads its wall clock in the writer's zone as UTC
+                const int64_t per_s = 1000000000 / d.unit_ns;
+                const int64_t inst = v / per_s - (v % per_s < 0);  // floor to seconds
+                const int64_t* at = (const int64_t*)d.tz_at;
+                uint32_t lo = 0, hi = d.tz_n;  // first transition after the instant
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (at[mid] <= inst) lo = mid + 1;
+                    else hi = mid;
+                }
+                const int64_t off = lo == 0 ? (int64_t)d.tz_first : (int64_t)((const int32_t*)d.tz_off)[lo - 1];
+                const __int128 w = (__int128)v + (__int128)off * per_s;
+                // the reference turns an unrepresentable nanosecond value into a null; not reproduced
+                if (w > (__int128)INT64_MAX || w < (__int128)INT64_MIN) set_err(err, d.colstripe, ORCB_NOT_IMPLEMENTED);
+                v = (int64_t)w;
+            }
+            ((int64_t*)d.out)[i] = v;
         }
     }
 }

@@ -49,8 +49,6 @@ def test_oracle_vs_reference_feather(fpath):
         pytest.skip("LZO/Zstd: out of scope for the device path")
     if name == "orc_split_elim":
         pytest.skip("DECIMAL(0,0): ignored by the reference itself (tests/integration/main.rs:347-351)")
-    if name == "TestOrcFile.testDate1900":
-        pytest.skip("US/Pacific writer zone: tz database alias not available in this image")
     _, got = _oracle_table(orc)
     exp = feather.read_table(fpath)
     assert got.num_rows == exp.num_rows
@@ -70,8 +68,6 @@ def test_oracle_vs_pyarrow(fpath):
     name = os.path.basename(fpath)
     if name in ("orc_split_elim.orc",):
         pytest.skip("DECIMAL(0,0)")
-    if name in ("TestOrcFile.testDate1900.orc", "TestOrcFile.testDate2038.orc"):
-        pytest.skip("US/Pacific writer zone alias")
     try:
         _, got = _oracle_table(fpath)
     except oo.OracleError as e:
