@@ -272,6 +272,69 @@ def test_string_dictionary_shapes(ob, tmp_path):
                 assert_batches_identical(got, exp, f"strings/{comp}/bs={bs}/index={use_index}")
 
 
+# ---- builder options (src/arrow_reader.rs:70-173) through the decode path -----------------------------------
+def test_builder_options(ob, tmp_path):
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tools"))
+    import gen_orc
+    from oracle import orc_oracle as oo
+    # several stripes, so that a byte range selects a strict subset of them
+    p = gen_orc.write(gen_orc.lineitem_table(40_000, 3), str(tmp_path / "li.orc"), stripe_size=2 << 20)
+    data = open(p, "rb").read()
+    of = oo.OracleFile(data)
+    assert len(of.stripes) >= 3
+    # projection (ProjectionMask::named_roots): the file's column order is kept, whatever the order asked for
+    cols = ["l_comment", "l_quantity", "l_orderkey", "l_shipmode"]
+    got = list(ob.ArrowReaderBuilder.try_new(data).with_projection(cols).with_batch_size(5000).build())
+    exp = of.read(batch_size=5000, columns=cols)
+    assert got[0].schema.names == exp[0].schema.names
+    assert_batches_identical(got, exp, "projection")
+    # with_file_byte_range: stripes whose offset lies inside the range (arrow_reader.rs:358-372)
+    lo, hi = of.stripes[1].offset, of.stripes[2].offset + 1
+    got = list(ob.ArrowReaderBuilder.try_new(data).with_file_byte_range(lo, hi).build())
+    exp = of.read(stripes=[1, 2])
+    assert_batches_identical(got, exp, "byte range")
+    assert list(ob.ArrowReaderBuilder.try_new(data).with_file_byte_range(1, 2).build()) == []
+    # timestamp precision, on timestamps with sub-microsecond digits (error) and without
+    nh = gen_orc.write(gen_orc.nullheavy_table(20_000, 1), str(tmp_path / "nh.orc"))
+    ndata = open(nh, "rb").read()
+    nof = oo.OracleFile(ndata)
+    got = list(ob.ArrowReaderBuilder.try_new(ndata).with_projection(["ts_ms"])
+               .with_timestamp_precision(ob.TimestampPrecision.Microsecond).build())
+    exp = nof.read(columns=["ts_ms"], ts_unit="us")
+    assert_batches_identical(got, exp, "microsecond timestamps")
+    with pytest.raises(oo.OracleError):
+        nof.read(columns=["ts"], ts_unit="us")  # random nanoseconds do not divide by 1000: DecodeTimestamp
+    with pytest.raises(ob.OrcError) as ei:
+        list(ob.ArrowReaderBuilder.try_new(ndata).with_projection(["ts"])
+             .with_timestamp_precision(ob.TimestampPrecision.Microsecond).build())
+    assert ei.value.variant == "DecodeTimestamp"
+    # writer time zone: pyarrow always writes "GMT"; the same three bytes patched to CET / EET / MST give files whose
+    # timestamps have to be moved through the zone's transition table (DST, pre-1970 history, the footer rule after 2037)
+    import numpy as np
+    import pyarrow as pa
+    rng = np.random.default_rng(5)
+    n = 30_000
+    secs = rng.integers(-2_300_000_000, 4_200_000_000, n)            # 1897 .. 2103
+    frac = np.where(secs >= 0, rng.integers(0, 1000, n) * 1_000_000, 0)  # (pyarrow writes unusable nanos before 1970)
+    ts = pa.array(secs * 1_000_000_000 + frac, pa.timestamp("ns"))
+    ts = pa.array([None if i % 11 == 0 else v for i, v in enumerate(ts.to_pylist())], pa.timestamp("ns"))
+    zp = gen_orc.write(pa.table({"t": ts, "k": pa.array(np.arange(n))}), str(tmp_path / "tz.orc"))
+    z0 = open(zp, "rb").read()
+    assert z0.count(b"GMT") >= 1
+    for zone in ("CET", "EET", "MST"):
+        zdata = z0.replace(b"GMT", zone.encode())
+        zof = oo.OracleFile(zdata)
+        assert zof._stripe_footer(zof.stripes[0])[2] == zone
+        for unit, prec in (("ns", ob.TimestampPrecision.Nanosecond), ("us", ob.TimestampPrecision.Microsecond)):
+            got = list(ob.ArrowReaderBuilder.try_new(zdata).with_timestamp_precision(prec).build())
+            assert_batches_identical(got, zof.read(ts_unit=unit), f"{zone}/{unit}")
+    # and the zone really moved the values
+    a = list(ob.ArrowReaderBuilder.try_new(z0.replace(b"GMT", b"CET")).build())[0].column(0)
+    b = list(ob.ArrowReaderBuilder.try_new(z0).build())[0].column(0)
+    assert a != b
+
+
 # ---- corrupted inputs: same verdict as the oracle, same bytes whenever both still decode ------------------
 def _mutations(data0: bytes, lo: int, hi: int, seed: int, count: int):
     import random
