@@ -1369,7 +1369,7 @@ void Job::export_batch(uint64_t i, ArrowArray* out) {
     const uint32_t* nulls = (const uint32_t*)(h_meta_ + o_nulls_);
     const uint64_t* ptrs = (const uint64_t*)(h_meta_ + o_ptrs_);
     const uint32_t cs0 = task_first_cs_[t];
-    const uint32_t n_rows = colstripes_.empty() ? 0 : (uint32_t)tasks_[t].file->stripes[tasks_[t].stripe].rows;
+    const uint32_t n_rows = (uint32_t)tasks_[t].file->stripes[tasks_[t].stripe].rows;  // also with an empty projection (mod.rs:538-549)
     const uint32_t rows = std::min(bs, n_rows - b * bs);
     build_batch(this, out, rows, cols_.size());
     auto* tp = (ArrayPriv*)out->private_data;

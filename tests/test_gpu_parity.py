@@ -289,6 +289,10 @@ def test_builder_options(ob, tmp_path):
     exp = of.read(batch_size=5000, columns=cols)
     assert got[0].schema.names == exp[0].schema.names
     assert_batches_identical(got, exp, "projection")
+    # a projection that matches nothing: batches that only carry their row count (array_decoder/mod.rs:538-549)
+    empty = list(ob.ArrowReaderBuilder.try_new(data).with_projection(["no_such_column"]).with_batch_size(50_000).build())
+    assert [b.num_columns for b in empty] == [0] * len(empty)
+    assert [b.num_rows for b in empty] == [b.num_rows for b in of.read(batch_size=50_000, columns=["l_tax"])]
     # with_file_byte_range: stripes whose offset lies inside the range (arrow_reader.rs:358-372)
     lo, hi = of.stripes[1].offset, of.stripes[2].offset + 1
     got = list(ob.ArrowReaderBuilder.try_new(data).with_file_byte_range(lo, hi).build())
