@@ -225,6 +225,17 @@ def main():
     job.finish()
     kstats = job.kernel_stats()
     st = job.stats()
+    # one more pass with every kernel on one stream (outside the timed region): per-kernel durations without the
+    # contention of the overlapped schedule, reported beside the in-step ones
+    kserial = None
+    if "ORCB_SERIAL" not in os.environ:
+        os.environ["ORCB_SERIAL"] = "1"
+        try:
+            job.launch()
+            job.finish()
+            kserial = job.kernel_stats()
+        finally:
+            del os.environ["ORCB_SERIAL"]
 
     # ---- end-to-end through the C ABI: H2D + decode + metadata D2H every step.  The file set is split into a
     #      few jobs, each on its own library stream, so the pinned H2D copy of group g+1 overlaps the decode of g.
@@ -281,6 +292,14 @@ def main():
                     "step_frac": (in_bytes + out_bytes) / (dev_ms / 1e3) / 1e9 / peak,
                     "kernels": [{"name": k["name"], "ms": round(k["ms"], 4), "alg_gb": round(k["alg_bytes"] / 1e9, 4)}
                                 for k in kstats]}
+        if kserial:
+            ks = {k["name"]: k for k in kserial}
+            if top["name"] in ks and ks[top["name"]]["ms"] > 0:
+                roofline["frac_alone"] = top["alg_bytes"] / (ks[top["name"]]["ms"] / 1e3) / 1e9 / peak
+            roofline["kernels_alone"] = [{"name": k["name"], "ms": round(k["ms"], 4),
+                                          "gbs": round(k["alg_bytes"] / max(k["ms"], 1e-9) / 1e6, 1)} for k in kserial]
+            roofline["note"] = ("frac / kernels: event pairs inside the timed, two-stream step (kernels of the other stream "
+                                "share the SMs); frac_alone / kernels_alone: one extra pass with all kernels on one stream")
     if rank != 0:
         return
     cpu = None

@@ -681,9 +681,18 @@ void Job::plan_stripe(uint32_t task_idx) {
                 // compressed): segments that open with a long run go to the warp-per-segment kernel,
                 // everything else to the lane-per-segment kernel.  Purely a scheduling hint.
                 bool long_runs = false;
-                if (!compressed && v2 && sr.present) {
+                if (v2 && sr.present) {
                     const uint8_t* sp = fm.data + (sf.find(cid, &sr == &s_data ? S_DATA : (&sr == &s_length ? S_LENGTH : S_SECONDARY))->offset);
-                    long_runs = rle2_opens_with_long_runs(sp, sr.len, sg.start_byte);
+                    if (!compressed) {
+                        long_runs = rle2_opens_with_long_runs(sp, sr.len, sg.start_byte);
+                    } else if (!sr.chunks.empty()) {
+                        // compressed file: the bytes are readable where the entry point lies in a chunk that was stored
+                        // as is (incompressible integer streams usually are)
+                        const size_t ci = (size_t)(std::upper_bound(sr.chunk_dst.begin(), sr.chunk_dst.end(), (uint64_t)sg.start_byte) - sr.chunk_dst.begin()) - 1;
+                        if (ci < sr.chunks.size() && sr.chunks[ci].original)
+                            long_runs = rle2_opens_with_long_runs(sp + sr.chunks[ci].src_off, sr.chunks[ci].src_len,
+                                                                  (uint32_t)(sg.start_byte - sr.chunk_dst[ci]));
+                    }
                 }
                 if (!long_runs) {
                     const uint32_t bound = (has_present && per_group_counts) ? rows_in_group(g) : sg.n_values;
@@ -1185,7 +1194,7 @@ void Job::launch() {
     // fork: the header-walk pre-pass is a long dependent chain on few warps, so it runs beside the
     // bandwidth-heavy kernels on a second stream and joins before the epilogues
     // ORCB_SERIAL=1 keeps everything on one stream (clean per-kernel timings when profiling)
-    static const bool serial_env = getenv("ORCB_SERIAL") != nullptr;
+    const bool serial_env = getenv("ORCB_SERIAL") != nullptr;  // read at every launch: bench.py times one serial pass
     const bool forked = N(int_segs_) > 0;
     cudaStream_t aux = serial_env ? st : aux_stream_;
     if (forked) {

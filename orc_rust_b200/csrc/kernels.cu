@@ -2201,23 +2201,24 @@ __global__ void __launch_bounds__(128) k_str_offsets(const StrCol* __restrict__ 
 }
 
 // Direct strings whose DATA stream has multi-byte characters: every value must start at a character boundary
-// (GenericByteArray::<Utf8>::try_new).  Pure-ASCII columns leave at once.
-__global__ void __launch_bounds__(128) k_utf8_bounds(const StrCol* __restrict__ cols, uint32_t ncols, uint32_t ntiles, uint32_t* err) {
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (warp >= ntiles) return;
-    const StrCol& c = find_strcol(cols, ncols, warp);
+// (GenericByteArray::<Utf8>::try_new).  One CTA per string column; pure-ASCII columns leave at once.
+__global__ void __launch_bounds__(128) k_utf8_bounds(const StrCol* __restrict__ cols, uint32_t ncols, uint32_t* err) {
+    if (blockIdx.x >= ncols) return;
+    const StrCol& c = cols[blockIdx.x];
     if (c.mode != 0 || !c.u8_src || ((const uint32_t*)c.u8_bad)[1] == 0) return;
-    const uint32_t tile = warp - c.tile0;
     const int lane = threadIdx.x & 31;
-    uint32_t b, r0, nr;
-    tile_rows(c, tile, b, r0, nr);
     const uint64_t* bb = (const uint64_t*)c.batch_base;
-    const uint64_t bbase = bb[b], total = min(bb[c.n_batches], (uint64_t)c.u8_len);
-    const int32_t* offs = (const int32_t*)c.offsets + (uint64_t)b * (c.batch_size + 1) + (r0 - b * c.batch_size);
+    const uint64_t total = min(bb[c.n_batches], (uint64_t)c.u8_len);
     bool mid = false;
-    for (uint32_t i = lane; i < nr; i += 32) {
-        const uint64_t a = bbase + (uint32_t)offs[i];
-        if (a < total) mid |= utf8_mid_char(c, (uint32_t)a);
+    for (uint32_t tile = threadIdx.x >> 5; tile < c.n_tiles; tile += blockDim.x >> 5) {
+        uint32_t b, r0, nr;
+        tile_rows(c, tile, b, r0, nr);
+        const uint64_t bbase = bb[b];
+        const int32_t* offs = (const int32_t*)c.offsets + (uint64_t)b * (c.batch_size + 1) + (r0 - b * c.batch_size);
+        for (uint32_t i = lane; i < nr; i += 32) {
+            const uint64_t a = bbase + (uint32_t)offs[i];
+            if (a < total) mid |= utf8_mid_char(c, (uint32_t)a);
+        }
     }
     if (mid) set_err(err, c.colstripe, ORCB_ARROW);
 }
@@ -2541,7 +2542,7 @@ int launch_strings(StrCol* cols, uint32_t ncols, uint32_t ntiles, uint32_t* err,
     LAUNCH_CHECK();
     k_str_offsets<<<blocks_for_warps(ntiles, 4), 128, 0, st>>>(cols, ncols, ntiles, err);
     LAUNCH_CHECK();
-    k_utf8_bounds<<<blocks_for_warps(ntiles, 4), 128, 0, st>>>(cols, ncols, ntiles, err);
+    k_utf8_bounds<<<ncols, 128, 0, st>>>(cols, ncols, err);
     LAUNCH_CHECK();
     return 0;
 }
