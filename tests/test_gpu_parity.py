@@ -272,6 +272,54 @@ def test_string_dictionary_shapes(ob, tmp_path):
                 assert_batches_identical(got, exp, f"strings/{comp}/bs={bs}/index={use_index}")
 
 
+# ---- degenerate shapes ----------------------------------------------------------------------------------------
+def test_edge_shapes(ob, tmp_path):
+    """All-null and constant columns, empty strings, one-row and zero-row files, batch sizes 1 / 7 / larger than the
+    stripe, with and without dictionary encoding and compression."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tools"))
+    import gen_orc
+    import numpy as np
+    import pyarrow as pa
+    from decimal import Decimal
+    from oracle import orc_oracle as oo
+
+    def table(n):
+        rng = np.random.default_rng(n)
+        return pa.table({
+            "null_i": pa.array([None] * n, pa.int64()),
+            "null_s": pa.array([None] * n, pa.string()),
+            "null_d": pa.array([None] * n, pa.decimal128(20, 4)),
+            "null_b": pa.array([None] * n, pa.bool_()),
+            "null_t": pa.array([None] * n, pa.timestamp("ns")),
+            "empty_s": pa.array([""] * n, pa.string()),
+            "const_i": pa.array([42] * n, pa.int32()),
+            "const_s": pa.array(["same"] * n, pa.string()),
+            "true_b": pa.array([True] * n, pa.bool_()),
+            "i8": pa.array(rng.integers(-128, 128, n), pa.int8()),
+            "i16": pa.array(rng.integers(-32768, 32768, n), pa.int16()),
+            "f32": pa.array(rng.random(n), pa.float32()),
+            "bin": pa.array([bytes([i % 256]) * (i % 5) for i in range(n)], pa.binary()),
+            "dec": pa.array([Decimal(int(v)).scaleb(-3) for v in rng.integers(-10**12, 10**12, n)], pa.decimal128(18, 3)),
+            "last_null": pa.array([i if i < n - 1 else None for i in range(n)], pa.int64()),
+            "date": pa.array(rng.integers(-30000, 60000, n), pa.int32()).cast(pa.date32()),
+        })
+
+    for n in (0, 1, 31, 1025, 20_001):
+        for comp in ("uncompressed", "snappy"):
+            for thr in (0.0, 1.0):
+                p = gen_orc.write(table(n), str(tmp_path / f"e{n}_{comp}_{thr}.orc"), compression=comp, block_size=64 << 10,
+                                  dict_threshold=thr, row_index_stride=1000)
+                data = open(p, "rb").read()
+                of = oo.OracleFile(data)
+                for bs in (1, 7, 8192, 100_000):
+                    if bs == 1 and n > 1025:
+                        continue
+                    exp = of.read(batch_size=bs)
+                    got = list(ob.ArrowReaderBuilder.try_new(data).with_batch_size(bs).build())
+                    assert_batches_identical(got, exp, f"edge n={n} {comp} dict={thr} bs={bs}")
+
+
 # ---- builder options (src/arrow_reader.rs:70-173) through the decode path -----------------------------------
 def test_builder_options(ob, tmp_path):
     import sys
