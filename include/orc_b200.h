@@ -137,6 +137,22 @@ int orcb_schema(const OrcbFile* f, const OrcbReadOptions* opt, struct ArrowSchem
 
 /* ArrowReaderBuilder::build (src/arrow_reader.rs:207-230) */
 int orcb_reader_new(OrcbFile* f, const OrcbReadOptions* opt, OrcbReader** out);
+/* ArrowReaderBuilder::with_row_selection (src/arrow_reader.rs:113-116; RowSelector src/row_selection.rs:32-57):
+ * runs of rows to skip / to read, counted over the stripes the reader visits.  Batches follow
+ * NaiveStripeDecoder::next_with_row_selection (src/array_decoder/mod.rs:313-364) exactly; they are views into
+ * the decoded stripe (Arrow `offset` != 0), stripes without a selected row are never staged. */
+typedef struct OrcbRowSelector {
+    uint64_t row_count;
+    int32_t skip;      /* 1 = skip these rows, 0 = read them */
+    int32_t reserved;
+} OrcbRowSelector;
+int orcb_reader_new_with_selection(OrcbFile* f, const OrcbReadOptions* opt, const OrcbRowSelector* selectors,
+                                   uint32_t n_selectors, OrcbReader** out);
+/* Host-only: the batches a selection yields, as (stripe ordinal, first row, rows) triples in output order, for stripes
+ * of the given row counts; applies[s] = 0 where the stripe is read whole because the selection was used up before it
+ * (src/arrow_reader.rs:296-309).  *n_triples is the number of triples (also when it exceeds cap_triples). */
+int orcb_selection_plan(const OrcbRowSelector* selectors, uint32_t n_selectors, const uint64_t* stripe_rows, uint32_t n_stripes,
+                        uint64_t batch_size, int32_t* applies, uint64_t* triples, size_t cap_triples, size_t* n_triples);
 void orcb_reader_free(OrcbReader* r);
 /* ArrowReader::total_row_count (src/arrow_reader.rs:243-247) */
 uint64_t orcb_reader_total_row_count(const OrcbReader* r);

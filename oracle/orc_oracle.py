@@ -462,7 +462,7 @@ class OracleFile:
             out.append((name, cid, present, payload))
         return n, out
 
-    def read_stripe(self, si: int, batch_size: int = 8192, columns=None, ts_unit: str = "ns"):
+    def read_stripe(self, si: int, batch_size: int = 8192, columns=None, ts_unit: str = "ns", views=None):
         """Batches of one stripe as pyarrow RecordBatches with the reference's physical layout."""
         import pyarrow as pa
         n, cols = self.decode_stripe_columns(si, columns, ts_unit)
@@ -471,22 +471,85 @@ class OracleFile:
         spaced = []
         for name, cid, present, payload in cols:
             spaced.append(_to_rows(present, payload, n))
+        if views is None:
+            views = [(a, min(batch_size, n - a)) for a in range(0, n, batch_size)]
         batches = []
-        a = 0
-        while a < n:
-            b = min(a + batch_size, n)
+        for a, k in views:
             arrays = []
             for (name, cid, present, payload), rows in zip(cols, spaced):
-                arrays.append(_slice_to_arrow(schema.field(name).type, present, payload, rows, a, b))
-            batches.append(pa.RecordBatch.from_arrays(arrays, schema=schema))
-            a = b
+                arrays.append(_slice_to_arrow(schema.field(name).type, present, payload, rows, a, a + k))
+            if not arrays:
+                batches.append(pa.RecordBatch.from_struct_array(pa.array([{}] * k, pa.struct([]))))
+            else:
+                batches.append(pa.RecordBatch.from_arrays(arrays, schema=schema))
         return batches
 
-    def read(self, batch_size: int = 8192, columns=None, ts_unit: str = "ns", stripes=None):
+    def read(self, batch_size: int = 8192, columns=None, ts_unit: str = "ns", stripes=None, selection=None):
+        """`selection`: [(skip, row_count), ...] as ArrowReaderBuilder::with_row_selection takes it."""
+        order = list(range(len(self.stripes)) if stripes is None else stripes)
+        plan = None if selection is None else selection_views(selection, [self.stripes[si].number_of_rows for si in order], batch_size)
         out = []
-        for si in (range(len(self.stripes)) if stripes is None else stripes):
-            out.extend(self.read_stripe(si, batch_size, columns, ts_unit))
+        for k, si in enumerate(order):
+            views = None
+            if plan is not None and plan[k] is not None:
+                views = plan[k]
+                if not views:
+                    continue
+            out.extend(self.read_stripe(si, batch_size, columns, ts_unit, views))
         return out
+
+
+def selection_views(selection, stripe_rows, batch_size):
+    """Row ranges each stripe yields under a row selection (None = the stripe is read whole).  Follows
+    RowSelection::from(Vec<RowSelector>) (src/row_selection.rs:466-482), ArrowReader::try_advance_stripe
+    (src/arrow_reader.rs:296-309: `split_off(stripe_rows)` while the selection still has rows, no selection at all
+    afterwards) and NaiveStripeDecoder::next_with_row_selection (src/array_decoder/mod.rs:313-364), including its
+    habit of staying on a selector until one step has covered the selector's whole row_count."""
+    sel = []
+    for skip, count in selection:
+        if count == 0:
+            continue
+        if sel and sel[-1][0] == bool(skip):
+            sel[-1][1] += count
+        else:
+            sel.append([bool(skip), count])
+    out = []
+    for rows in stripe_rows:
+        if sum(c for _, c in sel) == 0:
+            out.append(None)
+            continue
+        # split_off(rows)
+        head, acc, idx = [], 0, None
+        for i, (sk, c) in enumerate(sel):
+            acc += c
+            if acc > rows:
+                idx = i
+                break
+        if idx is None:
+            head, sel = sel, []
+        else:
+            head, rest = [list(x) for x in sel[:idx]], [list(x) for x in sel[idx:]]
+            overflow = acc - rows
+            if rest[0][1] != overflow:
+                head.append([rest[0][0], rest[0][1] - overflow])
+            rest[0][1] = overflow
+            sel = rest
+        # next_with_row_selection
+        views, index, si = [], 0, 0
+        while index < rows and si < len(head):
+            skip, count = head[si]
+            remaining = rows - index
+            k = min(count, remaining) if skip else min(count, batch_size, remaining)
+            if k == 0:
+                si += 1
+                continue
+            if not skip:
+                views.append((index, k))
+            index += k
+            if k >= count:
+                si += 1
+        out.append(views)
+    return out
 
 
 # old link names ("backward" file of the tz database) that minimal tzdata installs leave out; chrono-tz knows them

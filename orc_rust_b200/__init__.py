@@ -104,7 +104,7 @@ EXPORTED_SYMBOLS = [
     "orcb_open_memory", "orcb_open_path", "orcb_file_free", "orcb_file_num_rows", "orcb_file_num_stripes",
     "orcb_file_compression", "orcb_file_compression_block_size", "orcb_file_row_index_stride",
     "orcb_file_num_root_columns", "orcb_file_root_column_name", "orcb_file_stripe_info", "orcb_schema",
-    "orcb_reader_new", "orcb_reader_free", "orcb_reader_total_row_count", "orcb_reader_next",
+    "orcb_reader_new", "orcb_reader_new_with_selection", "orcb_selection_plan", "orcb_reader_free", "orcb_reader_total_row_count", "orcb_reader_next",
     "orcb_reader_next_device", "orcb_job_new", "orcb_job_free", "orcb_job_plan", "orcb_job_stage",
     "orcb_job_launch", "orcb_job_finish", "orcb_job_stats", "orcb_job_restage", "orcb_job_kernel_stats", "orcb_job_num_batches", "orcb_job_export_batch",
     "orcb_job_export_batch_device", "orcb_decode_int_rle", "orcb_decode_byte_rle", "orcb_decode_bool_rle",
@@ -133,6 +133,10 @@ def lib() -> ctypes.CDLL:
                      "orcb_reader_total_row_count", "orcb_job_num_batches"):
             getattr(L, name).argtypes = [ctypes.c_void_p]
         L.orcb_file_root_column_name.argtypes = [ctypes.c_void_p, ctypes.c_uint32]
+        L.orcb_selection_plan.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint64,
+                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+        L.orcb_reader_new_with_selection.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32,
+                                                     ctypes.c_void_p]
         L.orcb_file_stripe_info.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint64)]
         L.orcb_open_memory.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]
         L.orcb_open_path.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]
@@ -251,6 +255,78 @@ def _import_schema(fh, opts):
     return pa.Schema._import_from_c(ctypes.addressof(cs))
 
 
+class _RowSelectorC(ctypes.Structure):
+    _fields_ = [("row_count", ctypes.c_uint64), ("skip", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+class RowSelector:
+    """src/row_selection.rs:32-57"""
+
+    def __init__(self, row_count: int, skip: bool):
+        self.row_count, self.skip = int(row_count), bool(skip)
+
+    @classmethod
+    def select(cls, row_count: int) -> "RowSelector":
+        return cls(row_count, False)
+
+    @classmethod
+    def skip_rows(cls, row_count: int) -> "RowSelector":  # `RowSelector::skip` (the attribute has the name)
+        return cls(row_count, True)
+
+    def __repr__(self):
+        return f"RowSelector({'skip' if self.skip else 'select'} {self.row_count})"
+
+
+class RowSelection:
+    """src/row_selection.rs:90-460 (the parts a reader needs): a list of selectors, normalised on construction
+    as `RowSelection::from(Vec<RowSelector>)` does (:466-482)."""
+
+    def __init__(self, selectors=()):
+        if isinstance(selectors, RowSelection):
+            selectors = selectors.selectors
+        out = []
+        for x in selectors:
+            if not isinstance(x, RowSelector):
+                skip, count = x
+                x = RowSelector(count, skip)
+            if x.row_count == 0:
+                continue
+            if out and out[-1].skip == x.skip:
+                out[-1] = RowSelector(out[-1].row_count + x.row_count, x.skip)
+            else:
+                out.append(RowSelector(x.row_count, x.skip))
+        self.selectors = out
+
+    @classmethod
+    def from_consecutive_ranges(cls, ranges, total_rows: int) -> "RowSelection":
+        """:158-199: ascending, non-overlapping [start, end) ranges to read out of `total_rows`."""
+        sel, last = [], 0
+        for a, b in ranges:
+            if b <= a:
+                continue
+            if a > last:
+                sel.append(RowSelector(a - last, True))
+            sel.append(RowSelector(b - a, False))
+            last = b
+        if last < total_rows:
+            sel.append(RowSelector(total_rows - last, True))
+        return cls(sel)
+
+    @classmethod
+    def select_all(cls, row_count: int) -> "RowSelection":
+        return cls([RowSelector(row_count, False)])
+
+    @classmethod
+    def skip_all(cls, row_count: int) -> "RowSelection":
+        return cls([RowSelector(row_count, True)])
+
+    def row_count(self) -> int:
+        return sum(x.row_count for x in self.selectors)
+
+    def selected_row_count(self) -> int:
+        return sum(x.row_count for x in self.selectors if not x.skip)
+
+
 class ArrowReaderBuilder:
     """Mirror of `ArrowReaderBuilder` (src/arrow_reader.rs:39-231) with one extra option, `with_device`."""
 
@@ -303,8 +379,11 @@ class ArrowReaderBuilder:
         self._max_stripes = n
         return self
 
-    def with_row_selection(self, *_a, **_k):
-        raise OrcError(22, "row selection is not on the device path yet (SURVEY §8(f) rank 1)")
+    def with_row_selection(self, selection) -> "ArrowReaderBuilder":
+        """`ArrowReaderBuilder::with_row_selection` (src/arrow_reader.rs:113-116).  `selection`: a RowSelection or an
+        iterable of RowSelector / (skip, row_count) pairs, counted over the stripes the reader visits."""
+        self._selection = RowSelection(selection)
+        return self
 
     def with_predicate(self, *_a, **_k):
         raise OrcError(22, "predicate pushdown is not on the device path yet (SURVEY §8(f) rank 1)")
@@ -329,7 +408,16 @@ class ArrowReader:
         self._opts, self._keep = b._options()
         self._schema = _import_schema(self._file._h, self._opts)
         self._h = ctypes.c_void_p()
-        _check(lib().orcb_reader_new(self._file._h, ctypes.byref(self._opts), ctypes.byref(self._h)))
+        sel = getattr(b, "_selection", None)
+        if sel is None:
+            _check(lib().orcb_reader_new(self._file._h, ctypes.byref(self._opts), ctypes.byref(self._h)))
+        else:
+            arr = (_RowSelectorC * max(len(sel.selectors), 1))()
+            for i, x in enumerate(sel.selectors):
+                arr[i].row_count = x.row_count
+                arr[i].skip = 1 if x.skip else 0
+            _check(lib().orcb_reader_new_with_selection(self._file._h, ctypes.addressof(self._opts), ctypes.addressof(arr),
+                                                        len(sel.selectors), ctypes.addressof(self._h)))
 
     def __del__(self):
         if getattr(self, "_h", None) and self._h.value and _lib is not None:
@@ -427,6 +515,27 @@ class DecodeJob:
 
     def batches(self):
         return [self.batch(i) for i in range(self.num_batches)]
+
+
+def selection_plan(selection, stripe_rows, batch_size=8192):
+    """Host-only view of `orcb_selection_plan`: per stripe None (read whole) or the list of (first row, rows)."""
+    raw = list(selection.selectors) if isinstance(selection, RowSelection) else [
+        x if isinstance(x, RowSelector) else RowSelector(x[1], x[0]) for x in selection]
+    arr = (_RowSelectorC * max(len(raw), 1))()
+    for i, x in enumerate(raw):  # un-normalised on purpose: the library normalises like RowSelection::from
+        arr[i].row_count, arr[i].skip = x.row_count, 1 if x.skip else 0
+    rows = (ctypes.c_uint64 * max(len(stripe_rows), 1))(*stripe_rows)
+    applies = (ctypes.c_int32 * max(len(stripe_rows), 1))()
+    n = ctypes.c_size_t(0)
+    _check(lib().orcb_selection_plan(ctypes.addressof(arr), len(raw), ctypes.addressof(rows), len(stripe_rows), batch_size,
+                                     ctypes.addressof(applies), None, 0, ctypes.addressof(n)))
+    tri = (ctypes.c_uint64 * max(3 * n.value, 1))()
+    _check(lib().orcb_selection_plan(ctypes.addressof(arr), len(raw), ctypes.addressof(rows), len(stripe_rows), batch_size,
+                                     ctypes.addressof(applies), ctypes.addressof(tri), n.value, ctypes.addressof(n)))
+    out = [([] if applies[s] else None) for s in range(len(stripe_rows))]
+    for k in range(n.value):
+        out[tri[3 * k]].append((tri[3 * k + 1], tri[3 * k + 2]))
+    return out
 
 
 # ---- stream-level entry points (parity tests against the reference's unit-test vectors) -------------

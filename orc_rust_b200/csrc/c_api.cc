@@ -35,6 +35,9 @@ struct OrcbReader {
     std::unique_ptr<Job> job;
     uint64_t next_batch = 0;
     bool failed = false;
+    // with_row_selection: per entry of `stripes`, whether a selection applies and the row ranges it yields
+    bool has_selection = false;
+    std::vector<std::pair<bool, std::vector<std::pair<uint32_t, uint32_t>>>> views;
 };
 
 template <typename F>
@@ -183,6 +186,48 @@ int orcb_reader_new(OrcbFile* f, const OrcbReadOptions* opt, OrcbReader** out) {
     });
 }
 
+int orcb_reader_new_with_selection(OrcbFile* f, const OrcbReadOptions* opt, const OrcbRowSelector* selectors, uint32_t n_selectors,
+                                   OrcbReader** out) {
+    return guarded([&] {
+        if (!f || !out || (!selectors && n_selectors)) fail(ORCB_INVALID_ARGUMENT, "NULL argument");
+        auto r = std::make_unique<OrcbReader>();
+        r->file = f;
+        r->opt = ReadOptions::from_c(opt);
+        (void)project_columns(f->meta, r->opt);
+        r->stripes = select_stripes(f->meta, r->opt);
+        std::vector<RowSelector> sel;
+        for (uint32_t i = 0; i < n_selectors; i++) sel.push_back({selectors[i].row_count, selectors[i].skip != 0});
+        std::vector<uint64_t> rows;
+        for (uint32_t s : r->stripes) rows.push_back(f->meta.stripes[s].rows);
+        r->views = selection_views(std::move(sel), rows, r->opt.batch_size);
+        r->has_selection = true;
+        *out = r.release();
+    });
+}
+
+int orcb_selection_plan(const OrcbRowSelector* selectors, uint32_t n_selectors, const uint64_t* stripe_rows, uint32_t n_stripes,
+                        uint64_t batch_size, int32_t* applies, uint64_t* triples, size_t cap_triples, size_t* n_triples) {
+    return guarded([&] {
+        if ((!selectors && n_selectors) || (!stripe_rows && n_stripes) || !n_triples) fail(ORCB_INVALID_ARGUMENT, "NULL argument");
+        std::vector<RowSelector> sel;
+        for (uint32_t i = 0; i < n_selectors; i++) sel.push_back({selectors[i].row_count, selectors[i].skip != 0});
+        const auto plan = selection_views(std::move(sel), std::vector<uint64_t>(stripe_rows, stripe_rows + n_stripes), batch_size ? batch_size : 8192);
+        size_t k = 0;
+        for (uint32_t s = 0; s < n_stripes; s++) {
+            if (applies) applies[s] = plan[s].first ? 1 : 0;
+            for (auto& v : plan[s].second) {
+                if (triples && k < cap_triples) {
+                    triples[3 * k] = s;
+                    triples[3 * k + 1] = v.first;
+                    triples[3 * k + 2] = v.second;
+                }
+                k++;
+            }
+        }
+        *n_triples = k;
+    });
+}
+
 void orcb_reader_free(OrcbReader* r) { delete r; }
 
 uint64_t orcb_reader_total_row_count(const OrcbReader* r) { return r->file->meta.num_rows; }
@@ -198,10 +243,20 @@ static bool reader_advance(OrcbReader* r) {
         while (r->next_stripe < r->stripes.size() && tasks.size() < group) {
             const StripeInfo& si = r->file->meta.stripes[r->stripes[r->next_stripe]];
             if (!tasks.empty() && bytes + si.data_length > (1ull << 30)) break;  // bound one launch plan to ~1 GiB in
+            StripeTask task{&r->file->meta, r->stripes[r->next_stripe]};
+            if (r->has_selection && r->views[r->next_stripe].first) {
+                task.has_views = true;
+                task.views = r->views[r->next_stripe].second;
+                if (task.views.empty()) {  // nothing selected in this stripe: not even staged
+                    r->next_stripe++;
+                    continue;
+                }
+            }
             bytes += si.data_length;
-            tasks.push_back({&r->file->meta, r->stripes[r->next_stripe]});
+            tasks.push_back(std::move(task));
             r->next_stripe++;
         }
+        if (tasks.empty()) continue;  // only unselected stripes were left in this round
         r->job = std::make_unique<Job>(std::move(tasks), r->opt);
         r->next_batch = 0;
         r->job->plan();

@@ -300,6 +300,15 @@ void Job::plan() {
     if (planned_) return;
     if (opt_.batch_size == 0) fail(ORCB_INVALID_ARGUMENT, "batch_size must be > 0");
     task_first_cs_.clear();
+    for (auto& t : tasks_) view_mode_ |= t.has_views;
+    user_batch_size_ = opt_.batch_size;
+    if (view_mode_) {
+        // row selection: one internal batch per stripe (stripe-level offsets and bitmaps); the user's batches are
+        // views into it, exported through the Arrow `offset` field
+        uint64_t mx = 1;
+        for (auto& t : tasks_) mx = std::max<uint64_t>(mx, t.file->stripes[t.stripe].rows);
+        opt_.batch_size = (uint32_t)std::min<uint64_t>(mx, 0xfffffff0ull);
+    }
     for (uint32_t t = 0; t < tasks_.size(); t++) plan_stripe(t);
 
     if (pool_blocks_) {
@@ -371,12 +380,32 @@ void Job::plan() {
     // batches
     batch_task_.clear();
     batch_idx_.clear();
+    batch_row0_.clear();
+    batch_rows_.clear();
     for (uint32_t t = 0; t < tasks_.size(); t++) {
         const StripeInfo& si = tasks_[t].file->stripes[tasks_[t].stripe];
+        if (view_mode_) {
+            std::vector<std::pair<uint32_t, uint32_t>> whole;
+            const auto* views = &tasks_[t].views;
+            if (!tasks_[t].has_views) {  // stripe without a selection inside a job that has one: consecutive batches
+                for (uint64_t r = 0; r < si.rows; r += user_batch_size_)
+                    whole.emplace_back((uint32_t)r, (uint32_t)std::min<uint64_t>(user_batch_size_, si.rows - r));
+                views = &whole;
+            }
+            for (auto& v : *views) {
+                batch_task_.push_back(t);
+                batch_idx_.push_back(0);
+                batch_row0_.push_back(v.first);
+                batch_rows_.push_back(v.second);
+            }
+            continue;
+        }
         uint32_t nb = (uint32_t)((si.rows + opt_.batch_size - 1) / opt_.batch_size);
         for (uint32_t b = 0; b < nb; b++) {
             batch_task_.push_back(t);
             batch_idx_.push_back(b);
+            batch_row0_.push_back(0);
+            batch_rows_.push_back((uint32_t)std::min<uint64_t>(opt_.batch_size, si.rows - (uint64_t)b * opt_.batch_size));
         }
     }
     planned_ = true;
@@ -1378,8 +1407,9 @@ void Job::export_batch(uint64_t i, ArrowArray* out) {
     const uint32_t* nulls = (const uint32_t*)(h_meta_ + o_nulls_);
     const uint64_t* ptrs = (const uint64_t*)(h_meta_ + o_ptrs_);
     const uint32_t cs0 = task_first_cs_[t];
-    const uint32_t n_rows = (uint32_t)tasks_[t].file->stripes[tasks_[t].stripe].rows;  // also with an empty projection (mod.rs:538-549)
-    const uint32_t rows = std::min(bs, n_rows - b * bs);
+    // (the stripe's row count also sizes the batches of an empty projection, mod.rs:538-549)
+    const uint32_t rows = batch_rows_[i];
+    const int64_t voff = view_mode_ ? (int64_t)batch_row0_[i] : 0;  // view into the stripe-wide internal batch
     build_batch(this, out, rows, cols_.size());
     auto* tp = (ArrayPriv*)out->private_data;
     tp->keep1 = host_out_;
@@ -1392,10 +1422,19 @@ void Job::export_batch(uint64_t i, ArrowArray* out) {
         int64_t nc = 0;
         const void* vbuf = nullptr;
         if (cp.has_present) {
-            nc = nulls[cp.nulls_idx + b];
-            if (nc) vbuf = host_out_->out + (cp.validity & omask) + (uint64_t)b * cp.validity_stride;
+            const uint8_t* bits = host_out_->out + (cp.validity & omask) + (uint64_t)b * cp.validity_stride;
+            if (view_mode_) {
+                // nulls inside the view: counted here, the device only knows the stripe-wide figure
+                int64_t valid = 0;
+                for (int64_t r = voff; r < voff + rows; r++) valid += (bits[r >> 3] >> (r & 7)) & 1;
+                nc = rows - valid;
+            } else {
+                nc = nulls[cp.nulls_idx + b];
+            }
+            if (nc) vbuf = bits;
         }
         init_array(a, rows, nc, is_str ? 3 : 2);
+        a->offset = voff;
         auto* ap = (ArrayPriv*)a->private_data;
         ap->keep1 = host_out_;
         ap->buffers[0] = vbuf;
@@ -1426,8 +1465,8 @@ void Job::export_batch_device(uint64_t i, ArrowDeviceArray* out) {
     const uint32_t* nulls = (const uint32_t*)(h_meta_ + o_nulls_);
     const uint64_t* ptrs = (const uint64_t*)(h_meta_ + o_ptrs_);
     const uint32_t cs0 = task_first_cs_[t];
-    const uint32_t n_rows = (uint32_t)tasks_[t].file->stripes[tasks_[t].stripe].rows;
-    const uint32_t rows = std::min(bs, n_rows - b * bs);
+    const uint32_t rows = batch_rows_[i];
+    const int64_t voff = view_mode_ ? (int64_t)batch_row0_[i] : 0;
     memset(out, 0, sizeof(*out));
     build_batch(this, &out->array, rows, cols_.size());
     out->device_id = opt_.device;
@@ -1444,10 +1483,11 @@ void Job::export_batch_device(uint64_t i, ArrowDeviceArray* out) {
         int64_t nc = 0;
         const void* vbuf = nullptr;
         if (cp.has_present) {
-            nc = nulls[cp.nulls_idx + b];
+            nc = view_mode_ ? (nulls[cp.nulls_idx + b] ? -1 : 0) : (int64_t)nulls[cp.nulls_idx + b];  // -1: not counted for a view
             if (nc) vbuf = base_[AR_OUT] + (cp.validity & omask) + (uint64_t)b * cp.validity_stride;
         }
         init_array(a, rows, nc, is_str ? 3 : 2);
+        a->offset = voff;
         auto* ap = (ArrayPriv*)a->private_data;
         ap->keep1 = dev_keepalive_;
         ap->buffers[0] = vbuf;
@@ -1463,6 +1503,73 @@ void Job::export_batch_device(uint64_t i, ArrowDeviceArray* out) {
             ap->buffers[1] = base_[AR_OUT] + (cp.values & omask) + (uint64_t)b * bs * oc.width;
         }
     }
+}
+
+
+std::vector<std::pair<bool, std::vector<std::pair<uint32_t, uint32_t>>>> selection_views(
+    std::vector<RowSelector> raw, const std::vector<uint64_t>& stripe_rows, uint64_t batch_size) {
+    // RowSelection::from(Vec<RowSelector>): empty selectors dropped, neighbours of the same kind merged
+    std::vector<RowSelector> sel;
+    for (auto& r : raw) {
+        if (r.row_count == 0) continue;
+        if (!sel.empty() && sel.back().skip == r.skip) sel.back().row_count += r.row_count;
+        else sel.push_back(r);
+    }
+    auto total = [](const std::vector<RowSelector>& v) {
+        uint64_t n = 0;
+        for (auto& x : v) n += x.row_count;
+        return n;
+    };
+    // RowSelection::split_off: the first `n` rows leave `self`
+    auto split_off = [](std::vector<RowSelector>& self, uint64_t n) {
+        uint64_t acc = 0;
+        size_t idx = self.size();
+        for (size_t i = 0; i < self.size(); i++) {
+            acc += self[i].row_count;
+            if (acc > n) { idx = i; break; }
+        }
+        if (idx == self.size()) {
+            std::vector<RowSelector> all;
+            all.swap(self);
+            return all;
+        }
+        std::vector<RowSelector> head(self.begin(), self.begin() + idx), rest(self.begin() + idx, self.end());
+        const uint64_t overflow = acc - n;
+        if (rest.front().row_count != overflow) head.push_back({rest.front().row_count - overflow, rest.front().skip});
+        rest.front().row_count = overflow;
+        self.swap(rest);
+        return head;
+    };
+    std::vector<std::pair<bool, std::vector<std::pair<uint32_t, uint32_t>>>> out;
+    for (uint64_t rows : stripe_rows) {
+        std::vector<std::pair<uint32_t, uint32_t>> views;
+        if (total(sel) == 0) {  // arrow_reader.rs:298: a used-up selection no longer restricts anything
+            out.emplace_back(false, views);
+            continue;
+        }
+        const std::vector<RowSelector> s = split_off(sel, rows);
+        // NaiveStripeDecoder::next / next_with_row_selection.  A selector is left behind only once a single step has
+        // covered its whole row_count, so a select longer than the batch size keeps yielding batches (kept as is)
+        uint64_t index = 0;
+        size_t si = 0;
+        while (index < rows && si < s.size()) {
+            const uint64_t remaining = rows - index;
+            if (s[si].skip) {
+                const uint64_t k = std::min(s[si].row_count, remaining);
+                if (k == 0) { si++; continue; }
+                index += k;
+                if (k >= s[si].row_count) si++;
+            } else {
+                const uint64_t k = std::min(std::min(s[si].row_count, batch_size), remaining);
+                if (k == 0) { si++; continue; }
+                views.emplace_back((uint32_t)index, (uint32_t)k);
+                index += k;
+                if (k >= s[si].row_count) si++;
+            }
+        }
+        out.emplace_back(true, views);
+    }
+    return out;
 }
 
 }  // namespace orcb

@@ -46,7 +46,22 @@ void export_schema(const FileMeta& fm, const std::vector<OutColumn>& cols, Arrow
 struct StripeTask {
     const FileMeta* file;
     uint32_t stripe;
+    // row selection (src/array_decoder/mod.rs:313-364): the batches of this stripe are these row ranges, in order,
+    // instead of consecutive batch_size slices.  The stripe is decoded once; the ranges are exported as views.
+    bool has_views = false;
+    std::vector<std::pair<uint32_t, uint32_t>> views;  // (first row, rows)
 };
+
+// RowSelector (src/row_selection.rs:32-57)
+struct RowSelector {
+    uint64_t row_count;
+    bool skip;
+};
+// The batches each stripe yields under a row selection: restates RowSelection::from(Vec) (:466-482), split_off
+// (:278-320), ArrowReader::try_advance_stripe (src/arrow_reader.rs:296-309) and next_with_row_selection.
+// out[i].first = false: the stripe is read without a selection (the selection was used up before it).
+std::vector<std::pair<bool, std::vector<std::pair<uint32_t, uint32_t>>>> selection_views(
+    std::vector<RowSelector> selectors, const std::vector<uint64_t>& stripe_rows, uint64_t batch_size);
 
 // where one column of one stripe lands
 struct ColStripePlan {
@@ -145,6 +160,9 @@ class Job {
     std::vector<ColStripePlan> colstripes_;
     // batch i -> (task, batch-in-stripe)
     std::vector<uint32_t> batch_task_, batch_idx_;
+    std::vector<uint32_t> batch_row0_, batch_rows_;  // views (row selection): first row inside the stripe / rows
+    uint32_t user_batch_size_ = 8192;
+    bool view_mode_ = false;                          // every stripe is one internal batch, user batches are views
     std::vector<uint32_t> task_first_cs_;
 
     // stats

@@ -387,6 +387,49 @@ def test_builder_options(ob, tmp_path):
     assert a != b
 
 
+# ---- row selection (ArrowReaderBuilder::with_row_selection) -------------------------------------------------
+def test_row_selection(ob, tmp_path):
+    """Same batches (row counts and contents) as the oracle's restatement of the reference's selection logic: the
+    reference's own cases, then random selections over a multi-stripe file with nulls, strings, booleans.  The
+    device batches are views (Arrow offset != 0), so the comparison is Arrow equality, not buffer bytes."""
+    import random
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tools"))
+    import gen_orc
+    import kat_vectors as kv
+    import pyarrow as pa
+    from oracle import orc_oracle as oo
+
+    def check(data, sel, what, **kw):
+        of = oo.OracleFile(data)
+        exp = of.read(batch_size=kw.get("batch_size", 8192), columns=kw.get("columns"), selection=sel)
+        b = ob.ArrowReaderBuilder.try_new(data).with_row_selection(sel)
+        if "batch_size" in kw:
+            b = b.with_batch_size(kw["batch_size"])
+        if kw.get("columns"):
+            b = b.with_projection(kw["columns"])
+        got = list(b.build())
+        assert [x.num_rows for x in got] == [x.num_rows for x in exp], what
+        for i, (g, e) in enumerate(zip(got, exp)):
+            assert g.schema.names == e.schema.names, what
+            assert g.equals(e), f"{what}: batch {i} differs"
+            for c in range(g.num_columns):
+                assert g.column(c).null_count == e.column(c).null_count, f"{what}: null count of batch {i} col {c}"
+
+    for name, fname, sel, proj, rows in kv.ROW_SELECTION:
+        check(open(os.path.join(GOLDEN, "ref_basic", fname), "rb").read(), sel, name, columns=proj)
+    p = gen_orc.write(gen_orc.nullheavy_table(25_000, 1), str(tmp_path / "nh.orc"), stripe_size=256 << 10)
+    data = open(p, "rb").read()
+    stripes = [s.number_of_rows for s in oo.OracleFile(data).stripes]
+    assert len(stripes) >= 3
+    rng = random.Random(9)
+    for k in range(25):
+        sel = [(rng.random() < 0.5, rng.choice([1, 3, 50, 999, 5000, 9000, 30000])) for _ in range(rng.randrange(1, 9))]
+        check(data, sel, f"random#{k} {sel}", batch_size=rng.choice([7, 1000, 8192]))
+    li = gen_orc.write(gen_orc.lineitem_table(8_000, 2), str(tmp_path / "li.orc"), compression="snappy", block_size=64 << 10)
+    check(open(li, "rb").read(), [(True, 10_000), (False, 300), (True, 12_000), (False, 5_000)], "lineitem snappy", batch_size=4096)
+
+
 # ---- corrupted inputs: same verdict as the oracle, same bytes whenever both still decode ------------------
 def _mutations(data0: bytes, lo: int, hi: int, seed: int, count: int):
     import random
