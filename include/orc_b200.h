@@ -148,6 +148,14 @@ typedef struct OrcbRowSelector {
 } OrcbRowSelector;
 int orcb_reader_new_with_selection(OrcbFile* f, const OrcbReadOptions* opt, const OrcbRowSelector* selectors,
                                    uint32_t n_selectors, OrcbReader** out);
+/* The builder with everything set: selection as above when has_selection != 0, and ArrowReaderBuilder::with_schema
+ * (src/arrow_reader.rs:80-83) when `schema` is not NULL: one field per projected column; every type must be the
+ * default one except timestamps, which may be asked for in any unit (TIMESTAMP: no zone; TIMESTAMP WITH LOCAL TIME
+ * ZONE: "UTC") or as Decimal128(38, 9) nanoseconds (src/array_decoder/timestamp.rs:150-232); anything else is
+ * MismatchedSchema / UnsupportedTypeVariant as in array_decoder_factory (src/array_decoder/mod.rs:390-511).
+ * The schema is only read; the caller keeps and releases it. */
+int orcb_reader_new_ex(OrcbFile* f, const OrcbReadOptions* opt, const OrcbRowSelector* selectors, uint32_t n_selectors,
+                       int has_selection, const struct ArrowSchema* schema, OrcbReader** out);
 /* Host-only: the batches a selection yields, as (stripe ordinal, first row, rows) triples in output order, for stripes
  * of the given row counts; applies[s] = 0 where the stripe is read whole because the selection was used up before it
  * (src/arrow_reader.rs:296-309).  *n_triples is the number of triples (also when it exceeds cap_triples). */

@@ -328,6 +328,8 @@ class OracleFile:
             return simple[k]
         if k == K_DECIMAL:
             return pa.decimal128(t.precision, t.scale)
+        if k in (K_TIMESTAMP, K_TIMESTAMP_INSTANT) and ts_unit == "dec":
+            return pa.decimal128(38, 9)  # with_schema: Decimal128(38, 9) nanoseconds (array_decoder/timestamp.rs:150-232)
         if k == K_TIMESTAMP:
             return pa.timestamp(ts_unit)
         if k == K_TIMESTAMP_INSTANT:
@@ -336,7 +338,7 @@ class OracleFile:
 
     def schema(self, columns: Optional[List[str]] = None, ts_unit: str = "ns"):
         import pyarrow as pa
-        fields = [pa.field(name, self.arrow_type(cid, ts_unit), True) for name, cid in self._projected(columns)]
+        fields = [pa.field(name, self.arrow_type(cid, _unit_of(ts_unit, name)), True) for name, cid in self._projected(columns)]
         md = {k: v.decode("utf-8", "replace") for k, v in self.user_metadata.items()}
         return pa.schema(fields, metadata=md or None)
 
@@ -449,13 +451,26 @@ class OracleFile:
                 if k == K_TIMESTAMP and tz is not None:
                     zone = _zone(tz)
                     base = int(_dt.datetime(2015, 1, 1, tzinfo=zone).timestamp())
-                unit_ns = {"ns": 1, "us": 1000, "ms": 1_000_000, "s": 1_000_000_000}[ts_unit]
-                o = np.empty(nn, dtype=np.int64)
-                _check(lib().orc_oracle_timestamp(_u8p(d), _u8p(sec), ctypes.c_size_t(nn), ctypes.c_int64(base),
-                                                  ctypes.c_int64(unit_ns), _u8p(o)), "timestamp")
-                tz_nulls = None
-                if zone is not None and tz not in ("UTC", "GMT", "Etc/UTC", "Etc/GMT"):
-                    o = _tz_to_utc(o, zone, unit_ns)
+                unit = _unit_of(ts_unit, name)
+                moved = zone is not None and tz not in ("UTC", "GMT", "Etc/UTC", "Etc/GMT")
+                if unit == "dec":
+                    # TimestampNanosecondAsDecimalDecoder (+ ...WithTzDecoder, array_decoder/timestamp.rs:316-333)
+                    o = np.empty((nn, 2), dtype=np.uint64)
+                    lib().orc_oracle_timestamp_i128(_u8p(d), _u8p(sec), ctypes.c_size_t(nn), ctypes.c_int64(base), _u8p(o))
+                    if moved:
+                        vals = [(int(hi) << 64 | int(lo)) - ((int(hi) >> 63) << 128) for lo, hi in o.tolist()]
+                        epoch = _dt.datetime(1970, 1, 1, tzinfo=_dt.timezone.utc)
+                        for i, v in enumerate(vals):
+                            off = int((epoch + _dt.timedelta(seconds=v // 1_000_000_000)).astimezone(zone).utcoffset().total_seconds())
+                            w = (v + off * 1_000_000_000) & ((1 << 128) - 1)
+                            o[i, 0], o[i, 1] = w & 0xFFFFFFFFFFFFFFFF, w >> 64
+                else:
+                    unit_ns = {"ns": 1, "us": 1000, "ms": 1_000_000, "s": 1_000_000_000}[unit]
+                    o = np.empty(nn, dtype=np.int64)
+                    _check(lib().orc_oracle_timestamp(_u8p(d), _u8p(sec), ctypes.c_size_t(nn), ctypes.c_int64(base),
+                                                      ctypes.c_int64(unit_ns), _u8p(o)), "timestamp")
+                    if moved:
+                        o = _tz_to_utc(o, zone, unit_ns)
                 payload = ("prim", o)
             else:
                 raise NotImplementedError(f"nested ORC type kind {k} not restated in the oracle yet")
@@ -557,6 +572,13 @@ _ZONE_LINKS = {"US/Pacific": "America/Los_Angeles", "US/Eastern": "America/New_Y
                "US/Mountain": "America/Denver", "US/Alaska": "America/Anchorage", "US/Hawaii": "Pacific/Honolulu",
                "US/Arizona": "America/Phoenix", "Asia/Calcutta": "Asia/Kolkata", "Japan": "Asia/Tokyo", "PRC": "Asia/Shanghai",
                "GB": "Europe/London", "Eire": "Europe/Dublin", "NZ": "Pacific/Auckland", "Singapore": "Asia/Singapore"}
+
+
+def _unit_of(ts_unit, name: str) -> str:
+    """`ts_unit`: one unit for every timestamp column, or {column: unit}; "dec" = Decimal128(38, 9) (with_schema)."""
+    if isinstance(ts_unit, dict):
+        return ts_unit.get(name, "ns")
+    return ts_unit
 
 
 def _zone(name: str):

@@ -104,7 +104,7 @@ EXPORTED_SYMBOLS = [
     "orcb_open_memory", "orcb_open_path", "orcb_file_free", "orcb_file_num_rows", "orcb_file_num_stripes",
     "orcb_file_compression", "orcb_file_compression_block_size", "orcb_file_row_index_stride",
     "orcb_file_num_root_columns", "orcb_file_root_column_name", "orcb_file_stripe_info", "orcb_schema",
-    "orcb_reader_new", "orcb_reader_new_with_selection", "orcb_selection_plan", "orcb_reader_free", "orcb_reader_total_row_count", "orcb_reader_next",
+    "orcb_reader_new", "orcb_reader_new_with_selection", "orcb_reader_new_ex", "orcb_selection_plan", "orcb_reader_free", "orcb_reader_total_row_count", "orcb_reader_next",
     "orcb_reader_next_device", "orcb_job_new", "orcb_job_free", "orcb_job_plan", "orcb_job_stage",
     "orcb_job_launch", "orcb_job_finish", "orcb_job_stats", "orcb_job_restage", "orcb_job_kernel_stats", "orcb_job_num_batches", "orcb_job_export_batch",
     "orcb_job_export_batch_device", "orcb_decode_int_rle", "orcb_decode_byte_rle", "orcb_decode_bool_rle",
@@ -135,6 +135,8 @@ def lib() -> ctypes.CDLL:
         L.orcb_file_root_column_name.argtypes = [ctypes.c_void_p, ctypes.c_uint32]
         L.orcb_selection_plan.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint64,
                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+        L.orcb_reader_new_ex.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int,
+                                         ctypes.c_void_p, ctypes.c_void_p]
         L.orcb_reader_new_with_selection.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32,
                                                      ctypes.c_void_p]
         L.orcb_file_stripe_info.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint64)]
@@ -385,6 +387,13 @@ class ArrowReaderBuilder:
         self._selection = RowSelection(selection)
         return self
 
+    def with_schema(self, schema) -> "ArrowReaderBuilder":
+        """`ArrowReaderBuilder::with_schema` (src/arrow_reader.rs:80-83): a pyarrow.Schema with one field per projected
+        column.  Types must be the default ones, except that timestamps may be asked for in any unit or as
+        Decimal128(38, 9); the batches carry this schema (its field names included)."""
+        self._schema_override = schema
+        return self
+
     def with_predicate(self, *_a, **_k):
         raise OrcError(22, "predicate pushdown is not on the device path yet (SURVEY §8(f) rank 1)")
 
@@ -409,15 +418,29 @@ class ArrowReader:
         self._schema = _import_schema(self._file._h, self._opts)
         self._h = ctypes.c_void_p()
         sel = getattr(b, "_selection", None)
-        if sel is None:
+        override = getattr(b, "_schema_override", None)
+        if sel is None and override is None:
             _check(lib().orcb_reader_new(self._file._h, ctypes.byref(self._opts), ctypes.byref(self._h)))
         else:
-            arr = (_RowSelectorC * max(len(sel.selectors), 1))()
-            for i, x in enumerate(sel.selectors):
-                arr[i].row_count = x.row_count
-                arr[i].skip = 1 if x.skip else 0
-            _check(lib().orcb_reader_new_with_selection(self._file._h, ctypes.addressof(self._opts), ctypes.addressof(arr),
-                                                        len(sel.selectors), ctypes.addressof(self._h)))
+            n_sel = len(sel.selectors) if sel is not None else 0
+            arr = (_RowSelectorC * max(n_sel, 1))()
+            for i in range(n_sel):
+                arr[i].row_count = sel.selectors[i].row_count
+                arr[i].skip = 1 if sel.selectors[i].skip else 0
+            c_schema = None
+            if override is not None:
+                c_schema = _ArrowSchema()
+                override._export_to_c(ctypes.addressof(c_schema))
+            try:
+                _check(lib().orcb_reader_new_ex(self._file._h, ctypes.addressof(self._opts), ctypes.addressof(arr), n_sel,
+                                                1 if sel is not None else 0,
+                                                ctypes.addressof(c_schema) if c_schema is not None else None,
+                                                ctypes.addressof(self._h)))
+            finally:
+                if c_schema is not None and c_schema.release:  # the library only reads it: release the export here
+                    ctypes.CFUNCTYPE(None, ctypes.c_void_p)(c_schema.release)(ctypes.addressof(c_schema))
+            if override is not None:
+                self._schema = override
 
     def __del__(self):
         if getattr(self, "_h", None) and self._h.value and _lib is not None:

@@ -186,23 +186,31 @@ int orcb_reader_new(OrcbFile* f, const OrcbReadOptions* opt, OrcbReader** out) {
     });
 }
 
-int orcb_reader_new_with_selection(OrcbFile* f, const OrcbReadOptions* opt, const OrcbRowSelector* selectors, uint32_t n_selectors,
-                                   OrcbReader** out) {
+int orcb_reader_new_ex(OrcbFile* f, const OrcbReadOptions* opt, const OrcbRowSelector* selectors, uint32_t n_selectors,
+                       int has_selection, const struct ArrowSchema* schema, OrcbReader** out) {
     return guarded([&] {
         if (!f || !out || (!selectors && n_selectors)) fail(ORCB_INVALID_ARGUMENT, "NULL argument");
         auto r = std::make_unique<OrcbReader>();
         r->file = f;
         r->opt = ReadOptions::from_c(opt);
+        apply_schema_hints(f->meta, r->opt, schema);
         (void)project_columns(f->meta, r->opt);
         r->stripes = select_stripes(f->meta, r->opt);
-        std::vector<RowSelector> sel;
-        for (uint32_t i = 0; i < n_selectors; i++) sel.push_back({selectors[i].row_count, selectors[i].skip != 0});
-        std::vector<uint64_t> rows;
-        for (uint32_t s : r->stripes) rows.push_back(f->meta.stripes[s].rows);
-        r->views = selection_views(std::move(sel), rows, r->opt.batch_size);
-        r->has_selection = true;
+        if (has_selection) {
+            std::vector<RowSelector> sel;
+            for (uint32_t i = 0; i < n_selectors; i++) sel.push_back({selectors[i].row_count, selectors[i].skip != 0});
+            std::vector<uint64_t> rows;
+            for (uint32_t s : r->stripes) rows.push_back(f->meta.stripes[s].rows);
+            r->views = selection_views(std::move(sel), rows, r->opt.batch_size);
+            r->has_selection = true;
+        }
         *out = r.release();
     });
+}
+
+int orcb_reader_new_with_selection(OrcbFile* f, const OrcbReadOptions* opt, const OrcbRowSelector* selectors, uint32_t n_selectors,
+                                   OrcbReader** out) {
+    return orcb_reader_new_ex(f, opt, selectors, n_selectors, 1, nullptr, out);
 }
 
 int orcb_selection_plan(const OrcbRowSelector* selectors, uint32_t n_selectors, const uint64_t* stripe_rows, uint32_t n_stripes,

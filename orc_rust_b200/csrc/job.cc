@@ -85,14 +85,64 @@ std::vector<OutColumn> project_columns(const FileMeta& fm, const ReadOptions& op
                 c.format = "d:" + std::to_string(t.precision) + "," + std::to_string(t.scale);
                 c.width = 16;
                 break;
-            case T_TIMESTAMP: c.format = ts_fmt[opt.timestamp_unit]; c.width = 8; break;
-            case T_TIMESTAMP_INSTANT: c.format = std::string(ts_fmt[opt.timestamp_unit]) + "UTC"; c.width = 8; break;
+            case T_TIMESTAMP: case T_TIMESTAMP_INSTANT: {
+                const int hint = out.size() < opt.ts_hint.size() ? opt.ts_hint[out.size()] : -1;
+                c.ts_unit = hint >= 0 && hint <= 3 ? hint : opt.timestamp_unit;
+                c.ts_decimal = hint == 4;
+                if (c.ts_decimal) {
+                    c.format = "d:38,9";
+                    c.width = 16;
+                    c.ts_unit = 0;
+                } else {
+                    c.format = std::string(ts_fmt[c.ts_unit]) + (t.kind == T_TIMESTAMP_INSTANT ? "UTC" : "");
+                    c.width = 8;
+                }
+                break;
+            }
             default:
                 fail(ORCB_NOT_IMPLEMENTED, "nested ORC types (struct/list/map/union) are not on the device path yet: column " + c.name);
         }
         out.push_back(std::move(c));
     }
     return out;
+}
+
+void apply_schema_hints(const FileMeta& fm, ReadOptions& opt, const ArrowSchema* schema) {
+    if (!schema) return;
+    opt.ts_hint.clear();
+    const std::vector<OutColumn> cols = project_columns(fm, opt);
+    if (!schema->format || strcmp(schema->format, "+s") != 0) fail(ORCB_INVALID_ARGUMENT, "with_schema: the schema must be a struct");
+    if ((size_t)schema->n_children != cols.size())
+        fail(ORCB_MISMATCHED_SCHEMA, "with_schema: " + std::to_string(schema->n_children) + " fields for " +
+                                         std::to_string(cols.size()) + " projected columns");
+    std::vector<int> hints(cols.size(), -1);
+    for (size_t i = 0; i < cols.size(); i++) {
+        const std::string fmt = schema->children[i]->format ? schema->children[i]->format : "";
+        const OutColumn& c = cols[i];
+        auto mismatch = [&]() {
+            fail(ORCB_MISMATCHED_SCHEMA, "column '" + c.name + "' (ORC type kind " + std::to_string(c.kind) + ") cannot be read as Arrow '" + fmt + "'");
+        };
+        if (c.kind == T_TIMESTAMP || c.kind == T_TIMESTAMP_INSTANT) {
+            if (fmt == "d:38,9") { hints[i] = 4; continue; }
+            static const char units[4] = {'n', 'u', 'm', 's'};
+            int unit = -1;
+            if (fmt.size() >= 4 && fmt[0] == 't' && fmt[1] == 's' && fmt[3] == ':')
+                for (int u = 0; u < 4; u++)
+                    if (fmt[2] == units[u]) unit = u;
+            if (unit < 0) mismatch();
+            const std::string tz = fmt.substr(4);
+            if (c.kind == T_TIMESTAMP) {
+                if (!tz.empty()) mismatch();  // new_timestamp_decoder only takes Timestamp(_, None)
+            } else {
+                if (tz.empty()) mismatch();
+                if (tz != "UTC") fail(ORCB_UNSUPPORTED_TYPE_VARIANT, "Non-UTC Arrow timestamps");  // timestamp.rs:214-217
+            }
+            hints[i] = unit;
+        } else if (fmt != c.format) {
+            mismatch();
+        }
+    }
+    opt.ts_hint = hints;
 }
 
 namespace {
@@ -1004,9 +1054,10 @@ void Job::plan_stripe(uint32_t task_idx) {
                 break;
             }
             case T_TIMESTAMP: case T_TIMESTAMP_INSTANT: {
-                cp.values = alloc(AR_OUT, (uint64_t)n_rows * 8);
+                const uint32_t tw = oc.ts_decimal ? 16 : 8;  // Decimal128(38, 9) on request (with_schema)
+                cp.values = alloc(AR_OUT, (uint64_t)n_rows * tw);
                 uint64_t dst = cp.values;
-                if (has_present) dst = alloc(AR_TMP, (uint64_t)n_rows * 8);
+                if (has_present) dst = alloc(AR_TMP, (uint64_t)n_rows * tw);
                 const uint64_t secs = alloc(AR_TMP, (uint64_t)n_rows * 8);
                 const uint64_t nanos = alloc(AR_TMP, (uint64_t)n_rows * 8);
                 add_int_segs(s_data, secs, true, 8, OUT_I64, 0, true);
@@ -1047,11 +1098,11 @@ void Job::plan_stripe(uint32_t task_idx) {
                 td.nanos = nanos;
                 td.out = dst;
                 td.base = base;
-                td.unit_ns = unit_ns[opt_.timestamp_unit];
+                td.unit_ns = unit_ns[oc.ts_unit];
                 td.n = n_rows;
                 td.cnt_idx = total_idx;
                 td.colstripe = cs;
-                td.as_i128 = 0;
+                td.as_i128 = oc.ts_decimal ? 1 : 0;
                 if (tz_on) {
                     td.tz_on = 1;
                     td.tz_at = tzt[0];   // offsets inside the zone-table blob until stage()
@@ -1060,8 +1111,8 @@ void Job::plan_stripe(uint32_t task_idx) {
                     td.tz_first = (int32_t)(uint32_t)(tzt[3] >> 32);
                 }
                 ts_.push_back(td);
-                ab_ts_ += (uint64_t)n_rows * 24;
-                if (has_present) add_spaced(dst, cp.values, 8, true);
+                ab_ts_ += (uint64_t)n_rows * (16 + tw);
+                if (has_present) add_spaced(dst, cp.values, tw, true);
                 break;
             }
             default: fail(ORCB_NOT_IMPLEMENTED, "unsupported column type on the device path");

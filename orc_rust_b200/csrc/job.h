@@ -27,6 +27,9 @@ struct ReadOptions {
     cudaStream_t stream = nullptr;
     bool own_stream = true;
     uint32_t shard_index = 0, shard_count = 1;
+    // with_schema (src/arrow_reader.rs:80-83): per projected column, in output order; -1 = the default mapping,
+    // 0..3 = timestamp unit ns/us/ms/s, 4 = Decimal128(38, 9) nanoseconds (array_decoder/timestamp.rs:150-190)
+    std::vector<int> ts_hint;
     static ReadOptions from_c(const OrcbReadOptions* o);
 };
 
@@ -38,10 +41,15 @@ struct OutColumn {
     uint32_t precision = 0, scale = 0;
     std::string format;  // Arrow C format string
     uint32_t width = 0;  // bytes per value (0 for bool / strings)
+    int ts_unit = 0;     // timestamps: 0 ns, 1 us, 2 ms, 3 s
+    bool ts_decimal = false;  // timestamps read as Decimal128(38, 9)
 };
 
 std::vector<OutColumn> project_columns(const FileMeta& fm, const ReadOptions& opt);
 void export_schema(const FileMeta& fm, const std::vector<OutColumn>& cols, ArrowSchema* out);
+// with_schema: checks the caller's Arrow schema against the file (array_decoder_factory, src/array_decoder/mod.rs:390-511)
+// and records the timestamp variants it asks for in opt.ts_hint
+void apply_schema_hints(const FileMeta& fm, ReadOptions& opt, const ArrowSchema* schema);
 
 struct StripeTask {
     const FileMeta* file;

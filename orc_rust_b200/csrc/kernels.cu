@@ -1722,7 +1722,24 @@ __global__ void __launch_bounds__(256) k_timestamp(const TsDesc* __restrict__ de
         if (sec < 0 && ns > 999999ull) sec -= 1;
         const __int128 t = (__int128)sec * 1000000000 + (__int128)ns;
         if (d.as_i128) {
-            ((__int128*)d.out)[i] = t;
+            // Decimal128(38, 9): nanoseconds, no range check (timestamp.rs:194-197); writer zone as below (:316-333)
+            __int128 w = t;
+            if (d.tz_on) {
+                const __int128 ns = 1000000000;
+                __int128 q = t / ns;
+                if (t % ns < 0) q -= 1;  // div_euclid
+                const int64_t inst = (int64_t)q;
+                const int64_t* at = (const int64_t*)d.tz_at;
+                uint32_t lo = 0, hi = d.tz_n;
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (at[mid] <= inst) lo = mid + 1;
+                    else hi = mid;
+                }
+                const int64_t off = lo == 0 ? (int64_t)d.tz_first : (int64_t)((const int32_t*)d.tz_off)[lo - 1];
+                w = t + (__int128)off * ns;
+            }
+            ((__int128*)d.out)[i] = w;
         } else {
             const __int128 u = (__int128)d.unit_ns;
             const __int128 q = t / u;

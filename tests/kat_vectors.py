@@ -115,3 +115,23 @@ ROW_SELECTION = [
     ("with_projection :198-234", "test.orc", [(True, 1), (False, 2), (True, 2)], ["a", "b"], [1, 2]),
     ("large_file :306-328", "string_long_long.orc", [(True, 1000), (False, 500), (True, 8500)], None, list(range(1000, 1500))),
 ]
+
+
+# ---- with_schema on timestamps (tests/basic/main.rs:594-770): file, {column: unit}, batch size, expected leading values ----
+import datetime as _dt
+from decimal import Decimal as _D
+TS_SCHEMA = [
+    ("second_timestamps_test :594-632", "ref_basic/overflowing_timestamps.orc", {"timestamp": "s"}, 8192, "timestamp",
+     [_dt.datetime(1970, 5, 23, 21, 21, 18), _dt.datetime(1, 1, 1), _dt.datetime(1970, 5, 23, 21, 21, 18)]),
+    ("millisecond_timestamps_test", "ref_basic/overflowing_timestamps.orc", {"timestamp": "ms"}, 8192, "timestamp",
+     [_dt.datetime(1970, 5, 23, 21, 21, 18), _dt.datetime(1, 1, 1), _dt.datetime(1970, 5, 23, 21, 21, 18)]),
+    ("microsecond_timestamps_test", "ref_basic/overflowing_timestamps.orc", {"timestamp": "us"}, 8192, "timestamp",
+     [_dt.datetime(1970, 5, 23, 21, 21, 18), _dt.datetime(1, 1, 1), _dt.datetime(1970, 5, 23, 21, 21, 18)]),
+    ("decimal128_timestamps_test :634-661", "ref_basic/overflowing_timestamps.orc", {"timestamp": "dec"}, 8192, "timestamp",
+     [_D("12345678.000000000"), _D("-62135596800.000000000"), _D("12345678.000000000")]),
+    ("decimal128_timestamps_1900_test :715-745 (US/Pacific writer)", "ref_integration/TestOrcFile.testDate1900.orc",
+     {"time": "dec"}, 11, "time",
+     [_D("-2198229903.900000000"), _D("-2198229903.899900000"), _D("-2198229903.899800000"), _D("-2198229903.899700000"),
+      _D("-2198229903.899600000"), _D("-2198229903.899500000"), _D("-2198229903.899400000"), _D("-2198229903.899300000"),
+      _D("-2198229903.899200000"), _D("-2198229903.899100000"), _D("-2198229903.899000000")]),
+]

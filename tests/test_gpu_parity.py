@@ -381,6 +381,41 @@ def test_builder_options(ob, tmp_path):
         for unit, prec in (("ns", ob.TimestampPrecision.Nanosecond), ("us", ob.TimestampPrecision.Microsecond)):
             got = list(ob.ArrowReaderBuilder.try_new(zdata).with_timestamp_precision(prec).build())
             assert_batches_identical(got, zof.read(ts_unit=unit), f"{zone}/{unit}")
+    # with_schema: every unit and Decimal128(38, 9) per column, with a writer zone (array_decoder/timestamp.rs:150-232)
+    zdata = z0.replace(b"GMT", b"CET")
+    zof = oo.OracleFile(zdata)
+    for unit, typ in (("s", None), ("ms", pa.timestamp("ms")), ("us", pa.timestamp("us")), ("dec", pa.decimal128(38, 9))):
+        if unit == "s":
+            continue  # the generated values carry milliseconds: DecodeTimestamp, checked below
+        schema = pa.schema([pa.field("when", typ), pa.field("k", pa.int64())])
+        got = list(ob.ArrowReaderBuilder.try_new(zdata).with_schema(schema).build())
+        exp = zof.read(ts_unit={"t": unit})
+        assert got[0].schema.names == ["when", "k"]          # the batches carry the caller's schema
+        for g, e in zip(got, exp):
+            assert g.num_rows == e.num_rows
+            for c in range(2):
+                assert g.column(c).equals(e.column(c)), f"with_schema {unit}"
+                assert g.column(c).buffers()[1].to_pybytes()[: g.num_rows * 8] == e.column(c).buffers()[1].to_pybytes()[: e.num_rows * 8]
+    with pytest.raises(ob.OrcError) as ei:
+        list(ob.ArrowReaderBuilder.try_new(zdata).with_schema(pa.schema([("t", pa.timestamp("s")), ("k", pa.int64())])).build())
+    assert ei.value.variant == "DecodeTimestamp"
+    for bad, variant in ((pa.schema([("t", pa.timestamp("ns", tz="UTC")), ("k", pa.int64())]), "MismatchedSchema"),
+                         (pa.schema([("t", pa.timestamp("ns")), ("k", pa.int32())]), "MismatchedSchema"),
+                         (pa.schema([("t", pa.decimal128(38, 8)), ("k", pa.int64())]), "MismatchedSchema"),
+                         (pa.schema([("t", pa.timestamp("ns"))]), "MismatchedSchema")):
+        with pytest.raises(ob.OrcError) as ei:
+            ob.ArrowReaderBuilder.try_new(zdata).with_schema(bad).build()
+        assert ei.value.variant == variant, bad
+    pdata = open(os.path.join(GOLDEN, "ref_basic", "pyarrow_timestamps.orc"), "rb").read()   # TIMESTAMP + TIMESTAMP_INSTANT
+    pof = oo.OracleFile(pdata)
+    schema = pa.schema([("timestamp_notz", pa.decimal128(38, 9)), ("timestamp_utc", pa.timestamp("us", tz="UTC"))])
+    got = list(ob.ArrowReaderBuilder.try_new(pdata).with_schema(schema).build())
+    exp = pof.read(ts_unit={"timestamp_notz": "dec", "timestamp_utc": "us"})
+    assert_batches_identical(got, exp, "pyarrow_timestamps with_schema")
+    with pytest.raises(ob.OrcError) as ei:
+        ob.ArrowReaderBuilder.try_new(pdata).with_schema(pa.schema([("timestamp_notz", pa.timestamp("ns")),
+                                                                   ("timestamp_utc", pa.timestamp("ns", tz="Europe/Paris"))])).build()
+    assert ei.value.variant == "UnsupportedTypeVariant"
     # and the zone really moved the values
     a = list(ob.ArrowReaderBuilder.try_new(z0.replace(b"GMT", b"CET")).build())[0].column(0)
     b = list(ob.ArrowReaderBuilder.try_new(z0).build())[0].column(0)

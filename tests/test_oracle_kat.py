@@ -89,3 +89,16 @@ def test_i16_i32_range_checks():
     # SHORT_REPEAT width 3 bytes into i16 (short_repeat.rs:44-51)
     with pytest.raises(oo.OracleError):
         oo.rle_v2(bytes([(2 << 3) | 0, 0, 0, 1]), 3, True, 2)
+
+
+def test_with_schema_timestamp_goldens():
+    """The reference's with_schema tests (tests/basic/main.rs:594-770): other units and Decimal128(38, 9), with and
+    without a writer time zone."""
+    import os
+    from conftest import GOLDEN
+    from oracle import orc_oracle as oo
+    import kat_vectors as kv
+    for name, rel, units, bs, col, expected in kv.TS_SCHEMA:
+        of = oo.OracleFile(open(os.path.join(GOLDEN, rel), "rb").read())
+        batch = of.read(batch_size=bs, ts_unit=units, stripes=[0])[0]
+        assert batch.column(batch.schema.get_field_index(col)).to_pylist()[: len(expected)] == expected, name
