@@ -408,6 +408,10 @@ class ArrowReaderBuilder:
     def build(self) -> "ArrowReader":
         return ArrowReader(self)
 
+    def build_async(self) -> "ArrowStreamReader":
+        """`ArrowReaderBuilder::build_async` (src/async_arrow_reader.rs:292-321)."""
+        return ArrowStreamReader(ArrowReader(self))
+
 
 class ArrowReader:
     """Mirror of `ArrowReader` (src/arrow_reader.rs:233-347): an iterator of RecordBatches."""
@@ -469,6 +473,35 @@ class ArrowReader:
         import pyarrow as pa
         batches = list(self)
         return pa.Table.from_batches(batches, schema=self._schema)
+
+
+class ArrowStreamReader:
+    """Mirror of `ArrowStreamReader` (src/async_arrow_reader.rs:283-290): an async stream of RecordBatches.  Each
+    batch is produced by the blocking reader on a worker thread, so the event loop stays free while the GPU works;
+    after an error the stream stays in the error state, like `StreamState::Error` (:262-277)."""
+
+    def __init__(self, reader: "ArrowReader"):
+        self._reader = reader
+
+    def schema(self):
+        return self._reader.schema()
+
+    def __aiter__(self):
+        return self
+
+    async def __anext__(self):
+        import asyncio
+
+        def step():
+            try:
+                return next(self._reader)
+            except StopIteration:
+                return None
+
+        batch = await asyncio.to_thread(step)
+        if batch is None:
+            raise StopAsyncIteration
+        return batch
 
 
 class DecodeJob:

@@ -337,6 +337,13 @@ def test_builder_options(ob, tmp_path):
     exp = of.read(batch_size=5000, columns=cols)
     assert got[0].schema.names == exp[0].schema.names
     assert_batches_identical(got, exp, "projection")
+    # build_async: the same batches as an async stream (src/async_arrow_reader.rs:283-321)
+    import asyncio
+
+    async def drain():
+        return [b async for b in ob.ArrowReaderBuilder.try_new(data).with_projection(cols).with_batch_size(5000).build_async()]
+
+    assert_batches_identical(asyncio.run(drain()), exp, "async stream")
     # a projection that matches nothing: batches that only carry their row count (array_decoder/mod.rs:538-549)
     empty = list(ob.ArrowReaderBuilder.try_new(data).with_projection(["no_such_column"]).with_batch_size(50_000).build())
     assert [b.num_columns for b in empty] == [0] * len(empty)
