@@ -161,6 +161,9 @@ int orcb_reader_new_ex(OrcbFile* f, const OrcbReadOptions* opt, const OrcbRowSel
  * (src/arrow_reader.rs:296-309).  *n_triples is the number of triples (also when it exceeds cap_triples). */
 int orcb_selection_plan(const OrcbRowSelector* selectors, uint32_t n_selectors, const uint64_t* stripe_rows, uint32_t n_stripes,
                         uint64_t batch_size, int32_t* applies, uint64_t* triples, size_t cap_triples, size_t* n_triples);
+/* Work done so far: out[0] = (stream, row-group) segments planned, out[1] = stripe tasks staged.  With a selection only
+ * the row groups that hold selected rows are decoded, so both shrink with it. */
+int orcb_reader_counters(const OrcbReader* r, uint64_t out[2]);
 void orcb_reader_free(OrcbReader* r);
 /* ArrowReader::total_row_count (src/arrow_reader.rs:243-247) */
 uint64_t orcb_reader_total_row_count(const OrcbReader* r);

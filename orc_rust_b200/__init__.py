@@ -104,7 +104,7 @@ EXPORTED_SYMBOLS = [
     "orcb_open_memory", "orcb_open_path", "orcb_file_free", "orcb_file_num_rows", "orcb_file_num_stripes",
     "orcb_file_compression", "orcb_file_compression_block_size", "orcb_file_row_index_stride",
     "orcb_file_num_root_columns", "orcb_file_root_column_name", "orcb_file_stripe_info", "orcb_schema",
-    "orcb_reader_new", "orcb_reader_new_with_selection", "orcb_reader_new_ex", "orcb_selection_plan", "orcb_reader_free", "orcb_reader_total_row_count", "orcb_reader_next",
+    "orcb_reader_new", "orcb_reader_new_with_selection", "orcb_reader_new_ex", "orcb_reader_counters", "orcb_selection_plan", "orcb_reader_free", "orcb_reader_total_row_count", "orcb_reader_next",
     "orcb_reader_next_device", "orcb_job_new", "orcb_job_free", "orcb_job_plan", "orcb_job_stage",
     "orcb_job_launch", "orcb_job_finish", "orcb_job_stats", "orcb_job_restage", "orcb_job_kernel_stats", "orcb_job_num_batches", "orcb_job_export_batch",
     "orcb_job_export_batch_device", "orcb_decode_int_rle", "orcb_decode_byte_rle", "orcb_decode_bool_rle",
@@ -456,6 +456,12 @@ class ArrowReader:
 
     def total_row_count(self) -> int:
         return lib().orcb_reader_total_row_count(self._h)
+
+    def counters(self) -> dict:
+        """Segments planned / stripe tasks staged so far (shrinks with a row selection: partial decode)."""
+        out = (ctypes.c_uint64 * 2)()
+        _check(lib().orcb_reader_counters(self._h, out))
+        return {"segments": int(out[0]), "stripe_tasks": int(out[1])}
 
     def __iter__(self) -> Iterator:
         return self

@@ -35,6 +35,7 @@ struct OrcbReader {
     std::unique_ptr<Job> job;
     uint64_t next_batch = 0;
     bool failed = false;
+    uint64_t segments_planned = 0, stripes_staged = 0;  // summed over the jobs run so far (orcb_reader_counters)
     // with_row_selection: per entry of `stripes`, whether a selection applies and the row ranges it yields
     bool has_selection = false;
     std::vector<std::pair<bool, std::vector<std::pair<uint32_t, uint32_t>>>> views;
@@ -236,6 +237,14 @@ int orcb_selection_plan(const OrcbRowSelector* selectors, uint32_t n_selectors, 
     });
 }
 
+int orcb_reader_counters(const OrcbReader* r, uint64_t out[2]) {
+    return guarded([&] {
+        if (!r || !out) fail(ORCB_INVALID_ARGUMENT, "NULL argument");
+        out[0] = r->segments_planned;
+        out[1] = r->stripes_staged;
+    });
+}
+
 void orcb_reader_free(OrcbReader* r) { delete r; }
 
 uint64_t orcb_reader_total_row_count(const OrcbReader* r) { return r->file->meta.num_rows; }
@@ -253,12 +262,35 @@ static bool reader_advance(OrcbReader* r) {
             if (!tasks.empty() && bytes + si.data_length > (1ull << 30)) break;  // bound one launch plan to ~1 GiB in
             StripeTask task{&r->file->meta, r->stripes[r->next_stripe]};
             if (r->has_selection && r->views[r->next_stripe].first) {
-                task.has_views = true;
-                task.views = r->views[r->next_stripe].second;
-                if (task.views.empty()) {  // nothing selected in this stripe: not even staged
+                const auto& views = r->views[r->next_stripe].second;
+                if (views.empty()) {  // nothing selected in this stripe: not even staged
                     r->next_stripe++;
                     continue;
                 }
+                task.has_views = true;
+                const uint64_t stride = r->file->meta.row_index_stride > 0 ? (uint64_t)r->file->meta.row_index_stride : 0;
+                if (r->opt.use_row_index && stride && si.rows > stride) {
+                    // partial decode: one task per run of consecutive row groups the selected ranges touch
+                    bytes += si.data_length;
+                    for (size_t i = 0; i < views.size();) {
+                        uint64_t g0 = views[i].first / stride, g1 = ((uint64_t)views[i].first + views[i].second - 1) / stride + 1;
+                        size_t j = i + 1;
+                        while (j < views.size() && views[j].first / stride <= g1) {
+                            g1 = std::max<uint64_t>(g1, ((uint64_t)views[j].first + views[j].second - 1) / stride + 1);
+                            j++;
+                        }
+                        StripeTask w = task;
+                        w.has_window = true;
+                        w.g_begin = (uint32_t)g0;
+                        w.g_end = (uint32_t)g1;
+                        w.views.assign(views.begin() + i, views.begin() + j);
+                        tasks.push_back(std::move(w));
+                        i = j;
+                    }
+                    r->next_stripe++;
+                    continue;
+                }
+                task.views = views;
             }
             bytes += si.data_length;
             tasks.push_back(std::move(task));
@@ -268,6 +300,12 @@ static bool reader_advance(OrcbReader* r) {
         r->job = std::make_unique<Job>(std::move(tasks), r->opt);
         r->next_batch = 0;
         r->job->plan();
+        {
+            OrcbJobStats st{};
+            r->job->stats(&st);
+            r->segments_planned += st.n_segments;
+            r->stripes_staged += st.n_stripes;
+        }
         r->job->stage();
         r->job->launch();
         r->job->finish();

@@ -350,6 +350,7 @@ void Job::plan() {
     if (planned_) return;
     if (opt_.batch_size == 0) fail(ORCB_INVALID_ARGUMENT, "batch_size must be > 0");
     task_first_cs_.clear();
+    staged_stripes_.clear();
     for (auto& t : tasks_) view_mode_ |= t.has_views;
     user_batch_size_ = opt_.batch_size;
     if (view_mode_) {
@@ -468,30 +469,42 @@ void Job::plan_stripe(uint32_t task_idx) {
     const StripeFooter sf = fm.read_stripe_footer(stripe);
     task_first_cs_.push_back((uint32_t)colstripes_.size());
     if (si.rows > 0xfffffff0ull) fail(ORCB_NOT_IMPLEMENTED, "stripes with more than 2^32 rows");
-    const uint32_t n_rows = (uint32_t)si.rows;
-    n_rows_ += n_rows;
+    const uint32_t stripe_rows = (uint32_t)si.rows;
+    n_rows_ += stripe_rows;
     const uint32_t bs = opt_.batch_size;
-    const uint32_t n_batches = (n_rows + bs - 1) / bs;
     const bool compressed = fm.compression != C_NONE;
     const uint64_t data_start = si.offset + si.index_length;
 
-    // stage the stripe's data area once
+    // stage the stripe's data area once (tasks that decode different row-group windows of one stripe share it)
     uint64_t in_off = 0;
     if (si.data_length) {
-        in_off = alloc(AR_IN, si.data_length);
-        stage_copies_.push_back({fm.data + data_start, in_off & ((1ull << 60) - 1), si.data_length});
+        auto key = std::make_pair((const void*)&fm, stripe);
+        auto it = staged_stripes_.find(key);
+        if (it != staged_stripes_.end()) {
+            in_off = it->second;
+        } else {
+            in_off = alloc(AR_IN, si.data_length);
+            stage_copies_.push_back({fm.data + data_start, in_off & ((1ull << 60) - 1), si.data_length});
+            staged_stripes_[key] = in_off;
+        }
     }
 
     // row-index stride usable for this stripe?
-    uint32_t stride = n_rows ? n_rows : 1;
-    bool want_index = opt_.use_row_index && fm.row_index_stride > 0 && n_rows > 0;
+    uint32_t stride = stripe_rows ? stripe_rows : 1;
+    bool want_index = opt_.use_row_index && fm.row_index_stride > 0 && stripe_rows > 0;
     if (want_index) stride = (uint32_t)std::min<uint64_t>((uint64_t)fm.row_index_stride, 0xffffffffull);
-    const uint32_t idx_groups = n_rows ? (n_rows + stride - 1) / stride : 0;
+    const uint32_t idx_groups = stripe_rows ? (stripe_rows + stride - 1) / stride : 0;
+    // partial decode (row selection): row groups [wg0, wg1) only
+    const StripeTask& task = tasks_[task_idx];
+    const bool windowed = task.has_window && want_index && idx_groups > 1 && task.g_begin < task.g_end && task.g_end <= idx_groups;
+    const uint32_t wg0 = windowed ? task.g_begin : 0, wg1 = windowed ? task.g_end : idx_groups;
 
     for (uint32_t ci = 0; ci < cols_.size(); ci++) {
         const OutColumn& oc = cols_[ci];
         const uint32_t cid = oc.col_id;
         const uint32_t cs = (uint32_t)colstripes_.size();
+        uint32_t n_rows = stripe_rows;  // rows this column decodes: the stripe's, or the window's once the index is known good
+        uint32_t n_batches = (n_rows + bs - 1) / bs;
         ColStripePlan cp;
         cp.task = task_idx;
         cp.col = ci;
@@ -655,6 +668,26 @@ void Job::plan_stripe(uint32_t task_idx) {
         if (!indexed) {
             for (size_t sidx = 0; sidx < specs.size(); sidx++) entries[sidx].assign(1, Entry{});
         }
+        // where each positioned stream stops being needed (raw-copied streams are cut there)
+        std::vector<uint32_t> win_end(specs.size());
+        for (size_t sidx = 0; sidx < specs.size(); sidx++) win_end[sidx] = specs[sidx].sr->len;
+        if (windowed && indexed) {
+            for (size_t sidx = 0; sidx < specs.size(); sidx++) {
+                if (wg1 < idx_groups) win_end[sidx] = entries[sidx][wg1].byte;
+                entries[sidx] = std::vector<Entry>(entries[sidx].begin() + wg0, entries[sidx].begin() + wg1);
+            }
+            cp.row_base = wg0 * stride;
+            n_rows = std::min<uint64_t>(stripe_rows, (uint64_t)wg1 * stride) - cp.row_base;
+            n_groups = wg1 - wg0;
+            n_batches = (n_rows + bs - 1) / bs;
+            cp.n_rows = n_rows;
+            cp.n_batches = n_batches;
+        }
+        auto win_end_of = [&](StreamRef* sr) -> uint32_t {
+            for (size_t sidx = 0; sidx < specs.size(); sidx++)
+                if (specs[sidx].sr == sr) return win_end[sidx];
+            return sr->len;
+        };
         auto spec_of = [&](StreamRef* sr) -> const std::vector<Entry>& {
             for (size_t sidx = 0; sidx < specs.size(); sidx++)
                 if (specs[sidx].sr == sr) return entries[sidx];
@@ -917,17 +950,20 @@ void Job::plan_stripe(uint32_t task_idx) {
             }
             case T_FLOAT: case T_DOUBLE: {
                 cp.values = alloc(AR_OUT, (uint64_t)n_rows * w);
+                // the window's values start at the first group's recorded byte
+                const uint32_t f0 = std::min(spec_of(&s_data)[0].byte, s_data.len);
                 if (has_present) {
                     const uint64_t dense = alloc(AR_TMP, (uint64_t)n_rows * w);
-                    add_copy(s_data.ptr, s_data.len, dense, 0, total_idx, w, (uint64_t)n_rows * w);
+                    add_copy(s_data.ptr + f0, s_data.len - f0, dense, 0, total_idx, w, (uint64_t)n_rows * w);
                     add_spaced(dense, cp.values, w, false);
                 } else {
-                    add_copy(s_data.ptr, s_data.len, cp.values, (uint64_t)n_rows * w, -1, w, (uint64_t)n_rows * w);
+                    add_copy(s_data.ptr + f0, s_data.len - f0, cp.values, (uint64_t)n_rows * w, -1, w, (uint64_t)n_rows * w);
                 }
                 n_segments_ += 1;
                 break;
             }
             case T_STRING: case T_VARCHAR: case T_CHAR: case T_BINARY: {
+                uint32_t str_d0 = 0, str_dn = 0;  // direct strings: first byte / number of bytes of DATA the decoded rows use
                 StrCol sc{};
                 sc.n_rows = n_rows;
                 sc.batch_size = bs;
@@ -983,11 +1019,14 @@ void Job::plan_stripe(uint32_t task_idx) {
                 } else {
                     sc.mode = 0;
                     add_int_segs(s_length, dense_i32, false, 8, OUT_LEN31, ORCB_OFFSET_OVERFLOW, true);
-                    cp.str_data = alloc(AR_OUT, (uint64_t)s_data.len + 16);
+                    // the bytes of the decoded rows: the whole DATA stream, or its part between the window's positions
+                    str_d0 = std::min(spec_of(&s_data)[0].byte, s_data.len);
+                    str_dn = std::max(std::min(win_end_of(&s_data), s_data.len), str_d0) - str_d0;
+                    cp.str_data = alloc(AR_OUT, (uint64_t)str_dn + 16);
                     sc.data = cp.str_data;
-                    sc.data_len = s_data.len;
-                    if (s_data.len) {
-                        add_copy(s_data.ptr, s_data.len, cp.str_data, s_data.len, -1, 1, s_data.len);
+                    sc.data_len = str_dn;
+                    if (str_dn) {
+                        add_copy(s_data.ptr + str_d0, str_dn, cp.str_data, str_dn, -1, 1, str_dn);
                         if (k != T_BINARY) copies_.back().u8_col = (int32_t)strcols_.size();  // validated on the way through
                     }
                     n_segments_ += 1;
@@ -998,16 +1037,17 @@ void Job::plan_stripe(uint32_t task_idx) {
                 if (k != T_BINARY) {
                     // Utf8 arrays are validated (string.rs:150-151): direct = the DATA stream, dictionary = its bytes
                     const StreamRef& u8 = use_dict ? s_dict : s_data;
-                    if (u8.present && u8.len) {
-                        sc.u8_src = u8.ptr;
-                        sc.u8_len = u8.len;
+                    const uint32_t u8_off = use_dict ? 0 : str_d0, u8_n = use_dict ? u8.len : str_dn;  // direct: the window's bytes
+                    if (u8.present && u8_n) {
+                        sc.u8_src = u8.ptr + u8_off;
+                        sc.u8_len = u8_n;
                         sc.u8_bad = alloc(AR_ZERO, 16);
-                        const uint32_t nt = (uint32_t)(((uint64_t)u8.len + 15) / U8_TILE + 1);  // tiles are cut at aligned addresses
+                        const uint32_t nt = (uint32_t)(((uint64_t)u8_n + 15) / U8_TILE + 1);  // tiles are cut at aligned addresses
                         sc.u8_flags = alloc(AR_ZERO, ((uint64_t)nt + 32) / 32 * 4 + 16);
                         if (use_dict) {
                             // dictionary bytes get their own pass; direct DATA is checked by the copy kernel
                             for (uint32_t t = 0; t < nt; t++) u8_tiles_.push_back(make_uint2((uint32_t)strcols_.size(), t));
-                            ab_utf8_ += u8.len;
+                            ab_utf8_ += u8_n;
                         }
                     }
                 }
@@ -1460,7 +1500,7 @@ void Job::export_batch(uint64_t i, ArrowArray* out) {
     const uint32_t cs0 = task_first_cs_[t];
     // (the stripe's row count also sizes the batches of an empty projection, mod.rs:538-549)
     const uint32_t rows = batch_rows_[i];
-    const int64_t voff = view_mode_ ? (int64_t)batch_row0_[i] : 0;  // view into the stripe-wide internal batch
+    const int64_t vrow0 = view_mode_ ? (int64_t)batch_row0_[i] : 0;  // view into the stripe-wide internal batch
     build_batch(this, out, rows, cols_.size());
     auto* tp = (ArrayPriv*)out->private_data;
     tp->keep1 = host_out_;
@@ -1470,6 +1510,7 @@ void Job::export_batch(uint64_t i, ArrowArray* out) {
         const OutColumn& oc = cols_[c];
         ArrowArray* a = &tp->child_store[c];
         const bool is_str = cp.str_slot >= 0;
+        const int64_t voff = view_mode_ ? vrow0 - (int64_t)cp.row_base : 0;  // the column may hold a row-group window only
         int64_t nc = 0;
         const void* vbuf = nullptr;
         if (cp.has_present) {
@@ -1517,7 +1558,7 @@ void Job::export_batch_device(uint64_t i, ArrowDeviceArray* out) {
     const uint64_t* ptrs = (const uint64_t*)(h_meta_ + o_ptrs_);
     const uint32_t cs0 = task_first_cs_[t];
     const uint32_t rows = batch_rows_[i];
-    const int64_t voff = view_mode_ ? (int64_t)batch_row0_[i] : 0;
+    const int64_t vrow0 = view_mode_ ? (int64_t)batch_row0_[i] : 0;
     memset(out, 0, sizeof(*out));
     build_batch(this, &out->array, rows, cols_.size());
     out->device_id = opt_.device;
@@ -1531,6 +1572,7 @@ void Job::export_batch_device(uint64_t i, ArrowDeviceArray* out) {
         const OutColumn& oc = cols_[c];
         ArrowArray* a = &tp->child_store[c];
         const bool is_str = cp.str_slot >= 0;
+        const int64_t voff = view_mode_ ? vrow0 - (int64_t)cp.row_base : 0;
         int64_t nc = 0;
         const void* vbuf = nullptr;
         if (cp.has_present) {

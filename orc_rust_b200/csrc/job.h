@@ -57,7 +57,11 @@ struct StripeTask {
     // row selection (src/array_decoder/mod.rs:313-364): the batches of this stripe are these row ranges, in order,
     // instead of consecutive batch_size slices.  The stripe is decoded once; the ranges are exported as views.
     bool has_views = false;
-    std::vector<std::pair<uint32_t, uint32_t>> views;  // (first row, rows)
+    std::vector<std::pair<uint32_t, uint32_t>> views;  // (first row, rows), rows counted from the start of the stripe
+    // partial decode: only row groups [g_begin, g_end) of the stripe are decoded (the views lie inside them).  Needs
+    // the row index; a column whose index entries are unusable is decoded whole instead.
+    bool has_window = false;
+    uint32_t g_begin = 0, g_end = 0;
 };
 
 // RowSelector (src/row_selection.rs:32-57)
@@ -73,6 +77,7 @@ std::vector<std::pair<bool, std::vector<std::pair<uint32_t, uint32_t>>>> selecti
 
 // where one column of one stripe lands
 struct ColStripePlan {
+    uint32_t row_base = 0;   // stripe row that row 0 of this column's buffers holds (> 0: windowed partial decode)
     uint32_t task = 0, col = 0;       // indices into tasks / out columns
     uint32_t n_rows = 0, n_batches = 0;
     bool has_present = false;
@@ -128,6 +133,7 @@ class Job {
     std::vector<uint2> copy_tiles_;
     std::vector<uint8_t> tz_blob_;                  // zone tables: i64 instants then i32 offsets, 16-byte aligned pieces
     std::map<std::string, std::array<uint64_t, 4>> tz_tables_;  // zone -> {offset of instants, offset of offsets, n, first}
+    std::map<std::pair<const void*, uint32_t>, uint64_t> staged_stripes_;  // (file, stripe) -> offset of its data in the IN arena
     std::vector<uint2> u8_tiles_;   // (string column, U8_TILE-byte tile) units of the UTF-8 check
     std::vector<SpacedDesc> spaced_, spaced_late_;
     std::vector<DecFixDesc> decfix_;
