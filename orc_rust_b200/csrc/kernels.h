@@ -1,4 +1,4 @@
-// Launch wrappers implemented in kernels.cu (each returns 0 or a cudaError_t value).
+// Launch wrappers implemented in the k_*.cu translation units (each returns 0 or a cudaError_t value).
 #pragma once
 #include <cuda_runtime.h>
 
