@@ -1,4 +1,4 @@
-// POD descriptor tables shared by the host planner (job.cc) and the CUDA kernels (k_*.cu).
+// POD descriptor tables shared by the host planner (plan.cc) and the CUDA kernels (k_*.cu).
 // One decode job = flat arrays of these, uploaded once; every kernel indexes them by warp.
 //
 // Pointer-typed fields (uint64_t) hold an arena-tagged offset while planning on the host

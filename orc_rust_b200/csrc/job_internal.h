@@ -1,0 +1,42 @@
+// Shared by the translation units that implement Job (job.cc, plan.cc, export.cc, schema.cc).
+#pragma once
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "job.h"
+#include "kernels.h"
+
+namespace orcb {
+
+#define CUDA_OK(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) fail(ORCB_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+static const int64_t ORC_EPOCH_UTC = 1420070400;  // array_decoder/timestamp.rs:51
+static const uint64_t ARENA_PAD = 256;            // slack so word-granular kernel loads may overrun streams
+
+// ------------------------------------------------------------------------------------------------
+// device memory owned jointly by the job and by exported device batches
+// ------------------------------------------------------------------------------------------------
+struct DeviceArenas {
+    int device = 0;
+    std::vector<void*> ptrs;
+    ~DeviceArenas() {
+        for (void* p : ptrs)
+            if (p) cudaFree(p);
+    }
+};
+
+struct HostOutput {
+    uint8_t* out = nullptr;   // pinned copy of AR_OUT
+    uint8_t* heap = nullptr;  // pinned copy of the used part of AR_HEAP
+    ~HostOutput() {
+        if (out) cudaFreeHost(out);
+        if (heap) cudaFreeHost(heap);
+    }
+};
+
+}  // namespace orcb
