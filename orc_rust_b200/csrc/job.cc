@@ -245,13 +245,15 @@ void Job::launch() {
     const char* order = order_env ? order_env : "kcv";
     for (const char* o = order; *o; o++) {
         if (*o == 'c' && N(int_big_segs_))
-            run("k_int_rle_coop", ab_intbig_, N(int_big_segs_), 1, [&] { return launch_int_rle_coop((Seg*)(d_desc_ + o_intbig_), N(int_big_segs_), cnt, dstart, err, mis, st); });
+            run("k_int_rle_coop", ab_intbig_, N(int_big_segs_), 1, [&] { return launch_int_rle_coop((Seg*)(d_desc_ + o_intbig_), N(int_big_segs_), cnt, dstart, err, mis, 0, st); });
         if (*o == 'v' && N(var_segs_))
             run("k_varint128", ab_var_, N(var_segs_), 1, [&] { return launch_varint128((Seg*)(d_desc_ + o_var_), N(var_segs_), cnt, dstart, err, st); });
         if (*o == 'k' && N(copy_tiles_))
             run("k_copy", ab_copy_, N(copy_tiles_), 1, [&] { return launch_copy((CopyDesc*)(d_desc_ + o_copy_), (uint2*)(d_desc_ + o_ctile_), N(copy_tiles_), cnt, err, (StrCol*)(d_desc_ + o_str_), st); });
     }
     if (forked && !serial_env) CUDA_OK(cudaStreamWaitEvent(st, ev_join_, 0));
+    if (N(decfix_) && N(int_big_segs_))  // scales that were only compared so far are written where one of them differed
+        run("k_int_rle_coop(scales)", 0, N(int_big_segs_), 1, [&] { return launch_int_rle_coop((Seg*)(d_desc_ + o_intbig_), N(int_big_segs_), cnt, dstart, err, mis, 1, st); });
     if (N(decfix_))
         run("k_decimal_fix", ab_dec_, N(decfix_), 1, [&] { return launch_decimal_fix((DecFixDesc*)(d_desc_ + o_dec_), N(decfix_), cnt, mis, st); });
     if (N(ts_))

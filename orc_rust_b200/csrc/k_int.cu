@@ -114,8 +114,15 @@ __device__ uint32_t coop_run2(const SegCtx& c, uint32_t cur, uint32_t skip, uint
             take = min(rl > skip ? rl - skip : 0u, room);
             const uint32_t i_end = min(rl, skip + take);
             const uint64_t ustep = (uint64_t)(int64_t)step;
-            for (uint32_t i = skip + lane; i < i_end; i += 32)
-                store_val(c, out_pos + (i - skip), (int64_t)((uint64_t)base + (uint64_t)i * ustep));
+            if (c.scale_lazy && s.out_kind == OUT_SCALE) {
+                // the whole run is the type's scale: nothing to write (k_decimal_fix will not look); otherwise raise
+                // the flag, the second pass writes every value of the column-stripe
+                const uint64_t first = (uint64_t)base + (uint64_t)skip * ustep;
+                if (take && ((uint32_t)first != s.aux || (take > 1 && ustep != 0)) && lane == 0) atomicOr(&c.mis[s.colstripe], 1u);
+            } else {
+                for (uint32_t i = skip + lane; i < i_end; i += 32)
+                    store_val(c, out_pos + (i - skip), (int64_t)((uint64_t)base + (uint64_t)i * ustep));
+            }
         } else {
             if (rl < 2) return ORCB_IO_ERROR;
             const uint32_t nd = rl - 2;
@@ -1013,7 +1020,7 @@ __global__ void __launch_bounds__(RLE_WARPS * 32) k_coop_runs(const Seg* __restr
 __global__ void __launch_bounds__(RLE_WARPS * 32) k_int_rle_coop(const Seg* __restrict__ segs, uint32_t nseg,
                                                                  const uint32_t* __restrict__ cnt,
                                                                  const uint32_t* __restrict__ dstart, uint32_t* err,
-                                                                 uint32_t* mis) {
+                                                                 uint32_t* mis, int second_pass) {
     __shared__ uint32_t patchmap_all[RLE_WARPS][16];
     uint32_t* patchmap = patchmap_all[threadIdx.x >> 5];
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -1023,6 +1030,9 @@ __global__ void __launch_bounds__(RLE_WARPS * 32) k_int_rle_coop(const Seg* __re
     c.err = err;
     c.mis = mis;
     const Seg& s = *c.s;
+    // second pass: only decimal scale segments of column-stripes where some scale differed, now with every value written
+    if (second_pass && (s.out_kind != OUT_SCALE || mis[s.colstripe] == 0)) return;
+    c.scale_lazy = !second_pass;
     const uint32_t n = s.cnt_idx >= 0 ? cnt[s.cnt_idx] : s.n_values;
     const uint64_t obase = s.start_idx >= 0 ? dstart[s.start_idx] : s.out_start;
     uint32_t cur = s.start_byte, skip = s.run_skip, produced = 0;
@@ -1084,9 +1094,9 @@ int launch_int_rle(const Seg* segs, const BlockRec* blocks, const uint32_t* nblo
     return 0;
 }
 int launch_int_rle_coop(const Seg* segs, uint32_t n, const uint32_t* cnt, const uint32_t* dstart, uint32_t* err,
-                        uint32_t* mis, cudaStream_t st) {
+                        uint32_t* mis, int second_pass, cudaStream_t st) {
     if (!n) return 0;
-    k_int_rle_coop<<<blocks_for_warps(n, RLE_WARPS), RLE_WARPS * 32, 0, st>>>(segs, n, cnt, dstart, err, mis);
+    k_int_rle_coop<<<blocks_for_warps(n, RLE_WARPS), RLE_WARPS * 32, 0, st>>>(segs, n, cnt, dstart, err, mis, second_pass);
     LAUNCH_CHECK();
     return 0;
 }

@@ -122,6 +122,9 @@ struct SegCtx {
     const Seg* s;
     uint32_t* err;
     uint32_t* mis;
+    // decimal SECONDARY streams are almost always one constant (the type's scale): their long constant runs are
+    // only compared, not written, unless a value differed somewhere in the column-stripe (second pass of the kernel)
+    bool scale_lazy = false;
 };
 
 __device__ __forceinline__ void store_val(const SegCtx& c, uint64_t idx, int64_t v) {

@@ -13,8 +13,9 @@ int launch_rle_index(const Seg* segs, uint32_t n, const uint32_t* cnt, RunRec* t
 int launch_int_rle(const Seg* segs, const BlockRec* blocks, const uint32_t* nblocks, uint32_t pool_blocks, const RunRec* table,
                    const uint32_t* cnt, const uint32_t* dstart, uint32_t* err, uint32_t* mis, uint32_t* slow_list,
                    uint32_t* slow_count, const CoopRec* coop_q, const uint32_t* ncoop, uint32_t coop_cap, cudaStream_t st);
+// second_pass = 1: only the decimal scale segments of column-stripes whose mismatch flag is set, every value written
 int launch_int_rle_coop(const Seg* segs, uint32_t n, const uint32_t* cnt, const uint32_t* dstart, uint32_t* err,
-                        uint32_t* mis, cudaStream_t st);
+                        uint32_t* mis, int second_pass, cudaStream_t st);
 int launch_byte_rle(const Seg* segs, uint32_t n, const uint32_t* cnt, const uint32_t* dstart, uint32_t* err,
                     cudaStream_t st);
 int launch_bits(const BitSeg* segs, uint32_t n, uint32_t* cnt, const uint32_t* dstart, cudaStream_t st);

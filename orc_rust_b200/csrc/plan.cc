@@ -542,7 +542,8 @@ void Job::plan_stripe(uint32_t task_idx) {
                 }
                 (long_runs ? int_big_segs_ : int_segs_).push_back(sg);
                 static const uint32_t ow1[6] = {2, 4, 8, 4, 4, 1};
-                (long_runs ? ab_intbig_ : ab_int_) += (uint64_t)(sr.len / ng) + (uint64_t)rows_in_group(g) * ow1[okind];
+                // (long constant runs of decimal scales are compared, not written: only their stream bytes count)
+                (long_runs ? ab_intbig_ : ab_int_) += (uint64_t)(sr.len / ng) + (long_runs && okind == OUT_SCALE ? 0ull : (uint64_t)rows_in_group(g) * ow1[okind]);
             }
             n_segments_ += ng;
         };

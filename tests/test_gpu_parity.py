@@ -320,6 +320,39 @@ def test_edge_shapes(ob, tmp_path):
                     assert_batches_identical(got, exp, f"edge n={n} {comp} dict={thr} bs={bs}")
 
 
+# ---- decimal scales that differ from the type's (array_decoder/decimal.rs:138-166) ----------------------------
+def test_decimal_scale_repair(ob, tmp_path):
+    """pyarrow writes one constant scale; patch single runs of the SECONDARY stream to other scales (both directions)
+    so that fix_i128_scale has to multiply / divide, in streams whose other runs are only compared, never written."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tools"))
+    import gen_orc
+    from oracle import orc_oracle as oo
+    p = gen_orc.write(gen_orc.lineitem_table(9_000, 4), str(tmp_path / "li.orc"), row_index_stride=2000)
+    data0 = open(p, "rb").read()
+    of = oo.OracleFile(data0)
+    streams, _enc, _tz = of._stripe_footer(of.stripes[0])
+    names = [n for n, _ in of.columns]
+    secondary = [st for st in streams if st.kind == 5]          # SECONDARY of the four decimal(15,2) columns
+    assert len(secondary) == 4
+    for k, (st, new_scale) in enumerate(zip(secondary, (0, 1, 3, 5))):
+        raw = data0[st.offset:st.offset + st.length]
+        # fixed-delta runs: header (0xC0 | ...), length byte, zigzag base (scale 2 -> 0x04), delta 0x00
+        starts = [i for i in range(0, len(raw) - 3, 4) if raw[i] >> 6 == 3 and raw[i + 2] == 0x04 and raw[i + 3] == 0x00]
+        assert len(starts) >= 3, "unexpected SECONDARY layout"
+        data = bytearray(data0)
+        for i in (starts[1], starts[-1]):
+            data[st.offset + i + 2] = new_scale * 2               # zigzag of the new scale
+        data = bytes(data)
+        exp = oo.OracleFile(data).read()
+        for use_index in (True, False):
+            got = list(ob.ArrowReaderBuilder.try_new(data).with_row_index(use_index).build())
+            assert_batches_identical(got, exp, f"scale {new_scale} in {names[st.column - 1]} index={use_index}")
+        ci = exp[0].schema.get_field_index(names[st.column - 1])
+        base = oo.OracleFile(data0).read()
+        assert any(not e.column(ci).equals(b.column(ci)) for e, b in zip(exp, base)), "the patch changed nothing"
+
+
 # ---- builder options (src/arrow_reader.rs:70-173) through the decode path -----------------------------------
 def test_builder_options(ob, tmp_path):
     import sys
