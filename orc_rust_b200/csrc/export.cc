@@ -57,6 +57,21 @@ void Job::ensure_host_output() {
         CUDA_OK(cudaHostAlloc((void**)&ho->heap, heap_used, cudaHostAllocDefault));
         CUDA_OK(cudaMemcpyAsync(ho->heap, base_[AR_HEAP], heap_used, cudaMemcpyDeviceToHost, stream_));
     }
+    // direct strings alias the staged / decompressed DATA streams: bring those byte ranges back as well
+    uint64_t strs_bytes = 0;
+    for (auto& cp : colstripes_) {
+        if (cp.str_slot < 0 || strcols_[cp.str_slot].mode != 0) continue;
+        cp.str_host_off = strs_bytes;
+        strs_bytes += (cp.str_data_len + 63) / 64 * 64;
+    }
+    if (strs_bytes) {
+        CUDA_OK(cudaHostAlloc((void**)&ho->strs, strs_bytes, cudaHostAllocDefault));
+        for (auto& cp : colstripes_) {
+            if (cp.str_slot < 0 || strcols_[cp.str_slot].mode != 0 || !cp.str_data_len) continue;
+            CUDA_OK(cudaMemcpyAsync(ho->strs + cp.str_host_off, (const void*)(uintptr_t)reloc(cp.str_data), cp.str_data_len,
+                                    cudaMemcpyDeviceToHost, stream_));
+        }
+    }
     CUDA_OK(cudaStreamSynchronize(stream_));
     host_out_ = ho;
 }
@@ -119,7 +134,7 @@ void Job::export_batch(uint64_t i, ArrowArray* out) {
                 const uint64_t p = ptrs[cp.str_slot];
                 dbase = host_out_->heap ? host_out_->heap + (p - (uint64_t)(uintptr_t)base_[AR_HEAP]) : host_out_->out;
             } else {
-                dbase = host_out_->out + (cp.str_data & omask);
+                dbase = host_out_->strs ? host_out_->strs + cp.str_host_off : host_out_->out;
             }
             ap->buffers[2] = dbase + bb[b];
         } else if (oc.kind == T_BOOLEAN) {
@@ -169,7 +184,7 @@ void Job::export_batch_device(uint64_t i, ArrowDeviceArray* out) {
             const int64_t* bb = (const int64_t*)(h_meta_ + o_bbase_ + cp.batch_base_off);
             ap->buffers[1] = base_[AR_OUT] + (cp.offsets & omask) + (uint64_t)b * (bs + 1) * 4;
             const uint8_t* dbase = strcols_[cp.str_slot].mode == 1 ? (const uint8_t*)(uintptr_t)ptrs[cp.str_slot]
-                                                                   : base_[AR_OUT] + (cp.str_data & omask);
+                                                                   : (const uint8_t*)(uintptr_t)reloc(cp.str_data);
             ap->buffers[2] = dbase + bb[b];
         } else if (oc.kind == T_BOOLEAN) {
             ap->buffers[1] = base_[AR_OUT] + (cp.values & omask) + (uint64_t)b * cp.values_stride;

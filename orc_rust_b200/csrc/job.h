@@ -87,7 +87,9 @@ struct ColStripePlan {
     uint64_t values = 0;              // AR_OUT offset (prims: n_rows*width; bool: per-batch bitmaps)
     uint32_t values_stride = 0;       // bool only
     uint64_t offsets = 0;             // AR_OUT offset, strings
-    uint64_t str_data = 0;            // AR_OUT offset (direct) — dictionary: from ptr_table
+    uint64_t str_data = 0;            // direct strings: arena-tagged start of the DATA bytes the rows use (no copy is made)
+    uint64_t str_data_len = 0;        //   and their number; dictionary: the heap pointer comes from ptr_table
+    uint64_t str_host_off = 0;        //   offset of their host copy in HostOutput::strs
     int32_t str_slot = -1;            // index into StrCol table / ptr_table
     uint64_t batch_base_off = 0;      // byte offset inside the meta blob of i64[n_batches+1]
 };

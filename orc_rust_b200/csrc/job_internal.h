@@ -33,9 +33,11 @@ struct DeviceArenas {
 struct HostOutput {
     uint8_t* out = nullptr;   // pinned copy of AR_OUT
     uint8_t* heap = nullptr;  // pinned copy of the used part of AR_HEAP
+    uint8_t* strs = nullptr;  // pinned copy of the DATA byte ranges that direct string columns point into
     ~HostOutput() {
         if (out) cudaFreeHost(out);
         if (heap) cudaFreeHost(heap);
+        if (strs) cudaFreeHost(strs);
     }
 };
 

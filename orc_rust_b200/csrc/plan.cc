@@ -752,13 +752,12 @@ void Job::plan_stripe(uint32_t task_idx) {
                     // the bytes of the decoded rows: the whole DATA stream, or its part between the window's positions
                     str_d0 = std::min(spec_of(&s_data)[0].byte, s_data.len);
                     str_dn = std::max(std::min(win_end_of(&s_data), s_data.len), str_d0) - str_d0;
-                    cp.str_data = alloc(AR_OUT, (uint64_t)str_dn + 16);
+                    // no copy: the values buffer of a batch IS its byte range of the staged (or decompressed) DATA stream,
+                    // where the reference reads the bytes into a new Vec (string.rs:135-140)
+                    cp.str_data = s_data.ptr + str_d0;
+                    cp.str_data_len = str_dn;
                     sc.data = cp.str_data;
                     sc.data_len = str_dn;
-                    if (str_dn) {
-                        add_copy(s_data.ptr + str_d0, str_dn, cp.str_data, str_dn, -1, 1, str_dn);
-                        if (k != T_BINARY) copies_.back().u8_col = (int32_t)strcols_.size();  // validated on the way through
-                    }
                     n_segments_ += 1;
                 }
                 if (has_present) add_spaced(dense_i32, rows_i32, 4, false);
@@ -774,11 +773,8 @@ void Job::plan_stripe(uint32_t task_idx) {
                         sc.u8_bad = alloc(AR_ZERO, 16);
                         const uint32_t nt = (uint32_t)(((uint64_t)u8_n + 15) / U8_TILE + 1);  // tiles are cut at aligned addresses
                         sc.u8_flags = alloc(AR_ZERO, ((uint64_t)nt + 32) / 32 * 4 + 16);
-                        if (use_dict) {
-                            // dictionary bytes get their own pass; direct DATA is checked by the copy kernel
-                            for (uint32_t t = 0; t < nt; t++) u8_tiles_.push_back(make_uint2((uint32_t)strcols_.size(), t));
-                            ab_utf8_ += u8_n;
-                        }
+                        for (uint32_t t = 0; t < nt; t++) u8_tiles_.push_back(make_uint2((uint32_t)strcols_.size(), t));
+                        ab_utf8_ += u8_n;
                     }
                 }
                 strcols_.push_back(sc);
