@@ -161,6 +161,53 @@ int orcb_reader_new_ex(OrcbFile* f, const OrcbReadOptions* opt, const OrcbRowSel
  * (src/arrow_reader.rs:296-309).  *n_triples is the number of triples (also when it exceeds cap_triples). */
 int orcb_selection_plan(const OrcbRowSelector* selectors, uint32_t n_selectors, const uint64_t* stripe_rows, uint32_t n_stripes,
                         uint64_t batch_size, int32_t* applies, uint64_t* triples, size_t cap_triples, size_t* n_triples);
+/* ArrowReaderBuilder::with_predicate (src/arrow_reader.rs:140-176): a predicate over the projected top-level columns,
+ * evaluated per stripe against the row groups' statistics and Bloom filters (src/row_group_filter.rs); the row groups
+ * that cannot match are neither staged nor decoded.  The tree (src/predicate.rs:28-104) is passed in pre-order: a
+ * node, then the subtrees of its n_children children. */
+enum OrcbPredicateKind { ORCB_PRED_COMPARISON = 0, ORCB_PRED_IS_NULL = 1, ORCB_PRED_IS_NOT_NULL = 2, ORCB_PRED_AND = 3,
+                         ORCB_PRED_OR = 4, ORCB_PRED_NOT = 5 };
+enum OrcbComparisonOp { ORCB_OP_EQ = 0, ORCB_OP_NE = 1, ORCB_OP_LT = 2, ORCB_OP_LE = 3, ORCB_OP_GT = 4, ORCB_OP_GE = 5 };
+enum OrcbPredicateValueType { ORCB_VAL_BOOLEAN = 0, ORCB_VAL_INT8 = 1, ORCB_VAL_INT16 = 2, ORCB_VAL_INT32 = 3,
+                              ORCB_VAL_INT64 = 4, ORCB_VAL_FLOAT32 = 5, ORCB_VAL_FLOAT64 = 6, ORCB_VAL_UTF8 = 7 };
+typedef struct OrcbPredicateNode {
+    int32_t kind;          /* OrcbPredicateKind */
+    int32_t op;            /* OrcbComparisonOp (comparisons) */
+    int32_t value_type;    /* OrcbPredicateValueType (comparisons) */
+    int32_t value_is_null; /* PredicateValue::X(None) */
+    int64_t i64;           /* Boolean (0 / 1), Int8 .. Int64 */
+    double f64;            /* Float32 (widened, as the reference does before comparing) and Float64 */
+    const char* column;    /* comparisons, IS NULL, IS NOT NULL: NUL-terminated column name */
+    const uint8_t* str;    /* Utf8: the value's bytes */
+    uint64_t str_len;
+    uint32_t n_children;   /* AND / OR: any number; NOT: 1; leaves: 0 */
+    uint32_t reserved;
+} OrcbPredicateNode;
+/* Everything ArrowReaderBuilder can be given, in one call; zero / NULL members mean "not set". */
+typedef struct OrcbReaderBuild {
+    const OrcbReadOptions* options;
+    const OrcbRowSelector* selectors; /* with_row_selection */
+    uint32_t n_selectors;
+    int32_t has_selection;
+    const struct ArrowSchema* schema; /* with_schema */
+    const OrcbPredicateNode* predicate; /* with_predicate */
+    uint32_t n_predicate_nodes;
+    uint32_t reserved;
+} OrcbReaderBuild;
+int orcb_reader_build(OrcbFile* f, const OrcbReaderBuild* build, OrcbReader** out);
+/* Host-only: the verdict of a predicate on one stripe.  *evaluated = 0 when the reference would fall back to reading
+ * the whole stripe (no row index, column not projected, value of the wrong type ...); else keep[g] = 1 for the row
+ * groups that may hold matching rows, *n_groups of them (also when that exceeds cap). */
+int orcb_predicate_row_groups(OrcbFile* f, uint32_t stripe, const OrcbReadOptions* opt, const OrcbPredicateNode* predicate,
+                              uint32_t n_predicate_nodes, uint8_t* keep, size_t cap, size_t* n_groups, int* evaluated);
+/* Host-only: what a reader built with a selection and / or a predicate will yield, in the form of
+ * orcb_selection_plan: triples (ordinal among the stripes the reader visits, first row, rows); applies[s] = 0 for a
+ * stripe that is read whole.  *n_stripes / *n_triples are the full counts, also when they exceed the capacities. */
+int orcb_reader_plan(OrcbReader* r, int32_t* applies, size_t cap_stripes, size_t* n_stripes, uint64_t* triples,
+                     size_t cap_triples, size_t* n_triples);
+/* Host-only: BloomFilter::hash_long / hash_bytes (src/bloom_filter.rs:136-149, 182-230) */
+uint64_t orcb_bloom_hash_long(int64_t value);
+uint64_t orcb_bloom_hash_bytes(const uint8_t* bytes, size_t len);
 /* Work done so far: out[0] = (stream, row-group) segments planned, out[1] = stripe tasks staged.  With a selection only
  * the row groups that hold selected rows are decoded, so both shrink with it. */
 int orcb_reader_counters(const OrcbReader* r, uint64_t out[2]);

@@ -477,6 +477,60 @@ class OracleFile:
             out.append((name, cid, present, payload))
         return n, out
 
+    # --- with_predicate (src/row_index.rs:204-331, src/arrow_reader.rs:256-293) ------------------------------------
+    def stripe_row_index(self, si: int, columns=None):
+        """{column id: [RowGroupEntry dict]} for the projected top-level columns that have a ROW_INDEX stream."""
+        s = self.stripes[si]
+        streams, _, _ = self._stripe_footer(s)
+        by_key = {}
+        for st in streams:
+            by_key.setdefault((st.column, st.kind), st)  # the reference's HashMap keeps the last; one per key in practice
+        out = {}
+        for name, cid in self.columns:
+            if columns is not None and name not in columns:
+                continue
+            st = by_key.get((cid, S_ROW_INDEX))
+            if st is None:
+                continue
+            raw = bytes(decompress_stream(self.compression, self.data[st.offset:st.offset + st.length], self.block_size))
+            entries = []
+            for f, wt, v in pb_fields(raw):
+                if f == 1:
+                    stats = None
+                    for g, _, w in pb_fields(v):
+                        if g == 2:
+                            stats = parse_column_statistics(w)
+                    entries.append({"stats": stats, "bloom": None})
+            out[cid] = entries
+        for name, cid in self.columns:
+            if cid not in out:
+                continue
+            st = by_key.get((cid, 7)) or by_key.get((cid, 8))  # BLOOM_FILTER, else BLOOM_FILTER_UTF8
+            if st is None:
+                continue
+            raw = bytes(decompress_stream(self.compression, self.data[st.offset:st.offset + st.length], self.block_size))
+            filters = [b for b in (parse_bloom_filter(v) for f, _, v in pb_fields(raw) if f == 1) if b is not None]
+            if len(filters) != len(out[cid]):
+                raise OracleError(13, "panic: Bloom filter count mismatch")
+            for e, b in zip(out[cid], filters):
+                e["bloom"] = b
+        return out
+
+    def predicate_selection(self, si: int, predicate, columns=None):
+        """([skip, count] selectors, row-group verdicts or None): what try_advance_stripe derives for one stripe."""
+        rows = self.stripes[si].number_of_rows
+        stride = 10_000 if self.row_index_stride is None else self.row_index_stride
+        try:
+            index = self.stripe_row_index(si, columns)
+            cols = [(n, c) for n, c in self.columns if columns is None or n in columns]
+            groups = 0 if stride == 0 else -(-rows // stride)
+            verdict = evaluate_predicate(predicate, index, cols, groups)
+        except OracleError as e:
+            if str(e.args[-1]).startswith("panic"):
+                raise
+            return [[False, rows]], None  # "Keep all rows (maybe)"
+        return from_row_group_filter(verdict, stride, rows), verdict
+
     def read_stripe(self, si: int, batch_size: int = 8192, columns=None, ts_unit: str = "ns", views=None):
         """Batches of one stripe as pyarrow RecordBatches with the reference's physical layout."""
         import pyarrow as pa
@@ -499,10 +553,14 @@ class OracleFile:
                 batches.append(pa.RecordBatch.from_arrays(arrays, schema=schema))
         return batches
 
-    def read(self, batch_size: int = 8192, columns=None, ts_unit: str = "ns", stripes=None, selection=None):
-        """`selection`: [(skip, row_count), ...] as ArrowReaderBuilder::with_row_selection takes it."""
+    def read(self, batch_size: int = 8192, columns=None, ts_unit: str = "ns", stripes=None, selection=None, predicate=None):
+        """`selection`: [(skip, row_count), ...] as ArrowReaderBuilder::with_row_selection takes it; `predicate`: a
+        nested tuple as `evaluate_predicate` below takes it (ArrowReaderBuilder::with_predicate)."""
         order = list(range(len(self.stripes)) if stripes is None else stripes)
-        plan = None if selection is None else selection_views(selection, [self.stripes[si].number_of_rows for si in order], batch_size)
+        psel = None if predicate is None else [self.predicate_selection(si, predicate, columns)[0] for si in order]
+        plan = None
+        if selection is not None or psel is not None:
+            plan = selection_views(selection, [self.stripes[si].number_of_rows for si in order], batch_size, psel)
         out = []
         for k, si in enumerate(order):
             views = None
@@ -514,14 +572,419 @@ class OracleFile:
         return out
 
 
-def selection_views(selection, stripe_rows, batch_size):
+# ------------------------------------------------------------------------------------------------
+# predicate pushdown: statistics, Bloom filters, row-group verdicts
+# ------------------------------------------------------------------------------------------------
+def _zz(v: int) -> int:
+    return (v >> 1) ^ -(v & 1)
+
+
+def _pb_str(v, wt) -> str:
+    if wt != 2:
+        raise OracleError(7, "wire type of a string field")
+    try:
+        return bytes(v).decode("utf-8")
+    except UnicodeDecodeError:
+        raise OracleError(7, "invalid string value: data is not UTF-8 encoded")
+
+
+def parse_column_statistics(b: bytes):
+    """TryFrom<&proto::ColumnStatistics> (src/statistics.rs:77-143): {"n", "has_null", "type": (variant, ...) | None}."""
+    import struct
+    n, has_null, sub = 0, False, {}
+    for f, wt, v in pb_fields(b):
+        if f == 1:
+            n = v
+        elif f == 10:
+            has_null = bool(v)
+        elif 2 <= f <= 9 or f == 12:
+            if wt != 2:
+                raise OracleError(7, "wire type of a statistics message")
+            sub.setdefault(f, []).append(bytes(v))
+    def fields(fno):
+        d = {}
+        for part in sub[fno]:  # prost merges repeated occurrences of a message field
+            for g, gw, w in pb_fields(part):
+                d.setdefault(g, []).append((gw, w))
+        return d
+    # strings are checked while decoding, whether or not the variant is used afterwards
+    for fno, str_fields in ((4, (1, 2, 4, 5)), (6, (1, 2, 3))):
+        if fno in sub:
+            d = fields(fno)
+            for g in str_fields:
+                for gw, w in d.get(g, []):
+                    _pb_str(w, gw)
+    typ = None
+    if n == 0:
+        typ = None
+    elif 2 in sub:
+        d = fields(2)
+        typ = ("int", _zz(d[1][-1][1]) if 1 in d else 0, _zz(d[2][-1][1]) if 2 in d else 0)
+    elif 3 in sub:
+        d = fields(3)
+        dbl = lambda g: struct.unpack("<d", d[g][-1][1])[0] if g in d else 0.0
+        typ = ("double", dbl(1), dbl(2))
+    elif 4 in sub:
+        d = fields(4)
+        txt = lambda g: _pb_str(d[g][-1][1], d[g][-1][0]) if g in d else None
+        lo, hi = txt(1), txt(2)
+        typ = ("string", lo if lo is not None else (txt(4) or ""), hi if hi is not None else (txt(5) or ""),
+               lo is not None, hi is not None)
+    elif 5 in sub:
+        d = fields(5)
+        counts = []
+        for gw, w in d.get(1, []):
+            counts.extend(_packed_u(w, gw))
+        if not counts:
+            raise OracleError(13, "panic: index out of bounds (bucket statistics without a count)")
+        typ = ("bucket", counts[0])
+    elif 6 in sub:
+        d = fields(6)
+        txt = lambda g: _pb_str(d[g][-1][1], d[g][-1][0]) if g in d else ""
+        typ = ("decimal", txt(1), txt(2))
+    elif 7 in sub:
+        d = fields(7)
+        z32 = lambda g: int(np.int32(np.uint32(_zz(d[g][-1][1] & 0xFFFFFFFF) & 0xFFFFFFFF))) if g in d else 0
+        typ = ("date", z32(1), z32(2))
+    elif 8 in sub:
+        typ = ("binary",)
+    elif 9 in sub:
+        d = fields(9)
+        typ = ("timestamp", _zz(d[3][-1][1]) if 3 in d else 0, _zz(d[4][-1][1]) if 4 in d else 0)  # minimumUtc / maximumUtc
+    elif 12 in sub:
+        typ = ("collection",)
+    return {"n": n, "has_null": has_null, "type": typ}
+
+
+def parse_bloom_filter(b: bytes):
+    """BloomFilter::try_from_proto (src/bloom_filter.rs:35-75): (k, [u64 words]) or None for an empty message."""
+    k, words, utf8 = 0, [], None
+    for f, wt, v in pb_fields(b):
+        if f == 1:
+            k = v
+        elif f == 2:
+            raw = bytes(v)
+            if wt not in (1, 2) or len(raw) % 8:
+                raise OracleError(7, "BloomFilter.bitset")
+            words.extend(int.from_bytes(raw[i:i + 8], "little") for i in range(0, len(raw), 8))
+        elif f == 3:
+            utf8 = bytes(v)
+    if words and utf8 is not None:
+        raise OracleError(13, "panic: Bloom filter proto has both bitset and utf8bitset populated")
+    if not words and utf8 is None:
+        return None
+    if not words:
+        words = [int.from_bytes(utf8[i:i + 8], "little") for i in range(0, len(utf8), 8)]
+    return (k if k else 3, words)
+
+
+_M64 = (1 << 64) - 1
+
+
+def _sar(x: int, n: int) -> int:
+    """arithmetic shift right of a 64-bit pattern"""
+    if x >> 63:
+        x -= 1 << 64
+    return (x >> n) & _M64
+
+
+def bloom_hash_long(v: int) -> int:
+    """BloomFilter::hash_long (src/bloom_filter.rs:136-149), Thomas Wang's mix on an i64"""
+    key = v & _M64
+    key = ((~key & _M64) + (key << 21)) & _M64
+    key ^= _sar(key, 24)
+    key = (key + (key << 3) + (key << 8)) & _M64
+    key ^= _sar(key, 14)
+    key = (key + (key << 2) + (key << 4)) & _M64
+    key ^= _sar(key, 28)
+    return (key + (key << 31)) & _M64
+
+
+def bloom_hash_bytes(data: bytes) -> int:
+    """murmur3_64_orc (src/bloom_filter.rs:182-242): Murmur3 x64, h1 only, seed 104729"""
+    c1, c2 = 0x87C37B91114253D5, 0x4CF5AD432745937F
+    rotl = lambda x, r: ((x << r) | (x >> (64 - r))) & _M64
+    h1 = 104729
+    nb = len(data) // 8
+    for i in range(nb):
+        k1 = int.from_bytes(data[8 * i:8 * i + 8], "little")
+        k1 = rotl(k1 * c1 & _M64, 31) * c2 & _M64
+        h1 = rotl(h1 ^ k1, 27)
+        h1 = (h1 * 5 + 1390208809) & _M64
+    tail = data[8 * nb:]
+    if tail:
+        k1 = int.from_bytes(tail, "little")
+        k1 = rotl(k1 * c1 & _M64, 31) * c2 & _M64
+        h1 ^= k1
+    h1 ^= len(data)
+    h1 ^= h1 >> 33
+    h1 = h1 * 0xFF51AFD7ED558CCD & _M64
+    h1 ^= h1 >> 33
+    h1 = h1 * 0xC4CEB9FE1A85EC53 & _M64
+    h1 ^= h1 >> 33
+    return h1
+
+
+def bloom_test_hash(bloom, h: int) -> bool:
+    """BloomFilter::test_hash (src/bloom_filter.rs:109-133)"""
+    k, words = bloom
+    bits = len(words) * 64
+    if bits == 0:
+        return True
+    as_i32 = lambda x: ((x & 0xFFFFFFFF) ^ 0x80000000) - 0x80000000
+    h1, h2 = as_i32(h), as_i32(h >> 32)
+    for i in range(1, k + 1):
+        combined = as_i32(h1 + as_i32(i * h2))
+        if combined < 0:
+            combined = ~combined
+        bit = combined % bits
+        if not (words[bit // 64] >> (bit % 64)) & 1:
+            return False
+    return True
+
+
+def bloom_add_hash(bloom, h: int):
+    """BloomFilter::add_hash (src/bloom_filter.rs:85-107), for the tests that build filters"""
+    k, words = bloom
+    bits = len(words) * 64
+    as_i32 = lambda x: ((x & 0xFFFFFFFF) ^ 0x80000000) - 0x80000000
+    h1, h2 = as_i32(h), as_i32(h >> 32)
+    for i in range(1, k + 1):
+        combined = as_i32(h1 + as_i32(i * h2))
+        if combined < 0:
+            combined = ~combined
+        bit = combined % bits
+        words[bit // 64] |= 1 << (bit % 64)
+
+
+_NEGATED = {"eq": "ne", "ne": "eq", "lt": "ge", "le": "gt", "gt": "le", "ge": "lt"}
+_INT_TYPES = ("Int8", "Int16", "Int32", "Int64")
+
+
+def _cmp_numbers(lo, hi, op, v):
+    return {"eq": lo <= v <= hi, "ne": not (lo == v and hi == v), "lt": lo < v, "le": lo <= v, "gt": hi > v, "ge": hi >= v}[op]
+
+
+def _cmp_floats(lo, hi, op, v):
+    eps = 1e-9
+    if op == "eq":
+        return (lo - eps) <= v <= (hi + eps)
+    if op == "ne":
+        return not (abs(lo - v) < eps and abs(hi - v) < eps)
+    return {"lt": lo < v, "le": lo <= v, "gt": hi > v, "ge": hi >= v}[op]
+
+
+def compare_strings(lo: str, hi: str, op: str, v: str, exact_min: bool, exact_max: bool) -> bool:
+    """evaluate_string_comparison (src/row_group_filter.rs:500-530); Rust orders str by bytes"""
+    lo_b, hi_b, v_b = lo.encode(), hi.encode(), v.encode()
+    min_le = lo_b < v_b or (lo_b == v_b and exact_min)
+    max_ge = hi_b > v_b or (hi_b == v_b and exact_max)
+    if op == "eq":
+        return min_le and max_ge
+    if op == "le":
+        return min_le
+    if op == "ge":
+        return max_ge
+    if op == "lt":
+        return lo_b < v_b
+    if op == "gt":
+        return hi_b > v_b
+    return not (lo_b == hi_b and exact_min and exact_max and lo_b == v_b)
+
+
+def _stats_verdict(stats, op, value):
+    """evaluate_comparison_with_stats (src/row_group_filter.rs:170-360); value = (type name, python value | None)"""
+    vt, v = value
+    t = stats["type"]
+    if t is None:
+        raise OracleError(13, "Statistics missing type-specific information")
+    kind = t[0]
+    def need(ok, what):
+        if not ok or v is None:
+            raise OracleError(13, "Type mismatch: expected " + what)
+    if kind == "int":
+        need(vt in _INT_TYPES, "integer value")
+        return _cmp_numbers(t[1], t[2], op, v)
+    if kind == "double":
+        need(vt in ("Float32", "Float64"), "float value")
+        return _cmp_floats(t[1], t[2], op, float(np.float32(v)) if vt == "Float32" else float(v))
+    if kind == "string":
+        need(vt == "Utf8", "string value")
+        return compare_strings(t[1], t[2], op, v, t[3], t[4])
+    if kind == "date":
+        need(vt in ("Int32", "Int64"), "integer value for date")
+        return _cmp_numbers(t[1], t[2], op, v)
+    if kind == "timestamp":
+        need(vt == "Int64", "integer value for timestamp")
+        return _cmp_numbers(t[1], t[2], op, v)
+    if kind == "decimal":
+        need(vt == "Utf8", "string value for decimal")
+        return compare_strings(t[1], t[2], op, v, True, True)
+    if kind == "bucket":
+        need(vt == "Boolean", "boolean value")
+        trues, falses = t[1], (stats["n"] - t[1]) & _M64
+        if op == "eq":
+            return trues > 0 if v else falses > 0
+        if op == "ne":
+            return falses > 0 if v else trues > 0
+        return True
+    return True
+
+
+def _bloom_verdict(entry, op, value):
+    """row_group_might_match_bloom + bloom_value_hash64 (src/row_group_filter.rs:362-406)"""
+    import struct
+    vt, v = value
+    if op != "eq" or entry["bloom"] is None or v is None:
+        return True
+    if vt == "Utf8":
+        h = bloom_hash_bytes(v.encode())
+    elif vt in ("Float32", "Float64"):
+        d = float(np.float32(v)) if vt == "Float32" else float(v)
+        h = bloom_hash_long(struct.unpack("<q", struct.pack("<d", d))[0])
+    elif vt == "Boolean":
+        h = bloom_hash_long(1 if v else 0)
+    else:
+        h = bloom_hash_long(int(v))
+    return bloom_test_hash(entry["bloom"], h)
+
+
+def evaluate_predicate(pred, index, cols, groups: int):
+    """evaluate_predicate (src/row_group_filter.rs:24-114).  `pred`: ("cmp", column, op, (type, value)) with op in
+    eq ne lt le gt ge, ("is_null", column), ("is_not_null", column), ("and", [..]), ("or", [..]), ("not", pred);
+    `index`: stripe_row_index(); `cols`: projected (name, column id).  Raises what the reference returns as Err."""
+    def entries_of(column):
+        for name, cid in cols:
+            if name == column:
+                if cid not in index:
+                    raise OracleError(13, f"Row index not found for column '{column}'")
+                return index[cid]
+        raise OracleError(13, f"Column '{column}' not found in schema")
+
+    def compare(column, op, value, result):
+        for g, e in enumerate(entries_of(column)[:len(result)]):
+            if e["stats"] is not None and not _stats_verdict(e["stats"], op, value):
+                result[g] = False
+            else:
+                result[g] = _bloom_verdict(e, op, value)
+
+    def null_test(column, want_null, result):
+        for g, e in enumerate(entries_of(column)[:len(result)]):
+            if e["stats"] is None:
+                result[g] = True
+            else:
+                result[g] = e["stats"]["has_null"] if want_null else e["stats"]["n"] > 0
+
+    def rec(p, result):
+        tag = p[0]
+        if tag == "cmp":
+            compare(p[1], p[2], p[3], result)
+        elif tag == "is_null":
+            null_test(p[1], True, result)
+        elif tag == "is_not_null":
+            null_test(p[1], False, result)
+        elif tag == "and":
+            for c in p[1]:
+                tmp = [True] * len(result)
+                rec(c, tmp)
+                for g in range(len(result)):
+                    result[g] = result[g] and tmp[g]
+        elif tag == "or":
+            tmps = []
+            for c in p[1]:
+                tmp = [True] * len(result)
+                rec(c, tmp)
+                tmps.append(tmp)
+            for g in range(len(result)):
+                result[g] = any(t[g] for t in tmps)
+        elif tag == "not":
+            q = p[1]
+            if q[0] == "not":
+                rec(q[1], result)
+            elif q[0] == "is_null":
+                null_test(q[1], False, result)
+            elif q[0] == "is_not_null":
+                null_test(q[1], True, result)
+            elif q[0] == "cmp":
+                compare(q[1], _NEGATED[q[2]], q[3], result)
+            elif q[0] == "and":
+                rec(("or", [("not", c) for c in q[1]]), result)
+            else:
+                rec(("and", [("not", c) for c in q[1]]), result)
+        else:
+            raise ValueError(tag)
+
+    result = [True] * groups
+    rec(pred, result)
+    return result
+
+
+def from_row_group_filter(verdict, stride: int, rows: int):
+    """RowSelection::from_row_group_filter (src/row_selection.rs:348-390) as [skip, count] lists"""
+    if not verdict:
+        return [[True, rows]]
+    sel = []
+    for keep in verdict:
+        if sel and sel[-1][0] == (not keep):
+            sel[-1][1] += stride
+        else:
+            sel.append([not keep, stride])
+    covered = len(verdict) * stride
+    if covered < rows:
+        if sel[-1][0]:
+            sel[-1][1] += rows - covered
+        else:
+            sel.append([True, rows - covered])
+    return sel
+
+
+def selection_and_then(first, second):
+    """RowSelection::and_then (src/row_selection.rs:401-463) on [skip, count] lists: `second` picks among the rows
+    `first` selects.  The reference panics when the two do not fit; that is OracleError(13, "panic: ...") here."""
+    first = [list(x) for x in first]
+    second = [list(x) for x in second]
+    out, to_skip, a, b = [], 0, 0, 0
+    while b < len(second):
+        if a >= len(first):
+            raise OracleError(13, "panic: selection exceeds the number of selected rows")
+        if second[b][1] == 0:
+            b += 1
+            continue
+        if first[a][1] == 0:
+            a += 1
+            continue
+        if first[a][0]:
+            to_skip += first[a][1]
+            a += 1
+            continue
+        k = min(first[a][1], second[b][1])
+        first[a][1] -= k
+        second[b][1] -= k
+        if second[b][0]:
+            to_skip += k
+        else:
+            if to_skip:
+                out.append([True, to_skip])
+                to_skip = 0
+            out.append([False, k])
+    for sk, c in first[a:]:
+        if c:
+            if not sk:
+                raise OracleError(13, "panic: selection contains less than the number of selected rows")
+            to_skip += c
+    if to_skip:
+        out.append([True, to_skip])
+    return out
+
+
+def selection_views(selection, stripe_rows, batch_size, predicate_selections=None):
     """Row ranges each stripe yields under a row selection (None = the stripe is read whole).  Follows
     RowSelection::from(Vec<RowSelector>) (src/row_selection.rs:466-482), ArrowReader::try_advance_stripe
     (src/arrow_reader.rs:296-309: `split_off(stripe_rows)` while the selection still has rows, no selection at all
     afterwards) and NaiveStripeDecoder::next_with_row_selection (src/array_decoder/mod.rs:313-364), including its
     habit of staying on a selector until one step has covered the selector's whole row_count."""
     sel = []
-    for skip, count in selection:
+    for skip, count in (selection or []):
         if count == 0:
             continue
         if sel and sel[-1][0] == bool(skip):
@@ -529,26 +992,31 @@ def selection_views(selection, stripe_rows, batch_size):
         else:
             sel.append([bool(skip), count])
     out = []
-    for rows in stripe_rows:
-        if sum(c for _, c in sel) == 0:
+    for k_stripe, rows in enumerate(stripe_rows):
+        # try_advance_stripe (src/arrow_reader.rs:256-309): the predicate's selection first, then the caller's while
+        # it still has rows, combined as caller.and_then(predicate's)
+        head = None if predicate_selections is None else [list(x) for x in predicate_selections[k_stripe]]
+        if selection is not None and sum(c for _, c in sel) > 0:
+            # split_off(rows)
+            mine, acc, idx = [], 0, None
+            for i, (sk, c) in enumerate(sel):
+                acc += c
+                if acc > rows:
+                    idx = i
+                    break
+            if idx is None:
+                mine, sel = sel, []
+            else:
+                mine, rest = [list(x) for x in sel[:idx]], [list(x) for x in sel[idx:]]
+                overflow = acc - rows
+                if rest[0][1] != overflow:
+                    mine.append([rest[0][0], rest[0][1] - overflow])
+                rest[0][1] = overflow
+                sel = rest
+            head = mine if head is None else selection_and_then(mine, head)
+        if head is None:
             out.append(None)
             continue
-        # split_off(rows)
-        head, acc, idx = [], 0, None
-        for i, (sk, c) in enumerate(sel):
-            acc += c
-            if acc > rows:
-                idx = i
-                break
-        if idx is None:
-            head, sel = sel, []
-        else:
-            head, rest = [list(x) for x in sel[:idx]], [list(x) for x in sel[idx:]]
-            overflow = acc - rows
-            if rest[0][1] != overflow:
-                head.append([rest[0][0], rest[0][1] - overflow])
-            rest[0][1] = overflow
-            sel = rest
         # next_with_row_selection
         views, index, si = [], 0, 0
         while index < rows and si < len(head):

@@ -104,7 +104,7 @@ EXPORTED_SYMBOLS = [
     "orcb_open_memory", "orcb_open_path", "orcb_file_free", "orcb_file_num_rows", "orcb_file_num_stripes",
     "orcb_file_compression", "orcb_file_compression_block_size", "orcb_file_row_index_stride",
     "orcb_file_num_root_columns", "orcb_file_root_column_name", "orcb_file_stripe_info", "orcb_schema",
-    "orcb_reader_new", "orcb_reader_new_with_selection", "orcb_reader_new_ex", "orcb_reader_counters", "orcb_selection_plan", "orcb_reader_free", "orcb_reader_total_row_count", "orcb_reader_next",
+    "orcb_reader_new", "orcb_reader_new_with_selection", "orcb_reader_new_ex", "orcb_reader_build", "orcb_reader_plan", "orcb_predicate_row_groups", "orcb_bloom_hash_long", "orcb_bloom_hash_bytes", "orcb_reader_counters", "orcb_selection_plan", "orcb_reader_free", "orcb_reader_total_row_count", "orcb_reader_next",
     "orcb_reader_next_device", "orcb_job_new", "orcb_job_free", "orcb_job_plan", "orcb_job_stage",
     "orcb_job_launch", "orcb_job_finish", "orcb_job_stats", "orcb_job_restage", "orcb_job_kernel_stats", "orcb_job_num_batches", "orcb_job_export_batch",
     "orcb_job_export_batch_device", "orcb_decode_int_rle", "orcb_decode_byte_rle", "orcb_decode_bool_rle",
@@ -135,6 +135,15 @@ def lib() -> ctypes.CDLL:
         L.orcb_file_root_column_name.argtypes = [ctypes.c_void_p, ctypes.c_uint32]
         L.orcb_selection_plan.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint64,
                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+        L.orcb_reader_plan.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_size_t, ctypes.c_void_p]
+        L.orcb_reader_build.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.orcb_predicate_row_groups.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32,
+                                                ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
+        L.orcb_bloom_hash_long.argtypes = [ctypes.c_int64]
+        L.orcb_bloom_hash_long.restype = ctypes.c_uint64
+        L.orcb_bloom_hash_bytes.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
+        L.orcb_bloom_hash_bytes.restype = ctypes.c_uint64
         L.orcb_reader_new_ex.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int,
                                          ctypes.c_void_p, ctypes.c_void_p]
         L.orcb_reader_new_with_selection.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32,
@@ -329,6 +338,127 @@ class RowSelection:
         return sum(x.row_count for x in self.selectors if not x.skip)
 
 
+class _PredicateNodeC(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("op", ctypes.c_int32), ("value_type", ctypes.c_int32),
+                ("value_is_null", ctypes.c_int32), ("i64", ctypes.c_int64), ("f64", ctypes.c_double),
+                ("column", ctypes.c_char_p), ("str", ctypes.c_char_p), ("str_len", ctypes.c_uint64),
+                ("n_children", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+
+
+class _ReaderBuildC(ctypes.Structure):
+    _fields_ = [("options", ctypes.c_void_p), ("selectors", ctypes.c_void_p), ("n_selectors", ctypes.c_uint32),
+                ("has_selection", ctypes.c_int32), ("schema", ctypes.c_void_p), ("predicate", ctypes.c_void_p),
+                ("n_predicate_nodes", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+
+
+class ComparisonOp:
+    """src/predicate.rs:55-77"""
+    Equal, NotEqual, LessThan, LessThanOrEqual, GreaterThan, GreaterThanOrEqual = range(6)
+
+
+class PredicateValue:
+    """`PredicateValue` / `ScalarValue` (src/predicate.rs:28-48): a typed scalar, `None` standing for X(None)."""
+    _TYPES = ("Boolean", "Int8", "Int16", "Int32", "Int64", "Float32", "Float64", "Utf8")
+
+    def __init__(self, type_name: str, value):
+        if type_name not in self._TYPES:
+            raise ValueError(f"unknown predicate value type {type_name}")
+        self.type_name, self.value = type_name, value
+
+    def __repr__(self):
+        return f"PredicateValue.{self.type_name}({self.value!r})"
+
+
+for _t in PredicateValue._TYPES:
+    setattr(PredicateValue, _t, staticmethod(lambda value=None, _t=_t: PredicateValue(_t, value)))
+ScalarValue = PredicateValue
+
+
+class Predicate:
+    """`Predicate` (src/predicate.rs:79-190): comparisons and null tests on top-level columns, combined with
+    AND / OR / NOT.  Row groups whose statistics or Bloom filters rule the predicate out are not decoded."""
+    _COMPARISON, _IS_NULL, _IS_NOT_NULL, _AND, _OR, _NOT = range(6)
+
+    def __init__(self, kind, column=None, op=None, value=None, children=()):
+        self.kind, self.column, self.op, self.value, self.children = kind, column, op, value, list(children)
+
+    @classmethod
+    def comparison(cls, column: str, op: int, value: PredicateValue) -> "Predicate":
+        if not isinstance(value, PredicateValue):
+            raise TypeError("value must be a PredicateValue")
+        return cls(cls._COMPARISON, column, op, value)
+
+    @classmethod
+    def eq(cls, column, value): return cls.comparison(column, ComparisonOp.Equal, value)
+
+    @classmethod
+    def ne(cls, column, value): return cls.comparison(column, ComparisonOp.NotEqual, value)
+
+    @classmethod
+    def lt(cls, column, value): return cls.comparison(column, ComparisonOp.LessThan, value)
+
+    @classmethod
+    def lte(cls, column, value): return cls.comparison(column, ComparisonOp.LessThanOrEqual, value)
+
+    @classmethod
+    def gt(cls, column, value): return cls.comparison(column, ComparisonOp.GreaterThan, value)
+
+    @classmethod
+    def gte(cls, column, value): return cls.comparison(column, ComparisonOp.GreaterThanOrEqual, value)
+
+    @classmethod
+    def is_null(cls, column): return cls(cls._IS_NULL, column)
+
+    @classmethod
+    def is_not_null(cls, column): return cls(cls._IS_NOT_NULL, column)
+
+    @classmethod
+    def and_(cls, predicates): return cls(cls._AND, children=predicates)
+
+    @classmethod
+    def or_(cls, predicates): return cls(cls._OR, children=predicates)
+
+    @classmethod
+    def not_(cls, predicate): return cls(cls._NOT, children=[predicate])
+
+    def _flatten(self, out, keep):
+        n = _PredicateNodeC()
+        n.kind = self.kind
+        n.n_children = len(self.children)
+        if self.column is not None:
+            raw_name = self.column.encode("utf-8")
+            keep.append(raw_name)
+            n.column = raw_name
+        if self.kind == self._COMPARISON:
+            v = self.value
+            n.op = self.op
+            n.value_type = PredicateValue._TYPES.index(v.type_name)
+            n.value_is_null = 1 if v.value is None else 0
+            if v.value is not None:
+                if v.type_name == "Utf8":
+                    raw = v.value.encode("utf-8")
+                    keep.append(raw)
+                    n.str = raw
+                    n.str_len = len(raw)
+                elif v.type_name == "Float32":
+                    import numpy as np
+                    n.f64 = float(np.float32(v.value))  # `*v as f64`
+                elif v.type_name == "Float64":
+                    n.f64 = float(v.value)
+                else:
+                    n.i64 = int(v.value)
+        out.append(n)
+        for c in self.children:
+            c._flatten(out, keep)
+
+    def _to_c(self):
+        nodes, keep = [], []
+        self._flatten(nodes, keep)
+        arr = (_PredicateNodeC * len(nodes))(*nodes)
+        keep.append(nodes)
+        return arr, keep
+
+
 class ArrowReaderBuilder:
     """Mirror of `ArrowReaderBuilder` (src/arrow_reader.rs:39-231) with one extra option, `with_device`."""
 
@@ -394,8 +524,13 @@ class ArrowReaderBuilder:
         self._schema_override = schema
         return self
 
-    def with_predicate(self, *_a, **_k):
-        raise OrcError(22, "predicate pushdown is not on the device path yet (SURVEY §8(f) rank 1)")
+    def with_predicate(self, predicate: "Predicate") -> "ArrowReaderBuilder":
+        """`ArrowReaderBuilder::with_predicate` (src/arrow_reader.rs:140-176): row groups are pruned by their
+        statistics and Bloom filters, stripe by stripe; combined with a row selection as the reference combines them."""
+        if not isinstance(predicate, Predicate):
+            raise TypeError("predicate must be a Predicate")
+        self._predicate = predicate
+        return self
 
     def _options(self):
         return _make_options(self._device, self._batch_size, self._projection, self._byte_range, self._ts,
@@ -423,7 +558,8 @@ class ArrowReader:
         self._h = ctypes.c_void_p()
         sel = getattr(b, "_selection", None)
         override = getattr(b, "_schema_override", None)
-        if sel is None and override is None:
+        pred = getattr(b, "_predicate", None)
+        if sel is None and override is None and pred is None:
             _check(lib().orcb_reader_new(self._file._h, ctypes.byref(self._opts), ctypes.byref(self._h)))
         else:
             n_sel = len(sel.selectors) if sel is not None else 0
@@ -435,11 +571,18 @@ class ArrowReader:
             if override is not None:
                 c_schema = _ArrowSchema()
                 override._export_to_c(ctypes.addressof(c_schema))
+            bc = _ReaderBuildC()
+            bc.options = ctypes.addressof(self._opts)
+            bc.selectors = ctypes.addressof(arr)
+            bc.n_selectors = n_sel
+            bc.has_selection = 1 if sel is not None else 0
+            bc.schema = ctypes.addressof(c_schema) if c_schema is not None else None
+            if pred is not None:
+                nodes, keep = pred._to_c()
+                bc.predicate = ctypes.addressof(nodes)
+                bc.n_predicate_nodes = len(nodes)
             try:
-                _check(lib().orcb_reader_new_ex(self._file._h, ctypes.addressof(self._opts), ctypes.addressof(arr), n_sel,
-                                                1 if sel is not None else 0,
-                                                ctypes.addressof(c_schema) if c_schema is not None else None,
-                                                ctypes.addressof(self._h)))
+                _check(lib().orcb_reader_build(self._file._h, ctypes.byref(bc), ctypes.byref(self._h)))
             finally:
                 if c_schema is not None and c_schema.release:  # the library only reads it: release the export here
                     ctypes.CFUNCTYPE(None, ctypes.c_void_p)(c_schema.release)(ctypes.addressof(c_schema))
@@ -456,6 +599,18 @@ class ArrowReader:
 
     def total_row_count(self) -> int:
         return lib().orcb_reader_total_row_count(self._h)
+
+    def plan(self):
+        """Host-only: per visited stripe, None (read whole) or the (first row, rows) ranges it will yield."""
+        n, ns = ctypes.c_size_t(0), ctypes.c_size_t(0)
+        _check(lib().orcb_reader_plan(self._h, None, 0, ctypes.byref(ns), None, 0, ctypes.byref(n)))
+        applies = (ctypes.c_int32 * max(ns.value, 1))()
+        tri = (ctypes.c_uint64 * (3 * max(n.value, 1)))()
+        _check(lib().orcb_reader_plan(self._h, applies, ns.value, ctypes.byref(ns), tri, n.value, ctypes.byref(n)))
+        out = [([] if applies[i] else None) for i in range(ns.value)]
+        for k in range(n.value):
+            out[int(tri[3 * k])].append((int(tri[3 * k + 1]), int(tri[3 * k + 2])))
+        return out
 
     def counters(self) -> dict:
         """Segments planned / stripe tasks staged so far (shrinks with a row selection: partial decode)."""
@@ -577,6 +732,23 @@ class DecodeJob:
 
     def batches(self):
         return [self.batch(i) for i in range(self.num_batches)]
+
+
+def predicate_row_groups(source, stripe: int, predicate: "Predicate", projection=None):
+    """Host-only: the row groups of one stripe a predicate keeps, or None where the reference falls back to reading the
+    whole stripe (src/arrow_reader.rs:281-291)."""
+    f = source if isinstance(source, _File) else _File(source)
+    opts, keep_opts = _make_options(0, 8192, projection)
+    nodes, keep = predicate._to_c()
+    n = ctypes.c_size_t(0)
+    ev = ctypes.c_int(0)
+    cap = 1 << 16
+    buf = (ctypes.c_uint8 * cap)()
+    _check(lib().orcb_predicate_row_groups(f._h, stripe, ctypes.addressof(opts), ctypes.addressof(nodes), len(nodes),
+                                           ctypes.addressof(buf), cap, ctypes.byref(n), ctypes.byref(ev)))
+    if not ev.value:
+        return None
+    return [bool(buf[i]) for i in range(n.value)]
 
 
 def selection_plan(selection, stripe_rows, batch_size=8192):

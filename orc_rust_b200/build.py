@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liborc_b200.so")
-SOURCES = ["k_int.cu", "k_streams.cu", "k_strings.cu", "k_decompress.cu", "meta.cc", "tz.cc", "schema.cc", "plan.cc", "job.cc", "export.cc", "selection.cc", "c_api.cc"]
+SOURCES = ["k_int.cu", "k_streams.cu", "k_strings.cu", "k_decompress.cu", "meta.cc", "tz.cc", "schema.cc", "plan.cc", "job.cc", "export.cc", "selection.cc", "predicate.cc", "c_api.cc"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "-x", "cu",

@@ -8,6 +8,7 @@
 #include <memory>
 
 #include "job.h"
+#include "predicate.h"
 #include "kernels.h"
 #include "meta.h"
 
@@ -39,6 +40,10 @@ struct OrcbReader {
     // with_row_selection: per entry of `stripes`, whether a selection applies and the row ranges it yields
     bool has_selection = false;
     std::vector<std::pair<bool, std::vector<std::pair<uint32_t, uint32_t>>>> views;
+    // with_predicate: evaluated on the first next(), like the reference does while iterating
+    bool has_predicate = false, planned = true;
+    Predicate predicate;
+    std::vector<RowSelector> selectors;
 };
 
 template <typename F>
@@ -209,6 +214,52 @@ int orcb_reader_new_ex(OrcbFile* f, const OrcbReadOptions* opt, const OrcbRowSel
     });
 }
 
+int orcb_reader_build(OrcbFile* f, const OrcbReaderBuild* b, OrcbReader** out) {
+    return guarded([&] {
+        if (!f || !b || !out || (!b->selectors && b->n_selectors)) fail(ORCB_INVALID_ARGUMENT, "NULL argument");
+        auto r = std::make_unique<OrcbReader>();
+        r->file = f;
+        r->opt = ReadOptions::from_c(b->options);
+        apply_schema_hints(f->meta, r->opt, b->schema);
+        (void)project_columns(f->meta, r->opt);
+        r->stripes = select_stripes(f->meta, r->opt);
+        if (b->predicate || b->n_predicate_nodes) {
+            r->predicate = predicate_from_c(b->predicate, b->n_predicate_nodes);
+            r->has_predicate = true;
+        }
+        if (b->has_selection)
+            for (uint32_t i = 0; i < b->n_selectors; i++) r->selectors.push_back({b->selectors[i].row_count, b->selectors[i].skip != 0});
+        r->has_selection = b->has_selection != 0;
+        if (!r->has_predicate && r->has_selection) {
+            std::vector<uint64_t> rows;
+            for (uint32_t s : r->stripes) rows.push_back(f->meta.stripes[s].rows);
+            r->views = selection_views(r->selectors, rows, r->opt.batch_size);
+        }
+        r->planned = !r->has_predicate;
+        *out = r.release();
+    });
+}
+
+int orcb_predicate_row_groups(OrcbFile* f, uint32_t stripe, const OrcbReadOptions* opt, const OrcbPredicateNode* predicate,
+                              uint32_t n_predicate_nodes, uint8_t* keep, size_t cap, size_t* n_groups, int* evaluated) {
+    return guarded([&] {
+        if (!f || !n_groups || !evaluated) fail(ORCB_INVALID_ARGUMENT, "NULL argument");
+        if (stripe >= f->meta.stripes.size()) fail(ORCB_INVALID_ARGUMENT, "stripe out of range");
+        const ReadOptions o = ReadOptions::from_c(opt);
+        const auto cols = project_columns(f->meta, o);
+        const Predicate p = predicate_from_c(predicate, n_predicate_nodes);
+        std::vector<uint8_t> filter;
+        bool ok = false;
+        (void)predicate_selection(f->meta, stripe, cols, p, &filter, &ok);
+        *evaluated = ok ? 1 : 0;
+        *n_groups = filter.size();
+        for (size_t i = 0; keep && i < filter.size() && i < cap; i++) keep[i] = filter[i];
+    });
+}
+
+uint64_t orcb_bloom_hash_long(int64_t value) { return bloom_hash_long(value); }
+uint64_t orcb_bloom_hash_bytes(const uint8_t* bytes, size_t len) { return bloom_hash_bytes(bytes, len); }
+
 int orcb_reader_new_with_selection(OrcbFile* f, const OrcbReadOptions* opt, const OrcbRowSelector* selectors, uint32_t n_selectors,
                                    OrcbReader** out) {
     return orcb_reader_new_ex(f, opt, selectors, n_selectors, 1, nullptr, out);
@@ -249,8 +300,48 @@ void orcb_reader_free(OrcbReader* r) { delete r; }
 
 uint64_t orcb_reader_total_row_count(const OrcbReader* r) { return r->file->meta.num_rows; }
 
+// with_predicate: the per-stripe verdicts, combined with the caller's selection (ArrowReader::try_advance_stripe)
+static void ensure_planned(OrcbReader* r) {
+    if (r->planned) return;
+    const auto cols = project_columns(r->file->meta, r->opt);
+    std::vector<uint64_t> rows;
+    std::vector<std::vector<RowSelector>> pred;
+    for (uint32_t s : r->stripes) {
+        rows.push_back(r->file->meta.stripes[s].rows);
+        pred.push_back(predicate_selection(r->file->meta, s, cols, r->predicate, nullptr, nullptr));
+    }
+    r->views = selection_views(r->selectors, rows, r->opt.batch_size, &pred, r->has_selection);
+    r->has_selection = true;  // from here on `views` says what every stripe yields
+    r->planned = true;
+}
+
+int orcb_reader_plan(OrcbReader* r, int32_t* applies, size_t cap_stripes, size_t* n_stripes, uint64_t* triples,
+                     size_t cap_triples, size_t* n_triples) {
+    return guarded([&] {
+        if (!r || !n_triples || !n_stripes) fail(ORCB_INVALID_ARGUMENT, "NULL argument");
+        ensure_planned(r);
+        *n_stripes = r->stripes.size();
+        size_t k = 0;
+        for (size_t s = 0; s < r->stripes.size(); s++) {
+            const bool restricted = r->has_selection && r->views[s].first;
+            if (applies && s < cap_stripes) applies[s] = restricted ? 1 : 0;
+            if (!restricted) continue;
+            for (auto& v : r->views[s].second) {
+                if (triples && k < cap_triples) {
+                    triples[3 * k] = s;
+                    triples[3 * k + 1] = v.first;
+                    triples[3 * k + 2] = v.second;
+                }
+                k++;
+            }
+        }
+        *n_triples = k;
+    });
+}
+
 static bool reader_advance(OrcbReader* r) {
     // returns false at end of stream
+    ensure_planned(r);
     while (!r->job || r->next_batch >= r->job->num_batches()) {
         r->job.reset();
         if (r->next_stripe >= r->stripes.size()) return false;

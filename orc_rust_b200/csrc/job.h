@@ -72,8 +72,10 @@ struct RowSelector {
 // The batches each stripe yields under a row selection: restates RowSelection::from(Vec) (:466-482), split_off
 // (:278-320), ArrowReader::try_advance_stripe (src/arrow_reader.rs:296-309) and next_with_row_selection.
 // out[i].first = false: the stripe is read without a selection (the selection was used up before it).
+// `predicate`: per stripe, the selection with_predicate derived (predicate.h); combined as `mine.and_then(predicate's)`.
 std::vector<std::pair<bool, std::vector<std::pair<uint32_t, uint32_t>>>> selection_views(
-    std::vector<RowSelector> selectors, const std::vector<uint64_t>& stripe_rows, uint64_t batch_size);
+    std::vector<RowSelector> selectors, const std::vector<uint64_t>& stripe_rows, uint64_t batch_size,
+    const std::vector<std::vector<RowSelector>>* predicate = nullptr, bool has_selection = true);
 
 // where one column of one stripe lands
 struct ColStripePlan {

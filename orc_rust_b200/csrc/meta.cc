@@ -1,5 +1,6 @@
 #include "meta.h"
 
+#include <algorithm>
 #include <cstring>
 
 #include "pb.h"
@@ -289,6 +290,211 @@ std::vector<std::vector<uint64_t>> FileMeta::read_row_index(const StripeInfo& si
             if (g.number == 1) PbCursor::packed_u64(g, pos);
         }
         out.push_back(std::move(pos));
+    }
+    return out;
+}
+
+// prost checks `string` fields while decoding; a bad one is a DecodeProto error
+static std::string pb_string(const PbField& f) {
+    if (f.wire != 2) fail(ORCB_DECODE_PROTO, "invalid wire type for a string field");
+    const uint8_t* p = f.data;
+    size_t i = 0, n = f.len;
+    while (i < n) {
+        const uint8_t b = p[i];
+        size_t need = 0;
+        uint32_t cp = 0;
+        if (b < 0x80) { i++; continue; }
+        if (b >= 0xc2 && b <= 0xdf) { need = 1; cp = b & 0x1f; }
+        else if (b >= 0xe0 && b <= 0xef) { need = 2; cp = b & 0x0f; }
+        else if (b >= 0xf0 && b <= 0xf4) { need = 3; cp = b & 0x07; }
+        else fail(ORCB_DECODE_PROTO, "invalid string value: data is not UTF-8 encoded");
+        for (size_t k = 1; k <= need; k++) {
+            if (i + k >= n || (p[i + k] & 0xc0) != 0x80) fail(ORCB_DECODE_PROTO, "invalid string value: data is not UTF-8 encoded");
+            cp = (cp << 6) | (p[i + k] & 0x3f);
+        }
+        if ((need == 2 && (cp < 0x800 || (cp >= 0xd800 && cp <= 0xdfff))) || (need == 3 && (cp < 0x10000 || cp > 0x10ffff)))
+            fail(ORCB_DECODE_PROTO, "invalid string value: data is not UTF-8 encoded");
+        i += need + 1;
+    }
+    return std::string((const char*)f.data, f.len);
+}
+static int64_t unzigzag(uint64_t v) { return (int64_t)(v >> 1) ^ -(int64_t)(v & 1); }
+static double pb_double(const PbField& f) {
+    if (f.wire != 1) fail(ORCB_DECODE_PROTO, "invalid wire type for a double field");
+    double d;
+    memcpy(&d, &f.value, 8);
+    return d;
+}
+static void want_wire(const PbField& f, uint32_t wire) {
+    if (f.wire != wire) fail(ORCB_DECODE_PROTO, "invalid wire type in ColumnStatistics");
+}
+
+// TryFrom<&proto::ColumnStatistics> (src/statistics.rs:77-143)
+static ColumnStats parse_column_stats(const uint8_t* p, size_t n) {
+    ColumnStats st;
+    bool has[13] = {};
+    bool has_smin = false, has_smax = false;
+    std::string lower, upper;
+    std::vector<uint64_t> counts;
+    int64_t ts_min_utc = 0, ts_max_utc = 0, date_min = 0, date_max = 0, int_min = 0, int_max = 0;
+    PbCursor c(p, n);
+    PbField f, g;
+    while (c.next(f)) {
+        if (f.number >= 2 && f.number <= 9) want_wire(f, 2);
+        if (f.number < 13) has[f.number] = true;
+        PbCursor sc(f.data, f.len);
+        switch (f.number) {
+            case 1: want_wire(f, 0); st.number_of_values = f.value; break;
+            case 10: want_wire(f, 0); st.has_null = f.value != 0; break;
+            case 2:
+                while (sc.next(g)) {
+                    if (g.number >= 1 && g.number <= 3) want_wire(g, 0);
+                    if (g.number == 1) int_min = unzigzag(g.value);
+                    else if (g.number == 2) int_max = unzigzag(g.value);
+                }
+                break;
+            case 3:
+                while (sc.next(g)) {
+                    if (g.number == 1) st.dmin = pb_double(g);
+                    else if (g.number == 2) st.dmax = pb_double(g);
+                    else if (g.number == 3) (void)pb_double(g);
+                }
+                break;
+            case 4:
+                while (sc.next(g)) {
+                    if (g.number == 1) { st.smin = pb_string(g); has_smin = true; }
+                    else if (g.number == 2) { st.smax = pb_string(g); has_smax = true; }
+                    else if (g.number == 3) want_wire(g, 0);
+                    else if (g.number == 4) lower = pb_string(g);
+                    else if (g.number == 5) upper = pb_string(g);
+                }
+                break;
+            case 5:
+                while (sc.next(g))
+                    if (g.number == 1) PbCursor::packed_u64(g, counts);
+                break;
+            case 6:
+                while (sc.next(g)) {
+                    if (g.number == 1) st.smin = pb_string(g);
+                    else if (g.number == 2) st.smax = pb_string(g);
+                    else if (g.number == 3) (void)pb_string(g);
+                }
+                break;
+            case 7:
+                while (sc.next(g)) {
+                    if (g.number == 1 || g.number == 2) want_wire(g, 0);
+                    if (g.number == 1) date_min = (int32_t)unzigzag(g.value & 0xffffffffull);
+                    else if (g.number == 2) date_max = (int32_t)unzigzag(g.value & 0xffffffffull);
+                }
+                break;
+            case 9:
+                while (sc.next(g)) {
+                    if (g.number >= 1 && g.number <= 6) want_wire(g, 0);
+                    if (g.number == 3) ts_min_utc = unzigzag(g.value);
+                    else if (g.number == 4) ts_max_utc = unzigzag(g.value);
+                }
+                break;
+            default: break;
+        }
+    }
+    if (st.number_of_values == 0) return st;
+    if (has[2]) { st.kind = ST_INTEGER; st.imin = int_min; st.imax = int_max; }
+    else if (has[3]) st.kind = ST_DOUBLE;
+    else if (has[4]) {
+        st.kind = ST_STRING;
+        st.exact_min = has_smin;
+        st.exact_max = has_smax;
+        if (!has_smin) st.smin = lower;
+        if (!has_smax) st.smax = upper;
+    } else if (has[5]) {
+        st.kind = ST_BUCKET;
+        if (counts.empty()) throw ReferencePanic("index out of bounds: the len is 0 but the index is 0 (bucket statistics without a count)");
+        st.true_count = counts[0];
+    } else if (has[6]) st.kind = ST_DECIMAL;
+    else if (has[7]) { st.kind = ST_DATE; st.imin = date_min; st.imax = date_max; }
+    else if (has[8]) st.kind = ST_BINARY;
+    else if (has[9]) { st.kind = ST_TIMESTAMP; st.imin = ts_min_utc; st.imax = ts_max_utc; }
+    else if (has[12]) st.kind = ST_COLLECTION;
+    return st;
+}
+
+// parse_stripe_row_indexes + parse_bloom_filters for one column (src/row_index.rs:204-331)
+std::vector<RowGroupEntry> FileMeta::read_row_group_entries(const StripeFooter& sf, uint32_t column, bool* present) const {
+    std::vector<RowGroupEntry> out;
+    const StreamInfo* st = sf.find(column, S_ROW_INDEX);
+    *present = st != nullptr;
+    if (!st) return out;
+    {
+        std::vector<uint8_t> raw = host_decompress_section(compression, block_size, data + st->offset, st->length);
+        PbCursor c(raw.data(), raw.size());
+        PbField f, g;
+        while (c.next(f)) {
+            if (f.number != 1) continue;
+            want_wire(f, 2);
+            RowGroupEntry e;
+            PbCursor ec(f.data, f.len);
+            while (ec.next(g)) {
+                if (g.number == 2) {
+                    want_wire(g, 2);
+                    e.has_stats = true;
+                    e.stats = parse_column_stats(g.data, g.len);
+                }
+            }
+            out.push_back(std::move(e));
+        }
+    }
+    const StreamInfo* bs = sf.find(column, S_BLOOM_FILTER);
+    if (!bs) bs = sf.find(column, S_BLOOM_FILTER_UTF8);
+    if (!bs) return out;
+    std::vector<uint8_t> raw = host_decompress_section(compression, block_size, data + bs->offset, bs->length);
+    std::vector<BloomBits> filters;
+    PbCursor c(raw.data(), raw.size());
+    PbField f, g;
+    while (c.next(f)) {
+        if (f.number != 1) continue;
+        want_wire(f, 2);
+        BloomBits b;
+        uint32_t k = 0;
+        bool has_utf8 = false;
+        std::vector<uint64_t> from_bytes;
+        PbCursor bc(f.data, f.len);
+        while (bc.next(g)) {
+            if (g.number == 1) {
+                want_wire(g, 0);
+                k = (uint32_t)g.value;
+            } else if (g.number == 2) {
+                if (g.wire == 1) b.bitset.push_back(g.value);
+                else if (g.wire == 2) {
+                    if (g.len % 8) fail(ORCB_DECODE_PROTO, "buffer underflow in a packed fixed64 field");
+                    for (size_t i = 0; i < g.len; i += 8) {
+                        uint64_t w;
+                        memcpy(&w, g.data + i, 8);
+                        b.bitset.push_back(w);
+                    }
+                } else fail(ORCB_DECODE_PROTO, "invalid wire type for BloomFilter.bitset");
+            } else if (g.number == 3) {
+                want_wire(g, 2);
+                has_utf8 = true;
+                from_bytes.clear();
+                for (size_t i = 0; i < g.len; i += 8) {  // little-endian words, the last one zero padded
+                    uint64_t w = 0;
+                    memcpy(&w, g.data + i, std::min<size_t>(8, g.len - i));
+                    from_bytes.push_back(w);
+                }
+            }
+        }
+        if (!b.bitset.empty() && has_utf8) throw ReferencePanic("Bloom filter proto has both bitset and utf8bitset populated");
+        if (b.bitset.empty() && !has_utf8) continue;  // try_from_proto -> None, dropped by filter_map
+        if (b.bitset.empty()) b.bitset = std::move(from_bytes);
+        b.num_hash_functions = k ? k : 3;
+        filters.push_back(std::move(b));
+    }
+    if (filters.size() != out.size())
+        throw ReferencePanic("Bloom filter count mismatch: expected " + std::to_string(out.size()) + " but got " +
+                             std::to_string(filters.size()) + " for column " + std::to_string(column));
+    for (size_t i = 0; i < out.size(); i++) {
+        out[i].has_bloom = true;
+        out[i].bloom = std::move(filters[i]);
     }
     return out;
 }

@@ -56,6 +56,37 @@ struct ChunkInfo {
     int64_t dst_len;    // decompressed bytes if known on the host (original: = src_len; snappy: preamble), else -1
 };
 
+// ColumnStatistics of one row group (src/statistics.rs:21-143); `kind` is the TypeStatistics variant the reference
+// would build: none when number_of_values == 0, else the first sub-message present in its order of tests
+enum StatsKind : int { ST_NONE = 0, ST_INTEGER, ST_DOUBLE, ST_STRING, ST_BUCKET, ST_DECIMAL, ST_DATE, ST_BINARY, ST_TIMESTAMP, ST_COLLECTION };
+struct ColumnStats {
+    uint64_t number_of_values = 0;
+    bool has_null = false;
+    int kind = ST_NONE;
+    int64_t imin = 0, imax = 0;  // Integer, Date; Timestamp: minimumUtc / maximumUtc
+    double dmin = 0, dmax = 0;
+    std::string smin, smax;      // String: minimum / maximum, else lowerBound / upperBound; Decimal: minimum / maximum
+    bool exact_min = false, exact_max = false;
+    uint64_t true_count = 0;     // Bucket: count[0]
+};
+// BloomFilter (src/bloom_filter.rs:28-75)
+struct BloomBits {
+    uint32_t num_hash_functions = 3;
+    std::vector<uint64_t> bitset;
+};
+// RowGroupEntry (src/row_index.rs:33-61)
+struct RowGroupEntry {
+    bool has_stats = false;
+    ColumnStats stats;
+    bool has_bloom = false;
+    BloomBits bloom;
+};
+// A place where the reference panics instead of returning an error (asserts, slice indexing); surfaces as
+// ORCB_UNEXPECTED with the panic message
+struct ReferencePanic : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
 struct FileMeta {
     const uint8_t* data = nullptr;
     size_t len = 0;
@@ -74,6 +105,9 @@ struct FileMeta {
     // positions of every row-index entry of `column` in `stripe` (empty if no ROW_INDEX stream)
     std::vector<std::vector<uint64_t>> read_row_index(const StripeInfo& si, const StripeFooter& sf,
                                                       uint32_t column) const;
+    // statistics and Bloom filter of every row-index entry of `column`; *present = false when the stripe has no
+    // ROW_INDEX stream for it (src/row_index.rs:204-289).  Throws what the reference returns as an error.
+    std::vector<RowGroupEntry> read_row_group_entries(const StripeFooter& sf, uint32_t column, bool* present) const;
     std::vector<ChunkInfo> chunk_table(uint64_t stream_off, uint64_t stream_len) const;
 };
 

@@ -4,7 +4,8 @@
 namespace orcb {
 
 std::vector<std::pair<bool, std::vector<std::pair<uint32_t, uint32_t>>>> selection_views(
-    std::vector<RowSelector> raw, const std::vector<uint64_t>& stripe_rows, uint64_t batch_size) {
+    std::vector<RowSelector> raw, const std::vector<uint64_t>& stripe_rows, uint64_t batch_size,
+    const std::vector<std::vector<RowSelector>>* predicate, bool has_selection) {
     // RowSelection::from(Vec<RowSelector>): empty selectors dropped, neighbours of the same kind merged
     std::vector<RowSelector> sel;
     for (auto& r : raw) {
@@ -37,14 +38,57 @@ std::vector<std::pair<bool, std::vector<std::pair<uint32_t, uint32_t>>>> selecti
         self.swap(rest);
         return head;
     };
+    // RowSelection::and_then (src/row_selection.rs:401-463): `second` picks among the rows `first` selects
+    auto and_then = [](std::vector<RowSelector> first, std::vector<RowSelector> second) {
+        std::vector<RowSelector> outsel;
+        size_t a = 0, b = 0;
+        uint64_t to_skip = 0;
+        while (b < second.size()) {
+            if (a >= first.size()) throw ReferencePanic("selection exceeds the number of selected rows");
+            if (second[b].row_count == 0) { b++; continue; }
+            if (first[a].row_count == 0) { a++; continue; }
+            if (first[a].skip) {
+                to_skip += first[a].row_count;
+                a++;
+                continue;
+            }
+            const uint64_t k = std::min(first[a].row_count, second[b].row_count);
+            first[a].row_count -= k;
+            second[b].row_count -= k;
+            if (second[b].skip) {
+                to_skip += k;
+            } else {
+                if (to_skip) outsel.push_back({to_skip, true});
+                to_skip = 0;
+                outsel.push_back({k, false});
+            }
+        }
+        for (; a < first.size(); a++) {
+            if (first[a].row_count == 0) continue;
+            if (!first[a].skip) throw ReferencePanic("selection contains less than the number of selected rows");
+            to_skip += first[a].row_count;
+        }
+        if (to_skip) outsel.push_back({to_skip, true});
+        return outsel;
+    };
     std::vector<std::pair<bool, std::vector<std::pair<uint32_t, uint32_t>>>> out;
-    for (uint64_t rows : stripe_rows) {
+    for (size_t sidx = 0; sidx < stripe_rows.size(); sidx++) {
+        const uint64_t rows = stripe_rows[sidx];
         std::vector<std::pair<uint32_t, uint32_t>> views;
-        if (total(sel) == 0) {  // arrow_reader.rs:298: a used-up selection no longer restricts anything
+        // ArrowReader::try_advance_stripe (src/arrow_reader.rs:256-309): the predicate's selection for this stripe,
+        // then the caller's while it still has rows (a used-up selection no longer restricts anything)
+        bool applies = predicate != nullptr;
+        std::vector<RowSelector> s;
+        if (predicate) s = (*predicate)[sidx];
+        if (has_selection && total(sel) > 0) {
+            std::vector<RowSelector> mine = split_off(sel, rows);
+            s = predicate ? and_then(std::move(mine), std::move(s)) : std::move(mine);
+            applies = true;
+        }
+        if (!applies) {
             out.emplace_back(false, views);
             continue;
         }
-        const std::vector<RowSelector> s = split_off(sel, rows);
         // NaiveStripeDecoder::next / next_with_row_selection.  A selector is left behind only once a single step has
         // covered its whole row_count, so a select longer than the batch size keeps yielding batches (kept as is)
         uint64_t index = 0;

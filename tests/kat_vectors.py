@@ -135,3 +135,78 @@ TS_SCHEMA = [
       _D("-2198229903.899600000"), _D("-2198229903.899500000"), _D("-2198229903.899400000"), _D("-2198229903.899300000"),
       _D("-2198229903.899200000"), _D("-2198229903.899100000"), _D("-2198229903.899000000")]),
 ]
+
+
+# ---- predicate pushdown --------------------------------------------------------------------------------------------
+# tests/integration/main.rs:366-487 (bloom_filter_predicate_prunes): predicate -> rows read out of bloom_filter.orc (204)
+# predicates as the oracle takes them: ("cmp", column, op, (value type, value))
+BLOOM_FILTER_PRUNES = [
+    (("cmp", "id", "eq", ("Int32", 2)), 0),
+    (("cmp", "id", "eq", ("Int32", 3)), 204),
+    (("cmp", "name", "eq", ("Utf8", "beta")), 0),
+    (("cmp", "name", "eq", ("Utf8", "alpha")), 204),
+    (("cmp", "score", "eq", ("Float64", 2.0)), 0),
+    (("cmp", "score", "eq", ("Float64", 1.0)), 204),
+    (("cmp", "event_date", "eq", ("Int32", 19359)), 0),    # 2023-01-02
+    (("cmp", "event_date", "eq", ("Int32", 19358)), 204),  # 2023-01-01
+    (("and", [("cmp", "flag", "eq", ("Boolean", True)), ("cmp", "id", "eq", ("Int32", 2))]), 0),
+    (("cmp", "data", "eq", ("Utf8", chr(2))), 0),
+    (("cmp", "data", "eq", ("Utf8", chr(1))), 204),
+    (("cmp", "dec", "eq", ("Utf8", "2.22")), 0),
+    (("cmp", "dec", "eq", ("Utf8", "1.11")), 204),
+]
+
+# src/row_group_filter.rs:576-1350 (unit tests): row groups as (number_of_values, has_null, (min, max) | None, values in
+# the Bloom filter | None) of an int column "age", predicate, expected verdicts (None = Err)
+def _age(v):
+    return ("Int32", v)
+ROW_GROUP_FILTER = [
+    ("gt :682", [(5000, False, (18, 25), None), (5000, False, (26, 65), None)], ("cmp", "age", "gt", _age(20)), [True, True]),
+    ("gte :700", [(5000, False, (18, 25), None), (5000, False, (26, 65), None)], ("cmp", "age", "ge", _age(30)), [False, True]),
+    ("lt :718", [(5000, False, (18, 25), None), (5000, False, (26, 65), None)], ("cmp", "age", "lt", _age(30)), [True, True]),
+    ("lte :736", [(5000, False, (18, 25), None), (5000, False, (26, 65), None)], ("cmp", "age", "le", _age(20)), [True, False]),
+    ("eq :754", [(5000, False, (18, 25), None), (5000, False, (26, 65), None)], ("cmp", "age", "eq", _age(20)), [True, False]),
+    ("ne :772", [(5000, False, (18, 25), None), (5000, False, (26, 65), None)], ("cmp", "age", "ne", _age(20)), [True, True]),
+    ("ne single value :813", [(1000, False, (20, 20), None)], ("cmp", "age", "ne", _age(20)), [False]),
+    ("bloom rejects :837", [(None, None, None, [10])], ("cmp", "age", "eq", _age(20)), [False]),
+    ("stats before bloom :875", [(1000, False, (100, 200), [50])], ("cmp", "age", "eq", _age(50)), [False]),
+    ("and :892", [(5000, False, (18, 25), None), (5000, False, (26, 65), None)],
+     ("and", [("cmp", "age", "ge", _age(20)), ("cmp", "age", "le", _age(30))]), [True, True]),
+    ("or :914", [(5000, False, (18, 25), None), (5000, False, (26, 65), None)],
+     ("or", [("cmp", "age", "lt", _age(20)), ("cmp", "age", "gt", _age(30))]), [True, True]),
+    ("is_null :974", [(4000, True, (18, 25), None), (5000, False, (26, 65), None)], ("is_null", "age"), [True, False]),
+    ("is_not_null :1025", [(5000, False, (18, 25), None), (0, True, None, None)], ("is_not_null", "age"), [True, False]),
+    ("missing column :1041", [(5000, False, (18, 25), None)], ("cmp", "nonexistent", "gt", _age(10)), None),
+    ("not is_null :1093", [(500, True, (18, 25), None)], ("not", ("is_null", "age")), [True]),
+    ("not is_not_null :1149", [(4000, True, (18, 25), None), (5000, False, (26, 65), None)], ("not", ("is_not_null", "age")), [True, False]),
+    ("not gt :1185", [(1000, False, (0, 10), None)], ("not", ("cmp", "age", "gt", _age(5))), [True]),
+    ("not and :1241", [(1000, False, (0, 10), None), (1000, False, (20, 30), None)],
+     ("not", ("and", [("cmp", "age", "ge", _age(15)), ("cmp", "age", "le", _age(25))])), [True, True]),
+    ("not or :1300", [(1000, False, (0, 5), None), (1000, False, (5, 15), None)],
+     ("not", ("or", [("cmp", "age", "lt", _age(10)), ("cmp", "age", "gt", _age(30))])), [False, True]),
+    ("not not :1341", [(1000, False, (0, 10), None)], ("not", ("not", ("cmp", "age", "gt", _age(5)))), [True]),
+]
+
+# src/row_group_filter.rs:1355-1470: (lower, upper, op, value, exact_min, exact_max) -> keep
+STRING_COMPARISON = [
+    ("a", "c", "eq", "b", True, True, True), ("a", "c", "eq", "d", True, True, False), ("a", "c", "eq", "a", True, True, True),
+    ("a", "c", "eq", "c", True, True, True), ("a", "c", "eq", "a", False, True, False), ("a", "c", "eq", "c", True, False, False),
+    ("a", "c", "lt", "b", True, True, True), ("d", "e", "lt", "b", True, True, False), ("a", "c", "lt", "a", True, True, False),
+    ("a", "c", "lt", "a", False, True, False), ("a", "c", "gt", "b", True, True, True), ("a", "b", "gt", "c", True, True, False),
+    ("a", "c", "gt", "c", True, True, False), ("a", "c", "gt", "c", True, False, False), ("a", "c", "ne", "b", True, True, True),
+    ("a", "a", "ne", "a", True, True, False), ("a", "c", "le", "b", True, True, True),
+]
+
+# src/row_selection.rs:636-710: (verdicts, stride, rows) -> selectors (skip, count)
+FROM_ROW_GROUP_FILTER = [
+    ([False, True, False], 10000, 30000, [(True, 10000), (False, 10000), (True, 10000)]),
+    ([True, True, True], 10000, 30000, [(False, 30000)]),
+    ([False, False, False], 10000, 30000, [(True, 30000)]),
+    ([False, False, True, True, False], 10000, 50000, [(True, 20000), (False, 20000), (True, 10000)]),
+    ([True, False], 10000, 25000, [(False, 10000), (True, 15000)]),
+    ([], 10000, 123, [(True, 123)]),
+]
+# src/row_selection.rs:582-603: first, second -> first.and_then(second)
+AND_THEN = [
+    ([(True, 5), (False, 10), (True, 5)], [(True, 2), (False, 5), (True, 3)], [(True, 7), (False, 5), (True, 8)]),
+]

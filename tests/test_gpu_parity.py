@@ -515,6 +515,84 @@ def test_row_selection(ob, tmp_path):
     assert narrow.counters()["segments"] * 8 < full.counters()["segments"], (narrow.counters(), full.counters())
 
 
+# ---- predicate pushdown (ArrowReaderBuilder::with_predicate) --------------------------------------------------
+def test_predicate_pushdown(ob, tmp_path):
+    """Batches under a predicate (alone and with a row selection) equal the oracle's restatement of the reference's
+    row-group pruning, on the reference's own file and on generated files with Bloom filters; pruned row groups are
+    not decoded (fewer segments planned)."""
+    import random
+    import zlib
+    import pyarrow.orc as paorc
+    from oracle import orc_oracle as oo
+    import test_predicate as tp
+
+    def check(path, pred, what, sel=None, batch_size=8192, columns=None):
+        data = open(path, "rb").read()
+        of = oo.OracleFile(data)
+        try:
+            exp = of.read(batch_size=batch_size, columns=columns, selection=sel, predicate=pred)
+        except oo.OracleError as e:
+            assert "panic" in str(e), what
+            exp = None
+        b = ob.ArrowReaderBuilder.try_new(data).with_predicate(tp.to_api(ob, pred)).with_batch_size(batch_size)
+        if sel is not None:
+            b = b.with_row_selection(sel)
+        if columns:
+            b = b.with_projection(columns)
+        reader = b.build()
+        if exp is None:
+            with pytest.raises(ob.OrcError):
+                list(reader)
+            return None
+        got = list(reader)
+        assert [x.num_rows for x in got] == [x.num_rows for x in exp], what
+        for i, (g, e) in enumerate(zip(got, exp)):
+            assert g.schema.names == e.schema.names, what
+            assert g.equals(e), f"{what}: batch {i} differs"
+            for c in range(g.num_columns):
+                assert g.column(c).null_count == e.column(c).null_count, f"{what}: null count of batch {i} col {c}"
+        return sum(x.num_rows for x in got), reader.counters()
+
+    # tests/integration/main.rs:163-243 on the reference's file: int1 = 300 * row, string1 = hex(10 * row), stride 1000
+    pp = os.path.join(GOLDEN, "ref_integration", "TestOrcFile.testPredicatePushdown.orc")
+    rows_all, c_all = check(pp, ("cmp", "int1", "gt", ("Int32", 2000)), "gt 2000")
+    assert rows_all == 3500
+    rows, c = check(pp, ("and", [("cmp", "int1", "ge", ("Int32", 1000)), ("cmp", "int1", "le", ("Int32", 5000))]), "range")
+    assert rows == 1000 and c["segments"] < c_all["segments"]
+    rows, _ = check(pp, ("cmp", "int1", "eq", ("Int32", 600000)), "eq in the third group")
+    assert rows == 1000
+    rows, _ = check(pp, ("cmp", "int1", "lt", ("Int32", 0)), "nothing")
+    assert rows == 0
+    check(pp, ("cmp", "int1", "eq", ("Int32", 3000)), "batch smaller than a group", batch_size=300)
+    check(pp, ("cmp", "string1", "ge", ("Utf8", "5")), "strings")
+    check(pp, ("cmp", "int1", "gt", ("Utf8", "x")), "type mismatch reads everything")
+    check(pp, ("cmp", "int1", "gt", ("Int32", 600000)), "projection without the column", columns=["string1"])
+    check(pp, ("cmp", "int1", "ge", ("Int32", 300000)), "with a selection", sel=[(True, 500), (False, 2500)], batch_size=1000)
+
+    files = []
+    for name, n, kw in [("plain", 12_500, dict(compression="uncompressed", row_index_stride=1000)),
+                        ("snappy_bloom", 9_000, dict(compression="snappy", row_index_stride=2000,
+                                                     bloom_filter_columns=[1, 2, 3, 5, 6, 7, 8])),
+                        ("lz4_stripes", 30_000, dict(compression="lz4", row_index_stride=1000, stripe_size=64 * 1024,
+                                                     bloom_filter_columns=[2, 6], bloom_filter_fpp=0.01))]:
+        path = str(tmp_path / (name + ".orc"))
+        paorc.write_table(tp._table(n, zlib.crc32(name.encode())), path, **kw)
+        files.append(path)
+    rng = random.Random(21)
+    pruned = 0
+    for path in files:
+        stripes = [s.number_of_rows for s in oo.OracleFile(open(path, "rb").read()).stripes]
+        for k in range(14):
+            pred = tp._random_predicate(rng)
+            sel = None
+            if rng.random() < 0.3:
+                sel = [(rng.random() < 0.5, rng.choice([10, 999, 1000, 4000, 20000])) for _ in range(rng.randrange(1, 5))]
+            r = check(path, pred, f"{os.path.basename(path)}#{k} {pred} {sel}", sel=sel, batch_size=rng.choice([1000, 2000, 8192]))
+            pruned += r is not None and sel is None and r[0] < sum(stripes)
+    assert pruned >= 5
+
+
+
 # ---- corrupted inputs: same verdict as the oracle, same bytes whenever both still decode ------------------
 def _mutations(data0: bytes, lo: int, hi: int, seed: int, count: int):
     import random
