@@ -5,7 +5,7 @@ namespace orcb {
 
 // ------------------------------------------------------------------------------------------------
 // Compression chunks (src/compression.rs:113-123, 244-275): original chunks are copied, Snappy and LZ4
-// blocks are decoded by one warp per chunk: lane 0 walks the tags, all lanes move the bytes.
+// blocks are decoded by one warp per chunk.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void warp_copy_fwd(uint8_t* dst, const uint8_t* src, uint32_t n, int lane) {
     if (n < 256) {
@@ -45,8 +45,169 @@ __device__ __forceinline__ void warp_copy_match(uint8_t* out, uint32_t o, uint32
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Snappy, 32 input positions at a time.  An element (a literal or a back-reference) is 2 or 3 input bytes on
+// average, so a serial tag loop spends a whole warp on ~6 bytes of output per step.  Here every lane decodes the
+// element that WOULD start at its byte of a 32-byte input window; the elements that really start there are the
+// chain 0 -> next[0] -> next[next[0]] .., found by pointer jumping over the lanes (4 rounds, at most 16 elements of
+// >= 2 bytes fit).  A warp scan of their output lengths places them, and the bytes are then produced 32 at a time,
+// one output byte per lane, whichever element it belongs to:
+//   * literal bytes come from the input, bytes of a back-reference whose source lies before this window's output
+//     come from the output already written (a source shorter than the copy repeats, i % dist);
+//   * a back-reference into this window's own output waits for the pass above, then is copied by the whole warp,
+//     in order.
+// A chunk is one serial chain of windows, so its time is windows x latency of one window, and a kernel of a few
+// thousand chunks is as slow as its slowest chunk.  The round trips through global memory are therefore kept off the
+// chain: every output byte also goes into a ring of the last SW_HIST bytes in shared memory, where nearly all
+// back-references (and all that point into the current window) find their source.
+// Anything out of the ordinary (a header or literal that crosses the end of the input, a distance of zero or
+// beyond the output so far, output past the announced length) leaves the window untouched and returns false: the
+// serial loop takes over from the same position and reports the error exactly as it always did.
+// ------------------------------------------------------------------------------------------------
+struct SnappyWin {
+    uint32_t out_off[32];  // where the element's output starts, relative to the window's first output byte
+    uint32_t src[32];      // literal: input offset of its first byte; back-reference: distance
+    uint32_t info[32];     // output length | literal << 31 | into-this-window << 30
+};
+constexpr uint32_t SW_LITERAL = 1u << 31, SW_DEPENDENT = 1u << 30, SW_LEN = SW_DEPENDENT - 1;
+constexpr uint32_t SW_LONG_LITERAL = 128;  // a literal this long ends its window and is copied word-wise
+constexpr uint32_t SW_HIST = 4096;         // bytes of recent output each warp keeps in shared memory (power of two)
+
+__device__ __forceinline__ bool snappy_window(const uint8_t* __restrict__ s, uint32_t n, uint8_t* d, uint64_t ulen, uint32_t& p,
+                                              uint32_t& o, SnappyWin& w, uint8_t* hist, int lane) {
+    // bytes q .. q+4 of the input for q = p + lane, out of ten aligned words
+    const uintptr_t a0 = (uintptr_t)(s + p);
+    const uint32_t* wp = (const uint32_t*)(a0 & ~(uintptr_t)3);
+    const uint32_t word = lane < 10 ? wp[lane] : 0u;
+    const uint32_t b = (uint32_t)(a0 & 3) + (uint32_t)lane;
+    const uint32_t w0 = __shfl_sync(FULL, word, b >> 2), w1 = __shfl_sync(FULL, word, (b >> 2) + 1);
+    const uint32_t lo = __funnelshift_r(w0, w1, (b & 3) * 8);  // bytes 0..3
+    const uint32_t b4 = (w1 >> ((b & 3) * 8)) & 0xffu;          // byte 4
+    const uint32_t q = p + (uint32_t)lane;
+    const uint32_t tag = lo & 0xffu, t = tag & 3u;
+    uint32_t hdr, len, src;
+    bool lit = false;
+    if (t == 0) {
+        lit = true;
+        len = tag >> 2;
+        hdr = 1;
+        if (len >= 60) {
+            const uint32_t extra = len - 59;  // 1..4 length bytes, little-endian
+            hdr += extra;
+            const uint32_t raw = (lo >> 8) | (b4 << 24);
+            len = extra == 4 ? raw : raw & ((1u << (8 * extra)) - 1u);
+        }
+        len += 1;
+        src = q + hdr;
+    } else if (t == 1) {
+        hdr = 2;
+        len = 4 + ((tag >> 2) & 7u);
+        src = ((tag >> 5) << 8) | ((lo >> 8) & 0xffu);
+    } else if (t == 2) {
+        hdr = 3;
+        len = 1 + (tag >> 2);
+        src = (lo >> 8) & 0xffffu;
+    } else {
+        hdr = 5;
+        len = 1 + (tag >> 2);
+        src = (lo >> 8) | (b4 << 24);
+    }
+    // input bytes the element takes; a lane past the end of the input starts nothing
+    const bool inside = q < n;
+    const uint64_t adv64 = (uint64_t)hdr + (lit ? len : 0u);
+    const bool sane = inside && len != 0 && (uint64_t)q + adv64 <= n;
+    const uint32_t nxt = sane ? (uint32_t)min((uint64_t)lane + adv64, (uint64_t)32) : 32u;
+    // the chain of real element starts
+    uint32_t reach = 1u, jump = nxt;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        reach |= __reduce_or_sync(FULL, (((reach >> lane) & 1u) && jump < 32u) ? (1u << jump) : 0u);
+        const uint32_t j2 = __shfl_sync(FULL, jump, jump & 31u);
+        jump = jump < 32u ? j2 : 32u;
+    }
+    const bool mine = ((reach >> lane) & 1u) && inside;
+    const uint32_t mask = __ballot_sync(FULL, mine);
+    // place the output
+    const uint32_t olen = mine ? len : 0u;
+    const uint32_t incl = warp_incl_scan(mine && sane ? olen : 0u, lane);
+    const uint32_t excl = incl - (mine && sane ? olen : 0u);
+    const uint32_t total = __shfl_sync(FULL, incl, 31);
+    const uint64_t oo = (uint64_t)o + excl;
+    bool bad = mine && (!sane || oo + len > ulen || (!lit && (src == 0 || (uint64_t)src > oo)));
+    if (__any_sync(FULL, bad)) return false;
+    // a back-reference reads [oo - dist, oo - dist + min(len, dist)); it depends on this window when that ends past o
+    const bool dep = mine && !lit && excl + min(len, src) > src;
+    const int last = 31 - __clz(mask);
+    const bool long_lit = lit && len >= SW_LONG_LITERAL;  // only possible for the window's last element
+    const uint32_t rank = __popc(mask & ((1u << lane) - 1u));
+    if (mine) {
+        w.out_off[rank] = excl;
+        w.src[rank] = src;
+        w.info[rank] = len | (lit ? SW_LITERAL : 0u) | ((dep || long_lit) ? SW_DEPENDENT : 0u);
+    }
+    __syncwarp();
+    const uint32_t depmask = __ballot_sync(FULL, dep);
+    const uint32_t long_len = __shfl_sync(FULL, long_lit && mine ? len : 0u, last);
+    uint8_t* const dw = d + o;
+    // pass 1: one output byte per lane
+    const uint32_t body = total - long_len;
+    for (uint32_t v0 = 0; v0 < body; v0 += 32) {
+        const uint32_t starts = __reduce_or_sync(FULL, (mine && excl >= v0 && excl < v0 + 32u) ? (1u << (excl - v0)) : 0u);
+        const uint32_t before = __popc(__ballot_sync(FULL, mine && excl < v0));
+        const uint32_t v = v0 + (uint32_t)lane;
+        if (v < body) {
+            const uint32_t r = before + __popc(starts & (0xffffffffu >> (31 - lane))) - 1u;
+            const uint32_t inf = w.info[r];
+            if (!(inf & SW_DEPENDENT)) {
+                const uint32_t k = v - w.out_off[r], sv = w.src[r];
+                uint8_t byte;
+                if (inf & SW_LITERAL) {
+                    byte = s[sv + k];
+                } else {
+                    const uint32_t kk = k < sv ? k : k % sv;
+                    const uint32_t a = o + v - k - sv + kk;  // output position of the source byte, < o
+                    // the ring still holds it unless this window's own output has come round to its slot
+                    byte = (o + total - a <= SW_HIST) ? hist[a & (SW_HIST - 1)] : d[a];
+                }
+                hist[(o + v) & (SW_HIST - 1)] = byte;
+                dw[v] = byte;
+            }
+        }
+    }
+    __syncwarp();
+    // pass 2: what reads this window's own output, in order
+    uint32_t dm = depmask;
+    while (dm) {
+        const int l = __ffs(dm) - 1;
+        dm &= dm - 1;
+        const uint32_t e_off = __shfl_sync(FULL, excl, l), e_len = __shfl_sync(FULL, len, l), e_dist = __shfl_sync(FULL, src, l);
+        // its source starts less than 64 bytes before the window: all of it is in the ring, and none of it is
+        // written by this copy (a source shorter than the copy repeats)
+        const uint32_t eo = o + e_off;
+        for (uint32_t i = lane; i < e_len; i += 32) {
+            const uint32_t kk = i < e_dist ? i : i % e_dist;
+            const uint8_t byte = hist[(eo - e_dist + kk) & (SW_HIST - 1)];
+            hist[(eo + i) & (SW_HIST - 1)] = byte;
+            d[eo + i] = byte;
+        }
+        __syncwarp();
+    }
+    if (long_len) {
+        const uint32_t e_off = __shfl_sync(FULL, excl, last), e_src = __shfl_sync(FULL, src, last);
+        warp_copy_fwd(dw + e_off, s + e_src, long_len, lane);
+        for (uint32_t i = (long_len > SW_HIST ? long_len - SW_HIST : 0u) + lane; i < long_len; i += 32)
+            hist[(o + e_off + i) & (SW_HIST - 1)] = s[e_src + i];
+        __syncwarp();
+    }
+    p += __shfl_sync(FULL, (uint32_t)min((uint64_t)lane + adv64, (uint64_t)0xffffffffu), last);
+    o += total;
+    return true;
+}
+
 __global__ void __launch_bounds__(128) k_decompress(const ChunkDesc* __restrict__ chunks, uint32_t nchunks, uint32_t* err,
                                                     uint32_t* out_lens) {
+    __shared__ SnappyWin win_all[4];
+    __shared__ uint8_t hist_all[4][SW_HIST];
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (warp >= nchunks) return;
     const ChunkDesc& c = chunks[warp];
@@ -71,6 +232,11 @@ __global__ void __launch_bounds__(128) k_decompress(const ChunkDesc* __restrict_
             if (b < 0x80) break;
         }
         if (!fail && ulen > c.dst_cap) fail = ORCB_BUILD_SNAPPY_DECODER;
+        // windows of 32 input bytes while all is well; the serial loop below finishes (and reports) the rest
+        if (!fail) {
+            SnappyWin& w = win_all[threadIdx.x >> 5];
+            while (p < n && snappy_window(s, n, d, ulen, p, o, w, hist_all[threadIdx.x >> 5], lane)) __syncwarp();
+        }
         while (!fail && p < n) {
             const uint32_t tag = s[p++];
             const uint32_t t = tag & 3;
