@@ -648,8 +648,24 @@ int orcb_decompress_stream(int device, int compression_kind, const uint8_t* in, 
             d.codec = chunks[i].original ? 0 : (uint8_t)compression_kind;
         }
         if (!chunks.empty()) CU(cudaMemcpy(ddesc.p, descs.data(), descs.size() * sizeof(ChunkDesc), cudaMemcpyHostToDevice));
+        const bool timing = getenv("ORCB_STREAM_TIMING") != nullptr;  // kernel time to stderr (tools/snappy_probe.py)
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (timing) {
+            CU(cudaEventCreate(&e0));
+            CU(cudaEventCreate(&e1));
+            CU(cudaEventRecord(e0, 0));
+        }
         int rc = launch_decompress((ChunkDesc*)ddesc.p, (uint32_t)chunks.size(), (uint32_t*)sr.err.p, (uint32_t*)dlens.p, 0);
         if (rc) fail(ORCB_CUDA, cudaGetErrorString((cudaError_t)rc));
+        if (timing) {
+            float ms = 0;
+            CU(cudaEventRecord(e1, 0));
+            CU(cudaEventSynchronize(e1));
+            CU(cudaEventElapsedTime(&ms, e0, e1));
+            fprintf(stderr, "orcb_decompress_stream: %zu chunks, kernel %.3f ms\n", chunks.size(), ms);
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+        }
         sr.check();
         std::vector<uint32_t> lens(chunks.size());
         if (!chunks.empty()) CU(cudaMemcpy(lens.data(), dlens.p, chunks.size() * 4, cudaMemcpyDeviceToHost));
