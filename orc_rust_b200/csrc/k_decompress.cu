@@ -64,6 +64,16 @@ __device__ __forceinline__ void warp_copy_match(uint8_t* out, uint32_t o, uint32
 // beyond the output so far, output past the announced length) leaves the window untouched and returns false: the
 // serial loop takes over from the same position and reports the error exactly as it always did.
 // ------------------------------------------------------------------------------------------------
+// tag byte -> header bytes [0:3] | literal [3] | length is in the following bytes [4] | bytes of offset / length
+// that follow [5:8] | high offset bits of a 1-byte-offset copy [8:11] | length [16:]
+__device__ __forceinline__ uint32_t snappy_tag_entry(uint32_t tag) {
+    const uint32_t t = tag & 3u, l = tag >> 2;
+    if (t == 0) return l < 60 ? (1u | 8u | ((l + 1u) << 16)) : ((1u + (l - 59u)) | 8u | 16u | ((l - 59u) << 5));
+    if (t == 1) return 2u | (1u << 5) | ((tag >> 5) << 8) | ((4u + (l & 7u)) << 16);
+    if (t == 2) return 3u | (2u << 5) | ((l + 1u) << 16);
+    return 5u | (4u << 5) | ((l + 1u) << 16);
+}
+
 struct SnappyWin {
     uint32_t out_off[32];  // where the element's output starts, relative to the window's first output byte
     uint32_t src[32];      // literal: input offset of its first byte; back-reference: distance
@@ -74,7 +84,7 @@ constexpr uint32_t SW_LONG_LITERAL = 128;  // a literal this long ends its windo
 constexpr uint32_t SW_HIST = 4096;         // bytes of recent output each warp keeps in shared memory (power of two)
 
 __device__ __forceinline__ bool snappy_window(const uint8_t* __restrict__ s, uint32_t n, uint8_t* d, uint64_t ulen, uint32_t& p,
-                                              uint32_t& o, SnappyWin& w, uint8_t* hist, int lane) {
+                                              uint32_t& o, SnappyWin& w, uint8_t* hist, const uint32_t* lut, int lane) {
     // bytes q .. q+4 of the input for q = p + lane, out of ten aligned words
     const uintptr_t a0 = (uintptr_t)(s + p);
     const uint32_t* wp = (const uint32_t*)(a0 & ~(uintptr_t)3);
@@ -83,40 +93,22 @@ __device__ __forceinline__ bool snappy_window(const uint8_t* __restrict__ s, uin
     const uint32_t w0 = __shfl_sync(FULL, word, b >> 2), w1 = __shfl_sync(FULL, word, (b >> 2) + 1);
     const uint32_t lo = __funnelshift_r(w0, w1, (b & 3) * 8);  // bytes 0..3
     const uint32_t b4 = (w1 >> ((b & 3) * 8)) & 0xffu;          // byte 4
+    // what the tag says comes out of a 256-entry table (snappy_tag_entry): header bytes, literal or not, the length
+    // when the tag holds it, and how many of the following bytes are an offset or a length
+    const uint32_t e = lut[lo & 0xffu];
+    const uint32_t hdr = e & 7u, nbytes = (e >> 5) & 7u;
+    const bool lit = (e >> 3) & 1u;
+    const uint32_t raw = (lo >> 8) | (b4 << 24);
+    const uint32_t field = raw & __funnelshift_rc(0xffffffffu, 0u, 32u - 8u * nbytes);  // the low `nbytes` bytes
+    const uint32_t len = (e >> 16) + (((e >> 4) & 1u) ? field + 1u : 0u);             // long literals: length bytes + 1
     const uint32_t q = p + (uint32_t)lane;
-    const uint32_t tag = lo & 0xffu, t = tag & 3u;
-    uint32_t hdr, len, src;
-    bool lit = false;
-    if (t == 0) {
-        lit = true;
-        len = tag >> 2;
-        hdr = 1;
-        if (len >= 60) {
-            const uint32_t extra = len - 59;  // 1..4 length bytes, little-endian
-            hdr += extra;
-            const uint32_t raw = (lo >> 8) | (b4 << 24);
-            len = extra == 4 ? raw : raw & ((1u << (8 * extra)) - 1u);
-        }
-        len += 1;
-        src = q + hdr;
-    } else if (t == 1) {
-        hdr = 2;
-        len = 4 + ((tag >> 2) & 7u);
-        src = ((tag >> 5) << 8) | ((lo >> 8) & 0xffu);
-    } else if (t == 2) {
-        hdr = 3;
-        len = 1 + (tag >> 2);
-        src = (lo >> 8) & 0xffffu;
-    } else {
-        hdr = 5;
-        len = 1 + (tag >> 2);
-        src = (lo >> 8) | (b4 << 24);
-    }
-    // input bytes the element takes; a lane past the end of the input starts nothing
+    const uint32_t src = lit ? q + hdr : (field | (((e >> 8) & 7u) << 8));
+    // input bytes the element takes; a lane past the end of the input starts nothing.  A literal longer than the
+    // input is not sane, so the 32-bit sums below cannot wrap for the lanes that matter
     const bool inside = q < n;
-    const uint64_t adv64 = (uint64_t)hdr + (lit ? len : 0u);
-    const bool sane = inside && len != 0 && (uint64_t)q + adv64 <= n;
-    const uint32_t nxt = sane ? (uint32_t)min((uint64_t)lane + adv64, (uint64_t)32) : 32u;
+    const uint32_t adv = hdr + (lit ? len : 0u);
+    const bool sane = inside && len != 0 && (!lit || len <= n) && adv <= n - q;
+    const uint32_t nxt = sane ? min((uint32_t)lane + adv, 32u) : 32u;
     // the chain of real element starts
     uint32_t reach = 1u, jump = nxt;
 #pragma unroll
@@ -199,7 +191,7 @@ __device__ __forceinline__ bool snappy_window(const uint8_t* __restrict__ s, uin
             hist[(o + e_off + i) & (SW_HIST - 1)] = s[e_src + i];
         __syncwarp();
     }
-    p += __shfl_sync(FULL, (uint32_t)min((uint64_t)lane + adv64, (uint64_t)0xffffffffu), last);
+    p += __shfl_sync(FULL, (uint32_t)lane + adv, last);
     o += total;
     return true;
 }
@@ -208,6 +200,10 @@ __global__ void __launch_bounds__(128) k_decompress(const ChunkDesc* __restrict_
                                                     uint32_t* out_lens) {
     __shared__ SnappyWin win_all[4];
     __shared__ uint8_t hist_all[4][SW_HIST];
+    __shared__ uint32_t lut[256];
+    lut[threadIdx.x] = snappy_tag_entry(threadIdx.x);
+    lut[threadIdx.x + 128] = snappy_tag_entry(threadIdx.x + 128);
+    __syncthreads();
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (warp >= nchunks) return;
     const ChunkDesc& c = chunks[warp];
@@ -235,7 +231,7 @@ __global__ void __launch_bounds__(128) k_decompress(const ChunkDesc* __restrict_
         // windows of 32 input bytes while all is well; the serial loop below finishes (and reports) the rest
         if (!fail) {
             SnappyWin& w = win_all[threadIdx.x >> 5];
-            while (p < n && snappy_window(s, n, d, ulen, p, o, w, hist_all[threadIdx.x >> 5], lane)) __syncwarp();
+            while (p < n && snappy_window(s, n, d, ulen, p, o, w, hist_all[threadIdx.x >> 5], lut, lane)) __syncwarp();
         }
         while (!fail && p < n) {
             const uint32_t tag = s[p++];
