@@ -137,7 +137,22 @@ def cpu_run(files, steps, warmup, max_stripes=None):
     return dict(seconds=sum(times) / len(times), rows=rows, arrow_bytes=nbytes, cores=cores, stripes=len(tasks))
 
 
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to fd 1
+    when NCCL_DEBUG is set), so fd 1 is pointed at stderr for the whole run and the line goes to the real stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return real
+
+
+def _emit(real_stdout: int, line: dict):
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    real_stdout = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -174,7 +189,7 @@ def main():
                                        "the Rust reference cannot be built in this image)"},
             "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
-        print(json.dumps(line))
+        _emit(real_stdout, line)
         return
 
     import torch
@@ -324,7 +339,7 @@ def main():
         "gpu_launches": st["n_kernel_launches"] * args.steps,
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clk.summary(),
     }
-    print(json.dumps(line))
+    _emit(real_stdout, line)
     if world > 1:
         dist.destroy_process_group()
 
