@@ -303,3 +303,27 @@ def test_predicate_argument_checks(ob):
     fh = ob._File(path)
     rc = ob.lib().orcb_predicate_row_groups(fh._h, 0, None, ctypes.addressof(bad), 1, None, 0, ctypes.byref(n), ctypes.byref(ev))
     assert rc == 21  # InvalidArgument
+
+
+def test_reader_plan_with_byte_range_and_projection(ob, generated):
+    """The predicate is evaluated for the stripes the reader visits only (with_file_byte_range), over the projected
+    columns only: a predicate on a column left out of the projection keeps every stripe whole."""
+    path = generated[2]  # many small stripes
+    of = oo.OracleFile(open(path, "rb").read())
+    assert len(of.stripes) >= 4
+    mid = of.stripes[len(of.stripes) // 2].offset
+    end = of.stripes[-1].offset + 1
+    chosen = [i for i, s in enumerate(of.stripes) if mid <= s.offset < end]
+    rows = [of.stripes[i].number_of_rows for i in chosen]
+    pred = ("cmp", "l", "eq", ("Int64", 7))
+    for proj in (None, ["l", "s"], ["s", "t"]):
+        b = ob.ArrowReaderBuilder.try_new(path).with_file_byte_range(mid, end).with_predicate(to_api(ob, pred))
+        if proj:
+            b = b.with_projection(proj)
+        got = b.build().plan()
+        psel = [of.predicate_selection(i, pred, proj)[0] for i in chosen]
+        exp = oo.selection_views(None, rows, 8192, psel)
+        assert [None if p is None else [tuple(v) for v in p] for p in got] == \
+               [None if p is None else [tuple(map(int, v)) for v in p] for p in exp], proj
+        if proj == ["s", "t"]:  # "Column 'l' not found in schema": select_all for every stripe
+            assert all(p == [(0, r)] for p, r in zip(got, rows))
