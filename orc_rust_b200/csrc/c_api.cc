@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -388,6 +389,12 @@ static bool reader_advance(OrcbReader* r) {
             r->next_stripe++;
         }
         if (tasks.empty()) continue;  // only unselected stripes were left in this round
+        const bool timing = getenv("ORCB_READER_TIMING") != nullptr;  // host phases to stderr (tools/reader_probe.py)
+        auto now = [] { return std::chrono::steady_clock::now(); };
+        auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+            return std::chrono::duration<double, std::milli>(b - a).count();
+        };
+        const auto t0 = now();
         r->job = std::make_unique<Job>(std::move(tasks), r->opt);
         r->next_batch = 0;
         r->job->plan();
@@ -397,9 +404,15 @@ static bool reader_advance(OrcbReader* r) {
             r->segments_planned += st.n_segments;
             r->stripes_staged += st.n_stripes;
         }
+        const auto t1 = now();
         r->job->stage();
+        const auto t2 = now();
         r->job->launch();
+        const auto t3 = now();
         r->job->finish();
+        if (timing)
+            fprintf(stderr, "orcb reader: plan %.2f ms, stage %.2f ms, launch %.2f ms, finish %.2f ms\n", ms(t0, t1), ms(t1, t2),
+                    ms(t2, t3), ms(t3, now()));
     }
     return true;
 }

@@ -1,8 +1,98 @@
 // Job life cycle and execution: arenas, staging (H2D), the kernel launch sequence on two streams, completion and
 // error mapping, statistics.  Planning is in plan.cc, Arrow export in export.cc.
+#include <chrono>
+#include <cstdio>
+#include <map>
+#include <mutex>
+
 #include "job_internal.h"
 
 namespace orcb {
+
+// cudaHostAlloc takes 3-14 ms on a busy host, more than staging and decoding a 100 MB stripe: the small pinned buffers
+// the per-job metadata comes back in are kept and handed to the next job (power-of-two sizes, at most 64 MiB held)
+namespace {
+struct PinnedCache {
+    std::mutex mu;
+    std::multimap<size_t, void*> spare;
+    size_t held = 0;
+    void* get(size_t want, size_t* cap) {
+        size_t c = 4096;
+        while (c < want) c <<= 1;
+        *cap = c;
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            auto it = spare.find(c);
+            if (it != spare.end()) {
+                void* p = it->second;
+                spare.erase(it);
+                held -= c;
+                return p;
+            }
+        }
+        void* p = nullptr;
+        CUDA_OK(cudaHostAlloc(&p, c, cudaHostAllocDefault));
+        return p;
+    }
+    void put(void* p, size_t cap) {
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            if (held + cap <= (64u << 20)) {
+                spare.emplace(cap, p);
+                held += cap;
+                return;
+            }
+        }
+        cudaFreeHost(p);
+    }
+};
+PinnedCache& pinned_cache() {
+    static PinnedCache* c = new PinnedCache();  // never destroyed: buffers may come back while the process exits
+    return *c;
+}
+}  // namespace
+
+bool DeviceArenas::use_pool(int device) {
+    static std::mutex mu;
+    static std::map<int, bool> ready;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = ready.find(device);
+    if (it != ready.end()) return it->second;
+    bool ok = false;
+    const char* e = getenv("ORCB_SYNC_ALLOC");
+    if (!(e && e[0] == '1')) {
+        int supported = 0;
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetAttribute(&supported, cudaDevAttrMemoryPoolsSupported, device) == cudaSuccess && supported &&
+            cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;  // freed memory stays in the pool instead of going back to the driver at every sync
+            ok = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep) == cudaSuccess;
+        }
+        cudaGetLastError();
+    }
+    ready[device] = ok;
+    return ok;
+}
+
+void* DeviceArenas::alloc(size_t bytes, cudaStream_t st) {
+    void* p = nullptr;
+    if (pooled) CUDA_OK(cudaMallocAsync(&p, bytes, st));
+    else CUDA_OK(cudaMalloc(&p, bytes));
+    ptrs.push_back(p);
+    return p;
+}
+
+DeviceArenas::~DeviceArenas() {
+    int cur = 0;
+    const bool switched = cudaGetDevice(&cur) == cudaSuccess && cur != device && cudaSetDevice(device) == cudaSuccess;
+    for (void* p : ptrs) {
+        if (!p) continue;
+        if (pooled) cudaFreeAsync(p, nullptr);
+        else cudaFree(p);
+    }
+    if (switched) cudaSetDevice(cur);
+}
+
 
 Job::Job(std::vector<StripeTask> tasks, const ReadOptions& opt) : tasks_(std::move(tasks)), opt_(opt) {
     if (!tasks_.empty()) cols_ = project_columns(*tasks_[0].file, opt_);
@@ -42,11 +132,17 @@ void Job::restage() {
 }
 
 Job::~Job() {
+    // pooled memory does not wait for pending work when it is freed (cudaFree did): a job dropped between launch()
+    // and finish(), or while an end-to-end restage is in flight, drains its streams first
+    if (staged_) {
+        if (stream_) cudaStreamSynchronize(stream_);
+        if (aux_stream_) cudaStreamSynchronize(aux_stream_);
+    }
     for (auto& k : kstats_) {
         if (k.e0) cudaEventDestroy(k.e0);
         if (k.e1) cudaEventDestroy(k.e1);
     }
-    if (h_meta_) cudaFreeHost(h_meta_);
+    if (h_meta_) pinned_cache().put(h_meta_, h_meta_cap_);
     if (done_) cudaEventDestroy(done_);
     if (ev_fork_) cudaEventDestroy(ev_fork_);
     if (ev_join_) cudaEventDestroy(ev_join_);
@@ -73,6 +169,16 @@ uint64_t Job::reloc(uint64_t tagged) const {
 void Job::stage() {
     if (!planned_) plan();
     if (staged_) return;
+    const bool timing = getenv("ORCB_READER_TIMING") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto lap = [&](std::chrono::steady_clock::time_point& t) {
+        const auto n = now();
+        const double d = std::chrono::duration<double, std::milli>(n - t).count();
+        t = n;
+        return d;
+    };
+    auto tl = now();
+    double t_streams = 0, t_alloc = 0, t_host = 0, t_reloc = 0, t_copy = 0;
     CUDA_OK(cudaSetDevice(opt_.device));
     if (opt_.own_stream) {
         CUDA_OK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
@@ -84,29 +190,18 @@ void Job::stage() {
     CUDA_OK(cudaStreamCreateWithFlags(&aux_stream_, cudaStreamNonBlocking));
     CUDA_OK(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming));
+    t_streams = lap(tl);
     auto arenas = std::make_shared<DeviceArenas>();
     arenas->device = opt_.device;
-    for (int a = 1; a < 8; a++) {
-        if (size_[a] <= ARENA_PAD && a != AR_TMP) {
-            // still give kernels a valid base for empty arenas
-        }
-        void* p = nullptr;
-        CUDA_OK(cudaMalloc(&p, std::max<uint64_t>(size_[a], 256)));
-        arenas->ptrs.push_back(p);
-        base_[a] = (uint8_t*)p;
-    }
-    void* p = nullptr;
-    CUDA_OK(cudaMalloc(&p, std::max<uint64_t>(desc_bytes_, 256)));
-    arenas->ptrs.push_back(p);
-    d_desc_ = (uint8_t*)p;
-    CUDA_OK(cudaMalloc(&p, std::max<uint64_t>(state_bytes_, 256)));
-    arenas->ptrs.push_back(p);
-    d_state_ = (uint8_t*)p;
-    CUDA_OK(cudaMalloc(&p, std::max<uint64_t>(meta_bytes_, 256)));
-    arenas->ptrs.push_back(p);
-    d_meta_ = (uint8_t*)p;
-    CUDA_OK(cudaHostAlloc((void**)&h_meta_, std::max<uint64_t>(meta_bytes_, 256), cudaHostAllocDefault));
+    arenas->pooled = DeviceArenas::use_pool(opt_.device);
+    for (int a = 1; a < 8; a++) base_[a] = (uint8_t*)arenas->alloc(std::max<uint64_t>(size_[a], 256), stream_);
+    d_desc_ = (uint8_t*)arenas->alloc(std::max<uint64_t>(desc_bytes_, 256), stream_);
+    d_state_ = (uint8_t*)arenas->alloc(std::max<uint64_t>(state_bytes_, 256), stream_);
+    d_meta_ = (uint8_t*)arenas->alloc(std::max<uint64_t>(meta_bytes_, 256), stream_);
+    t_alloc = lap(tl);
+    h_meta_ = (uint8_t*)pinned_cache().get(std::max<uint64_t>(meta_bytes_, 256), &h_meta_cap_);
     dev_keepalive_ = arenas;
+    t_host = lap(tl);
 
     // relocate
     auto R = [&](uint64_t& v) { v = reloc(v); };
@@ -160,9 +255,14 @@ void Job::stage() {
     put(o_rep_, repacks_.data(), repacks_.size() * sizeof(RepackDesc));
     put(o_chunk_, chunks_.data(), chunks_.size() * sizeof(ChunkDesc));
     put(o_tz_, tz_blob_.data(), tz_blob_.size());
+    t_reloc = lap(tl);
     CUDA_OK(cudaMemcpyAsync(d_desc_, desc_blob_.data(), desc_blob_.size(), cudaMemcpyHostToDevice, stream_));
     for (auto& sc : stage_copies_)
         CUDA_OK(cudaMemcpyAsync(base_[AR_IN] + sc.dst_off, sc.src, sc.bytes, cudaMemcpyHostToDevice, stream_));
+    t_copy = lap(tl);
+    if (timing)
+        fprintf(stderr, "orcb stage: streams/events %.2f ms, device memory %.2f ms, pinned meta %.2f ms, descriptors %.2f ms (%zu KiB), "
+                        "copies issued %.2f ms\n", t_streams, t_alloc, t_host, t_reloc, desc_blob_.size() >> 10, t_copy);
     staged_ = true;
 }
 

@@ -171,7 +171,8 @@ class Job {
     uint64_t state_bytes_ = 0, o_cnt_ = 0, o_dstart_ = 0, o_mis_ = 0, o_jobstate_ = 0, o_nblocks_ = 0;
     // meta blob (device, zeroed per launch, copied to host at finish): err[], nulls[], ptr_table[], batch_base[]
     uint8_t* d_meta_ = nullptr;
-    uint8_t* h_meta_ = nullptr;  // pinned
+    uint8_t* h_meta_ = nullptr;  // pinned, from the process-wide cache of small pinned buffers (job.cc)
+    size_t h_meta_cap_ = 0;
     uint64_t meta_bytes_ = 0, o_err_ = 0, o_nulls_ = 0, o_ptrs_ = 0, o_bbase_ = 0;
     uint32_t n_nulls_ = 0;
 

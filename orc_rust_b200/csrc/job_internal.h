@@ -21,13 +21,19 @@ static const uint64_t ARENA_PAD = 256;            // slack so word-granular kern
 // ------------------------------------------------------------------------------------------------
 // device memory owned jointly by the job and by exported device batches
 // ------------------------------------------------------------------------------------------------
+// Device memory of one job.  Allocated from the device's stream-ordered pool (cudaMallocAsync) with the pool told to
+// keep what is freed, so that a reader that builds one job per group of stripes does not pay cudaMalloc / cudaFree
+// (and the device-wide synchronisation of cudaFree) for every group: 3 ms -> 0.3 ms per job.  As with any
+// stream-ordered allocator, memory goes back to the pool when the last holder lets go (the job, or the last
+// device-resident batch exported from it), and the holder's work on it must be complete by then.
+// ORCB_SYNC_ALLOC=1 selects plain cudaMalloc / cudaFree.
 struct DeviceArenas {
     int device = 0;
+    bool pooled = false;
     std::vector<void*> ptrs;
-    ~DeviceArenas() {
-        for (void* p : ptrs)
-            if (p) cudaFree(p);
-    }
+    static bool use_pool(int device);
+    void* alloc(size_t bytes, cudaStream_t st);
+    ~DeviceArenas();
 };
 
 struct HostOutput {
