@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <exception>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -42,6 +43,8 @@ struct OrcbReader {
     bool has_selection = false;
     std::vector<std::pair<bool, std::vector<std::pair<uint32_t, uint32_t>>>> views;
     // with_predicate: evaluated on the first next(), like the reference does while iterating
+    std::unique_ptr<Job> ahead;        // the next group of stripes, already launched
+    std::exception_ptr ahead_error;    // what starting it ran into; reported when its turn comes
     bool has_predicate = false, planned = true;
     Predicate predicate;
     std::vector<RowSelector> selectors;
@@ -340,12 +343,11 @@ int orcb_reader_plan(OrcbReader* r, int32_t* applies, size_t cap_stripes, size_t
     });
 }
 
-static bool reader_advance(OrcbReader* r) {
-    // returns false at end of stream
-    ensure_planned(r);
-    while (!r->job || r->next_batch >= r->job->num_batches()) {
-        r->job.reset();
-        if (r->next_stripe >= r->stripes.size()) return false;
+// The next group of stripes (at most max_stripes_per_launch, ~1 GiB of input) as a job that is planned, staged and
+// launched but not waited for; nullptr when no stripe is left.
+static std::unique_ptr<Job> reader_start_group(OrcbReader* r) {
+    for (;;) {
+        if (r->next_stripe >= r->stripes.size()) return nullptr;
         const uint32_t group = r->opt.max_stripes_per_launch ? r->opt.max_stripes_per_launch : 16;
         std::vector<StripeTask> tasks;
         uint64_t bytes = 0;
@@ -395,24 +397,50 @@ static bool reader_advance(OrcbReader* r) {
             return std::chrono::duration<double, std::milli>(b - a).count();
         };
         const auto t0 = now();
-        r->job = std::make_unique<Job>(std::move(tasks), r->opt);
-        r->next_batch = 0;
-        r->job->plan();
+        auto job = std::make_unique<Job>(std::move(tasks), r->opt);
+        job->plan();
         {
             OrcbJobStats st{};
-            r->job->stats(&st);
+            job->stats(&st);
             r->segments_planned += st.n_segments;
             r->stripes_staged += st.n_stripes;
         }
         const auto t1 = now();
-        r->job->stage();
+        job->stage();
         const auto t2 = now();
-        r->job->launch();
-        const auto t3 = now();
-        r->job->finish();
+        job->launch();
         if (timing)
-            fprintf(stderr, "orcb reader: plan %.2f ms, stage %.2f ms, launch %.2f ms, finish %.2f ms\n", ms(t0, t1), ms(t1, t2),
-                    ms(t2, t3), ms(t3, now()));
+            fprintf(stderr, "orcb reader: plan %.2f ms, stage %.2f ms, launch %.2f ms\n", ms(t0, t1), ms(t1, t2), ms(t2, now()));
+        return job;
+    }
+}
+
+// Makes r->job hold the group that r->next_batch indexes; false at end of stream.  While the caller consumes one
+// group, the next one is already copied and decoded on its own streams (ORCB_NO_PREFETCH=1 turns that off).  What goes
+// wrong while starting a group ahead of time is reported when that group's turn comes, after every batch before it,
+// as the reference reports a bad stripe only when it gets there.
+static bool reader_advance(OrcbReader* r) {
+    ensure_planned(r);
+    static const bool prefetch = !(getenv("ORCB_NO_PREFETCH") && getenv("ORCB_NO_PREFETCH")[0] == '1');
+    while (!r->job || r->next_batch >= r->job->num_batches()) {
+        r->job.reset();
+        if (r->ahead_error) {
+            std::exception_ptr e = r->ahead_error;
+            r->ahead_error = nullptr;
+            std::rethrow_exception(e);
+        }
+        if (!r->ahead) r->ahead = reader_start_group(r);
+        if (!r->ahead) return false;
+        r->job = std::move(r->ahead);
+        r->next_batch = 0;
+        if (prefetch) {  // planned and launched on the host while the device still works on r->job
+            try {
+                r->ahead = reader_start_group(r);
+            } catch (...) {
+                r->ahead_error = std::current_exception();
+            }
+        }
+        r->job->finish();
     }
     return true;
 }
