@@ -42,7 +42,7 @@ void Job::ensure_host_output() {
     auto ho = std::make_shared<HostOutput>();
     CUDA_OK(cudaSetDevice(opt_.device));
     const uint64_t out_bytes = std::max<uint64_t>(size_[AR_OUT], 256);
-    CUDA_OK(cudaHostAlloc((void**)&ho->out, out_bytes, cudaHostAllocDefault));
+    ho->out = (uint8_t*)pinned_get(out_bytes, &ho->out_cap);
     CUDA_OK(cudaMemcpyAsync(ho->out, base_[AR_OUT], out_bytes, cudaMemcpyDeviceToHost, stream_));
     // used part of the heap: max over dictionary columns of (ptr - heap_base + total)
     uint64_t heap_used = 0;
@@ -54,7 +54,7 @@ void Job::ensure_host_output() {
         if (p) heap_used = std::max<uint64_t>(heap_used, p - (uint64_t)(uintptr_t)base_[AR_HEAP] + (uint64_t)bb[cp.n_batches]);
     }
     if (heap_used) {
-        CUDA_OK(cudaHostAlloc((void**)&ho->heap, heap_used, cudaHostAllocDefault));
+        ho->heap = (uint8_t*)pinned_get(heap_used, &ho->heap_cap);
         CUDA_OK(cudaMemcpyAsync(ho->heap, base_[AR_HEAP], heap_used, cudaMemcpyDeviceToHost, stream_));
     }
     // direct strings alias the staged / decompressed DATA streams: bring those byte ranges back as well
@@ -65,7 +65,7 @@ void Job::ensure_host_output() {
         strs_bytes += (cp.str_data_len + 63) / 64 * 64;
     }
     if (strs_bytes) {
-        CUDA_OK(cudaHostAlloc((void**)&ho->strs, strs_bytes, cudaHostAllocDefault));
+        ho->strs = (uint8_t*)pinned_get(strs_bytes, &ho->strs_cap);
         for (auto& cp : colstripes_) {
             if (cp.str_slot < 0 || strcols_[cp.str_slot].mode != 0 || !cp.str_data_len) continue;
             CUDA_OK(cudaMemcpyAsync(ho->strs + cp.str_host_off, (const void*)(uintptr_t)reloc(cp.str_data), cp.str_data_len,

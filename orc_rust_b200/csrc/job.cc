@@ -9,16 +9,27 @@
 
 namespace orcb {
 
-// cudaHostAlloc takes 3-14 ms on a busy host, more than staging and decoding a 100 MB stripe: the small pinned buffers
-// the per-job metadata comes back in are kept and handed to the next job (power-of-two sizes, at most 64 MiB held)
+// pinned host buffers, kept between jobs (job_internal.h).  Sizes are rounded up to a power of two below 1 MiB and to a
+// multiple of 1/8 of the next lower power of two above, so a request finds a spare buffer at most 12.5 % larger
 namespace {
 struct PinnedCache {
     std::mutex mu;
     std::multimap<size_t, void*> spare;
-    size_t held = 0;
-    void* get(size_t want, size_t* cap) {
+    size_t held = 0, limit = 4096ull << 20;
+    PinnedCache() {
+        if (const char* e = getenv("ORCB_PINNED_CACHE_MB")) limit = (size_t)strtoull(e, nullptr, 10) << 20;
+    }
+    static size_t size_class(size_t want) {
         size_t c = 4096;
-        while (c < want) c <<= 1;
+        while (c < want && c < (1u << 20)) c <<= 1;
+        if (c >= want) return c;
+        size_t p2 = 1u << 20;
+        while (p2 * 2 <= want) p2 <<= 1;
+        const size_t step = p2 / 8;
+        return (want + step - 1) / step * step;
+    }
+    void* get(size_t want, size_t* cap) {
+        const size_t c = size_class(want);
         *cap = c;
         {
             std::lock_guard<std::mutex> lock(mu);
@@ -31,13 +42,18 @@ struct PinnedCache {
             }
         }
         void* p = nullptr;
-        CUDA_OK(cudaHostAlloc(&p, c, cudaHostAllocDefault));
+        if (cudaHostAlloc(&p, c, cudaHostAllocDefault) != cudaSuccess) {
+            // host memory is short: give back what is held and try once more
+            cudaGetLastError();
+            drop_all();
+            CUDA_OK(cudaHostAlloc(&p, c, cudaHostAllocDefault));
+        }
         return p;
     }
     void put(void* p, size_t cap) {
         {
             std::lock_guard<std::mutex> lock(mu);
-            if (held + cap <= (64u << 20)) {
+            if (held + cap <= limit) {
                 spare.emplace(cap, p);
                 held += cap;
                 return;
@@ -45,12 +61,24 @@ struct PinnedCache {
         }
         cudaFreeHost(p);
     }
+    void drop_all() {
+        std::multimap<size_t, void*> old;
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            old.swap(spare);
+            held = 0;
+        }
+        for (auto& kv : old) cudaFreeHost(kv.second);
+    }
 };
 PinnedCache& pinned_cache() {
     static PinnedCache* c = new PinnedCache();  // never destroyed: buffers may come back while the process exits
     return *c;
 }
 }  // namespace
+
+void* pinned_get(size_t bytes, size_t* capacity) { return pinned_cache().get(bytes, capacity); }
+void pinned_put(void* p, size_t capacity) { pinned_cache().put(p, capacity); }
 
 bool DeviceArenas::use_pool(int device) {
     static std::mutex mu;
@@ -142,7 +170,7 @@ Job::~Job() {
         if (k.e0) cudaEventDestroy(k.e0);
         if (k.e1) cudaEventDestroy(k.e1);
     }
-    if (h_meta_) pinned_cache().put(h_meta_, h_meta_cap_);
+    if (h_meta_) pinned_put(h_meta_, h_meta_cap_);
     if (done_) cudaEventDestroy(done_);
     if (ev_fork_) cudaEventDestroy(ev_fork_);
     if (ev_join_) cudaEventDestroy(ev_join_);
@@ -199,7 +227,7 @@ void Job::stage() {
     d_state_ = (uint8_t*)arenas->alloc(std::max<uint64_t>(state_bytes_, 256), stream_);
     d_meta_ = (uint8_t*)arenas->alloc(std::max<uint64_t>(meta_bytes_, 256), stream_);
     t_alloc = lap(tl);
-    h_meta_ = (uint8_t*)pinned_cache().get(std::max<uint64_t>(meta_bytes_, 256), &h_meta_cap_);
+    h_meta_ = (uint8_t*)pinned_get(std::max<uint64_t>(meta_bytes_, 256), &h_meta_cap_);
     dev_keepalive_ = arenas;
     t_host = lap(tl);
 

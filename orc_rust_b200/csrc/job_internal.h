@@ -36,14 +36,22 @@ struct DeviceArenas {
     ~DeviceArenas();
 };
 
+// Pinned host memory is expensive to get and to give back (cudaHostAlloc pins pages: 3-14 ms for a few KiB on a busy
+// host, ~0.4 ms per MiB for the copies of a job's output), far more than copying and decoding the stripe it is for.
+// Buffers are therefore kept when their holder lets go and handed to the next job that asks for about that size
+// (job.cc).  At most ORCB_PINNED_CACHE_MB (default 4096) MiB are held; ORCB_PINNED_CACHE_MB=0 turns the cache off.
+void* pinned_get(size_t bytes, size_t* capacity);
+void pinned_put(void* p, size_t capacity);
+
 struct HostOutput {
     uint8_t* out = nullptr;   // pinned copy of AR_OUT
     uint8_t* heap = nullptr;  // pinned copy of the used part of AR_HEAP
     uint8_t* strs = nullptr;  // pinned copy of the DATA byte ranges that direct string columns point into
+    size_t out_cap = 0, heap_cap = 0, strs_cap = 0;
     ~HostOutput() {
-        if (out) cudaFreeHost(out);
-        if (heap) cudaFreeHost(heap);
-        if (strs) cudaFreeHost(strs);
+        if (out) pinned_put(out, out_cap);
+        if (heap) pinned_put(heap, heap_cap);
+        if (strs) pinned_put(strs, strs_cap);
     }
 };
 
