@@ -10,6 +10,7 @@
 #include <memory>
 
 #include "job.h"
+#include "job_internal.h"
 #include "predicate.h"
 #include "kernels.h"
 #include "meta.h"
@@ -23,6 +24,7 @@ static thread_local std::string g_last_error;
 
 struct OrcbFile {
     FileMeta meta;
+    size_t pinned_cap = 0;  // capacity of meta.pinned (from the pinned-buffer cache)
 };
 
 struct OrcbJob {
@@ -106,9 +108,17 @@ int orcb_open_path(const char* path, OrcbFile** out) {
         fseek(fp, 0, SEEK_SET);
         auto f = std::make_unique<OrcbFile>();
         uint8_t* buf = nullptr;
-        if (n > 0 && orcb_device_available() && cudaHostAlloc((void**)&buf, (size_t)n, cudaHostAllocDefault) == cudaSuccess) {
-            f->meta.pinned = buf;
-        } else {
+        // with a device present the file is read into pinned memory (asynchronous H2D copies); the buffer comes from
+        // the cache of pinned buffers, so opening file after file does not pin and unpin 100 MB each time
+        if (n > 0 && orcb_device_available()) {
+            try {
+                buf = (uint8_t*)pinned_get((size_t)n, &f->pinned_cap);
+                f->meta.pinned = buf;
+            } catch (const OrcException&) {
+                buf = nullptr;
+            }
+        }
+        if (!buf) {
             cudaGetLastError();
             f->meta.owned.resize((size_t)std::max<long>(n, 0));
             buf = f->meta.owned.data();
@@ -116,7 +126,7 @@ int orcb_open_path(const char* path, OrcbFile** out) {
         size_t got = n > 0 ? fread(buf, 1, (size_t)n, fp) : 0;
         fclose(fp);
         if ((long)got != n) {
-            if (f->meta.pinned) cudaFreeHost(f->meta.pinned);
+            if (f->meta.pinned) pinned_put(f->meta.pinned, f->pinned_cap);
             fail(ORCB_IO_ERROR, std::string("short read on ") + path);
         }
         f->meta.data = buf;
@@ -124,7 +134,7 @@ int orcb_open_path(const char* path, OrcbFile** out) {
         try {
             parse_file_tail(f->meta);
         } catch (...) {
-            if (f->meta.pinned) cudaFreeHost(f->meta.pinned);
+            if (f->meta.pinned) pinned_put(f->meta.pinned, f->pinned_cap);
             throw;
         }
         *out = f.release();
@@ -133,7 +143,7 @@ int orcb_open_path(const char* path, OrcbFile** out) {
 
 void orcb_file_free(OrcbFile* f) {
     if (!f) return;
-    if (f->meta.pinned) cudaFreeHost(f->meta.pinned);
+    if (f->meta.pinned) pinned_put(f->meta.pinned, f->pinned_cap);
     delete f;
 }
 
