@@ -4,6 +4,7 @@ what starting the next group of stripes ahead of time buys on a file with severa
 
     python tools/reader_probe.py            # one reader per file over the bench's 32 SF10 files + the multi-stripe file
     python tools/reader_probe.py --multi    # the multi-stripe file only (ORCB_NO_PREFETCH=1 to compare)
+    python tools/reader_probe.py --host     # batches copied back to host memory (`for batch in reader`), 6 files
 ORCB_READER_TIMING=1 prints the host phases of every group to stderr."""
 import ctypes
 import os
@@ -58,6 +59,18 @@ def best_of(n, fn):
             best, out = t, o
     return best, out
 
+
+if "--host" in sys.argv:
+    files = gen_orc.lineitem_dataset(os.environ.get("ORCB_BENCH_DIR", "/tmp/orcb200_bench"), 59_986_052, 32)[:6]
+    handles = [ob._File(f) for f in files]
+
+    def host_pass():
+        return sum(b.num_rows for fh in handles for b in ob.ArrowReaderBuilder(fh).build())
+
+    host_pass()
+    t, rows = best_of(3, host_pass)
+    print(f"host-resident batches: {rows} rows over {len(files)} files, {t * 1e3 / len(files):.1f} ms per file")
+    sys.exit(0)
 
 if "--multi" not in sys.argv:
     files = gen_orc.lineitem_dataset(os.environ.get("ORCB_BENCH_DIR", "/tmp/orcb200_bench"), 59_986_052, 32)
