@@ -7,7 +7,8 @@
  *
  * Threading: handles are not thread-safe; distinct handles may be used from distinct threads.
  * Errors: every call returns 0 (ORCB_OK) or an OrcbStatus; details via orcb_last_error().  Nothing
- * panics or aborts across this boundary (reference panics are reported as ORCB_OUT_OF_SPEC).
+ * panics or aborts across this boundary (reference panics are reported as a status: ORCB_OUT_OF_SPEC on the decode
+ * path, ORCB_UNEXPECTED with the panic's message for with_predicate / row-selection combinations).
  */
 #ifndef ORC_B200_H
 #define ORC_B200_H
