@@ -101,6 +101,9 @@ int orcb_open_memory(const uint8_t* data, size_t len, OrcbFile** out);
 /* Reads the whole file into (pinned, if a device is present) host memory owned by the handle
  * (ChunkReader for File, src/reader/mod.rs:48-62). */
 int orcb_open_path(const char* path, OrcbFile** out);
+/* A second handle on the same bytes (they stay with `f`, which must outlive the clone).  A bulk job stages every
+ * handle's stripes separately, so clones let one host copy of a file stand in for several files of a larger set. */
+int orcb_file_clone(const OrcbFile* f, OrcbFile** out);
 void orcb_file_free(OrcbFile* f);
 
 /* FileMetadata accessors (src/reader/metadata.rs:141-178) */
@@ -130,7 +133,10 @@ typedef struct OrcbReadOptions {
     void* cuda_stream;         /* cudaStream_t to enqueue on, or NULL for the reader's own stream */
     uint32_t flags;            /* bit0: no_row_index */
     uint32_t stripe_shard_index;  /* multi-GPU stripe sharding: keep stripes with */
-    uint32_t stripe_shard_count;  /*   (ordinal % count) == index; count 0 or 1 = all */
+    uint32_t stripe_shard_count;  /*   (ordinal % count) == index; count 0 or 1 = all.  A reader counts the stripes
+                                     of its file (after the byte range), a bulk job the stripes of all its files in order */
+    uint32_t waves;            /* bulk jobs: stripe waves kept in flight on separate streams (0 = automatic) */
+    uint32_t reserved0;
 } OrcbReadOptions;
 
 /* ArrowReaderBuilder::schema (src/arrow_reader.rs:182-198) for the given options */
@@ -221,6 +227,11 @@ int orcb_reader_next(OrcbReader* r, struct ArrowArray* out, int* eos);
 /* Same, batch buffers stay in HBM (device_type = ARROW_DEVICE_CUDA).  Requires device_resident = 1. */
 int orcb_reader_next_device(OrcbReader* r, struct ArrowDeviceArray* out, int* eos);
 
+/* Drains the reader inside the library: every remaining batch is produced as orcb_reader_next (host-resident readers,
+ * device-to-host copy included) or orcb_reader_next_device would, and released at once.  out[0] = batches,
+ * out[1] = rows.  The `for batch in reader {}` of benches/arrow_reader.rs:53-59 without per-batch FFI calls. */
+int orcb_reader_drain(OrcbReader* r, uint64_t out[2]);
+
 /* ---- bulk job API: NaiveStripeDecoder::new_with_selection + drain (src/array_decoder/mod.rs:570-594,
  *      371-387) for many stripes in one launch plan.  Used by the reader internally and by bench.py. ---- */
 int orcb_job_new(OrcbFile* const* files, uint32_t n_files, const OrcbReadOptions* opt, OrcbJob** out);
@@ -244,6 +255,9 @@ typedef struct OrcbJobStats {
     uint64_t n_kernel_launches; /* kernels enqueued by one launch() */
     uint64_t n_batches;
     uint64_t d2h_meta_bytes;    /* per-batch metadata + error words read back in finish() */
+    uint64_t aliased_output_bytes; /* part of output_bytes that no kernel writes: values buffers of direct string
+                                      columns are views of the staged / decompressed DATA stream (valid after finish()) */
+    uint64_t n_waves;
 } OrcbJobStats;
 int orcb_job_stats(const OrcbJob* j, OrcbJobStats* out);
 /* Re-copies the compressed stripe bytes H2D into the already allocated arenas (end-to-end timing loops). */

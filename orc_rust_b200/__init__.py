@@ -52,13 +52,14 @@ class _ReadOptions(ctypes.Structure):
         ("timestamp_unit", ctypes.c_int32), ("use_row_index", ctypes.c_int32), ("device_resident", ctypes.c_int32),
         ("max_stripes_per_launch", ctypes.c_uint32), ("cuda_stream", ctypes.c_void_p), ("flags", ctypes.c_uint32),
         ("stripe_shard_index", ctypes.c_uint32), ("stripe_shard_count", ctypes.c_uint32),
+        ("waves", ctypes.c_uint32), ("reserved0", ctypes.c_uint32),
     ]
 
 
 class JobStats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint64) for n in (
         "n_stripes", "n_rows", "n_columns", "input_bytes", "staged_bytes", "output_bytes", "device_bytes",
-        "n_segments", "n_kernel_launches", "n_batches", "d2h_meta_bytes")]
+        "n_segments", "n_kernel_launches", "n_batches", "d2h_meta_bytes", "aliased_output_bytes", "n_waves")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -101,11 +102,11 @@ class _ArrowDeviceArray(ctypes.Structure):
 _lib = None
 
 EXPORTED_SYMBOLS = [
-    "orcb_open_memory", "orcb_open_path", "orcb_file_free", "orcb_file_num_rows", "orcb_file_num_stripes",
+    "orcb_open_memory", "orcb_open_path", "orcb_file_clone", "orcb_file_free", "orcb_file_num_rows", "orcb_file_num_stripes",
     "orcb_file_compression", "orcb_file_compression_block_size", "orcb_file_row_index_stride",
     "orcb_file_num_root_columns", "orcb_file_root_column_name", "orcb_file_stripe_info", "orcb_schema",
     "orcb_reader_new", "orcb_reader_new_with_selection", "orcb_reader_new_ex", "orcb_reader_build", "orcb_reader_plan", "orcb_predicate_row_groups", "orcb_bloom_hash_long", "orcb_bloom_hash_bytes", "orcb_reader_counters", "orcb_selection_plan", "orcb_reader_free", "orcb_reader_total_row_count", "orcb_reader_next",
-    "orcb_reader_next_device", "orcb_job_new", "orcb_job_free", "orcb_job_plan", "orcb_job_stage",
+    "orcb_reader_next_device", "orcb_reader_drain", "orcb_job_new", "orcb_job_free", "orcb_job_plan", "orcb_job_stage",
     "orcb_job_launch", "orcb_job_finish", "orcb_job_stats", "orcb_job_restage", "orcb_job_kernel_stats", "orcb_job_num_batches", "orcb_job_export_batch",
     "orcb_job_export_batch_device", "orcb_decode_int_rle", "orcb_decode_byte_rle", "orcb_decode_bool_rle",
     "orcb_decode_varint128", "orcb_decompress_stream", "orcb_last_error", "orcb_build_info",
@@ -151,10 +152,12 @@ def lib() -> ctypes.CDLL:
         L.orcb_file_stripe_info.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint64)]
         L.orcb_open_memory.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]
         L.orcb_open_path.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]
+        L.orcb_file_clone.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]
         L.orcb_schema.argtypes = [ctypes.c_void_p, ctypes.POINTER(_ReadOptions), ctypes.c_void_p]
         L.orcb_reader_new.argtypes = [ctypes.c_void_p, ctypes.POINTER(_ReadOptions), ctypes.POINTER(ctypes.c_void_p)]
         L.orcb_reader_next.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]
         L.orcb_reader_next_device.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]
+        L.orcb_reader_drain.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]
         L.orcb_job_new.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_uint32, ctypes.POINTER(_ReadOptions),
                                    ctypes.POINTER(ctypes.c_void_p)]
         L.orcb_job_kernel_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(KernelStat), ctypes.c_uint32,
@@ -203,6 +206,14 @@ class _File:
             _lib.orcb_file_free(self._h)
             self._h = ctypes.c_void_p()
 
+    def clone(self) -> "_File":
+        """A second handle on the same host bytes (a bulk job stages each handle's stripes separately)."""
+        c = object.__new__(_File)
+        c._h = ctypes.c_void_p()
+        c._keep = self  # the original owns the bytes
+        _check(lib().orcb_file_clone(self._h, ctypes.byref(c._h)))
+        return c
+
     @property
     def number_of_rows(self) -> int:
         return lib().orcb_file_num_rows(self._h)
@@ -237,8 +248,9 @@ class _File:
 
 def _make_options(device=0, batch_size=8192, projection=None, byte_range=None, timestamp_precision=0,
                   use_row_index=True, device_resident=False, max_stripes_per_launch=0, cuda_stream=None,
-                  shard=None):
+                  shard=None, waves=0):
     o = _ReadOptions()
+    o.waves = waves
     o.device = device
     o.batch_size = batch_size
     keep = None
@@ -630,6 +642,12 @@ class ArrowReader:
             raise StopIteration
         return pa.RecordBatch._import_from_c(ctypes.addressof(arr), self._schema)
 
+    def drain(self):
+        """Consumes every remaining batch inside the library (`for _ in reader {}`): returns (batches, rows)."""
+        out = (ctypes.c_uint64 * 2)()
+        _check(lib().orcb_reader_drain(self._h, out))
+        return int(out[0]), int(out[1])
+
     def read_all(self):
         import pyarrow as pa
         batches = list(self)
@@ -669,10 +687,10 @@ class DecodeJob:
     """One device launch plan over many stripes of many files (bulk API used by bench.py)."""
 
     def __init__(self, sources, *, device=0, batch_size=8192, projection=None, use_row_index=True,
-                 cuda_stream=None, shard=None, timestamp_precision=0):
+                 cuda_stream=None, shard=None, timestamp_precision=0, waves=0):
         self._files = [s if isinstance(s, _File) else _File(s) for s in sources]
         self._opts, self._keep = _make_options(device, batch_size, projection, None, timestamp_precision,
-                                               use_row_index, True, 0, cuda_stream, shard)
+                                               use_row_index, True, 0, cuda_stream, shard, waves)
         arr = (ctypes.c_void_p * len(self._files))(*[f._h for f in self._files])
         self._h = ctypes.c_void_p()
         _check(lib().orcb_job_new(arr, len(self._files), ctypes.byref(self._opts), ctypes.byref(self._h)))

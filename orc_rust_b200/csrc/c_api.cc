@@ -27,8 +27,29 @@ struct OrcbFile {
     size_t pinned_cap = 0;  // capacity of meta.pinned (from the pinned-buffer cache)
 };
 
+// Bulk job = one or more "waves": contiguous slices of the stripe list, each its own Job on its own pair of streams.
+// The integer path of a job is a chain (header walk -> run decode -> strings) whose links are latency- or
+// issue-bound rather than bandwidth-bound; several waves in flight let the links of one wave run under those of another.
 struct OrcbJob {
-    std::unique_ptr<Job> job;
+    std::vector<std::unique_ptr<Job>> waves;
+    int device = 0;
+    cudaStream_t user_stream = nullptr;  // the caller's stream (timing, ordering); waves fork from / join to it
+    bool has_user_stream = false;
+    cudaEvent_t ev_fork = nullptr;
+    std::vector<cudaEvent_t> ev_join;
+    ~OrcbJob() {
+        waves.clear();
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        for (auto e : ev_join) cudaEventDestroy(e);
+    }
+    // batch i of the job -> (wave, batch of that wave)
+    std::pair<Job*, uint64_t> locate(uint64_t i) const {
+        for (auto& w : waves) {
+            if (i < w->num_batches()) return {w.get(), i};
+            i -= w->num_batches();
+        }
+        fail(ORCB_INVALID_ARGUMENT, "batch index out of range");
+    }
 };
 
 // ArrowReader: walks the selected stripes in groups, one Job per group (src/arrow_reader.rs:233-347)
@@ -138,6 +159,18 @@ int orcb_open_path(const char* path, OrcbFile** out) {
             throw;
         }
         *out = f.release();
+    });
+}
+
+int orcb_file_clone(const OrcbFile* f, OrcbFile** out) {
+    return guarded([&] {
+        if (!f || !out) fail(ORCB_INVALID_ARGUMENT, "NULL argument");
+        auto c = std::make_unique<OrcbFile>();
+        c->meta = f->meta;  // parsed tail; the bytes stay with the original
+        c->meta.owned.clear();
+        c->meta.pinned = nullptr;
+        c->meta.data = f->meta.data;
+        *out = c.release();
     });
 }
 
@@ -491,34 +524,179 @@ int orcb_reader_next_device(OrcbReader* r, struct ArrowDeviceArray* out, int* eo
     });
 }
 
+// `for batch in reader {}` without leaving the library: every batch is produced exactly as orcb_reader_next /
+// orcb_reader_next_device would hand it out (host copy included for host-resident readers) and released at once.
+int orcb_reader_drain(OrcbReader* r, uint64_t out[2]) {
+    return guarded([&] {
+        if (!r || !out) fail(ORCB_INVALID_ARGUMENT, "NULL argument");
+        out[0] = out[1] = 0;
+        if (r->failed) fail(ORCB_UNEXPECTED, "reader is in the error state");
+        try {
+            while (reader_advance(r)) {
+                if (r->opt.device_resident) {
+                    ArrowDeviceArray a;
+                    r->job->export_batch_device(r->next_batch++, &a);
+                    out[1] += (uint64_t)a.array.length;
+                    a.array.release(&a.array);
+                } else {
+                    ArrowArray a;
+                    r->job->export_batch(r->next_batch++, &a);
+                    out[1] += (uint64_t)a.length;
+                    a.release(&a);
+                }
+                out[0]++;
+            }
+        } catch (...) {
+            r->failed = true;
+            throw;
+        }
+    });
+}
+
+// stripes of all files in order; multi-GPU sharding counts over this list (stripe i -> rank i % count), not per file
+static std::vector<StripeTask> job_tasks(OrcbFile* const* files, uint32_t n_files, const ReadOptions& o) {
+    ReadOptions per_file = o;
+    per_file.shard_index = 0;
+    per_file.shard_count = 1;
+    std::vector<StripeTask> tasks;
+    uint64_t ordinal = 0;
+    for (uint32_t i = 0; i < n_files; i++)
+        for (uint32_t s : select_stripes(files[i]->meta, per_file)) {
+            if (o.shard_count <= 1 || ordinal % o.shard_count == o.shard_index) tasks.push_back({&files[i]->meta, s});
+            ordinal++;
+        }
+    return tasks;
+}
+
 int orcb_job_new(OrcbFile* const* files, uint32_t n_files, const OrcbReadOptions* opt, OrcbJob** out) {
     return guarded([&] {
         if (!files || !n_files || !out) fail(ORCB_INVALID_ARGUMENT, "NULL argument");
         ReadOptions o = ReadOptions::from_c(opt);
-        std::vector<StripeTask> tasks;
-        for (uint32_t i = 0; i < n_files; i++)
-            for (uint32_t s : select_stripes(files[i]->meta, o)) tasks.push_back({&files[i]->meta, s});
+        std::vector<StripeTask> tasks = job_tasks(files, n_files, o);
         auto j = std::make_unique<OrcbJob>();
-        j->job = std::make_unique<Job>(std::move(tasks), o);
+        j->device = o.device;
+        // waves: the caller's number, else ORCB_WAVES, else one per ~24 stripes up to 4
+        uint32_t waves = o.waves;
+        if (!waves)
+            if (const char* e = getenv("ORCB_WAVES")) waves = (uint32_t)atoi(e);
+        if (!waves) waves = (uint32_t)std::min<size_t>(4, (tasks.size() + 23) / 24);
+        waves = std::max<uint32_t>(1, std::min<uint32_t>(waves, (uint32_t)std::max<size_t>(tasks.size(), 1)));
+        if (waves > 1) {
+            j->has_user_stream = !o.own_stream;
+            j->user_stream = o.stream;
+            o.own_stream = true;
+            o.stream = nullptr;
+        }
+        const size_t per = (tasks.size() + waves - 1) / waves;
+        for (uint32_t w = 0; w < waves; w++) {
+            const size_t a = std::min(tasks.size(), w * per), b = std::min(tasks.size(), (w + 1) * per);
+            if (w > 0 && a == b) break;
+            j->waves.push_back(std::make_unique<Job>(std::vector<StripeTask>(tasks.begin() + a, tasks.begin() + b), o));
+        }
         *out = j.release();
     });
 }
 void orcb_job_free(OrcbJob* j) { delete j; }
-int orcb_job_plan(OrcbJob* j) { return guarded([&] { j->job->plan(); }); }
-int orcb_job_stage(OrcbJob* j) { return guarded([&] { j->job->stage(); }); }
-int orcb_job_launch(OrcbJob* j) { return guarded([&] { j->job->launch(); }); }
-int orcb_job_finish(OrcbJob* j) { return guarded([&] { j->job->finish(); }); }
-int orcb_job_stats(const OrcbJob* j, OrcbJobStats* out) { return guarded([&] { j->job->stats(out); }); }
-int orcb_job_restage(OrcbJob* j) { return guarded([&] { j->job->restage(); }); }
-int orcb_job_kernel_stats(const OrcbJob* j, OrcbKernelStat* out, uint32_t cap, uint32_t* n) {
-    return guarded([&] { *n = j->job->kernel_stats(out, cap); });
+int orcb_job_plan(OrcbJob* j) {
+    return guarded([&] { for (auto& w : j->waves) w->plan(); });
 }
-uint64_t orcb_job_num_batches(const OrcbJob* j) { return j->job->num_batches(); }
+int orcb_job_stage(OrcbJob* j) {
+    return guarded([&] { for (auto& w : j->waves) w->stage(); });
+}
+int orcb_job_launch(OrcbJob* j) {
+    return guarded([&] {
+        const bool serial = getenv("ORCB_SERIAL") != nullptr;  // one kernel at a time: clean per-kernel timings
+        if (j->waves.size() > 1 && j->has_user_stream) {
+            for (auto& w : j->waves) w->stage();
+            CUDA_OK(cudaSetDevice(j->device));
+            if (!j->ev_fork) CUDA_OK(cudaEventCreateWithFlags(&j->ev_fork, cudaEventDisableTiming));
+            while (j->ev_join.size() < j->waves.size()) {
+                cudaEvent_t e = nullptr;
+                CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                j->ev_join.push_back(e);
+            }
+            CUDA_OK(cudaEventRecord(j->ev_fork, j->user_stream));
+            for (auto& w : j->waves) CUDA_OK(cudaStreamWaitEvent(w->stream(), j->ev_fork, 0));
+        }
+        for (size_t i = 0; i < j->waves.size(); i++) {
+            j->waves[i]->launch();
+            if (serial && j->waves.size() > 1) CUDA_OK(cudaStreamSynchronize(j->waves[i]->stream()));
+        }
+        if (j->waves.size() > 1 && j->has_user_stream) {
+            for (size_t i = 0; i < j->waves.size(); i++) {
+                CUDA_OK(cudaEventRecord(j->ev_join[i], j->waves[i]->stream()));
+                CUDA_OK(cudaStreamWaitEvent(j->user_stream, j->ev_join[i], 0));
+            }
+        }
+    });
+}
+int orcb_job_finish(OrcbJob* j) {
+    return guarded([&] { for (auto& w : j->waves) w->finish(); });
+}
+int orcb_job_stats(const OrcbJob* j, OrcbJobStats* out) {
+    return guarded([&] {
+        memset(out, 0, sizeof(*out));
+        for (auto& w : j->waves) {
+            OrcbJobStats s{};
+            w->stats(&s);
+            out->n_stripes += s.n_stripes;
+            out->n_rows += s.n_rows;
+            out->n_columns = s.n_columns;
+            out->input_bytes += s.input_bytes;
+            out->staged_bytes += s.staged_bytes;
+            out->output_bytes += s.output_bytes;
+            out->device_bytes += s.device_bytes;
+            out->n_segments += s.n_segments;
+            out->n_kernel_launches += s.n_kernel_launches;
+            out->n_batches += s.n_batches;
+            out->d2h_meta_bytes += s.d2h_meta_bytes;
+            out->aliased_output_bytes += s.aliased_output_bytes;
+        }
+        out->n_waves = j->waves.size();
+    });
+}
+int orcb_job_restage(OrcbJob* j) {
+    return guarded([&] { for (auto& w : j->waves) w->restage(); });
+}
+int orcb_job_kernel_stats(const OrcbJob* j, OrcbKernelStat* out, uint32_t cap, uint32_t* n) {
+    return guarded([&] {
+        // summed over the waves by kernel name (waves overlap: the sum of a kernel's times can exceed the step)
+        uint32_t total = 0;
+        std::vector<OrcbKernelStat> tmp(64);
+        for (auto& w : j->waves) {
+            const uint32_t k = w->kernel_stats(tmp.data(), (uint32_t)tmp.size());
+            for (uint32_t i = 0; i < k; i++) {
+                uint32_t at = 0;
+                while (at < total && strncmp(out[at].name, tmp[i].name, sizeof(out[at].name)) != 0) at++;
+                if (at == total) {
+                    if (total >= cap) continue;
+                    out[total++] = tmp[i];
+                } else {
+                    out[at].ms += tmp[i].ms;
+                    out[at].alg_bytes += tmp[i].alg_bytes;
+                    out[at].work_items += tmp[i].work_items;
+                }
+            }
+        }
+        *n = total;
+    });
+}
+uint64_t orcb_job_num_batches(const OrcbJob* j) {
+    uint64_t n = 0;
+    for (auto& w : j->waves) n += w->num_batches();
+    return n;
+}
 int orcb_job_export_batch(OrcbJob* j, uint64_t i, struct ArrowArray* out) {
-    return guarded([&] { j->job->export_batch(i, out); });
+    return guarded([&] {
+        auto at = j->locate(i);
+        at.first->export_batch(at.second, out);
+    });
 }
 int orcb_job_export_batch_device(OrcbJob* j, uint64_t i, struct ArrowDeviceArray* out) {
-    return guarded([&] { j->job->export_batch_device(i, out); });
+    return guarded([&] {
+        auto at = j->locate(i);
+        at.first->export_batch_device(at.second, out);
+    });
 }
 
 // ---------------------------------------------------------------------------------------------

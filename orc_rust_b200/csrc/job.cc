@@ -424,6 +424,7 @@ void Job::finish() {
     }
     // logical output bytes: values + offsets + string bytes + validity where emitted
     output_bytes_ = 0;
+    aliased_bytes_ = 0;
     const uint32_t* nulls = (const uint32_t*)(h_meta_ + o_nulls_);
     for (auto& cp : colstripes_) {
         const OutColumn& oc = cols_[cp.col];
@@ -435,6 +436,7 @@ void Job::finish() {
             else if (cp.str_slot >= 0) {
                 const int64_t* bb = (const int64_t*)(h_meta_ + o_bbase_ + cp.batch_base_off);
                 output_bytes_ += 4ull * (rows + 1) + (uint64_t)(bb[b + 1] - bb[b]);
+                if (strcols_[cp.str_slot].mode == 0) aliased_bytes_ += (uint64_t)(bb[b + 1] - bb[b]);
             } else output_bytes_ += (uint64_t)rows * oc.width;
         }
     }
@@ -450,6 +452,8 @@ void Job::stats(OrcbJobStats* out) const {
     for (auto& sc : stage_copies_) out->staged_bytes += sc.bytes;
     out->staged_bytes += desc_bytes_;
     out->output_bytes = output_bytes_;
+    out->aliased_output_bytes = aliased_bytes_;
+    out->n_waves = 1;
     for (int a = 1; a < 8; a++) out->device_bytes += size_[a];
     out->device_bytes += desc_bytes_ + state_bytes_ + meta_bytes_;
     out->n_segments = n_segments_;

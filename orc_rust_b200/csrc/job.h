@@ -27,6 +27,7 @@ struct ReadOptions {
     cudaStream_t stream = nullptr;
     bool own_stream = true;
     uint32_t shard_index = 0, shard_count = 1;
+    uint32_t waves = 0;      // bulk jobs: number of stripe waves in flight (0 = automatic)
     // with_schema (src/arrow_reader.rs:80-83): per projected column, in output order; -1 = the default mapping,
     // 0..3 = timestamp unit ns/us/ms/s, 4 = Decimal128(38, 9) nanoseconds (array_decoder/timestamp.rs:150-190)
     std::vector<int> ts_hint;
@@ -110,6 +111,7 @@ class Job {
     void stats(OrcbJobStats* out) const;
     uint32_t kernel_stats(OrcbKernelStat* out, uint32_t cap) const;
     uint64_t num_batches() const { return batch_task_.size(); }
+    cudaStream_t stream() const { return stream_; }
     void export_batch(uint64_t i, ArrowArray* out);
     void export_batch_device(uint64_t i, ArrowDeviceArray* out);
     const std::vector<OutColumn>& columns() const { return cols_; }
@@ -185,7 +187,7 @@ class Job {
     std::vector<uint32_t> task_first_cs_;
 
     // stats
-    uint64_t input_bytes_ = 0, n_rows_ = 0, n_segments_ = 0, n_launches_ = 0, output_bytes_ = 0;
+    uint64_t input_bytes_ = 0, n_rows_ = 0, n_segments_ = 0, n_launches_ = 0, output_bytes_ = 0, aliased_bytes_ = 0;
 
     struct KStat {
         std::string name;

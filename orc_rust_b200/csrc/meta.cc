@@ -178,7 +178,8 @@ void parse_file_tail(FileMeta& fm) {
         fail(ORCB_UNSUPPORTED_DEVICE_CODEC,
              "file is compressed with Zlib/Zstd/LZO: not decodable on the device path (no CPU fallback)");
     if (fm.compression < 0 || fm.compression > C_ZSTD) fail(ORCB_DECODE_PROTO, "unknown compression kind");
-    if (footer_len + meta_len + ps_len + 1 > n) fail(ORCB_OUT_OF_SPEC, "footer exceeds file");
+    // subtraction-style checks: the lengths come from the file and their sum may wrap
+    if (footer_len > n - 1 - ps_len || meta_len > n - 1 - ps_len - footer_len) fail(ORCB_OUT_OF_SPEC, "footer exceeds file");
     size_t fend = n - 1 - ps_len;
     std::vector<uint8_t> footer = host_decompress_section(fm.compression, fm.block_size, d + fend - footer_len, footer_len);
     PbCursor c(footer.data(), footer.size());
@@ -226,8 +227,11 @@ void parse_file_tail(FileMeta& fm) {
         fm.root_columns.emplace_back(root.field_names[i], root.subtypes[i]);
     }
     for (auto& s : fm.stripes) {
-        if (s.offset + s.index_length + s.data_length + s.footer_length > n)
-            fail(ORCB_IO_ERROR, "stripe exceeds file length");
+        uint64_t room = n;
+        for (uint64_t part : {s.offset, s.index_length, s.data_length, s.footer_length}) {
+            if (part > room) fail(ORCB_IO_ERROR, "stripe exceeds file length");
+            room -= part;
+        }
     }
 }
 
@@ -251,8 +255,8 @@ StripeFooter FileMeta::read_stripe_footer(uint32_t stripe) const {
                 else if (g.number == 3) s.length = g.value;
             }
             s.offset = pos;
+            if (s.length > len - pos) fail(ORCB_IO_ERROR, "stream exceeds file length");
             pos += s.length;
-            if (pos > len) fail(ORCB_IO_ERROR, "stream exceeds file length");
             sf.streams.push_back(s);
         } else if (f.number == 2) {
             ColumnEncoding e;

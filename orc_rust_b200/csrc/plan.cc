@@ -91,6 +91,15 @@ void Job::plan() {
     }
     for (uint32_t t = 0; t < tasks_.size(); t++) plan_stripe(t);
 
+    // The header walk gives every segment one lane for as long as the segment has runs: the longest chains go first
+    // (they bound the kernel's duration) and lanes of one warp get chains of similar length.  Nothing refers to a
+    // short-run segment by index before the walk assigns it blocks on the device.
+    {
+        static const char* e = getenv("ORCB_SORT_SEGS");
+        if (!(e && e[0] == '0'))
+            std::stable_sort(int_segs_.begin(), int_segs_.end(), [](const Seg& a, const Seg& b) { return a.run_cap > b.run_cap; });
+    }
+
     if (pool_blocks_) {
         run_table_ = alloc(AR_TMP, (uint64_t)pool_blocks_ * 32 * sizeof(RunRec));
         block_recs_ = alloc(AR_TMP, (uint64_t)pool_blocks_ * sizeof(BlockRec));
@@ -254,7 +263,7 @@ void Job::plan_stripe(uint32_t task_idx) {
             const StreamInfo* st = sf.find(cid, kind);
             if (!st) return r;
             r.present = true;
-            if (st->offset < data_start || st->offset + st->length > data_start + si.data_length)
+            if (st->offset < data_start || st->offset - data_start > si.data_length || st->length > si.data_length - (st->offset - data_start))
                 fail(ORCB_OUT_OF_SPEC, "data stream outside the stripe's data area");
             input_bytes_ += st->length;
             const uint64_t rel = st->offset - data_start;

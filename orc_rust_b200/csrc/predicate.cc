@@ -63,8 +63,9 @@ bool bloom_test_hash(const BloomBits& b, uint64_t hash64) {
     const uint64_t bit_count = (uint64_t)b.bitset.size() * 64;
     if (bit_count == 0) return true;
     const uint32_t h1 = (uint32_t)hash64, h2 = (uint32_t)(hash64 >> 32);
-    for (uint32_t i = 1; i <= b.num_hash_functions; i++) {
-        uint32_t combined = h1 + i * h2;  // i32 wrapping arithmetic
+    // 64-bit counter: `1..=k` ends for k = u32::MAX (a 32-bit one would wrap and never leave the loop)
+    for (uint64_t i = 1; i <= b.num_hash_functions; i++) {
+        uint32_t combined = h1 + (uint32_t)i * h2;  // i32 wrapping arithmetic
         if ((int32_t)combined < 0) combined = ~combined;
         const uint64_t bit = (uint64_t)combined % bit_count;
         if (!((b.bitset[bit / 64] >> (bit % 64)) & 1)) return false;

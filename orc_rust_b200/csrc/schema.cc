@@ -23,6 +23,7 @@ ReadOptions ReadOptions::from_c(const OrcbReadOptions* o) {
     r.own_stream = o->cuda_stream == nullptr;
     r.shard_index = o->stripe_shard_index;
     r.shard_count = o->stripe_shard_count ? o->stripe_shard_count : 1;
+    r.waves = o->waves;
     return r;
 }
 
