@@ -864,7 +864,8 @@ int orcb_decompress_stream(int device, int compression_kind, const uint8_t* in, 
         StreamRun sr(device, in, in_len);
         const size_t cap = chunks.size() * block_size + 256;
         if (chunks.size() * block_size > out_cap) fail(ORCB_INVALID_ARGUMENT, "out_cap must be >= chunks * block_size");
-        DevBuf dout(cap), ddesc(chunks.size() * sizeof(ChunkDesc) + 16), dlens(chunks.size() * 4 + 16);
+        DevBuf dout(cap), ddesc(chunks.size() * sizeof(ChunkDesc) + 16), dlens(chunks.size() * 4 + 16), dctr(16);
+        CU(cudaMemset(dctr.p, 0, 16));
         std::vector<ChunkDesc> descs(chunks.size());
         for (size_t i = 0; i < chunks.size(); i++) {
             ChunkDesc& d = descs[i];
@@ -884,7 +885,7 @@ int orcb_decompress_stream(int device, int compression_kind, const uint8_t* in, 
             CU(cudaEventCreate(&e1));
             CU(cudaEventRecord(e0, 0));
         }
-        int rc = launch_decompress((ChunkDesc*)ddesc.p, (uint32_t)chunks.size(), (uint32_t*)sr.err.p, (uint32_t*)dlens.p, 0);
+        int rc = launch_decompress((ChunkDesc*)ddesc.p, (uint32_t)chunks.size(), (uint32_t*)sr.err.p, (uint32_t*)dlens.p, (uint32_t*)dctr.p, 0);
         if (rc) fail(ORCB_CUDA, cudaGetErrorString((cudaError_t)rc));
         if (timing) {
             float ms = 0;

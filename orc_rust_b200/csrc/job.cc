@@ -335,7 +335,7 @@ void Job::launch() {
         launches += nk;
     };
     if (N(chunks_))
-        run("k_decompress", ab_decomp_, N(chunks_), 1, [&] { return launch_decompress((ChunkDesc*)(d_desc_ + o_chunk_), N(chunks_), err, nullptr, st); });
+        run("k_decompress", ab_decomp_, N(chunks_), 1, [&] { return launch_decompress((ChunkDesc*)(d_desc_ + o_chunk_), N(chunks_), err, nullptr, (uint32_t*)(d_state_ + o_nblocks_) + 3, st); });
     if (N(present_byte_segs_)) {
         run("k_byte_rle(present)", ab_present_, N(present_byte_segs_), 1, [&] { return launch_byte_rle((Seg*)(d_desc_ + o_pbyte_), N(present_byte_segs_), cnt, dstart, err, st); });
         run("k_bits(present)", ab_present_, N(present_bit_segs_), 1, [&] { return launch_bits((BitSeg*)(d_desc_ + o_pbit_), N(present_bit_segs_), cnt, dstart, st); });

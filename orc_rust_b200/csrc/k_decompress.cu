@@ -45,36 +45,6 @@ __device__ __forceinline__ void warp_copy_match(uint8_t* out, uint32_t o, uint32
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Snappy, 32 input positions at a time.
-//
-// An element (a literal or a back-reference) is 2 or 3 input bytes on average, so a serial tag loop spends a whole
-// warp on a few bytes of output per step; and a chunk is one serial chain, so a launch of a few thousand chunks is as
-// slow as its slowest chunk (decimal varints and dictionary keys: up to 120 000 elements of 4 bytes in 256 KiB).
-//   * Every lane decodes the element that WOULD start at its byte of a 32-byte input window (snappy_parse); the
-//     elements that really start there are the chain 0 -> next[0] -> next[next[0]] .., found by pointer jumping over
-//     the lanes (4 rounds, at most 16 elements of >= 2 bytes fit).  A warp scan of their output lengths places them.
-//   * The bytes are then produced 32 at a time, one output byte per lane, whichever element it belongs to
-//     (snappy_copy).  Literal bytes come from the input, bytes of a back-reference from a ring of the last SW_HIST
-//     output bytes in shared memory (older ones from global memory); a back-reference into its own window's output
-//     waits for the rest of the window and is then copied by the whole warp, in order.
-//   * Where elements start and where their output goes depends on the input only, never on the output.  Large
-//     launches (more chunks than the GPU holds warps) run both steps in one warp per chunk, k_decompress: they are
-//     bound by instruction issue and a second warp would only take a slot away.  Small launches (a reader's group of
-//     stripes) are bound by the latency of the slowest chunk; there k_decompress_pair gives each chunk a PARSER
-//     warp that runs ahead and leaves one descriptor per window in a small shared-memory queue, and a COPIER warp
-//     that turns descriptors into bytes, which shortens the chain per window by about a third.
-// Anything out of the ordinary (a header or literal that crosses the end of the input, a distance of zero or
-// beyond the output so far, output past the announced length) is not parsed as a window: the element-by-element
-// loop takes over from that position (in the pair, after the copier has drained the queue) and reports the error
-// exactly as it always did.
-// ------------------------------------------------------------------------------------------------
-constexpr uint32_t SW_LITERAL = 1u << 31, SW_DEPENDENT = 1u << 30, SW_LONG = 1u << 29, SW_LEN = SW_LONG - 1;
-constexpr uint32_t SW_LONG_LITERAL = 128;  // a literal this long ends its window and is copied word-wise
-constexpr uint32_t SW_HIST = 4096;         // bytes of recent output the copier keeps in shared memory (power of two)
-constexpr uint32_t SW_QUEUE = 4;           // windows the parser may be ahead
-enum : uint32_t { SW_WINDOW = 1, SW_END = 2, SW_FALLBACK = 3 };
-
 // tag byte -> header bytes [0:3] | literal [3] | length is in the following bytes [4] | bytes of offset / length
 // that follow [5:8] | high offset bits of a 1-byte-offset copy [8:11] | length [16:]
 __device__ __forceinline__ uint32_t snappy_tag_entry(uint32_t tag) {
@@ -83,197 +53,6 @@ __device__ __forceinline__ uint32_t snappy_tag_entry(uint32_t tag) {
     if (t == 1) return 2u | (1u << 5) | ((tag >> 5) << 8) | ((4u + (l & 7u)) << 16);
     if (t == 2) return 3u | (2u << 5) | ((l + 1u) << 16);
     return 5u | (4u << 5) | ((l + 1u) << 16);
-}
-
-struct SnappyWin {
-    uint32_t out_off[32];  // where the element's output starts, relative to the window's first output byte
-    uint32_t src[32];      // literal: input offset of its first byte; back-reference: distance
-    uint32_t info[32];     // output length | SW_LITERAL | SW_DEPENDENT (reads this window's output) | SW_LONG
-    uint32_t state, count, total, o, p;  // o: output position of the window; p: input position (FALLBACK)
-    uint32_t pad[3];
-};
-struct SnappyPair {
-    SnappyWin win[SW_QUEUE];
-    uint32_t head, tail;  // windows published / consumed
-    uint8_t hist[SW_HIST];
-};
-
-// parser: one window at input position p / output position o into `w`; false = not a regular window
-__device__ __forceinline__ bool snappy_parse(const uint8_t* __restrict__ s, uint32_t n, const uint8_t* d, uint64_t ulen, uint32_t& p,
-                                             uint32_t& o, SnappyWin& w, const uint32_t* lut, int lane) {
-    // bytes q .. q+4 of the input for q = p + lane, out of ten aligned words
-    const uintptr_t a0 = (uintptr_t)(s + p);
-    const uint32_t* wp = (const uint32_t*)(a0 & ~(uintptr_t)3);
-    const uint32_t word = lane < 10 ? wp[lane] : 0u;
-    if (lane == 10) asm volatile("prefetch.global.L1 [%0];" ::"l"(s + p + 160));
-    const uint32_t b = (uint32_t)(a0 & 3) + (uint32_t)lane;
-    const uint32_t w0 = __shfl_sync(FULL, word, b >> 2), w1 = __shfl_sync(FULL, word, (b >> 2) + 1);
-    const uint32_t lo = __funnelshift_r(w0, w1, (b & 3) * 8);  // bytes 0..3
-    const uint32_t b4 = (w1 >> ((b & 3) * 8)) & 0xffu;          // byte 4
-    // what the tag says comes out of a 256-entry table (snappy_tag_entry): header bytes, literal or not, the length
-    // when the tag holds it, and how many of the following bytes are an offset or a length
-    const uint32_t e = lut[lo & 0xffu];
-    const uint32_t hdr = e & 7u, nbytes = (e >> 5) & 7u;
-    const bool lit = (e >> 3) & 1u;
-    const uint32_t raw = (lo >> 8) | (b4 << 24);
-    const uint32_t field = raw & __funnelshift_rc(0xffffffffu, 0u, 32u - 8u * nbytes);  // the low `nbytes` bytes
-    const uint32_t len = (e >> 16) + (((e >> 4) & 1u) ? field + 1u : 0u);             // long literals: length bytes + 1
-    const uint32_t q = p + (uint32_t)lane;
-    const uint32_t src = lit ? q + hdr : (field | (((e >> 8) & 7u) << 8));
-    // input bytes the element takes; a lane past the end of the input starts nothing.  A literal longer than the
-    // input is not sane, so the 32-bit sums below cannot wrap for the lanes that matter
-    const bool inside = q < n;
-    const uint32_t adv = hdr + (lit ? len : 0u);
-    const bool sane = inside && len != 0 && (!lit || len <= n) && adv <= n - q;
-    const uint32_t nxt = sane ? min((uint32_t)lane + adv, 32u) : 32u;
-    // the chain of real element starts
-    uint32_t reach = 1u, jump = nxt;
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-        reach |= __reduce_or_sync(FULL, (((reach >> lane) & 1u) && jump < 32u) ? (1u << jump) : 0u);
-        const uint32_t j2 = __shfl_sync(FULL, jump, jump & 31u);
-        jump = jump < 32u ? j2 : 32u;
-    }
-    const bool mine = ((reach >> lane) & 1u) && inside;
-    const uint32_t mask = __ballot_sync(FULL, mine);
-    // place the output
-    const uint32_t olen = mine && sane ? len : 0u;
-    const uint32_t incl = warp_incl_scan(olen, lane);
-    const uint32_t excl = incl - olen;
-    const uint32_t total = __shfl_sync(FULL, incl, 31);
-    const uint64_t oo = (uint64_t)o + excl;
-    const bool bad = mine && (!sane || oo + len > ulen || (!lit && (src == 0 || (uint64_t)src > oo)));
-    if (__any_sync(FULL, bad)) return false;
-    // a back-reference reads [oo - dist, oo - dist + min(len, dist)); it depends on this window when that ends past o
-    const bool dep = mine && !lit && excl + min(len, src) > src;
-    const bool long_lit = mine && lit && len >= SW_LONG_LITERAL;  // only possible for the window's last element
-    if (mine && !lit && !dep && src > SW_HIST / 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(d + (oo - src)));
-    const int last = 31 - __clz(mask);
-    const uint32_t rank = __popc(mask & ((1u << lane) - 1u));
-    if (mine) {
-        w.out_off[rank] = excl;
-        w.src[rank] = src;
-        w.info[rank] = len | (lit ? SW_LITERAL : 0u) | (dep ? SW_DEPENDENT : 0u) | (long_lit ? SW_LONG : 0u);
-    }
-    if (lane == 0) {
-        w.count = __popc(mask);
-        w.total = total;
-        w.o = o;
-    }
-    p += __shfl_sync(FULL, (uint32_t)lane + adv, last);
-    o += total;
-    return true;
-}
-
-// copier: the bytes of one window
-__device__ __forceinline__ void snappy_copy(const uint8_t* __restrict__ s, uint8_t* d, const SnappyWin& w, uint8_t* hist, int lane) {
-    const uint32_t count = w.count, total = w.total, o = w.o;
-    const bool mine = (uint32_t)lane < count;  // lane r holds element r
-    const uint32_t excl = mine ? w.out_off[lane] : 0u, info = mine ? w.info[lane] : 0u, src = mine ? w.src[lane] : 0u;
-    const uint32_t len = info & SW_LEN;
-    const uint32_t depmask = __ballot_sync(FULL, (info & SW_DEPENDENT) != 0);
-    const uint32_t long_len = __shfl_sync(FULL, (info & SW_LONG) ? len : 0u, (count - 1u) & 31u);
-    uint8_t* const dw = d + o;
-    // pass 1: one output byte per lane
-    const uint32_t body = total - long_len;
-    for (uint32_t v0 = 0; v0 < body; v0 += 32) {
-        const uint32_t starts = __reduce_or_sync(FULL, (mine && excl >= v0 && excl < v0 + 32u) ? (1u << (excl - v0)) : 0u);
-        const uint32_t before = __popc(__ballot_sync(FULL, mine && excl < v0));
-        const uint32_t v = v0 + (uint32_t)lane;
-        if (v < body) {
-            const uint32_t r = before + __popc(starts & (0xffffffffu >> (31 - lane))) - 1u;
-            const uint32_t inf = w.info[r];
-            if (!(inf & (SW_DEPENDENT | SW_LONG))) {
-                const uint32_t k = v - w.out_off[r], sv = w.src[r];
-                uint8_t byte;
-                if (inf & SW_LITERAL) {
-                    byte = s[sv + k];
-                } else {
-                    const uint32_t kk = k < sv ? k : k % sv;
-                    const uint32_t a = o + v - k - sv + kk;  // output position of the source byte, < o
-                    // the ring still holds it unless this window's own output has come round to its slot
-                    byte = (o + total - a <= SW_HIST) ? hist[a & (SW_HIST - 1)] : d[a];
-                }
-                hist[(o + v) & (SW_HIST - 1)] = byte;
-                dw[v] = byte;
-            }
-        }
-    }
-    __syncwarp();
-    // pass 2: what reads this window's own output, in order
-    uint32_t dm = depmask;
-    while (dm) {
-        const int l = __ffs(dm) - 1;
-        dm &= dm - 1;
-        const uint32_t e_off = __shfl_sync(FULL, excl, l), e_len = __shfl_sync(FULL, len, l), e_dist = __shfl_sync(FULL, src, l);
-        // its source starts less than 64 bytes before the window: all of it is in the ring, and none of it is
-        // written by this copy (a source shorter than the copy repeats)
-        const uint32_t eo = o + e_off;
-        for (uint32_t i = lane; i < e_len; i += 32) {
-            const uint32_t kk = i < e_dist ? i : i % e_dist;
-            const uint8_t byte = hist[(eo - e_dist + kk) & (SW_HIST - 1)];
-            hist[(eo + i) & (SW_HIST - 1)] = byte;
-            d[eo + i] = byte;
-        }
-        __syncwarp();
-    }
-    if (long_len) {
-        const uint32_t e_off = __shfl_sync(FULL, excl, (count - 1u) & 31u), e_src = __shfl_sync(FULL, src, (count - 1u) & 31u);
-        warp_copy_fwd(dw + e_off, s + e_src, long_len, lane);
-        for (uint32_t i = (long_len > SW_HIST ? long_len - SW_HIST : 0u) + lane; i < long_len; i += 32)
-            hist[(o + e_off + i) & (SW_HIST - 1)] = s[e_src + i];
-        __syncwarp();
-    }
-}
-
-__device__ __forceinline__ uint32_t ld_volatile(const uint32_t* p) { return *(const volatile uint32_t*)p; }
-__device__ __forceinline__ void st_volatile(uint32_t* p, uint32_t v) { *(volatile uint32_t*)p = v; }
-
-// what the windows leave over: element by element (damaged input ends up here and is reported)
-__device__ __forceinline__ uint32_t snappy_serial(const uint8_t* __restrict__ s, uint32_t n, uint8_t* d, uint64_t ulen, uint32_t p,
-                                                  uint32_t& o, int lane) {
-    while (p < n) {
-        const uint32_t tag = s[p++];
-        const uint32_t t = tag & 3;
-        if (t == 0) {
-            uint32_t l = tag >> 2;
-            if (l >= 60) {
-                const uint32_t extra = l - 59;
-                if (p + extra > n) return ORCB_BUILD_SNAPPY_DECODER;
-                l = 0;
-                for (uint32_t k = 0; k < extra; k++) l |= (uint32_t)s[p + k] << (8 * k);
-                p += extra;
-            }
-            l += 1;
-            if (p + l > n || (uint64_t)o + l > ulen) return ORCB_BUILD_SNAPPY_DECODER;
-            warp_copy_fwd(d + o, s + p, l, lane);
-            __syncwarp();
-            p += l;
-            o += l;
-        } else {
-            uint32_t l, dist;
-            if (t == 1) {
-                if (p + 1 > n) return ORCB_BUILD_SNAPPY_DECODER;
-                l = 4 + ((tag >> 2) & 7);
-                dist = ((tag >> 5) << 8) | s[p];
-                p += 1;
-            } else if (t == 2) {
-                if (p + 2 > n) return ORCB_BUILD_SNAPPY_DECODER;
-                l = 1 + (tag >> 2);
-                dist = s[p] | ((uint32_t)s[p + 1] << 8);
-                p += 2;
-            } else {
-                if (p + 4 > n) return ORCB_BUILD_SNAPPY_DECODER;
-                l = 1 + (tag >> 2);
-                dist = s[p] | ((uint32_t)s[p + 1] << 8) | ((uint32_t)s[p + 2] << 16) | ((uint32_t)s[p + 3] << 24);
-                p += 4;
-            }
-            if (dist == 0 || dist > o || (uint64_t)o + l > ulen) return ORCB_BUILD_SNAPPY_DECODER;
-            warp_copy_match(d, o, dist, l, lane);
-            o += l;
-        }
-    }
-    return o != ulen ? (uint32_t)ORCB_BUILD_SNAPPY_DECODER : 0u;
 }
 
 // uncompressed length preamble (snap::raw::decompress_len, compression.rs:163-165)
@@ -289,46 +68,6 @@ __device__ __forceinline__ uint32_t snappy_preamble(const uint8_t* __restrict__ 
     return ulen > dst_cap ? (uint32_t)ORCB_BUILD_SNAPPY_DECODER : 0u;
 }
 
-// LZ4 block (lz4_flex::block::decompress(src, max), compression.rs:185-195)
-__device__ __forceinline__ uint32_t lz4_block(const uint8_t* __restrict__ s, uint32_t n, uint8_t* d, uint32_t dst_cap, uint32_t& o, int lane) {
-    uint32_t p = 0;
-    while (p < n) {
-        const uint32_t tok = s[p++];
-        uint32_t ll = tok >> 4;
-        if (ll == 15) {
-            for (;;) {
-                if (p >= n) return ORCB_BUILD_LZ4_DECODER;
-                const uint32_t b = s[p++];
-                ll += b;
-                if (b != 255) break;
-            }
-        }
-        if (p + ll > n || o + ll > dst_cap) return ORCB_BUILD_LZ4_DECODER;
-        warp_copy_fwd(d + o, s + p, ll, lane);
-        __syncwarp();
-        p += ll;
-        o += ll;
-        if (p >= n) break;
-        if (p + 2 > n) return ORCB_BUILD_LZ4_DECODER;
-        const uint32_t dist = s[p] | ((uint32_t)s[p + 1] << 8);
-        p += 2;
-        uint32_t ml = tok & 15;
-        if (ml == 15) {
-            for (;;) {
-                if (p >= n) return ORCB_BUILD_LZ4_DECODER;
-                const uint32_t b = s[p++];
-                ml += b;
-                if (b != 255) break;
-            }
-        }
-        ml += 4;
-        if (dist == 0 || dist > o || o + ml > dst_cap) return ORCB_BUILD_LZ4_DECODER;
-        warp_copy_match(d, o, dist, ml, lane);
-        o += ml;
-    }
-    return 0;
-}
-
 __device__ __forceinline__ void chunk_done(const ChunkDesc& c, uint32_t ci, uint32_t fail, uint32_t o, uint32_t* err, uint32_t* out_lens,
                                            int lane) {
     if (!fail && c.expect_len >= 0 && o != (uint32_t)c.expect_len) fail = ORCB_UNEXPECTED;
@@ -338,152 +77,537 @@ __device__ __forceinline__ void chunk_done(const ChunkDesc& c, uint32_t ci, uint
     }
 }
 
-// One chunk per warp: launches with more chunks than the GPU holds warps
-__global__ void __launch_bounds__(128) k_decompress(const ChunkDesc* __restrict__ chunks, uint32_t nchunks, uint32_t* err,
-                                                    uint32_t* out_lens) {
-    __shared__ SnappyWin win_all[4];
-    __shared__ uint8_t hist_all[4][SW_HIST];
-    __shared__ uint32_t lut[256];
-    lut[threadIdx.x] = snappy_tag_entry(threadIdx.x);
-    lut[threadIdx.x + 128] = snappy_tag_entry(threadIdx.x + 128);
-    __syncthreads();
-    const uint32_t ci = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (ci >= nchunks) return;
-    const ChunkDesc& c = chunks[ci];
-    const int lane = threadIdx.x & 31;
-    const uint8_t* s = (const uint8_t*)c.src;
-    uint8_t* d = (uint8_t*)c.dst;
-    const uint32_t n = c.src_len;
-    uint32_t o = 0, fail = 0;
-    if (c.codec == 0) {
-        if (n > c.dst_cap) fail = ORCB_UNEXPECTED;
-        else warp_copy_fwd(d, s, n, lane);
-        o = n;
-    } else if (c.codec == 2) {
-        uint32_t p;
-        uint64_t ulen;
-        fail = snappy_preamble(s, n, c.dst_cap, p, ulen);
-        if (!fail) {
-            SnappyWin& w = win_all[threadIdx.x >> 5];
-            uint8_t* hist = hist_all[threadIdx.x >> 5];
-            while (p < n && snappy_parse(s, n, d, ulen, p, o, w, lut, lane)) {
-                __syncwarp();
-                snappy_copy(s, d, w, hist, lane);
-                __syncwarp();
-            }
-            fail = snappy_serial(s, n, d, ulen, p, o, lane);
-        }
-    } else {
-        fail = lz4_block(s, n, d, c.dst_cap, o, lane);
-    }
-    chunk_done(c, ci, fail, o, err, out_lens, lane);
+// ------------------------------------------------------------------------------------------------
+// Tile decoder (Snappy and LZ4): lane-parallel parsing and lane-per-element copying.
+//
+// A compressed chunk is one chain of elements (Snappy: literal | copy; LZ4: sequence = literals + match), each two or
+// three input bytes on average, so any scheme that spends a warp instruction per element and phase is issue-bound at
+// a few hundred MB/s per warp.  Here a warp takes LZ_TILE (2 KiB) of input at a time:
+//   1. the tile is staged in shared memory, one padded row per 64-byte sub-block (rows overlap by 12 bytes so that a
+//      header is always read inside one row; 19-word rows keep the 32 lanes on different banks);
+//   2. SPECULATIVE WALK: every lane walks the elements of its own sub-block from the sub-block's first byte, which is
+//      usually not an element start, and remembers which positions it visited.  LZ streams re-synchronise within a
+//      few elements, so when the lane before hands over the true entry position it is almost always one the lane
+//      has visited: everything from there on (and the lane's exit position) is then already right.  The hand-over
+//      runs lane by lane (32 short steps); a lane whose walk never met the true chain re-walks alone;
+//   3. every lane walks its now certain elements twice more: once to count elements and output bytes (warp scan ->
+//      rank and output position of each lane's first element), once to write one 32-bit descriptor per element;
+//   4. the descriptors are consumed 32 at a time, ONE ELEMENT PER LANE: a lane copies its own element (<= 32 bytes)
+//      from the staged input (literal) or from a 4 KiB ring of recent output (older bytes from global memory);
+//      elements that read the output of their own group, and elements of 33..64 bytes, follow in order, copied by
+//      the whole warp; the group's output range is then written out from the ring in whole words.
+// Elements longer than 64 bytes, literals that run out of the staged tile and anything irregular are decoded by the
+// element-by-element loop (one element, or - for damaged input - the rest of the chunk, so errors are reported
+// exactly as by the serial decoder).
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t LZ_SB = 64, LZ_TILE = 32 * LZ_SB, LZ_ROW_WORDS = 19, LZ_HIST = 4096, LZ_DESC_CAP = 1024;
+constexpr uint32_t LZ_INLINE = 32, LZ_MAX_ELEM = 64;
+constexpr uint32_t LZ_INVALID = 0xffffffffu;
+constexpr uint32_t LZD_LIT = 1u << 14;  // descriptor: len [0:14) | literal [14] | src [16:32) (literal: tile position; match: distance)
+
+struct LzWarp {
+    uint32_t in[32 * LZ_ROW_WORDS];
+    uint32_t desc[LZ_DESC_CAP];
+    uint8_t hist[LZ_HIST];
+};
+
+// one element (Snappy) / one sequence (LZ4) as the walks see it
+struct LzElem {
+    uint32_t adv;      // input bytes to the next element (LZ_INVALID: cannot be handled here)
+    uint32_t lit_len;  // literal bytes (0: none)
+    uint32_t lit_pos;  // absolute input position of the first literal byte
+    uint32_t m_len;    // match bytes (0: none)
+    uint32_t m_dist;
+};
+
+// 8 input bytes at tile position x (x < LZ_TILE + 4) out of the padded rows
+__device__ __forceinline__ uint64_t lz_window(const uint32_t* in, uint32_t x) {
+    const uint32_t row = min(x >> 6, 31u), col = x - (row << 6);  // col < 76 - 8
+    const uint32_t* r = in + row * LZ_ROW_WORDS + (col >> 2);
+    const uint32_t sh = (col & 3) * 8;
+    const uint32_t w0 = r[0], w1 = r[1], w2 = r[2];
+    return ((uint64_t)__funnelshift_r(w1, w2, sh) << 32) | __funnelshift_r(w0, w1, sh);
+}
+__device__ __forceinline__ uint32_t lz_byte(const uint32_t* in, uint32_t x) {
+    const uint32_t row = min(x >> 6, 31u), col = x - (row << 6);
+    return (in[row * LZ_ROW_WORDS + (col >> 2)] >> ((col & 3) * 8)) & 0xffu;
+}
+// 8 input bytes at absolute position q: from the staged tile when they lie in it, else from global memory
+__device__ __forceinline__ uint64_t lz_fetch(const uint32_t* in, const uint8_t* __restrict__ s, uint32_t tb, uint32_t q) {
+    if (q >= tb && q - tb < LZ_TILE + 4) return lz_window(in, q - tb);
+    uint64_t w = 0;
+    for (int k = 0; k < 8; k++) w |= (uint64_t)s[q + k] << (8 * k);  // arenas are padded: reading past the chunk is safe
+    return w;
 }
 
-// One chunk per pair of warps (two pairs per block): launches the GPU has warps to spare for
-__global__ void __launch_bounds__(128) k_decompress_pair(const ChunkDesc* __restrict__ chunks, uint32_t nchunks, uint32_t* err,
-                                                         uint32_t* out_lens) {
-    __shared__ SnappyPair pairs[2];
+template <int CODEC>
+__device__ __forceinline__ LzElem lz_decode(const uint32_t* in, const uint8_t* __restrict__ s, uint32_t n, uint32_t tb, uint32_t q,
+                                            const uint32_t* lut) {
+    LzElem e;
+    e.lit_len = e.m_len = e.m_dist = 0;
+    e.lit_pos = 0;
+    const uint64_t w = lz_window(in, q - tb);
+    if (CODEC == 2) {
+        const uint32_t lo = (uint32_t)w, b4 = (uint32_t)(w >> 32) & 0xffu;
+        const uint32_t t = lut[lo & 0xffu];
+        const uint32_t hdr = t & 7u, nbytes = (t >> 5) & 7u;
+        const bool lit = (t >> 3) & 1u;
+        const uint32_t raw = (lo >> 8) | (b4 << 24);
+        const uint32_t field = raw & __funnelshift_rc(0xffffffffu, 0u, 32u - 8u * nbytes);
+        if (lit) {
+            const bool longl = (t >> 4) & 1u;
+            if (longl && field >= 0x40000000u) { e.adv = LZ_INVALID; return e; }
+            e.lit_len = (t >> 16) + (longl ? field + 1u : 0u);
+            e.lit_pos = q + hdr;
+            e.adv = hdr + e.lit_len;
+        } else {
+            e.m_len = t >> 16;
+            e.m_dist = field | (((t >> 8) & 7u) << 8);
+            e.adv = hdr;
+        }
+        if (e.adv > n - q) e.adv = LZ_INVALID;  // runs past the end of the chunk
+        return e;
+    }
+    // LZ4: token, literal-length bytes, literals, 2 offset bytes, match-length bytes
+    const uint32_t tok = (uint32_t)w & 0xffu;
+    uint32_t ll = tok >> 4, p = q + 1;
+    if (ll == 15) {
+        uint32_t k = 1;
+        for (;;) {
+            if (k >= 7) { e.adv = LZ_INVALID; return e; }  // length bytes beyond the window: a very long literal
+            const uint32_t b = (uint32_t)(w >> (8 * k)) & 0xffu;
+            k++;
+            ll += b;
+            if (b != 255) break;
+        }
+        p = q + k;
+    }
+    if (p > n || ll > n - p) { e.adv = LZ_INVALID; return e; }
+    e.lit_len = ll;
+    e.lit_pos = p;
+    p += ll;
+    if (p >= n) {  // last sequence: literals only
+        e.adv = p - q;
+        return e;
+    }
+    if (p + 2 > n) { e.adv = LZ_INVALID; return e; }
+    const uint64_t m = lz_fetch(in, s, tb, p);
+    e.m_dist = (uint32_t)m & 0xffffu;
+    uint32_t ml = tok & 15u;
+    p += 2;
+    if (ml == 15) {
+        uint32_t k = 2;
+        for (;;) {
+            if (k >= 8 || p >= n) { e.adv = LZ_INVALID; return e; }
+            const uint32_t b = (uint32_t)(m >> (8 * k)) & 0xffu;
+            k++;
+            p++;
+            ml += b;
+            if (b != 255) break;
+        }
+    }
+    e.m_len = ml + 4;
+    e.adv = p - q;
+    return e;
+}
+
+// refill the ring with the last bytes of output (after an element was written to global memory only)
+__device__ __forceinline__ void lz_hist_reload(uint8_t* hist, const uint8_t* d, uint32_t o, int lane) {
+    const uint32_t from = o > LZ_HIST ? o - LZ_HIST : 0u;
+    for (uint32_t a = from + lane; a < o; a += 32) hist[a & (LZ_HIST - 1)] = __ldcg(d + a);
+    __syncwarp();
+}
+
+// One element / sequence by the whole warp, straight to global memory: what the tiles leave to it (long elements,
+// literals that run out of the staged input).  Returns a status; p and o advance.
+template <int CODEC>
+__device__ __forceinline__ uint32_t lz_serial_step(const uint8_t* __restrict__ s, uint32_t n, uint8_t* d, uint64_t ulen, uint32_t& p,
+                                                   uint32_t& o, int lane) {
+    const uint32_t bad = CODEC == 2 ? (uint32_t)ORCB_BUILD_SNAPPY_DECODER : (uint32_t)ORCB_BUILD_LZ4_DECODER;
+    if (CODEC == 2) {
+        const uint32_t tag = s[p++];
+        const uint32_t t = tag & 3;
+        if (t == 0) {
+            uint64_t l = tag >> 2;
+            if (l >= 60) {
+                const uint32_t extra = (uint32_t)l - 59;
+                if (extra > n - p) return bad;
+                l = 0;
+                for (uint32_t k = 0; k < extra; k++) l |= (uint64_t)s[p + k] << (8 * k);
+                p += extra;
+            }
+            l += 1;
+            if (l > n - p || (uint64_t)o + l > ulen) return bad;
+            warp_copy_fwd(d + o, s + p, (uint32_t)l, lane);
+            __syncwarp();
+            p += (uint32_t)l;
+            o += (uint32_t)l;
+            return 0;
+        }
+        uint32_t l, dist;
+        if (t == 1) {
+            if (p + 1 > n) return bad;
+            l = 4 + ((tag >> 2) & 7);
+            dist = ((tag >> 5) << 8) | s[p];
+            p += 1;
+        } else if (t == 2) {
+            if (p + 2 > n) return bad;
+            l = 1 + (tag >> 2);
+            dist = s[p] | ((uint32_t)s[p + 1] << 8);
+            p += 2;
+        } else {
+            if (p + 4 > n) return bad;
+            l = 1 + (tag >> 2);
+            dist = s[p] | ((uint32_t)s[p + 1] << 8) | ((uint32_t)s[p + 2] << 16) | ((uint32_t)s[p + 3] << 24);
+            p += 4;
+        }
+        if (dist == 0 || dist > o || (uint64_t)o + l > ulen) return bad;
+        warp_copy_match(d, o, dist, l, lane);
+        o += l;
+        return 0;
+    }
+    const uint32_t tok = s[p++];
+    uint64_t ll = tok >> 4;
+    if (ll == 15) {
+        for (;;) {
+            if (p >= n) return bad;
+            const uint32_t b = s[p++];
+            ll += b;
+            if (b != 255) break;
+        }
+    }
+    if (ll > n - p || (uint64_t)o + ll > ulen) return bad;
+    warp_copy_fwd(d + o, s + p, (uint32_t)ll, lane);
+    __syncwarp();
+    p += (uint32_t)ll;
+    o += (uint32_t)ll;
+    if (p >= n) return 0;
+    if (p + 2 > n) return bad;
+    const uint32_t dist = s[p] | ((uint32_t)s[p + 1] << 8);
+    p += 2;
+    uint64_t ml = tok & 15;
+    if (ml == 15) {
+        for (;;) {
+            if (p >= n) return bad;
+            const uint32_t b = s[p++];
+            ml += b;
+            if (b != 255) break;
+        }
+    }
+    ml += 4;
+    if (dist == 0 || dist > o || (uint64_t)o + ml > ulen) return bad;
+    warp_copy_match(d, o, dist, (uint32_t)ml, lane);
+    o += (uint32_t)ml;
+    return 0;
+}
+
+// the rest of a chunk, element by element (damaged input is reported from here)
+template <int CODEC>
+__device__ __forceinline__ uint32_t lz_serial_rest(const uint8_t* __restrict__ s, uint32_t n, uint8_t* d, uint64_t ulen, uint32_t p,
+                                                   uint32_t& o, int lane) {
+    while (p < n) {
+        const uint32_t st = lz_serial_step<CODEC>(s, n, d, ulen, p, o, lane);
+        if (st) return st;
+    }
+    if (CODEC == 2 && o != ulen) return ORCB_BUILD_SNAPPY_DECODER;
+    return 0;
+}
+
+enum : uint32_t { LZT_OK = 0, LZT_CUT = 1, LZT_IRREGULAR = 2 };
+
+// One tile starting at input position p / output position o.  On LZT_OK / LZT_CUT p and o are behind the last element
+// the tile decoded (CUT: the element at p is for lz_serial_step); on LZT_IRREGULAR nothing was decoded.
+template <int CODEC>
+__device__ __forceinline__ uint32_t lz_tile(const uint8_t* __restrict__ s, uint32_t n, uint8_t* d, uint64_t ulen, uint32_t& p,
+                                            uint32_t& o, LzWarp& sm, const uint32_t* lut, int lane, uint32_t& cut_lane_out) {
+    const uint32_t tb = p;
+    // ---- 1. stage the tile: row r = input bytes [tb + 64 r, tb + 64 r + 76)
+    {
+        const uintptr_t a0 = (uintptr_t)(s + tb);
+        const uint32_t* g = (const uint32_t*)(a0 & ~(uintptr_t)3);
+        const uint32_t sh = (uint32_t)(a0 & 3) * 8;
+        for (uint32_t k = lane; k < 32 * LZ_ROW_WORDS; k += 32) {
+            const uint32_t row = k / LZ_ROW_WORDS, j = k - row * LZ_ROW_WORDS;
+            const uint32_t wi = row * 16 + j;
+            // nothing is read more than a few bytes behind the chunk (the arenas are padded, but not by a tile)
+            sm.in[k] = tb + 4u * wi < n + 8u ? __funnelshift_r(__ldg(g + wi), __ldg(g + wi + 1), sh) : 0u;
+        }
+    }
+    __syncwarp();
+    const uint32_t s_i = tb + (uint32_t)lane * LZ_SB;
+    const uint32_t end_i = min(s_i + LZ_SB, n);
+    // ---- 2. speculative walk: positions visited from the sub-block's first byte
+    uint64_t visited = 0;
+    uint32_t exit_i = s_i;
+    if (s_i < n) {
+        uint32_t q = s_i;
+        while (q < end_i) {
+            visited |= 1ull << (q - s_i);
+            const LzElem e = lz_decode<CODEC>(sm.in, s, n, tb, q, lut);
+            if (e.adv == LZ_INVALID) { q = LZ_INVALID; break; }
+            q += e.adv;
+        }
+        exit_i = q;
+    }
+    // ---- hand-over of the true entry positions, lane by lane
+    uint32_t my_entry = LZ_INVALID, final_exit;
+    {
+        uint32_t cur = tb;
+        for (int i = 0; i < 32; i++) {
+            bool rewalk = false;
+            uint32_t my_exit = cur;
+            if (lane == i) {
+                my_entry = cur;
+                if (cur != LZ_INVALID && cur < end_i) {
+                    if ((visited >> (cur - s_i)) & 1ull) my_exit = exit_i;
+                    else rewalk = true;
+                }
+            }
+            if (__shfl_sync(FULL, (int)rewalk, i)) {
+                if (lane == i) {
+                    // the speculative walk never met the true chain: walk again from the entry until it does
+                    uint32_t q = cur;
+                    uint64_t mine = 0;
+                    while (q < end_i) {
+                        if ((visited >> (q - s_i)) & 1ull) break;
+                        mine |= 1ull << (q - s_i);
+                        const LzElem e = lz_decode<CODEC>(sm.in, s, n, tb, q, lut);
+                        if (e.adv == LZ_INVALID) { q = LZ_INVALID; break; }
+                        q += e.adv;
+                    }
+                    if (q != LZ_INVALID && q < end_i) {  // merged: the old walk is right from here on
+                        visited = mine | (visited & ~((1ull << (q - s_i)) - 1ull));
+                        my_exit = exit_i;
+                    } else {
+                        visited = mine;
+                        my_exit = q;
+                    }
+                    exit_i = my_exit;
+                }
+            }
+            cur = __shfl_sync(FULL, my_exit, i);
+        }
+        final_exit = cur;
+    }
+    // ---- 3a. count: elements and output bytes of every lane; a lane stops in front of what the tile cannot take
+    uint32_t cnt = 0, bytes = 0, stop = LZ_INVALID;  // stop: position of the element the lane stopped at
+    bool irregular = my_entry == LZ_INVALID;
+    if (!irregular && my_entry < end_i) {
+        uint32_t q = my_entry;
+        while (q < end_i) {
+            const LzElem e = lz_decode<CODEC>(sm.in, s, n, tb, q, lut);
+            if (e.adv == LZ_INVALID || e.lit_len > LZ_MAX_ELEM || e.m_len > LZ_MAX_ELEM ||
+                (e.lit_len && e.lit_pos + e.lit_len > tb + LZ_TILE + 8)) {
+                stop = q;
+                break;
+            }
+            cnt += (e.lit_len ? 1u : 0u) + (e.m_len ? 1u : 0u);
+            bytes += e.lit_len + e.m_len;
+            q += e.adv;
+        }
+    }
+    // the tile ends in front of the first stop; lanes behind it are dropped
+    const uint32_t stopmask = __ballot_sync(FULL, stop != LZ_INVALID || irregular);
+    const int cut_lane = stopmask ? __ffs(stopmask) - 1 : 32;
+    if (lane > cut_lane) { cnt = 0; bytes = 0; }
+    const bool cut_irregular = cut_lane < 32 && __shfl_sync(FULL, (int)irregular, cut_lane & 31);
+    const uint32_t cnt_incl = warp_incl_scan(cnt, lane), bytes_incl = warp_incl_scan(bytes, lane);
+    const uint32_t total_cnt = __shfl_sync(FULL, cnt_incl, 31), total_bytes = __shfl_sync(FULL, bytes_incl, 31);
+    cut_lane_out = (uint32_t)cut_lane;
+    if (cut_irregular && total_cnt == 0) return LZT_IRREGULAR;
+    if ((uint64_t)o + total_bytes > ulen) return LZT_IRREGULAR;  // output past the announced length: the serial loop reports it
+    // ---- 3b. emit the descriptors
+    bool bad = false;
+    if (cnt) {
+        uint32_t q = my_entry, r = cnt_incl - cnt, op = o + (bytes_incl - bytes);
+        const uint32_t lim = stop != LZ_INVALID ? stop : end_i;
+        while (q < lim) {
+            const LzElem e = lz_decode<CODEC>(sm.in, s, n, tb, q, lut);
+            if (e.lit_len) {
+                sm.desc[r++] = e.lit_len | LZD_LIT | ((e.lit_pos - tb) << 16);
+                op += e.lit_len;
+            }
+            if (e.m_len) {
+                if (e.m_dist == 0 || e.m_dist > op || e.m_dist > 0xffffu) bad = true;
+                sm.desc[r++] = e.m_len | (e.m_dist << 16);
+                op += e.m_len;
+            }
+            q += e.adv;
+        }
+    }
+    if (__any_sync(FULL, bad)) return LZT_IRREGULAR;
+    __syncwarp();
+    // where the next tile (or the serial step) starts
+    uint32_t next_p;
+    if (cut_lane < 32) next_p = __shfl_sync(FULL, stop, cut_lane);
+    else next_p = final_exit;
+    // ---- 4. copy, 32 elements at a time
+    const bool words_ok = (((uintptr_t)d) & 3) == 0;
+    uint32_t gO = o;
+    for (uint32_t g0 = 0; g0 < total_cnt; g0 += 32) {
+        const uint32_t di = g0 + (uint32_t)lane;
+        const uint32_t desc = di < total_cnt ? sm.desc[di] : 0u;
+        const uint32_t len = desc & 0x3fffu, src = desc >> 16;
+        const bool lit = (desc & LZD_LIT) != 0;
+        const uint32_t incl = warp_incl_scan(len, lane);
+        const uint32_t T = __shfl_sync(FULL, incl, 31);
+        const uint32_t op = gO + incl - len, gEnd = gO + T;
+        // a match reads [op - src, op - src + min(len, src)); it depends on this group when that ends behind gO
+        const bool dep = len && !lit && op - src + min(len, src) > gO;
+        const bool later = len && (dep || len > LZ_INLINE);
+        if (len && !later) {
+            if (lit) {
+                for (uint32_t k = 0; k < len; k++) sm.hist[(op + k) & (LZ_HIST - 1)] = (uint8_t)lz_byte(sm.in, src + k);
+            } else {
+                const uint32_t a0 = op - src;
+                if (gEnd - a0 <= LZ_HIST) {
+                    for (uint32_t k = 0; k < len; k++) sm.hist[(op + k) & (LZ_HIST - 1)] = sm.hist[(a0 + k) & (LZ_HIST - 1)];
+                } else {
+                    for (uint32_t k = 0; k < len; k++) {
+                        const uint32_t a = a0 + k;
+                        sm.hist[(op + k) & (LZ_HIST - 1)] = (gEnd - a <= LZ_HIST) ? sm.hist[a & (LZ_HIST - 1)] : __ldcg(d + a);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        uint32_t lm = __ballot_sync(FULL, later);
+        while (lm) {
+            const int l = __ffs(lm) - 1;
+            lm &= lm - 1;
+            const uint32_t e_len = __shfl_sync(FULL, len, l), e_src = __shfl_sync(FULL, src, l), e_op = __shfl_sync(FULL, op, l);
+            const bool e_lit = __shfl_sync(FULL, (int)lit, l);
+            if (e_lit) {
+                for (uint32_t k = lane; k < e_len; k += 32) sm.hist[(e_op + k) & (LZ_HIST - 1)] = (uint8_t)lz_byte(sm.in, e_src + k);
+            } else if (e_src >= e_len || e_src >= 32) {
+                // source and destination do not overlap within one step of 32 bytes
+                for (uint32_t k0 = 0; k0 < e_len; k0 += 32) {
+                    const uint32_t k = k0 + lane;
+                    uint8_t b = 0;
+                    if (k < e_len) {
+                        const uint32_t a = e_op - e_src + k;
+                        b = (gEnd - a <= LZ_HIST) ? sm.hist[a & (LZ_HIST - 1)] : __ldcg(d + a);
+                    }
+                    __syncwarp();
+                    if (k < e_len) sm.hist[(e_op + k) & (LZ_HIST - 1)] = b;
+                    __syncwarp();
+                }
+            } else {
+                // short period: byte k repeats byte k mod dist of the source
+                const uint32_t a0 = e_op - e_src;
+                uint8_t pat = 0;
+                if ((uint32_t)lane < e_src) {
+                    const uint32_t a = a0 + lane;
+                    pat = (gEnd - a <= LZ_HIST) ? sm.hist[a & (LZ_HIST - 1)] : __ldcg(d + a);
+                }
+                __syncwarp();
+                for (uint32_t k0 = 0; k0 < e_len; k0 += 32) {
+                    const uint32_t k = k0 + lane;
+                    const uint8_t b = (uint8_t)__shfl_sync(FULL, (uint32_t)pat, (int)(k % e_src));
+                    if (k < e_len) sm.hist[(e_op + k) & (LZ_HIST - 1)] = b;
+                }
+            }
+            __syncwarp();
+        }
+        // write the group's bytes out of the ring
+        if (words_ok) {
+            const uint32_t a_head = min((gO + 3u) & ~3u, gEnd), a_tail = max(gEnd & ~3u, a_head);
+            if (gO + lane < a_head) d[gO + lane] = sm.hist[(gO + lane) & (LZ_HIST - 1)];
+            for (uint32_t a = a_head + 4u * lane; a < a_tail; a += 128)
+                *(uint32_t*)(d + a) = *(const uint32_t*)(sm.hist + (a & (LZ_HIST - 1)));
+            if (a_tail + lane < gEnd) d[a_tail + lane] = sm.hist[(a_tail + lane) & (LZ_HIST - 1)];
+        } else {
+            for (uint32_t a = gO + lane; a < gEnd; a += 32) d[a] = sm.hist[a & (LZ_HIST - 1)];
+        }
+        __syncwarp();
+        gO = gEnd;
+    }
+    o = gO;
+    p = next_p;
+    return cut_lane < 32 ? LZT_CUT : LZT_OK;
+}
+
+template <int CODEC>
+__device__ __forceinline__ uint32_t lz_chunk(const uint8_t* __restrict__ s, uint32_t n, uint8_t* d, uint64_t ulen, uint32_t p, uint32_t& o,
+                                             LzWarp& sm, const uint32_t* lut, int lane) {
+    uint32_t serial_budget = 0, early_cuts = 0;
+    while (p < n) {
+        if (serial_budget) {
+            const uint32_t st = lz_serial_step<CODEC>(s, n, d, ulen, p, o, lane);
+            if (st) return st;
+            if (--serial_budget == 0) lz_hist_reload(sm.hist, d, o, lane);
+            continue;
+        }
+        uint32_t cut_lane = 32;
+        const uint32_t r = lz_tile<CODEC>(s, n, d, ulen, p, o, sm, lut, lane, cut_lane);
+        if (r == LZT_IRREGULAR) return lz_serial_rest<CODEC>(s, n, d, ulen, p, o, lane);
+        if (r == LZT_CUT) {
+            // data made of long elements: the more often tiles end early, the longer the serial loop keeps the chunk
+            early_cuts = cut_lane < 8 ? min(early_cuts + 1, 6u) : 0u;
+            serial_budget = 1u << early_cuts;
+        } else {
+            early_cuts = 0;
+        }
+    }
+    if (CODEC == 2 && o != ulen) return ORCB_BUILD_SNAPPY_DECODER;
+    return 0;
+}
+
+// Persistent warps over the chunk list (most expensive chunks first, see plan.cc); one chunk per warp at a time.
+__global__ void __launch_bounds__(128) k_decompress(const ChunkDesc* __restrict__ chunks, uint32_t nchunks, uint32_t* err,
+                                                    uint32_t* out_lens, uint32_t* counter) {
+    __shared__ LzWarp warp_sm[4];
     __shared__ uint32_t lut[256];
     lut[threadIdx.x] = snappy_tag_entry(threadIdx.x);
     lut[threadIdx.x + 128] = snappy_tag_entry(threadIdx.x + 128);
-    if (threadIdx.x < 2) {
-        pairs[threadIdx.x].head = 0;
-        pairs[threadIdx.x].tail = 0;
-    }
     __syncthreads();
-    const uint32_t pair_in_block = threadIdx.x >> 6;
-    const uint32_t ci = blockIdx.x * 2 + pair_in_block;
-    if (ci >= nchunks) return;
-    const bool parser = ((threadIdx.x >> 5) & 1u) == 0;
-    const ChunkDesc& c = chunks[ci];
     const int lane = threadIdx.x & 31;
-    const uint8_t* s = (const uint8_t*)c.src;
-    uint8_t* d = (uint8_t*)c.dst;
-    const uint32_t n = c.src_len;
-    SnappyPair& sp = pairs[pair_in_block];
-    uint32_t o = 0, fail = 0;
-    if (c.codec == 0) {
-        // both warps copy, half each
-        const uint32_t half = (n / 2) & ~127u;
-        if (n > c.dst_cap) fail = ORCB_UNEXPECTED;
-        else if (parser) warp_copy_fwd(d, s, half, lane);
-        else warp_copy_fwd(d + half, s + half, n - half, lane);
-        if (parser) return;
-        o = n;
-    } else if (c.codec == 2) {
-        uint32_t p;
-        uint64_t ulen;
-        fail = snappy_preamble(s, n, c.dst_cap, p, ulen);  // both warps read it; the copier reports
-        if (parser) {
-            // ---- parser: descriptors of regular windows, then END or FALLBACK
-            if (fail) return;
-            uint32_t head = 0;
-            for (;;) {
-                while (head - ld_volatile(&sp.tail) >= SW_QUEUE) {}
-                __threadfence_block();
-                SnappyWin& w = sp.win[head % SW_QUEUE];
-                uint32_t state = SW_WINDOW;
-                if (p >= n) state = SW_END;
-                else if (!snappy_parse(s, n, d, ulen, p, o, w, lut, lane)) state = SW_FALLBACK;
-                if (lane == 0) {
-                    w.state = state;
-                    if (state != SW_WINDOW) {
-                        w.o = o;
-                        w.p = p;
-                    }
-                }
-                __syncwarp();
-                __threadfence_block();
-                head++;
-                if (lane == 0) st_volatile(&sp.head, head);
-                if (state != SW_WINDOW) return;
-            }
+    LzWarp& sm = warp_sm[threadIdx.x >> 5];
+    for (;;) {
+        uint32_t ci = 0;
+        if (lane == 0) ci = atomicAdd(counter, 1u);
+        ci = __shfl_sync(FULL, ci, 0);
+        if (ci >= nchunks) return;
+        const ChunkDesc& c = chunks[ci];
+        const uint8_t* s = (const uint8_t*)c.src;
+        uint8_t* d = (uint8_t*)c.dst;
+        const uint32_t n = c.src_len;
+        uint32_t o = 0, fail = 0;
+        if (c.codec == 0) {
+            if (n > c.dst_cap) fail = ORCB_UNEXPECTED;
+            else warp_copy_fwd(d, s, n, lane);
+            o = n;
+        } else if (c.codec == 2) {
+            uint32_t p;
+            uint64_t ulen;
+            fail = snappy_preamble(s, n, c.dst_cap, p, ulen);
+            if (!fail) fail = lz_chunk<2>(s, n, d, ulen, p, o, sm, lut, lane);
+        } else {
+            fail = lz_chunk<4>(s, n, d, c.dst_cap, 0, o, sm, lut, lane);
+            // the size of a stream's last LZ4 chunk is only known here: what the layout reserved beyond it reads as zeros
+            if (c.expect_len < 0 && !fail)
+                for (uint32_t a = o + lane; a < c.dst_cap; a += 32) d[a] = 0;
         }
-        // ---- copier
-        if (!fail) {
-            uint32_t tail = 0;
-            for (;;) {
-                while (ld_volatile(&sp.head) == tail) {}
-                __threadfence_block();
-                const SnappyWin& w = sp.win[tail % SW_QUEUE];
-                const uint32_t state = w.state;
-                if (state != SW_WINDOW) {
-                    o = w.o;
-                    p = state == SW_END ? n : w.p;
-                    break;
-                }
-                snappy_copy(s, d, w, sp.hist, lane);
-                __syncwarp();
-                __threadfence_block();
-                tail++;
-                if (lane == 0) st_volatile(&sp.tail, tail);
-            }
-            fail = snappy_serial(s, n, d, ulen, p, o, lane);
-        }
-    } else {
-        if (parser) return;
-        fail = lz4_block(s, n, d, c.dst_cap, o, lane);
+        chunk_done(c, ci, fail, o, err, out_lens, lane);
+        __syncwarp();
     }
-    chunk_done(c, ci, fail, o, err, out_lens, lane);
 }
 
 // ------------------------------------------------------------------------------------------------
 // host-side launch wrappers
 // ------------------------------------------------------------------------------------------------
-int launch_decompress(const ChunkDesc* c, uint32_t n, uint32_t* err, uint32_t* out_lens, cudaStream_t st) {
+int launch_decompress(const ChunkDesc* c, uint32_t n, uint32_t* err, uint32_t* out_lens, uint32_t* counter, cudaStream_t st) {
     if (!n) return 0;
-    // the pair kernel while all its warps are resident at once: 16 blocks of two pairs per SM
-    // (ORCB_DECOMP_PAIR=0/1 forces either, for measurements)
-    static int sm_count = 0;
-    if (!sm_count) {
-        int dev = 0;
+    static int ctas = 0;
+    if (!ctas) {
+        int dev = 0, sms = 148, per_sm = 4;
         cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0) sm_count = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decompress, 128, 0);
+        ctas = sms * (per_sm > 0 ? per_sm : 1);
     }
-    bool pair = n <= (uint32_t)sm_count * 32u;
-    if (const char* e = getenv("ORCB_DECOMP_PAIR")) pair = e[0] == '1';
-    if (pair) k_decompress_pair<<<(n + 1) / 2, 128, 0, st>>>(c, n, err, out_lens);
-    else k_decompress<<<blocks_for_warps(n, 4), 128, 0, st>>>(c, n, err, out_lens);
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)ctas, ((uint64_t)n + 3) / 4);
+    k_decompress<<<grid, 128, 0, st>>>(c, n, err, out_lens, counter);
     LAUNCH_CHECK();
     return 0;
 }

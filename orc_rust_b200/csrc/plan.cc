@@ -100,6 +100,13 @@ void Job::plan() {
             std::stable_sort(int_segs_.begin(), int_segs_.end(), [](const Seg& a, const Seg& b) { return a.run_cap > b.run_cap; });
     }
 
+    // chunks that take longest first (compressed before stored, long before short): the persistent decompression
+    // warps draw them in this order, so the launch does not end on one late, expensive chunk
+    std::stable_sort(chunks_.begin(), chunks_.end(), [](const ChunkDesc& a, const ChunkDesc& b) {
+        const uint64_t ka = ((uint64_t)(a.codec != 0) << 32) | a.src_len, kb = ((uint64_t)(b.codec != 0) << 32) | b.src_len;
+        return ka > kb;
+    });
+
     if (pool_blocks_) {
         run_table_ = alloc(AR_TMP, (uint64_t)pool_blocks_ * 32 * sizeof(RunRec));
         block_recs_ = alloc(AR_TMP, (uint64_t)pool_blocks_ * sizeof(BlockRec));

@@ -1,0 +1,103 @@
+/* Small LZ4-block and Snappy-raw COMPRESSORS (test and bench tooling, C twins of tools/blockcodecs.py):
+ * pyarrow's ORC writer stores every LZ4 chunk uncompressed, so ORC files with real LZ4 chunks (and Snappy files with
+ * the same chunking) are produced by tools/orc_recompress.py with these.  Greedy matcher over a hash table of 4-byte
+ * sequences; the output is what any conforming decoder accepts, not what a particular encoder would write.
+ * Built by tools/lzcodec.py with gcc. */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define HASH_BITS 15
+static inline uint32_t rd32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+static inline uint32_t hash4(uint32_t v) { return (v * 2654435761u) >> (32 - HASH_BITS); }
+
+/* worst case: LZ4 n + n/255 + 16, Snappy 32 + n + n/6 */
+size_t lzc_bound(size_t n) { return n + n / 6 + 64; }
+
+size_t lzc_lz4_compress(const uint8_t* src, size_t n, uint8_t* dst) {
+    int32_t* table = (int32_t*)malloc(sizeof(int32_t) << HASH_BITS);
+    for (int i = 0; i < (1 << HASH_BITS); i++) table[i] = -1;
+    uint8_t* o = dst;
+    size_t i = 0, lit = 0;
+    /* LZ4 end-of-block rules: the last 5 bytes are literals, the last match starts >= 12 bytes before the end */
+    const size_t match_limit = n >= 12 ? n - 12 : 0;
+    while (n >= 13 && i <= match_limit) {
+        const uint32_t h = hash4(rd32(src + i));
+        const int32_t j = table[h];
+        table[h] = (int32_t)i;
+        if (j >= 0 && i - (size_t)j <= 65535 && rd32(src + j) == rd32(src + i)) {
+            size_t ml = 4;
+            const size_t max_ml = n - 5 - i;
+            while (ml < max_ml && src[j + ml] == src[i + ml]) ml++;
+            if (ml >= 4) {
+                const size_t ll = i - lit, dist = i - (size_t)j;
+                *o++ = (uint8_t)(((ll < 15 ? ll : 15) << 4) | (ml - 4 < 15 ? ml - 4 : 15));
+                if (ll >= 15) { size_t v = ll - 15; while (v >= 255) { *o++ = 255; v -= 255; } *o++ = (uint8_t)v; }
+                memcpy(o, src + lit, ll); o += ll;
+                *o++ = (uint8_t)(dist & 255); *o++ = (uint8_t)(dist >> 8);
+                if (ml - 4 >= 15) { size_t v = ml - 4 - 15; while (v >= 255) { *o++ = 255; v -= 255; } *o++ = (uint8_t)v; }
+                i += ml;
+                lit = i;
+                continue;
+            }
+        }
+        i++;
+    }
+    {
+        const size_t ll = n - lit;
+        *o++ = (uint8_t)((ll < 15 ? ll : 15) << 4);
+        if (ll >= 15) { size_t v = ll - 15; while (v >= 255) { *o++ = 255; v -= 255; } *o++ = (uint8_t)v; }
+        memcpy(o, src + lit, ll); o += ll;
+    }
+    free(table);
+    return (size_t)(o - dst);
+}
+
+static uint8_t* snappy_literal(uint8_t* o, const uint8_t* p, size_t ll) {
+    if (!ll) return o;
+    if (ll <= 60) *o++ = (uint8_t)((ll - 1) << 2);
+    else if (ll <= 256) { *o++ = 60 << 2; *o++ = (uint8_t)(ll - 1); }
+    else if (ll <= 65536) { *o++ = 61 << 2; *o++ = (uint8_t)((ll - 1) & 255); *o++ = (uint8_t)((ll - 1) >> 8); }
+    else { *o++ = 62 << 2; *o++ = (uint8_t)((ll - 1) & 255); *o++ = (uint8_t)(((ll - 1) >> 8) & 255); *o++ = (uint8_t)((ll - 1) >> 16); }
+    memcpy(o, p, ll);
+    return o + ll;
+}
+
+size_t lzc_snappy_compress(const uint8_t* src, size_t n, uint8_t* dst) {
+    int32_t* table = (int32_t*)malloc(sizeof(int32_t) << HASH_BITS);
+    for (int i = 0; i < (1 << HASH_BITS); i++) table[i] = -1;
+    uint8_t* o = dst;
+    { size_t v = n; while (v >= 128) { *o++ = (uint8_t)(v | 128); v >>= 7; } *o++ = (uint8_t)v; }
+    size_t i = 0, lit = 0;
+    while (i + 4 <= n) {
+        const uint32_t h = hash4(rd32(src + i));
+        const int32_t j = table[h];
+        table[h] = (int32_t)i;
+        if (j >= 0 && i - (size_t)j <= 65535 && rd32(src + j) == rd32(src + i)) {
+            size_t ml = 4;
+            while (i + ml < n && src[j + ml] == src[i + ml]) ml++;
+            const size_t dist = i - (size_t)j;
+            o = snappy_literal(o, src + lit, i - lit);
+            size_t left = ml;
+            while (left > 0) {
+                size_t take = left < 64 ? left : 64;
+                if (left - take >= 1 && left - take <= 3) take = left - 4 >= 4 ? left - 4 : take;  /* keep >= 4 for the next copy */
+                if (take >= 4 && take <= 11 && dist < 2048) {
+                    *o++ = (uint8_t)(1 | ((take - 4) << 2) | ((dist >> 8) << 5));
+                    *o++ = (uint8_t)(dist & 255);
+                } else {
+                    *o++ = (uint8_t)(2 | ((take - 1) << 2));
+                    *o++ = (uint8_t)(dist & 255); *o++ = (uint8_t)(dist >> 8);
+                }
+                left -= take;
+            }
+            i += ml;
+            lit = i;
+            continue;
+        }
+        i++;
+    }
+    o = snappy_literal(o, src + lit, n - lit);
+    free(table);
+    return (size_t)(o - dst);
+}

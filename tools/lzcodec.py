@@ -1,0 +1,45 @@
+"""ctypes front of tools/lzcodec.c (LZ4-block / Snappy-raw compressors for test and bench inputs)."""
+import ctypes
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(HERE, "_liblzcodec.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        src = os.path.join(HERE, "lzcodec.c")
+        if not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+            subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-o", _SO, src])
+        L = ctypes.CDLL(_SO)
+        for f in (L.lzc_lz4_compress, L.lzc_snappy_compress):
+            f.restype = ctypes.c_size_t
+            f.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p]
+        L.lzc_bound.restype = ctypes.c_size_t
+        L.lzc_bound.argtypes = [ctypes.c_size_t]
+        _lib = L
+    return _lib
+
+
+def compress_block(kind: str, data: bytes) -> bytes:
+    L = lib()
+    buf = ctypes.create_string_buffer(L.lzc_bound(len(data)))
+    n = (L.lzc_lz4_compress if kind == "lz4" else L.lzc_snappy_compress)(bytes(data), len(data), buf)
+    return buf.raw[:n]
+
+
+def orc_frame(data: bytes, kind: str, block_size: int, keep_if_smaller: bool = True) -> bytes:
+    """`data` as an ORC stream: <= block_size chunks, each compressed (or stored when that is not smaller) behind the
+    3-byte header (len << 1) | is_original (reference src/compression.rs:113-123)."""
+    out = bytearray()
+    for p in range(0, len(data), block_size):
+        chunk = data[p:p + block_size]
+        c = compress_block(kind, chunk)
+        if keep_if_smaller and len(c) >= len(chunk):
+            out += ((len(chunk) << 1) | 1).to_bytes(3, "little") + chunk
+        else:
+            out += (len(c) << 1).to_bytes(3, "little") + c
+    return bytes(out)
