@@ -101,7 +101,7 @@ __device__ __forceinline__ void chunk_done(const ChunkDesc& c, uint32_t ci, uint
 // exactly as by the serial decoder).
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t LZ_SB = 64, LZ_TILE = 32 * LZ_SB, LZ_ROW_WORDS = 19, LZ_HIST = 4096, LZ_DESC_CAP = 1024;
-constexpr uint32_t LZ_INLINE = 32, LZ_MAX_ELEM = 64;
+constexpr uint32_t LZ_INLINE = 32, LZ_MAX_ELEM = 64, LZ_MAX_MATCH = 1024;
 constexpr uint32_t LZ_INVALID = 0xffffffffu;
 constexpr uint32_t LZD_LIT = 1u << 14;  // descriptor: len [0:14) | literal [14] | src [16:32) (literal: tile position; match: distance)
 
@@ -140,12 +140,43 @@ __device__ __forceinline__ uint64_t lz_fetch(const uint32_t* in, const uint8_t* 
     return w;
 }
 
-template <int CODEC>
+// DIST = false: lengths and `adv` only (the walks that do not write descriptors); most elements then need no more
+// than their first byte
+template <int CODEC, bool DIST = true>
 __device__ __forceinline__ LzElem lz_decode(const uint32_t* in, const uint8_t* __restrict__ s, uint32_t n, uint32_t tb, uint32_t q,
                                             const uint32_t* lut) {
     LzElem e;
     e.lit_len = e.m_len = e.m_dist = 0;
     e.lit_pos = 0;
+    if (!DIST) {
+        const uint32_t b0 = lz_byte(in, q - tb);
+        if (CODEC == 2) {
+            const uint32_t t = lut[b0];
+            if (!((t >> 4) & 1u)) {  // not a literal with length bytes
+                const uint32_t hdr = t & 7u;
+                if ((t >> 3) & 1u) {
+                    e.lit_len = t >> 16;
+                    e.lit_pos = q + hdr;
+                    e.adv = hdr + e.lit_len;
+                } else {
+                    e.m_len = t >> 16;
+                    e.adv = hdr;
+                }
+                if (e.adv > n - q) e.adv = LZ_INVALID;
+                return e;
+            }
+        } else if ((b0 >> 4) != 15u && (b0 & 15u) != 15u) {
+            const uint32_t ll = b0 >> 4;
+            if (ll > n - (q + 1)) { e.adv = LZ_INVALID; return e; }
+            e.lit_len = ll;
+            e.lit_pos = q + 1;
+            if (q + 1 + ll >= n) { e.adv = 1 + ll; return e; }  // last sequence: literals only
+            if (q + 1 + ll + 2 > n) { e.adv = LZ_INVALID; return e; }
+            e.m_len = (b0 & 15u) + 4u;
+            e.adv = 1 + ll + 2;
+            return e;
+        }
+    }
     const uint64_t w = lz_window(in, q - tb);
     if (CODEC == 2) {
         const uint32_t lo = (uint32_t)w, b4 = (uint32_t)(w >> 32) & 0xffu;
@@ -214,7 +245,13 @@ __device__ __forceinline__ LzElem lz_decode(const uint32_t* in, const uint8_t* _
 // refill the ring with the last bytes of output (after an element was written to global memory only)
 __device__ __forceinline__ void lz_hist_reload(uint8_t* hist, const uint8_t* d, uint32_t o, int lane) {
     const uint32_t from = o > LZ_HIST ? o - LZ_HIST : 0u;
-    for (uint32_t a = from + lane; a < o; a += 32) hist[a & (LZ_HIST - 1)] = __ldcg(d + a);
+    if ((((uintptr_t)d) & 3) == 0) {
+        // whole words (a word that reaches behind o brings bytes the ring does not hold yet: they are written before read)
+        for (uint32_t a = (from & ~3u) + 4u * lane; a < o; a += 128)
+            *(uint32_t*)(hist + (a & (LZ_HIST - 1))) = __ldcg((const uint32_t*)(d + a));
+    } else {
+        for (uint32_t a = from + lane; a < o; a += 32) hist[a & (LZ_HIST - 1)] = __ldcg(d + a);
+    }
     __syncwarp();
 }
 
@@ -326,7 +363,9 @@ __device__ __forceinline__ uint32_t lz_tile(const uint8_t* __restrict__ s, uint3
         const uintptr_t a0 = (uintptr_t)(s + tb);
         const uint32_t* g = (const uint32_t*)(a0 & ~(uintptr_t)3);
         const uint32_t sh = (uint32_t)(a0 & 3) * 8;
-        for (uint32_t k = lane; k < 32 * LZ_ROW_WORDS; k += 32) {
+#pragma unroll
+        for (uint32_t it = 0; it < LZ_ROW_WORDS; it++) {
+            const uint32_t k = it * 32 + (uint32_t)lane;
             const uint32_t row = k / LZ_ROW_WORDS, j = k - row * LZ_ROW_WORDS;
             const uint32_t wi = row * 16 + j;
             // nothing is read more than a few bytes behind the chunk (the arenas are padded, but not by a tile)
@@ -343,51 +382,49 @@ __device__ __forceinline__ uint32_t lz_tile(const uint8_t* __restrict__ s, uint3
         uint32_t q = s_i;
         while (q < end_i) {
             visited |= 1ull << (q - s_i);
-            const LzElem e = lz_decode<CODEC>(sm.in, s, n, tb, q, lut);
+            const LzElem e = lz_decode<CODEC, false>(sm.in, s, n, tb, q, lut);
             if (e.adv == LZ_INVALID) { q = LZ_INVALID; break; }
             q += e.adv;
         }
         exit_i = q;
     }
-    // ---- hand-over of the true entry positions, lane by lane
-    uint32_t my_entry = LZ_INVALID, final_exit;
-    {
+    // ---- hand-over of the true entry positions, lane by lane.  A lane whose walk never met the position it is handed
+    //      walks again from there; all such lanes do so at once, then the hand-over is repeated (the first of them had
+    //      the right entry for certain, so every round settles at least one lane; usually one round settles all).
+    uint32_t my_entry = LZ_INVALID, final_exit = tb;
+    for (int round = 0; round < 34; round++) {
         uint32_t cur = tb;
+        bool flagged = false;
         for (int i = 0; i < 32; i++) {
-            bool rewalk = false;
             uint32_t my_exit = cur;
             if (lane == i) {
                 my_entry = cur;
                 if (cur != LZ_INVALID && cur < end_i) {
-                    if ((visited >> (cur - s_i)) & 1ull) my_exit = exit_i;
-                    else rewalk = true;
-                }
-            }
-            if (__shfl_sync(FULL, (int)rewalk, i)) {
-                if (lane == i) {
-                    // the speculative walk never met the true chain: walk again from the entry until it does
-                    uint32_t q = cur;
-                    uint64_t mine = 0;
-                    while (q < end_i) {
-                        if ((visited >> (q - s_i)) & 1ull) break;
-                        mine |= 1ull << (q - s_i);
-                        const LzElem e = lz_decode<CODEC>(sm.in, s, n, tb, q, lut);
-                        if (e.adv == LZ_INVALID) { q = LZ_INVALID; break; }
-                        q += e.adv;
-                    }
-                    if (q != LZ_INVALID && q < end_i) {  // merged: the old walk is right from here on
-                        visited = mine | (visited & ~((1ull << (q - s_i)) - 1ull));
-                        my_exit = exit_i;
-                    } else {
-                        visited = mine;
-                        my_exit = q;
-                    }
-                    exit_i = my_exit;
+                    my_exit = exit_i;
+                    flagged = !((visited >> (cur - s_i)) & 1ull);
                 }
             }
             cur = __shfl_sync(FULL, my_exit, i);
         }
         final_exit = cur;
+        if (!__any_sync(FULL, flagged)) break;
+        if (flagged) {
+            uint32_t q = my_entry;
+            uint64_t mine = 0;
+            while (q < end_i) {
+                if ((visited >> (q - s_i)) & 1ull) break;
+                mine |= 1ull << (q - s_i);
+                const LzElem e = lz_decode<CODEC, false>(sm.in, s, n, tb, q, lut);
+                if (e.adv == LZ_INVALID) { q = LZ_INVALID; break; }
+                q += e.adv;
+            }
+            if (q != LZ_INVALID && q < end_i) {  // merged: the old walk is right from here on
+                visited = mine | (visited & ~((1ull << (q - s_i)) - 1ull));
+            } else {
+                visited = mine;
+                exit_i = q;
+            }
+        }
     }
     // ---- 3a. count: elements and output bytes of every lane; a lane stops in front of what the tile cannot take
     uint32_t cnt = 0, bytes = 0, stop = LZ_INVALID;  // stop: position of the element the lane stopped at
@@ -395,24 +432,36 @@ __device__ __forceinline__ uint32_t lz_tile(const uint8_t* __restrict__ s, uint3
     if (!irregular && my_entry < end_i) {
         uint32_t q = my_entry;
         while (q < end_i) {
-            const LzElem e = lz_decode<CODEC>(sm.in, s, n, tb, q, lut);
-            if (e.adv == LZ_INVALID || e.lit_len > LZ_MAX_ELEM || e.m_len > LZ_MAX_ELEM ||
-                (e.lit_len && e.lit_pos + e.lit_len > tb + LZ_TILE + 8)) {
+            const LzElem e = lz_decode<CODEC, false>(sm.in, s, n, tb, q, lut);
+            if (e.adv == LZ_INVALID || e.m_len > LZ_MAX_MATCH || (e.lit_len && e.lit_pos + e.lit_len > tb + LZ_TILE + 8)) {
                 stop = q;
                 break;
             }
-            cnt += (e.lit_len ? 1u : 0u) + (e.m_len ? 1u : 0u);
+            // long literals: pieces of LZ_INLINE bytes; long matches: pieces of LZ_MAX_ELEM bytes at the same distance
+            cnt += (e.lit_len + LZ_INLINE - 1) / LZ_INLINE + (e.m_len + LZ_MAX_ELEM - 1) / LZ_MAX_ELEM;
             bytes += e.lit_len + e.m_len;
             q += e.adv;
         }
     }
     // the tile ends in front of the first stop; lanes behind it are dropped
     const uint32_t stopmask = __ballot_sync(FULL, stop != LZ_INVALID || irregular);
-    const int cut_lane = stopmask ? __ffs(stopmask) - 1 : 32;
+    int cut_lane = stopmask ? __ffs(stopmask) - 1 : 32;
     if (lane > cut_lane) { cnt = 0; bytes = 0; }
     const bool cut_irregular = cut_lane < 32 && __shfl_sync(FULL, (int)irregular, cut_lane & 31);
-    const uint32_t cnt_incl = warp_incl_scan(cnt, lane), bytes_incl = warp_incl_scan(bytes, lane);
-    const uint32_t total_cnt = __shfl_sync(FULL, cnt_incl, 31), total_bytes = __shfl_sync(FULL, bytes_incl, 31);
+    uint32_t cnt_incl = warp_incl_scan(cnt, lane), bytes_incl = warp_incl_scan(bytes, lane);
+    uint32_t total_cnt = __shfl_sync(FULL, cnt_incl, 31), total_bytes = __shfl_sync(FULL, bytes_incl, 31);
+    if (total_cnt > LZ_DESC_CAP) {
+        // more pieces than the descriptor table holds (LZ4 sequences of long matches): the tile ends in front of the lane
+        // that would overflow it
+        const int lo = __ffs(__ballot_sync(FULL, cnt_incl > LZ_DESC_CAP)) - 1;
+        if (lane >= lo) { cnt = 0; bytes = 0; }
+        if (lane == lo) stop = my_entry;
+        cut_lane = lo;
+        cnt_incl = warp_incl_scan(cnt, lane);
+        bytes_incl = warp_incl_scan(bytes, lane);
+        total_cnt = __shfl_sync(FULL, cnt_incl, 31);
+        total_bytes = __shfl_sync(FULL, bytes_incl, 31);
+    }
     cut_lane_out = (uint32_t)cut_lane;
     if (cut_irregular && total_cnt == 0) return LZT_IRREGULAR;
     if ((uint64_t)o + total_bytes > ulen) return LZT_IRREGULAR;  // output past the announced length: the serial loop reports it
@@ -423,13 +472,12 @@ __device__ __forceinline__ uint32_t lz_tile(const uint8_t* __restrict__ s, uint3
         const uint32_t lim = stop != LZ_INVALID ? stop : end_i;
         while (q < lim) {
             const LzElem e = lz_decode<CODEC>(sm.in, s, n, tb, q, lut);
-            if (e.lit_len) {
-                sm.desc[r++] = e.lit_len | LZD_LIT | ((e.lit_pos - tb) << 16);
-                op += e.lit_len;
-            }
+            for (uint32_t done = 0; done < e.lit_len; done += LZ_INLINE)
+                sm.desc[r++] = min(e.lit_len - done, LZ_INLINE) | LZD_LIT | ((e.lit_pos + done - tb) << 16);
+            op += e.lit_len;
             if (e.m_len) {
                 if (e.m_dist == 0 || e.m_dist > op || e.m_dist > 0xffffu) bad = true;
-                sm.desc[r++] = e.m_len | (e.m_dist << 16);
+                for (uint32_t done = 0; done < e.m_len; done += LZ_MAX_ELEM) sm.desc[r++] = min(e.m_len - done, LZ_MAX_ELEM) | (e.m_dist << 16);
                 op += e.m_len;
             }
             q += e.adv;
@@ -452,31 +500,78 @@ __device__ __forceinline__ uint32_t lz_tile(const uint8_t* __restrict__ s, uint3
         const uint32_t incl = warp_incl_scan(len, lane);
         const uint32_t T = __shfl_sync(FULL, incl, 31);
         const uint32_t op = gO + incl - len, gEnd = gO + T;
-        // a match reads [op - src, op - src + min(len, src)); it depends on this group when that ends behind gO
-        const bool dep = len && !lit && op - src + min(len, src) > gO;
-        const bool later = len && (dep || len > LZ_INLINE);
-        if (len && !later) {
-            if (lit) {
-                for (uint32_t k = 0; k < len; k++) sm.hist[(op + k) & (LZ_HIST - 1)] = (uint8_t)lz_byte(sm.in, src + k);
-            } else {
-                const uint32_t a0 = op - src;
-                if (gEnd - a0 <= LZ_HIST) {
-                    for (uint32_t k = 0; k < len; k++) sm.hist[(op + k) & (LZ_HIST - 1)] = sm.hist[(a0 + k) & (LZ_HIST - 1)];
-                } else {
-                    for (uint32_t k = 0; k < len; k++) {
-                        const uint32_t a = a0 + k;
-                        sm.hist[(op + k) & (LZ_HIST - 1)] = (gEnd - a <= LZ_HIST) ? sm.hist[a & (LZ_HIST - 1)] : __ldcg(d + a);
+        // Rounds: every element whose source lies in front of the first unfinished element is copied by its own lane, all
+        // of them at once; an element that needs the whole warp (33..64 bytes, or a match that overlaps its own output)
+        // is copied when it is the first unfinished one.  Every round finishes at least that first element.
+        const bool big = len > LZ_INLINE || (!lit && src < len);
+        const uint32_t need = (len && !lit) ? op - src + min(len, src) : 0u;  // end of the source range
+        uint32_t rem = __ballot_sync(FULL, len != 0);
+        while (rem) {
+            const int first = __ffs(rem) - 1;
+            const uint32_t resolved = __shfl_sync(FULL, op, first);
+            const bool ready = ((rem >> lane) & 1u) && !big && need <= resolved;
+            const uint32_t rmask = __ballot_sync(FULL, ready);
+            // (with only a few ready elements the whole-warp copy of the first one is cheaper than a round)
+            if (__popc(rmask) >= 4) {
+                rem &= ~rmask;
+                const uint32_t maxlen = __reduce_max_sync(FULL, ready ? len : 0u);
+                if (ready) {
+                    // All source bytes exist: aligned words are loaded back to back, shifted into place and stored.
+                    // No load waits for a store, so a lane's bytes cost one memory latency.
+                    uint32_t w[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                    uint32_t sh;
+                    if (lit) {
+                        sh = (src & 3) * 8;
+#pragma unroll
+                        for (int j = 0; j < 9; j++) {
+                            if (4u * j >= maxlen + 3u) break;
+                            const uint32_t x = (src & ~3u) + 4u * j;
+                            const uint32_t rr = min(x >> 6, 31u), cc = x - (rr << 6);
+                            w[j] = 4u * j < len + (src & 3) ? sm.in[rr * LZ_ROW_WORDS + (cc >> 2)] : 0u;
+                        }
+                    } else {
+                        const uint32_t a0 = op - src;
+                        sh = (a0 & 3) * 8;
+                        if (gEnd - a0 <= LZ_HIST) {
+                            const uint32_t* hw = (const uint32_t*)sm.hist;
+#pragma unroll
+                            for (int j = 0; j < 9; j++) {
+                                if (4u * j >= maxlen + 3u) break;
+                                w[j] = 4u * j < len + (a0 & 3) ? hw[((a0 >> 2) + j) & (LZ_HIST / 4 - 1)] : 0u;
+                            }
+                        } else if (words_ok) {
+                            const uint32_t* gw = (const uint32_t*)(d + (a0 & ~3u));
+#pragma unroll
+                            for (int j = 0; j < 9; j++) {
+                                if (4u * j >= maxlen + 3u) break;
+                                w[j] = 4u * j < len + (a0 & 3) ? __ldcg(gw + j) : 0u;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 9; j++) {
+                                uint32_t v = 0;
+                                if (4u * j < len + (a0 & 3))
+                                    for (int b = 0; b < 4; b++) v |= (uint32_t)__ldcg(d + (a0 & ~3u) + 4 * j + b) << (8 * b);
+                                w[j] = v;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        if (4u * j >= maxlen) break;
+                        const uint32_t v = __funnelshift_r(w[j], w[j + 1], sh);
+#pragma unroll
+                        for (int b = 0; b < 4; b++)
+                            if (4u * j + b < len) sm.hist[(op + 4u * j + b) & (LZ_HIST - 1)] = (uint8_t)(v >> (8 * b));
                     }
                 }
+                __syncwarp();
+                continue;
             }
-        }
-        __syncwarp();
-        uint32_t lm = __ballot_sync(FULL, later);
-        while (lm) {
-            const int l = __ffs(lm) - 1;
-            lm &= lm - 1;
-            const uint32_t e_len = __shfl_sync(FULL, len, l), e_src = __shfl_sync(FULL, src, l), e_op = __shfl_sync(FULL, op, l);
-            const bool e_lit = __shfl_sync(FULL, (int)lit, l);
+            // the first unfinished element needs the whole warp
+            rem &= ~(1u << first);
+            const uint32_t e_len = __shfl_sync(FULL, len, first), e_src = __shfl_sync(FULL, src, first), e_op = resolved;
+            const bool e_lit = __shfl_sync(FULL, (int)lit, first);
             if (e_lit) {
                 for (uint32_t k = lane; k < e_len; k += 32) sm.hist[(e_op + k) & (LZ_HIST - 1)] = (uint8_t)lz_byte(sm.in, e_src + k);
             } else if (e_src >= e_len || e_src >= 32) {
@@ -554,7 +649,7 @@ __device__ __forceinline__ uint32_t lz_chunk(const uint8_t* __restrict__ s, uint
 }
 
 // Persistent warps over the chunk list (most expensive chunks first, see plan.cc); one chunk per warp at a time.
-__global__ void __launch_bounds__(128) k_decompress(const ChunkDesc* __restrict__ chunks, uint32_t nchunks, uint32_t* err,
+__global__ void __launch_bounds__(128, 5) k_decompress(const ChunkDesc* __restrict__ chunks, uint32_t nchunks, uint32_t* err,
                                                     uint32_t* out_lens, uint32_t* counter) {
     __shared__ LzWarp warp_sm[4];
     __shared__ uint32_t lut[256];
