@@ -73,6 +73,24 @@ struct OrcbReader {
     std::vector<RowSelector> selectors;
 };
 
+// finish() with the re-plan a LayoutRetry asks for (at most a few rounds: every round fixes the sizes of all chunks the
+// device could decode)
+static void finish_job(std::unique_ptr<Job>& job) {
+    for (int round = 0;; round++) {
+        try {
+            job->finish();
+            return;
+        } catch (const LayoutRetry&) {
+            if (round >= 3) fail(ORCB_UNEXPECTED, "compressed chunk sizes keep changing between decode passes");
+            std::unique_ptr<Job> again = job->rebuild();
+            again->plan();
+            again->stage();
+            again->launch();
+            job = std::move(again);
+        }
+    }
+}
+
 template <typename F>
 static int guarded(F&& f) {
     try {
@@ -81,6 +99,9 @@ static int guarded(F&& f) {
     } catch (const OrcException& e) {
         g_last_error = e.msg;
         return e.code;
+    } catch (const LayoutRetry&) {
+        g_last_error = "compressed chunk sizes differ from the planned layout (finish the job before exporting from it)";
+        return ORCB_UNEXPECTED;
     } catch (const std::bad_alloc&) {
         g_last_error = "out of host memory";
         return ORCB_UNEXPECTED;
@@ -483,7 +504,7 @@ static bool reader_advance(OrcbReader* r) {
                 r->ahead_error = std::current_exception();
             }
         }
-        r->job->finish();
+        finish_job(r->job);
     }
     return true;
 }
@@ -631,7 +652,7 @@ int orcb_job_launch(OrcbJob* j) {
     });
 }
 int orcb_job_finish(OrcbJob* j) {
-    return guarded([&] { for (auto& w : j->waves) w->finish(); });
+    return guarded([&] { for (auto& w : j->waves) finish_job(w); });
 }
 int orcb_job_stats(const OrcbJob* j, OrcbJobStats* out) {
     return guarded([&] {
@@ -688,12 +709,14 @@ uint64_t orcb_job_num_batches(const OrcbJob* j) {
 }
 int orcb_job_export_batch(OrcbJob* j, uint64_t i, struct ArrowArray* out) {
     return guarded([&] {
+        for (auto& w : j->waves) finish_job(w);
         auto at = j->locate(i);
         at.first->export_batch(at.second, out);
     });
 }
 int orcb_job_export_batch_device(OrcbJob* j, uint64_t i, struct ArrowDeviceArray* out) {
     return guarded([&] {
+        for (auto& w : j->waves) finish_job(w);
         auto at = j->locate(i);
         at.first->export_batch_device(at.second, out);
     });
@@ -847,8 +870,8 @@ int orcb_decode_varint128(int device, const uint8_t* in, size_t in_len, uint8_t*
 int orcb_decompress_stream(int device, int compression_kind, const uint8_t* in, size_t in_len, size_t block_size,
                            uint8_t* out, size_t out_cap, size_t* out_len) {
     return guarded([&] {
-        if (compression_kind != C_NONE && compression_kind != C_SNAPPY && compression_kind != C_LZ4)
-            fail(ORCB_UNSUPPORTED_DEVICE_CODEC, "Zlib/Zstd/LZO are not supported on the device path");
+        if (compression_kind != C_NONE && compression_kind != C_SNAPPY && compression_kind != C_LZ4 && compression_kind != C_ZLIB)
+            fail(ORCB_UNSUPPORTED_DEVICE_CODEC, "Zstd/LZO are not supported on the device path");
         if (compression_kind == C_NONE) {
             if (in_len > out_cap) fail(ORCB_INVALID_ARGUMENT, "output too small");
             memcpy(out, in, in_len);
@@ -876,6 +899,7 @@ int orcb_decompress_stream(int device, int compression_kind, const uint8_t* in, 
             d.dst_cap = (uint32_t)block_size;
             d.expect_len = -1;
             d.codec = chunks[i].original ? 0 : (uint8_t)compression_kind;
+            d.id = (uint32_t)i;
         }
         if (!chunks.empty()) CU(cudaMemcpy(ddesc.p, descs.data(), descs.size() * sizeof(ChunkDesc), cudaMemcpyHostToDevice));
         const bool timing = getenv("ORCB_STREAM_TIMING") != nullptr;  // kernel time to stderr (tools/snappy_probe.py)
@@ -885,7 +909,7 @@ int orcb_decompress_stream(int device, int compression_kind, const uint8_t* in, 
             CU(cudaEventCreate(&e1));
             CU(cudaEventRecord(e0, 0));
         }
-        int rc = launch_decompress((ChunkDesc*)ddesc.p, (uint32_t)chunks.size(), (uint32_t*)sr.err.p, (uint32_t*)dlens.p, (uint32_t*)dctr.p, 0);
+        int rc = launch_decompress((ChunkDesc*)ddesc.p, (uint32_t)chunks.size(), (uint32_t*)sr.err.p, (uint32_t*)dlens.p, (uint32_t*)dctr.p, nullptr, 0);
         if (rc) fail(ORCB_CUDA, cudaGetErrorString((cudaError_t)rc));
         if (timing) {
             float ms = 0;

@@ -122,7 +122,7 @@ DeviceArenas::~DeviceArenas() {
 }
 
 
-Job::Job(std::vector<StripeTask> tasks, const ReadOptions& opt) : tasks_(std::move(tasks)), opt_(opt) {
+Job::Job(std::vector<StripeTask> tasks, const ReadOptions& opt) : tasks_(std::move(tasks)), opt_(opt), orig_opt_(opt) {
     if (!tasks_.empty()) cols_ = project_columns(*tasks_[0].file, opt_);
 }
 
@@ -335,7 +335,7 @@ void Job::launch() {
         launches += nk;
     };
     if (N(chunks_))
-        run("k_decompress", ab_decomp_, N(chunks_), 1, [&] { return launch_decompress((ChunkDesc*)(d_desc_ + o_chunk_), N(chunks_), err, nullptr, (uint32_t*)(d_state_ + o_nblocks_) + 3, st); });
+        run("k_decompress", ab_decomp_, N(chunks_), 1, [&] { return launch_decompress((ChunkDesc*)(d_desc_ + o_chunk_), N(chunks_), err, (uint32_t*)(d_meta_ + o_clens_), (uint32_t*)(d_state_ + o_nblocks_) + 3, (uint32_t*)(d_meta_ + o_retry_), st); });
     if (N(present_byte_segs_)) {
         run("k_byte_rle(present)", ab_present_, N(present_byte_segs_), 1, [&] { return launch_byte_rle((Seg*)(d_desc_ + o_pbyte_), N(present_byte_segs_), cnt, dstart, err, st); });
         run("k_bits(present)", ab_present_, N(present_bit_segs_), 1, [&] { return launch_bits((BitSeg*)(d_desc_ + o_pbit_), N(present_bit_segs_), cnt, dstart, st); });
@@ -413,6 +413,17 @@ void Job::finish() {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, k.e0, k.e1) == cudaSuccess) k.ms = ms;
         else cudaGetLastError();
+    }
+    if (*(const uint32_t*)(h_meta_ + o_retry_)) {
+        // some chunk did not have the size the layout assumed: remember every size the device found and ask for a re-plan
+        const uint32_t* cl = (const uint32_t*)(h_meta_ + o_clens_);
+        for (size_t i = 0; i < chunk_keys_.size(); i++) {
+            if (cl[i] == 0xffffffffu) continue;
+            ChunkSizeCache& c = *chunk_keys_[i].first->chunk_sizes;
+            std::lock_guard<std::mutex> lock(c.mu);
+            c.size[chunk_keys_[i].second] = cl[i];
+        }
+        throw LayoutRetry{};
     }
     const uint32_t* err = (const uint32_t*)(h_meta_ + o_err_);
     for (uint32_t i = 0; i < n_colstripes_; i++) {

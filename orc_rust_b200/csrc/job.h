@@ -99,9 +99,15 @@ struct ColStripePlan {
 
 struct HostOutput;  // D2H copy of the output arenas, shared by exported batches
 
+// Thrown by Job::finish when chunks of unknown decompressed size (Zlib, LZ4) turned out not to fill their blocks: the
+// sizes found are in the files' ChunkSizeCache by then, and the same tasks planned again get an exact layout.
+struct LayoutRetry {};
+
 class Job {
   public:
     Job(std::vector<StripeTask> tasks, const ReadOptions& opt);
+    // a fresh job over the same tasks and options (after LayoutRetry)
+    std::unique_ptr<Job> rebuild() const { return std::make_unique<Job>(tasks_, orig_opt_); }
     ~Job();
     void plan();
     void stage();
@@ -123,7 +129,7 @@ class Job {
     void ensure_host_output();
 
     std::vector<StripeTask> tasks_;
-    ReadOptions opt_;
+    ReadOptions opt_, orig_opt_;
     std::vector<OutColumn> cols_;
     bool planned_ = false, staged_ = false, launched_ = false, finished_ = false;
 
@@ -175,7 +181,8 @@ class Job {
     uint8_t* d_meta_ = nullptr;
     uint8_t* h_meta_ = nullptr;  // pinned, from the process-wide cache of small pinned buffers (job.cc)
     size_t h_meta_cap_ = 0;
-    uint64_t meta_bytes_ = 0, o_err_ = 0, o_nulls_ = 0, o_ptrs_ = 0, o_bbase_ = 0;
+    uint64_t meta_bytes_ = 0, o_err_ = 0, o_nulls_ = 0, o_ptrs_ = 0, o_bbase_ = 0, o_clens_ = 0, o_retry_ = 0;
+    std::vector<std::pair<const FileMeta*, uint64_t>> chunk_keys_;  // chunk id -> (file, offset of the chunk header)
     uint32_t n_nulls_ = 0;
 
     std::vector<ColStripePlan> colstripes_;

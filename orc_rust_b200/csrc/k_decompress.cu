@@ -68,12 +68,17 @@ __device__ __forceinline__ uint32_t snappy_preamble(const uint8_t* __restrict__ 
     return ulen > dst_cap ? (uint32_t)ORCB_BUILD_SNAPPY_DECODER : 0u;
 }
 
-__device__ __forceinline__ void chunk_done(const ChunkDesc& c, uint32_t ci, uint32_t fail, uint32_t o, uint32_t* err, uint32_t* out_lens,
-                                           int lane) {
-    if (!fail && c.expect_len >= 0 && o != (uint32_t)c.expect_len) fail = ORCB_UNEXPECTED;
+__device__ __forceinline__ void chunk_done(const ChunkDesc& c, uint32_t fail, uint32_t o, uint32_t* err, uint32_t* out_lens,
+                                           uint32_t* retry, int lane) {
+    bool again = false;
+    if (!fail && c.expect_len >= 0 && o != (uint32_t)c.expect_len) {
+        if (c.assumed && retry) again = true;  // the host laid the stream out on a guess: it re-plans with the real sizes
+        else fail = ORCB_UNEXPECTED;
+    }
     if (lane == 0) {
         if (fail) set_err(err, c.colstripe, fail);
-        if (out_lens) out_lens[ci] = o;
+        if (again) atomicOr(retry, 1u);
+        if (out_lens) out_lens[c.id] = fail ? 0xffffffffu : o;
     }
 }
 
@@ -648,9 +653,293 @@ __device__ __forceinline__ uint32_t lz_chunk(const uint8_t* __restrict__ s, uint
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Zlib chunks: raw DEFLATE (src/compression.rs:142-149, flate2::read::DeflateDecoder).
+//
+// Huffman decoding is a serial bit chain; one lane walks it and queues up to 32 tokens (a literal byte or a match),
+// then the warp places them: a scan of the token lengths gives every token its output position, all literals are
+// written at once, matches follow in order, copied by the whole warp.  The tables of a block are built by the whole
+// warp: canonical codes come from per-length counters (rank among the symbols of the same length through
+// __match_any_sync), every lane fills the lookup entries of its own symbols.  Codes longer than the lookup index are
+// resolved bit by bit against the canonical first-code table.
+// ------------------------------------------------------------------------------------------------
+constexpr int INF_LBITS = 10, INF_DBITS = 8;
+struct InfWarp {
+    uint16_t llut[1 << INF_LBITS];   // (symbol << 4) | code length; 0 = longer than INF_LBITS or unused
+    uint16_t dlut[1 << INF_DBITS];
+    uint16_t lsorted[288], dsorted[32];  // symbols ordered by (length, symbol): canonical decode of long codes
+    uint16_t lfirst[16], dfirst[16];     // first canonical code of each length
+    uint16_t loffs[16], doffs[16];       // index of that code's symbol in *sorted
+    uint16_t lcount[16], dcount[16];
+    uint8_t lens[320];                   // literal/length code lengths at 0.., distance code lengths at 288..
+    uint8_t stage[352];                  // dynamic blocks: 19 code-length lengths, then (from 32 on) the lengths as they are read
+    uint32_t tok[32];                    // literal: byte | 1 << 31; match: len | dist << 9  (len <= 258, dist <= 32768)
+};
+static_assert(sizeof(InfWarp) <= sizeof(LzWarp), "the inflate tables reuse the LZ decoder's shared memory");
+
+__device__ __forceinline__ uint32_t brev_n(uint32_t v, int n) { return __brev(v) >> (32 - n); }
+
+// canonical Huffman tables of `nsym` symbols with the given code lengths; false = over-subscribed
+__device__ __forceinline__ bool inf_build(const uint8_t* lens, int nsym, uint16_t* lut, int lut_bits, uint16_t* sorted, uint16_t* first,
+                                          uint16_t* offs, uint16_t* count, int lane) {
+    for (int i = lane; i < (1 << lut_bits); i += 32) lut[i] = 0;
+    if (lane < 16) count[lane] = 0;
+    __syncwarp();
+    for (int b = 0; b < nsym; b += 32) {
+        const int sym = b + lane;
+        const int L = sym < nsym ? lens[sym] : 0;
+        const uint32_t same = __match_any_sync(FULL, L);
+        if (L && lane == __ffs(same) - 1) count[L] += (uint16_t)__popc(same);
+        __syncwarp();
+    }
+    // first codes / offsets (15 serial steps), over-subscription check
+    bool ok = true;
+    if (lane == 0) {
+        uint32_t code = 0, off = 0;
+        int left = 1;
+        for (int L = 1; L <= 15; L++) {
+            left = (left << 1) - (int)count[L];
+            if (left < 0) ok = false;
+            first[L] = (uint16_t)code;
+            offs[L] = (uint16_t)off;
+            code = (code + count[L]) << 1;
+            off += count[L];
+        }
+        first[0] = offs[0] = 0;
+    }
+    ok = __shfl_sync(FULL, (int)ok, 0);
+    if (!ok) return false;
+    if (lane < 16) count[lane] = 0;  // reused as running counters
+    __syncwarp();
+    for (int b = 0; b < nsym; b += 32) {
+        const int sym = b + lane;
+        const int L = sym < nsym ? lens[sym] : 0;
+        const uint32_t same = __match_any_sync(FULL, L);
+        const uint32_t rank = __popc(same & ((1u << lane) - 1u));
+        if (L) {
+            const uint32_t idx = count[L] + rank;  // among the symbols of length L, in symbol order
+            const uint32_t code = first[L] + idx;
+            sorted[offs[L] + idx] = (uint16_t)sym;
+            if (L <= lut_bits) {
+                const uint32_t rev = brev_n(code, L);
+                for (uint32_t k = rev; k < (1u << lut_bits); k += 1u << L) lut[k] = (uint16_t)((sym << 4) | L);
+            }
+        }
+        __syncwarp();
+        if (L && lane == __ffs(same) - 1) count[L] += (uint16_t)__popc(same);
+        __syncwarp();
+    }
+    return true;
+}
+
+struct InfBits {
+    const uint8_t* s;
+    uint32_t n, pos;   // pos: next input byte
+    uint64_t buf;
+    int cnt;
+    __device__ __forceinline__ void refill() {
+        while (cnt <= 56) {
+            buf |= (uint64_t)(pos < n ? s[pos] : 0u) << cnt;
+            pos++;
+            cnt += 8;
+        }
+    }
+    __device__ __forceinline__ uint32_t take(int k) {
+        const uint32_t v = (uint32_t)buf & ((1u << k) - 1u);
+        buf >>= k;
+        cnt -= k;
+        return v;
+    }
+    __device__ __forceinline__ bool overrun() const { return (uint64_t)pos * 8 - (uint64_t)cnt > (uint64_t)n * 8; }
+};
+
+// one symbol; -1 = invalid code
+__device__ __forceinline__ int inf_symbol(InfBits& b, const uint16_t* lut, int lut_bits, const uint16_t* sorted, const uint16_t* first,
+                                          const uint16_t* offs, const uint16_t* count) {
+    const uint32_t e = lut[(uint32_t)b.buf & ((1u << lut_bits) - 1u)];
+    if (e) {
+        b.take(e & 15);
+        return (int)(e >> 4);
+    }
+    // long code: canonical decode, one bit at a time (count[] holds the number of codes per length after the build)
+    uint32_t code = 0;
+    for (int L = 1; L <= 15; L++) {
+        code = (code << 1) | b.take(1);
+        const uint32_t c = count[L];
+        if (code - first[L] < c && code >= first[L]) return sorted[offs[L] + (code - first[L])];
+    }
+    return -1;
+}
+
+__device__ uint32_t inflate_chunk(const uint8_t* __restrict__ s, uint32_t n, uint8_t* d, uint32_t cap, uint32_t& o_out, InfWarp& w, int lane) {
+    static const uint16_t LBASE[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+    static const uint8_t LEXT[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+    static const uint16_t DBASE[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+    static const uint8_t DEXT[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+    static const uint8_t CLORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+    const uint32_t BAD = ORCB_IO_ERROR;
+    InfBits b{s, n, 0, 0, 0};
+    uint32_t o = 0;
+    int last = 0;
+    while (!last) {
+        // ---- block header (lane 0 reads, everyone follows)
+        uint32_t type = 0;
+        if (lane == 0) {
+            b.refill();
+            last = (int)b.take(1);
+            type = b.take(2);
+        }
+        last = __shfl_sync(FULL, last, 0);
+        type = __shfl_sync(FULL, type, 0);
+        if (type == 3) return BAD;
+        if (type == 0) {
+            // stored block: to the next byte boundary, LEN, ~LEN, bytes
+            uint32_t len = 0, from = 0, bad = 0;
+            if (lane == 0) {
+                b.take(b.cnt & 7);
+                b.refill();
+                len = b.take(16);
+                const uint32_t nlen = b.take(16);
+                if ((len ^ nlen) != 0xffffu) bad = 1;
+                from = b.pos - (uint32_t)(b.cnt >> 3);  // first byte not yet consumed
+                if (from > n || len > n - from || len > cap - o) bad = 1;
+                if (!bad) {
+                    b.pos = from + len;
+                    b.buf = 0;
+                    b.cnt = 0;
+                }
+            }
+            if (__shfl_sync(FULL, bad, 0)) return BAD;
+            len = __shfl_sync(FULL, len, 0);
+            from = __shfl_sync(FULL, from, 0);
+            warp_copy_fwd(d + o, s + from, len, lane);
+            __syncwarp();
+            o += len;
+            continue;
+        }
+        int nlen = 288, ndist = 30;
+        if (type == 1) {
+            // fixed code
+            for (int i = lane; i < 288; i += 32) w.lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
+            w.lens[288 + lane] = lane < 30 ? 5 : 0;
+        } else {
+            // dynamic code: code-length code, then the literal/length and distance code lengths
+            uint32_t bad = 0;
+            if (lane == 0) {
+                b.refill();
+                nlen = (int)b.take(5) + 257;
+                ndist = (int)b.take(5) + 1;
+                const int ncode = (int)b.take(4) + 4;
+                if (nlen > 286 || ndist > 30) bad = 1;
+                for (int i = 0; i < 19; i++) w.stage[i] = 0;
+                for (int i = 0; i < ncode && !bad; i++) {
+                    b.refill();
+                    w.stage[CLORDER[i]] = (uint8_t)b.take(3);
+                }
+            }
+            if (__shfl_sync(FULL, bad, 0)) return BAD;
+            nlen = __shfl_sync(FULL, nlen, 0);
+            ndist = __shfl_sync(FULL, ndist, 0);
+            __syncwarp();
+            // the code-length code borrows the distance tables (built again below)
+            if (!inf_build(w.stage, 19, w.dlut, 7, w.dsorted, w.dfirst, w.doffs, w.dcount, lane)) return BAD;
+            __syncwarp();
+            if (lane == 0) {
+                int i = 0, prev = 0;
+                uint8_t* out = w.stage + 32;
+                while (i < nlen + ndist && !bad) {
+                    b.refill();
+                    const int sym = inf_symbol(b, w.dlut, 7, w.dsorted, w.dfirst, w.doffs, w.dcount);
+                    if (sym < 0) { bad = 1; break; }
+                    if (sym < 16) {
+                        out[i++] = (uint8_t)sym;
+                        prev = sym;
+                    } else {
+                        int rep, val = 0;
+                        if (sym == 16) {
+                            if (i == 0) { bad = 1; break; }
+                            val = prev;
+                            rep = 3 + (int)b.take(2);
+                        } else if (sym == 17) {
+                            rep = 3 + (int)b.take(3);
+                            prev = 0;
+                        } else {
+                            rep = 11 + (int)b.take(7);
+                            prev = 0;
+                        }
+                        if (i + rep > nlen + ndist) { bad = 1; break; }
+                        while (rep--) out[i++] = (uint8_t)val;
+                    }
+                }
+                if (!bad && out[256] == 0) bad = 1;  // no end-of-block code
+                if (b.overrun()) bad = 1;
+            }
+            if (__shfl_sync(FULL, bad, 0)) return BAD;
+            __syncwarp();
+            for (int i = lane; i < 288; i += 32) w.lens[i] = i < nlen ? w.stage[32 + i] : 0;
+            w.lens[288 + lane] = lane < ndist ? w.stage[32 + nlen + lane] : 0;
+        }
+        __syncwarp();
+        if (!inf_build(w.lens, 288, w.llut, INF_LBITS, w.lsorted, w.lfirst, w.loffs, w.lcount, lane)) return BAD;
+        if (!inf_build(w.lens + 288, 32, w.dlut, INF_DBITS, w.dsorted, w.dfirst, w.doffs, w.dcount, lane)) return BAD;
+        __syncwarp();
+        // ---- symbols: lane 0 queues up to 32 tokens, the warp writes them
+        bool end = false;
+        while (!end) {
+            uint32_t nt = 0, bad = 0;
+            if (lane == 0) {
+                while (nt < 32) {
+                    b.refill();
+                    const int sym = inf_symbol(b, w.llut, INF_LBITS, w.lsorted, w.lfirst, w.loffs, w.lcount);
+                    if (sym < 0) { bad = 1; break; }
+                    if (sym < 256) {
+                        w.tok[nt++] = (uint32_t)sym | (1u << 31);
+                    } else if (sym == 256) {
+                        end = true;
+                        break;
+                    } else {
+                        if (sym > 285) { bad = 1; break; }
+                        const uint32_t len = LBASE[sym - 257] + b.take(LEXT[sym - 257]);
+                        const int ds = inf_symbol(b, w.dlut, INF_DBITS, w.dsorted, w.dfirst, w.doffs, w.dcount);
+                        if (ds < 0 || ds > 29) { bad = 1; break; }
+                        const uint32_t dist = DBASE[ds] + b.take(DEXT[ds]);
+                        w.tok[nt++] = len | (dist << 9);
+                    }
+                }
+                if (b.overrun()) bad = 1;
+            }
+            if (__shfl_sync(FULL, bad, 0)) return BAD;
+            nt = __shfl_sync(FULL, nt, 0);
+            end = __shfl_sync(FULL, (int)end, 0);
+            __syncwarp();
+            const uint32_t t = (uint32_t)lane < nt ? w.tok[lane] : 0u;
+            const bool lit = (t >> 31) != 0;
+            const uint32_t len = (uint32_t)lane < nt ? (lit ? 1u : (t & 511u)) : 0u;
+            const uint32_t incl = warp_incl_scan(len, lane);
+            const uint32_t total = __shfl_sync(FULL, incl, 31);
+            if (total > cap - o) return BAD;
+            const uint32_t op = o + incl - len;
+            if (lit) d[op] = (uint8_t)t;
+            uint32_t mm = __ballot_sync(FULL, len != 0 && !lit);
+            __syncwarp();
+            while (mm) {
+                const int l = __ffs(mm) - 1;
+                mm &= mm - 1;
+                const uint32_t e_len = __shfl_sync(FULL, len, l), e_dist = __shfl_sync(FULL, t >> 9, l), e_op = __shfl_sync(FULL, op, l);
+                if (e_dist == 0 || e_dist > e_op) return BAD;
+                warp_copy_match(d, e_op, e_dist, e_len, lane);
+                __syncwarp();
+            }
+            o += total;
+        }
+    }
+    o_out = o;
+    return 0;
+}
+
 // Persistent warps over the chunk list (most expensive chunks first, see plan.cc); one chunk per warp at a time.
 __global__ void __launch_bounds__(128, 5) k_decompress(const ChunkDesc* __restrict__ chunks, uint32_t nchunks, uint32_t* err,
-                                                    uint32_t* out_lens, uint32_t* counter) {
+                                                       uint32_t* out_lens, uint32_t* counter, uint32_t* retry) {
     __shared__ LzWarp warp_sm[4];
     __shared__ uint32_t lut[256];
     lut[threadIdx.x] = snappy_tag_entry(threadIdx.x);
@@ -677,13 +966,17 @@ __global__ void __launch_bounds__(128, 5) k_decompress(const ChunkDesc* __restri
             uint64_t ulen;
             fail = snappy_preamble(s, n, c.dst_cap, p, ulen);
             if (!fail) fail = lz_chunk<2>(s, n, d, ulen, p, o, sm, lut, lane);
+        } else if (c.codec == 1) {
+            fail = inflate_chunk(s, n, d, c.dst_cap, o, *(InfWarp*)&sm, lane);
+            if (c.expect_len < 0 && !fail)
+                for (uint32_t a = o + lane; a < c.dst_cap; a += 32) d[a] = 0;
         } else {
             fail = lz_chunk<4>(s, n, d, c.dst_cap, 0, o, sm, lut, lane);
             // the size of a stream's last LZ4 chunk is only known here: what the layout reserved beyond it reads as zeros
             if (c.expect_len < 0 && !fail)
                 for (uint32_t a = o + lane; a < c.dst_cap; a += 32) d[a] = 0;
         }
-        chunk_done(c, ci, fail, o, err, out_lens, lane);
+        chunk_done(c, fail, o, err, out_lens, retry, lane);
         __syncwarp();
     }
 }
@@ -691,7 +984,7 @@ __global__ void __launch_bounds__(128, 5) k_decompress(const ChunkDesc* __restri
 // ------------------------------------------------------------------------------------------------
 // host-side launch wrappers
 // ------------------------------------------------------------------------------------------------
-int launch_decompress(const ChunkDesc* c, uint32_t n, uint32_t* err, uint32_t* out_lens, uint32_t* counter, cudaStream_t st) {
+int launch_decompress(const ChunkDesc* c, uint32_t n, uint32_t* err, uint32_t* out_lens, uint32_t* counter, uint32_t* retry, cudaStream_t st) {
     if (!n) return 0;
     static int ctas = 0;
     if (!ctas) {
@@ -702,7 +995,7 @@ int launch_decompress(const ChunkDesc* c, uint32_t n, uint32_t* err, uint32_t* o
         ctas = sms * (per_sm > 0 ? per_sm : 1);
     }
     const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)ctas, ((uint64_t)n + 3) / 4);
-    k_decompress<<<grid, 128, 0, st>>>(c, n, err, out_lens, counter);
+    k_decompress<<<grid, 128, 0, st>>>(c, n, err, out_lens, counter, retry);
     LAUNCH_CHECK();
     return 0;
 }

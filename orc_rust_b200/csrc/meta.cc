@@ -98,6 +98,134 @@ static void host_lz4_block(const uint8_t* s, size_t n, size_t max_out, std::vect
     }
 }
 
+// Raw DEFLATE for metadata sections of Zlib files (footer, stripe footers, row indexes); data streams are inflated on the
+// device (k_decompress.cu).  Bit-by-bit canonical decode: these sections are a few KiB.
+namespace {
+struct HostBits {
+    const uint8_t* s;
+    size_t n, pos = 0;
+    uint32_t buf = 0;
+    int cnt = 0;
+    uint32_t bits(int k) {
+        while (cnt < k) {
+            if (pos >= n) fail(ORCB_IO_ERROR, "corrupt deflate stream");
+            buf |= (uint32_t)s[pos++] << cnt;
+            cnt += 8;
+        }
+        const uint32_t v = buf & ((1u << k) - 1u);
+        buf >>= k;
+        cnt -= k;
+        return v;
+    }
+};
+struct HostHuff {
+    uint16_t count[16] = {0}, symbol[288] = {0};
+    void build(const uint8_t* len, int n) {
+        for (int i = 0; i < 16; i++) count[i] = 0;
+        for (int i = 0; i < n; i++) count[len[i]]++;
+        int left = 1;
+        for (int l = 1; l <= 15; l++) {
+            left = (left << 1) - count[l];
+            if (left < 0) fail(ORCB_IO_ERROR, "corrupt deflate stream");
+        }
+        uint16_t offs[16];
+        offs[1] = 0;
+        for (int l = 1; l < 15; l++) offs[l + 1] = offs[l] + count[l];
+        for (int i = 0; i < n; i++)
+            if (len[i]) symbol[offs[len[i]]++] = (uint16_t)i;
+    }
+    int decode(HostBits& b) const {
+        int code = 0, first = 0, index = 0;
+        for (int l = 1; l <= 15; l++) {
+            code |= (int)b.bits(1);
+            const int c = count[l];
+            if (code - c < first) return symbol[index + (code - first)];
+            index += c;
+            first += c;
+            first <<= 1;
+            code <<= 1;
+        }
+        fail(ORCB_IO_ERROR, "corrupt deflate stream");
+    }
+};
+}  // namespace
+
+static void host_inflate(const uint8_t* s, size_t n, std::vector<uint8_t>& out) {
+    static const uint16_t LBASE[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+    static const uint8_t LEXT[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+    static const uint16_t DBASE[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+    static const uint8_t DEXT[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+    static const uint8_t ORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+    HostBits b{s, n};
+    const size_t base = out.size();
+    int last;
+    do {
+        last = (int)b.bits(1);
+        const uint32_t type = b.bits(2);
+        if (type == 0) {
+            b.buf = 0;
+            b.cnt = 0;
+            if (b.pos + 4 > n) fail(ORCB_IO_ERROR, "corrupt deflate stream");
+            const uint32_t len = s[b.pos] | (s[b.pos + 1] << 8), nlen = s[b.pos + 2] | (s[b.pos + 3] << 8);
+            b.pos += 4;
+            if ((len ^ nlen) != 0xffffu || b.pos + len > n) fail(ORCB_IO_ERROR, "corrupt deflate stream");
+            out.insert(out.end(), s + b.pos, s + b.pos + len);
+            b.pos += len;
+            continue;
+        }
+        if (type == 3) fail(ORCB_IO_ERROR, "corrupt deflate stream");
+        HostHuff lc, dc;
+        uint8_t lens[320];
+        if (type == 1) {
+            for (int i = 0; i < 288; i++) lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
+            lc.build(lens, 288);
+            for (int i = 0; i < 30; i++) lens[i] = 5;
+            dc.build(lens, 30);
+        } else {
+            const int nl = (int)b.bits(5) + 257, nd = (int)b.bits(5) + 1, nc = (int)b.bits(4) + 4;
+            if (nl > 286 || nd > 30) fail(ORCB_IO_ERROR, "corrupt deflate stream");
+            uint8_t cl[19] = {0};
+            for (int i = 0; i < nc; i++) cl[ORDER[i]] = (uint8_t)b.bits(3);
+            HostHuff cc;
+            cc.build(cl, 19);
+            int i = 0;
+            while (i < nl + nd) {
+                const int sym = cc.decode(b);
+                if (sym < 16) {
+                    lens[i++] = (uint8_t)sym;
+                } else {
+                    int rep, val = 0;
+                    if (sym == 16) {
+                        if (i == 0) fail(ORCB_IO_ERROR, "corrupt deflate stream");
+                        val = lens[i - 1];
+                        rep = 3 + (int)b.bits(2);
+                    } else if (sym == 17) rep = 3 + (int)b.bits(3);
+                    else rep = 11 + (int)b.bits(7);
+                    if (i + rep > nl + nd) fail(ORCB_IO_ERROR, "corrupt deflate stream");
+                    while (rep--) lens[i++] = (uint8_t)val;
+                }
+            }
+            if (lens[256] == 0) fail(ORCB_IO_ERROR, "corrupt deflate stream");
+            lc.build(lens, nl);
+            dc.build(lens + nl, nd);
+        }
+        for (;;) {
+            const int sym = lc.decode(b);
+            if (sym < 256) out.push_back((uint8_t)sym);
+            else if (sym == 256) break;
+            else {
+                if (sym > 285) fail(ORCB_IO_ERROR, "corrupt deflate stream");
+                const size_t len = LBASE[sym - 257] + b.bits(LEXT[sym - 257]);
+                const int ds = dc.decode(b);
+                if (ds > 29) fail(ORCB_IO_ERROR, "corrupt deflate stream");
+                const size_t dist = DBASE[ds] + b.bits(DEXT[ds]);
+                if (dist > out.size() - base) fail(ORCB_IO_ERROR, "corrupt deflate stream");
+                for (size_t k = 0; k < len; k++) out.push_back(out[out.size() - dist]);
+            }
+        }
+    } while (!last);
+}
+
 std::vector<uint8_t> host_decompress_section(int compression, uint64_t block_size, const uint8_t* in, size_t len) {
     std::vector<uint8_t> out;
     if (compression == C_NONE) {
@@ -117,8 +245,10 @@ std::vector<uint8_t> host_decompress_section(int compression, uint64_t block_siz
             host_snappy_block(in + p, clen, out);
         } else if (compression == C_LZ4) {
             host_lz4_block(in + p, clen, block_size, out);
+        } else if (compression == C_ZLIB) {
+            host_inflate(in + p, clen, out);
         } else {
-            fail(ORCB_UNSUPPORTED_DEVICE_CODEC, "Zlib/Zstd/LZO are not supported on the device path");
+            fail(ORCB_UNSUPPORTED_DEVICE_CODEC, "Zstd/LZO are not supported on the device path");
         }
         p += clen;
     }
@@ -174,9 +304,9 @@ void parse_file_tail(FileMeta& fm) {
     }
     if (!have_footer) fail(ORCB_OUT_OF_SPEC, "Footer length is empty");
     if (!have_meta) fail(ORCB_OUT_OF_SPEC, "Metadata length is empty");
-    if (fm.compression == C_ZLIB || fm.compression == C_ZSTD || fm.compression == C_LZO)
+    if (fm.compression == C_ZSTD || fm.compression == C_LZO)
         fail(ORCB_UNSUPPORTED_DEVICE_CODEC,
-             "file is compressed with Zlib/Zstd/LZO: not decodable on the device path (no CPU fallback)");
+             "file is compressed with Zstd/LZO: not decodable on the device path (no CPU fallback)");
     if (fm.compression < 0 || fm.compression > C_ZSTD) fail(ORCB_DECODE_PROTO, "unknown compression kind");
     // subtraction-style checks: the lengths come from the file and their sum may wrap
     if (footer_len > n - 1 - ps_len || meta_len > n - 1 - ps_len - footer_len) fail(ORCB_OUT_OF_SPEC, "footer exceeds file");
@@ -532,6 +662,10 @@ std::vector<ChunkInfo> FileMeta::chunk_table(uint64_t stream_off, uint64_t strea
             }
             if (!ok) fail(ORCB_BUILD_SNAPPY_DECODER, "bad snappy preamble");
             ci.dst_len = (int64_t)v;
+        } else {
+            std::lock_guard<std::mutex> lock(chunk_sizes->mu);
+            auto it = chunk_sizes->size.find(stream_off + p);
+            if (it != chunk_sizes->size.end()) ci.dst_len = it->second;
         }
         out.push_back(ci);
         p = ci.src_off + ci.src_len;

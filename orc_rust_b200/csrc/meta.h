@@ -3,6 +3,8 @@
 // src/column.rs:40-59, src/schema.rs:390-495, src/row_index.rs:204-289 of the reference.
 #pragma once
 #include <memory>
+#include <mutex>
+#include <unordered_map>
 #include <string>
 #include <utility>
 #include <vector>
@@ -87,7 +89,16 @@ struct ReferencePanic : std::runtime_error {
     using std::runtime_error::runtime_error;
 };
 
+// Decompressed sizes of chunks whose size only the device can find (Zlib and LZ4 carry none in their framing), keyed by
+// the file offset of the chunk header.  Filled by the first job that meets a chunk that does not fill its block; shared
+// by the clones of a file handle.
+struct ChunkSizeCache {
+    std::mutex mu;
+    std::unordered_map<uint64_t, uint32_t> size;
+};
+
 struct FileMeta {
+    std::shared_ptr<ChunkSizeCache> chunk_sizes = std::make_shared<ChunkSizeCache>();
     const uint8_t* data = nullptr;
     size_t len = 0;
     std::vector<uint8_t> owned;   // when opened from a path without pinned memory

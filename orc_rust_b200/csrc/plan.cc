@@ -167,6 +167,8 @@ void Job::plan() {
     mplace(o_nulls_, (size_t)(n_nulls_ + 1) * 4);
     mplace(o_ptrs_, (strcols_.size() + 1) * 8);
     mplace(o_bbase_, bbase_bytes + 8);
+    mplace(o_clens_, (chunk_keys_.size() + 1) * 4);
+    mplace(o_retry_, 16);
     meta_bytes_ = align_up(meta_bytes_, 256);
 
     // heap capacity: dictionary string bytes are bump-allocated on the device
@@ -298,13 +300,18 @@ void Job::plan_stripe(uint32_t task_idx) {
                 d.src_len = c.src_len;
                 d.codec = c.original ? 0 : (uint8_t)fm.compression;
                 d.colstripe = cs;
+                d.id = (uint32_t)chunk_keys_.size();
+                chunk_keys_.emplace_back(&fm, st->offset + c.hdr_off);
                 if (c.dst_len >= 0) {
                     d.dst_cap = (uint32_t)c.dst_len;
                     d.expect_len = (int32_t)c.dst_len;
                 } else {
                     d.dst_cap = (uint32_t)fm.block_size;
-                    // layout assumes every non-final chunk fills the block; verified on the device
+                    // The layout assumes that every non-final chunk fills the block (writers cut a chunk when their
+                    // buffer is full).  The device checks; where it does not hold (Java writers also cut chunks at
+                    // other points) the job learns the real sizes and is planned again (Job::finish, LayoutRetry).
                     d.expect_len = i + 1 < r.chunks.size() ? (int32_t)fm.block_size : -1;
+                    d.assumed = 1;
                 }
                 chunks_.push_back(d);
                 ab_decomp_ += c.src_len + (uint64_t)d.dst_cap;

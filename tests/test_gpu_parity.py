@@ -30,7 +30,7 @@ def _device_ok_files():
             of = oo.OracleFile(open(f, "rb").read())
         except oo.OracleError:
             continue
-        if of.is_flat() and of.compression in (0, 2, 4) and os.path.basename(f) != "orc_split_elim.orc":
+        if of.is_flat() and of.compression in (0, 1, 2, 4) and os.path.basename(f) != "orc_split_elim.orc":
             out.append(f)
     return out
 
@@ -742,6 +742,46 @@ def test_decompress_streams_vs_oracle(ob, kind):
         oo.decompress_stream(code, bad, 4096)
     with pytest.raises(ob.OrcError):
         ob.decompress_stream(code, bad, 4096)
+
+
+def test_inflate_streams(ob):
+    """Zlib chunks (raw DEFLATE, src/compression.rs:142-149): stored, fixed-Huffman and dynamic-Huffman blocks written
+    by zlib at several levels / strategies, framed as ORC chunks, decoded on the device."""
+    import zlib
+    rng = np.random.default_rng(5)
+    pats = _lz_patterns(rng)
+    pats["noise"] = bytes(rng.integers(0, 256, 150_000, dtype=np.uint8))
+    pats["skewed"] = bytes(np.minimum(rng.geometric(0.02, 300_000), 255).astype(np.uint8))  # long codes (> 10 bits)
+    for name, data in pats.items():
+        for level, strategy in ((0, zlib.Z_DEFAULT_STRATEGY), (1, zlib.Z_DEFAULT_STRATEGY), (6, zlib.Z_DEFAULT_STRATEGY),
+                                (9, zlib.Z_DEFAULT_STRATEGY), (6, zlib.Z_FIXED), (6, zlib.Z_HUFFMAN_ONLY), (6, zlib.Z_RLE)):
+            for bs in (262144, 65536):
+                framed = bytearray()
+                for p in range(0, len(data), bs):
+                    co = zlib.compressobj(level, zlib.DEFLATED, -15, 9, strategy)
+                    c = co.compress(data[p:p + bs]) + co.flush()
+                    framed += (len(c) << 1).to_bytes(3, "little") + c
+                got = ob.decompress_stream(1, bytes(framed), bs)
+                assert got == data, f"inflate {name} level {level} strategy {strategy} block {bs}: {len(got)} vs {len(data)}"
+    # damaged streams are reported (flate2 -> IoError) or decode to something; they never hang or crash
+    data = pats["text"][:100_000]
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    c = co.compress(data) + co.flush()
+    for it in range(40):
+        bad = bytearray(c)
+        for _ in range(int(rng.integers(1, 4))):
+            bad[int(rng.integers(0, len(bad)))] = int(rng.integers(0, 256))
+        framed = (len(bad) << 1).to_bytes(3, "little") + bytes(bad)
+        try:
+            exp = zlib.decompress(bytes(bad), -15)
+        except zlib.error:
+            exp = None
+        try:
+            got = ob.decompress_stream(1, framed, 262144)
+        except ob.OrcError:
+            got = None
+        if exp is not None and got is not None:
+            assert got == exp, f"damaged #{it}: both decode, bytes differ"
 
 
 def _lz_patterns(rng):
