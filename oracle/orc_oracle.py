@@ -17,7 +17,7 @@ oracle/codecs.c; this module restates the planner half:
 
 Parity pinning: tests/test_oracle_kat.py (reference unit-test vectors) and tests/test_oracle_files.py
 (reference expected_arrow feather goldens + pyarrow.orc as an independent reader).
-Only flat (non-nested) root columns are restated so far; nested columns raise NotImplementedError.
+Nested columns (struct / list / map / union) are restated as a recursive walk (OracleFile._decode_node).
 """
 from __future__ import annotations
 
@@ -334,7 +334,18 @@ class OracleFile:
             return pa.timestamp(ts_unit)
         if k == K_TIMESTAMP_INSTANT:
             return pa.timestamp(ts_unit, tz="UTC")
-        raise NotImplementedError(f"nested ORC type kind {k} not restated in the oracle yet")
+        # nested types (src/schema.rs:530-577)
+        if k == K_STRUCT:
+            return pa.struct([pa.field(n, self.arrow_type(c, ts_unit), True) for n, c in zip(t.field_names, t.subtypes)])
+        if k == K_LIST:
+            return pa.list_(pa.field("item", self.arrow_type(t.subtypes[0], ts_unit), True))
+        if k == K_MAP:
+            return pa.map_(pa.field("keys", self.arrow_type(t.subtypes[0], ts_unit), False),
+                           pa.field("values", self.arrow_type(t.subtypes[1], ts_unit), True))
+        if k == K_UNION:
+            return pa.sparse_union([pa.field(f"_union_{i}", self.arrow_type(c, ts_unit), True) for i, c in enumerate(t.subtypes)],
+                                   type_codes=list(range(len(t.subtypes))))
+        raise NotImplementedError(f"ORC type kind {k}")
 
     def schema(self, columns: Optional[List[str]] = None, ts_unit: str = "ns"):
         import pyarrow as pa
@@ -391,91 +402,133 @@ class OracleFile:
         raw = np.frombuffer(self.data, dtype=np.uint8, count=st.length, offset=st.offset)
         return decompress_stream(self.compression, raw, self.block_size)
 
+    def _decode_leaf(self, smap, encodings, tz, cid, nn, name, ts_unit):
+        """The value streams of one primitive column: `nn` non-null values (array_decoder_factory, mod.rs:390-463)."""
+        t = self.types[cid]
+        ek, dict_size = encodings[cid] if cid < len(encodings) else (0, 0)
+        ver = 2 if ek in (2, 3) else 1  # column.rs:52-59
+        k = t.kind
+        if k == K_BOOLEAN:
+            vals = bool_rle(self._stream(smap, cid, S_DATA), nn)
+            payload = ("bool", vals)
+        elif k == K_BYTE:
+            payload = ("prim", byte_rle(self._stream(smap, cid, S_DATA), nn).view(np.int8))
+        elif k in (K_SHORT, K_INT, K_LONG, K_DATE):
+            nb = {K_SHORT: 2, K_INT: 4, K_LONG: 8, K_DATE: 4}[k]
+            v = int_rle(self._stream(smap, cid, S_DATA), nn, True, nb, ver)
+            payload = ("prim", v.astype({2: np.int16, 4: np.int32, 8: np.int64}[nb]))
+        elif k in (K_FLOAT, K_DOUBLE):
+            w = 4 if k == K_FLOAT else 8
+            raw = self._stream(smap, cid, S_DATA)
+            if raw.size < nn * w:
+                raise OracleError(1, "float stream too short")  # read_exact -> IoError
+            payload = ("prim", raw[: nn * w].copy().view(np.float32 if k == K_FLOAT else np.float64))
+        elif k in (K_STRING, K_VARCHAR, K_CHAR, K_BINARY):
+            if k != K_BINARY and ek in (1, 3):
+                dl = int_rle(self._stream(smap, cid, S_LENGTH), dict_size, False, 8, ver)
+                doff = np.empty(dict_size + 1, dtype=np.int32)
+                _check(lib().orc_oracle_offsets(_u8p(dl), ctypes.c_size_t(dict_size), _u8p(doff)), "dict offsets")
+                ddata = self._stream(smap, cid, S_DICTIONARY_DATA)
+                if ddata.size < int(doff[-1]):
+                    # the dictionary is built by the same next_byte_batch as direct strings (string.rs:65-74):
+                    # offsets past the bytes that could be read fail GenericByteArray::try_new
+                    raise OracleError(18, "dictionary data shorter than its lengths")
+                _validate_utf8(ddata, doff)  # the dictionary is a StringArray of its own
+                keys = int_rle(self._stream(smap, cid, S_DATA), nn, False, 8, ver)
+                payload = ("dict", keys, doff, np.ascontiguousarray(ddata))
+            else:
+                lens = int_rle(self._stream(smap, cid, S_LENGTH), nn, False, 8, ver)
+                payload = ("bytes", lens, self._stream(smap, cid, S_DATA))
+        elif k == K_DECIMAL:
+            v = varint_i128(self._stream(smap, cid, S_DATA), nn)
+            sc = int_rle(self._stream(smap, cid, S_SECONDARY), nn, True, 4, ver)
+            lib().orc_oracle_decimal_fix_scale(_u8p(v), _u8p(sc), ctypes.c_size_t(nn), ctypes.c_uint32(t.scale))
+            payload = ("prim", v)
+        elif k in (K_TIMESTAMP, K_TIMESTAMP_INSTANT):
+            d = int_rle(self._stream(smap, cid, S_DATA), nn, True, 8, ver)
+            sec = int_rle(self._stream(smap, cid, S_SECONDARY), nn, False, 8, ver)
+            base = ORC_EPOCH
+            zone = None
+            if k == K_TIMESTAMP and tz is not None:
+                zone = _zone(tz)
+                base = int(_dt.datetime(2015, 1, 1, tzinfo=zone).timestamp())
+            unit = _unit_of(ts_unit, name)
+            moved = zone is not None and tz not in ("UTC", "GMT", "Etc/UTC", "Etc/GMT")
+            if unit == "dec":
+                # TimestampNanosecondAsDecimalDecoder (+ ...WithTzDecoder, array_decoder/timestamp.rs:316-333)
+                o = np.empty((nn, 2), dtype=np.uint64)
+                lib().orc_oracle_timestamp_i128(_u8p(d), _u8p(sec), ctypes.c_size_t(nn), ctypes.c_int64(base), _u8p(o))
+                if moved:
+                    vals = [(int(hi) << 64 | int(lo)) - ((int(hi) >> 63) << 128) for lo, hi in o.tolist()]
+                    epoch = _dt.datetime(1970, 1, 1, tzinfo=_dt.timezone.utc)
+                    for i, v in enumerate(vals):
+                        off = int((epoch + _dt.timedelta(seconds=v // 1_000_000_000)).astimezone(zone).utcoffset().total_seconds())
+                        w = (v + off * 1_000_000_000) & ((1 << 128) - 1)
+                        o[i, 0], o[i, 1] = w & 0xFFFFFFFFFFFFFFFF, w >> 64
+            else:
+                unit_ns = {"ns": 1, "us": 1000, "ms": 1_000_000, "s": 1_000_000_000}[unit]
+                o = np.empty(nn, dtype=np.int64)
+                _check(lib().orc_oracle_timestamp(_u8p(d), _u8p(sec), ctypes.c_size_t(nn), ctypes.c_int64(base),
+                                                  ctypes.c_int64(unit_ns), _u8p(o)), "timestamp")
+                if moved:
+                    o = _tz_to_utc(o, zone, unit_ns)
+            payload = ("prim", o)
+        else:
+            raise NotImplementedError(f"ORC type kind {k}")
+        return payload
+
+    def _decode_node(self, smap, encodings, tz, cid, n, parent_present, name, ts_unit):
+        """One column over `n` slots of its parent (rows for a root column), recursively.  parent_present: bool array over
+        the slots or None.  Returns {"cid", "kind", "n", "present" (merged, derive_present_vec mod.rs:231-252, or None),
+        ...}: leaves carry "payload" and "rows"; struct "children"; list / map "lens" (per slot, 0 for nulls) and
+        "children" over sum(lens) slots; union "tags" (per slot, 0 for nulls) and "children"."""
+        t = self.types[cid]
+        k = t.kind
+        ek, _ = encodings[cid] if cid < len(encodings) else (0, 0)
+        ver = 2 if ek in (2, 3) else 1
+        present = parent_present
+        if (cid, S_PRESENT) in smap:
+            count = n if parent_present is None else int(parent_present.sum())
+            own = bool_rle(self._stream(smap, cid, S_PRESENT), count)
+            if parent_present is None:
+                present = own
+            else:  # merge_parent_present (mod.rs:216-229)
+                present = np.zeros(n, dtype=own.dtype)
+                present[parent_present.astype(bool)] = own
+        nn = int(present.sum()) if present is not None else n
+        node = {"cid": cid, "kind": k, "n": n, "present": present, "name": name}
+        if k == K_STRUCT:  # struct_decoder.rs:59-78
+            node["children"] = [self._decode_node(smap, encodings, tz, c, n, present, cn, ts_unit)
+                                for cn, c in zip(t.field_names, t.subtypes)]
+        elif k in (K_LIST, K_MAP):  # list.rs:63-87, map.rs:74-104
+            lens = int_rle(self._stream(smap, cid, S_LENGTH), nn, False, 8, ver)
+            rows = _to_rows(present, ("prim", lens), n)
+            total = int(rows.sum())
+            node["lens"] = rows
+            node["children"] = [self._decode_node(smap, encodings, tz, c, total, None, "", ts_unit) for c in t.subtypes]
+        elif k == K_UNION:  # union.rs:69-136
+            tags = byte_rle(self._stream(smap, cid, S_DATA), nn).view(np.int8)
+            rows = _to_rows(present, ("prim", tags), n)
+            node["tags"] = rows
+            kids = []
+            for i, c in enumerate(t.subtypes):
+                cp = rows == i
+                if i == 0 and present is not None:
+                    cp = cp & present.astype(bool)
+                kids.append(self._decode_node(smap, encodings, tz, c, n, cp.astype(np.uint8), "", ts_unit))
+            node["children"] = kids
+        else:
+            node["payload"] = self._decode_leaf(smap, encodings, tz, cid, nn, name, ts_unit)
+            node["rows"] = _to_rows(present, node["payload"], n)
+        return node
+
     def decode_stripe_columns(self, si: int, columns=None, ts_unit: str = "ns"):
-        """Whole-stripe decode: returns list of (name, col_id, present_bools|None, payload)."""
+        """Whole-stripe decode: returns (rows, [node]) with one node per projected root column (see _decode_node)."""
         s = self.stripes[si]
         streams, encodings, tz = self._stripe_footer(s)
         smap = {(st.column, st.kind): st for st in streams}
         n = s.number_of_rows
-        out = []
-        for name, cid in self._projected(columns):
-            t = self.types[cid]
-            ek, dict_size = encodings[cid] if cid < len(encodings) else (0, 0)
-            ver = 2 if ek in (2, 3) else 1  # column.rs:52-59
-            present = None
-            if (cid, S_PRESENT) in smap:
-                present = bool_rle(self._stream(smap, cid, S_PRESENT), n)
-            nn = int(present.sum()) if present is not None else n
-            k = t.kind
-            if k == K_BOOLEAN:
-                vals = bool_rle(self._stream(smap, cid, S_DATA), nn)
-                payload = ("bool", vals)
-            elif k == K_BYTE:
-                payload = ("prim", byte_rle(self._stream(smap, cid, S_DATA), nn).view(np.int8))
-            elif k in (K_SHORT, K_INT, K_LONG, K_DATE):
-                nb = {K_SHORT: 2, K_INT: 4, K_LONG: 8, K_DATE: 4}[k]
-                v = int_rle(self._stream(smap, cid, S_DATA), nn, True, nb, ver)
-                payload = ("prim", v.astype({2: np.int16, 4: np.int32, 8: np.int64}[nb]))
-            elif k in (K_FLOAT, K_DOUBLE):
-                w = 4 if k == K_FLOAT else 8
-                raw = self._stream(smap, cid, S_DATA)
-                if raw.size < nn * w:
-                    raise OracleError(1, "float stream too short")  # read_exact -> IoError
-                payload = ("prim", raw[: nn * w].copy().view(np.float32 if k == K_FLOAT else np.float64))
-            elif k in (K_STRING, K_VARCHAR, K_CHAR, K_BINARY):
-                if k != K_BINARY and ek in (1, 3):
-                    dl = int_rle(self._stream(smap, cid, S_LENGTH), dict_size, False, 8, ver)
-                    doff = np.empty(dict_size + 1, dtype=np.int32)
-                    _check(lib().orc_oracle_offsets(_u8p(dl), ctypes.c_size_t(dict_size), _u8p(doff)), "dict offsets")
-                    ddata = self._stream(smap, cid, S_DICTIONARY_DATA)
-                    if ddata.size < int(doff[-1]):
-                        # the dictionary is built by the same next_byte_batch as direct strings (string.rs:65-74):
-                        # offsets past the bytes that could be read fail GenericByteArray::try_new
-                        raise OracleError(18, "dictionary data shorter than its lengths")
-                    _validate_utf8(ddata, doff)  # the dictionary is a StringArray of its own
-                    keys = int_rle(self._stream(smap, cid, S_DATA), nn, False, 8, ver)
-                    payload = ("dict", keys, doff, np.ascontiguousarray(ddata))
-                else:
-                    lens = int_rle(self._stream(smap, cid, S_LENGTH), nn, False, 8, ver)
-                    payload = ("bytes", lens, self._stream(smap, cid, S_DATA))
-            elif k == K_DECIMAL:
-                v = varint_i128(self._stream(smap, cid, S_DATA), nn)
-                sc = int_rle(self._stream(smap, cid, S_SECONDARY), nn, True, 4, ver)
-                lib().orc_oracle_decimal_fix_scale(_u8p(v), _u8p(sc), ctypes.c_size_t(nn), ctypes.c_uint32(t.scale))
-                payload = ("prim", v)
-            elif k in (K_TIMESTAMP, K_TIMESTAMP_INSTANT):
-                d = int_rle(self._stream(smap, cid, S_DATA), nn, True, 8, ver)
-                sec = int_rle(self._stream(smap, cid, S_SECONDARY), nn, False, 8, ver)
-                base = ORC_EPOCH
-                zone = None
-                if k == K_TIMESTAMP and tz is not None:
-                    zone = _zone(tz)
-                    base = int(_dt.datetime(2015, 1, 1, tzinfo=zone).timestamp())
-                unit = _unit_of(ts_unit, name)
-                moved = zone is not None and tz not in ("UTC", "GMT", "Etc/UTC", "Etc/GMT")
-                if unit == "dec":
-                    # TimestampNanosecondAsDecimalDecoder (+ ...WithTzDecoder, array_decoder/timestamp.rs:316-333)
-                    o = np.empty((nn, 2), dtype=np.uint64)
-                    lib().orc_oracle_timestamp_i128(_u8p(d), _u8p(sec), ctypes.c_size_t(nn), ctypes.c_int64(base), _u8p(o))
-                    if moved:
-                        vals = [(int(hi) << 64 | int(lo)) - ((int(hi) >> 63) << 128) for lo, hi in o.tolist()]
-                        epoch = _dt.datetime(1970, 1, 1, tzinfo=_dt.timezone.utc)
-                        for i, v in enumerate(vals):
-                            off = int((epoch + _dt.timedelta(seconds=v // 1_000_000_000)).astimezone(zone).utcoffset().total_seconds())
-                            w = (v + off * 1_000_000_000) & ((1 << 128) - 1)
-                            o[i, 0], o[i, 1] = w & 0xFFFFFFFFFFFFFFFF, w >> 64
-                else:
-                    unit_ns = {"ns": 1, "us": 1000, "ms": 1_000_000, "s": 1_000_000_000}[unit]
-                    o = np.empty(nn, dtype=np.int64)
-                    _check(lib().orc_oracle_timestamp(_u8p(d), _u8p(sec), ctypes.c_size_t(nn), ctypes.c_int64(base),
-                                                      ctypes.c_int64(unit_ns), _u8p(o)), "timestamp")
-                    if moved:
-                        o = _tz_to_utc(o, zone, unit_ns)
-                payload = ("prim", o)
-            else:
-                raise NotImplementedError(f"nested ORC type kind {k} not restated in the oracle yet")
-            out.append((name, cid, present, payload))
-        return n, out
+        return n, [self._decode_node(smap, encodings, tz, cid, n, None, name, ts_unit) for name, cid in self._projected(columns)]
 
     # --- with_predicate (src/row_index.rs:204-331, src/arrow_reader.rs:256-293) ------------------------------------
     def stripe_row_index(self, si: int, columns=None):
@@ -536,17 +589,11 @@ class OracleFile:
         import pyarrow as pa
         n, cols = self.decode_stripe_columns(si, columns, ts_unit)
         schema = self.schema(columns, ts_unit)
-        # spaced (row-domain) representation per column
-        spaced = []
-        for name, cid, present, payload in cols:
-            spaced.append(_to_rows(present, payload, n))
         if views is None:
             views = [(a, min(batch_size, n - a)) for a in range(0, n, batch_size)]
         batches = []
         for a, k in views:
-            arrays = []
-            for (name, cid, present, payload), rows in zip(cols, spaced):
-                arrays.append(_slice_to_arrow(schema.field(name).type, present, payload, rows, a, a + k))
+            arrays = [_node_to_arrow(schema.field(node["name"]).type, node, a, a + k) for node in cols]
             if not arrays:
                 batches.append(pa.RecordBatch.from_struct_array(pa.array([{}] * k, pa.struct([]))))
             else:
@@ -1153,6 +1200,38 @@ def _slice_to_arrow(typ, present, payload, rows, a, b):
         return pa.Array.from_buffers(typ, n, [vbuf, pa.py_buffer(offs.tobytes()),
                                               pa.py_buffer(data[: total.value].tobytes())], null_count=nulls)
     raise AssertionError(kind)
+
+
+def _node_to_arrow(typ, node, a, b):
+    """Slots [a, b) of a decoded column as the Arrow array the reference builds for that batch."""
+    import pyarrow as pa
+    k = node["kind"]
+    n = b - a
+    if k not in (K_STRUCT, K_LIST, K_MAP, K_UNION):
+        return _slice_to_arrow(typ, node["present"], node["payload"], node["rows"], a, b)
+    vbuf, nulls = _validity(node["present"], a, b)
+    if k == K_STRUCT:
+        kids = [_node_to_arrow(typ.field(i).type, c, a, b) for i, c in enumerate(node["children"])]
+        return pa.Array.from_buffers(typ, n, [vbuf], null_count=nulls, children=kids)
+    if k in (K_LIST, K_MAP):
+        lens = np.ascontiguousarray(node["lens"][a:b])
+        offs = np.empty(n + 1, dtype=np.int32)
+        _check(lib().orc_oracle_offsets(_u8p(lens), ctypes.c_size_t(n), _u8p(offs)), "offsets")
+        start = int(node["lens"][:a].sum())
+        end = start + int(offs[-1])
+        if k == K_LIST:
+            child = _node_to_arrow(typ.value_type, node["children"][0], start, end)
+            return pa.Array.from_buffers(typ, n, [vbuf, pa.py_buffer(offs.tobytes())], null_count=nulls, children=[child])
+        keys = _node_to_arrow(typ.key_type, node["children"][0], start, end)
+        items = _node_to_arrow(typ.item_type, node["children"][1], start, end)
+        entries = pa.Array.from_buffers(pa.struct([typ.key_field, typ.item_field]), end - start, [None], null_count=0,
+                                        children=[keys, items])
+        return pa.Array.from_buffers(typ, n, [vbuf, pa.py_buffer(offs.tobytes())], null_count=nulls, children=[entries])
+    # sparse union: type ids + one child per variant, each over every slot (union.rs:118-124)
+    tags = np.ascontiguousarray(node["tags"][a:b]).astype(np.int8)
+    kids = [_node_to_arrow(typ.field(i).type, c, a, b) for i, c in enumerate(node["children"])]
+    return pa.UnionArray.from_sparse(pa.array(tags, pa.int8()), kids, [typ.field(i).name for i in range(typ.num_fields)],
+                                     list(range(typ.num_fields)))
 
 
 def _validate_utf8(data: np.ndarray, offs: np.ndarray):
