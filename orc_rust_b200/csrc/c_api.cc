@@ -226,7 +226,7 @@ int orcb_schema(const OrcbFile* f, const OrcbReadOptions* opt, struct ArrowSchem
     return guarded([&] {
         ReadOptions o = ReadOptions::from_c(opt);
         auto cols = project_columns(f->meta, o);
-        export_schema(f->meta, cols, out);
+        export_schema(f->meta, cols, o, out);
     });
 }
 

@@ -9,7 +9,8 @@
 namespace orcb {
 
 // AR_ZERO: temporaries that must be zero before every launch (atomicOr targets)
-enum Arena : uint64_t { AR_NULL = 0, AR_IN = 1, AR_DEC = 2, AR_OUT = 3, AR_TMP = 4, AR_HEAP = 5, AR_ZERO = 6 };
+// AR_ABS: not an arena - the offset is an absolute device address (buffers of an earlier job, e.g. a parent's validity)
+enum Arena : uint64_t { AR_NULL = 0, AR_IN = 1, AR_DEC = 2, AR_OUT = 3, AR_TMP = 4, AR_HEAP = 5, AR_ZERO = 6, AR_ABS = 7 };
 static inline uint64_t aref(Arena a, uint64_t off) { return ((uint64_t)a << 60) | off; }
 
 // how an integer-RLE segment stores its values
@@ -200,6 +201,25 @@ struct ChunkDesc {
     uint8_t pad[2];
     uint32_t colstripe;
     uint32_t id;         // slot of this chunk in the table of decompressed sizes
+};
+
+// popcount of a validity bitmap into cnt[] (a column whose validity comes from its parent, merged or as is)
+struct PopcDesc {
+    uint64_t bits;
+    uint32_t n_bits;
+    uint32_t out;        // cnt[out] = number of set bits
+};
+
+// sparse union (array_decoder/union.rs:83-113): the validity every child decodes under.  Child i is valid where
+// tag == i; child 0 additionally only where the union itself is valid (null slots carry tag 0).
+struct UnionDesc {
+    uint64_t tags;       // i8 per slot (null slots 0)
+    uint64_t valid;      // the union's own validity bitmap or 0
+    uint64_t bits;       // out: n_children bitmaps, `stride` bytes apart, zero-initialised
+    uint32_t n;
+    uint32_t n_children;
+    uint32_t stride;
+    uint32_t counts;     // meta: nulls[counts + i] = set bits of child i's bitmap
 };
 
 // job-wide mutable device state

@@ -123,7 +123,15 @@ DeviceArenas::~DeviceArenas() {
 
 
 Job::Job(std::vector<StripeTask> tasks, const ReadOptions& opt) : tasks_(std::move(tasks)), opt_(opt), orig_opt_(opt) {
-    if (!tasks_.empty()) cols_ = project_columns(*tasks_[0].file, opt_);
+    if (tasks_.empty()) return;
+    if (tasks_[0].roots.empty()) {
+        cols_ = project_columns(*tasks_[0].file, opt_);
+    } else {
+        // a later nesting level: the columns are the children the level before handed over (same ids for every task)
+        for (auto& r : tasks_[0].roots) cols_.push_back(column_info(*tasks_[0].file, r.col_id, "", opt_, -1));
+        for (auto& t : tasks_)
+            if (t.roots.size() != cols_.size()) fail(ORCB_UNEXPECTED, "stripes of one job disagree on their nested columns");
+    }
 }
 
 Job::KStat& Job::kstat(const char* name) {
@@ -160,6 +168,7 @@ void Job::restage() {
 }
 
 Job::~Job() {
+    next_level_.reset();  // the levels below run on this job's stream: they go first
     // pooled memory does not wait for pending work when it is freed (cudaFree did): a job dropped between launch()
     // and finish(), or while an end-to-end restage is in flight, drains its streams first
     if (staged_) {
@@ -188,6 +197,7 @@ uint64_t Job::alloc(Arena a, uint64_t bytes, uint64_t align) {
 uint64_t Job::reloc(uint64_t tagged) const {
     const uint64_t a = tagged >> 60;
     if (a == AR_NULL) return 0;
+    if (a == AR_ABS) return tagged & ((1ull << 60) - 1);
     return (uint64_t)(uintptr_t)base_[a] + (tagged & ((1ull << 60) - 1));
 }
 
@@ -222,7 +232,7 @@ void Job::stage() {
     auto arenas = std::make_shared<DeviceArenas>();
     arenas->device = opt_.device;
     arenas->pooled = DeviceArenas::use_pool(opt_.device);
-    for (int a = 1; a < 8; a++) base_[a] = (uint8_t*)arenas->alloc(std::max<uint64_t>(size_[a], 256), stream_);
+    for (int a = 1; a < 7; a++) base_[a] = (uint8_t*)arenas->alloc(std::max<uint64_t>(size_[a], 256), stream_);
     d_desc_ = (uint8_t*)arenas->alloc(std::max<uint64_t>(desc_bytes_, 256), stream_);
     d_state_ = (uint8_t*)arenas->alloc(std::max<uint64_t>(state_bytes_, 256), stream_);
     d_meta_ = (uint8_t*)arenas->alloc(std::max<uint64_t>(meta_bytes_, 256), stream_);
@@ -242,8 +252,10 @@ void Job::stage() {
     for (auto* v : {&present_bit_segs_, &data_bit_segs_})
         for (auto& b : *v) { R(b.src); R(b.dst); }
     for (auto& c : copies_) { R(c.src); R(c.dst); }
-    for (auto* v : {&spaced_, &spaced_late_})
+    for (auto* v : {&spaced_, &spaced_late_, &merge_spaced_})
         for (auto& d : *v) { R(d.src); R(d.dst); R(d.valid); }
+    for (auto& d : popcs_) R(d.bits);
+    for (auto& d : unions_) { R(d.tags); R(d.valid); R(d.bits); }
     for (auto& d : decfix_) { R(d.vals); R(d.scales); }
     for (auto& d : ts_) {
         R(d.secs); R(d.nanos); R(d.out);
@@ -277,6 +289,9 @@ void Job::stage() {
     put(o_u8tile_, u8_tiles_.data(), u8_tiles_.size() * sizeof(uint2));
     put(o_sp_, spaced_.data(), spaced_.size() * sizeof(SpacedDesc));
     put(o_sp2_, spaced_late_.data(), spaced_late_.size() * sizeof(SpacedDesc));
+    put(o_spm_, merge_spaced_.data(), merge_spaced_.size() * sizeof(SpacedDesc));
+    put(o_popc_, popcs_.data(), popcs_.size() * sizeof(PopcDesc));
+    put(o_union_, unions_.data(), unions_.size() * sizeof(UnionDesc));
     put(o_dec_, decfix_.data(), decfix_.size() * sizeof(DecFixDesc));
     put(o_ts_, ts_.data(), ts_.size() * sizeof(TsDesc));
     put(o_str_, strcols_.data(), strcols_.size() * sizeof(StrCol));
@@ -339,8 +354,14 @@ void Job::launch() {
     if (N(present_byte_segs_)) {
         run("k_byte_rle(present)", ab_present_, N(present_byte_segs_), 1, [&] { return launch_byte_rle((Seg*)(d_desc_ + o_pbyte_), N(present_byte_segs_), cnt, dstart, err, st); });
         run("k_bits(present)", ab_present_, N(present_bit_segs_), 1, [&] { return launch_bits((BitSeg*)(d_desc_ + o_pbit_), N(present_bit_segs_), cnt, dstart, st); });
-        run("k_seg_scan", 0, N(scans_), 1, [&] { return launch_seg_scan((ScanDesc*)(d_desc_ + o_scan_), N(scans_), cnt, dstart, st); });
     }
+    // validity handed down by a parent column: own PRESENT bits scattered into the parent's valid slots, then counted
+    if (N(merge_spaced_))
+        run("k_spaced(validity)", 0, N(merge_spaced_), 1, [&] { return launch_spaced((SpacedDesc*)(d_desc_ + o_spm_), N(merge_spaced_), dstart, st); });
+    if (N(popcs_))
+        run("k_popc", 0, N(popcs_), 1, [&] { return launch_popc((PopcDesc*)(d_desc_ + o_popc_), N(popcs_), cnt, st); });
+    if (N(scans_))
+        run("k_seg_scan", 0, N(scans_), 1, [&] { return launch_seg_scan((ScanDesc*)(d_desc_ + o_scan_), N(scans_), cnt, dstart, st); });
     if (N(data_byte_segs_))
         run("k_byte_rle", ab_byte_, N(data_byte_segs_), 1, [&] { return launch_byte_rle((Seg*)(d_desc_ + o_dbyte_), N(data_byte_segs_), cnt, dstart, err, st); });
     if (N(data_bit_segs_))
@@ -390,6 +411,8 @@ void Job::launch() {
         run("k_spaced", ab_spaced_, N(spaced_), 1, [&] { return launch_spaced((SpacedDesc*)(d_desc_ + o_sp_), N(spaced_), dstart, st); });
     if (N(spaced_late_))
         run("k_spaced(late)", ab_spaced_, N(spaced_late_), 1, [&] { return launch_spaced((SpacedDesc*)(d_desc_ + o_sp2_), N(spaced_late_), dstart, st); });
+    if (N(unions_))
+        run("k_union_valid", 0, N(unions_), 1, [&] { return launch_union_valid((UnionDesc*)(d_desc_ + o_union_), N(unions_), nulls, st); });
     if (N(strcols_))
         run("k_strings(5 kernels)", ab_str_, str_tiles_, 5, [&] { return launch_strings((StrCol*)(d_desc_ + o_str_), N(strcols_), str_tiles_, err, dstate, (uint64_t)(uintptr_t)base_[AR_HEAP], heap_cap, ptrs, st); });
     if (repack_work_)
@@ -444,6 +467,9 @@ void Job::finish() {
             const uint32_t rows = std::min(bs, cp.n_rows - b * bs);
             if (cp.has_present && nulls[cp.nulls_idx + b]) output_bytes_ += (rows + 7) / 8;
             if (oc.kind == T_BOOLEAN) output_bytes_ += (rows + 7) / 8;
+            else if (cp.is_list) output_bytes_ += 4ull * (rows + 1);
+            else if (oc.kind == T_STRUCT) {}
+            else if (oc.kind == T_UNION) output_bytes_ += rows;
             else if (cp.str_slot >= 0) {
                 const int64_t* bb = (const int64_t*)(h_meta_ + o_bbase_ + cp.batch_base_off);
                 output_bytes_ += 4ull * (rows + 1) + (uint64_t)(bb[b + 1] - bb[b]);
@@ -452,6 +478,68 @@ void Job::finish() {
         }
     }
     finished_ = true;
+    run_next_level();
+}
+
+// the roots of the next nesting level for task t: the children of this level's struct / list / map / union columns
+std::vector<RootSpec> Job::next_roots(uint32_t t) const {
+    std::vector<RootSpec> out;
+    const uint32_t* nulls = (const uint32_t*)(h_meta_ + o_nulls_);
+    const uint32_t cs0 = task_first_cs_[t];
+    for (uint32_t c = 0; c < cols_.size(); c++) {
+        const ColStripePlan& cp = colstripes_[cs0 + c];
+        const int kind = cols_[c].kind;
+        for (size_t i = 0; i < cp.kids.size(); i++) {
+            RootSpec r;
+            r.col_id = cp.kids[i];
+            if (cp.n_rows == 0) {
+                out.push_back(r);
+                continue;
+            }
+            if (kind == T_LIST || kind == T_MAP) {
+                const int64_t* bb = (const int64_t*)(h_meta_ + o_bbase_ + cp.batch_base_off);
+                r.n_slots = (uint64_t)bb[cp.n_batches];
+            } else if (kind == T_UNION) {
+                r.n_slots = cp.n_rows;
+                r.has_parent = true;
+                r.parent_bits = reloc(cp.union_bits) + (uint64_t)i * cp.union_stride;
+                r.parent_count = nulls[cp.union_counts + i];
+            } else {  // struct
+                r.n_slots = cp.n_rows;
+                if (cp.has_present) {
+                    uint64_t n_null = 0;
+                    for (uint32_t b = 0; b < cp.n_batches; b++) n_null += nulls[cp.nulls_idx + b];
+                    r.has_parent = true;
+                    r.parent_bits = reloc(cp.valid_bits);
+                    r.parent_count = cp.n_rows - n_null;
+                }
+            }
+            out.push_back(r);
+        }
+    }
+    return out;
+}
+
+void Job::run_next_level() {
+    bool any = false;
+    for (auto& cp : colstripes_) any |= !cp.kids.empty();
+    if (!any) return;
+    std::vector<StripeTask> tasks;
+    for (uint32_t t = 0; t < tasks_.size(); t++) {
+        StripeTask nt{tasks_[t].file, tasks_[t].stripe};
+        nt.roots = next_roots(t);
+        tasks.push_back(std::move(nt));
+    }
+    ReadOptions o = orig_opt_;
+    o.stream = stream_;       // same stream: the children read this level's validity bitmaps
+    o.own_stream = false;
+    next_level_ = std::make_unique<Job>(std::move(tasks), o);
+    next_level_->plan();
+    next_level_->stage();
+    next_level_->launch();
+    next_level_->finish();    // (recursively runs the levels below)
+    output_bytes_ += next_level_->output_bytes_;
+    aliased_bytes_ += next_level_->aliased_bytes_;
 }
 
 void Job::stats(OrcbJobStats* out) const {

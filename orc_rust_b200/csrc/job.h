@@ -44,17 +44,31 @@ struct OutColumn {
     uint32_t width = 0;  // bytes per value (0 for bool / strings)
     int ts_unit = 0;     // timestamps: 0 ns, 1 us, 2 ms, 3 s
     bool ts_decimal = false;  // timestamps read as Decimal128(38, 9)
+    std::vector<uint32_t> child_ids;  // struct / list / map / union: the children's column ids
 };
 
 std::vector<OutColumn> project_columns(const FileMeta& fm, const ReadOptions& opt);
-void export_schema(const FileMeta& fm, const std::vector<OutColumn>& cols, ArrowSchema* out);
+OutColumn column_info(const FileMeta& fm, uint32_t col_id, const std::string& name, const ReadOptions& opt, int hint);
+bool has_nested_columns(const std::vector<OutColumn>& cols);
+void export_schema(const FileMeta& fm, const std::vector<OutColumn>& cols, const ReadOptions& opt, ArrowSchema* out);
 // with_schema: checks the caller's Arrow schema against the file (array_decoder_factory, src/array_decoder/mod.rs:390-511)
 // and records the timestamp variants it asks for in opt.ts_hint
 void apply_schema_hints(const FileMeta& fm, ReadOptions& opt, const ArrowSchema* schema);
 
+// A column decoded by a job over `n_slots` slots: a projected root column over the stripe's rows, or - in the jobs
+// that follow for nested types - a child column over the slots its parent gives it.
+struct RootSpec {
+    uint32_t col_id = 0;
+    uint64_t n_slots = 0;
+    bool has_parent = false;    // decodes under a parent's validity (struct and union children)
+    uint64_t parent_bits = 0;   // device address of that validity bitmap over the slots, LSB first
+    uint64_t parent_count = 0;  // set bits in it = entries of this column's own PRESENT stream (merge_parent_present)
+};
+
 struct StripeTask {
     const FileMeta* file;
     uint32_t stripe;
+    std::vector<RootSpec> roots;  // empty: the projected root columns over the stripe's rows
     // row selection (src/array_decoder/mod.rs:313-364): the batches of this stripe are these row ranges, in order,
     // instead of consecutive batch_size slices.  The stripe is decoded once; the ranges are exported as views.
     bool has_views = false;
@@ -95,6 +109,12 @@ struct ColStripePlan {
     uint64_t str_host_off = 0;        //   offset of their host copy in HostOutput::strs
     int32_t str_slot = -1;            // index into StrCol table / ptr_table
     uint64_t batch_base_off = 0;      // byte offset inside the meta blob of i64[n_batches+1]
+    // nested types (struct / list / map / union): the children are decoded by the next-level job
+    bool is_list = false;             // list / map: `offsets` are element offsets, batch_base[1] the children's slot count
+    std::vector<uint32_t> kids;       // children's column ids
+    uint64_t valid_bits = 0;          // arena-tagged stripe-level validity bitmap of this column (0 = none)
+    uint64_t union_bits = 0;          // union: arena-tagged child validity bitmaps, union_stride bytes apart
+    uint32_t union_stride = 0, union_counts = 0;  // nulls[union_counts + i] = valid slots of child i
 };
 
 struct HostOutput;  // D2H copy of the output arenas, shared by exported batches
@@ -117,12 +137,17 @@ class Job {
     void stats(OrcbJobStats* out) const;
     uint32_t kernel_stats(OrcbKernelStat* out, uint32_t cap) const;
     uint64_t num_batches() const { return batch_task_.size(); }
+    // nested columns: the roots the next-level job decodes for task `t` (valid after finish())
+    std::vector<RootSpec> next_roots(uint32_t t) const;
     cudaStream_t stream() const { return stream_; }
     void export_batch(uint64_t i, ArrowArray* out);
     void export_batch_device(uint64_t i, ArrowDeviceArray* out);
     const std::vector<OutColumn>& columns() const { return cols_; }
 
   private:
+    void run_next_level();
+    // one column (any depth) of batch rows [slot0, slot0 + n): `top` = a root column of the batch (carries the view offset)
+    void export_node(uint32_t cs, int64_t slot0, int64_t n, bool top, bool device, ArrowArray* a);
     uint64_t alloc(Arena a, uint64_t bytes, uint64_t align = 256);
     uint64_t reloc(uint64_t tagged) const;
     void plan_stripe(uint32_t task_idx);
@@ -147,7 +172,11 @@ class Job {
     std::map<std::string, std::array<uint64_t, 4>> tz_tables_;  // zone -> {offset of instants, offset of offsets, n, first}
     std::map<std::pair<const void*, uint32_t>, uint64_t> staged_stripes_;  // (file, stripe) -> offset of its data in the IN arena
     std::vector<uint2> u8_tiles_;   // (string column, U8_TILE-byte tile) units of the UTF-8 check
-    std::vector<SpacedDesc> spaced_, spaced_late_;
+    std::vector<SpacedDesc> spaced_, spaced_late_, merge_spaced_;
+    std::vector<PopcDesc> popcs_;
+    std::vector<UnionDesc> unions_;
+    bool nested_ = false;                  // some column is (or descends from) a struct / list / map / union
+    std::unique_ptr<Job> next_level_;      // decodes the children of this job's nested columns
     std::vector<DecFixDesc> decfix_;
     std::vector<TsDesc> ts_;
     std::vector<StrCol> strcols_;
@@ -170,7 +199,7 @@ class Job {
     uint64_t desc_bytes_ = 0;
     // offsets of each table inside the descriptor blob
     uint64_t o_pbyte_ = 0, o_dbyte_ = 0, o_int_ = 0, o_intbig_ = 0, o_var_ = 0, o_pbit_ = 0, o_dbit_ = 0, o_scan_ = 0, o_copy_ = 0,
-             o_ctile_ = 0, o_sp_ = 0, o_sp2_ = 0, o_dec_ = 0, o_ts_ = 0, o_str_ = 0, o_rep_ = 0, o_chunk_ = 0, o_u8tile_ = 0, o_tz_ = 0;
+             o_ctile_ = 0, o_sp_ = 0, o_sp2_ = 0, o_spm_ = 0, o_popc_ = 0, o_union_ = 0, o_dec_ = 0, o_ts_ = 0, o_str_ = 0, o_rep_ = 0, o_chunk_ = 0, o_u8tile_ = 0, o_tz_ = 0;
     std::vector<uint8_t> desc_blob_;
 
     // state blob (device only, zeroed per launch): cnt[], dstart[], mis[], JobState

@@ -116,6 +116,47 @@ __global__ void k_seg_scan(const ScanDesc* __restrict__ descs, uint32_t ndesc, u
     }
 }
 
+// popcount of a bitmap (validity handed down by a parent column)
+__global__ void __launch_bounds__(128) k_popc(const PopcDesc* __restrict__ descs, uint32_t ndesc, uint32_t* cnt) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= ndesc) return;
+    const PopcDesc d = descs[warp];
+    const int lane = threadIdx.x & 31;
+    const uint32_t* bm = (const uint32_t*)d.bits;
+    uint32_t pc = 0;
+    const uint32_t nw = (d.n_bits + 31) / 32;
+    for (uint32_t w = lane; w < nw; w += 32) {
+        uint32_t v = bm[w];
+        if (w == nw - 1 && (d.n_bits & 31)) v &= (1u << (d.n_bits & 31)) - 1u;
+        pc += __popc(v);
+    }
+    pc = (uint32_t)warp_sum64(pc);
+    if (lane == 0) cnt[d.out] = pc;
+}
+
+// validity of the children of a sparse union (union.rs:83-113)
+__global__ void __launch_bounds__(128) k_union_valid(const UnionDesc* __restrict__ descs, uint32_t ndesc, uint32_t* meta) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= ndesc) return;
+    const UnionDesc d = descs[warp];
+    const int lane = threadIdx.x & 31;
+    const int8_t* tags = (const int8_t*)d.tags;
+    const uint32_t* valid = (const uint32_t*)d.valid;
+    for (uint32_t c = 0; c < d.n_children; c++) {
+        uint32_t* out = (uint32_t*)(d.bits + (uint64_t)c * d.stride);
+        uint32_t pc = 0;
+        for (uint32_t r0 = 0; r0 < d.n; r0 += 32) {
+            const uint32_t r = r0 + lane;
+            bool on = r < d.n && (uint32_t)(int32_t)tags[r] == c;
+            if (on && c == 0 && valid) on = (valid[r >> 5] >> (r & 31)) & 1u;
+            const uint32_t word = __ballot_sync(FULL, on);
+            if (lane == 0) out[r0 >> 5] = word;
+            pc += __popc(word);
+        }
+        if (lane == 0) meta[d.counts + c] = pc;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Decimal DATA: unbounded zigzag varints -> i128 (encoding/decimal.rs:46-51, integer/util.rs:475-527).
 // Terminator bytes found with ballot; the lane owning a terminator assembles its value.
@@ -564,6 +605,19 @@ int launch_timestamp(const TsDesc* d, uint32_t n, const uint32_t* cnt, uint32_t*
 int launch_repack(const RepackDesc* d, uint32_t ndesc, uint32_t nwork, uint32_t* nulls, cudaStream_t st) {
     if (!nwork) return 0;
     k_repack<<<blocks_for_warps(nwork, 4), 128, 0, st>>>(d, ndesc, nwork, nulls);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_popc(const PopcDesc* d, uint32_t n, uint32_t* cnt, cudaStream_t st) {
+    if (!n) return 0;
+    k_popc<<<blocks_for_warps(n, 4), 128, 0, st>>>(d, n, cnt);
+    LAUNCH_CHECK();
+    return 0;
+}
+int launch_union_valid(const UnionDesc* d, uint32_t n, uint32_t* meta, cudaStream_t st) {
+    if (!n) return 0;
+    k_union_valid<<<blocks_for_warps(n, 4), 128, 0, st>>>(d, n, meta);
     LAUNCH_CHECK();
     return 0;
 }

@@ -25,6 +25,8 @@ int launch_varint128(const Seg* segs, uint32_t n, const uint32_t* cnt, const uin
 int launch_copy(const CopyDesc* d, const uint2* tiles, uint32_t ntiles, const uint32_t* cnt, uint32_t* err,
                 const StrCol* strcols, cudaStream_t st);
 int launch_spaced(const SpacedDesc* d, uint32_t n, const uint32_t* dstart, cudaStream_t st);
+int launch_popc(const PopcDesc* d, uint32_t n, uint32_t* cnt, cudaStream_t st);
+int launch_union_valid(const UnionDesc* d, uint32_t n, uint32_t* meta, cudaStream_t st);
 int launch_decimal_fix(const DecFixDesc* d, uint32_t n, const uint32_t* cnt, const uint32_t* mis, cudaStream_t st);
 int launch_timestamp(const TsDesc* d, uint32_t n, const uint32_t* cnt, uint32_t* err, cudaStream_t st);
 int launch_utf8(const StrCol* cols, const uint2* tiles, uint32_t ntiles, cudaStream_t st);

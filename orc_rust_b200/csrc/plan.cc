@@ -81,13 +81,22 @@ void Job::plan() {
     task_first_cs_.clear();
     staged_stripes_.clear();
     for (auto& t : tasks_) view_mode_ |= t.has_views;
+    // nested columns: children have as many slots as their parents' data says, batches of a list's children do not
+    // fall on fixed boundaries - everything is decoded as one internal batch and exported as views
+    nested_ = has_nested_columns(cols_);
+    for (auto& t : tasks_) nested_ |= !t.roots.empty();
+    view_mode_ |= nested_;
     user_batch_size_ = opt_.batch_size;
     if (view_mode_) {
         // row selection: one internal batch per stripe (stripe-level offsets and bitmaps); the user's batches are
         // views into it, exported through the Arrow `offset` field
         uint64_t mx = 1;
-        for (auto& t : tasks_) mx = std::max<uint64_t>(mx, t.file->stripes[t.stripe].rows);
-        opt_.batch_size = (uint32_t)std::min<uint64_t>(mx, 0xfffffff0ull);
+        for (auto& t : tasks_) {
+            mx = std::max<uint64_t>(mx, t.file->stripes[t.stripe].rows);
+            for (auto& r : t.roots) mx = std::max<uint64_t>(mx, r.n_slots);
+        }
+        if (mx > 0xfffffff0ull) fail(ORCB_NOT_IMPLEMENTED, "more than 2^32 slots in one nested column of a stripe");
+        opt_.batch_size = (uint32_t)mx;
     }
     for (uint32_t t = 0; t < tasks_.size(); t++) plan_stripe(t);
 
@@ -134,6 +143,9 @@ void Job::plan() {
     place(o_u8tile_, u8_tiles_.size() * sizeof(uint2));
     place(o_sp_, spaced_.size() * sizeof(SpacedDesc));
     place(o_sp2_, spaced_late_.size() * sizeof(SpacedDesc));
+    place(o_spm_, merge_spaced_.size() * sizeof(SpacedDesc));
+    place(o_popc_, popcs_.size() * sizeof(PopcDesc));
+    place(o_union_, unions_.size() * sizeof(UnionDesc));
     place(o_dec_, decfix_.size() * sizeof(DecFixDesc));
     place(o_ts_, ts_.size() * sizeof(TsDesc));
     place(o_str_, strcols_.size() * sizeof(StrCol));
@@ -243,14 +255,18 @@ void Job::plan_stripe(uint32_t task_idx) {
     const uint32_t idx_groups = stripe_rows ? (stripe_rows + stride - 1) / stride : 0;
     // partial decode (row selection): row groups [wg0, wg1) only
     const StripeTask& task = tasks_[task_idx];
-    const bool windowed = task.has_window && want_index && idx_groups > 1 && task.g_begin < task.g_end && task.g_end <= idx_groups;
+    const bool windowed = !nested_ && task.has_window && want_index && idx_groups > 1 && task.g_begin < task.g_end && task.g_end <= idx_groups;
     const uint32_t wg0 = windowed ? task.g_begin : 0, wg1 = windowed ? task.g_end : idx_groups;
 
     for (uint32_t ci = 0; ci < cols_.size(); ci++) {
         const OutColumn& oc = cols_[ci];
         const uint32_t cid = oc.col_id;
         const uint32_t cs = (uint32_t)colstripes_.size();
-        uint32_t n_rows = stripe_rows;  // rows this column decodes: the stripe's, or the window's once the index is known good
+        // a column of a later nesting level decodes the slots its parent gave it, possibly under the parent's validity
+        const RootSpec* rs = task.roots.empty() ? nullptr : &task.roots.at(ci);
+        const bool has_parent = rs && rs->has_parent;
+        if (rs && rs->n_slots > 0xfffffff0ull) fail(ORCB_NOT_IMPLEMENTED, "more than 2^32 slots in one nested column of a stripe");
+        uint32_t n_rows = rs ? (uint32_t)rs->n_slots : stripe_rows;  // rows this column decodes: the stripe's, or the window's once the index is known good
         uint32_t n_batches = (n_rows + bs - 1) / bs;
         ColStripePlan cp;
         cp.task = task_idx;
@@ -258,6 +274,8 @@ void Job::plan_stripe(uint32_t task_idx) {
         cp.n_rows = n_rows;
         cp.n_batches = n_batches;
         if (n_rows == 0) {
+            cp.kids = oc.child_ids;
+            cp.is_list = oc.kind == T_LIST || oc.kind == T_MAP;
             colstripes_.push_back(cp);
             continue;
         }
@@ -325,11 +343,13 @@ void Job::plan_stripe(uint32_t task_idx) {
         const int k = oc.kind;
         const bool is_str = k == T_STRING || k == T_VARCHAR || k == T_CHAR || k == T_BINARY;
         const bool use_dict = is_str && k != T_BINARY && dict_enc;  // string.rs:51-84 (binary is always direct)
-        if (is_str) s_length = resolve(S_LENGTH);
+        if (is_str || k == T_LIST || k == T_MAP) s_length = resolve(S_LENGTH);
         if (use_dict) s_dict = resolve(S_DICTIONARY_DATA);
         if (k == T_DECIMAL || k == T_TIMESTAMP || k == T_TIMESTAMP_INSTANT) s_secondary = resolve(S_SECONDARY);
-        const bool has_present = s_present.present;
+        const bool own_present = s_present.present;
+        const bool has_present = own_present || has_parent;  // the column has a validity bitmap of its own slots
         cp.has_present = has_present;
+        cp.kids = oc.child_ids;
 
         // ---- row-index entries -> per-stream entry points
         // stream order inside a RowIndexEntry.positions list follows the writers' (Java/C++) recording order
@@ -338,7 +358,7 @@ void Job::plan_stripe(uint32_t task_idx) {
             int extra;
         };
         std::vector<PosSpec> specs;
-        if (has_present) specs.push_back({&s_present, 2});
+        if (own_present) specs.push_back({&s_present, 2});
         switch (k) {
             case T_BOOLEAN: specs.push_back({&s_data, 2}); break;
             case T_BYTE: specs.push_back({&s_data, 1}); break;
@@ -351,13 +371,15 @@ void Job::plan_stripe(uint32_t task_idx) {
             case T_DECIMAL: specs.push_back({&s_data, 0}); specs.push_back({&s_secondary, 1}); break;
             case T_TIMESTAMP: case T_TIMESTAMP_INSTANT:
                 specs.push_back({&s_data, 1}); specs.push_back({&s_secondary, 1}); break;
+            case T_LIST: case T_MAP: specs.push_back({&s_length, 1}); break;
+            case T_UNION: specs.push_back({&s_data, 1}); break;
             default: break;
         }
         uint32_t n_groups = 1;
         uint32_t gstride = n_rows;
         std::vector<std::vector<Entry>> entries(specs.size());  // [spec][group]
         bool indexed = false;
-        if (want_index && idx_groups > 1) {
+        if (want_index && idx_groups > 1 && !rs && oc.child_ids.empty()) {
             std::vector<std::vector<uint64_t>> ri = fm.read_row_index(si, sf, cid);
             size_t expect = 0;
             for (auto& sp : specs) expect += (compressed ? 2 : 1) + sp.extra;
@@ -454,36 +476,81 @@ void Job::plan_stripe(uint32_t task_idx) {
         if (has_present) {
             cnt_base = n_cnt_;
             n_cnt_ += n_groups + 1;
-            const uint32_t slot = (gstride + 7) / 8 + 8;
-            const uint64_t raw = alloc(AR_TMP, (uint64_t)slot * n_groups + 16);
-            valid_raw = alloc(AR_ZERO, ((uint64_t)n_rows + 31) / 32 * 4 + 16);
-            const std::vector<Entry>& pe = spec_of(&s_present);
-            for (uint32_t g = 0; g < n_groups; g++) {
-                const uint32_t rows = rows_in_group(g);
-                Seg sg{};
-                sg.in = s_present.ptr;
-                sg.in_len = s_present.len;
-                sg.out = raw;
-                sg.start_byte = pe[g].byte;
-                sg.run_skip = pe[g].skip;
-                sg.n_values = rows;
-                sg.cnt_idx = -1;
-                sg.start_idx = -1;
-                sg.out_start = g * slot;
-                sg.colstripe = cs;
-                sg.out_kind = OUT_I8;
-                sg.aux = 1u | (pe[g].bit << 1);
-                                present_byte_segs_.push_back(sg);
-                BitSeg b{};
-                b.src = raw + (uint64_t)g * slot;
-                b.dst = valid_raw;
-                b.bit_skip = pe[g].bit;
-                b.n_bits = rows;
-                b.cnt_idx = -1;
-                b.start_idx = -1;
-                b.dst_bit0 = g * gstride;
-                b.popc_out = (int32_t)(cnt_base + g);
-                present_bit_segs_.push_back(b);
+            if (!has_parent) {
+                const uint32_t slot = (gstride + 7) / 8 + 8;
+                const uint64_t raw = alloc(AR_TMP, (uint64_t)slot * n_groups + 16);
+                valid_raw = alloc(AR_ZERO, ((uint64_t)n_rows + 31) / 32 * 4 + 16);
+                const std::vector<Entry>& pe = spec_of(&s_present);
+                for (uint32_t g = 0; g < n_groups; g++) {
+                    const uint32_t rows = rows_in_group(g);
+                    Seg sg{};
+                    sg.in = s_present.ptr;
+                    sg.in_len = s_present.len;
+                    sg.out = raw;
+                    sg.start_byte = pe[g].byte;
+                    sg.run_skip = pe[g].skip;
+                    sg.n_values = rows;
+                    sg.cnt_idx = -1;
+                    sg.start_idx = -1;
+                    sg.out_start = g * slot;
+                    sg.colstripe = cs;
+                    sg.out_kind = OUT_I8;
+                    sg.aux = 1u | (pe[g].bit << 1);
+                    present_byte_segs_.push_back(sg);
+                    BitSeg b{};
+                    b.src = raw + (uint64_t)g * slot;
+                    b.dst = valid_raw;
+                    b.bit_skip = pe[g].bit;
+                    b.n_bits = rows;
+                    b.cnt_idx = -1;
+                    b.start_idx = -1;
+                    b.dst_bit0 = g * gstride;
+                    b.popc_out = (int32_t)(cnt_base + g);
+                    present_bit_segs_.push_back(b);
+                }
+            } else {
+                // Validity handed down by the parent (struct and union children; one group).  The column's own PRESENT
+                // stream has one entry per valid slot of the parent and is scattered into those slots
+                // (merge_parent_present, array_decoder/mod.rs:216-229); without one the parent's bitmap is the column's.
+                const uint64_t parent_bits = aref(AR_ABS, rs->parent_bits);
+                if (own_present) {
+                    if (rs->parent_count > n_rows) fail(ORCB_UNEXPECTED, "parent validity count exceeds the slots");
+                    const uint32_t pc = (uint32_t)rs->parent_count;
+                    const uint64_t raw = alloc(AR_TMP, (uint64_t)pc / 8 + 32);
+                    const uint64_t own_bits = alloc(AR_ZERO, ((uint64_t)pc + 31) / 32 * 4 + 16);
+                    Seg sg{};
+                    sg.in = s_present.ptr;
+                    sg.in_len = s_present.len;
+                    sg.out = raw;
+                    sg.n_values = pc;
+                    sg.cnt_idx = -1;
+                    sg.start_idx = -1;
+                    sg.colstripe = cs;
+                    sg.out_kind = OUT_I8;
+                    sg.aux = 1u;
+                    present_byte_segs_.push_back(sg);
+                    BitSeg b{};
+                    b.src = raw;
+                    b.dst = own_bits;
+                    b.n_bits = pc;
+                    b.cnt_idx = -1;
+                    b.start_idx = -1;
+                    b.popc_out = -1;
+                    present_bit_segs_.push_back(b);
+                    valid_raw = alloc(AR_ZERO, ((uint64_t)n_rows + 31) / 32 * 4 + 16);
+                    SpacedDesc d{};
+                    d.src = own_bits;
+                    d.dst = valid_raw;
+                    d.valid = parent_bits;
+                    d.n_rows = n_rows;
+                    d.start_idx = (int32_t)n_cnt_++;  // a slot nothing writes: its dense start stays 0
+                    d.width = 0;
+                    merge_spaced_.push_back(d);
+                    ab_present_ += s_present.len;
+                } else {
+                    valid_raw = parent_bits;
+                }
+                popcs_.push_back({valid_raw, n_rows, cnt_base});
             }
             scans_.push_back({cnt_base, n_groups});
             cp.validity_stride = (uint32_t)align_up((bs + 7) / 8, 64);
@@ -502,8 +569,9 @@ void Job::plan_stripe(uint32_t task_idx) {
             repack_work_ += n_batches;
             repacks_.push_back(rp);
             n_segments_ += n_groups;
-            ab_present_ += s_present.len + (uint64_t)n_rows / 8;
+            ab_present_ += (has_parent ? 0 : s_present.len) + (uint64_t)n_rows / 8;
             ab_repack_ += (uint64_t)n_rows / 4;
+            cp.valid_bits = valid_raw;
         }
         const int32_t total_idx = has_present ? (int32_t)(cnt_base + n_groups) : -1;
 
@@ -902,6 +970,80 @@ void Job::plan_stripe(uint32_t task_idx) {
                 ts_.push_back(td);
                 ab_ts_ += (uint64_t)n_rows * (16 + tw);
                 if (has_present) add_spaced(dst, cp.values, tw, true);
+                break;
+            }
+            case T_STRUCT:
+                // struct_decoder.rs:59-78: nothing of its own but the validity; the children decode under it (next level)
+                break;
+            case T_LIST: case T_MAP: {
+                // list.rs:63-87 / map.rs:74-104: LENGTH -> element offsets, exactly the offsets of a direct string column
+                // without bytes behind them; their total is the slot count of the children (next level)
+                StrCol sc{};
+                sc.n_rows = n_rows;
+                sc.batch_size = bs;
+                sc.n_batches = n_batches;
+                sc.tiles_per_batch = std::max<uint32_t>(1, (std::min(bs, n_rows) + STR_TILE - 1) / STR_TILE);
+                sc.n_tiles = sc.tiles_per_batch * n_batches;
+                sc.colstripe = cs;
+                sc.tile0 = str_tiles_;
+                str_tiles_ += sc.n_tiles;
+                sc.meta_slot = (uint32_t)strcols_.size();
+                cp.str_slot = (int32_t)strcols_.size();
+                cp.is_list = true;
+                cp.offsets = alloc(AR_OUT, (uint64_t)n_batches * (bs + 1) * 4);
+                sc.offsets = cp.offsets;
+                sc.tile_base = alloc(AR_TMP, ((uint64_t)sc.n_tiles + 1) * 8);
+                cp.batch_base_off = meta_bytes_;
+                meta_bytes_ += ((uint64_t)n_batches + 1) * 8;
+                sc.batch_base = cp.batch_base_off;
+                const uint64_t rows_i32 = alloc(AR_TMP, (uint64_t)n_rows * 4 + 16);
+                const uint64_t dense_i32 = has_present ? alloc(AR_TMP, (uint64_t)n_rows * 4 + 16) : rows_i32;
+                sc.lens = rows_i32;
+                sc.mode = 0;
+                sc.data = 0;
+                sc.data_len = 0xffffffffu;
+                add_int_segs(s_length, dense_i32, false, 8, OUT_LEN31, ORCB_OFFSET_OVERFLOW, true);
+                if (has_present) add_spaced(dense_i32, rows_i32, 4, false);
+                ab_str_ += (uint64_t)n_rows * 12;
+                strcols_.push_back(sc);
+                break;
+            }
+            case T_UNION: {
+                // union.rs:69-136: tags are a byte-RLE stream over the valid slots (null slots 0) = the type ids of a sparse
+                // union; each child decodes every slot under the validity `tag == child` (next level)
+                cp.values = alloc(AR_OUT, (uint64_t)n_rows);
+                uint64_t dst = cp.values;
+                if (has_present) dst = alloc(AR_TMP, (uint64_t)n_rows);
+                Seg sg{};
+                sg.in = s_data.ptr;
+                sg.in_len = s_data.len;
+                sg.out = dst;
+                sg.colstripe = cs;
+                sg.out_kind = OUT_I8;
+                if (has_present) {
+                    sg.cnt_idx = (int32_t)cnt_base;
+                    sg.start_idx = (int32_t)cnt_base;
+                } else {
+                    sg.cnt_idx = -1;
+                    sg.start_idx = -1;
+                    sg.n_values = n_rows;
+                }
+                data_byte_segs_.push_back(sg);
+                n_segments_ += 1;
+                if (has_present) add_spaced(dst, cp.values, 1, false);
+                UnionDesc ud{};
+                ud.tags = cp.values;
+                ud.valid = has_present ? valid_raw : 0;
+                ud.n = n_rows;
+                ud.n_children = (uint32_t)oc.child_ids.size();
+                ud.stride = (uint32_t)align_up(((uint64_t)n_rows + 31) / 32 * 4 + 16, 16);
+                ud.bits = alloc(AR_ZERO, (uint64_t)ud.stride * ud.n_children);
+                ud.counts = n_nulls_;
+                n_nulls_ += ud.n_children;
+                cp.union_bits = ud.bits;
+                cp.union_stride = ud.stride;
+                cp.union_counts = ud.counts;
+                unions_.push_back(ud);
                 break;
             }
             default: fail(ORCB_NOT_IMPLEMENTED, "unsupported column type on the device path");

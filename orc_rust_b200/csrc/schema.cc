@@ -30,59 +30,96 @@ ReadOptions ReadOptions::from_c(const OrcbReadOptions* o) {
 // ------------------------------------------------------------------------------------------------
 // schema (src/schema.rs:503-577, src/arrow_reader.rs:182-198)
 // ------------------------------------------------------------------------------------------------
+// One column of the type tree as the decoder sees it (any depth; `hint`: with_schema's timestamp variant, -1 = none)
+OutColumn column_info(const FileMeta& fm, uint32_t col_id, const std::string& name, const ReadOptions& opt, int hint) {
+    static const char* ts_fmt[4] = {"tsn:", "tsu:", "tsm:", "tss:"};
+    if (col_id >= fm.types.size()) fail(ORCB_UNEXPECTED, "Column index out of bounds");
+    const OrcType& t = fm.types[col_id];
+    OutColumn c;
+    c.name = name;
+    c.col_id = col_id;
+    c.kind = t.kind;
+    switch (t.kind) {
+        case T_BOOLEAN: c.format = "b"; c.width = 0; break;
+        case T_BYTE: c.format = "c"; c.width = 1; break;
+        case T_SHORT: c.format = "s"; c.width = 2; break;
+        case T_INT: c.format = "i"; c.width = 4; break;
+        case T_LONG: c.format = "l"; c.width = 8; break;
+        case T_FLOAT: c.format = "f"; c.width = 4; break;
+        case T_DOUBLE: c.format = "g"; c.width = 8; break;
+        case T_STRING: case T_VARCHAR: case T_CHAR: c.format = "u"; break;
+        case T_BINARY: c.format = "z"; break;
+        case T_DATE: c.format = "tdD"; c.width = 4; break;
+        case T_DECIMAL:
+            c.precision = t.precision;
+            c.scale = t.scale;
+            // arrow validates Decimal128 precision/scale (array_decoder/decimal.rs:99)
+            if (t.precision == 0 || t.precision > 38 || t.scale > t.precision)
+                fail(ORCB_ARROW, "invalid Decimal128 precision/scale for column " + c.name);
+            c.format = "d:" + std::to_string(t.precision) + "," + std::to_string(t.scale);
+            c.width = 16;
+            break;
+        case T_TIMESTAMP: case T_TIMESTAMP_INSTANT: {
+            c.ts_unit = hint >= 0 && hint <= 3 ? hint : opt.timestamp_unit;
+            c.ts_decimal = hint == 4;
+            if (c.ts_decimal) {
+                c.format = "d:38,9";
+                c.width = 16;
+                c.ts_unit = 0;
+            } else {
+                c.format = std::string(ts_fmt[c.ts_unit]) + (t.kind == T_TIMESTAMP_INSTANT ? "UTC" : "");
+                c.width = 8;
+            }
+            break;
+        }
+        // nested types (src/schema.rs:530-577); the children are columns of their own
+        case T_STRUCT:
+            if (t.subtypes.size() != t.field_names.size())
+                fail(ORCB_UNEXPECTED, "Struct type must have matching lengths for subtypes and field names lists");
+            c.format = "+s";
+            c.child_ids = t.subtypes;
+            break;
+        case T_LIST:
+            if (t.subtypes.size() != 1) fail(ORCB_UNEXPECTED, "List type must have exactly one subtype");
+            c.format = "+l";
+            c.child_ids = t.subtypes;
+            break;
+        case T_MAP:
+            if (t.subtypes.size() != 2) fail(ORCB_UNEXPECTED, "Map type must have exactly two subtypes");
+            c.format = "+m";
+            c.child_ids = t.subtypes;
+            break;
+        case T_UNION: {
+            if (t.subtypes.empty() || t.subtypes.size() > 127) fail(ORCB_UNEXPECTED, "Union type must have 1..127 variants");
+            c.format = "+us:";
+            for (size_t i = 0; i < t.subtypes.size(); i++) c.format += (i ? "," : "") + std::to_string(i);
+            c.child_ids = t.subtypes;
+            break;
+        }
+        default: fail(ORCB_UNEXPECTED, "unknown ORC type kind " + std::to_string(t.kind));
+    }
+    for (uint32_t ch : c.child_ids)
+        if (ch >= fm.types.size() || ch <= col_id) fail(ORCB_UNEXPECTED, "Column index out of bounds");
+    return c;
+}
+
 std::vector<OutColumn> project_columns(const FileMeta& fm, const ReadOptions& opt) {
     std::vector<OutColumn> out;
-    static const char* ts_fmt[4] = {"tsn:", "tsu:", "tsm:", "tss:"};
     if (opt.timestamp_unit < 0 || opt.timestamp_unit > 3) fail(ORCB_INVALID_ARGUMENT, "timestamp_unit must be 0..3");
     for (auto& rc : fm.root_columns) {
         if (!opt.project_all &&
             std::find(opt.projection.begin(), opt.projection.end(), rc.first) == opt.projection.end())
             continue;
-        const OrcType& t = fm.types[rc.second];
-        OutColumn c;
-        c.name = rc.first;
-        c.col_id = rc.second;
-        c.kind = t.kind;
-        switch (t.kind) {
-            case T_BOOLEAN: c.format = "b"; c.width = 0; break;
-            case T_BYTE: c.format = "c"; c.width = 1; break;
-            case T_SHORT: c.format = "s"; c.width = 2; break;
-            case T_INT: c.format = "i"; c.width = 4; break;
-            case T_LONG: c.format = "l"; c.width = 8; break;
-            case T_FLOAT: c.format = "f"; c.width = 4; break;
-            case T_DOUBLE: c.format = "g"; c.width = 8; break;
-            case T_STRING: case T_VARCHAR: case T_CHAR: c.format = "u"; break;
-            case T_BINARY: c.format = "z"; break;
-            case T_DATE: c.format = "tdD"; c.width = 4; break;
-            case T_DECIMAL:
-                c.precision = t.precision;
-                c.scale = t.scale;
-                // arrow validates Decimal128 precision/scale (array_decoder/decimal.rs:99)
-                if (t.precision == 0 || t.precision > 38 || t.scale > t.precision)
-                    fail(ORCB_ARROW, "invalid Decimal128 precision/scale for column " + c.name);
-                c.format = "d:" + std::to_string(t.precision) + "," + std::to_string(t.scale);
-                c.width = 16;
-                break;
-            case T_TIMESTAMP: case T_TIMESTAMP_INSTANT: {
-                const int hint = out.size() < opt.ts_hint.size() ? opt.ts_hint[out.size()] : -1;
-                c.ts_unit = hint >= 0 && hint <= 3 ? hint : opt.timestamp_unit;
-                c.ts_decimal = hint == 4;
-                if (c.ts_decimal) {
-                    c.format = "d:38,9";
-                    c.width = 16;
-                    c.ts_unit = 0;
-                } else {
-                    c.format = std::string(ts_fmt[c.ts_unit]) + (t.kind == T_TIMESTAMP_INSTANT ? "UTC" : "");
-                    c.width = 8;
-                }
-                break;
-            }
-            default:
-                fail(ORCB_NOT_IMPLEMENTED, "nested ORC types (struct/list/map/union) are not on the device path yet: column " + c.name);
-        }
-        out.push_back(std::move(c));
+        const int hint = out.size() < opt.ts_hint.size() ? opt.ts_hint[out.size()] : -1;
+        out.push_back(column_info(fm, rc.second, rc.first, opt, hint));
     }
     return out;
+}
+
+bool has_nested_columns(const std::vector<OutColumn>& cols) {
+    for (auto& c : cols)
+        if (!c.child_ids.empty()) return true;
+    return false;
 }
 
 void apply_schema_hints(const FileMeta& fm, ReadOptions& opt, const ArrowSchema* schema) {
@@ -152,7 +189,42 @@ void fill_schema(ArrowSchema* s, const std::string& fmt, const std::string& name
 }
 }  // namespace
 
-void export_schema(const FileMeta& fm, const std::vector<OutColumn>& cols, ArrowSchema* out) {
+static void export_column_schema(const FileMeta& fm, const OutColumn& c, const ReadOptions& opt, const std::string& name,
+                                 int64_t flags, ArrowSchema* out) {
+    fill_schema(out, c.format, name, flags);
+    if (c.child_ids.empty()) return;
+    auto* p = (SchemaPriv*)out->private_data;
+    const OrcType& t = fm.types[c.col_id];
+    const int64_t NULLABLE = 2;
+    auto child = [&](size_t i, uint32_t id, const std::string& nm, int64_t fl) {
+        export_column_schema(fm, column_info(fm, id, nm, opt, -1), opt, nm, fl, &p->child_store[i]);
+    };
+    if (c.kind == T_MAP) {
+        // Map(entries: Struct(keys non-null, values nullable), non-null), not sorted (src/schema.rs:548-557)
+        p->child_store.resize(1);
+        p->child_ptrs = {&p->child_store[0]};
+        fill_schema(&p->child_store[0], "+s", "entries", 0);
+        auto* ep = (SchemaPriv*)p->child_store[0].private_data;
+        ep->child_store.resize(2);
+        ep->child_ptrs = {&ep->child_store[0], &ep->child_store[1]};
+        export_column_schema(fm, column_info(fm, c.child_ids[0], "keys", opt, -1), opt, "keys", 0, &ep->child_store[0]);
+        export_column_schema(fm, column_info(fm, c.child_ids[1], "values", opt, -1), opt, "values", NULLABLE, &ep->child_store[1]);
+        p->child_store[0].n_children = 2;
+        p->child_store[0].children = ep->child_ptrs.data();
+    } else {
+        p->child_store.resize(c.child_ids.size());
+        p->child_ptrs.resize(c.child_ids.size());
+        for (size_t i = 0; i < c.child_ids.size(); i++) {
+            p->child_ptrs[i] = &p->child_store[i];
+            const std::string nm = c.kind == T_STRUCT ? t.field_names[i] : c.kind == T_LIST ? std::string("item") : "_union_" + std::to_string(i);
+            child(i, c.child_ids[i], nm, NULLABLE);
+        }
+    }
+    out->n_children = (int64_t)p->child_ptrs.size();
+    out->children = p->child_ptrs.data();
+}
+
+void export_schema(const FileMeta& fm, const std::vector<OutColumn>& cols, const ReadOptions& opt, ArrowSchema* out) {
     fill_schema(out, "+s", "", 0);
     auto* p = (SchemaPriv*)out->private_data;
     if (!fm.user_metadata.empty()) {
@@ -170,7 +242,7 @@ void export_schema(const FileMeta& fm, const std::vector<OutColumn>& cols, Arrow
     p->child_store.resize(cols.size());
     p->child_ptrs.resize(cols.size());
     for (size_t i = 0; i < cols.size(); i++) {
-        fill_schema(&p->child_store[i], cols[i].format, cols[i].name, 2 /* ARROW_FLAG_NULLABLE: src/schema.rs:131 */);
+        export_column_schema(fm, cols[i], opt, cols[i].name, 2 /* ARROW_FLAG_NULLABLE: src/schema.rs:131 */, &p->child_store[i]);
         p->child_ptrs[i] = &p->child_store[i];
     }
     out->n_children = (int64_t)cols.size();
