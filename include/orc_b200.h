@@ -101,6 +101,17 @@ int orcb_open_memory(const uint8_t* data, size_t len, OrcbFile** out);
 /* Reads the whole file into (pinned, if a device is present) host memory owned by the handle
  * (ChunkReader for File, src/reader/mod.rs:48-62). */
 int orcb_open_path(const char* path, OrcbFile** out);
+/* The file behind a read callback: ChunkReader (src/reader/mod.rs:27-46) as a C function.  `read_at` fills dst with
+ * `length` bytes from `offset` and returns 0, or a non-zero status that surfaces as ORCB_IO_ERROR; it may be called from
+ * any thread that uses the handle (readers built from one handle call it one at a time per reader).  Open reads the
+ * tail (the last 16 KiB, then the exact footer range if that was short: read_metadata, src/reader/metadata.rs:180-236);
+ * decoding reads each stripe with ONE call (index, data and footer together - the reference issues one get_bytes per
+ * stream, src/stripe.rs:161) straight into pinned memory the stripe is staged from; with_predicate reads only the index
+ * area and the footer of a stripe before deciding whether any of it is needed.  `ctx` must outlive the handle. */
+typedef int (*OrcbReadAt)(void* ctx, uint64_t offset, uint64_t length, uint8_t* dst);
+int orcb_open_callbacks(uint64_t len, OrcbReadAt read_at, void* ctx, OrcbFile** out);
+/* out[0] = read_at calls so far, out[1] = bytes they returned (0, 0 for files opened from memory or a path) */
+int orcb_file_io_stats(const OrcbFile* f, uint64_t out[2]);
 /* A second handle on the same bytes (they stay with `f`, which must outlive the clone).  A bulk job stages every
  * handle's stripes separately, so clones let one host copy of a file stand in for several files of a larger set. */
 int orcb_file_clone(const OrcbFile* f, OrcbFile** out);
@@ -224,6 +235,12 @@ uint64_t orcb_reader_total_row_count(const OrcbReader* r);
 /* Iterator::next (src/arrow_reader.rs:333-346): one RecordBatch as a struct ArrowArray in host memory.
  * *eos = 1 and `out` untouched at end of stream. */
 int orcb_reader_next(OrcbReader* r, struct ArrowArray* out, int* eos);
+/* ArrowStreamReader::poll_next (src/async_arrow_reader.rs:283-290, 252-277) as a completion callback: starts producing
+ * the next batch on a thread of the library and returns at once; `done(ctx, status, eos, error)` is called from that
+ * thread when `out` is filled (status 0, eos 0), the stream has ended (eos 1) or failed (status != 0; the reader stays in
+ * the error state, StreamState::Error).  One request per reader at a time; `out` and `ctx` must stay valid until `done`. */
+typedef void (*OrcbBatchCallback)(void* ctx, int status, int eos, const char* error);
+int orcb_reader_next_async(OrcbReader* r, struct ArrowArray* out, OrcbBatchCallback done, void* ctx);
 /* Same, batch buffers stay in HBM (device_type = ARROW_DEVICE_CUDA).  Requires device_resident = 1. */
 int orcb_reader_next_device(OrcbReader* r, struct ArrowDeviceArray* out, int* eos);
 

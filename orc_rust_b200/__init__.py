@@ -14,7 +14,7 @@ from typing import Iterator, List, Optional, Sequence
 
 from . import build as _build
 
-__all__ = ["ArrowReaderBuilder", "ArrowReader", "DecodeJob", "OrcError", "lib", "device_available",
+__all__ = ["ArrowReaderBuilder", "ArrowReader", "DecodeJob", "ChunkReader", "FileChunkReader", "OrcError", "lib", "device_available",
            "TimestampPrecision", "decode_int_rle", "decode_byte_rle", "decode_bool_rle", "decode_varint128",
            "decompress_stream"]
 
@@ -100,13 +100,15 @@ class _ArrowDeviceArray(ctypes.Structure):
 
 
 _lib = None
+BATCH_DONE = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_char_p)
+READ_AT = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint8))
 
 EXPORTED_SYMBOLS = [
-    "orcb_open_memory", "orcb_open_path", "orcb_file_clone", "orcb_file_free", "orcb_file_num_rows", "orcb_file_num_stripes",
+    "orcb_open_memory", "orcb_open_path", "orcb_open_callbacks", "orcb_file_io_stats", "orcb_file_clone", "orcb_file_free", "orcb_file_num_rows", "orcb_file_num_stripes",
     "orcb_file_compression", "orcb_file_compression_block_size", "orcb_file_row_index_stride",
     "orcb_file_num_root_columns", "orcb_file_root_column_name", "orcb_file_stripe_info", "orcb_schema",
     "orcb_reader_new", "orcb_reader_new_with_selection", "orcb_reader_new_ex", "orcb_reader_build", "orcb_reader_plan", "orcb_predicate_row_groups", "orcb_bloom_hash_long", "orcb_bloom_hash_bytes", "orcb_reader_counters", "orcb_selection_plan", "orcb_reader_free", "orcb_reader_total_row_count", "orcb_reader_next",
-    "orcb_reader_next_device", "orcb_reader_drain", "orcb_job_new", "orcb_job_free", "orcb_job_plan", "orcb_job_stage",
+    "orcb_reader_next_device", "orcb_reader_next_async", "orcb_reader_drain", "orcb_job_new", "orcb_job_free", "orcb_job_plan", "orcb_job_stage",
     "orcb_job_launch", "orcb_job_finish", "orcb_job_stats", "orcb_job_restage", "orcb_job_kernel_stats", "orcb_job_num_batches", "orcb_job_export_batch",
     "orcb_job_export_batch_device", "orcb_decode_int_rle", "orcb_decode_byte_rle", "orcb_decode_bool_rle",
     "orcb_decode_varint128", "orcb_decompress_stream", "orcb_last_error", "orcb_build_info",
@@ -153,11 +155,14 @@ def lib() -> ctypes.CDLL:
         L.orcb_open_memory.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]
         L.orcb_open_path.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]
         L.orcb_file_clone.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]
+        L.orcb_open_callbacks.argtypes = [ctypes.c_uint64, READ_AT, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]
+        L.orcb_file_io_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]
         L.orcb_schema.argtypes = [ctypes.c_void_p, ctypes.POINTER(_ReadOptions), ctypes.c_void_p]
         L.orcb_reader_new.argtypes = [ctypes.c_void_p, ctypes.POINTER(_ReadOptions), ctypes.POINTER(ctypes.c_void_p)]
         L.orcb_reader_next.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]
         L.orcb_reader_next_device.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]
         L.orcb_reader_drain.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]
+        L.orcb_reader_next_async.argtypes = [ctypes.c_void_p, ctypes.c_void_p, BATCH_DONE, ctypes.c_void_p]
         L.orcb_job_new.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_uint32, ctypes.POINTER(_ReadOptions),
                                    ctypes.POINTER(ctypes.c_void_p)]
         L.orcb_job_kernel_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(KernelStat), ctypes.c_uint32,
@@ -187,13 +192,52 @@ def device_available() -> bool:
     return bool(lib().orcb_device_available())
 
 
+class ChunkReader:
+    """Mirror of the reference's `ChunkReader` trait (src/reader/mod.rs:27-46): subclass with `len()` and
+    `get_bytes(offset_from_start, length) -> bytes`.  `FileChunkReader` serves a local file."""
+
+    def len(self) -> int:
+        raise NotImplementedError
+
+    def get_bytes(self, offset_from_start: int, length: int) -> bytes:
+        raise NotImplementedError
+
+
+class FileChunkReader(ChunkReader):
+    def __init__(self, path):
+        self._f = open(path, "rb")
+        self._n = os.fstat(self._f.fileno()).st_size
+        self.calls = []
+
+    def len(self):
+        return self._n
+
+    def get_bytes(self, offset_from_start, length):
+        self.calls.append((offset_from_start, length))
+        return os.pread(self._f.fileno(), length, offset_from_start)
+
+
 class _File:
     """FileMetadata handle (src/reader/metadata.rs:63-178)."""
 
     def __init__(self, source):
         self._h = ctypes.c_void_p()
         self._keep = None
-        if isinstance(source, (str, os.PathLike)):
+        if isinstance(source, ChunkReader):
+            # ChunkReader (src/reader/mod.rs:27-46): len() + get_bytes(offset, length) behind a C callback
+            def read_at(ctx, offset, length, dst, _src=source):
+                try:
+                    b = _src.get_bytes(int(offset), int(length))
+                    if len(b) != length:
+                        return 2
+                    ctypes.memmove(dst, bytes(b), length)
+                    return 0
+                except Exception:
+                    return 1
+            cb = READ_AT(read_at)
+            self._keep = (cb, source)
+            _check(lib().orcb_open_callbacks(source.len(), cb, None, ctypes.byref(self._h)))
+        elif isinstance(source, (str, os.PathLike)):
             _check(lib().orcb_open_path(os.fspath(source).encode(), ctypes.byref(self._h)))
         else:
             data = bytes(source) if not isinstance(source, bytes) else source
@@ -205,6 +249,12 @@ class _File:
         if getattr(self, "_h", None) and self._h.value and _lib is not None:
             _lib.orcb_file_free(self._h)
             self._h = ctypes.c_void_p()
+
+    def io_stats(self) -> dict:
+        """read_at calls and bytes so far (files opened through a ChunkReader)."""
+        out = (ctypes.c_uint64 * 2)()
+        _check(lib().orcb_file_io_stats(self._h, out))
+        return {"reads": int(out[0]), "bytes": int(out[1])}
 
     def clone(self) -> "_File":
         """A second handle on the same host bytes (a bulk job stages each handle's stripes separately)."""
@@ -655,9 +705,10 @@ class ArrowReader:
 
 
 class ArrowStreamReader:
-    """Mirror of `ArrowStreamReader` (src/async_arrow_reader.rs:283-290): an async stream of RecordBatches.  Each
-    batch is produced by the blocking reader on a worker thread, so the event loop stays free while the GPU works;
-    after an error the stream stays in the error state, like `StreamState::Error` (:262-277)."""
+    """Mirror of `ArrowStreamReader` (src/async_arrow_reader.rs:283-290): an async stream of RecordBatches over
+    `orcb_reader_next_async`: the batch is produced on a thread of the library and the awaiting task is woken from its
+    completion callback, so the event loop stays free while the GPU works; after an error the stream stays in the
+    error state, like `StreamState::Error` (:262-277)."""
 
     def __init__(self, reader: "ArrowReader"):
         self._reader = reader
@@ -670,17 +721,23 @@ class ArrowStreamReader:
 
     async def __anext__(self):
         import asyncio
+        import pyarrow as pa
+        loop = asyncio.get_running_loop()
+        fut = loop.create_future()
+        arr = _ArrowArray()
 
-        def step():
-            try:
-                return next(self._reader)
-            except StopIteration:
-                return None
+        def done(ctx, status, eos, error):
+            msg = (error or b"").decode("utf-8", "replace")
+            loop.call_soon_threadsafe(fut.set_result, (status, eos, msg))
 
-        batch = await asyncio.to_thread(step)
-        if batch is None:
+        cb = BATCH_DONE(done)
+        _check(lib().orcb_reader_next_async(self._reader._h, ctypes.byref(arr), cb, None))
+        status, eos, msg = await fut
+        if status:
+            raise OrcError(status, msg)
+        if eos:
             raise StopAsyncIteration
-        return batch
+        return pa.RecordBatch._import_from_c(ctypes.addressof(arr), self._reader._schema)
 
 
 class DecodeJob:

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <fstream>
 #include <memory>
+#include <thread>
 
 #include "job.h"
 #include "job_internal.h"
@@ -71,6 +72,14 @@ struct OrcbReader {
     bool has_predicate = false, planned = true;
     Predicate predicate;
     std::vector<RowSelector> selectors;
+    // stripes (indices into `stripes`) of the group started last, of r->job and of r->ahead; `single`: one stripe per
+    // group from here on (a group failed: its good stripes are yielded first, the error surfaces at the bad one)
+    size_t grp_first = 0, grp_end = 0, job_first = 0, job_end = 0;
+    bool single = false;
+    std::thread worker;  // orcb_reader_next_async: at most one request in flight
+    ~OrcbReader() {
+        if (worker.joinable()) worker.join();
+    }
 };
 
 // finish() with the re-plan a LayoutRetry asks for (at most a few rounds: every round fixes the sizes of all chunks the
@@ -180,6 +189,31 @@ int orcb_open_path(const char* path, OrcbFile** out) {
             throw;
         }
         *out = f.release();
+    });
+}
+
+int orcb_open_callbacks(uint64_t len, OrcbReadAt read_at, void* ctx, OrcbFile** out) {
+    return guarded([&] {
+        if (!out || !read_at) fail(ORCB_INVALID_ARGUMENT, "NULL argument");
+        auto f = std::make_unique<OrcbFile>();
+        f->meta.len = (size_t)len;
+        f->meta.source = std::make_shared<RangeSource>();
+        f->meta.source->read_at = read_at;
+        f->meta.source->ctx = ctx;
+        parse_file_tail(f->meta);
+        *out = f.release();
+    });
+}
+
+int orcb_file_io_stats(const OrcbFile* f, uint64_t out[2]) {
+    return guarded([&] {
+        if (!f || !out) fail(ORCB_INVALID_ARGUMENT, "NULL argument");
+        out[0] = out[1] = 0;
+        if (f->meta.source) {
+            std::lock_guard<std::mutex> lock(f->meta.source->mu);
+            out[0] = f->meta.source->reads;
+            out[1] = f->meta.source->bytes_read;
+        }
     });
 }
 
@@ -412,7 +446,8 @@ int orcb_reader_plan(OrcbReader* r, int32_t* applies, size_t cap_stripes, size_t
 static std::unique_ptr<Job> reader_start_group(OrcbReader* r) {
     for (;;) {
         if (r->next_stripe >= r->stripes.size()) return nullptr;
-        const uint32_t group = r->opt.max_stripes_per_launch ? r->opt.max_stripes_per_launch : 16;
+        r->grp_first = r->grp_end = r->next_stripe;
+        const uint32_t group = r->single ? 1u : (r->opt.max_stripes_per_launch ? r->opt.max_stripes_per_launch : 16);
         std::vector<StripeTask> tasks;
         uint64_t bytes = 0;
         while (r->next_stripe < r->stripes.size() && tasks.size() < group) {
@@ -454,6 +489,7 @@ static std::unique_ptr<Job> reader_start_group(OrcbReader* r) {
             tasks.push_back(std::move(task));
             r->next_stripe++;
         }
+        r->grp_end = r->next_stripe;
         if (tasks.empty()) continue;  // only unselected stripes were left in this round
         const bool timing = getenv("ORCB_READER_TIMING") != nullptr;  // host phases to stderr (tools/reader_probe.py)
         auto now = [] { return std::chrono::steady_clock::now(); };
@@ -486,16 +522,38 @@ static std::unique_ptr<Job> reader_start_group(OrcbReader* r) {
 static bool reader_advance(OrcbReader* r) {
     ensure_planned(r);
     static const bool prefetch = !(getenv("ORCB_NO_PREFETCH") && getenv("ORCB_NO_PREFETCH")[0] == '1');
+    // A group of several stripes that fails (while it is planned, or on the device) is started again one stripe at a
+    // time: every batch of the stripes before the bad one is yielded first, as the reference does
+    // (src/arrow_reader.rs:296-316 decodes stripe by stripe).
+    auto retry_single = [&](size_t first, size_t end) {
+        if (r->single || end - first <= 1) return false;
+        r->single = true;
+        r->next_stripe = first;
+        r->job.reset();
+        r->ahead.reset();
+        r->ahead_error = nullptr;
+        return true;
+    };
     while (!r->job || r->next_batch >= r->job->num_batches()) {
         r->job.reset();
         if (r->ahead_error) {
             std::exception_ptr e = r->ahead_error;
             r->ahead_error = nullptr;
+            if (retry_single(r->grp_first, r->grp_end > r->grp_first ? r->grp_end : r->stripes.size())) continue;
             std::rethrow_exception(e);
         }
-        if (!r->ahead) r->ahead = reader_start_group(r);
+        if (!r->ahead) {
+            try {
+                r->ahead = reader_start_group(r);
+            } catch (const OrcException&) {
+                if (retry_single(r->grp_first, r->grp_end > r->grp_first ? r->grp_end : r->stripes.size())) continue;
+                throw;
+            }
+        }
         if (!r->ahead) return false;
         r->job = std::move(r->ahead);
+        r->job_first = r->grp_first;
+        r->job_end = r->grp_end;
         r->next_batch = 0;
         if (prefetch) {  // planned and launched on the host while the device still works on r->job
             try {
@@ -504,7 +562,12 @@ static bool reader_advance(OrcbReader* r) {
                 r->ahead_error = std::current_exception();
             }
         }
-        finish_job(r->job);
+        try {
+            finish_job(r->job);
+        } catch (const OrcException&) {
+            if (retry_single(r->job_first, r->job_end)) continue;
+            throw;
+        }
     }
     return true;
 }
@@ -524,6 +587,20 @@ int orcb_reader_next(OrcbReader* r, struct ArrowArray* out, int* eos) {
             r->failed = true;  // StreamState::Error analogue (src/async_arrow_reader.rs:262-277)
             throw;
         }
+    });
+}
+
+// poll_next of ArrowStreamReader (src/async_arrow_reader.rs:283-290) in callback form: the batch is produced on a
+// thread of the library, the caller's thread returns at once
+int orcb_reader_next_async(OrcbReader* r, struct ArrowArray* out, OrcbBatchCallback done, void* ctx) {
+    return guarded([&] {
+        if (!r || !out || !done) fail(ORCB_INVALID_ARGUMENT, "NULL argument");
+        if (r->worker.joinable()) r->worker.join();  // the request before this one has completed or is completing
+        r->worker = std::thread([r, out, done, ctx] {
+            int eos = 0;
+            const int rc = orcb_reader_next(r, out, &eos);
+            done(ctx, rc, eos, rc ? orcb_last_error() : "");
+        });
     });
 }
 

@@ -193,6 +193,7 @@ class Job {
         uint64_t dst_off, bytes;
     };
     std::vector<StageCopy> stage_copies_;
+    std::vector<std::shared_ptr<RangeBuf>> range_keep_;  // stripes read through callbacks, held while this job stages from them
 
     // device blobs
     uint8_t* d_desc_ = nullptr;

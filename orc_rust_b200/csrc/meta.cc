@@ -4,6 +4,7 @@
 #include <cstring>
 
 #include "pb.h"
+#include "job_internal.h"
 
 namespace orcb {
 
@@ -256,6 +257,76 @@ std::vector<uint8_t> host_decompress_section(int compression, uint64_t block_siz
 }
 
 // ---------------------------------------------------------------------------------------------
+// Files behind read callbacks
+// ---------------------------------------------------------------------------------------------
+RangeBuf::~RangeBuf() {
+    if (pinned_cap) pinned_put(p, pinned_cap);
+}
+
+std::shared_ptr<RangeBuf> FileMeta::load_range(uint64_t off, uint64_t n) const {
+    if (!source) return nullptr;
+    {
+        std::lock_guard<std::mutex> lock(source->mu);
+        auto& v = source->live;
+        for (size_t i = 0; i < v.size();) {
+            std::shared_ptr<RangeBuf> r = v[i].lock();
+            if (!r) {
+                v[i] = v.back();
+                v.pop_back();
+                continue;
+            }
+            if (r->off <= off && off + n <= r->off + r->len) return r;
+            i++;
+        }
+    }
+    if (off > len || n > len - off) fail(ORCB_IO_ERROR, "read beyond the end of the file");
+    auto r = std::make_shared<RangeBuf>();
+    r->off = off;
+    r->len = n;
+    int dev = 0;
+    if (n && cudaGetDeviceCount(&dev) == cudaSuccess && dev > 0) {
+        try {
+            r->p = (uint8_t*)pinned_get((size_t)n + 256, &r->pinned_cap);
+        } catch (const OrcException&) {
+            r->p = nullptr;
+            r->pinned_cap = 0;
+        }
+    } else {
+        cudaGetLastError();
+    }
+    if (!r->p) {
+        r->heap.resize((size_t)n + 256);
+        r->p = r->heap.data();
+    }
+    if (n) {
+        const int rc = source->read_at(source->ctx, off, n, r->p);
+        if (rc != 0) fail(ORCB_IO_ERROR, "read callback failed with status " + std::to_string(rc));
+    }
+    std::lock_guard<std::mutex> lock(source->mu);
+    source->reads++;
+    source->bytes_read += n;
+    source->live.push_back(r);
+    return r;
+}
+
+std::shared_ptr<RangeBuf> FileMeta::load_stripe(uint32_t stripe) const {
+    if (!source) return nullptr;
+    const StripeInfo& si = stripes.at(stripe);
+    return load_range(si.offset, si.index_length + si.data_length + si.footer_length);
+}
+
+const uint8_t* FileMeta::base_for(uint64_t off) const {
+    if (!source) return data;
+    if (tail && off >= tail->off && off <= tail->off + tail->len) return tail->p - tail->off;
+    std::lock_guard<std::mutex> lock(source->mu);
+    for (auto& w : source->live) {
+        std::shared_ptr<RangeBuf> r = w.lock();
+        if (r && r->off <= off && off <= r->off + r->len) return r->p - r->off;
+    }
+    fail(ORCB_UNEXPECTED, "file bytes at offset " + std::to_string(off) + " are not loaded");
+}
+
+// ---------------------------------------------------------------------------------------------
 // File tail (src/reader/metadata.rs:180-263)
 // ---------------------------------------------------------------------------------------------
 static OrcType parse_type(const uint8_t* p, size_t n) {
@@ -282,9 +353,30 @@ static OrcType parse_type(const uint8_t* p, size_t n) {
 }
 
 void parse_file_tail(FileMeta& fm) {
-    const uint8_t* d = fm.data;
     const size_t n = fm.len;
     if (n == 0) fail(ORCB_EMPTY_FILE, "Empty file");
+    if (fm.source) {
+        // read_metadata (src/reader/metadata.rs:180-236): the last 16 KiB first; once the postscript says how long
+        // footer and metadata are, the whole tail if that was not enough
+        fm.tail = fm.load_range(n - std::min<size_t>(n, 16384), std::min<size_t>(n, 16384));
+        const uint8_t* t = fm.tail->p - fm.tail->off;
+        const size_t ps_len = t[n - 1];
+        if (n - 1 >= ps_len && ps_len <= fm.tail->len - 1) {
+            uint64_t fl = 0, ml = 0;
+            PbCursor c(t + n - 1 - ps_len, ps_len);
+            PbField f;
+            while (c.next(f)) {
+                if (f.number == 1) fl = f.value;
+                else if (f.number == 5) ml = f.value;
+            }
+            const uint64_t room = n - 1 - ps_len;
+            if (fl <= room && ml <= room - fl && fl + ml + ps_len + 1 > fm.tail->len) {
+                const uint64_t need = fl + ml + ps_len + 1;
+                fm.tail = fm.load_range(n - need, need);
+            }
+        }
+    }
+    const uint8_t* d = fm.base_for(n - 1);
     size_t ps_len = d[n - 1];
     if (n - 1 < ps_len) fail(ORCB_OUT_OF_SPEC, "File too small for given postscript length");
     bool have_footer = false, have_meta = false;
@@ -369,7 +461,7 @@ void parse_file_tail(FileMeta& fm) {
 StripeFooter FileMeta::read_stripe_footer(uint32_t stripe) const {
     const StripeInfo& si = stripes.at(stripe);
     uint64_t off = si.offset + si.index_length + si.data_length;
-    std::vector<uint8_t> raw = host_decompress_section(compression, block_size, data + off, si.footer_length);
+    std::vector<uint8_t> raw = host_decompress_section(compression, block_size, base_for(off) + off, si.footer_length);
     StripeFooter sf;
     PbCursor c(raw.data(), raw.size());
     PbField f;
@@ -412,7 +504,7 @@ std::vector<std::vector<uint64_t>> FileMeta::read_row_index(const StripeInfo& si
     std::vector<std::vector<uint64_t>> out;
     const StreamInfo* st = sf.find(column, S_ROW_INDEX);
     if (!st || st->length == 0) return out;
-    std::vector<uint8_t> raw = host_decompress_section(compression, block_size, data + st->offset, st->length);
+    std::vector<uint8_t> raw = host_decompress_section(compression, block_size, base_for(st->offset) + st->offset, st->length);
     PbCursor c(raw.data(), raw.size());
     PbField f;
     while (c.next(f)) {
@@ -559,7 +651,7 @@ std::vector<RowGroupEntry> FileMeta::read_row_group_entries(const StripeFooter& 
     *present = st != nullptr;
     if (!st) return out;
     {
-        std::vector<uint8_t> raw = host_decompress_section(compression, block_size, data + st->offset, st->length);
+        std::vector<uint8_t> raw = host_decompress_section(compression, block_size, base_for(st->offset) + st->offset, st->length);
         PbCursor c(raw.data(), raw.size());
         PbField f, g;
         while (c.next(f)) {
@@ -580,7 +672,7 @@ std::vector<RowGroupEntry> FileMeta::read_row_group_entries(const StripeFooter& 
     const StreamInfo* bs = sf.find(column, S_BLOOM_FILTER);
     if (!bs) bs = sf.find(column, S_BLOOM_FILTER_UTF8);
     if (!bs) return out;
-    std::vector<uint8_t> raw = host_decompress_section(compression, block_size, data + bs->offset, bs->length);
+    std::vector<uint8_t> raw = host_decompress_section(compression, block_size, base_for(bs->offset) + bs->offset, bs->length);
     std::vector<BloomBits> filters;
     PbCursor c(raw.data(), raw.size());
     PbField f, g;
@@ -636,7 +728,7 @@ std::vector<RowGroupEntry> FileMeta::read_row_group_entries(const StripeFooter& 
 // src/compression.rs:244-275 — header walk only
 std::vector<ChunkInfo> FileMeta::chunk_table(uint64_t stream_off, uint64_t stream_len) const {
     std::vector<ChunkInfo> out;
-    const uint8_t* s = data + stream_off;
+    const uint8_t* s = base_for(stream_off) + stream_off;
     uint64_t p = 0;
     while (p < stream_len) {
         if (p + 3 > stream_len) fail(ORCB_OUT_OF_SPEC, "truncated compression chunk header");

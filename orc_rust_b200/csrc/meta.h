@@ -97,8 +97,36 @@ struct ChunkSizeCache {
     std::unordered_map<uint64_t, uint32_t> size;
 };
 
+// A byte range of a file opened through read callbacks (ChunkReader::get_bytes, src/reader/mod.rs:27-46): one read per
+// stripe (index + data + footer together, where the reference reads stream by stream, src/stripe.rs:161), or the file
+// tail.  Lives as long as someone holds it: the job that stages from it, the reader that plans with it.
+struct RangeBuf {
+    uint64_t off = 0, len = 0;
+    uint8_t* p = nullptr;
+    size_t pinned_cap = 0;            // > 0: from the pinned-buffer cache (asynchronous H2D copies)
+    std::vector<uint8_t> heap;        // without a device
+    ~RangeBuf();
+};
+typedef int (*OrcbReadAtFn)(void* ctx, uint64_t offset, uint64_t length, uint8_t* dst);
+struct RangeSource {
+    OrcbReadAtFn read_at = nullptr;
+    void* ctx = nullptr;
+    std::mutex mu;
+    std::vector<std::weak_ptr<RangeBuf>> live;
+    uint64_t reads = 0, bytes_read = 0;
+};
+
 struct FileMeta {
     std::shared_ptr<ChunkSizeCache> chunk_sizes = std::make_shared<ChunkSizeCache>();
+    // callback-backed files: `data` is null, bytes come through `source` (shared by the clones of a handle)
+    std::shared_ptr<RangeSource> source;
+    std::shared_ptr<RangeBuf> tail;   // footer + metadata + postscript
+    // Pointer q such that q[off] is the file's byte at offset `off`.  Memory files: `data`.  Callback files: the range
+    // that holds `off` must be alive (load_stripe / the tail), else Unexpected.
+    const uint8_t* base_for(uint64_t off) const;
+    // the stripe's bytes (index, data, footer) in one read; null for memory files
+    std::shared_ptr<RangeBuf> load_stripe(uint32_t stripe) const;
+    std::shared_ptr<RangeBuf> load_range(uint64_t off, uint64_t len) const;
     const uint8_t* data = nullptr;
     size_t len = 0;
     std::vector<uint8_t> owned;   // when opened from a path without pinned memory

@@ -225,6 +225,7 @@ void Job::plan_stripe(uint32_t task_idx) {
     const FileMeta& fm = *tasks_[task_idx].file;
     const uint32_t stripe = tasks_[task_idx].stripe;
     const StripeInfo& si = fm.stripes[stripe];
+    if (std::shared_ptr<RangeBuf> held = fm.load_stripe(stripe)) range_keep_.push_back(held);  // callback files: one read per stripe
     const StripeFooter sf = fm.read_stripe_footer(stripe);
     task_first_cs_.push_back((uint32_t)colstripes_.size());
     if (si.rows > 0xfffffff0ull) fail(ORCB_NOT_IMPLEMENTED, "stripes with more than 2^32 rows");
@@ -243,7 +244,7 @@ void Job::plan_stripe(uint32_t task_idx) {
             in_off = it->second;
         } else {
             in_off = alloc(AR_IN, si.data_length);
-            stage_copies_.push_back({fm.data + data_start, in_off & ((1ull << 60) - 1), si.data_length});
+            stage_copies_.push_back({fm.base_for(data_start) + data_start, in_off & ((1ull << 60) - 1), si.data_length});
             staged_stripes_[key] = in_off;
         }
     }
@@ -614,7 +615,7 @@ void Job::plan_stripe(uint32_t task_idx) {
                 // everything else to the lane-per-segment kernel.  Purely a scheduling hint.
                 bool long_runs = false;
                 if (v2 && sr.present) {
-                    const uint8_t* sp = fm.data + (sf.find(cid, &sr == &s_data ? S_DATA : (&sr == &s_length ? S_LENGTH : S_SECONDARY))->offset);
+                    const uint8_t* sp = fm.base_for(data_start) + (sf.find(cid, &sr == &s_data ? S_DATA : (&sr == &s_length ? S_LENGTH : S_SECONDARY))->offset);
                     if (!compressed) {
                         long_runs = rle2_opens_with_long_runs(sp, sr.len, sg.start_byte);
                     } else if (!sr.chunks.empty()) {

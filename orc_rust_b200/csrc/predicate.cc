@@ -298,7 +298,13 @@ std::vector<RowSelector> predicate_selection(const FileMeta& fm, uint32_t stripe
     const uint64_t rows_per_group = fm.row_index_stride >= 0 ? (uint64_t)fm.row_index_stride : 10000;  // src/stripe.rs:300
     std::vector<uint8_t> result;
     bool ok = true;
+    // callback files: the index area and the stripe footer, not the data in between (a pruned stripe is never read)
+    std::shared_ptr<RangeBuf> held_index, held_footer;
     try {
+        if (fm.source) {
+            held_index = fm.load_range(si.offset, si.index_length);
+            held_footer = fm.load_range(si.offset + si.index_length + si.data_length, si.footer_length);
+        }
         StripeIndex idx;
         const StripeFooter sf = fm.read_stripe_footer(stripe);
         for (auto& c : cols) {

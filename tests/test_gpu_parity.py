@@ -948,6 +948,84 @@ def test_recompressed_files(ob, tmp_path, kind, block):
         assert ob.DecodeJob([dst]).plan().stats()["n_segments"] == ob.DecodeJob([src]).plan().stats()["n_segments"]
 
 
+def test_error_after_good_stripes(ob, tmp_path):
+    """A damaged stripe in the middle of a file: every batch of the stripes before it is yielded, then the error - as the
+    reference, which decodes stripe by stripe (src/arrow_reader.rs:296-316), although the device decodes groups."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tools"))
+    import gen_orc
+    from oracle import orc_oracle as oo
+    p = str(tmp_path / "li.orc")
+    gen_orc.write(gen_orc.lineitem_table(40_000, 13), p, stripe_size=2 << 20)
+    data0 = open(p, "rb").read()
+    of0 = oo.OracleFile(data0)
+    assert len(of0.stripes) >= 4
+    s2 = of0.stripes[2]
+    rng = np.random.default_rng(99)
+    found = 0
+    for _ in range(200):
+        data = bytearray(data0)
+        for _ in range(8):
+            data[int(rng.integers(s2.offset + s2.index_length, s2.offset + s2.index_length + s2.data_length))] ^= 0xFF
+        data = bytes(data)
+        of = oo.OracleFile(data)
+        try:
+            of.read_stripe(2)
+            continue  # this damage still decodes
+        except oo.OracleError:
+            pass
+        good = of.read_stripe(0) + of.read_stripe(1)
+        got = []
+        with pytest.raises(ob.OrcError):
+            for b in ob.ArrowReaderBuilder.try_new(data).with_row_index(False).build():
+                got.append(b)
+        assert_batches_identical(got, good, "batches before the damaged stripe")
+        found += 1
+        if found >= 3:
+            break
+    assert found >= 1
+
+
+def test_chunk_reader_feed(ob, tmp_path):
+    """orcb_open_callbacks (ChunkReader::get_bytes, src/reader/mod.rs:27-46): the file is only ever seen through the read
+    callback - one read for the tail, one per stripe - and decodes to the same batches; with a predicate the stripes
+    that are pruned are never read beyond their index area and footer."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tools"))
+    import gen_orc
+    from oracle import orc_oracle as oo
+    p = str(tmp_path / "li.orc")
+    gen_orc.write(gen_orc.lineitem_table(60_000, 9), p, compression="snappy", stripe_size=1 << 20)
+    exp = oo.OracleFile(open(p, "rb").read()).read()
+    cr = ob.FileChunkReader(p)
+    b = ob.ArrowReaderBuilder.try_new(cr)
+    n_stripes = b.file_metadata().num_stripes
+    assert n_stripes >= 3
+    got = list(b.build())
+    assert_batches_identical(got, exp, "chunk reader")
+    infos = [b.file_metadata().stripe_info(i) for i in range(n_stripes)]
+    whole = {(s["offset"], s["index_length"] + s["data_length"] + s["footer_length"]) for s in infos}
+    assert len(cr.calls) == 1 + n_stripes and set(cr.calls[1:]) == whole, cr.calls
+    assert b.file_metadata().io_stats()["reads"] == 1 + n_stripes
+    # predicate that keeps nothing: index + footer of every stripe, no data
+    cr2 = ob.FileChunkReader(p)
+    pred = ob.Predicate.lt("l_orderkey", ob.PredicateValue("Int64", -5))
+    got2 = list(ob.ArrowReaderBuilder.try_new(cr2).with_predicate(pred).build())
+    assert sum(x.num_rows for x in got2) == 0
+    data_reads = [c for c in cr2.calls[1:] if c in whole]
+    # (a footer that lies inside the tail already read costs no call of its own)
+    assert not data_reads and len(cr2.calls) <= 1 + 2 * n_stripes and sum(c[1] for c in cr2.calls) < 100_000, cr2.calls
+    # a failing callback is an IoError, not a crash
+    class Broken(ob.FileChunkReader):
+        def get_bytes(self, off, n):
+            if off < 1000:
+                raise OSError("disk on fire")
+            return super().get_bytes(off, n)
+    with pytest.raises(ob.OrcError) as e:
+        list(ob.ArrowReaderBuilder.try_new(Broken(p)).build())
+    assert e.value.variant == "IoError"
+
+
 def test_device_resident_batches(ob, tmp_path):
     """with_device(resident=True): ArrowDeviceArray buffers in HBM, read back through torch and compared."""
     import ctypes
