@@ -552,12 +552,13 @@ __global__ void __launch_bounds__(128) k_rle_index(const Seg* __restrict__ segs,
                                                    const uint32_t* __restrict__ cnt, RunRec* __restrict__ table,
                                                    BlockRec* __restrict__ blocks, uint32_t* __restrict__ nblocks,
                                                    uint32_t pool_blocks, CoopRec* __restrict__ coop_q,
-                                                   uint32_t* __restrict__ ncoop, uint32_t coop_cap, uint32_t* err) {
-    // only IDX_LANES lanes of each warp own a segment: a warp advances at the pace of its slowest lane
+                                                   uint32_t* __restrict__ ncoop, uint32_t coop_cap, uint32_t* err,
+                                                   uint32_t idx_lanes) {
+    // only `idx_lanes` lanes of each warp own a segment: a warp advances at the pace of its slowest lane
     // (the one that misses L1 this step), so fewer streams per warp and more warps hide more latency
     const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
-    if ((gt & 31) >= IDX_LANES) return;
-    const uint32_t segi = (gt >> 5) * IDX_LANES + (gt & 31);
+    if ((gt & 31) >= idx_lanes) return;
+    const uint32_t segi = (gt >> 5) * idx_lanes + (gt & 31);
     if (segi >= nseg) return;
     const Seg& s = segs[segi];
     const uint32_t n = s.cnt_idx >= 0 ? cnt[s.cnt_idx] : s.n_values;
@@ -1058,8 +1059,16 @@ __global__ void __launch_bounds__(RLE_WARPS * 32) k_int_rle_coop(const Seg* __re
 int launch_rle_index(const Seg* segs, uint32_t n, const uint32_t* cnt, RunRec* table, BlockRec* blocks, uint32_t* nblocks,
                      uint32_t pool_blocks, CoopRec* coop_q, uint32_t* ncoop, uint32_t coop_cap, uint32_t* err, cudaStream_t st) {
     if (!n) return 0;
-    const uint32_t nwarps = (n + IDX_LANES - 1) / IDX_LANES;
-    k_rle_index<<<(nwarps + 3) / 4, 128, 0, st>>>(segs, n, cnt, table, blocks, nblocks, pool_blocks, coop_q, ncoop, coop_cap, err);
+    static uint32_t lanes = 0;
+    if (!lanes) {
+        lanes = IDX_LANES;
+        if (const char* e = getenv("ORCB_IDX_LANES")) {
+            const int v = atoi(e);
+            if (v >= 1 && v <= 32) lanes = (uint32_t)v;
+        }
+    }
+    const uint32_t nwarps = (n + lanes - 1) / lanes;
+    k_rle_index<<<(nwarps + 3) / 4, 128, 0, st>>>(segs, n, cnt, table, blocks, nblocks, pool_blocks, coop_q, ncoop, coop_cap, err, lanes);
     LAUNCH_CHECK();
     return 0;
 }
