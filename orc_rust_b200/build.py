@@ -29,6 +29,7 @@ def _stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
+    extra = os.environ.get("ORCB_NVCC_DEFS", "").split()  # e.g. "-DORCB_LZ_SB=32 -DORCB_LZ_CTAS=7" (experiments)
     objs = []
     build_dir = os.path.join(HERE, "build")
     os.makedirs(build_dir, exist_ok=True)
@@ -36,7 +37,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for src in SOURCES:
         obj = os.path.join(build_dir, src + ".o")
         objs.append(obj)
-        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = ["nvcc"] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
     for cmd, p in procs:
         out, _ = p.communicate()

@@ -105,7 +105,16 @@ __device__ __forceinline__ void chunk_done(const ChunkDesc& c, uint32_t fail, ui
 // element-by-element loop (one element, or - for damaged input - the rest of the chunk, so errors are reported
 // exactly as by the serial decoder).
 // ------------------------------------------------------------------------------------------------
-constexpr uint32_t LZ_SB = 64, LZ_TILE = 32 * LZ_SB, LZ_ROW_WORDS = 19, LZ_HIST = 4096, LZ_DESC_CAP = 1024;
+#ifndef ORCB_LZ_SB
+#define ORCB_LZ_SB 64   // sub-block bytes per lane: 64 (2 KiB tiles) or 32 (1 KiB tiles, less shared memory, more warps)
+#endif
+#ifndef ORCB_LZ_CTAS
+#define ORCB_LZ_CTAS 5  // resident CTAs per SM the register allocation aims for
+#endif
+constexpr uint32_t LZ_SB = ORCB_LZ_SB, LZ_SHIFT = LZ_SB == 64 ? 6 : 5, LZ_TILE = 32 * LZ_SB;
+// rows overlap by 12 bytes; 19 (or 11) words per row keep the 32 lanes' rows on different banks
+constexpr uint32_t LZ_ROW_WORDS = LZ_SB / 4 + 3, LZ_HIST = 4096, LZ_DESC_CAP = 16 * LZ_SB;
+static_assert(LZ_SB == 64 || LZ_SB == 32, "sub-blocks of 32 or 64 bytes");
 constexpr uint32_t LZ_INLINE = 32, LZ_MAX_ELEM = 64, LZ_MAX_MATCH = 1024;
 constexpr uint32_t LZ_INVALID = 0xffffffffu;
 constexpr uint32_t LZD_LIT = 1u << 14;  // descriptor: len [0:14) | literal [14] | src [16:32) (literal: tile position; match: distance)
@@ -127,14 +136,14 @@ struct LzElem {
 
 // 8 input bytes at tile position x (x < LZ_TILE + 4) out of the padded rows
 __device__ __forceinline__ uint64_t lz_window(const uint32_t* in, uint32_t x) {
-    const uint32_t row = min(x >> 6, 31u), col = x - (row << 6);  // col < 76 - 8
+    const uint32_t row = min(x >> LZ_SHIFT, 31u), col = x - (row << LZ_SHIFT);  // col < row bytes - 8
     const uint32_t* r = in + row * LZ_ROW_WORDS + (col >> 2);
     const uint32_t sh = (col & 3) * 8;
     const uint32_t w0 = r[0], w1 = r[1], w2 = r[2];
     return ((uint64_t)__funnelshift_r(w1, w2, sh) << 32) | __funnelshift_r(w0, w1, sh);
 }
 __device__ __forceinline__ uint32_t lz_byte(const uint32_t* in, uint32_t x) {
-    const uint32_t row = min(x >> 6, 31u), col = x - (row << 6);
+    const uint32_t row = min(x >> LZ_SHIFT, 31u), col = x - (row << LZ_SHIFT);
     return (in[row * LZ_ROW_WORDS + (col >> 2)] >> ((col & 3) * 8)) & 0xffu;
 }
 // 8 input bytes at absolute position q: from the staged tile when they lie in it, else from global memory
@@ -372,7 +381,7 @@ __device__ __forceinline__ uint32_t lz_tile(const uint8_t* __restrict__ s, uint3
         for (uint32_t it = 0; it < LZ_ROW_WORDS; it++) {
             const uint32_t k = it * 32 + (uint32_t)lane;
             const uint32_t row = k / LZ_ROW_WORDS, j = k - row * LZ_ROW_WORDS;
-            const uint32_t wi = row * 16 + j;
+            const uint32_t wi = row * (LZ_SB / 4) + j;
             // nothing is read more than a few bytes behind the chunk (the arenas are padded, but not by a tile)
             sm.in[k] = tb + 4u * wi < n + 8u ? __funnelshift_r(__ldg(g + wi), __ldg(g + wi + 1), sh) : 0u;
         }
@@ -531,7 +540,7 @@ __device__ __forceinline__ uint32_t lz_tile(const uint8_t* __restrict__ s, uint3
                         for (int j = 0; j < 9; j++) {
                             if (4u * j >= maxlen + 3u) break;
                             const uint32_t x = (src & ~3u) + 4u * j;
-                            const uint32_t rr = min(x >> 6, 31u), cc = x - (rr << 6);
+                            const uint32_t rr = min(x >> LZ_SHIFT, 31u), cc = x - (rr << LZ_SHIFT);
                             w[j] = 4u * j < len + (src & 3) ? sm.in[rr * LZ_ROW_WORDS + (cc >> 2)] : 0u;
                         }
                     } else {
@@ -938,7 +947,7 @@ __device__ uint32_t inflate_chunk(const uint8_t* __restrict__ s, uint32_t n, uin
 }
 
 // Persistent warps over the chunk list (most expensive chunks first, see plan.cc); one chunk per warp at a time.
-__global__ void __launch_bounds__(128, 5) k_decompress(const ChunkDesc* __restrict__ chunks, uint32_t nchunks, uint32_t* err,
+__global__ void __launch_bounds__(128, ORCB_LZ_CTAS) k_decompress(const ChunkDesc* __restrict__ chunks, uint32_t nchunks, uint32_t* err,
                                                        uint32_t* out_lens, uint32_t* counter, uint32_t* retry) {
     __shared__ LzWarp warp_sm[4];
     __shared__ uint32_t lut[256];
