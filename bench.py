@@ -626,16 +626,27 @@ def main():
     top = max((k for k in kstats if k["alg_bytes"]), key=lambda k: k["ms"]) if kstats else None
     roofline = None
     if top:
-        ach = top["alg_bytes"] / (top["ms"] / 1e3) / 1e9
+        # Waves and launch groups overlap, so the event pair around a kernel also spans whatever ran beside it and the
+        # pairs of one step add up to several times the step.  The kernel is charged its SHARE of the step:
+        # step time x (its event time / sum of all kernels' event times) - the quantity the ncu launch list
+        # (profiles/r02_launches_sf10_summary.txt, serialised) reports as well.
+        ev_sum = sum(k["ms"] for k in kstats)
+        share = top["ms"] / ev_sum
+        attributed_ms = dev_ms * share
+        ach = top["alg_bytes"] / (attributed_ms / 1e3) / 1e9
         traffic = None
-        try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch group, from the committed ncu capture
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum of one SF10 launch, from the committed ncu launch list
             with open(os.path.join(ROOT, "profiles", "r02_traffic_sf10.json")) as f:
                 traffic = json.load(f).get(top["name"])
         except Exception:
             pass
+        groups_per_gpu = max(1, len(groups))
         roofline = {"bound": "hbm", "kernel": top["name"], "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
-                    "kernel_ms": top["ms"], "kernel_alg_bytes": top["alg_bytes"],
+                    "frac": ach / peak, "traffic": traffic, "traffic_unit": "bytes per SF10 launch group (ncu)",
+                    "peak_source": peak_src,
+                    "kernel_share_of_step": share, "kernel_ms": attributed_ms, "kernel_alg_bytes": top["alg_bytes"],
+                    "kernel_alg_bytes_per_launch_group": top["alg_bytes"] / groups_per_gpu,
+                    "kernel_event_ms_raw": top["ms"], "frac_raw_events": top["alg_bytes"] / (top["ms"] / 1e3) / 1e9 / peak,
                     "step_achieved": (in_bytes + out_bytes) / world / (dev_ms / 1e3) / 1e9,
                     "step_frac": (in_bytes + out_bytes) / world / (dev_ms / 1e3) / 1e9 / peak,
                     "aliased_output_bytes": aliased,
@@ -648,8 +659,9 @@ def main():
                 roofline["frac_alone"] = top["alg_bytes"] / (ks[top["name"]]["ms"] / 1e3) / 1e9 / peak
             roofline["kernels_alone"] = [{"name": k["name"], "ms": round(k["ms"], 4),
                                           "gbs": round(k["alg_bytes"] / max(k["ms"], 1e-9) / 1e6, 1)} for k in kserial]
-            roofline["note"] = ("rank 0, summed over its launch groups.  frac / kernels: event pairs inside the timed step, where "
-                                "waves and groups overlap (a kernel's time includes what runs beside it); frac_alone / kernels_alone: "
+            roofline["note"] = ("rank 0, summed over its launch groups.  kernels: CUDA event pairs inside the timed step, where waves and "
+                                "groups overlap (a pair also spans what runs beside the kernel: frac_raw_events); frac: the dominant "
+                                "kernel charged its share of the step (kernel_share_of_step x ms_per_step); frac_alone / kernels_alone: "
                                 "one extra pass with one kernel at a time; step_frac: (stored stream bytes + Arrow bytes) per GPU / "
                                 "step time / peak; aliased_output_bytes are Arrow bytes no kernel writes (direct-string values "
                                 "alias the staged stream)")
