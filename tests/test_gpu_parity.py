@@ -282,6 +282,146 @@ def test_rle_v2_random_streams_vs_oracle(ob, nbytes, signed):
     assert agree_ok > 20 and agree_err > 20
 
 
+def _rand_rle1_stream(rng, n_runs, nbytes, signed):
+    """RLE v1 (integer/rle_v1.rs:54-132): runs (header 0..127 = length - 3, delta byte, base varint) and literal
+    groups (header -1..-128, that many varints), with bases that stay inside N or - sometimes - run out of it."""
+    out = bytearray()
+
+    def varint(v):
+        v &= (1 << 64) - 1
+        while v >= 0x80:
+            out.append((v & 0x7F) | 0x80)
+            v >>= 7
+        out.append(v)
+
+    lim = 1 << (8 * nbytes - 1)
+    for _ in range(n_runs):
+        big = rng.random() < 0.15
+        def val():
+            x = int(rng.integers(-lim, lim)) if big else int(rng.integers(-1000, 1000))
+            if not signed:
+                x = abs(x)
+            return ((x << 1) ^ (x >> 63)) if signed else x
+        if rng.random() < 0.5:
+            out.append(int(rng.integers(0, 128)))
+            out.append(int(rng.integers(0, 256)))
+            varint(val())
+        else:
+            k = int(rng.integers(1, 129))
+            out.append(256 - k)
+            for _ in range(k):
+                varint(val())
+    return bytes(out)
+
+
+@pytest.mark.parametrize("nbytes", [2, 4, 8])
+@pytest.mark.parametrize("signed", [False, True])
+def test_rle_v1_random_streams_vs_oracle(ob, nbytes, signed):
+    from oracle import orc_oracle as oo
+    rng = np.random.default_rng(4321 + nbytes + int(signed))
+    agree_ok = agree_err = 0
+    for it in range(60):
+        data = _rand_rle1_stream(rng, int(rng.integers(1, 12)), nbytes, signed)
+        n_ok = 0
+        for n_try in (1500, 500, 150, 50, 15, 5, 1):
+            try:
+                oo.rle_v1(data, n_try, signed, nbytes)
+                n_ok = n_try
+                break
+            except oo.OracleError:
+                continue
+        for n_req in ([n_ok] if n_ok else []) + [n_ok + 3000]:
+            try:
+                exp = oo.rle_v1(data, n_req, signed, nbytes)
+                exp_err = None
+            except oo.OracleError as e:
+                exp, exp_err = None, e
+            try:
+                got = ob.decode_int_rle(data, n_req, version=1, signed=signed, nbytes=nbytes)
+                got_err = None
+            except ob.OrcError as e:
+                got, got_err = None, e
+            assert (exp_err is None) == (got_err is None), \
+                f"iter {it} n={n_req}: oracle {exp_err} vs cuda {got_err} ({data.hex()})"
+            if exp_err is None:
+                assert np.array_equal(exp, got), f"iter {it} n={n_req}: values differ ({data.hex()})"
+                agree_ok += 1
+            else:
+                agree_err += 1
+    assert agree_ok > 20 and agree_err > 20
+
+
+FEATHERS = sorted(glob.glob(os.path.join(GOLDEN, "ref_expected_arrow", "*.feather")))
+
+
+@pytest.mark.parametrize("fpath", FEATHERS, ids=[os.path.basename(f) for f in FEATHERS])
+def test_gpu_vs_reference_feather(ob, fpath):
+    """The device output against the reference's own expected_arrow goldens, directly (tests/integration/main.rs:35-70),
+    not through the oracle.  Normalised as the reference's test does: pyarrow wrote the feathers (map fields key /
+    value, dense unions), so nested columns are compared by value."""
+    import pyarrow as pa
+    import pyarrow.feather as feather
+    name = os.path.basename(fpath)[: -len(".feather")]
+    orc = os.path.join(GOLDEN, "ref_integration", name + ".orc")
+    if name in ("orc-file-11-format", "orc_split_elim"):
+        pytest.skip("ignored by the reference itself (tests/integration/main.rs:334-351)")
+    try:
+        reader = ob.ArrowReaderBuilder.try_new(orc).build()
+    except ob.OrcError as e:
+        if e.variant == "UnsupportedDeviceCodec":
+            pytest.skip("Zstd / LZO: explicit error on the device path")
+        raise
+    got = reader.read_all()
+    exp = feather.read_table(fpath)
+    assert got.num_rows == exp.num_rows
+    for c in got.column_names:
+        a = got[c].combine_chunks()
+        b = exp[c].combine_chunks()
+        if pa.types.is_nested(a.type):
+            assert a.to_pylist() == b.to_pylist(), f"column {c} differs"
+            continue
+        if a.type != b.type:
+            b = b.cast(a.type)
+        assert a.equals(b), f"column {c} differs"
+
+
+def test_two_shards_equal_unsharded(ob, tmp_path):
+    """Multi-GPU recipe on one device: the union of the stripes two shards decode (stripe i -> shard i % 2, counted over
+    all files of the job) is the unsharded decode, batch for batch and byte for byte."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tools"))
+    import gen_orc
+    paths = []
+    for k in range(3):
+        p = str(tmp_path / f"li{k}.orc")
+        gen_orc.write(gen_orc.lineitem_table(25_000 + 7_000 * k, 40 + k), p, stripe_size=1 << 20, compression="snappy" if k == 1 else "uncompressed")
+        paths.append(p)
+    whole = ob.DecodeJob(paths).plan().stage().launch().finish()
+    n_stripes = whole.stats()["n_stripes"]
+    assert n_stripes >= 7
+    all_batches = whole.batches()
+    # batches per stripe, in job order
+    per_stripe = []
+    for p in paths:
+        f = ob._File(p)
+        for s in range(f.num_stripes):
+            rows = f.stripe_info(s)["number_of_rows"]
+            per_stripe.append(-(-rows // 8192))
+    assert sum(per_stripe) == len(all_batches)
+    starts = np.concatenate([[0], np.cumsum(per_stripe)])
+    shards = [ob.DecodeJob(paths, shard=(r, 2)).plan().stage().launch().finish() for r in range(2)]
+    assert sum(j.stats()["n_stripes"] for j in shards) == n_stripes
+    got = [j.batches() for j in shards]
+    cursor = [0, 0]
+    for i in range(n_stripes):
+        r = i % 2
+        for k in range(per_stripe[i]):
+            g = got[r][cursor[r]]
+            cursor[r] += 1
+            assert_batches_identical([g], [all_batches[starts[i] + k]], f"stripe {i} batch {k} (shard {r})")
+    assert cursor == [len(got[0]), len(got[1])]
+
+
 def test_synthetic_configs(ob, tmp_path):
     """Seeded synthetic files of the BASELINE configs (reduced sizes), all codecs the writer offers."""
     import sys
