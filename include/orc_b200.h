@@ -309,6 +309,9 @@ int orcb_decode_varint128(int device, const uint8_t* in, size_t in_len, uint8_t*
 int orcb_decompress_stream(int device, int compression_kind, const uint8_t* in, size_t in_len, size_t block_size,
                            uint8_t* out, size_t out_cap, size_t* out_len);
 
+/* Jobs of this process that were decoded a second time without the row index because a (stream, row group) segment did
+ * not end where the index says the next one starts (damaged stream or index).  0 on well-formed files. */
+uint64_t orcb_index_retries(void);
 /* Error detail of the last failing call on this thread. */
 const char* orcb_last_error(void);
 /* Build identification: "sm_100a" etc. */

@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <atomic>
 #include <memory>
 #include <thread>
 
@@ -85,6 +86,8 @@ struct OrcbReader {
     }
 };
 
+static std::atomic<uint64_t> g_index_retries{0};
+
 // finish() with the re-plan a LayoutRetry asks for (at most a few rounds: every round fixes the sizes of all chunks the
 // device could decode)
 static void finish_job(std::unique_ptr<Job>& job) {
@@ -92,6 +95,15 @@ static void finish_job(std::unique_ptr<Job>& job) {
         try {
             job->finish();
             return;
+        } catch (const IndexRetry&) {
+            // a segment did not end where the row index says the next one starts: decode as the reference does,
+            // sequentially (the damaged stream is then reported - or not - exactly as there)
+            g_index_retries++;
+            std::unique_ptr<Job> again = job->rebuild(true);
+            again->plan();
+            again->stage();
+            again->launch();
+            job = std::move(again);
         } catch (const LayoutRetry&) {
             if (round >= 3) fail(ORCB_UNEXPECTED, "compressed chunk sizes keep changing between decode passes");
             std::unique_ptr<Job> again = job->rebuild();
@@ -114,6 +126,9 @@ static int guarded(F&& f) {
     } catch (const LayoutRetry&) {
         g_last_error = "compressed chunk sizes differ from the planned layout (finish the job before exporting from it)";
         return ORCB_UNEXPECTED;
+    } catch (const IndexRetry&) {
+        g_last_error = "row-index positions do not agree with the streams (finish the job before exporting from it)";
+        return ORCB_UNEXPECTED;
     } catch (const std::bad_alloc&) {
         g_last_error = "out of host memory";
         return ORCB_UNEXPECTED;
@@ -129,6 +144,7 @@ static int guarded(F&& f) {
 extern "C" {
 
 const char* orcb_last_error(void) { return g_last_error.c_str(); }
+uint64_t orcb_index_retries(void) { return g_index_retries.load(); }
 const char* orcb_build_info(void) { return "orc_b200 " __DATE__ " sm_100a cuda " ORCB_STR(CUDART_VERSION); }
 
 int orcb_device_available(void) {
@@ -897,7 +913,7 @@ int orcb_decode_int_rle(int device, const uint8_t* in, size_t in_len, int versio
         s.run_cap = cap;
         CU(cudaMemcpy(dseg.p, &s, sizeof(s), cudaMemcpyHostToDevice));
         int rc = launch_rle_index((Seg*)dseg.p, 1, nullptr, (RunRec*)dtab.p, (BlockRec*)dblk.p, (uint32_t*)dcnt.p, pool,
-                                  (CoopRec*)dq.p, (uint32_t*)dcnt.p + 2, qcap, (uint32_t*)sr.err.p, 0);
+                                  (CoopRec*)dq.p, (uint32_t*)dcnt.p + 2, qcap, (uint32_t*)sr.err.p, nullptr, 0);
         if (rc) fail(ORCB_CUDA, cudaGetErrorString((cudaError_t)rc));
         rc = launch_int_rle((Seg*)dseg.p, (BlockRec*)dblk.p, (uint32_t*)dcnt.p, pool, (RunRec*)dtab.p, nullptr, nullptr,
                             (uint32_t*)sr.err.p, (uint32_t*)mis.p, (uint32_t*)dslow.p, (uint32_t*)dcnt.p + 1,
@@ -921,7 +937,7 @@ int orcb_decode_byte_rle(int device, const uint8_t* in, size_t in_len, uint8_t* 
         s.start_idx = -1;
         s.out_kind = OUT_I8;
         CU(cudaMemcpy(dseg.p, &s, sizeof(s), cudaMemcpyHostToDevice));
-        int rc = launch_byte_rle((Seg*)dseg.p, 1, nullptr, nullptr, (uint32_t*)sr.err.p, 0);
+        int rc = launch_byte_rle((Seg*)dseg.p, 1, nullptr, nullptr, (uint32_t*)sr.err.p, nullptr, 0);
         if (rc) fail(ORCB_CUDA, cudaGetErrorString((cudaError_t)rc));
         sr.check();
         if (n_values) CU(cudaMemcpy(out, dout.p, n_values, cudaMemcpyDeviceToHost));
@@ -954,7 +970,7 @@ int orcb_decode_bool_rle(int device, const uint8_t* in, size_t in_len, uint8_t* 
         b.start_idx = -1;
         b.popc_out = 0;
         CU(cudaMemcpy(dbit.p, &b, sizeof(b), cudaMemcpyHostToDevice));
-        int rc = launch_byte_rle((Seg*)dseg.p, 1, nullptr, nullptr, (uint32_t*)sr.err.p, 0);
+        int rc = launch_byte_rle((Seg*)dseg.p, 1, nullptr, nullptr, (uint32_t*)sr.err.p, nullptr, 0);
         if (rc) fail(ORCB_CUDA, cudaGetErrorString((cudaError_t)rc));
         rc = launch_bits((BitSeg*)dbit.p, 1, (uint32_t*)cnt.p, nullptr, 0);
         if (rc) fail(ORCB_CUDA, cudaGetErrorString((cudaError_t)rc));
@@ -975,7 +991,7 @@ int orcb_decode_varint128(int device, const uint8_t* in, size_t in_len, uint8_t*
         s.cnt_idx = -1;
         s.start_idx = -1;
         CU(cudaMemcpy(dseg.p, &s, sizeof(s), cudaMemcpyHostToDevice));
-        int rc = launch_varint128((Seg*)dseg.p, 1, nullptr, nullptr, (uint32_t*)sr.err.p, 0);
+        int rc = launch_varint128((Seg*)dseg.p, 1, nullptr, nullptr, (uint32_t*)sr.err.p, nullptr, 0);
         if (rc) fail(ORCB_CUDA, cudaGetErrorString((cudaError_t)rc));
         sr.check();
         if (n_values) CU(cudaMemcpy(out16, dout.p, n_values * 16, cudaMemcpyDeviceToHost));

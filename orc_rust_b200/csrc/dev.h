@@ -42,8 +42,18 @@ struct Seg {
     uint8_t out_kind;
     uint8_t pad0;
     uint32_t aux;
-    uint32_t run_base;   // unused (run blocks are allocated dynamically by k_rle_index)
+    uint32_t chk;        // > 0: slot + 1 in the position-check table (row-index consistency, see SegCheck)
     uint32_t run_cap;
+};
+
+// Row-index consistency.  With the row index in use every (stream, row group) segment starts from the position the
+// writer recorded.  The reference decodes sequentially and never looks at those positions, so a damaged stream (or a
+// wrong index) would make the two differ.  Every segment therefore leaves where it started and where it stopped, both
+// in canonical form: (byte of the run header, values of that run already consumed < run length [| bit << 16 for
+// boolean streams]); a segment must stop exactly where the next one of its stream starts, else the job is decoded again
+// without the row index (Job::finish, IndexRetry).
+struct SegCheck {
+    uint32_t start_byte, start_cons, end_byte, end_cons;
 };
 
 // A run that needs the whole warp (long DIRECT, DELTA with packed deltas, PATCHED_BASE), queued by the pre-pass

@@ -292,6 +292,7 @@ void Job::stage() {
     put(o_spm_, merge_spaced_.data(), merge_spaced_.size() * sizeof(SpacedDesc));
     put(o_popc_, popcs_.data(), popcs_.size() * sizeof(PopcDesc));
     put(o_union_, unions_.data(), unions_.size() * sizeof(UnionDesc));
+    put(o_chkpair_, chk_pairs_.data(), chk_pairs_.size() * sizeof(uint2));
     put(o_dec_, decfix_.data(), decfix_.size() * sizeof(DecFixDesc));
     put(o_ts_, ts_.data(), ts_.size() * sizeof(TsDesc));
     put(o_str_, strcols_.data(), strcols_.size() * sizeof(StrCol));
@@ -332,6 +333,7 @@ void Job::launch() {
     uint32_t* err = (uint32_t*)(d_meta_ + o_err_);
     uint32_t* nulls = (uint32_t*)(d_meta_ + o_nulls_);
     uint64_t* ptrs = (uint64_t*)(d_meta_ + o_ptrs_);
+    SegCheck* segchk = n_chk_ ? (SegCheck*)(uintptr_t)reloc(chk_table_) : nullptr;
     uint64_t launches = 0;
     auto chk = [&](int rc, const char* what) {
         if (rc) fail(ORCB_CUDA, std::string("launch ") + what + ": " + cudaGetErrorString((cudaError_t)rc));
@@ -352,7 +354,7 @@ void Job::launch() {
     if (N(chunks_))
         run("k_decompress", ab_decomp_, N(chunks_), 1, [&] { return launch_decompress((ChunkDesc*)(d_desc_ + o_chunk_), N(chunks_), err, (uint32_t*)(d_meta_ + o_clens_), (uint32_t*)(d_state_ + o_nblocks_) + 3, (uint32_t*)(d_meta_ + o_retry_), st); });
     if (N(present_byte_segs_)) {
-        run("k_byte_rle(present)", ab_present_, N(present_byte_segs_), 1, [&] { return launch_byte_rle((Seg*)(d_desc_ + o_pbyte_), N(present_byte_segs_), cnt, dstart, err, st); });
+        run("k_byte_rle(present)", ab_present_, N(present_byte_segs_), 1, [&] { return launch_byte_rle((Seg*)(d_desc_ + o_pbyte_), N(present_byte_segs_), cnt, dstart, err, segchk, st); });
         run("k_bits(present)", ab_present_, N(present_bit_segs_), 1, [&] { return launch_bits((BitSeg*)(d_desc_ + o_pbit_), N(present_bit_segs_), cnt, dstart, st); });
     }
     // validity handed down by a parent column: own PRESENT bits scattered into the parent's valid slots, then counted
@@ -363,7 +365,7 @@ void Job::launch() {
     if (N(scans_))
         run("k_seg_scan", 0, N(scans_), 1, [&] { return launch_seg_scan((ScanDesc*)(d_desc_ + o_scan_), N(scans_), cnt, dstart, st); });
     if (N(data_byte_segs_))
-        run("k_byte_rle", ab_byte_, N(data_byte_segs_), 1, [&] { return launch_byte_rle((Seg*)(d_desc_ + o_dbyte_), N(data_byte_segs_), cnt, dstart, err, st); });
+        run("k_byte_rle", ab_byte_, N(data_byte_segs_), 1, [&] { return launch_byte_rle((Seg*)(d_desc_ + o_dbyte_), N(data_byte_segs_), cnt, dstart, err, segchk, st); });
     if (N(data_bit_segs_))
         run("k_bits", ab_bits_, N(data_bit_segs_), 1, [&] { return launch_bits((BitSeg*)(d_desc_ + o_dbit_), N(data_bit_segs_), cnt, dstart, st); });
     // fork: the header-walk pre-pass is a long dependent chain on few warps, so it runs beside the
@@ -381,7 +383,7 @@ void Job::launch() {
         RunRec* rtab = (RunRec*)(uintptr_t)reloc(run_table_);
         BlockRec* brec = (BlockRec*)(uintptr_t)reloc(block_recs_);
         uint32_t* nblk = (uint32_t*)(d_state_ + o_nblocks_);
-        run("k_rle_index", 0, N(int_segs_), 1, [&] { return launch_rle_index((Seg*)(d_desc_ + o_int_), N(int_segs_), cnt, rtab, brec, nblk, pool_blocks_, (CoopRec*)(uintptr_t)reloc(coop_q_), nblk + 2, coop_cap_, err, aux); });
+        run("k_rle_index", 0, N(int_segs_), 1, [&] { return launch_rle_index((Seg*)(d_desc_ + o_int_), N(int_segs_), cnt, rtab, brec, nblk, pool_blocks_, (CoopRec*)(uintptr_t)reloc(coop_q_), nblk + 2, coop_cap_, err, segchk, aux); });
         run("k_int_rle(+general,+coop_runs)", ab_int_, pool_blocks_, 3, [&] { return launch_int_rle((Seg*)(d_desc_ + o_int_), brec, nblk, pool_blocks_, rtab, cnt, dstart, err, mis, (uint32_t*)(uintptr_t)reloc(slow_list_), nblk + 1, (CoopRec*)(uintptr_t)reloc(coop_q_), nblk + 2, coop_cap_, aux); });
         if (!serial_env) CUDA_OK(cudaEventRecord(ev_join_, aux));
         cur_st = st;
@@ -394,15 +396,17 @@ void Job::launch() {
     const char* order = order_env ? order_env : "kcv";
     for (const char* o = order; *o; o++) {
         if (*o == 'c' && N(int_big_segs_))
-            run("k_int_rle_coop", ab_intbig_, N(int_big_segs_), 1, [&] { return launch_int_rle_coop((Seg*)(d_desc_ + o_intbig_), N(int_big_segs_), cnt, dstart, err, mis, 0, st); });
+            run("k_int_rle_coop", ab_intbig_, N(int_big_segs_), 1, [&] { return launch_int_rle_coop((Seg*)(d_desc_ + o_intbig_), N(int_big_segs_), cnt, dstart, err, mis, 0, segchk, st); });
         if (*o == 'v' && N(var_segs_))
-            run("k_varint128", ab_var_, N(var_segs_), 1, [&] { return launch_varint128((Seg*)(d_desc_ + o_var_), N(var_segs_), cnt, dstart, err, st); });
+            run("k_varint128", ab_var_, N(var_segs_), 1, [&] { return launch_varint128((Seg*)(d_desc_ + o_var_), N(var_segs_), cnt, dstart, err, segchk, st); });
         if (*o == 'k' && N(copy_tiles_))
             run("k_copy", ab_copy_, N(copy_tiles_), 1, [&] { return launch_copy((CopyDesc*)(d_desc_ + o_copy_), (uint2*)(d_desc_ + o_ctile_), N(copy_tiles_), cnt, err, (StrCol*)(d_desc_ + o_str_), st); });
     }
     if (forked && !serial_env) CUDA_OK(cudaStreamWaitEvent(st, ev_join_, 0));
+    if (N(chk_pairs_))  // every segment has left its start and end position: do they join up?
+        run("k_seg_check", 0, N(chk_pairs_), 1, [&] { return launch_seg_check((uint2*)(d_desc_ + o_chkpair_), N(chk_pairs_), segchk, (uint32_t*)(d_meta_ + o_retry_), st); });
     if (N(decfix_) && N(int_big_segs_))  // scales that were only compared so far are written where one of them differed
-        run("k_int_rle_coop(scales)", 0, N(int_big_segs_), 1, [&] { return launch_int_rle_coop((Seg*)(d_desc_ + o_intbig_), N(int_big_segs_), cnt, dstart, err, mis, 1, st); });
+        run("k_int_rle_coop(scales)", 0, N(int_big_segs_), 1, [&] { return launch_int_rle_coop((Seg*)(d_desc_ + o_intbig_), N(int_big_segs_), cnt, dstart, err, mis, 1, nullptr, st); });
     if (N(decfix_))
         run("k_decimal_fix", ab_dec_, N(decfix_), 1, [&] { return launch_decimal_fix((DecFixDesc*)(d_desc_ + o_dec_), N(decfix_), cnt, mis, st); });
     if (N(ts_))
@@ -437,7 +441,9 @@ void Job::finish() {
         if (cudaEventElapsedTime(&ms, k.e0, k.e1) == cudaSuccess) k.ms = ms;
         else cudaGetLastError();
     }
-    if (*(const uint32_t*)(h_meta_ + o_retry_)) {
+    const uint32_t retry = *(const uint32_t*)(h_meta_ + o_retry_);
+    if ((retry & 2u) && !(retry & 1u)) throw IndexRetry{};
+    if (retry & 1u) {
         // some chunk did not have the size the layout assumed: remember every size the device found and ask for a re-plan
         const uint32_t* cl = (const uint32_t*)(h_meta_ + o_clens_);
         for (size_t i = 0; i < chunk_keys_.size(); i++) {

@@ -122,12 +122,19 @@ struct HostOutput;  // D2H copy of the output arenas, shared by exported batches
 // Thrown by Job::finish when chunks of unknown decompressed size (Zlib, LZ4) turned out not to fill their blocks: the
 // sizes found are in the files' ChunkSizeCache by then, and the same tasks planned again get an exact layout.
 struct LayoutRetry {};
+// Thrown by Job::finish when a (stream, row group) segment did not stop where the row index says the next one starts
+// (damaged stream or index): the same tasks are decoded again without the row index, as the reference decodes.
+struct IndexRetry {};
 
 class Job {
   public:
     Job(std::vector<StripeTask> tasks, const ReadOptions& opt);
     // a fresh job over the same tasks and options (after LayoutRetry)
-    std::unique_ptr<Job> rebuild() const { return std::make_unique<Job>(tasks_, orig_opt_); }
+    std::unique_ptr<Job> rebuild(bool without_row_index = false) const {
+        ReadOptions o = orig_opt_;
+        if (without_row_index) o.use_row_index = false;
+        return std::make_unique<Job>(tasks_, o);
+    }
     ~Job();
     void plan();
     void stage();
@@ -174,6 +181,9 @@ class Job {
     std::vector<uint2> u8_tiles_;   // (string column, U8_TILE-byte tile) units of the UTF-8 check
     std::vector<SpacedDesc> spaced_, spaced_late_, merge_spaced_;
     std::vector<PopcDesc> popcs_;
+    std::vector<uint2> chk_pairs_;         // (slot, slot of the next segment of the same stream)
+    uint32_t n_chk_ = 0;
+    uint64_t chk_table_ = 0, o_chkpair_ = 0;  // AR_TMP offset of SegCheck[n_chk_]
     std::vector<UnionDesc> unions_;
     bool nested_ = false;                  // some column is (or descends from) a struct / list / map / union
     std::unique_ptr<Job> next_level_;      // decodes the children of this job's nested columns

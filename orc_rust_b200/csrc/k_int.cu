@@ -553,7 +553,7 @@ __global__ void __launch_bounds__(128) k_rle_index(const Seg* __restrict__ segs,
                                                    BlockRec* __restrict__ blocks, uint32_t* __restrict__ nblocks,
                                                    uint32_t pool_blocks, CoopRec* __restrict__ coop_q,
                                                    uint32_t* __restrict__ ncoop, uint32_t coop_cap, uint32_t* err,
-                                                   uint32_t idx_lanes) {
+                                                   uint32_t idx_lanes, SegCheck* __restrict__ chk) {
     // only `idx_lanes` lanes of each warp own a segment: a warp advances at the pace of its slowest lane
     // (the one that misses L1 this step), so fewer streams per warp and more warps hide more latency
     const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
@@ -576,6 +576,12 @@ __global__ void __launch_bounds__(128) k_rle_index(const Seg* __restrict__ segs,
     const bool v2 = (s.flags & SEG_RLE_V2) != 0;
     const uint32_t len = s.in_len;
     RunRec* slot = nullptr;
+    // row-index consistency: canonical start now, canonical end after the walk (from the last run's bookkeeping)
+    SegCheck ck;
+    ck.start_byte = ck.end_byte = cur;
+    ck.start_cons = ck.end_cons = skip;
+    uint32_t last_cur = cur, last_skip = skip, last_produced = 0;
+    bool walked = false, broken = false;
     // every instruction of this loop sits on the segment's serial chain: keep it short
     while (produced < n) {
         if (in_blk == 0) {
@@ -610,9 +616,15 @@ __global__ void __launch_bounds__(128) k_rle_index(const Seg* __restrict__ segs,
         *slot++ = r;
         in_blk++;
         if (!stop) {
+            last_cur = cur;
+            last_skip = skip;
+            last_produced = produced;
+            walked = true;
             produced += min(rl - min(skip, rl), n - produced);
             skip = 0;
             cur += nbytes;
+        } else {
+            broken = true;
         }
         if (in_blk == 32 || stop || produced >= n) {
             BlockRec br;
@@ -625,6 +637,21 @@ __global__ void __launch_bounds__(128) k_rle_index(const Seg* __restrict__ segs,
             blk_skip = 0;
             if (stop) break;
         }
+    }
+    if (chk && s.chk) {
+        if (walked && !broken) {
+            // the last run again: was it used up?
+            uint32_t rl = 0, nbytes = 0;
+            bool cq;
+            if (measure_run(s, last_cur, rl, nbytes, cq) == 0) {
+                const uint32_t cons = min(last_skip, rl) + min(rl - min(last_skip, rl), n - last_produced);
+                ck.end_byte = cons >= rl ? last_cur + nbytes : last_cur;
+                ck.end_cons = cons >= rl ? 0u : cons;
+            }
+        } else if (broken) {
+            ck.end_byte = ck.end_cons = 0xffffffffu;  // the stream failed here: the error is what gets reported
+        }
+        chk[s.chk - 1] = ck;
     }
 }
 
@@ -1021,7 +1048,8 @@ __global__ void __launch_bounds__(RLE_WARPS * 32) k_coop_runs(const Seg* __restr
 __global__ void __launch_bounds__(RLE_WARPS * 32) k_int_rle_coop(const Seg* __restrict__ segs, uint32_t nseg,
                                                                  const uint32_t* __restrict__ cnt,
                                                                  const uint32_t* __restrict__ dstart, uint32_t* err,
-                                                                 uint32_t* mis, int second_pass) {
+                                                                 uint32_t* mis, int second_pass,
+                                                                 SegCheck* __restrict__ chk) {
     __shared__ uint32_t patchmap_all[RLE_WARPS][16];
     uint32_t* patchmap = patchmap_all[threadIdx.x >> 5];
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -1037,6 +1065,23 @@ __global__ void __launch_bounds__(RLE_WARPS * 32) k_int_rle_coop(const Seg* __re
     const uint32_t n = s.cnt_idx >= 0 ? cnt[s.cnt_idx] : s.n_values;
     const uint64_t obase = s.start_idx >= 0 ? dstart[s.start_idx] : s.out_start;
     uint32_t cur = s.start_byte, skip = s.run_skip, produced = 0;
+    const bool checking = chk && s.chk && !second_pass;
+    SegCheck ck;
+    bool started = false;
+    ck.start_byte = ck.end_byte = cur;
+    ck.start_cons = ck.end_cons = skip;
+    // (n == 0: the start is put into canonical form by stepping over the runs the skip covers)
+    if (checking && n == 0) {
+        while (skip > 0 && cur < s.in_len) {
+            uint32_t rl, nbytes;
+            bool cq;
+            if (measure_run(s, cur, rl, nbytes, cq) || skip < rl) break;
+            skip -= rl;
+            cur += nbytes;
+        }
+        ck.start_byte = ck.end_byte = cur;
+        ck.start_cons = ck.end_cons = skip;
+    }
     while (produced < n) {
         if (cur >= s.in_len) { set_err(err, s.colstripe, ORCB_OUT_OF_SPEC); return; }
         // pull the bytes of the following runs into L2 while this run is decoded (one line per lane, 4 KiB)
@@ -1048,16 +1093,29 @@ __global__ void __launch_bounds__(RLE_WARPS * 32) k_int_rle_coop(const Seg* __re
         const uint32_t st = coop_run2(c, cur, skip, n - produced, obase + produced, patchmap, rl, nbytes, take);
         if (st) { set_err(err, s.colstripe, st); return; }
         if (skip >= rl) skip -= rl;
-        else { produced += take; skip = 0; }
+        else {
+            if (!started) {  // the first run that yields a value: canonical start
+                started = true;
+                ck.start_byte = cur;
+                ck.start_cons = skip;
+            }
+            const uint32_t cons = skip + take;
+            ck.end_byte = cons >= rl ? cur + nbytes : cur;
+            ck.end_cons = cons >= rl ? 0u : cons;
+            produced += take;
+            skip = 0;
+        }
         cur += nbytes;
     }
+    if (checking && (threadIdx.x & 31) == 0) chk[s.chk - 1] = ck;
 }
 
 // ------------------------------------------------------------------------------------------------
 // host-side launch wrappers
 // ------------------------------------------------------------------------------------------------
 int launch_rle_index(const Seg* segs, uint32_t n, const uint32_t* cnt, RunRec* table, BlockRec* blocks, uint32_t* nblocks,
-                     uint32_t pool_blocks, CoopRec* coop_q, uint32_t* ncoop, uint32_t coop_cap, uint32_t* err, cudaStream_t st) {
+                     uint32_t pool_blocks, CoopRec* coop_q, uint32_t* ncoop, uint32_t coop_cap, uint32_t* err, SegCheck* chk,
+                     cudaStream_t st) {
     if (!n) return 0;
     static uint32_t lanes = 0;
     if (!lanes) {
@@ -1068,7 +1126,7 @@ int launch_rle_index(const Seg* segs, uint32_t n, const uint32_t* cnt, RunRec* t
         }
     }
     const uint32_t nwarps = (n + lanes - 1) / lanes;
-    k_rle_index<<<(nwarps + 3) / 4, 128, 0, st>>>(segs, n, cnt, table, blocks, nblocks, pool_blocks, coop_q, ncoop, coop_cap, err, lanes);
+    k_rle_index<<<(nwarps + 3) / 4, 128, 0, st>>>(segs, n, cnt, table, blocks, nblocks, pool_blocks, coop_q, ncoop, coop_cap, err, lanes, chk);
     LAUNCH_CHECK();
     return 0;
 }
@@ -1103,9 +1161,9 @@ int launch_int_rle(const Seg* segs, const BlockRec* blocks, const uint32_t* nblo
     return 0;
 }
 int launch_int_rle_coop(const Seg* segs, uint32_t n, const uint32_t* cnt, const uint32_t* dstart, uint32_t* err,
-                        uint32_t* mis, int second_pass, cudaStream_t st) {
+                        uint32_t* mis, int second_pass, SegCheck* chk, cudaStream_t st) {
     if (!n) return 0;
-    k_int_rle_coop<<<blocks_for_warps(n, RLE_WARPS), RLE_WARPS * 32, 0, st>>>(segs, n, cnt, dstart, err, mis, second_pass);
+    k_int_rle_coop<<<blocks_for_warps(n, RLE_WARPS), RLE_WARPS * 32, 0, st>>>(segs, n, cnt, dstart, err, mis, second_pass, chk);
     LAUNCH_CHECK();
     return 0;
 }

@@ -9,7 +9,8 @@ namespace orcb {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(RLE_WARPS * 32) k_byte_rle(const Seg* __restrict__ segs, uint32_t nseg,
                                                              const uint32_t* __restrict__ cnt,
-                                                             const uint32_t* __restrict__ dstart, uint32_t* err) {
+                                                             const uint32_t* __restrict__ dstart, uint32_t* err,
+                                                             SegCheck* __restrict__ chk) {
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (warp >= nseg) return;
     const Seg& s = segs[warp];
@@ -18,35 +19,73 @@ __global__ void __launch_bounds__(RLE_WARPS * 32) k_byte_rle(const Seg* __restri
     const uint32_t len = s.in_len;
     // for boolean streams n_values counts BITS; aux = 1 marks "bits": convert to bytes incl. the bit offset
     uint32_t n = s.cnt_idx >= 0 ? cnt[s.cnt_idx] : s.n_values;
-    if (s.aux & 1) n = (n + (s.aux >> 1) + 7) / 8;  // aux>>1 = bit_skip
+    const uint32_t bit0 = (s.aux & 1) ? (s.aux >> 1) : 0u;  // bit_skip
+    // bytes used up completely: where the next row group of the stream starts (a partly used byte is its first)
+    const uint32_t full = (s.aux & 1) ? (n + bit0) / 8 : n;
+    const uint32_t end_bit = (s.aux & 1) ? (n + bit0) & 7u : 0u;
+    if (s.aux & 1) n = (n + bit0 + 7) / 8;
     uint8_t* out = (uint8_t*)s.out + (s.start_idx >= 0 ? dstart[s.start_idx] : s.out_start);
     uint32_t cur = s.start_byte, skip = s.run_skip, produced = 0;
+    const bool checking = chk && s.chk;
+    SegCheck ck;
+    if (checking) {
+        // canonical start: step over the runs the skip covers entirely
+        while (cur < len) {
+            const uint32_t h = in[cur];
+            const uint32_t rl = h < 0x80 ? h + 3 : 0x100 - h;
+            if (skip < rl) break;
+            skip -= rl;
+            cur += h < 0x80 ? 2u : 1u + rl;
+        }
+        ck.start_byte = ck.end_byte = cur;
+        ck.start_cons = skip | (bit0 << 16);
+        ck.end_cons = skip | (end_bit << 16);
+    }
     while (produced < n) {
         if (cur >= len) { set_err(err, s.colstripe, ORCB_IO_ERROR); return; }
         const uint32_t h = in[cur];
-        uint32_t rl, run_bytes;
+        uint32_t rl, run_bytes, take;
+        const uint32_t skip0 = skip;
         if (h < 0x80) {
             rl = h + 3;
             run_bytes = 2;
             if (cur + 2 > len) { set_err(err, s.colstripe, ORCB_IO_ERROR); return; }
             const uint8_t v = in[cur + 1];
             const uint32_t avail = rl > skip ? rl - skip : 0;
-            const uint32_t take = min(avail, n - produced);
+            take = min(avail, n - produced);
             for (uint32_t i = lane; i < take; i += 32) out[produced + i] = v;
-            if (skip >= rl) skip -= rl;
-            else { produced += take; skip = 0; }
         } else {
             rl = 0x100 - h;
             run_bytes = 1 + rl;
             if (cur + run_bytes > len) { set_err(err, s.colstripe, ORCB_IO_ERROR); return; }
             const uint32_t avail = rl > skip ? rl - skip : 0;
-            const uint32_t take = min(avail, n - produced);
+            take = min(avail, n - produced);
             for (uint32_t i = lane; i < take; i += 32) out[produced + i] = in[cur + 1 + skip + i];
-            if (skip >= rl) skip -= rl;
-            else { produced += take; skip = 0; }
+        }
+        if (skip >= rl) {
+            skip -= rl;
+        } else {
+            if (checking && full > produced && full <= produced + take) {
+                // the byte position `full` bytes into the segment falls in this run
+                const uint32_t cons = skip0 + (full - produced);
+                ck.end_byte = cons >= rl ? cur + run_bytes : cur;
+                ck.end_cons = (cons >= rl ? 0u : cons) | (end_bit << 16);
+            }
+            produced += take;
+            skip = 0;
         }
         cur += run_bytes;
     }
+    if (checking && lane == 0) chk[s.chk - 1] = ck;
+}
+
+// Row-index consistency: a segment must stop where the next segment of its stream starts (SegCheck, dev.h)
+__global__ void k_seg_check(const uint2* __restrict__ pairs, uint32_t npairs, const SegCheck* __restrict__ chk, uint32_t* retry) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npairs) return;
+    const SegCheck a = chk[pairs[i].x], b = chk[pairs[i].y];
+    if (a.end_byte == 0xffffffffu) return;  // the segment failed: its error is reported
+    if (a.end_byte != b.start_byte || a.end_cons != b.start_cons) atomicOr(retry, 2u);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -163,7 +202,8 @@ __global__ void __launch_bounds__(128) k_union_valid(const UnionDesc* __restrict
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_varint128(const Seg* __restrict__ segs, uint32_t nseg,
                                                    const uint32_t* __restrict__ cnt,
-                                                   const uint32_t* __restrict__ dstart, uint32_t* err) {
+                                                   const uint32_t* __restrict__ dstart, uint32_t* err,
+                                                   SegCheck* __restrict__ chk) {
     // 128-byte windows.  Lane l looks at bytes l, l+32, l+64, l+96 so that each ballot is a terminator
     // bitmap in byte order.  Every window starts at the first byte of a value; terminator lanes publish the
     // end position of "their" value in shared memory, then the values are assembled one per lane per round.
@@ -188,7 +228,12 @@ __global__ void __launch_bounds__(128) k_varint128(const Seg* __restrict__ segs,
     uint32_t produced = 0;
     uint32_t cur = s.start_byte;
     const uint32_t lt = (1u << lane) - 1;
-    if (n == 0) return;
+    const bool checking = chk && s.chk;
+    if (n == 0) {
+        if (checking && lane == 0) chk[s.chk - 1] = SegCheck{cur, 0u, cur, 0u};
+        return;
+    }
+    const uint32_t start_byte = cur;
     const uint64_t a0 = (uint64_t)(uintptr_t)s.in;
     const uint64_t a_lim = a0 + len + 128;  // chunks are fetched only below this address (inside the arena slack)
     auto fetch = [&](uint64_t chunk) -> uint32_t {
@@ -286,6 +331,8 @@ __global__ void __launch_bounds__(128) k_varint128(const Seg* __restrict__ segs,
             const uint64_t rhi = (hi >> 1) ^ sgn;
             out[produced + k] = make_uint4((uint32_t)rlo, (uint32_t)(rlo >> 32), (uint32_t)rhi, (uint32_t)(rhi >> 32));
         }
+        // (the segment ends behind its last value, wherever the window's last terminator lies)
+        if (checking && total >= room && lane == 0) chk[s.chk - 1] = SegCheck{start_byte, 0u, cur + (uint32_t)ends[room - 1] + 1, 0u};
         produced += total;
         cur += (uint32_t)ends[total - 1] + 1;
         __syncwarp();
@@ -550,10 +597,10 @@ __global__ void __launch_bounds__(128) k_repack(const RepackDesc* __restrict__ d
 // ------------------------------------------------------------------------------------------------
 // host-side launch wrappers
 // ------------------------------------------------------------------------------------------------
-int launch_byte_rle(const Seg* segs, uint32_t n, const uint32_t* cnt, const uint32_t* dstart, uint32_t* err,
+int launch_byte_rle(const Seg* segs, uint32_t n, const uint32_t* cnt, const uint32_t* dstart, uint32_t* err, SegCheck* chk,
                     cudaStream_t st) {
     if (!n) return 0;
-    k_byte_rle<<<blocks_for_warps(n, RLE_WARPS), RLE_WARPS * 32, 0, st>>>(segs, n, cnt, dstart, err);
+    k_byte_rle<<<blocks_for_warps(n, RLE_WARPS), RLE_WARPS * 32, 0, st>>>(segs, n, cnt, dstart, err, chk);
     LAUNCH_CHECK();
     return 0;
 }
@@ -569,10 +616,10 @@ int launch_seg_scan(const ScanDesc* d, uint32_t n, uint32_t* cnt, uint32_t* dsta
     LAUNCH_CHECK();
     return 0;
 }
-int launch_varint128(const Seg* segs, uint32_t n, const uint32_t* cnt, const uint32_t* dstart, uint32_t* err,
+int launch_varint128(const Seg* segs, uint32_t n, const uint32_t* cnt, const uint32_t* dstart, uint32_t* err, SegCheck* chk,
                      cudaStream_t st) {
     if (!n) return 0;
-    k_varint128<<<blocks_for_warps(n, 4), 128, 0, st>>>(segs, n, cnt, dstart, err);
+    k_varint128<<<blocks_for_warps(n, 4), 128, 0, st>>>(segs, n, cnt, dstart, err, chk);
     LAUNCH_CHECK();
     return 0;
 }
@@ -609,6 +656,12 @@ int launch_repack(const RepackDesc* d, uint32_t ndesc, uint32_t nwork, uint32_t*
     return 0;
 }
 
+int launch_seg_check(const uint2* pairs, uint32_t n, const SegCheck* chk, uint32_t* retry, cudaStream_t st) {
+    if (!n) return 0;
+    k_seg_check<<<(n + 255) / 256, 256, 0, st>>>(pairs, n, chk, retry);
+    LAUNCH_CHECK();
+    return 0;
+}
 int launch_popc(const PopcDesc* d, uint32_t n, uint32_t* cnt, cudaStream_t st) {
     if (!n) return 0;
     k_popc<<<blocks_for_warps(n, 4), 128, 0, st>>>(d, n, cnt);

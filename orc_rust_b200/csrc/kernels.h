@@ -9,18 +9,21 @@ namespace orcb {
 
 // short-run integer path: header-walk pre-pass into the run table, then one warp per 32 runs
 int launch_rle_index(const Seg* segs, uint32_t n, const uint32_t* cnt, RunRec* table, BlockRec* blocks, uint32_t* nblocks,
-                     uint32_t pool_blocks, CoopRec* coop_q, uint32_t* ncoop, uint32_t coop_cap, uint32_t* err, cudaStream_t st);
+                     uint32_t pool_blocks, CoopRec* coop_q, uint32_t* ncoop, uint32_t coop_cap, uint32_t* err, SegCheck* chk,
+                     cudaStream_t st);
 int launch_int_rle(const Seg* segs, const BlockRec* blocks, const uint32_t* nblocks, uint32_t pool_blocks, const RunRec* table,
                    const uint32_t* cnt, const uint32_t* dstart, uint32_t* err, uint32_t* mis, uint32_t* slow_list,
                    uint32_t* slow_count, const CoopRec* coop_q, const uint32_t* ncoop, uint32_t coop_cap, cudaStream_t st);
 // second_pass = 1: only the decimal scale segments of column-stripes whose mismatch flag is set, every value written
 int launch_int_rle_coop(const Seg* segs, uint32_t n, const uint32_t* cnt, const uint32_t* dstart, uint32_t* err,
-                        uint32_t* mis, int second_pass, cudaStream_t st);
-int launch_byte_rle(const Seg* segs, uint32_t n, const uint32_t* cnt, const uint32_t* dstart, uint32_t* err,
+                        uint32_t* mis, int second_pass, SegCheck* chk, cudaStream_t st);
+// chk (may be NULL): position-check table, see SegCheck in dev.h
+int launch_byte_rle(const Seg* segs, uint32_t n, const uint32_t* cnt, const uint32_t* dstart, uint32_t* err, SegCheck* chk,
                     cudaStream_t st);
+int launch_seg_check(const uint2* pairs, uint32_t n, const SegCheck* chk, uint32_t* retry, cudaStream_t st);
 int launch_bits(const BitSeg* segs, uint32_t n, uint32_t* cnt, const uint32_t* dstart, cudaStream_t st);
 int launch_seg_scan(const ScanDesc* d, uint32_t n, uint32_t* cnt, uint32_t* dstart, cudaStream_t st);
-int launch_varint128(const Seg* segs, uint32_t n, const uint32_t* cnt, const uint32_t* dstart, uint32_t* err,
+int launch_varint128(const Seg* segs, uint32_t n, const uint32_t* cnt, const uint32_t* dstart, uint32_t* err, SegCheck* chk,
                      cudaStream_t st);
 int launch_copy(const CopyDesc* d, const uint2* tiles, uint32_t ntiles, const uint32_t* cnt, uint32_t* err,
                 const StrCol* strcols, cudaStream_t st);

@@ -116,6 +116,7 @@ void Job::plan() {
         return ka > kb;
     });
 
+    if (n_chk_) chk_table_ = alloc(AR_TMP, (uint64_t)n_chk_ * sizeof(SegCheck));
     if (pool_blocks_) {
         run_table_ = alloc(AR_TMP, (uint64_t)pool_blocks_ * 32 * sizeof(RunRec));
         block_recs_ = alloc(AR_TMP, (uint64_t)pool_blocks_ * sizeof(BlockRec));
@@ -146,6 +147,7 @@ void Job::plan() {
     place(o_spm_, merge_spaced_.size() * sizeof(SpacedDesc));
     place(o_popc_, popcs_.size() * sizeof(PopcDesc));
     place(o_union_, unions_.size() * sizeof(UnionDesc));
+    place(o_chkpair_, chk_pairs_.size() * sizeof(uint2));
     place(o_dec_, decfix_.size() * sizeof(DecFixDesc));
     place(o_ts_, ts_.size() * sizeof(TsDesc));
     place(o_str_, strcols_.size() * sizeof(StrCol));
@@ -470,10 +472,19 @@ void Job::plan_stripe(uint32_t task_idx) {
             return one;
         };
         auto rows_in_group = [&](uint32_t g) { return std::min(gstride, n_rows - g * gstride); };
+        // row-index consistency (SegCheck): consecutive row groups of one stream are linked; `prev` is per stream
+        auto link = [&](Seg& sg, uint32_t g, uint32_t& prev) {
+            if (!indexed) return;
+            const uint32_t slot = n_chk_++;
+            sg.chk = slot + 1;
+            if (g > 0) chk_pairs_.push_back(make_uint2(prev, slot));
+            prev = slot;
+        };
 
         // ---- PRESENT -> stripe-level validity bitmap, per-group non-null counts, per-batch bitmaps
         uint32_t cnt_base = 0;
         uint64_t valid_raw = 0;
+        uint32_t chk_prev_present = 0;
         if (has_present) {
             cnt_base = n_cnt_;
             n_cnt_ += n_groups + 1;
@@ -497,6 +508,7 @@ void Job::plan_stripe(uint32_t task_idx) {
                     sg.colstripe = cs;
                     sg.out_kind = OUT_I8;
                     sg.aux = 1u | (pe[g].bit << 1);
+                    link(sg, g, chk_prev_present);
                     present_byte_segs_.push_back(sg);
                     BitSeg b{};
                     b.src = raw + (uint64_t)g * slot;
@@ -589,11 +601,13 @@ void Job::plan_stripe(uint32_t task_idx) {
                                 bool per_group_counts) {
             const std::vector<Entry>& en = spec_of(&sr);
             const uint32_t ng = indexed ? n_groups : 1;
+            uint32_t chk_prev = 0;
             for (uint32_t g = 0; g < ng; g++) {
                 Seg sg{};
                 sg.in = sr.ptr;
                 sg.in_len = sr.len;
                 sg.out = dst;
+                link(sg, g, chk_prev);
                 sg.start_byte = en[g].byte;
                 sg.run_skip = en[g].skip;
                 sg.colstripe = cs;
@@ -689,6 +703,7 @@ void Job::plan_stripe(uint32_t task_idx) {
                 if (has_present) dst = alloc(AR_TMP, (uint64_t)n_rows);
                 const std::vector<Entry>& en = spec_of(&s_data);
                 const uint32_t ng = indexed ? n_groups : 1;
+                uint32_t chk_prev = 0;
                 for (uint32_t g = 0; g < ng; g++) {
                     Seg sg{};
                     sg.in = s_data.ptr;
@@ -698,7 +713,7 @@ void Job::plan_stripe(uint32_t task_idx) {
                     sg.run_skip = en[g].skip;
                     sg.colstripe = cs;
                     sg.out_kind = OUT_I8;
-                                        if (has_present) {
+                    if (has_present) {
                         sg.cnt_idx = (int32_t)(cnt_base + g);
                         sg.start_idx = (int32_t)(cnt_base + g);
                     } else {
@@ -707,6 +722,7 @@ void Job::plan_stripe(uint32_t task_idx) {
                         sg.n_values = rows_in_group(g);
                         sg.out_start = g * gstride;
                     }
+                    link(sg, g, chk_prev);
                     data_byte_segs_.push_back(sg);
                 }
                 n_segments_ += ng;
@@ -714,6 +730,7 @@ void Job::plan_stripe(uint32_t task_idx) {
                 break;
             }
             case T_BOOLEAN: {
+                uint32_t chk_prev_bool = 0;
                 const uint32_t ng = indexed ? n_groups : 1;
                 const uint32_t slot = (gstride + 7) / 8 + 8;
                 const uint64_t raw = alloc(AR_TMP, (uint64_t)slot * ng + 16);
@@ -750,6 +767,7 @@ void Job::plan_stripe(uint32_t task_idx) {
                         b.start_idx = -1;
                         b.dst_bit0 = g * gstride;
                     }
+                    link(sg, g, chk_prev_bool);
                     data_byte_segs_.push_back(sg);
                     data_bit_segs_.push_back(b);
                 }
@@ -879,6 +897,7 @@ void Job::plan_stripe(uint32_t task_idx) {
                 const uint64_t scales = alloc(AR_TMP, (uint64_t)n_rows * 4 + 16);
                 const std::vector<Entry>& en = spec_of(&s_data);
                 const uint32_t ng = indexed ? n_groups : 1;
+                uint32_t chk_prev_var = 0;
                 for (uint32_t g = 0; g < ng; g++) {
                     Seg sg{};
                     sg.in = s_data.ptr;
@@ -895,6 +914,7 @@ void Job::plan_stripe(uint32_t task_idx) {
                         sg.n_values = rows_in_group(g);
                         sg.out_start = g * gstride;
                     }
+                    link(sg, g, chk_prev_var);
                     var_segs_.push_back(sg);
                 }
                 n_segments_ += ng;
