@@ -580,8 +580,8 @@ __global__ void __launch_bounds__(128) k_rle_index(const Seg* __restrict__ segs,
     SegCheck ck;
     ck.start_byte = ck.end_byte = cur;
     ck.start_cons = ck.end_cons = skip;
-    uint32_t last_cur = cur, last_skip = skip, last_produced = 0;
-    bool walked = false, broken = false;
+    const uint32_t skip0 = skip;
+    bool broken = false;
     // every instruction of this loop sits on the segment's serial chain: keep it short
     while (produced < n) {
         if (in_blk == 0) {
@@ -616,15 +616,9 @@ __global__ void __launch_bounds__(128) k_rle_index(const Seg* __restrict__ segs,
         *slot++ = r;
         in_blk++;
         if (!stop) {
-            last_cur = cur;
-            last_skip = skip;
-            last_produced = produced;
-            walked = true;
             produced += min(rl - min(skip, rl), n - produced);
             skip = 0;
             cur += nbytes;
-        } else {
-            broken = true;
         }
         if (in_blk == 32 || stop || produced >= n) {
             BlockRec br;
@@ -635,12 +629,16 @@ __global__ void __launch_bounds__(128) k_rle_index(const Seg* __restrict__ segs,
             blocks[blk] = br;
             in_blk = 0;
             blk_skip = 0;
-            if (stop) break;
+            if (stop) { broken = true; break; }
         }
     }
     if (chk && s.chk) {
-        if (walked && !broken) {
-            // the last run again: was it used up?
+        if (slot && !broken) {
+            // The last run again (nothing of this sits on the walk's chain): its record says where it starts and how
+            // many values came before it; only a segment's first run is entered with values to skip.  Was it used up?
+            const RunRec last = slot[-1];
+            const uint32_t last_cur = last.byte_off, last_produced = last.out_off & ~RUN_QUEUED;
+            const uint32_t last_skip = last_produced == 0 ? skip0 : 0u;
             uint32_t rl = 0, nbytes = 0;
             bool cq;
             if (measure_run(s, last_cur, rl, nbytes, cq) == 0) {
