@@ -6,6 +6,7 @@ import os
 import re
 
 import pyarrow as pa
+import numpy as np
 import pytest
 
 from conftest import GOLDEN
@@ -196,3 +197,39 @@ def test_oracle_row_selection_golden():
         assert n == len(rows), name
         if n:
             assert pa.Table.from_batches(got).equals(full.take(pa.array(rows, pa.int64()))), name
+
+
+def _varint(v):
+    out = bytearray()
+    while v >= 0x80:
+        out.append((v & 0x7F) | 0x80)
+        v >>= 7
+    out.append(v)
+    return bytes(out)
+
+
+def test_crafted_tail_lengths_do_not_wrap(ob):
+    """File-controlled 64-bit lengths whose sums wrap (footerLength = 2^64 - 5 and friends) are an error, never an
+    out-of-bounds read: the reference returns OutOfSpec / IoError here (src/reader/metadata.rs:199-236)."""
+    for comp in (0, 2, 1, 4):
+        for footer_len, meta_len in ((2**64 - 5, 0), (2**64 - 1, 2**64 - 1), (40, 2**64 - 30), (2**63, 2**63), (10**6, 0)):
+            ps = b"\x08" + _varint(footer_len) + b"\x10" + _varint(comp) + b"\x18" + _varint(262144) + b"\x28" + _varint(meta_len)
+            body = b"ORC" + bytes(88 - 3 - len(ps) - 1) if len(ps) + 4 <= 88 else b"ORC"
+            data = body + ps + bytes([len(ps)])
+            with pytest.raises(ob.OrcError) as e:
+                ob.ArrowReaderBuilder.try_new(data)
+            assert e.value.variant in ("OutOfSpec", "IoError", "DecodeProto"), (comp, footer_len, meta_len, e.value)
+    # stripe and stream lengths of a real file pushed past 2^64
+    path = os.path.join(GOLDEN, "ref_basic", "test.orc")
+    data0 = open(path, "rb").read()
+    rng = np.random.default_rng(5)
+    for _ in range(300):  # random damage in the tail: footer, postscript
+        data = bytearray(data0)
+        for _ in range(int(rng.integers(1, 4))):
+            data[int(rng.integers(len(data) - 400, len(data)))] = int(rng.integers(0, 256))
+        try:
+            b = ob.ArrowReaderBuilder.try_new(bytes(data))
+            b.schema()
+            ob.DecodeJob([bytes(data)]).plan()  # host planning walks stripe footers, streams and row indexes
+        except ob.OrcError:
+            pass
