@@ -471,7 +471,11 @@ class OracleFile:
                 _check(lib().orc_oracle_timestamp(_u8p(d), _u8p(sec), ctypes.c_size_t(nn), ctypes.c_int64(base),
                                                   ctypes.c_int64(unit_ns), _u8p(o)), "timestamp")
                 if moved:
-                    o = _tz_to_utc(o, zone, unit_ns)
+                    # a value the move pushes out of the unit's range becomes a null (try_unary, then unary_opt:
+                    # array_decoder/timestamp.rs:277-283)
+                    o, over = _tz_to_utc(o, zone, unit_ns)
+                    if over.any():
+                        return ("prim", o, over)
             payload = ("prim", o)
         else:
             raise NotImplementedError(f"ORC type kind {k}")
@@ -518,7 +522,16 @@ class OracleFile:
                 kids.append(self._decode_node(smap, encodings, tz, c, n, cp.astype(np.uint8), "", ts_unit))
             node["children"] = kids
         else:
-            node["payload"] = self._decode_leaf(smap, encodings, tz, cid, nn, name, ts_unit)
+            payload = self._decode_leaf(smap, encodings, tz, cid, nn, name, ts_unit)
+            if payload[0] == "prim" and len(payload) == 3:
+                # dense values that turned into nulls (writer-zone move out of range): out of the validity they go
+                over = payload[2]
+                present = np.ones(n, dtype=np.uint8) if present is None else present.copy()
+                idx = np.flatnonzero(present)
+                present[idx[over]] = 0
+                payload = ("prim", payload[1][~over])
+                node["present"] = present
+            node["payload"] = payload
             node["rows"] = _to_rows(present, node["payload"], n)
         return node
 
@@ -1116,7 +1129,15 @@ def _tz_to_utc(vals: np.ndarray, zone, unit_ns: int) -> np.ndarray:
     offs = np.empty(uniq.size, dtype=np.int64)
     for i, sv in enumerate(uniq.tolist()):
         offs[i] = int((epoch + _dt.timedelta(seconds=sv)).astimezone(zone).utcoffset().total_seconds())
-    return vals + offs[inv] * per_s
+    with np.errstate(over="ignore"):
+        out = vals + offs[inv] * per_s  # wraps where the sum leaves i64: those values become nulls (caller)
+    over = np.zeros(vals.size, dtype=bool)
+    sus = np.flatnonzero((np.abs(vals.astype(np.float64)) > 9.2e18))  # only values near the ends of i64 can overflow
+    for i in sus.tolist():
+        w = int(vals[i]) + int(offs[inv[i]]) * per_s
+        over[i] = not (-(1 << 63) <= w < (1 << 63))
+    out[over] = 0
+    return out, over
 
 
 def _to_rows(present, payload, n):

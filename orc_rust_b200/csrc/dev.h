@@ -150,6 +150,9 @@ struct TsDesc {
     int32_t tz_first;    // offset before the first transition
     uint32_t tz_on;
     uint32_t pad;
+    // A value the zone move pushes out of i64 becomes NULL (try_unary -> unary_opt, array_decoder/timestamp.rs:277-283):
+    // bit i of this zero-initialised bitmap (dense domain) is raised and 0 stored; 0 = report an error instead
+    uint64_t tznull;
 };
 
 // string column of one stripe
@@ -188,7 +191,8 @@ constexpr uint32_t U8_TILE = 16384;
 
 // stripe-level bitmap -> per-batch bitmaps (+ null counts)
 struct RepackDesc {
-    uint64_t src;
+    uint64_t src;        // stripe-level bitmap; 0 = every row valid
+    uint64_t mask;       // optional: rows whose bit is set here are nulls whatever `src` says (zone-move overflow)
     uint64_t dst;        // batch b at dst + b * dst_stride
     uint32_t dst_stride; // bytes
     uint32_t n_rows;

@@ -258,7 +258,7 @@ void Job::stage() {
     for (auto& d : unions_) { R(d.tags); R(d.valid); R(d.bits); }
     for (auto& d : decfix_) { R(d.vals); R(d.scales); }
     for (auto& d : ts_) {
-        R(d.secs); R(d.nanos); R(d.out);
+        R(d.secs); R(d.nanos); R(d.out); R(d.tznull);
         if (d.tz_on) {
             d.tz_at = (uint64_t)(uintptr_t)(d_desc_ + o_tz_ + d.tz_at);
             d.tz_off = (uint64_t)(uintptr_t)(d_desc_ + o_tz_ + d.tz_off);
@@ -269,7 +269,7 @@ void Job::stage() {
         R(c.u8_src); R(c.u8_bad); R(c.u8_flags);
         c.batch_base = (uint64_t)(uintptr_t)(d_meta_ + o_bbase_ + c.batch_base);
     }
-    for (auto& d : repacks_) { R(d.src); R(d.dst); }
+    for (auto& d : repacks_) { R(d.src); R(d.mask); R(d.dst); }
     for (auto& c : chunks_) { R(c.src); R(c.dst); }
 
     desc_blob_.assign(std::max<uint64_t>(desc_bytes_, 256), 0);

@@ -550,9 +550,14 @@ __global__ void __launch_bounds__(256) k_timestamp(const TsDesc* __restrict__ de
                 }
                 const int64_t off = lo == 0 ? (int64_t)d.tz_first : (int64_t)((const int32_t*)d.tz_off)[lo - 1];
                 const __int128 w = (__int128)v + (__int128)off * per_s;
-                // the reference turns an unrepresentable nanosecond value into a null; not reproduced
-                if (w > (__int128)INT64_MAX || w < (__int128)INT64_MIN) set_err(err, d.colstripe, ORCB_NOT_IMPLEMENTED);
-                v = (int64_t)w;
+                if (w > (__int128)INT64_MAX || w < (__int128)INT64_MIN) {
+                    // out of the unit's range: the reference makes the value a null (timestamp.rs:277-283)
+                    if (d.tznull) atomicOr((uint32_t*)d.tznull + (i >> 5), 1u << (i & 31));
+                    else set_err(err, d.colstripe, ORCB_NOT_IMPLEMENTED);
+                    v = 0;
+                } else {
+                    v = (int64_t)w;
+                }
             }
             ((int64_t*)d.out)[i] = v;
         }
@@ -578,11 +583,13 @@ __global__ void __launch_bounds__(128) k_repack(const RepackDesc* __restrict__ d
     const uint32_t row0 = b * d.batch_size;
     const uint32_t rows = min(d.batch_size, d.n_rows - row0);
     const uint32_t* src = (const uint32_t*)d.src;
+    const uint32_t* mask = (const uint32_t*)d.mask;
     uint32_t* dst = (uint32_t*)((uint8_t*)d.dst + (uint64_t)b * d.dst_stride);
     const uint32_t nwords = (rows + 31) >> 5;
     uint32_t pc = 0;
     for (uint32_t w = lane; w < nwords; w += 32) {
-        uint32_t v = load_bits32(src, (uint64_t)row0 + (uint64_t)w * 32);
+        uint32_t v = src ? load_bits32(src, (uint64_t)row0 + (uint64_t)w * 32) : 0xffffffffu;
+        if (mask) v &= ~load_bits32(mask, (uint64_t)row0 + (uint64_t)w * 32);
         const uint32_t rem = rows - w * 32;
         if (rem < 32) v &= (1u << rem) - 1;
         dst[w] = v;

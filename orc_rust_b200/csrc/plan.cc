@@ -485,6 +485,7 @@ void Job::plan_stripe(uint32_t task_idx) {
         uint32_t cnt_base = 0;
         uint64_t valid_raw = 0;
         uint32_t chk_prev_present = 0;
+        int32_t validity_repack = -1;  // index of the RepackDesc that builds this column's per-batch validity
         if (has_present) {
             cnt_base = n_cnt_;
             n_cnt_ += n_groups + 1;
@@ -580,6 +581,7 @@ void Job::plan_stripe(uint32_t task_idx) {
             rp.null_out = (int32_t)cp.nulls_idx;
             rp.batch0 = repack_work_;
             repack_work_ += n_batches;
+            validity_repack = (int32_t)repacks_.size();
             repacks_.push_back(rp);
             n_segments_ += n_groups;
             ab_present_ += (has_parent ? 0 : s_present.len) + (uint64_t)n_rows / 8;
@@ -987,6 +989,36 @@ void Job::plan_stripe(uint32_t task_idx) {
                     td.tz_off = tzt[1];
                     td.tz_n = (uint32_t)tzt[2];
                     td.tz_first = (int32_t)(uint32_t)(tzt[3] >> 32);
+                }
+                if (tz_on && !oc.ts_decimal) {
+                    // values the zone move pushes out of range become nulls: marked in the dense domain, carried to the
+                    // rows like any dense value, and taken out of the validity when it is cut into batches
+                    const uint64_t bm = ((uint64_t)n_rows + 31) / 32 * 4 + 16;
+                    td.tznull = alloc(AR_ZERO, bm);
+                    uint64_t null_rows = td.tznull;
+                    if (has_present) {
+                        null_rows = alloc(AR_ZERO, bm);
+                        add_spaced(td.tznull, null_rows, 0, true);
+                        repacks_[validity_repack].mask = null_rows;
+                    } else {
+                        cp.has_present = true;  // (for export: a validity buffer exists, attached where a batch has nulls)
+                        cp.validity_stride = (uint32_t)align_up((bs + 7) / 8, 64);
+                        cp.validity = alloc(AR_OUT, (uint64_t)cp.validity_stride * n_batches);
+                        cp.nulls_idx = n_nulls_;
+                        n_nulls_ += n_batches;
+                        RepackDesc rp{};
+                        rp.src = 0;
+                        rp.mask = null_rows;
+                        rp.dst = cp.validity;
+                        rp.dst_stride = cp.validity_stride;
+                        rp.n_rows = n_rows;
+                        rp.batch_size = bs;
+                        rp.n_batches = n_batches;
+                        rp.null_out = (int32_t)cp.nulls_idx;
+                        rp.batch0 = repack_work_;
+                        repack_work_ += n_batches;
+                        repacks_.push_back(rp);
+                    }
                 }
                 ts_.push_back(td);
                 ab_ts_ += (uint64_t)n_rows * (16 + tw);

@@ -674,6 +674,22 @@ def test_builder_options(ob, tmp_path):
         ob.ArrowReaderBuilder.try_new(pdata).with_schema(pa.schema([("timestamp_notz", pa.timestamp("ns")),
                                                                    ("timestamp_utc", pa.timestamp("ns", tz="Europe/Paris"))])).build()
     assert ei.value.variant == "UnsupportedTypeVariant"
+    # a value the zone move pushes out of i64 nanoseconds becomes a NULL (try_unary -> unary_opt, timestamp.rs:277-283):
+    # CET in April 2262 is one hour further from UTC than at the ORC epoch, so the last hour before i64::MAX overflows
+    mx, hour = (1 << 63) - 1, 3_600_000_000_000
+    edge = [mx - 5, mx - hour + 1, mx - hour - 1, 0, None, 1_000_000_000, mx - 2 * hour, None, 5, mx - hour + 10**9]
+    et = pa.table({"t": pa.array(edge * 900, pa.timestamp("ns")),
+                   "u": pa.array([v for v in edge if v is not None] * 1125, pa.timestamp("ns"))})
+    ep = gen_orc.write(et, str(tmp_path / "tz_edge.orc"), row_index_stride=1000)
+    e0 = open(ep, "rb").read()
+    for zone in (b"GMT", b"CET"):
+        edata = e0.replace(b"GMT", zone)
+        exp = oo.OracleFile(edata).read()
+        nulls = sum(b.column(1).null_count for b in exp)
+        assert (nulls > 0) == (zone == b"CET")  # `u` has no PRESENT stream: its nulls come from the move alone
+        for use_index in (True, False):
+            got = list(ob.ArrowReaderBuilder.try_new(edata).with_row_index(use_index).build())
+            assert_batches_identical(got, exp, f"zone-move nulls {zone} index={use_index}")
     # and the zone really moved the values
     a = list(ob.ArrowReaderBuilder.try_new(z0.replace(b"GMT", b"CET")).build())[0].column(0)
     b = list(ob.ArrowReaderBuilder.try_new(z0).build())[0].column(0)
