@@ -482,7 +482,7 @@ def main():
     ap.add_argument("--no-configs", action="store_true", help="skip the configs array (1, 2, 3, 4)")
     ap.add_argument("--no-readers", action="store_true", help="skip the ArrowReader end-to-end figures")
     ap.add_argument("--waves", type=int, default=0, help="stripe waves per DecodeJob (0 = library default)")
-    ap.add_argument("--group-streams", type=int, default=2, help="launch groups in flight")
+    ap.add_argument("--group-streams", type=int, default=3, help="launch groups in flight")
     ap.add_argument("--reader-threads", type=int, default=4)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

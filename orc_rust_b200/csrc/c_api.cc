@@ -727,11 +727,11 @@ int orcb_job_new(OrcbFile* const* files, uint32_t n_files, const OrcbReadOptions
         std::vector<StripeTask> tasks = job_tasks(files, n_files, o);
         auto j = std::make_unique<OrcbJob>();
         j->device = o.device;
-        // waves: the caller's number, else ORCB_WAVES, else one per ~24 stripes up to 4
+        // waves: the caller's number, else ORCB_WAVES, else one per ~48 stripes up to 2 (more measured slower)
         uint32_t waves = o.waves;
         if (!waves)
             if (const char* e = getenv("ORCB_WAVES")) waves = (uint32_t)atoi(e);
-        if (!waves) waves = (uint32_t)std::min<size_t>(4, (tasks.size() + 23) / 24);
+        if (!waves) waves = (uint32_t)std::min<size_t>(2, (tasks.size() + 47) / 48);
         waves = std::max<uint32_t>(1, std::min<uint32_t>(waves, (uint32_t)std::max<size_t>(tasks.size(), 1)));
         if (waves > 1) {
             j->has_user_stream = !o.own_stream;
