@@ -72,7 +72,7 @@ def _config(args):
         "workload": (f"lineitem SF{rows / SF10_ROWS * 10:.3g}-shaped ORC: SF{args.rows / SF10_ROWS * 10:g} set "
                      f"({args.rows} rows, {args.files} files, 64 MiB stripes) tiled {args.tiles}x = {rows} rows; "
                      f"compression {args.compression}; RLEv2 + dictionary strings + decimal128(15,2) + date32; "
-                     f"stripe i -> GPU i % N, launch groups of <= {GROUP_STRIPES} stripes"),
+                     f"stripe i -> GPU i % N, launch groups of <= {args.group_stripes} stripes"),
         "batch_size": 8192, "rows": rows, "tiles": args.tiles, "files_per_tile": args.files,
         "compression": args.compression, "row_index": not args.no_row_index,
         "l2_policy": "inputs+outputs per launch group (>= 13 GB) far exceed the 126 MB L2",
@@ -484,6 +484,7 @@ def main():
     ap.add_argument("--waves", type=int, default=0, help="stripe waves per DecodeJob (0 = library default)")
     ap.add_argument("--group-streams", type=int, default=3, help="launch groups in flight")
     ap.add_argument("--reader-threads", type=int, default=4)
+    ap.add_argument("--group-stripes", type=int, default=GROUP_STRIPES, help="stripes per launch group and rank")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -540,7 +541,7 @@ def main():
     t_open = time.time()
     base = [ob._File(f) for f in files]   # one pinned host copy per file and rank
     stripes_per_tile = sum(f.num_stripes for f in base)
-    tiles_per_group = max(1, min(args.tiles, (GROUP_STRIPES * world) // max(stripes_per_tile, 1)))
+    tiles_per_group = max(1, min(args.tiles, (args.group_stripes * world) // max(stripes_per_tile, 1)))
     tiles = [base] + [[f.clone() for f in base] for _ in range(args.tiles - 1)]
     groups = []
     for t0 in range(0, args.tiles, tiles_per_group):

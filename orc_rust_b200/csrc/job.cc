@@ -174,8 +174,6 @@ Job::~Job() {
     if (staged_) {
         if (stream_) cudaStreamSynchronize(stream_);
         if (aux_stream_) cudaStreamSynchronize(aux_stream_);
-        if (walk_stream_) cudaStreamSynchronize(walk_stream_);
-        if (bg_stream_) cudaStreamSynchronize(bg_stream_);
     }
     for (auto& k : kstats_) {
         if (k.e0) cudaEventDestroy(k.e0);
@@ -186,10 +184,6 @@ Job::~Job() {
     if (ev_fork_) cudaEventDestroy(ev_fork_);
     if (ev_join_) cudaEventDestroy(ev_join_);
     if (aux_stream_) cudaStreamDestroy(aux_stream_);
-    if (walk_stream_) cudaStreamDestroy(walk_stream_);
-    if (ev_walk_) cudaEventDestroy(ev_walk_);
-    if (bg_stream_) cudaStreamDestroy(bg_stream_);
-    if (ev_bg_) cudaEventDestroy(ev_bg_);
     if (own_stream_ && stream_) cudaStreamDestroy(stream_);
     // device arenas are released by dev_keepalive_ (shared with exported device batches)
 }
@@ -233,20 +227,15 @@ void Job::stage() {
     CUDA_OK(cudaEventCreateWithFlags(&done_, cudaEventDisableTiming));
     {
         // The header walk is a latency-bound chain at the head of the integer path: on a stream of higher priority its
-        // few warps are placed as soon as they are launched, whatever else is queued.  ORCB_AUX_PRIO: 0 = no priorities,
-        // 1 = walk and run decode both on the high-priority stream (default), 2 = only the walk
-        static const int mode = getenv("ORCB_AUX_PRIO") ? atoi(getenv("ORCB_AUX_PRIO")) : 1;
+        // few warps (and the run decode that follows) are placed as soon as they are launched, whatever else is queued:
+        // 6.98 -> 6.68 ms at SF10 (ORCB_AUX_PRIO=0: no priority).  Tried and dropped: the walk alone at high priority
+        // (7.14 ms), the decimal varint decoder on a third, low-priority stream (7.10 vs 6.91 ms).
+        static const bool prio = !(getenv("ORCB_AUX_PRIO") && getenv("ORCB_AUX_PRIO")[0] == '0');
         int least = 0, greatest = 0;
-        const bool can = cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess && greatest != least;
-        if (mode == 1 && can) CUDA_OK(cudaStreamCreateWithPriority(&aux_stream_, cudaStreamNonBlocking, greatest));
-        else CUDA_OK(cudaStreamCreateWithFlags(&aux_stream_, cudaStreamNonBlocking));
-        if (mode == 2 && can) {
-            CUDA_OK(cudaStreamCreateWithPriority(&walk_stream_, cudaStreamNonBlocking, greatest));
-            CUDA_OK(cudaEventCreateWithFlags(&ev_walk_, cudaEventDisableTiming));
-        }
-        if (can) CUDA_OK(cudaStreamCreateWithPriority(&bg_stream_, cudaStreamNonBlocking, least));
-        else CUDA_OK(cudaStreamCreateWithFlags(&bg_stream_, cudaStreamNonBlocking));
-        CUDA_OK(cudaEventCreateWithFlags(&ev_bg_, cudaEventDisableTiming));
+        if (prio && cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess && greatest != least)
+            CUDA_OK(cudaStreamCreateWithPriority(&aux_stream_, cudaStreamNonBlocking, greatest));
+        else
+            CUDA_OK(cudaStreamCreateWithFlags(&aux_stream_, cudaStreamNonBlocking));
     }
     CUDA_OK(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming));
@@ -405,17 +394,7 @@ void Job::launch() {
         RunRec* rtab = (RunRec*)(uintptr_t)reloc(run_table_);
         BlockRec* brec = (BlockRec*)(uintptr_t)reloc(block_recs_);
         uint32_t* nblk = (uint32_t*)(d_state_ + o_nblocks_);
-        cudaStream_t wst = (walk_stream_ && !serial_env) ? walk_stream_ : aux;
-        if (wst != aux) {
-            CUDA_OK(cudaStreamWaitEvent(wst, ev_fork_, 0));
-            cur_st = wst;
-        }
-        run("k_rle_index", 0, N(int_segs_), 1, [&] { return launch_rle_index((Seg*)(d_desc_ + o_int_), N(int_segs_), cnt, rtab, brec, nblk, pool_blocks_, (CoopRec*)(uintptr_t)reloc(coop_q_), nblk + 2, coop_cap_, err, segchk, wst); });
-        if (wst != aux) {
-            CUDA_OK(cudaEventRecord(ev_walk_, wst));
-            CUDA_OK(cudaStreamWaitEvent(aux, ev_walk_, 0));
-            cur_st = aux;
-        }
+        run("k_rle_index", 0, N(int_segs_), 1, [&] { return launch_rle_index((Seg*)(d_desc_ + o_int_), N(int_segs_), cnt, rtab, brec, nblk, pool_blocks_, (CoopRec*)(uintptr_t)reloc(coop_q_), nblk + 2, coop_cap_, err, segchk, aux); });
         run("k_int_rle(+general,+coop_runs)", ab_int_, pool_blocks_, 3, [&] { return launch_int_rle((Seg*)(d_desc_ + o_int_), brec, nblk, pool_blocks_, rtab, cnt, dstart, err, mis, (uint32_t*)(uintptr_t)reloc(slow_list_), nblk + 1, (CoopRec*)(uintptr_t)reloc(coop_q_), nblk + 2, coop_cap_, aux); });
         if (!serial_env) CUDA_OK(cudaEventRecord(ev_join_, aux));
         cur_st = st;
@@ -424,40 +403,24 @@ void Job::launch() {
     // the issue slots to the latency-bound header walk), then the issue-bound decoders
     if (N(u8_tiles_))
         run("k_utf8", ab_utf8_, N(u8_tiles_), 1, [&] { return launch_utf8((StrCol*)(d_desc_ + o_str_), (uint2*)(d_desc_ + o_u8tile_), N(u8_tiles_), st); });
-    // The decimal varint decoder depends on nothing else and nothing but the decimal epilogue depends on it.  ORCB_BG=1
-    // runs it on a third, low-priority stream to fill whatever issue slots the two chains leave; measured slower
-    // (7.10 vs 6.91 ms at SF10: the main stream then has nothing to run beside the walk), so it stays an experiment.
-    static const bool bg_on = getenv("ORCB_BG") && getenv("ORCB_BG")[0] == '1';
-    const bool bg = bg_on && !serial_env && bg_stream_ && N(var_segs_);
-    auto varint = [&](cudaStream_t vs) {
-        cur_st = vs;
-        run("k_varint128", ab_var_, N(var_segs_), 1, [&] { return launch_varint128((Seg*)(d_desc_ + o_var_), N(var_segs_), cnt, dstart, err, segchk, vs); });
-        cur_st = st;
-    };
-    if (bg) {
-        if (!forked) CUDA_OK(cudaEventRecord(ev_fork_, st));
-        CUDA_OK(cudaStreamWaitEvent(bg_stream_, ev_fork_, 0));
-        varint(bg_stream_);
-        CUDA_OK(cudaEventRecord(ev_bg_, bg_stream_));
-    }
     static const char* order_env = getenv("ORCB_MAIN_ORDER");
     const char* order = order_env ? order_env : "kcv";
     for (const char* o = order; *o; o++) {
         if (*o == 'c' && N(int_big_segs_))
             run("k_int_rle_coop", ab_intbig_, N(int_big_segs_), 1, [&] { return launch_int_rle_coop((Seg*)(d_desc_ + o_intbig_), N(int_big_segs_), cnt, dstart, err, mis, 0, segchk, st); });
-        if (*o == 'v' && N(var_segs_) && !bg) varint(st);
+        if (*o == 'v' && N(var_segs_))
+            run("k_varint128", ab_var_, N(var_segs_), 1, [&] { return launch_varint128((Seg*)(d_desc_ + o_var_), N(var_segs_), cnt, dstart, err, segchk, st); });
         if (*o == 'k' && N(copy_tiles_))
             run("k_copy", ab_copy_, N(copy_tiles_), 1, [&] { return launch_copy((CopyDesc*)(d_desc_ + o_copy_), (uint2*)(d_desc_ + o_ctile_), N(copy_tiles_), cnt, err, (StrCol*)(d_desc_ + o_str_), st); });
     }
     if (forked && !serial_env) CUDA_OK(cudaStreamWaitEvent(st, ev_join_, 0));
-    // strings first: they close the longer chain; the decimal epilogue waits for the background stream
+    // strings first: they close the longer chain
     if (N(spaced_))
         run("k_spaced", ab_spaced_, N(spaced_), 1, [&] { return launch_spaced((SpacedDesc*)(d_desc_ + o_sp_), N(spaced_), dstart, st); });
     if (N(unions_))
         run("k_union_valid", 0, N(unions_), 1, [&] { return launch_union_valid((UnionDesc*)(d_desc_ + o_union_), N(unions_), nulls, st); });
     if (N(strcols_))
         run("k_strings(5 kernels)", ab_str_, str_tiles_, 5, [&] { return launch_strings((StrCol*)(d_desc_ + o_str_), N(strcols_), str_tiles_, err, dstate, (uint64_t)(uintptr_t)base_[AR_HEAP], heap_cap, ptrs, st); });
-    if (bg) CUDA_OK(cudaStreamWaitEvent(st, ev_bg_, 0));
     if (N(chk_pairs_))  // every segment has left its start and end position: do they join up?
         run("k_seg_check", 0, N(chk_pairs_), 1, [&] { return launch_seg_check((uint2*)(d_desc_ + o_chkpair_), N(chk_pairs_), segchk, (uint32_t*)(d_meta_ + o_retry_), st); });
     if (N(decfix_) && N(int_big_segs_))  // scales that were only compared so far are written where one of them differed

@@ -250,10 +250,7 @@ class Job {
              ab_spaced_ = 0, ab_dec_ = 0, ab_ts_ = 0, ab_str_ = 0, ab_repack_ = 0;
 
     cudaStream_t aux_stream_ = nullptr;  // latency-bound pre-pass + short-run integer decode overlap the rest
-    cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr, ev_walk_ = nullptr;
-    cudaStream_t bg_stream_ = nullptr;    // independent kernels (decimal varints) at low priority
-    cudaEvent_t ev_bg_ = nullptr;
-    cudaStream_t walk_stream_ = nullptr;  // ORCB_AUX_PRIO=2: the header walk alone on a high-priority stream
+    cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr;
     cudaStream_t stream_ = nullptr;
     bool own_stream_ = false;
     cudaEvent_t done_ = nullptr;
