@@ -309,6 +309,13 @@ int orcb_decode_varint128(int device, const uint8_t* in, size_t in_len, uint8_t*
 int orcb_decompress_stream(int device, int compression_kind, const uint8_t* in, size_t in_len, size_t block_size,
                            uint8_t* out, size_t out_cap, size_t* out_len);
 
+/* The host decoder of METADATA sections (postscript-described footer, stripe footers, row indexes: parsed on the host
+ * like the reference does, src/reader/metadata.rs:238-263, src/stripe.rs:215-244), exposed so that it can be tested
+ * without a GPU.  Data streams never go through it.  *out_len receives the size; ORCB_INVALID_ARGUMENT when out_cap is
+ * too small. */
+int orcb_host_decompress_section(int compression_kind, const uint8_t* in, size_t in_len, size_t block_size, uint8_t* out,
+                                 size_t out_cap, size_t* out_len);
+
 /* Jobs of this process that were decoded a second time without the row index because a (stream, row group) segment did
  * not end where the index says the next one starts (damaged stream or index).  0 on well-formed files. */
 uint64_t orcb_index_retries(void);

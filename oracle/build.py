@@ -14,7 +14,7 @@ def build(force: bool = False) -> str:
     os.makedirs(OUT_DIR, exist_ok=True)
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= os.path.getmtime(src):
         return LIB
-    cmd = ["gcc", "-O2", "-std=gnu11", "-shared", "-fPIC", "-Wall", "-o", LIB, src, "-lz"]
+    cmd = ["gcc", "-O2", "-std=gnu11", "-shared", "-fPIC", "-Wall", "-o", LIB, src, "-lz", "-ldl"]
     subprocess.check_call(cmd)
     return LIB
 

@@ -19,6 +19,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include <zlib.h>
+#include <dlfcn.h>
 
 #define ORC_OK 0
 #define ERR_IO 1
@@ -688,6 +689,117 @@ static int64_t zlib_block(const uint8_t *s, size_t n, uint8_t *d, size_t cap) {
     return produced;
 }
 
+/* Zstandard (zstd 0.13 crate = libzstd, `zstd::Decoder` + read_to_end, compression.rs:151-159): the system's libzstd,
+ * loaded at run time (the image ships libzstd.so.1 without headers).  ZSTD_decompress handles concatenated and
+ * skippable frames like the streaming decoder does.  Decode errors surface from read_to_end: IoError. */
+static int64_t zstd_block(const uint8_t *s, size_t n, uint8_t *d, size_t cap) {
+    typedef size_t (*dec_fn)(void *, size_t, const void *, size_t);
+    typedef unsigned (*err_fn)(size_t);
+    static dec_fn dec;
+    static err_fn is_err;
+    static int tried;
+    if (!tried) {
+        void *h = dlopen("libzstd.so.1", RTLD_NOW);
+        if (h) {
+            dec = (dec_fn)dlsym(h, "ZSTD_decompress");
+            is_err = (err_fn)dlsym(h, "ZSTD_isError");
+        }
+        tried = 1;
+    }
+    if (!dec || !is_err) return -ERR_BUILD_ZSTD; /* no libzstd on this machine */
+    if (n == 0) return 0;
+    size_t r = dec(d, cap, s, n);
+    if (is_err(r)) return -ERR_IO;
+    return (int64_t)r;
+}
+
+/* LZO1X (lzokay-native 0.1 `decompress_all`, call site compression.rs:174-183; the published LZO1X stream format:
+ * first byte > 17 = literal run of byte-17; then instructions M1 (0..15, meaning depends on how many literals the
+ * previous instruction copied), M2 (>= 64), M3 (32..63), M4 (16..31, distance 16384 = end of stream). */
+static int64_t lzo_block(const uint8_t *s, size_t n, uint8_t *d, size_t cap) {
+    size_t ip = 0, op = 0;
+    unsigned state = 0; /* literals copied by the previous instruction: 0..3, or 4 after a run */
+    if (n == 0) return -ERR_BUILD_LZO;
+    if (s[0] > 17) {
+        size_t len = (size_t)s[0] - 17;
+        ip = 1;
+        if (ip + len > n || op + len > cap) return -ERR_BUILD_LZO;
+        memcpy(d + op, s + ip, len);
+        ip += len;
+        op += len;
+        state = len < 4 ? (unsigned)len : 4;
+    }
+    for (;;) {
+        if (ip >= n) return -ERR_BUILD_LZO;
+        unsigned inst = s[ip++];
+        size_t mlen, mdist;
+        unsigned trail;
+        if (inst >= 64) {
+            if (ip >= n) return -ERR_BUILD_LZO;
+            mlen = (inst >> 5) + 1;
+            mdist = ((size_t)s[ip++] << 3) + ((inst >> 2) & 7) + 1;
+            trail = inst & 3;
+        } else if (inst >= 32) {
+            mlen = inst & 31;
+            if (mlen == 0) {
+                while (ip < n && s[ip] == 0) { mlen += 255; ip++; }
+                if (ip >= n) return -ERR_BUILD_LZO;
+                mlen += 31 + s[ip++];
+            }
+            mlen += 2;
+            if (ip + 2 > n) return -ERR_BUILD_LZO;
+            unsigned v = s[ip] | ((unsigned)s[ip + 1] << 8);
+            ip += 2;
+            mdist = (v >> 2) + 1;
+            trail = v & 3;
+        } else if (inst >= 16) {
+            mlen = inst & 7;
+            if (mlen == 0) {
+                while (ip < n && s[ip] == 0) { mlen += 255; ip++; }
+                if (ip >= n) return -ERR_BUILD_LZO;
+                mlen += 7 + s[ip++];
+            }
+            mlen += 2;
+            if (ip + 2 > n) return -ERR_BUILD_LZO;
+            unsigned v = s[ip] | ((unsigned)s[ip + 1] << 8);
+            ip += 2;
+            mdist = 16384 + ((size_t)(inst & 8) << 11) + (v >> 2);
+            trail = v & 3;
+            if (mdist == 16384) {
+                if (mlen != 3) return -ERR_BUILD_LZO;
+                if (ip != n) return -ERR_BUILD_LZO; /* InputNotConsumed */
+                return (int64_t)op;
+            }
+        } else if (state == 0) {
+            size_t len = inst;
+            if (len == 0) {
+                while (ip < n && s[ip] == 0) { len += 255; ip++; }
+                if (ip >= n) return -ERR_BUILD_LZO;
+                len += 15 + s[ip++];
+            }
+            len += 3;
+            if (ip + len > n || op + len > cap) return -ERR_BUILD_LZO;
+            memcpy(d + op, s + ip, len);
+            ip += len;
+            op += len;
+            state = 4;
+            continue;
+        } else {
+            if (ip >= n) return -ERR_BUILD_LZO;
+            unsigned h = s[ip++];
+            if (state == 4) { mdist = ((size_t)h << 2) + (inst >> 2) + 2049; mlen = 3; }
+            else { mdist = ((size_t)h << 2) + (inst >> 2) + 1; mlen = 2; }
+            trail = inst & 3;
+        }
+        if (mdist > op || op + mlen > cap) return -ERR_BUILD_LZO;
+        for (size_t i = 0; i < mlen; i++) d[op + i] = d[op + i - mdist];
+        op += mlen;
+        if (ip + trail > n || op + trail > cap) return -ERR_BUILD_LZO;
+        for (unsigned i = 0; i < trail; i++) d[op++] = s[ip++];
+        state = trail;
+    }
+}
+
 /* Decompressor (compression.rs:244-347): concatenate all chunks of a stream.
  * kind: 0 NONE 1 ZLIB 2 SNAPPY 3 LZO 4 LZ4 5 ZSTD.  Returns output length or -(error code).
  * stats (optional): [0] chunks, [1] compressed chunks. */
@@ -718,8 +830,8 @@ int64_t orc_oracle_decompress_stream(int kind, const uint8_t *in, size_t in_len,
             if (kind == 2) r = snappy_block(in + p, len, out + o, room);
             else if (kind == 4) r = lz4_block(in + p, len, out + o, room < block_size ? room : block_size);
             else if (kind == 1) r = zlib_block(in + p, len, out + o, room);
-            else if (kind == 3) r = -ERR_BUILD_LZO;
-            else r = -ERR_BUILD_ZSTD;
+            else if (kind == 3) r = lzo_block(in + p, len, out + o, room);
+            else r = zstd_block(in + p, len, out + o, room);
             if (r < 0) return r;
             o += (size_t)r;
         }

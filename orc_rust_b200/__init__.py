@@ -111,7 +111,7 @@ EXPORTED_SYMBOLS = [
     "orcb_reader_next_device", "orcb_reader_next_async", "orcb_reader_drain", "orcb_job_new", "orcb_job_free", "orcb_job_plan", "orcb_job_stage",
     "orcb_job_launch", "orcb_job_finish", "orcb_job_stats", "orcb_job_restage", "orcb_job_kernel_stats", "orcb_job_num_batches", "orcb_job_export_batch",
     "orcb_job_export_batch_device", "orcb_decode_int_rle", "orcb_decode_byte_rle", "orcb_decode_bool_rle",
-    "orcb_decode_varint128", "orcb_decompress_stream", "orcb_last_error", "orcb_index_retries", "orcb_build_info",
+    "orcb_decode_varint128", "orcb_decompress_stream", "orcb_host_decompress_section", "orcb_last_error", "orcb_index_retries", "orcb_build_info",
     "orcb_device_available",
 ]
 
@@ -887,6 +887,23 @@ def decode_varint128(data: bytes, n: int, device: int = 0):
     buf = ctypes.cast(ctypes.c_char_p(bytes(data)), ctypes.c_void_p)
     _check(lib().orcb_decode_varint128(device, buf, len(data), out.ctypes.data_as(ctypes.c_void_p), n))
     return out
+
+
+def host_decompress_section(kind: int, data: bytes, block_size: int) -> bytes:
+    """The host decoder of metadata sections (footers, row indexes); works without a GPU.  Data streams never use it."""
+    import numpy as np
+    cap = 1 << 16
+    while True:
+        out = np.empty(cap, dtype=np.uint8)
+        out_len = ctypes.c_size_t(0)
+        buf = ctypes.cast(ctypes.c_char_p(bytes(data)), ctypes.c_void_p)
+        rc = lib().orcb_host_decompress_section(kind, buf, len(data), block_size, out.ctypes.data_as(ctypes.c_void_p), cap,
+                                                ctypes.byref(out_len))
+        if rc == 21 and out_len.value > cap:
+            cap = out_len.value
+            continue
+        _check(rc)
+        return out[: out_len.value].tobytes()
 
 
 def decompress_stream(kind: int, data: bytes, block_size: int, device: int = 0) -> bytes:

@@ -998,11 +998,20 @@ int orcb_decode_varint128(int device, const uint8_t* in, size_t in_len, uint8_t*
     });
 }
 
+int orcb_host_decompress_section(int compression_kind, const uint8_t* in, size_t in_len, size_t block_size, uint8_t* out,
+                                 size_t out_cap, size_t* out_len) {
+    return guarded([&] {
+        std::vector<uint8_t> v = host_decompress_section(compression_kind, block_size, in, in_len);
+        *out_len = v.size();
+        if (v.size() > out_cap) fail(ORCB_INVALID_ARGUMENT, "output too small");
+        if (!v.empty()) memcpy(out, v.data(), v.size());
+    });
+}
+
 int orcb_decompress_stream(int device, int compression_kind, const uint8_t* in, size_t in_len, size_t block_size,
                            uint8_t* out, size_t out_cap, size_t* out_len) {
     return guarded([&] {
-        if (compression_kind != C_NONE && compression_kind != C_SNAPPY && compression_kind != C_LZ4 && compression_kind != C_ZLIB)
-            fail(ORCB_UNSUPPORTED_DEVICE_CODEC, "Zstd/LZO are not supported on the device path");
+        if (compression_kind < C_NONE || compression_kind > C_ZSTD) fail(ORCB_INVALID_ARGUMENT, "unknown compression kind");
         if (compression_kind == C_NONE) {
             if (in_len > out_cap) fail(ORCB_INVALID_ARGUMENT, "output too small");
             memcpy(out, in, in_len);

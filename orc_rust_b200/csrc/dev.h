@@ -209,7 +209,7 @@ struct ChunkDesc {
     uint32_t src_len;
     uint32_t dst_cap;    // bytes this chunk may produce (exact when known, else block size)
     int32_t expect_len;  // >= 0: decompressed size must equal this (layout was planned on it)
-    uint8_t codec;       // 0 original (copy), 1 zlib, 2 snappy, 4 lz4
+    uint8_t codec;       // 0 original (copy), 1 zlib, 2 snappy, 3 lzo, 4 lz4, 5 zstd
     uint8_t assumed;     // expect_len is the planner's assumption (a non-final chunk fills the block), not a known size:
                          // a different size asks for a re-plan with the sizes found instead of being an error
     uint8_t pad[2];

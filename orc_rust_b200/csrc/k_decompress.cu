@@ -1,5 +1,6 @@
 // Compression chunks: original copies, Snappy and LZ4 block decoding.
 #include "kernel_util.cuh"
+#include "zstd_dec.h"
 
 namespace orcb {
 
@@ -946,6 +947,284 @@ __device__ uint32_t inflate_chunk(const uint8_t* __restrict__ s, uint32_t n, uin
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Zstandard frames and LZO1X streams (src/compression.rs:151-159, 174-183).  Both are decoded the way the inflate
+// path is: lane 0 runs the sequential part (zstd_dec.h: headers, FSE / Huffman tables, the sequence bitstream, the LZO
+// instruction bytes) and queues up to 32 (literals, match) tokens, the warp then places them.  Huffman-coded
+// literals of a Zstandard block are decoded first, one lane per stream (a block has 1 or 4), into the END of the
+// chunk's output range: the literals still waiting there always lie at or above the write position (what separates
+// the two is the match bytes the block has yet to produce), so executing the sequences front to back never
+// overwrites a literal before it has been copied down.
+// ------------------------------------------------------------------------------------------------
+struct ZstdWarp {
+    zstd::Tables T;
+    uint32_t tok[32 * 4];  // literal bytes | literal source offset | match bytes | match distance
+};
+static_assert(sizeof(ZstdWarp) <= sizeof(LzWarp), "the Zstandard tables reuse the LZ decoder's shared memory");
+
+// literals: the source is the input, or the tail of the output at or above dst: read a round, then write it
+__device__ __forceinline__ void warp_copy_lit(uint8_t* dst, const uint8_t* src, uint32_t n, int lane) {
+    for (uint32_t i0 = 0; i0 < n; i0 += 128) {
+        uint8_t v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t i = i0 + u * 32 + lane;
+            v[u] = i < n ? src[i] : (uint8_t)0;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t i = i0 + u * 32 + lane;
+            if (i < n) dst[i] = v[u];
+        }
+        __syncwarp();
+    }
+}
+
+// Places `cnt` queued tokens at d + o.  `reserve`: bytes at the end of the output range that must stay untouched
+// (Zstandard literals not yet consumed after this batch).  `win_base`: matches may not reach below this offset.
+// rle >= 0: literals are this byte.  Returns non-zero when the output does not fit or a match is out of range.
+__device__ __forceinline__ uint32_t lz_exec_tokens(uint8_t* d, uint32_t& o, uint32_t cap, uint32_t reserve, uint32_t win_base,
+                                                   const uint32_t* tok, uint32_t cnt, const uint8_t* lit_base, int rle, int lane) {
+    const bool on = (uint32_t)lane < cnt;
+    const uint32_t ll = on ? tok[4 * lane] : 0u, lo = on ? tok[4 * lane + 1] : 0u;
+    const uint32_t ml = on ? tok[4 * lane + 2] : 0u, dist = on ? tok[4 * lane + 3] : 0u;
+    const uint32_t len = ll + ml;
+    const uint32_t incl = warp_incl_scan(len, lane);
+    const uint32_t total = __shfl_sync(FULL, incl, 31);
+    if (total > cap - o || reserve > cap - o - total) return 1;
+    const uint32_t op = o + incl - len;
+    for (uint32_t l = 0; l < cnt; l++) {
+        const uint32_t e_ll = __shfl_sync(FULL, ll, l), e_lo = __shfl_sync(FULL, lo, l), e_ml = __shfl_sync(FULL, ml, l);
+        const uint32_t e_dist = __shfl_sync(FULL, dist, l), e_op = __shfl_sync(FULL, op, l);
+        if (e_ll) {
+            if (rle >= 0) {
+                for (uint32_t i = lane; i < e_ll; i += 32) d[e_op + i] = (uint8_t)rle;
+                __syncwarp();
+            } else {
+                warp_copy_lit(d + e_op, lit_base + e_lo, e_ll, lane);
+            }
+        }
+        if (e_ml) {
+            const uint32_t at = e_op + e_ll;
+            if (e_dist == 0 || e_dist > at - win_base) return 1;
+            warp_copy_match(d, at, e_dist, e_ml, lane);
+            __syncwarp();
+        }
+    }
+    o += total;
+    return 0;
+}
+
+// one Compressed_Block of `size` bytes at b
+__device__ uint32_t zstd_block(const uint8_t* __restrict__ b, uint32_t size, uint8_t* d, uint32_t cap, uint32_t& o, uint32_t win_base,
+                               zstd::FrameState& fs, ZstdWarp& w, int lane) {
+    using namespace zstd;
+    LitHeader lh;
+    uint32_t bad = 0;
+    if (lane == 0) bad = !lit_header(b, size, lh);
+    if (__shfl_sync(FULL, bad, 0)) return 1;
+    lh.type = __shfl_sync(FULL, lh.type, 0);
+    lh.regen = __shfl_sync(FULL, lh.regen, 0);
+    lh.comp = __shfl_sync(FULL, lh.comp, 0);
+    lh.streams = __shfl_sync(FULL, lh.streams, 0);
+    lh.hdr = __shfl_sync(FULL, lh.hdr, 0);
+    if (lh.regen > cap - o) return 1;
+    const uint8_t* lp = b + lh.hdr;
+    const uint8_t* lit_base = lp;
+    int rle = -1;
+    if (lh.type == 1) {
+        rle = lp[0];
+    } else if (lh.type >= 2) {
+        uint32_t used = 0;
+        if (lane == 0) {
+            if (lh.type == 2) bad = !huf_read(lp, lh.comp, w.T, fs.huf_log, used);
+            else bad = fs.huf_log < 0;
+        }
+        if (__shfl_sync(FULL, bad, 0)) return 1;
+        used = __shfl_sync(FULL, used, 0);
+        fs.huf_log = __shfl_sync(FULL, fs.huf_log, 0);
+        __syncwarp();
+        const uint8_t* sp = lp + used;
+        const uint32_t sn = lh.comp - used;
+        uint8_t* area = d + (cap - lh.regen);
+        bool ok = true;
+        if (lh.streams == 1) {
+            if (lane == 0) ok = huf_stream(sp, sn, w.T.huf, fs.huf_log, area, lh.regen);
+        } else {
+            if (sn < 6) return 1;
+            const uint32_t l1 = sp[0] | (sp[1] << 8), l2 = sp[2] | (sp[3] << 8), l3 = sp[4] | (sp[5] << 8);
+            if (6u + l1 + l2 + l3 > sn) return 1;
+            const uint32_t q = (lh.regen + 3) / 4;
+            if (3ull * q > lh.regen) return 1;
+            if (lane < 4) {
+                const uint32_t at = 6 + (lane > 0 ? l1 : 0u) + (lane > 1 ? l2 : 0u) + (lane > 2 ? l3 : 0u);
+                const uint32_t sl = lane == 0 ? l1 : lane == 1 ? l2 : lane == 2 ? l3 : sn - 6 - l1 - l2 - l3;
+                ok = huf_stream(sp + at, sl, w.T.huf, fs.huf_log, area + lane * q, lane < 3 ? q : lh.regen - 3 * q);
+            }
+        }
+        if (!__all_sync(FULL, ok)) return 1;
+        __syncwarp();
+        lit_base = area;
+    }
+    // ---- sequences
+    const uint8_t* sq = b + lh.hdr + lh.comp;
+    const uint32_t sqn = size - lh.hdr - lh.comp;
+    uint32_t nseq = 0, used = 0;
+    SeqReader r;
+    if (lane == 0) {
+        bad = !seq_header(sq, sqn, w.T, fs, nseq, used);
+        if (!bad && nseq) bad = !r.init(sq + used, sqn - used, fs);
+        if (!bad && !nseq && used != sqn) bad = 1;
+    }
+    if (__shfl_sync(FULL, bad, 0)) return 1;
+    nseq = __shfl_sync(FULL, nseq, 0);
+    uint32_t lit_at = 0;  // lane 0 keeps it
+    for (uint32_t s0 = 0; s0 < nseq; s0 += 32) {
+        const uint32_t cnt = min(32u, nseq - s0);
+        if (lane == 0) {
+            for (uint32_t i = 0; i < cnt && !bad; i++) {
+                uint32_t ll, ml, off;
+                if (!r.next(w.T, fs, s0 + i + 1 == nseq, ll, ml, off) || ll > lh.regen - lit_at) {
+                    bad = 1;
+                    break;
+                }
+                w.tok[4 * i] = ll;
+                w.tok[4 * i + 1] = lit_at;
+                w.tok[4 * i + 2] = ml;
+                w.tok[4 * i + 3] = off;
+                lit_at += ll;
+            }
+            if (!bad && s0 + cnt == nseq && r.b.bits != 0) bad = 1;
+        }
+        if (__shfl_sync(FULL, bad, 0)) return 1;
+        const uint32_t reserve = lh.regen - __shfl_sync(FULL, lit_at, 0);
+        __syncwarp();
+        if (lz_exec_tokens(d, o, cap, reserve, win_base, w.tok, cnt, lit_base, rle, lane)) return 1;
+        __syncwarp();
+    }
+    // literals after the last sequence
+    lit_at = __shfl_sync(FULL, lit_at, 0);
+    const uint32_t rest = lh.regen - lit_at;
+    if (rest > cap - o) return 1;
+    if (rest) {
+        if (rle >= 0) {
+            for (uint32_t i = lane; i < rest; i += 32) d[o + i] = (uint8_t)rle;
+            __syncwarp();
+        } else {
+            warp_copy_lit(d + o, lit_base + lit_at, rest, lane);
+        }
+        o += rest;
+    }
+    return 0;
+}
+
+__device__ uint32_t zstd_chunk(const uint8_t* __restrict__ s, uint32_t n, uint8_t* d, uint32_t cap, uint32_t& o_out, ZstdWarp& w, int lane) {
+    using namespace zstd;
+    const uint32_t BAD = ORCB_IO_ERROR;
+    uint32_t p = 0, o = 0;
+    FrameState fs;
+    while (p < n) {
+        FrameHeader fh;
+        uint32_t bad = 0;
+        if (lane == 0) bad = !frame_header(s + p, n - p, fh);
+        if (__shfl_sync(FULL, bad, 0)) return BAD;
+        p += __shfl_sync(FULL, fh.hdr, 0);
+        if (__shfl_sync(FULL, fh.skippable, 0)) continue;
+        const uint32_t csum = __shfl_sync(FULL, fh.checksum, 0);
+        const uint32_t c_lo = __shfl_sync(FULL, (uint32_t)fh.content, 0), c_hi = __shfl_sync(FULL, (uint32_t)(fh.content >> 32), 0);
+        fs.reset();
+        const uint32_t base = o;
+        for (;;) {
+            if (n - p < 3) return BAD;
+            const uint32_t bh = s[p] | ((uint32_t)s[p + 1] << 8) | ((uint32_t)s[p + 2] << 16);
+            p += 3;
+            const uint32_t last = bh & 1, type = (bh >> 1) & 3, size = bh >> 3;
+            if (type == 3) return BAD;
+            if (type == 0) {
+                if (size > n - p || size > cap - o) return BAD;
+                warp_copy_fwd(d + o, s + p, size, lane);
+                __syncwarp();
+                o += size;
+                p += size;
+            } else if (type == 1) {
+                if (p >= n || size > cap - o) return BAD;
+                const uint8_t v = s[p];
+                for (uint32_t i = lane; i < size; i += 32) d[o + i] = v;
+                __syncwarp();
+                o += size;
+                p += 1;
+            } else {
+                if (size > n - p || size > (128u << 10)) return BAD;
+                if (zstd_block(s + p, size, d, cap, o, base, fs, w, lane)) return BAD;
+                p += size;
+            }
+            if (last) break;
+        }
+        if (csum) {
+            if (n - p < 4) return BAD;
+            p += 4;  // content checksum: not verified
+        }
+        if ((c_lo & c_hi) != 0xffffffffu && (c_hi != 0 || o - base != c_lo)) return BAD;
+    }
+    o_out = o;
+    return 0;
+}
+
+__device__ uint32_t lzo_chunk(const uint8_t* __restrict__ s, uint32_t n, uint8_t* d, uint32_t cap, uint32_t& o_out, uint32_t* tok, int lane) {
+    const uint32_t BAD = ORCB_BUILD_LZO_DECODER;
+    uint32_t p = 0, state = 0, o = 0;
+    uint32_t carry_pos = 0, carry_len = 0;  // literals waiting for the match they precede (lane 0)
+    bool first = true, done = false;
+    while (!done) {
+        uint32_t cnt = 0, bad = 0;
+        if (lane == 0) {
+            while (cnt < 32) {
+                lzo::Token t;
+                if (!lzo::next(s, n, p, state, first, t)) {
+                    bad = 1;
+                    break;
+                }
+                first = false;
+                if (t.end || t.m_len == 0) {
+                    // a literal instruction: flush literals already waiting (crafted input only), then wait for the match
+                    if (carry_len && (t.end || t.lit_len)) {
+                        tok[4 * cnt] = carry_len;
+                        tok[4 * cnt + 1] = carry_pos;
+                        tok[4 * cnt + 2] = 0;
+                        tok[4 * cnt + 3] = 0;
+                        cnt++;
+                        carry_len = 0;
+                    }
+                    if (t.end) {
+                        done = true;
+                        if (p != n) bad = 1;  // bytes after the end marker
+                        break;
+                    }
+                    carry_pos = t.lit_pos;
+                    carry_len = t.lit_len;
+                    continue;
+                }
+                tok[4 * cnt] = carry_len;
+                tok[4 * cnt + 1] = carry_pos;
+                tok[4 * cnt + 2] = t.m_len;
+                tok[4 * cnt + 3] = t.m_dist;
+                cnt++;
+                carry_pos = t.lit_pos;
+                carry_len = t.lit_len;
+            }
+        }
+        if (__shfl_sync(FULL, bad, 0)) return BAD;
+        cnt = __shfl_sync(FULL, cnt, 0);
+        done = __shfl_sync(FULL, (int)done, 0);
+        __syncwarp();
+        if (lz_exec_tokens(d, o, cap, 0, 0, tok, cnt, s, -1, lane)) return BAD;
+        __syncwarp();
+    }
+    o_out = o;
+    return 0;
+}
+
 // Persistent warps over the chunk list (most expensive chunks first, see plan.cc); one chunk per warp at a time.
 __global__ void __launch_bounds__(128, ORCB_LZ_CTAS) k_decompress(const ChunkDesc* __restrict__ chunks, uint32_t nchunks, uint32_t* err,
                                                        uint32_t* out_lens, uint32_t* counter, uint32_t* retry) {
@@ -977,6 +1256,14 @@ __global__ void __launch_bounds__(128, ORCB_LZ_CTAS) k_decompress(const ChunkDes
             if (!fail) fail = lz_chunk<2>(s, n, d, ulen, p, o, sm, lut, lane);
         } else if (c.codec == 1) {
             fail = inflate_chunk(s, n, d, c.dst_cap, o, *(InfWarp*)&sm, lane);
+            if (c.expect_len < 0 && !fail)
+                for (uint32_t a = o + lane; a < c.dst_cap; a += 32) d[a] = 0;
+        } else if (c.codec == 5) {
+            fail = zstd_chunk(s, n, d, c.dst_cap, o, *(ZstdWarp*)&sm, lane);
+            if (c.expect_len < 0 && !fail)
+                for (uint32_t a = o + lane; a < c.dst_cap; a += 32) d[a] = 0;
+        } else if (c.codec == 3) {
+            fail = lzo_chunk(s, n, d, c.dst_cap, o, (uint32_t*)&sm, lane);
             if (c.expect_len < 0 && !fail)
                 for (uint32_t a = o + lane; a < c.dst_cap; a += 32) d[a] = 0;
         } else {

@@ -2,9 +2,11 @@
 
 #include <algorithm>
 #include <cstring>
+#include <memory>
 
 #include "pb.h"
 #include "job_internal.h"
+#include "zstd_dec.h"
 
 namespace orcb {
 
@@ -227,6 +229,124 @@ static void host_inflate(const uint8_t* s, size_t n, std::vector<uint8_t>& out) 
     } while (!last);
 }
 
+// Zstandard frames and LZO1X streams of metadata sections; the parsing is shared with the device decoder (zstd_dec.h).
+static void host_zstd_frames(const uint8_t* s, size_t n, std::vector<uint8_t>& out) {
+    using namespace zstd;
+    auto bad = [] { fail(ORCB_IO_ERROR, "corrupt zstd frame"); };
+    std::unique_ptr<Tables> T(new Tables);
+    size_t p = 0;
+    while (p < n) {
+        FrameHeader fh;
+        if (!frame_header(s + p, (uint32_t)std::min<size_t>(n - p, 0xffffffffu), fh)) {
+            bad();
+        }
+        p += fh.hdr;
+        if (fh.skippable) continue;
+        FrameState fs;
+        fs.reset();
+        const size_t base = out.size();
+        for (;;) {
+            if (p + 3 > n) bad();
+            const uint32_t bh = s[p] | ((uint32_t)s[p + 1] << 8) | ((uint32_t)s[p + 2] << 16);
+            p += 3;
+            const uint32_t last = bh & 1, type = (bh >> 1) & 3, size = bh >> 3;
+            if (type == 3) bad();
+            if (type == 0) {
+                if (size > n - p) bad();
+                out.insert(out.end(), s + p, s + p + size);
+                p += size;
+            } else if (type == 1) {
+                if (p >= n) bad();
+                out.insert(out.end(), size, s[p]);
+                p += 1;
+            } else {
+                if (size > n - p || size > (128u << 10)) bad();
+                const uint8_t* b = s + p;
+                LitHeader lh;
+                if (!lit_header(b, size, lh)) bad();
+                std::vector<uint8_t> lits(lh.regen);
+                const uint8_t* lp = b + lh.hdr;
+                if (lh.type == 0) {
+                    std::copy(lp, lp + lh.regen, lits.begin());
+                } else if (lh.type == 1) {
+                    std::fill(lits.begin(), lits.end(), lp[0]);
+                } else {
+                    uint32_t used = 0;
+                    if (lh.type == 2) {
+                        if (!huf_read(lp, lh.comp, *T, fs.huf_log, used)) bad();
+                    } else if (fs.huf_log < 0) {
+                        bad();
+                    }
+                    const uint8_t* sp = lp + used;
+                    const uint32_t sn = lh.comp - used;
+                    if (lh.streams == 1) {
+                        if (!huf_stream(sp, sn, T->huf, fs.huf_log, lits.data(), lh.regen)) bad();
+                    } else {
+                        if (sn < 6) bad();
+                        const uint32_t l1 = sp[0] | (sp[1] << 8), l2 = sp[2] | (sp[3] << 8), l3 = sp[4] | (sp[5] << 8);
+                        if ((uint64_t)6 + l1 + l2 + l3 > sn) bad();
+                        const uint32_t l4 = sn - 6 - l1 - l2 - l3, q = (lh.regen + 3) / 4;
+                        if (3 * (uint64_t)q > lh.regen) bad();
+                        const uint32_t lens[4] = {l1, l2, l3, l4};
+                        const uint8_t* at = sp + 6;
+                        for (int k = 0; k < 4; k++) {
+                            if (!huf_stream(at, lens[k], T->huf, fs.huf_log, lits.data() + k * q, k < 3 ? q : lh.regen - 3 * q)) bad();
+                            at += lens[k];
+                        }
+                    }
+                }
+                const uint8_t* sq = b + lh.hdr + lh.comp;
+                const uint32_t sqn = size - lh.hdr - lh.comp;
+                uint32_t nseq = 0, used = 0;
+                if (!seq_header(sq, sqn, *T, fs, nseq, used)) bad();
+                size_t lit_at = 0;
+                if (nseq) {
+                    SeqReader r;
+                    if (!r.init(sq + used, sqn - used, fs)) bad();
+                    for (uint32_t i = 0; i < nseq; i++) {
+                        uint32_t ll, ml, off;
+                        if (!r.next(*T, fs, i + 1 == nseq, ll, ml, off)) bad();
+                        if (ll > lits.size() - lit_at) bad();
+                        out.insert(out.end(), lits.begin() + lit_at, lits.begin() + lit_at + ll);
+                        lit_at += ll;
+                        if (off > out.size() - base) bad();
+                        for (uint32_t k = 0; k < ml; k++) out.push_back(out[out.size() - off]);
+                    }
+                    if (r.b.bits != 0) bad();
+                } else if (used != sqn) {
+                    bad();
+                }
+                out.insert(out.end(), lits.begin() + lit_at, lits.end());
+                p += size;
+            }
+            if (last) break;
+        }
+        if (fh.checksum) {
+            if (p + 4 > n) bad();
+            p += 4;  // content checksum: not verified
+        }
+        if (fh.content != ~0ull && out.size() - base != fh.content) bad();
+    }
+}
+
+static void host_lzo_block(const uint8_t* s, size_t n, std::vector<uint8_t>& out) {
+    const size_t base = out.size();
+    uint32_t p = 0, state = 0;
+    bool first = true;
+    for (;;) {
+        lzo::Token t;
+        if (!lzo::next(s, (uint32_t)n, p, state, first, t)) fail(ORCB_BUILD_LZO_DECODER, "corrupt LZO stream");
+        first = false;
+        if (t.end) break;
+        if (t.m_len) {
+            if (t.m_dist > out.size() - base) fail(ORCB_BUILD_LZO_DECODER, "LZO match before the start of the block");
+            for (uint32_t k = 0; k < t.m_len; k++) out.push_back(out[out.size() - t.m_dist]);
+        }
+        out.insert(out.end(), s + t.lit_pos, s + t.lit_pos + t.lit_len);
+    }
+    if (p != n) fail(ORCB_BUILD_LZO_DECODER, "bytes after the end of the LZO stream");
+}
+
 std::vector<uint8_t> host_decompress_section(int compression, uint64_t block_size, const uint8_t* in, size_t len) {
     std::vector<uint8_t> out;
     if (compression == C_NONE) {
@@ -248,8 +368,12 @@ std::vector<uint8_t> host_decompress_section(int compression, uint64_t block_siz
             host_lz4_block(in + p, clen, block_size, out);
         } else if (compression == C_ZLIB) {
             host_inflate(in + p, clen, out);
+        } else if (compression == C_ZSTD) {
+            host_zstd_frames(in + p, clen, out);
+        } else if (compression == C_LZO) {
+            host_lzo_block(in + p, clen, out);
         } else {
-            fail(ORCB_UNSUPPORTED_DEVICE_CODEC, "Zstd/LZO are not supported on the device path");
+            fail(ORCB_DECODE_PROTO, "unknown compression kind");
         }
         p += clen;
     }
@@ -396,9 +520,6 @@ void parse_file_tail(FileMeta& fm) {
     }
     if (!have_footer) fail(ORCB_OUT_OF_SPEC, "Footer length is empty");
     if (!have_meta) fail(ORCB_OUT_OF_SPEC, "Metadata length is empty");
-    if (fm.compression == C_ZSTD || fm.compression == C_LZO)
-        fail(ORCB_UNSUPPORTED_DEVICE_CODEC,
-             "file is compressed with Zstd/LZO: not decodable on the device path (no CPU fallback)");
     if (fm.compression < 0 || fm.compression > C_ZSTD) fail(ORCB_DECODE_PROTO, "unknown compression kind");
     // subtraction-style checks: the lengths come from the file and their sum may wrap
     if (footer_len > n - 1 - ps_len || meta_len > n - 1 - ps_len - footer_len) fail(ORCB_OUT_OF_SPEC, "footer exceeds file");
@@ -758,6 +879,28 @@ std::vector<ChunkInfo> FileMeta::chunk_table(uint64_t stream_off, uint64_t strea
             std::lock_guard<std::mutex> lock(chunk_sizes->mu);
             auto it = chunk_sizes->size.find(stream_off + p);
             if (it != chunk_sizes->size.end()) ci.dst_len = it->second;
+        }
+        if (ci.dst_len < 0 && compression == C_ZSTD) {
+            // Frame_Content_Size of the (normally only) frame of the chunk
+            // ... when that frame is all there is in the chunk (block headers walked, nothing decoded)
+            zstd::FrameHeader fh;
+            const uint8_t* f = s + ci.src_off;
+            if (zstd::frame_header(f, ci.src_len, fh) && !fh.skippable && fh.content <= block_size) {
+                uint64_t q = fh.hdr;
+                bool whole = false;
+                while (q + 3 <= ci.src_len) {
+                    const uint32_t bh = f[q] | ((uint32_t)f[q + 1] << 8) | ((uint32_t)f[q + 2] << 16);
+                    q += 3 + (((bh >> 1) & 3) == 1 ? 1u : (bh >> 3));
+                    if (bh & 1) {
+                        whole = q + (fh.checksum ? 4 : 0) == ci.src_len;
+                        break;
+                    }
+                }
+                if (whole) {
+                    ci.dst_len = (int64_t)fh.content;
+                    ci.guess = true;
+                }
+            }
         }
         out.push_back(ci);
         p = ci.src_off + ci.src_len;

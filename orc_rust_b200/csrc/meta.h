@@ -56,6 +56,7 @@ struct ChunkInfo {
     uint32_t hdr_off;   // offset of the 3-byte header relative to stream start
     bool original;
     int64_t dst_len;    // decompressed bytes if known on the host (original: = src_len; snappy: preamble), else -1
+    bool guess = false; // dst_len is what a Zstandard frame header announces: planned on, checked on the device
 };
 
 // ColumnStatistics of one row group (src/statistics.rs:21-143); `kind` is the TypeStatistics variant the reference

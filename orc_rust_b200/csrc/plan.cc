@@ -326,6 +326,7 @@ void Job::plan_stripe(uint32_t task_idx) {
                 if (c.dst_len >= 0) {
                     d.dst_cap = (uint32_t)c.dst_len;
                     d.expect_len = (int32_t)c.dst_len;
+                    d.assumed = c.guess ? 1 : 0;
                 } else {
                     d.dst_cap = (uint32_t)fm.block_size;
                     // The layout assumes that every non-final chunk fills the block (writers cut a chunk when their

@@ -28,7 +28,7 @@ def _flat_files(sub):
             of = oo.OracleFile(open(f, "rb").read())
         except oo.OracleError:
             continue
-        if of.is_flat() and of.compression not in (3, 5):
+        if of.is_flat():
             out.append(f)
     return out
 
@@ -43,8 +43,6 @@ def test_oracle_vs_reference_feather(fpath):
     if name == "orc-file-11-format":
         pytest.skip("0.11 file without metadataLength: ignored by the reference (tests/integration/main.rs:334-337)")
     of = oo.OracleFile(open(orc, "rb").read())
-    if of.compression in (3, 5):
-        pytest.skip("LZO/Zstd: out of scope for the device path")
     if name == "orc_split_elim":
         pytest.skip("DECIMAL(0,0): ignored by the reference itself (tests/integration/main.rs:347-351)")
     _, got = _oracle_table(orc)
@@ -71,7 +69,7 @@ def _nested_files():
                 of = oo.OracleFile(open(f, "rb").read())
             except oo.OracleError:
                 continue
-            if not of.is_flat() and of.compression not in (3, 5):
+            if not of.is_flat():
                 out.append(f)
     return out
 

@@ -101,3 +101,107 @@ size_t lzc_snappy_compress(const uint8_t* src, size_t n, uint8_t* dst) {
     free(table);
     return (size_t)(o - dst);
 }
+
+/* ---- LZO1X (test inputs for the LZO chunk decoder) -------------------------------------------------
+ * A greedy compressor that exercises every instruction of the published LZO1X stream format: the first-byte literal
+ * forms, literal runs, M1 (2-byte match after 1..3 literals, 3-byte match at 2049..3072 after a run), M2, M3, M4, the
+ * 1..3 literals riding on a match instruction, and the end marker. */
+static uint8_t* lzo_run_len(uint8_t* o, size_t t) { /* t >= 1: zero bytes of 255 each, then the rest */
+    while (t > 255) { *o++ = 0; t -= 255; }
+    *o++ = (uint8_t)t;
+    return o;
+}
+
+size_t lzc_lzo_compress(const uint8_t* src, size_t n, uint8_t* dst) {
+    enum { HB = 15 };
+    static int32_t h3[1 << HB], h2[1 << 16];
+    memset(h3, -1, sizeof h3);
+    memset(h2, -1, sizeof h2);
+    uint8_t* o = dst;
+    uint8_t* sbits = NULL; /* byte holding the S bits of the previous match instruction */
+    size_t ip = 0, lit_start = 0;
+    int started = 0;
+    unsigned state = 0;
+    while (ip <= n) {
+        size_t mlen = 0, mdist = 0;
+        if (ip + 3 <= n) {
+            uint32_t v = src[ip] | (src[ip + 1] << 8) | ((uint32_t)src[ip + 2] << 16);
+            uint32_t h = (v * 2654435761u) >> (32 - HB);
+            int32_t c = h3[h];
+            h3[h] = (int32_t)ip;
+            if (c >= 0 && ip - (size_t)c <= 49151) {
+                size_t l = 0, lim = n - ip < 3000 ? n - ip : 3000;
+                while (l < lim && src[c + l] == src[ip + l]) l++;
+                if (l >= 3) { mlen = l; mdist = ip - (size_t)c; }
+            }
+        }
+        size_t ll = ip - lit_start;
+        if (!mlen && ip + 2 <= n && started && ll >= 1 && ll <= 3) {
+            uint32_t k = src[ip] | (src[ip + 1] << 8);
+            int32_t c = h2[k];
+            if (c >= 0 && ip - (size_t)c <= 1024) { mlen = 2; mdist = ip - (size_t)c; }
+        }
+        if (ip + 2 <= n) h2[src[ip] | (src[ip + 1] << 8)] = (int32_t)ip;
+        if (!mlen && ip < n) { ip++; continue; }
+        /* ---- pending literals */
+        if (ll) {
+            if (!started) {
+                if (ll <= 238) { *o++ = (uint8_t)(17 + ll); state = ll < 4 ? (unsigned)ll : 4; }
+                else { *o++ = 0; o = lzo_run_len(o, ll - 18); state = 4; }
+            } else if (ll <= 3) {
+                *sbits |= (uint8_t)ll;
+                state = (unsigned)ll;
+            } else {
+                if (ll - 3 <= 15) *o++ = (uint8_t)(ll - 3);
+                else { *o++ = 0; o = lzo_run_len(o, ll - 18); }
+                state = 4;
+            }
+            memcpy(o, src + lit_start, ll);
+            o += ll;
+            started = 1;
+        } else if (started) {
+            state = 0;
+        }
+        if (ip >= n) break;
+        /* ---- the match */
+        if (mlen == 2) {
+            size_t d = mdist - 1;
+            sbits = o;
+            *o++ = (uint8_t)((d & 3) << 2);
+            *o++ = (uint8_t)(d >> 2);
+        } else if (mlen == 3 && state == 4 && mdist >= 2049 && mdist <= 3072) {
+            size_t d = mdist - 2049;
+            sbits = o;
+            *o++ = (uint8_t)((d & 3) << 2);
+            *o++ = (uint8_t)(d >> 2);
+        } else if (mlen <= 8 && mdist <= 2048) {
+            size_t d = mdist - 1;
+            sbits = o;
+            *o++ = (uint8_t)(((mlen - 1) << 5) | ((d & 7) << 2));
+            *o++ = (uint8_t)(d >> 3);
+        } else if (mdist <= 16384) {
+            if (mlen - 2 <= 31) *o++ = (uint8_t)(32 | (mlen - 2));
+            else { *o++ = 32; o = lzo_run_len(o, mlen - 2 - 31); }
+            size_t d = mdist - 1;
+            sbits = o;
+            *o++ = (uint8_t)((d << 2) & 0xff);
+            *o++ = (uint8_t)(d >> 6);
+        } else {
+            size_t d = mdist - 16384;
+            uint8_t hbit = (uint8_t)(((d >> 14) & 1) << 3);
+            if (mlen - 2 <= 7) *o++ = (uint8_t)(16 | hbit | (mlen - 2));
+            else { *o++ = (uint8_t)(16 | hbit); o = lzo_run_len(o, mlen - 2 - 7); }
+            d &= 0x3fff;
+            sbits = o;
+            *o++ = (uint8_t)((d << 2) & 0xff);
+            *o++ = (uint8_t)(d >> 6);
+        }
+        started = 1;
+        ip += mlen;
+        lit_start = ip;
+    }
+    *o++ = 0x11;
+    *o++ = 0;
+    *o++ = 0;
+    return (size_t)(o - dst);
+}

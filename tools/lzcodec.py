@@ -1,4 +1,5 @@
-"""ctypes front of tools/lzcodec.c (LZ4-block / Snappy-raw compressors for test and bench inputs)."""
+"""ctypes front of tools/lzcodec.c (LZ4-block / Snappy-raw / LZO1X compressors for test and bench inputs; Zstandard
+frames come from pyarrow's codec)."""
 import ctypes
 import os
 import subprocess
@@ -15,7 +16,7 @@ def lib():
         if not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
             subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-o", _SO, src])
         L = ctypes.CDLL(_SO)
-        for f in (L.lzc_lz4_compress, L.lzc_snappy_compress):
+        for f in (L.lzc_lz4_compress, L.lzc_snappy_compress, L.lzc_lzo_compress):
             f.restype = ctypes.c_size_t
             f.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p]
         L.lzc_bound.restype = ctypes.c_size_t
@@ -27,7 +28,11 @@ def lib():
 def compress_block(kind: str, data: bytes) -> bytes:
     L = lib()
     buf = ctypes.create_string_buffer(L.lzc_bound(len(data)))
-    n = (L.lzc_lz4_compress if kind == "lz4" else L.lzc_snappy_compress)(bytes(data), len(data), buf)
+    if kind == "zstd":
+        import pyarrow as pa
+        return pa.Codec("zstd", compression_level=3).compress(bytes(data), asbytes=True)
+    fn = {"lz4": L.lzc_lz4_compress, "snappy": L.lzc_snappy_compress, "lzo": L.lzc_lzo_compress}[kind]
+    n = fn(bytes(data), len(data), buf)
     return buf.raw[:n]
 
 
