@@ -984,8 +984,12 @@ __device__ __forceinline__ void warp_copy_lit(uint8_t* dst, const uint8_t* src, 
 // Places `cnt` queued tokens at d + o.  `reserve`: bytes at the end of the output range that must stay untouched
 // (Zstandard literals not yet consumed after this batch).  `win_base`: matches may not reach below this offset.
 // rle >= 0: literals are this byte.  Returns non-zero when the output does not fit or a match is out of range.
+// Short literals, and short matches whose source lies wholly before the batch, do not depend on anything the batch
+// writes: every lane copies its own.  What is left (long copies, matches that read the batch's own output) follows
+// in token order, copied by the whole warp.
 __device__ __forceinline__ uint32_t lz_exec_tokens(uint8_t* d, uint32_t& o, uint32_t cap, uint32_t reserve, uint32_t win_base,
                                                    const uint32_t* tok, uint32_t cnt, const uint8_t* lit_base, int rle, int lane) {
+    constexpr uint32_t OWN_MAX = 48;  // longest copy a lane does alone
     const bool on = (uint32_t)lane < cnt;
     const uint32_t ll = on ? tok[4 * lane] : 0u, lo = on ? tok[4 * lane + 1] : 0u;
     const uint32_t ml = on ? tok[4 * lane + 2] : 0u, dist = on ? tok[4 * lane + 3] : 0u;
@@ -993,22 +997,42 @@ __device__ __forceinline__ uint32_t lz_exec_tokens(uint8_t* d, uint32_t& o, uint
     const uint32_t incl = warp_incl_scan(len, lane);
     const uint32_t total = __shfl_sync(FULL, incl, 31);
     if (total > cap - o || reserve > cap - o - total) return 1;
-    const uint32_t op = o + incl - len;
-    for (uint32_t l = 0; l < cnt; l++) {
-        const uint32_t e_ll = __shfl_sync(FULL, ll, l), e_lo = __shfl_sync(FULL, lo, l), e_ml = __shfl_sync(FULL, ml, l);
-        const uint32_t e_dist = __shfl_sync(FULL, dist, l), e_op = __shfl_sync(FULL, op, l);
-        if (e_ll) {
-            if (rle >= 0) {
-                for (uint32_t i = lane; i < e_ll; i += 32) d[e_op + i] = (uint8_t)rle;
-                __syncwarp();
-            } else {
-                warp_copy_lit(d + e_op, lit_base + e_lo, e_ll, lane);
-            }
+    const uint32_t op = o + incl - len, at = op + ll;
+    if (__any_sync(FULL, ml && (dist == 0 || dist > at - win_base))) return 1;
+    // literals that wait in the tail of the output range must not be overwritten before they are read: lanes copy on
+    // their own only when everything the batch writes lies below the first literal it reads
+    const uint64_t lit0 = (uint64_t)(uintptr_t)(lit_base + __shfl_sync(FULL, lo, 0));
+    const uint64_t d0 = (uint64_t)(uintptr_t)d;
+    const bool lit_apart = lit0 < d0 || lit0 >= d0 + cap || lit0 >= d0 + o + total;
+    const bool lit_own = ll && (rle >= 0 || (lit_apart && ll <= OWN_MAX));
+    if (lit_own) {
+        if (rle >= 0) {
+            for (uint32_t i = 0; i < ll; i++) d[op + i] = (uint8_t)rle;
+        } else {
+            const uint8_t* sp = lit_base + lo;
+            for (uint32_t i = 0; i < ll; i++) d[op + i] = sp[i];
         }
-        if (e_ml) {
-            const uint32_t at = e_op + e_ll;
-            if (e_dist == 0 || e_dist > at - win_base) return 1;
-            warp_copy_match(d, at, e_dist, e_ml, lane);
+    }
+    uint32_t lm = __ballot_sync(FULL, ll && !lit_own);
+    const bool m_own = ml && ml <= OWN_MAX && at - dist + ml <= o && !lm;
+    // (with cooperative literals pending, matches wait: the literal phase below must stay in token order with them)
+    if (m_own) {
+        const uint8_t* sp = d + (at - dist);
+        for (uint32_t i = 0; i < ml; i++) d[at + i] = sp[i];
+    }
+    uint32_t mm = __ballot_sync(FULL, ml && !m_own);
+    __syncwarp();
+    uint32_t rest = lm | mm;
+    while (rest) {
+        const int l = __ffs(rest) - 1;
+        rest &= rest - 1;
+        if ((lm >> l) & 1u) {
+            const uint32_t e_ll = __shfl_sync(FULL, ll, l), e_lo = __shfl_sync(FULL, lo, l), e_op = __shfl_sync(FULL, op, l);
+            warp_copy_lit(d + e_op, lit_base + e_lo, e_ll, lane);
+        }
+        if ((mm >> l) & 1u) {
+            const uint32_t e_ml = __shfl_sync(FULL, ml, l), e_dist = __shfl_sync(FULL, dist, l), e_at = __shfl_sync(FULL, at, l);
+            warp_copy_match(d, e_at, e_dist, e_ml, lane);
             __syncwarp();
         }
     }
@@ -1079,6 +1103,8 @@ __device__ uint32_t zstd_block(const uint8_t* __restrict__ b, uint32_t size, uin
     }
     if (__shfl_sync(FULL, bad, 0)) return 1;
     nseq = __shfl_sync(FULL, nseq, 0);
+    fill_codes(w.T, (uint32_t)lane, 32);  // over the Huffman weights, which are not needed any more
+    __syncwarp();
     uint32_t lit_at = 0;  // lane 0 keeps it
     for (uint32_t s0 = 0; s0 < nseq; s0 += 32) {
         const uint32_t cnt = min(32u, nseq - s0);

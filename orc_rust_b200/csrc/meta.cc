@@ -301,6 +301,7 @@ static void host_zstd_frames(const uint8_t* s, size_t n, std::vector<uint8_t>& o
                 if (!seq_header(sq, sqn, *T, fs, nseq, used)) bad();
                 size_t lit_at = 0;
                 if (nseq) {
+                    fill_codes(*T, 0, 1);
                     SeqReader r;
                     if (!r.init(sq + used, sqn - used, fs)) bad();
                     for (uint32_t i = 0; i < nseq; i++) {

@@ -31,8 +31,15 @@ constexpr int LL_SYMS = 36, ML_SYMS = 53, OF_SYMS = 32, WT_SYMS = 16;
 struct Tables {
     uint32_t ll[1 << LL_MAX_LOG], ml[1 << ML_MAX_LOG], of[1 << OF_MAX_LOG];
     uint16_t huf[1 << HUF_MAX_LOG];
-    uint32_t wt[1 << WT_MAX_LOG];   // FSE table of the Huffman weights
-    uint8_t weights[256];
+    union {
+        struct {
+            uint32_t wt[1 << WT_MAX_LOG];  // FSE table of the Huffman weights
+            uint8_t weights[256];
+        };
+        // once the literals of a block are decoded: baseline [0:24) | extra bits [24:32) of the literal length codes
+        // (0..35) and, from 36 on, of the match length codes
+        uint32_t codes[LL_SYMS + ML_SYMS];
+    };
     int16_t norm[64];
     uint16_t sdesc[64];
 };
@@ -64,21 +71,25 @@ struct Fwd {
 };
 
 // backward: the stream ends with a 1 bit marking the end of the padding; the first bit read is the most significant
-// of a value; bits below the start of the stream read as zeros and leave `bits` negative
+// of a value; bits below the start of the stream read as zeros and leave `bits` negative.  Reads are served from a
+// 64-bit window of the stream that is reloaded (8 byte loads) once its lower end is reached.
 struct Back {
     const uint8_t* s;
     uint32_t n;
     int64_t bits;  // unread bits: [0, bits)
+    uint64_t win;  // stream bits [wlo, wlo + 64)
+    int64_t wlo;   // multiple of 8; -1: nothing loaded
     ORCB_HD bool init(const uint8_t* p, uint32_t len) {
         s = p;
         n = len;
         bits = 0;
+        wlo = -1;
+        win = 0;
         if (!len || !p[len - 1]) return false;
         bits = (int64_t)(len - 1) * 8 + highbit(p[len - 1]);
         return true;
     }
-    ORCB_HD uint32_t peek(int k) const {  // k <= 32
-        if (k == 0) return 0;
+    ORCB_HD uint32_t refill_peek(int k) {
         int64_t lo = bits - k;
         int below = 0;
         if (lo < 0) {
@@ -86,13 +97,21 @@ struct Back {
             if (below >= k) return 0;
             lo = 0;
         }
-        const uint32_t byte = (uint32_t)(lo >> 3), sh = (uint32_t)(lo & 7);
+        int64_t top = (bits + 7) & ~(int64_t)7;
+        wlo = top > 64 ? top - 64 : 0;
+        const uint32_t byte = (uint32_t)(wlo >> 3);
         uint64_t v = 0;
-        for (uint32_t i = 0; i < 5; i++) v |= (uint64_t)(byte + i < n ? s[byte + i] : 0u) << (8 * i);
-        v >>= sh;
+        for (uint32_t i = 0; i < 8; i++) v |= (uint64_t)(byte + i < n ? s[byte + i] : 0u) << (8 * i);
+        win = v;
         const int have = k - below;
-        v &= (1ull << have) - 1ull;
+        v = (v >> (lo - wlo)) & ((1ull << have) - 1ull);
         return (uint32_t)(v << below);
+    }
+    ORCB_HD uint32_t peek(int k) {  // k <= 32
+        if (k == 0) return 0;
+        const int64_t lo = bits - k;
+        if (wlo >= 0 && lo >= wlo && bits <= wlo + 64) return (uint32_t)((win >> (lo - wlo)) & ((1ull << k) - 1ull));
+        return refill_peek(k);
     }
     ORCB_HD uint32_t read(int k) {
         const uint32_t v = peek(k);
@@ -197,6 +216,12 @@ ORCB_HD uint32_t ll_base(uint32_t c) {
 }
 ORCB_HD uint32_t ml_base(uint32_t c) {
     return base3("\3\0\0\4\0\0\5\0\0\6\0\0\7\0\0\10\0\0\11\0\0\12\0\0\13\0\0\14\0\0\15\0\0\16\0\0\17\0\0\20\0\0\21\0\0\22\0\0\23\0\0\24\0\0\25\0\0\26\0\0\27\0\0\30\0\0\31\0\0\32\0\0\33\0\0\34\0\0\35\0\0\36\0\0\37\0\0\40\0\0\41\0\0\42\0\0\43\0\0\45\0\0\47\0\0\51\0\0\53\0\0\57\0\0\63\0\0\73\0\0\103\0\0\123\0\0\143\0\0\203\0\0\3\1\0\3\2\0\3\4\0\3\10\0\3\20\0\3\40\0\3\100\0\3\200\0\3\0\1", c);
+}
+
+// fills T.codes; with `stride` callers of index `first` each writes its share (the 32 lanes of a warp, or one thread)
+ORCB_HD void fill_codes(Tables& T, uint32_t first, uint32_t stride) {
+    for (uint32_t c = first; c < (uint32_t)(LL_SYMS + ML_SYMS); c += stride)
+        T.codes[c] = c < (uint32_t)LL_SYMS ? (ll_base(c) | (ll_bits(c) << 24)) : (ml_base(c - LL_SYMS) | (ml_bits(c - LL_SYMS) << 24));
 }
 
 // ---- Huffman -----------------------------------------------------------------------------------
@@ -402,8 +427,9 @@ struct SeqReader {
         const uint32_t of_code = oe & 0xff, ml_code = me & 0xff, ll_code = le & 0xff;
         if (of_code > 31 || ml_code >= (uint32_t)ML_SYMS || ll_code >= (uint32_t)LL_SYMS) return false;
         const uint32_t of_val = (of_code == 31 ? 0x80000000u : (1u << of_code)) + b.read((int)of_code);
-        ml = ml_base(ml_code) + b.read((int)ml_bits(ml_code));
-        ll = ll_base(ll_code) + b.read((int)ll_bits(ll_code));
+        const uint32_t mc = T.codes[LL_SYMS + ml_code], lc = T.codes[ll_code];  // fill_codes() ran for this block
+        ml = (mc & 0xffffffu) + b.read((int)(mc >> 24));
+        ll = (lc & 0xffffffu) + b.read((int)(lc >> 24));
         if (of_val > 3) {
             off = of_val - 3;
             fs.rep[2] = fs.rep[1];
