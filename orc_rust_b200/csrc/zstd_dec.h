@@ -18,9 +18,13 @@ namespace zstd {
 #define ORCB_ZT(lit, i) ((uint32_t)(uint8_t)(lit)[(i)])
 
 ORCB_HD int highbit(uint32_t v) {  // index of the highest set bit, v != 0
+#ifdef __CUDA_ARCH__
+    return 31 - __clz((int)v);
+#else
     int r = 0;
     while (v >>= 1) r++;
     return r;
+#endif
 }
 
 constexpr int LL_MAX_LOG = 9, ML_MAX_LOG = 9, OF_MAX_LOG = 8, HUF_MAX_LOG = 11, WT_MAX_LOG = 6;
@@ -71,47 +75,55 @@ struct Fwd {
 };
 
 // backward: the stream ends with a 1 bit marking the end of the padding; the first bit read is the most significant
-// of a value; bits below the start of the stream read as zeros and leave `bits` negative.  Reads are served from a
-// 64-bit window of the stream that is reloaded (8 byte loads) once its lower end is reached.
+// of a value; bits below the start of the stream read as zeros and leave `bits` negative.  On the device a read is two
+// aligned word loads and a funnel shift (the words may extend a few bytes beyond the stream: inside the arena, and
+// never part of the value); the host reads byte by byte inside the stream.
 struct Back {
     const uint8_t* s;
     uint32_t n;
-    int64_t bits;  // unread bits: [0, bits)
-    uint64_t win;  // stream bits [wlo, wlo + 64)
-    int64_t wlo;   // multiple of 8; -1: nothing loaded
+    int32_t bits;  // unread bits: [0, bits)
+#ifdef __CUDA_ARCH__
+    const uint32_t* W;  // s rounded down to a word
+    uint32_t boff;      // bit offset of s in W
+#endif
     ORCB_HD bool init(const uint8_t* p, uint32_t len) {
         s = p;
         n = len;
         bits = 0;
-        wlo = -1;
-        win = 0;
-        if (!len || !p[len - 1]) return false;
-        bits = (int64_t)(len - 1) * 8 + highbit(p[len - 1]);
+#ifdef __CUDA_ARCH__
+        W = (const uint32_t*)((uintptr_t)p & ~(uintptr_t)3);
+        boff = (uint32_t)((uintptr_t)p & 3) * 8;
+#endif
+        if (!len || len > (1u << 27) || !p[len - 1]) return false;
+        bits = (int32_t)(len - 1) * 8 + highbit(p[len - 1]);
         return true;
     }
-    ORCB_HD uint32_t refill_peek(int k) {
-        int64_t lo = bits - k;
+    ORCB_HD uint32_t peek_slow(int k) const {
+        if (k == 0) return 0;
+        int32_t lo = bits - k;
         int below = 0;
         if (lo < 0) {
-            below = (int)(-lo < 64 ? -lo : 64);
+            below = -lo < 64 ? -lo : 64;
             if (below >= k) return 0;
             lo = 0;
         }
-        int64_t top = (bits + 7) & ~(int64_t)7;
-        wlo = top > 64 ? top - 64 : 0;
-        const uint32_t byte = (uint32_t)(wlo >> 3);
+        const uint32_t byte = (uint32_t)lo >> 3, sh = (uint32_t)lo & 7;
         uint64_t v = 0;
-        for (uint32_t i = 0; i < 8; i++) v |= (uint64_t)(byte + i < n ? s[byte + i] : 0u) << (8 * i);
-        win = v;
+        for (uint32_t i = 0; i < 5; i++) v |= (uint64_t)(byte + i < n ? s[byte + i] : 0u) << (8 * i);
+        v >>= sh;
         const int have = k - below;
-        v = (v >> (lo - wlo)) & ((1ull << have) - 1ull);
+        v &= (1ull << have) - 1ull;
         return (uint32_t)(v << below);
     }
-    ORCB_HD uint32_t peek(int k) {  // k <= 32
-        if (k == 0) return 0;
-        const int64_t lo = bits - k;
-        if (wlo >= 0 && lo >= wlo && bits <= wlo + 64) return (uint32_t)((win >> (lo - wlo)) & ((1ull << k) - 1ull));
-        return refill_peek(k);
+    ORCB_HD uint32_t peek(int k) const {  // k <= 31
+#ifdef __CUDA_ARCH__
+        const int32_t lo = bits - k;
+        if (lo < 0) return peek_slow(k);
+        const uint32_t a = (uint32_t)lo + boff;
+        return __funnelshift_r(W[a >> 5], W[(a >> 5) + 1], a & 31) & ((1u << k) - 1u);
+#else
+        return peek_slow(k);
+#endif
     }
     ORCB_HD uint32_t read(int k) {
         const uint32_t v = peek(k);
@@ -421,15 +433,28 @@ struct SeqReader {
         ml_s = b.read(fs.ml_log);
         return b.bits >= 0;
     }
-    // one sequence; `last`: no state update follows.  false = corrupt
+    // one sequence; `last`: no state update follows.  false = corrupt.  The three fields of a sequence are adjacent in
+    // the bitstream (offset bits first = most significant), and so are the three state updates: one or two reads each.
     ORCB_HD bool next(const Tables& T, FrameState& fs, bool last, uint32_t& ll, uint32_t& ml, uint32_t& off) {
         const uint32_t le = T.ll[ll_s], oe = T.of[of_s], me = T.ml[ml_s];
         const uint32_t of_code = oe & 0xff, ml_code = me & 0xff, ll_code = le & 0xff;
         if (of_code > 31 || ml_code >= (uint32_t)ML_SYMS || ll_code >= (uint32_t)LL_SYMS) return false;
-        const uint32_t of_val = (of_code == 31 ? 0x80000000u : (1u << of_code)) + b.read((int)of_code);
         const uint32_t mc = T.codes[LL_SYMS + ml_code], lc = T.codes[ll_code];  // fill_codes() ran for this block
-        ml = (mc & 0xffffffu) + b.read((int)(mc >> 24));
-        ll = (lc & 0xffffffu) + b.read((int)(lc >> 24));
+        const uint32_t mb = mc >> 24, lb = lc >> 24;
+        uint32_t of_x, ml_x, ll_x;
+        if (of_code + mb + lb <= 31) {
+            const uint32_t v = b.read((int)(of_code + mb + lb));
+            ll_x = v & ((1u << lb) - 1u);
+            ml_x = (v >> lb) & ((1u << mb) - 1u);
+            of_x = v >> (lb + mb);
+        } else {
+            of_x = b.read((int)of_code);
+            ml_x = b.read((int)mb);
+            ll_x = b.read((int)lb);
+        }
+        const uint32_t of_val = (1u << of_code) + of_x;
+        ml = (mc & 0xffffffu) + ml_x;
+        ll = (lc & 0xffffffu) + ll_x;
         if (of_val > 3) {
             off = of_val - 3;
             fs.rep[2] = fs.rep[1];
@@ -440,7 +465,7 @@ struct SeqReader {
             if (idx == 0) {
                 off = fs.rep[0];
             } else {
-                off = idx == 3 ? fs.rep[0] - 1 : fs.rep[idx];
+                off = idx == 1 ? fs.rep[1] : idx == 2 ? fs.rep[2] : fs.rep[0] - 1;
                 if (off == 0) off = 1;  // libzstd forces a corrupt zero offset to 1
                 if (idx != 1) fs.rep[2] = fs.rep[1];
                 fs.rep[1] = fs.rep[0];
@@ -448,9 +473,11 @@ struct SeqReader {
             }
         }
         if (!last) {
-            ll_s = (le >> 16) + b.read((le >> 8) & 0xff);
-            ml_s = (me >> 16) + b.read((me >> 8) & 0xff);
-            of_s = (oe >> 16) + b.read((oe >> 8) & 0xff);
+            const uint32_t nl = (le >> 8) & 0xff, nm = (me >> 8) & 0xff, no = (oe >> 8) & 0xff;  // <= 9 + 9 + 8 bits
+            const uint32_t v = b.read((int)(nl + nm + no));
+            of_s = (oe >> 16) + (v & ((1u << no) - 1u));
+            ml_s = (me >> 16) + ((v >> no) & ((1u << nm) - 1u));
+            ll_s = (le >> 16) + (v >> (no + nm));
         }
         return b.bits >= 0;
     }
