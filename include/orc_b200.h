@@ -41,7 +41,8 @@ typedef enum OrcbStatus {
     ORCB_BUILD_LZO_DECODER = 16,
     ORCB_BUILD_LZ4_DECODER = 17,
     ORCB_ARROW = 18,
-    /* new on the device path (BASELINE north_star): Zlib / Zstd / LZO are rejected, never CPU-decoded */
+    /* device-path additions.  UNSUPPORTED_DEVICE_CODEC is no longer produced: every compression kind is decoded on the
+     * device (kept so that the numbering stays stable) */
     ORCB_UNSUPPORTED_DEVICE_CODEC = 19,
     ORCB_CUDA = 20,
     ORCB_INVALID_ARGUMENT = 21,
