@@ -1252,6 +1252,9 @@ __device__ uint32_t lzo_chunk(const uint8_t* __restrict__ s, uint32_t n, uint8_t
 }
 
 // Persistent warps over the chunk list (most expensive chunks first, see plan.cc); one chunk per warp at a time.
+// Two kernels, so that the tile decoder keeps its register allocation: k_decompress takes stored, Snappy and LZ4
+// chunks, k_decompress_bits the codecs whose chunk is one serial bit / instruction chain (Zlib, Zstandard, LZO) - and
+// stored chunks too when a list holds nothing else for the first kernel.
 __global__ void __launch_bounds__(128, ORCB_LZ_CTAS) k_decompress(const ChunkDesc* __restrict__ chunks, uint32_t nchunks, uint32_t* err,
                                                        uint32_t* out_lens, uint32_t* counter, uint32_t* retry) {
     __shared__ LzWarp warp_sm[4];
@@ -1280,24 +1283,59 @@ __global__ void __launch_bounds__(128, ORCB_LZ_CTAS) k_decompress(const ChunkDes
             uint64_t ulen;
             fail = snappy_preamble(s, n, c.dst_cap, p, ulen);
             if (!fail) fail = lz_chunk<2>(s, n, d, ulen, p, o, sm, lut, lane);
-        } else if (c.codec == 1) {
-            fail = inflate_chunk(s, n, d, c.dst_cap, o, *(InfWarp*)&sm, lane);
-            if (c.expect_len < 0 && !fail)
-                for (uint32_t a = o + lane; a < c.dst_cap; a += 32) d[a] = 0;
-        } else if (c.codec == 5) {
-            fail = zstd_chunk(s, n, d, c.dst_cap, o, *(ZstdWarp*)&sm, lane);
-            if (c.expect_len < 0 && !fail)
-                for (uint32_t a = o + lane; a < c.dst_cap; a += 32) d[a] = 0;
-        } else if (c.codec == 3) {
-            fail = lzo_chunk(s, n, d, c.dst_cap, o, (uint32_t*)&sm, lane);
-            if (c.expect_len < 0 && !fail)
-                for (uint32_t a = o + lane; a < c.dst_cap; a += 32) d[a] = 0;
-        } else {
+        } else if (c.codec == 4) {
             fail = lz_chunk<4>(s, n, d, c.dst_cap, 0, o, sm, lut, lane);
             // the size of a stream's last LZ4 chunk is only known here: what the layout reserved beyond it reads as zeros
             if (c.expect_len < 0 && !fail)
                 for (uint32_t a = o + lane; a < c.dst_cap; a += 32) d[a] = 0;
+        } else {
+            fail = ORCB_UNEXPECTED;  // not this kernel's (launch_decompress splits the list)
         }
+        chunk_done(c, fail, o, err, out_lens, retry, lane);
+        __syncwarp();
+    }
+}
+
+union BitsWarp {
+    InfWarp inf;
+    ZstdWarp zstd;
+    uint32_t tok[32 * 4];
+};
+
+#ifndef ORCB_BITS_CTAS
+#define ORCB_BITS_CTAS 5
+#endif
+__global__ void __launch_bounds__(128, ORCB_BITS_CTAS) k_decompress_bits(const ChunkDesc* __restrict__ chunks, uint32_t nchunks, uint32_t* err,
+                                                            uint32_t* out_lens, uint32_t* counter, uint32_t* retry) {
+    __shared__ BitsWarp warp_sm[4];
+    const int lane = threadIdx.x & 31;
+    BitsWarp& sm = warp_sm[threadIdx.x >> 5];
+    for (;;) {
+        uint32_t ci = 0;
+        if (lane == 0) ci = atomicAdd(counter, 1u);
+        ci = __shfl_sync(FULL, ci, 0);
+        if (ci >= nchunks) return;
+        const ChunkDesc& c = chunks[ci];
+        const uint8_t* s = (const uint8_t*)c.src;
+        uint8_t* d = (uint8_t*)c.dst;
+        const uint32_t n = c.src_len;
+        uint32_t o = 0, fail = 0;
+        if (c.codec == 0) {
+            if (n > c.dst_cap) fail = ORCB_UNEXPECTED;
+            else warp_copy_fwd(d, s, n, lane);
+            o = n;
+        } else if (c.codec == 1) {
+            fail = inflate_chunk(s, n, d, c.dst_cap, o, sm.inf, lane);
+        } else if (c.codec == 5) {
+            fail = zstd_chunk(s, n, d, c.dst_cap, o, sm.zstd, lane);
+        } else if (c.codec == 3) {
+            fail = lzo_chunk(s, n, d, c.dst_cap, o, sm.tok, lane);
+        } else {
+            fail = ORCB_UNEXPECTED;
+        }
+        // the size of a stream's last chunk is only known here: what the layout reserved beyond it reads as zeros
+        if (c.codec != 0 && c.expect_len < 0 && !fail)
+            for (uint32_t a = o + lane; a < c.dst_cap; a += 32) d[a] = 0;
         chunk_done(c, fail, o, err, out_lens, retry, lane);
         __syncwarp();
     }
@@ -1306,19 +1344,34 @@ __global__ void __launch_bounds__(128, ORCB_LZ_CTAS) k_decompress(const ChunkDes
 // ------------------------------------------------------------------------------------------------
 // host-side launch wrappers
 // ------------------------------------------------------------------------------------------------
-int launch_decompress(const ChunkDesc* c, uint32_t n, uint32_t* err, uint32_t* out_lens, uint32_t* counter, uint32_t* retry, cudaStream_t st) {
-    if (!n) return 0;
-    static int ctas = 0;
-    if (!ctas) {
+template <class K>
+static uint32_t resident_ctas(K kernel, int& cache) {
+    if (!cache) {
         int dev = 0, sms = 148, per_sm = 4;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decompress, 128, 0);
-        ctas = sms * (per_sm > 0 ? per_sm : 1);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 128, 0);
+        cache = sms * (per_sm > 0 ? per_sm : 1);
     }
-    const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)ctas, ((uint64_t)n + 3) / 4);
-    k_decompress<<<grid, 128, 0, st>>>(c, n, err, out_lens, counter, retry);
-    LAUNCH_CHECK();
+    return (uint32_t)cache;
+}
+
+// The first n_bits chunks of the list go to k_decompress_bits, the rest to k_decompress.
+int launch_decompress(const ChunkDesc* c, uint32_t n, uint32_t n_bits, uint32_t* err, uint32_t* out_lens, uint32_t* counter, uint32_t* retry,
+                      cudaStream_t st) {
+    if (!n) return 0;
+    static int ctas_tile = 0, ctas_bits = 0;
+    if (n_bits > n) n_bits = n;
+    if (n_bits) {
+        const uint32_t grid = (uint32_t)std::min<uint64_t>(resident_ctas(k_decompress_bits, ctas_bits), ((uint64_t)n_bits + 3) / 4);
+        k_decompress_bits<<<grid, 128, 0, st>>>(c, n_bits, err, out_lens, counter + 1, retry);
+        LAUNCH_CHECK();
+    }
+    if (n > n_bits) {
+        const uint32_t grid = (uint32_t)std::min<uint64_t>(resident_ctas(k_decompress, ctas_tile), ((uint64_t)(n - n_bits) + 3) / 4);
+        k_decompress<<<grid, 128, 0, st>>>(c + n_bits, n - n_bits, err, out_lens, counter, retry);
+        LAUNCH_CHECK();
+    }
     return 0;
 }
 

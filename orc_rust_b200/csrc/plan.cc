@@ -111,10 +111,14 @@ void Job::plan() {
 
     // chunks that take longest first (compressed before stored, long before short): the persistent decompression
     // warps draw them in this order, so the launch does not end on one late, expensive chunk
-    std::stable_sort(chunks_.begin(), chunks_.end(), [](const ChunkDesc& a, const ChunkDesc& b) {
-        const uint64_t ka = ((uint64_t)(a.codec != 0) << 32) | a.src_len, kb = ((uint64_t)(b.codec != 0) << 32) | b.src_len;
-        return ka > kb;
-    });
+    // (Zlib / Zstandard / LZO chunks in front: they have a kernel of their own, launch_decompress)
+    auto chunk_key = [](const ChunkDesc& c) {
+        const bool bits = c.codec == 1 || c.codec == 3 || c.codec == 5;
+        return ((uint64_t)bits << 40) | ((uint64_t)(c.codec != 0) << 32) | c.src_len;
+    };
+    std::stable_sort(chunks_.begin(), chunks_.end(), [&](const ChunkDesc& a, const ChunkDesc& b) { return chunk_key(a) > chunk_key(b); });
+    n_bits_chunks_ = 0;
+    for (auto& c : chunks_) n_bits_chunks_ += (chunk_key(c) >> 40) & 1;
 
     if (n_chk_) chk_table_ = alloc(AR_TMP, (uint64_t)n_chk_ * sizeof(SegCheck));
     if (pool_blocks_) {
@@ -167,7 +171,7 @@ void Job::plan() {
     splace(o_dstart_, (size_t)(n_cnt_ + 1) * 4);
     splace(o_mis_, (size_t)(n_colstripes_ + 1) * 4);
     splace(o_jobstate_, sizeof(JobState));
-    splace(o_nblocks_, 16);
+    splace(o_nblocks_, 32);
     state_bytes_ = align_up(state_bytes_, 256);
 
     // ---- meta blob: err | nulls | ptr table | batch bases (batch_base_off were assigned relative to o_bbase_)
