@@ -294,3 +294,31 @@ def test_host_section_decoders(ob):
                 assert got == exp, f"zstd damaged #{it}"
             else:
                 assert got is None, f"zstd damaged #{it}: libzstd fails, this decoder returns bytes"
+
+
+def test_mutated_files_plan_or_fail_cleanly(ob):
+    """Host robustness: every fixture with 1-3 random bytes overwritten (in the postscript / footer area, in the last
+    4 KB, or anywhere) either opens and plans, or fails with an OrcError - no crash, no hang, no giant allocation.
+    (What the device then decodes from damaged data streams is covered by the -m gpu corruption tests.)"""
+    import glob
+    import numpy as np
+    files = [f for sub in ("ref_basic", "ref_integration") for f in sorted(glob.glob(os.path.join(GOLDEN, sub, "*.orc")))
+             if 0 < os.path.getsize(f) < 400_000]
+    rng = np.random.default_rng(11)
+    ok = err = 0
+    for f in files:
+        data0 = open(f, "rb").read()
+        n = len(data0)
+        for it in range(45):
+            bad = bytearray(data0)
+            span = (min(n, 400), min(n, 4000), n)[it % 3]
+            for _ in range(int(rng.integers(1, 4))):
+                bad[n - 1 - int(rng.integers(0, span))] = int(rng.integers(0, 256))
+            try:
+                b = ob.ArrowReaderBuilder.try_new(bytes(bad))
+                b.schema()
+                ob.DecodeJob([bytes(bad)]).plan()
+                ok += 1
+            except ob.OrcError:
+                err += 1
+    assert ok > 500 and err > 500
