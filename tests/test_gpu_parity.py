@@ -122,7 +122,7 @@ def test_nested_generated(ob, tmp_path):
         "m": pa.array(rows_map, pa.map_(pa.string(), pa.int16())),
         "ll": pa.array(rows_ll, pa.list_(pa.list_(pa.string()))),
     })
-    for comp in ("uncompressed", "snappy", "zlib"):
+    for comp in ("uncompressed", "snappy", "zlib", "zstd"):
         p = str(tmp_path / f"nested_{comp}.orc")
         po.write_table(t, p, compression=comp, stripe_size=200_000, row_index_stride=1000)
         data = open(p, "rb").read()
@@ -430,7 +430,7 @@ def test_synthetic_configs(ob, tmp_path):
         ("nullheavy", gen_orc.nullheavy_table(60_000, 1), dict()),
     ]
     for name, table, kw in cases:
-        for comp in ("uncompressed", "snappy", "lz4"):
+        for comp in ("uncompressed", "snappy", "lz4", "zlib", "zstd"):
             p = str(tmp_path / f"{name}_{comp}.orc")
             gen_orc.write(table, p, compression=comp, block_size=64 << 10, **kw)
             data = open(p, "rb").read()
