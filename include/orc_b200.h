@@ -126,6 +126,8 @@ uint64_t orcb_file_compression_block_size(const OrcbFile* f);
 int64_t orcb_file_row_index_stride(const OrcbFile* f);     /* -1 when absent */
 uint32_t orcb_file_num_root_columns(const OrcbFile* f);
 const char* orcb_file_root_column_name(const OrcbFile* f, uint32_t i);
+/* ORC column index of root column i (what ProjectionMask::roots takes, src/projection.rs:37-50); 0 when out of range */
+uint32_t orcb_file_root_column_id(const OrcbFile* f, uint32_t i);
 /* StripeMetadata (src/stripe.rs:38-81): out[0..5) = offset, index_length, data_length, footer_length, rows */
 int orcb_file_stripe_info(const OrcbFile* f, uint32_t stripe, uint64_t out[5]);
 

@@ -106,7 +106,7 @@ READ_AT = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64, ctype
 EXPORTED_SYMBOLS = [
     "orcb_open_memory", "orcb_open_path", "orcb_open_callbacks", "orcb_file_io_stats", "orcb_file_clone", "orcb_file_free", "orcb_file_num_rows", "orcb_file_num_stripes",
     "orcb_file_compression", "orcb_file_compression_block_size", "orcb_file_row_index_stride",
-    "orcb_file_num_root_columns", "orcb_file_root_column_name", "orcb_file_stripe_info", "orcb_schema",
+    "orcb_file_num_root_columns", "orcb_file_root_column_name", "orcb_file_root_column_id", "orcb_file_stripe_info", "orcb_schema",
     "orcb_reader_new", "orcb_reader_new_with_selection", "orcb_reader_new_ex", "orcb_reader_build", "orcb_reader_plan", "orcb_predicate_row_groups", "orcb_bloom_hash_long", "orcb_bloom_hash_bytes", "orcb_reader_counters", "orcb_selection_plan", "orcb_reader_free", "orcb_reader_total_row_count", "orcb_reader_next",
     "orcb_reader_next_device", "orcb_reader_next_async", "orcb_reader_drain", "orcb_job_new", "orcb_job_free", "orcb_job_plan", "orcb_job_stage",
     "orcb_job_launch", "orcb_job_finish", "orcb_job_stats", "orcb_job_restage", "orcb_job_kernel_stats", "orcb_job_num_batches", "orcb_job_export_batch",
@@ -137,6 +137,8 @@ def lib() -> ctypes.CDLL:
                      "orcb_reader_total_row_count", "orcb_job_num_batches"):
             getattr(L, name).argtypes = [ctypes.c_void_p]
         L.orcb_file_root_column_name.argtypes = [ctypes.c_void_p, ctypes.c_uint32]
+        L.orcb_file_root_column_id.argtypes = [ctypes.c_void_p, ctypes.c_uint32]
+        L.orcb_file_root_column_id.restype = ctypes.c_uint32
         L.orcb_selection_plan.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint64,
                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
         L.orcb_reader_plan.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p,
@@ -296,6 +298,12 @@ class _File:
         n = lib().orcb_file_num_root_columns(self._h)
         return [lib().orcb_file_root_column_name(self._h, i).decode() for i in range(n)]
 
+    @property
+    def column_ids(self) -> List[int]:
+        """ORC column index of every root column (`DataType::column_index`, src/schema.rs:325)."""
+        n = lib().orcb_file_num_root_columns(self._h)
+        return [int(lib().orcb_file_root_column_id(self._h, i)) for i in range(n)]
+
     def stripe_info(self, i: int):
         out = (ctypes.c_uint64 * 5)()
         _check(lib().orcb_file_stripe_info(self._h, i, out))
@@ -355,6 +363,9 @@ class RowSelector:
     def __repr__(self):
         return f"RowSelector({'skip' if self.skip else 'select'} {self.row_count})"
 
+    def __eq__(self, other):
+        return isinstance(other, RowSelector) and (self.row_count, self.skip) == (other.row_count, other.skip)
+
 
 class RowSelection:
     """src/row_selection.rs:90-460 (the parts a reader needs): a list of selectors, normalised on construction
@@ -383,6 +394,8 @@ class RowSelection:
         for a, b in ranges:
             if b <= a:
                 continue
+            if a < last:
+                raise ValueError("ranges must be provided in order and must not overlap")
             if a > last:
                 sel.append(RowSelector(a - last, True))
             sel.append(RowSelector(b - a, False))
@@ -399,11 +412,123 @@ class RowSelection:
     def skip_all(cls, row_count: int) -> "RowSelection":
         return cls([RowSelector(row_count, True)])
 
+    @classmethod
+    def from_filters(cls, filters) -> "RowSelection":
+        """:105-142: boolean arrays (pyarrow BooleanArray or sequences of bool, no nulls), one after the other."""
+        ranges, offset = [], 0
+        for f in filters:
+            if hasattr(f, "null_count"):
+                assert f.null_count == 0, "filter arrays must not contain nulls"
+                f = f.to_pylist()
+            start = None
+            for idx, v in enumerate(f):
+                if v and start is None:
+                    start = idx
+                elif not v and start is not None:
+                    ranges.append((start + offset, idx + offset))
+                    start = None
+            if start is not None:
+                ranges.append((start + offset, len(f) + offset))
+            offset += len(f)
+        return cls.from_consecutive_ranges(ranges, offset)
+
+    @classmethod
+    def from_row_group_filter(cls, row_group_filter, rows_per_group: int, total_rows: int) -> "RowSelection":
+        """:348-392: one bool per row group; rows behind the last group are skipped."""
+        if not len(row_group_filter):
+            return cls.skip_all(total_rows)
+        sel = [RowSelector(rows_per_group, not keep) for keep in row_group_filter]
+        covered = len(row_group_filter) * rows_per_group
+        if covered < total_rows:
+            sel.append(RowSelector(total_rows - covered, True))
+        return cls(sel)
+
     def row_count(self) -> int:
         return sum(x.row_count for x in self.selectors)
 
     def selected_row_count(self) -> int:
         return sum(x.row_count for x in self.selectors if not x.skip)
+
+    def skipped_row_count(self) -> int:
+        return sum(x.row_count for x in self.selectors if x.skip)
+
+    def selects_any(self) -> bool:
+        return any(not x.skip for x in self.selectors)
+
+    def iter(self):
+        return iter(self.selectors)
+
+    def __iter__(self):
+        return iter(self.selectors)
+
+    def __eq__(self, other):
+        return isinstance(other, RowSelection) and [(x.row_count, x.skip) for x in self.selectors] == \
+            [(x.row_count, x.skip) for x in other.selectors]
+
+    def __repr__(self):
+        return f"RowSelection({self.selectors})"
+
+    def split_off(self, row_count: int) -> "RowSelection":
+        """:278-317: returns the first `row_count` rows, keeps the rest."""
+        total = 0
+        for idx, x in enumerate(self.selectors):
+            total += x.row_count
+            if total > row_count:
+                break
+        else:
+            first, self.selectors = self.selectors, []
+            return RowSelection(first)
+        first, rest = self.selectors[:idx], [RowSelector(x.row_count, x.skip) for x in self.selectors[idx:]]
+        overflow = total - row_count
+        if rest[0].row_count != overflow:
+            first.append(RowSelector(rest[0].row_count - overflow, rest[0].skip))
+        rest[0].row_count = overflow
+        self.selectors = rest
+        out = RowSelection()
+        out.selectors = first
+        return out
+
+    def and_then(self, other: "RowSelection") -> "RowSelection":
+        """:401-463: `other` addresses the rows this selection selects; the result addresses all rows."""
+        out, to_skip = [], 0
+        first = [[x.row_count, x.skip] for x in self.selectors]
+        second = [[x.row_count, x.skip] for x in other.selectors]
+        i = j = 0
+        while j < len(second):
+            b = second[j]
+            if i >= len(first):
+                raise ValueError("selection exceeds the number of selected rows")
+            a = first[i]
+            if b[0] == 0:
+                j += 1
+                continue
+            if a[0] == 0:
+                i += 1
+                continue
+            if a[1]:
+                to_skip += a[0]
+                i += 1
+                continue
+            n = min(a[0], b[0])
+            a[0] -= n
+            b[0] -= n
+            if b[1]:
+                to_skip += n
+            else:
+                if to_skip:
+                    out.append(RowSelector(to_skip, True))
+                    to_skip = 0
+                out.append(RowSelector(n, False))
+        for cnt, skip in first[i:]:
+            if cnt:
+                if not skip:
+                    raise ValueError("selection contains less than the number of selected rows")
+                to_skip += cnt
+        if to_skip:
+            out.append(RowSelector(to_skip, True))
+        res = RowSelection()
+        res.selectors = out
+        return res
 
 
 class _PredicateNodeC(ctypes.Structure):
@@ -527,6 +652,31 @@ class Predicate:
         return arr, keep
 
 
+class ProjectionMask:
+    """src/projection.rs:24-80: which root columns to read (a root column brings its whole subtree)."""
+
+    def __init__(self, names=None):
+        self.names = None if names is None else list(names)
+
+    @classmethod
+    def all(cls) -> "ProjectionMask":
+        return cls(None)
+
+    @classmethod
+    def roots(cls, file, indices) -> "ProjectionMask":
+        """By ORC column index of the root columns (:37-50); indices that name no root column are ignored."""
+        f = file.file_metadata() if hasattr(file, "file_metadata") else file
+        want = set(int(i) for i in indices)
+        return cls([n for n, cid in zip(f.column_names, f.column_ids) if cid in want])
+
+    @classmethod
+    def named_roots(cls, file, names) -> "ProjectionMask":
+        """By name (:53-69); names the file does not have are ignored."""
+        f = file.file_metadata() if hasattr(file, "file_metadata") else file
+        want = set(names)
+        return cls([n for n in f.column_names if n in want])
+
+
 class ArrowReaderBuilder:
     """Mirror of `ArrowReaderBuilder` (src/arrow_reader.rs:39-231) with one extra option, `with_device`."""
 
@@ -553,9 +703,12 @@ class ArrowReaderBuilder:
         self._batch_size = batch_size
         return self
 
-    def with_projection(self, names: Sequence[str]) -> "ArrowReaderBuilder":
-        """ProjectionMask::named_roots (src/projection.rs:58-73)."""
-        self._projection = list(names)
+    def with_projection(self, names) -> "ArrowReaderBuilder":
+        """A ProjectionMask, or root column names (= ProjectionMask::named_roots, src/projection.rs:53-69)."""
+        if isinstance(names, ProjectionMask):
+            self._projection = None if names.names is None else list(names.names)
+        else:
+            self._projection = list(names)
         return self
 
     def with_file_byte_range(self, start: int, end: int) -> "ArrowReaderBuilder":

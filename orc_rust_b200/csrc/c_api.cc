@@ -298,6 +298,7 @@ uint32_t orcb_file_num_root_columns(const OrcbFile* f) { return (uint32_t)f->met
 const char* orcb_file_root_column_name(const OrcbFile* f, uint32_t i) {
     return i < f->meta.root_columns.size() ? f->meta.root_columns[i].first.c_str() : nullptr;
 }
+uint32_t orcb_file_root_column_id(const OrcbFile* f, uint32_t i) { return i < f->meta.root_columns.size() ? f->meta.root_columns[i].second : 0u; }
 int orcb_file_stripe_info(const OrcbFile* f, uint32_t stripe, uint64_t out[5]) {
     return guarded([&] {
         if (stripe >= f->meta.stripes.size()) fail(ORCB_INVALID_ARGUMENT, "stripe index out of range");

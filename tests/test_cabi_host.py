@@ -322,3 +322,62 @@ def test_mutated_files_plan_or_fail_cleanly(ob):
             except ob.OrcError:
                 err += 1
     assert ok > 500 and err > 500
+
+
+def test_row_selection_api(ob):
+    """The reference's own unit tests of RowSelection (src/row_selection.rs:497-722), against the mirror."""
+    RS, S = ob.RowSelection, ob.RowSelector
+    sel, skip = S.select, S.skip_rows
+    assert (sel(100).row_count, sel(100).skip) == (100, False) and (skip(50).row_count, skip(50).skip) == (50, True)
+    s = RS.from_consecutive_ranges([(5, 10), (15, 20)], 25)
+    assert s.selectors == [skip(5), sel(5), skip(5), sel(5), skip(5)]
+    assert (s.row_count(), s.selected_row_count(), s.skipped_row_count()) == (25, 10, 15)
+    assert RS([skip(5), skip(5), sel(10), sel(5)]).selectors == [skip(10), sel(15)]
+    a = RS.select_all(100)
+    assert (a.row_count(), a.selected_row_count(), a.skipped_row_count(), a.selects_any()) == (100, 100, 0, True)
+    a = RS.skip_all(100)
+    assert (a.row_count(), a.selected_row_count(), a.skipped_row_count(), a.selects_any()) == (100, 0, 100, False)
+    s = RS.from_consecutive_ranges([(10, 30), (40, 60)], 100)
+    first = s.split_off(35)
+    assert (first.row_count(), s.row_count(), first.selected_row_count(), s.selected_row_count()) == (35, 65, 20, 20)
+    assert first.selectors == [skip(10), sel(20), skip(5)] and s.selectors == [skip(5), sel(20), skip(40)]
+    whole = RS.select_all(10)
+    assert whole.split_off(50).selectors == [sel(10)] and whole.selectors == []
+    r = RS.from_consecutive_ranges([(5, 15)], 20).and_then(RS.from_consecutive_ranges([(2, 7)], 10))
+    assert r.selectors == [skip(7), sel(5), skip(8)] and (r.row_count(), r.selected_row_count()) == (20, 5)
+    with pytest.raises(ValueError):
+        RS.select_all(5).and_then(RS.select_all(6))
+    assert RS.from_filters([[False, False, True, True, False]]).selectors == [skip(2), sel(2), skip(1)]
+    assert RS.from_filters([pa.array([True, False]), pa.array([False, True, True])]).selectors == [sel(1), skip(2), sel(2)]
+    e = RS()
+    assert (e.row_count(), e.selected_row_count(), e.selects_any()) == (0, 0, False)
+    with pytest.raises(ValueError):
+        RS.from_consecutive_ranges([(10, 20), (5, 15)], 25)
+    f = RS.from_row_group_filter
+    s = f([False, True, False], 10000, 30000)
+    assert s.selectors == [skip(10000), sel(10000), skip(10000)]
+    assert (s.row_count(), s.selected_row_count(), s.skipped_row_count()) == (30000, 10000, 20000)
+    assert f([True, True, True], 10000, 30000).selectors == [sel(30000)]
+    assert f([False, False, False], 10000, 30000).selectors == [skip(30000)]
+    assert f([False, False, True, True, False], 10000, 50000).selectors == [skip(20000), sel(20000), skip(10000)]
+    assert f([True, False], 10000, 25000).selectors == [sel(10000), skip(15000)]
+    assert f([], 10000, 50000).selectors == [skip(50000)]
+    assert list(s.iter()) == s.selectors
+
+
+def test_projection_mask(ob):
+    """ProjectionMask::{all, roots, named_roots} (src/projection.rs:24-80): root columns by ORC column index or name."""
+    path = os.path.join(GOLDEN, "ref_basic", "nested_struct.orc")
+    b = ob.ArrowReaderBuilder.try_new(path)
+    f = b.file_metadata()
+    names, ids = f.column_names, f.column_ids
+    assert len(names) == len(ids) and ids == sorted(ids) and ids[0] == 1
+    assert ob.ProjectionMask.all().names is None
+    assert ob.ProjectionMask.roots(f, [ids[0], 999]).names == [names[0]]
+    assert ob.ProjectionMask.named_roots(b, [names[-1], "no such column"]).names == [names[-1]]
+    path = os.path.join(GOLDEN, "ref_basic", "test.orc")
+    b = ob.ArrowReaderBuilder.try_new(path)
+    f = b.file_metadata()
+    m = ob.ProjectionMask.roots(f, [f.column_ids[0], f.column_ids[3]])
+    assert b.with_projection(m).schema().names == [f.column_names[0], f.column_names[3]]
+    assert ob.ArrowReaderBuilder.try_new(path).with_projection(ob.ProjectionMask.all()).schema().names == f.column_names
