@@ -546,6 +546,11 @@ void Job::run_next_level() {
     for (uint32_t t = 0; t < tasks_.size(); t++) {
         StripeTask nt{tasks_[t].file, tasks_[t].stripe};
         nt.roots = next_roots(t);
+        if (tasks_[t].file->stripes[tasks_[t].stripe].data_length) {
+            // the level below decodes from the stripe bytes this level staged (this job outlives it)
+            nt.has_staged = true;
+            nt.staged_abs = reloc(task_in_off_[t]);
+        }
         tasks.push_back(std::move(nt));
     }
     ReadOptions o = orig_opt_;

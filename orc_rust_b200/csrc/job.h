@@ -69,6 +69,9 @@ struct StripeTask {
     const FileMeta* file;
     uint32_t stripe;
     std::vector<RootSpec> roots;  // empty: the projected root columns over the stripe's rows
+    // a later nesting level reads the stripe bytes its parent level staged (absolute device address of the data area)
+    bool has_staged = false;
+    uint64_t staged_abs = 0;
     // row selection (src/array_decoder/mod.rs:313-364): the batches of this stripe are these row ranges, in order,
     // instead of consecutive batch_size slices.  The stripe is decoded once; the ranges are exported as views.
     bool has_views = false;
@@ -203,6 +206,7 @@ class Job {
         uint64_t dst_off, bytes;
     };
     std::vector<StageCopy> stage_copies_;
+    std::vector<uint64_t> task_in_off_;  // per task: tagged address of the stripe's staged data area
     std::vector<std::shared_ptr<RangeBuf>> range_keep_;  // stripes read through callbacks, held while this job stages from them
 
     // device blobs

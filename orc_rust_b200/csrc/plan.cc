@@ -79,6 +79,7 @@ void Job::plan() {
     if (planned_) return;
     if (opt_.batch_size == 0) fail(ORCB_INVALID_ARGUMENT, "batch_size must be > 0");
     task_first_cs_.clear();
+    task_in_off_.clear();
     staged_stripes_.clear();
     for (auto& t : tasks_) view_mode_ |= t.has_views;
     // nested columns: children have as many slots as their parents' data says, batches of a list's children do not
@@ -243,7 +244,9 @@ void Job::plan_stripe(uint32_t task_idx) {
 
     // stage the stripe's data area once (tasks that decode different row-group windows of one stripe share it)
     uint64_t in_off = 0;
-    if (si.data_length) {
+    if (tasks_[task_idx].has_staged) {
+        in_off = aref(AR_ABS, tasks_[task_idx].staged_abs);
+    } else if (si.data_length) {
         auto key = std::make_pair((const void*)&fm, stripe);
         auto it = staged_stripes_.find(key);
         if (it != staged_stripes_.end()) {
@@ -254,6 +257,8 @@ void Job::plan_stripe(uint32_t task_idx) {
             staged_stripes_[key] = in_off;
         }
     }
+
+    task_in_off_.push_back(in_off);
 
     // row-index stride usable for this stripe?
     uint32_t stride = stripe_rows ? stripe_rows : 1;
