@@ -54,7 +54,7 @@ def _bench_dir():
 def _dataset(rows: int, n_files: int, compression: str):
     import gen_orc
     t0 = time.time()
-    if compression in ("lz4", "snappy-recompressed", "zstd", "lzo"):
+    if compression in ("lz4", "lz4-lib", "snappy-recompressed", "zstd", "lzo"):
         # pyarrow's LZ4 writer stores every chunk "original": real LZ4 (and an identically chunked Snappy variant)
         # comes from the in-repo re-compressor applied to the uncompressed set
         import orc_recompress
@@ -437,7 +437,7 @@ def other_configs(torch, ob, args, device, peak, sf10_files):
     case("2", lambda: single_job_case(torch, ob, f"2: lineitem SF10 ({args.rows} rows, {args.files} files), NONE, one DecodeJob",
                                       sf10_files, device, peak, steps=10, parity=(sf10_files[0], 1) if check else None))
     for comp, label in (("snappy", "Snappy (pyarrow writer, 256 KiB chunks)"), ("snappy-recompressed", "Snappy (in-repo re-compressor, 256 KiB chunks)"),
-                        ("lz4", "LZ4 (in-repo re-compressor, 256 KiB chunks)"),
+                        ("lz4-lib", "LZ4 (liblz4 blocks framed by the in-repo re-compressor, 256 KiB chunks)"),
                         ("zstd", "Zstandard level 3 (in-repo re-compressor, 256 KiB chunks)")):
         def mk(comp=comp, label=label):
             files, _ = _dataset(args.rows, args.files, comp)
@@ -477,7 +477,7 @@ def main():
     ap.add_argument("--rows", type=int, default=SF10_ROWS, help="rows of one tile (default: SF10)")
     ap.add_argument("--files", type=int, default=32, help="ORC files of one tile")
     ap.add_argument("--tiles", type=int, default=7, help="times the tile is repeated (7 x SF10 = 672 stripes)")
-    ap.add_argument("--compression", default="uncompressed", choices=["uncompressed", "snappy", "lz4", "snappy-recompressed", "zstd", "lzo"])
+    ap.add_argument("--compression", default="uncompressed", choices=["uncompressed", "snappy", "lz4", "lz4-lib", "snappy-recompressed", "zstd", "lzo"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-row-index", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the configs array (1, 2, 3, 4)")

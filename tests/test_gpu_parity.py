@@ -1141,12 +1141,14 @@ def test_decompress_tile_decoder(ob, kind):
         for bs in (65536, 262144, 1000):
             if bs == 1000 and len(data) > 200_000:
                 continue
-            framed = lzcodec.orc_frame(data, kind, bs)
-            assert bytes(oo.decompress_stream(code, framed, bs)) == data
-            got = ob.decompress_stream(code, framed, bs)
-            if got != data:
-                bad = next(i for i in range(min(len(got), len(data))) if got[i] != data[i]) if len(got) == len(data) else -1
-                raise AssertionError(f"{kind} {name} block {bs}: device output differs (len {len(got)} vs {len(data)}, first at {bad})")
+            # the in-repo compressor (shapes chosen to exercise the decoder) and the library's own output (liblz4 / snappy)
+            for comp in (kind, kind + "-lib"):
+                framed = lzcodec.orc_frame(data, comp, bs)
+                assert bytes(oo.decompress_stream(code, framed, bs)) == data
+                got = ob.decompress_stream(code, framed, bs)
+                if got != data:
+                    bad = next(i for i in range(min(len(got), len(data))) if got[i] != data[i]) if len(got) == len(data) else -1
+                    raise AssertionError(f"{comp} {name} block {bs}: device output differs (len {len(got)} vs {len(data)}, first at {bad})")
     # damaged blocks: same verdict as the oracle, same bytes when both decode
     text = _lz_patterns(rng)["text"][:100_000]
     framed0 = bytearray(lzcodec.orc_frame(text, kind, 65536))

@@ -28,9 +28,11 @@ def lib():
 def compress_block(kind: str, data: bytes) -> bytes:
     L = lib()
     buf = ctypes.create_string_buffer(L.lzc_bound(len(data)))
-    if kind == "zstd":
+    if kind in ("zstd", "lz4-lib", "snappy-lib"):
+        # the libraries themselves (libzstd, liblz4, snappy) through pyarrow's codecs
         import pyarrow as pa
-        return pa.Codec("zstd", compression_level=3).compress(bytes(data), asbytes=True)
+        codec = pa.Codec("zstd", compression_level=3) if kind == "zstd" else pa.Codec("lz4_raw" if kind == "lz4-lib" else "snappy")
+        return codec.compress(bytes(data), asbytes=True) if len(data) else b""
     fn = {"lz4": L.lzc_lz4_compress, "snappy": L.lzc_snappy_compress, "lzo": L.lzc_lzo_compress}[kind]
     n = fn(bytes(data), len(data), buf)
     return buf.raw[:n]
