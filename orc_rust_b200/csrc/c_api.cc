@@ -1051,7 +1051,8 @@ int orcb_decompress_stream(int device, int compression_kind, const uint8_t* in, 
             CU(cudaEventRecord(e0, 0));
         }
         const bool bits = compression_kind == C_ZLIB || compression_kind == C_ZSTD || compression_kind == C_LZO;
-        int rc = launch_decompress((ChunkDesc*)ddesc.p, (uint32_t)chunks.size(), bits ? (uint32_t)chunks.size() : 0u, (uint32_t*)sr.err.p, (uint32_t*)dlens.p,
+        const uint32_t nc = (uint32_t)chunks.size();
+        int rc = launch_decompress((ChunkDesc*)ddesc.p, nc, bits ? nc : 0u, compression_kind == C_SNAPPY ? nc : 0u, (uint32_t*)sr.err.p, (uint32_t*)dlens.p,
                                    (uint32_t*)dctr.p, nullptr, 0);
         if (rc) fail(ORCB_CUDA, cudaGetErrorString((cudaError_t)rc));
         if (timing) {

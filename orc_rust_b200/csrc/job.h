@@ -220,7 +220,7 @@ class Job {
     // state blob (device only, zeroed per launch): cnt[], dstart[], mis[], JobState
     uint32_t n_cnt_ = 0, n_colstripes_ = 0;
     uint8_t* d_state_ = nullptr;
-    uint32_t n_bits_chunks_ = 0;  // leading chunks_ that go to k_decompress_bits
+    uint32_t n_bits_chunks_ = 0, n_snappy_chunks_ = 0;  // chunks_ is ordered: serial-chain codecs, Snappy, then LZ4 / stored
     uint64_t state_bytes_ = 0, o_cnt_ = 0, o_dstart_ = 0, o_mis_ = 0, o_jobstate_ = 0, o_nblocks_ = 0;
     // meta blob (device, zeroed per launch, copied to host at finish): err[], nulls[], ptr_table[], batch_base[]
     uint8_t* d_meta_ = nullptr;

@@ -1252,16 +1252,20 @@ __device__ uint32_t lzo_chunk(const uint8_t* __restrict__ s, uint32_t n, uint8_t
 }
 
 // Persistent warps over the chunk list (most expensive chunks first, see plan.cc); one chunk per warp at a time.
-// Two kernels, so that the tile decoder keeps its register allocation: k_decompress takes stored, Snappy and LZ4
-// chunks, k_decompress_bits the codecs whose chunk is one serial bit / instruction chain (Zlib, Zstandard, LZO) - and
-// stored chunks too when a list holds nothing else for the first kernel.
+// Three kernels, so that each keeps its register allocation and its code stays small (the Snappy and the LZ4 tile
+// decoder in one kernel are 175 KB of SASS: the LZ4 path then waits for instruction fetches a third of the time):
+// k_decompress<2> takes Snappy chunks, k_decompress<4> LZ4 and stored chunks, k_decompress_bits the codecs whose chunk is
+// one serial bit / instruction chain (Zlib, Zstandard, LZO).  Every kernel copies stored chunks it is handed.
+template <int CODEC>
 __global__ void __launch_bounds__(128, ORCB_LZ_CTAS) k_decompress(const ChunkDesc* __restrict__ chunks, uint32_t nchunks, uint32_t* err,
                                                        uint32_t* out_lens, uint32_t* counter, uint32_t* retry) {
     __shared__ LzWarp warp_sm[4];
     __shared__ uint32_t lut[256];
-    lut[threadIdx.x] = snappy_tag_entry(threadIdx.x);
-    lut[threadIdx.x + 128] = snappy_tag_entry(threadIdx.x + 128);
-    __syncthreads();
+    if (CODEC == 2) {
+        lut[threadIdx.x] = snappy_tag_entry(threadIdx.x);
+        lut[threadIdx.x + 128] = snappy_tag_entry(threadIdx.x + 128);
+        __syncthreads();
+    }
     const int lane = threadIdx.x & 31;
     LzWarp& sm = warp_sm[threadIdx.x >> 5];
     for (;;) {
@@ -1278,12 +1282,12 @@ __global__ void __launch_bounds__(128, ORCB_LZ_CTAS) k_decompress(const ChunkDes
             if (n > c.dst_cap) fail = ORCB_UNEXPECTED;
             else warp_copy_fwd(d, s, n, lane);
             o = n;
-        } else if (c.codec == 2) {
+        } else if (CODEC == 2 && c.codec == 2) {
             uint32_t p;
             uint64_t ulen;
             fail = snappy_preamble(s, n, c.dst_cap, p, ulen);
             if (!fail) fail = lz_chunk<2>(s, n, d, ulen, p, o, sm, lut, lane);
-        } else if (c.codec == 4) {
+        } else if (CODEC == 4 && c.codec == 4) {
             fail = lz_chunk<4>(s, n, d, c.dst_cap, 0, o, sm, lut, lane);
             // the size of a stream's last LZ4 chunk is only known here: what the layout reserved beyond it reads as zeros
             if (c.expect_len < 0 && !fail)
@@ -1356,20 +1360,28 @@ static uint32_t resident_ctas(K kernel, int& cache) {
     return (uint32_t)cache;
 }
 
-// The first n_bits chunks of the list go to k_decompress_bits, the rest to k_decompress.
-int launch_decompress(const ChunkDesc* c, uint32_t n, uint32_t n_bits, uint32_t* err, uint32_t* out_lens, uint32_t* counter, uint32_t* retry,
-                      cudaStream_t st) {
+// The first n_bits chunks of the list go to k_decompress_bits, the next n_snappy to k_decompress<2>, the rest (LZ4,
+// stored) to k_decompress<4>.  counter: three zeroed words.
+int launch_decompress(const ChunkDesc* c, uint32_t n, uint32_t n_bits, uint32_t n_snappy, uint32_t* err, uint32_t* out_lens, uint32_t* counter,
+                      uint32_t* retry, cudaStream_t st) {
     if (!n) return 0;
-    static int ctas_tile = 0, ctas_bits = 0;
+    static int ctas_snappy = 0, ctas_lz4 = 0, ctas_bits = 0;
     if (n_bits > n) n_bits = n;
+    if (n_snappy > n - n_bits) n_snappy = n - n_bits;
     if (n_bits) {
         const uint32_t grid = (uint32_t)std::min<uint64_t>(resident_ctas(k_decompress_bits, ctas_bits), ((uint64_t)n_bits + 3) / 4);
         k_decompress_bits<<<grid, 128, 0, st>>>(c, n_bits, err, out_lens, counter + 1, retry);
         LAUNCH_CHECK();
     }
-    if (n > n_bits) {
-        const uint32_t grid = (uint32_t)std::min<uint64_t>(resident_ctas(k_decompress, ctas_tile), ((uint64_t)(n - n_bits) + 3) / 4);
-        k_decompress<<<grid, 128, 0, st>>>(c + n_bits, n - n_bits, err, out_lens, counter, retry);
+    if (n_snappy) {
+        const uint32_t grid = (uint32_t)std::min<uint64_t>(resident_ctas(k_decompress<2>, ctas_snappy), ((uint64_t)n_snappy + 3) / 4);
+        k_decompress<2><<<grid, 128, 0, st>>>(c + n_bits, n_snappy, err, out_lens, counter, retry);
+        LAUNCH_CHECK();
+    }
+    const uint32_t rest = n - n_bits - n_snappy;
+    if (rest) {
+        const uint32_t grid = (uint32_t)std::min<uint64_t>(resident_ctas(k_decompress<4>, ctas_lz4), ((uint64_t)rest + 3) / 4);
+        k_decompress<4><<<grid, 128, 0, st>>>(c + n_bits + n_snappy, rest, err, out_lens, counter + 2, retry);
         LAUNCH_CHECK();
     }
     return 0;

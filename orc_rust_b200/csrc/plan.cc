@@ -112,14 +112,15 @@ void Job::plan() {
 
     // chunks that take longest first (compressed before stored, long before short): the persistent decompression
     // warps draw them in this order, so the launch does not end on one late, expensive chunk
-    // (Zlib / Zstandard / LZO chunks in front: they have a kernel of their own, launch_decompress)
-    auto chunk_key = [](const ChunkDesc& c) {
-        const bool bits = c.codec == 1 || c.codec == 3 || c.codec == 5;
-        return ((uint64_t)bits << 40) | ((uint64_t)(c.codec != 0) << 32) | c.src_len;
-    };
+    // (Zlib / Zstandard / LZO chunks in front, then Snappy, then LZ4 and stored: one kernel each, launch_decompress)
+    auto chunk_class = [](const ChunkDesc& c) -> uint64_t { return c.codec == 1 || c.codec == 3 || c.codec == 5 ? 2 : c.codec == 2 ? 1 : 0; };
+    auto chunk_key = [&](const ChunkDesc& c) { return (chunk_class(c) << 40) | ((uint64_t)(c.codec != 0) << 32) | c.src_len; };
     std::stable_sort(chunks_.begin(), chunks_.end(), [&](const ChunkDesc& a, const ChunkDesc& b) { return chunk_key(a) > chunk_key(b); });
-    n_bits_chunks_ = 0;
-    for (auto& c : chunks_) n_bits_chunks_ += (chunk_key(c) >> 40) & 1;
+    n_bits_chunks_ = n_snappy_chunks_ = 0;
+    for (auto& c : chunks_) {
+        n_bits_chunks_ += chunk_class(c) == 2;
+        n_snappy_chunks_ += chunk_class(c) == 1;
+    }
 
     if (n_chk_) chk_table_ = alloc(AR_TMP, (uint64_t)n_chk_ * sizeof(SegCheck));
     if (pool_blocks_) {
