@@ -7,7 +7,7 @@ nvidia-smi topo -m > $out/topo.txt 2>&1
 lscpu | grep -i -E "numa|model name|^cpu\(s\)|socket" >> $out/topo.txt 2>&1
 for d in /sys/bus/pci/devices/*; do if [ -f $d/class ] && grep -q "^0x0302" $d/class; then echo "$d numa $(cat $d/numa_node) $(cat $d/current_link_speed 2>/dev/null) x$(cat $d/current_link_width 2>/dev/null)"; fi; done >> $out/topo.txt 2>&1
 free -g >> $out/topo.txt
-( time python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps ${STEPS:-20} --warmup ${WARMUP:-5} ) > $out/bench_n$N.json 2> $out/bench_n$N.err
+( time python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps ${STEPS:-20} --warmup ${WARMUP:-5} $EXTRA ) > $out/bench_n$N.json 2> $out/bench_n$N.err
 tail -5 $out/bench_n$N.err
 python - "$out/bench_n$N.json" <<'PY'
 import json,sys
