@@ -652,6 +652,11 @@ void Job::plan_stripe(uint32_t task_idx) {
                         if (ci < sr.chunks.size() && sr.chunks[ci].original)
                             long_runs = rle2_opens_with_long_runs(sp + sr.chunks[ci].src_off, sr.chunks[ci].src_len,
                                                                   (uint32_t)(sg.start_byte - sr.chunk_dst[ci]));
+                        else
+                            // not readable here: decimal scales are constant runs in practice, and so is any stream that
+                            // spends less than a bit per value (sr.len is exact for Snappy and sized Zstandard frames,
+                            // an upper bound otherwise)
+                            long_runs = okind == OUT_SCALE || (uint64_t)sr.len * 8 < (uint64_t)n_rows;
                     }
                 }
                 if (!long_runs) {
