@@ -151,8 +151,8 @@ struct FileMeta {
     std::vector<ChunkInfo> chunk_table(uint64_t stream_off, uint64_t stream_len) const;
 };
 
-// Parses PostScript + Footer. Throws OrcException.  Zlib/Zstd/LZO files are rejected here with
-// ORCB_UNSUPPORTED_DEVICE_CODEC (their footers are never inflated on the host).
+// Parses PostScript + Footer. Throws OrcException.  The sections are decompressed on the host whatever the file's
+// compression kind (host_decompress_section); data streams never are.
 void parse_file_tail(FileMeta& fm);
 
 // Host-side chunk decompression for METADATA sections only (footer, stripe footer, row index).
