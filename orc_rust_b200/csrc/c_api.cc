@@ -918,7 +918,7 @@ int orcb_decode_int_rle(int device, const uint8_t* in, size_t in_len, int versio
         if (rc) fail(ORCB_CUDA, cudaGetErrorString((cudaError_t)rc));
         rc = launch_int_rle((Seg*)dseg.p, (BlockRec*)dblk.p, (uint32_t*)dcnt.p, pool, (RunRec*)dtab.p, nullptr, nullptr,
                             (uint32_t*)sr.err.p, (uint32_t*)mis.p, (uint32_t*)dslow.p, (uint32_t*)dcnt.p + 1,
-                            (CoopRec*)dq.p, (uint32_t*)dcnt.p + 2, qcap, 0);
+                            (CoopRec*)dq.p, (uint32_t*)dcnt.p + 2, qcap, nullptr, 0);
         if (rc) fail(ORCB_CUDA, cudaGetErrorString((cudaError_t)rc));
         sr.check();
         if (n_values) CU(cudaMemcpy(out, dout.p, n_values * 8, cudaMemcpyDeviceToHost));

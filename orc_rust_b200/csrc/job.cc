@@ -183,6 +183,7 @@ Job::~Job() {
     if (done_) cudaEventDestroy(done_);
     if (ev_fork_) cudaEventDestroy(ev_fork_);
     if (ev_join_) cudaEventDestroy(ev_join_);
+    if (ev_str_) cudaEventDestroy(ev_str_);
     if (aux_stream_) cudaStreamDestroy(aux_stream_);
     if (own_stream_ && stream_) cudaStreamDestroy(stream_);
     // device arenas are released by dev_keepalive_ (shared with exported device batches)
@@ -239,6 +240,7 @@ void Job::stage() {
     }
     CUDA_OK(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&ev_str_, cudaEventDisableTiming));
     t_streams = lap(tl);
     auto arenas = std::make_shared<DeviceArenas>();
     arenas->device = opt_.device;
@@ -384,6 +386,11 @@ void Job::launch() {
     // ORCB_SERIAL=1 keeps everything on one stream (clean per-kernel timings when profiling)
     const bool serial_env = getenv("ORCB_SERIAL") != nullptr;  // read at every launch: bench.py times one serial pass
     const bool forked = N(int_segs_) > 0;
+    // two phases of the short-run integer path when string columns wait for part of it and nothing sits between the
+    // integer decode and the string kernels (no dense -> rows expansion, no unions); ORCB_SPLIT_INT=0 disables
+    static const bool split_env = !(getenv("ORCB_SPLIT_INT") && getenv("ORCB_SPLIT_INT")[0] == '0');
+    const bool split_int = forked && !serial_env && split_env && n_str_int_segs_ > 0 && n_str_int_segs_ < N(int_segs_) &&
+                           N(strcols_) > 0 && N(spaced_) == 0 && N(unions_) == 0;
     cudaStream_t aux = serial_env ? st : aux_stream_;
     if (forked) {
         if (!serial_env) {
@@ -394,8 +401,25 @@ void Job::launch() {
         RunRec* rtab = (RunRec*)(uintptr_t)reloc(run_table_);
         BlockRec* brec = (BlockRec*)(uintptr_t)reloc(block_recs_);
         uint32_t* nblk = (uint32_t*)(d_state_ + o_nblocks_);
-        run("k_rle_index", 0, N(int_segs_), 1, [&] { return launch_rle_index((Seg*)(d_desc_ + o_int_), N(int_segs_), cnt, rtab, brec, nblk, pool_blocks_, (CoopRec*)(uintptr_t)reloc(coop_q_), nblk + 2, coop_cap_, err, segchk, aux); });
-        run("k_int_rle(+general,+coop_runs)", ab_int_, pool_blocks_, 3, [&] { return launch_int_rle((Seg*)(d_desc_ + o_int_), brec, nblk, pool_blocks_, rtab, cnt, dstart, err, mis, (uint32_t*)(uintptr_t)reloc(slow_list_), nblk + 1, (CoopRec*)(uintptr_t)reloc(coop_q_), nblk + 2, coop_cap_, aux); });
+        Seg* isegs = (Seg*)(d_desc_ + o_int_);
+        CoopRec* coopq = (CoopRec*)(uintptr_t)reloc(coop_q_);
+        uint32_t* slow = (uint32_t*)(uintptr_t)reloc(slow_list_);
+        if (split_int) {
+            // phase 1: the segments the string kernels wait for; phase 2 (the rest) appends to the same block pool and
+            // starts where the snapshot of the three counters says
+            const uint32_t na = n_str_int_segs_, nb = N(int_segs_) - n_str_int_segs_;
+            uint32_t* snap = nblk + 8;
+            run("k_rle_index(strings)", 0, na, 1, [&] { return launch_rle_index(isegs, na, cnt, rtab, brec, nblk, pool_blocks_, coopq, nblk + 2, coop_cap_, err, segchk, aux); });
+            run("k_int_rle(strings)", 0, pool_blocks_, 3, [&] { return launch_int_rle(isegs, brec, nblk, pool_blocks_, rtab, cnt, dstart, err, mis, slow, nblk + 1, coopq, nblk + 2, coop_cap_, nullptr, aux); });
+            CUDA_OK(cudaEventRecord(ev_str_, aux));
+            chk(launch_snapshot3(nblk, snap, aux), "k_snapshot3");
+            launches += 1;
+            run("k_rle_index", 0, nb, 1, [&] { return launch_rle_index(isegs + na, nb, cnt, rtab, brec, nblk, pool_blocks_, coopq, nblk + 2, coop_cap_, err, segchk, aux); });
+            run("k_int_rle(+general,+coop_runs)", ab_int_, pool_blocks_, 3, [&] { return launch_int_rle(isegs + na, brec, nblk, pool_blocks_, rtab, cnt, dstart, err, mis, slow, nblk + 1, coopq, nblk + 2, coop_cap_, snap, aux); });
+        } else {
+            run("k_rle_index", 0, N(int_segs_), 1, [&] { return launch_rle_index(isegs, N(int_segs_), cnt, rtab, brec, nblk, pool_blocks_, coopq, nblk + 2, coop_cap_, err, segchk, aux); });
+            run("k_int_rle(+general,+coop_runs)", ab_int_, pool_blocks_, 3, [&] { return launch_int_rle(isegs, brec, nblk, pool_blocks_, rtab, cnt, dstart, err, mis, slow, nblk + 1, coopq, nblk + 2, coop_cap_, nullptr, aux); });
+        }
         if (!serial_env) CUDA_OK(cudaEventRecord(ev_join_, aux));
         cur_st = st;
     }
@@ -413,14 +437,20 @@ void Job::launch() {
         if (*o == 'k' && N(copy_tiles_))
             run("k_copy", ab_copy_, N(copy_tiles_), 1, [&] { return launch_copy((CopyDesc*)(d_desc_ + o_copy_), (uint2*)(d_desc_ + o_ctile_), N(copy_tiles_), cnt, err, (StrCol*)(d_desc_ + o_str_), st); });
     }
+    auto strings = [&] {
+        run("k_strings(5 kernels)", ab_str_, str_tiles_, 5, [&] { return launch_strings((StrCol*)(d_desc_ + o_str_), N(strcols_), str_tiles_, err, dstate, (uint64_t)(uintptr_t)base_[AR_HEAP], heap_cap, ptrs, st); });
+    };
+    if (split_int) {
+        CUDA_OK(cudaStreamWaitEvent(st, ev_str_, 0));
+        strings();
+    }
     if (forked && !serial_env) CUDA_OK(cudaStreamWaitEvent(st, ev_join_, 0));
     // strings first: they close the longer chain
     if (N(spaced_))
         run("k_spaced", ab_spaced_, N(spaced_), 1, [&] { return launch_spaced((SpacedDesc*)(d_desc_ + o_sp_), N(spaced_), dstart, st); });
     if (N(unions_))
         run("k_union_valid", 0, N(unions_), 1, [&] { return launch_union_valid((UnionDesc*)(d_desc_ + o_union_), N(unions_), nulls, st); });
-    if (N(strcols_))
-        run("k_strings(5 kernels)", ab_str_, str_tiles_, 5, [&] { return launch_strings((StrCol*)(d_desc_ + o_str_), N(strcols_), str_tiles_, err, dstate, (uint64_t)(uintptr_t)base_[AR_HEAP], heap_cap, ptrs, st); });
+    if (N(strcols_) && !split_int) strings();
     if (N(chk_pairs_))  // every segment has left its start and end position: do they join up?
         run("k_seg_check", 0, N(chk_pairs_), 1, [&] { return launch_seg_check((uint2*)(d_desc_ + o_chkpair_), N(chk_pairs_), segchk, (uint32_t*)(d_meta_ + o_retry_), st); });
     if (N(decfix_) && N(int_big_segs_))  // scales that were only compared so far are written where one of them differed

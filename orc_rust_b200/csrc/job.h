@@ -220,6 +220,7 @@ class Job {
     // state blob (device only, zeroed per launch): cnt[], dstart[], mis[], JobState
     uint32_t n_cnt_ = 0, n_colstripes_ = 0;
     uint8_t* d_state_ = nullptr;
+    uint32_t n_str_int_segs_ = 0;  // leading int_segs_ that feed the string kernels (string lengths, dictionary keys)
     uint32_t n_bits_chunks_ = 0, n_snappy_chunks_ = 0;  // chunks_ is ordered: serial-chain codecs, Snappy, then LZ4 / stored
     uint64_t state_bytes_ = 0, o_cnt_ = 0, o_dstart_ = 0, o_mis_ = 0, o_jobstate_ = 0, o_nblocks_ = 0;
     // meta blob (device, zeroed per launch, copied to host at finish): err[], nulls[], ptr_table[], batch_base[]
@@ -255,7 +256,7 @@ class Job {
              ab_spaced_ = 0, ab_dec_ = 0, ab_ts_ = 0, ab_str_ = 0, ab_repack_ = 0;
 
     cudaStream_t aux_stream_ = nullptr;  // latency-bound pre-pass + short-run integer decode overlap the rest
-    cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr;
+    cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr, ev_str_ = nullptr;
     cudaStream_t stream_ = nullptr;
     bool own_stream_ = false;
     cudaEvent_t done_ = nullptr;

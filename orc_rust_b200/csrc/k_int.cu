@@ -981,14 +981,16 @@ __global__ void __launch_bounds__(RLE_WARPS * 32) k_int_rle(const Seg* __restric
                                                             const RunRec* __restrict__ table,
                                                             const uint32_t* __restrict__ cnt,
                                                             const uint32_t* __restrict__ dstart, uint32_t* err,
-                                                            uint32_t* mis, uint32_t* slow_list, uint32_t* slow_count) {
+                                                            uint32_t* mis, uint32_t* slow_list, uint32_t* slow_count,
+                                                            const uint32_t* __restrict__ first) {
     __shared__ int64_t tile_all[RLE_WARPS][TILE_VALUES];
     const uint32_t nblocks = *nblocks_ptr;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
     const int lane = threadIdx.x & 31;
     RunSlot* slots = nullptr;
-    // persistent warps: the number of run blocks is only known on the device
-    for (uint32_t blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; blk < nblocks; blk += nwarps) {
+    // persistent warps: the number of run blocks is only known on the device.  `first`: (blocks, general blocks, queued
+    // runs) an earlier phase of this launch has already decoded (the segments that feed the string kernels go first)
+    for (uint32_t blk = (first ? first[0] : 0u) + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); blk < nblocks; blk += nwarps) {
         const bool done = int_rle_block<true>(segs, blocks[blk], table + (uint64_t)blk * 32, cnt, dstart, err, mis, nullptr,
                                               slots, tile_all[threadIdx.x >> 5], lane);
         if (!done && lane == 0) slow_list[atomicAdd(slow_count, 1u)] = blk;
@@ -1003,13 +1005,13 @@ __global__ void __launch_bounds__(RLE_WARPS * 32) k_int_rle_general(const Seg* _
                                                                     const RunRec* __restrict__ table,
                                                                     const uint32_t* __restrict__ cnt,
                                                                     const uint32_t* __restrict__ dstart, uint32_t* err,
-                                                                    uint32_t* mis) {
+                                                                    uint32_t* mis, const uint32_t* __restrict__ first) {
     __shared__ uint32_t patchmap_all[RLE_WARPS][16];
     __shared__ RunSlot slots_all[RLE_WARPS][32];
     const uint32_t nslow = *slow_count;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
     const int lane = threadIdx.x & 31;
-    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nslow; i += nwarps) {
+    for (uint32_t i = (first ? first[1] : 0u) + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); i < nslow; i += nwarps) {
         const uint32_t blk = slow_list[i];
         int_rle_block<false>(segs, blocks[blk], table + (uint64_t)blk * 32, cnt, dstart, err, mis,
                              patchmap_all[threadIdx.x >> 5], slots_all[threadIdx.x >> 5], nullptr, lane);
@@ -1021,11 +1023,11 @@ __global__ void __launch_bounds__(RLE_WARPS * 32) k_coop_runs(const Seg* __restr
                                                               const uint32_t* __restrict__ nq_ptr, uint32_t cap,
                                                               const uint32_t* __restrict__ cnt,
                                                               const uint32_t* __restrict__ dstart, uint32_t* err,
-                                                              uint32_t* mis) {
+                                                              uint32_t* mis, const uint32_t* __restrict__ first) {
     __shared__ uint32_t patchmap_all[RLE_WARPS][16];
     const uint32_t nq = min(*nq_ptr, cap);
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nq; i += nwarps) {
+    for (uint32_t i = (first ? min(first[2], cap) : 0u) + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); i < nq; i += nwarps) {
         const CoopRec r = q[i];
         SegCtx c;
         c.s = &segs[r.seg];
@@ -1130,7 +1132,8 @@ int launch_rle_index(const Seg* segs, uint32_t n, const uint32_t* cnt, RunRec* t
 }
 int launch_int_rle(const Seg* segs, const BlockRec* blocks, const uint32_t* nblocks, uint32_t pool_blocks, const RunRec* table,
                    const uint32_t* cnt, const uint32_t* dstart, uint32_t* err, uint32_t* mis, uint32_t* slow_list,
-                   uint32_t* slow_count, const CoopRec* coop_q, const uint32_t* ncoop, uint32_t coop_cap, cudaStream_t st) {
+                   uint32_t* slow_count, const CoopRec* coop_q, const uint32_t* ncoop, uint32_t coop_cap, const uint32_t* first,
+                   cudaStream_t st) {
     if (!pool_blocks) return 0;
     // persistent grids: enough CTAs to fill every SM, never more warps than blocks could exist
     static int ctas_fast = 0, ctas_gen = 0;
@@ -1145,17 +1148,26 @@ int launch_int_rle(const Seg* segs, const BlockRec* blocks, const uint32_t* nblo
     }
     const uint64_t need = ((uint64_t)pool_blocks + RLE_WARPS - 1) / RLE_WARPS;
     k_int_rle<<<(uint32_t)std::min<uint64_t>(ctas_fast, need), RLE_WARPS * 32, 0, st>>>(segs, blocks, nblocks, table, cnt, dstart,
-                                                                                         err, mis, slow_list, slow_count);
+                                                                                         err, mis, slow_list, slow_count, first);
     LAUNCH_CHECK();
     k_int_rle_general<<<(uint32_t)std::min<uint64_t>(ctas_gen, need), RLE_WARPS * 32, 0, st>>>(segs, blocks, slow_list, slow_count,
-                                                                                                table, cnt, dstart, err, mis);
+                                                                                                table, cnt, dstart, err, mis, first);
     LAUNCH_CHECK();
     if (coop_cap) {
         const uint64_t needq = ((uint64_t)coop_cap + RLE_WARPS - 1) / RLE_WARPS;
         k_coop_runs<<<(uint32_t)std::min<uint64_t>(ctas_gen, needq), RLE_WARPS * 32, 0, st>>>(segs, coop_q, ncoop, coop_cap, cnt, dstart,
-                                                                                               err, mis);
+                                                                                               err, mis, first);
         LAUNCH_CHECK();
     }
+    return 0;
+}
+// (blocks, general blocks, queued runs) so far -> dst[0..2]: where the next phase of the integer path starts
+__global__ void k_snapshot3(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst) {
+    if (threadIdx.x < 3) dst[threadIdx.x] = src[threadIdx.x];
+}
+int launch_snapshot3(const uint32_t* src, uint32_t* dst, cudaStream_t st) {
+    k_snapshot3<<<1, 32, 0, st>>>(src, dst);
+    LAUNCH_CHECK();
     return 0;
 }
 int launch_int_rle_coop(const Seg* segs, uint32_t n, const uint32_t* cnt, const uint32_t* dstart, uint32_t* err,

@@ -13,7 +13,11 @@ int launch_rle_index(const Seg* segs, uint32_t n, const uint32_t* cnt, RunRec* t
                      cudaStream_t st);
 int launch_int_rle(const Seg* segs, const BlockRec* blocks, const uint32_t* nblocks, uint32_t pool_blocks, const RunRec* table,
                    const uint32_t* cnt, const uint32_t* dstart, uint32_t* err, uint32_t* mis, uint32_t* slow_list,
-                   uint32_t* slow_count, const CoopRec* coop_q, const uint32_t* ncoop, uint32_t coop_cap, cudaStream_t st);
+                   uint32_t* slow_count, const CoopRec* coop_q, const uint32_t* ncoop, uint32_t coop_cap, const uint32_t* first,
+                   cudaStream_t st);
+// first (may be NULL): three device words = (blocks, general blocks, queued runs) an earlier phase already decoded;
+// launch_snapshot3 copies the three counters there between the phases
+int launch_snapshot3(const uint32_t* src, uint32_t* dst, cudaStream_t st);
 // second_pass = 1: only the decimal scale segments of column-stripes whose mismatch flag is set, every value written
 int launch_int_rle_coop(const Seg* segs, uint32_t n, const uint32_t* cnt, const uint32_t* dstart, uint32_t* err,
                         uint32_t* mis, int second_pass, SegCheck* chk, cudaStream_t st);

@@ -106,8 +106,14 @@ void Job::plan() {
     // short-run segment by index before the walk assigns it blocks on the device.
     {
         static const char* e = getenv("ORCB_SORT_SEGS");
-        if (!(e && e[0] == '0'))
-            std::stable_sort(int_segs_.begin(), int_segs_.end(), [](const Seg& a, const Seg& b) { return a.run_cap > b.run_cap; });
+        n_str_int_segs_ = 0;
+        if (!(e && e[0] == '0')) {
+            // ... and the segments the string kernels wait for (lengths, dictionary keys) in front of all others: they are
+            // walked and decoded as a first phase, so that the string kernels start while the rest is still being decoded
+            auto key = [](const Seg& a) { return ((uint64_t)(a.out_kind == OUT_LEN31) << 32) | a.run_cap; };
+            std::stable_sort(int_segs_.begin(), int_segs_.end(), [&](const Seg& a, const Seg& b) { return key(a) > key(b); });
+            for (auto& sg : int_segs_) n_str_int_segs_ += sg.out_kind == OUT_LEN31;
+        }
     }
 
     // chunks that take longest first (compressed before stored, long before short): the persistent decompression
@@ -173,7 +179,7 @@ void Job::plan() {
     splace(o_dstart_, (size_t)(n_cnt_ + 1) * 4);
     splace(o_mis_, (size_t)(n_colstripes_ + 1) * 4);
     splace(o_jobstate_, sizeof(JobState));
-    splace(o_nblocks_, 32);
+    splace(o_nblocks_, 48);
     state_bytes_ = align_up(state_bytes_, 256);
 
     // ---- meta blob: err | nulls | ptr table | batch bases (batch_base_off were assigned relative to o_bbase_)
