@@ -70,10 +70,13 @@ struct OrcbReader {
     // with_row_selection: per entry of `stripes`, whether a selection applies and the row ranges it yields
     bool has_selection = false;
     std::vector<std::pair<bool, std::vector<std::pair<uint32_t, uint32_t>>>> views;
-    // with_predicate: evaluated on the first next(), like the reference does while iterating
+    // with_predicate: a stripe's verdict is worked out when the reader gets to the stripe, like the reference does while
+    // iterating (`views` grows stripe by stripe; `cursor` holds what is left of the caller's selection)
+    bool lazy = false;
+    SelectionCursor cursor;
     std::unique_ptr<Job> ahead;        // the next group of stripes, already launched
     std::exception_ptr ahead_error;    // what starting it ran into; reported when its turn comes
-    bool has_predicate = false, planned = true;
+    bool has_predicate = false;
     Predicate predicate;
     std::vector<RowSelector> selectors;
     // stripes (indices into `stripes`) of the group started last, of r->job and of r->ahead; `single`: one stripe per
@@ -392,7 +395,11 @@ int orcb_reader_build(OrcbFile* f, const OrcbReaderBuild* b, OrcbReader** out) {
             for (uint32_t s : r->stripes) rows.push_back(f->meta.stripes[s].rows);
             r->views = selection_views(r->selectors, rows, r->opt.batch_size);
         }
-        r->planned = !r->has_predicate;
+        if (r->has_predicate) {
+            r->lazy = true;
+            r->cursor = SelectionCursor(r->selectors, r->has_selection);
+            r->has_selection = true;  // `views` (filled as the reader advances) says what every stripe yields
+        }
         *out = r.release();
     });
 }
@@ -457,26 +464,23 @@ void orcb_reader_free(OrcbReader* r) { delete r; }
 
 uint64_t orcb_reader_total_row_count(const OrcbReader* r) { return r->file->meta.num_rows; }
 
-// with_predicate: the per-stripe verdicts, combined with the caller's selection (ArrowReader::try_advance_stripe)
-static void ensure_planned(OrcbReader* r) {
-    if (r->planned) return;
-    const auto cols = project_columns(r->file->meta, r->opt);
-    std::vector<uint64_t> rows;
-    std::vector<std::vector<RowSelector>> pred;
-    for (uint32_t s : r->stripes) {
-        rows.push_back(r->file->meta.stripes[s].rows);
-        pred.push_back(predicate_selection(r->file->meta, s, cols, r->predicate, nullptr, nullptr));
+// with_predicate: the verdict of stripe `idx` (and of every stripe before it), combined with the caller's selection
+// (ArrowReader::try_advance_stripe)
+static void ensure_views(OrcbReader* r, size_t idx) {
+    if (!r->lazy) return;
+    while (r->views.size() <= idx && r->views.size() < r->stripes.size()) {
+        const uint32_t s = r->stripes[r->views.size()];
+        const auto cols = project_columns(r->file->meta, r->opt);
+        const std::vector<RowSelector> pred = predicate_selection(r->file->meta, s, cols, r->predicate, nullptr, nullptr);
+        r->views.push_back(r->cursor.next_stripe(r->file->meta.stripes[s].rows, r->opt.batch_size, &pred));
     }
-    r->views = selection_views(r->selectors, rows, r->opt.batch_size, &pred, r->has_selection);
-    r->has_selection = true;  // from here on `views` says what every stripe yields
-    r->planned = true;
 }
 
 int orcb_reader_plan(OrcbReader* r, int32_t* applies, size_t cap_stripes, size_t* n_stripes, uint64_t* triples,
                      size_t cap_triples, size_t* n_triples) {
     return guarded([&] {
         if (!r || !n_triples || !n_stripes) fail(ORCB_INVALID_ARGUMENT, "NULL argument");
-        ensure_planned(r);
+        if (!r->stripes.empty()) ensure_views(r, r->stripes.size() - 1);
         *n_stripes = r->stripes.size();
         size_t k = 0;
         for (size_t s = 0; s < r->stripes.size(); s++) {
@@ -509,6 +513,7 @@ static std::unique_ptr<Job> reader_start_group(OrcbReader* r) {
             const StripeInfo& si = r->file->meta.stripes[r->stripes[r->next_stripe]];
             if (!tasks.empty() && bytes + si.data_length > (1ull << 30)) break;  // bound one launch plan to ~1 GiB in
             StripeTask task{&r->file->meta, r->stripes[r->next_stripe]};
+            ensure_views(r, r->next_stripe);
             if (r->has_selection && r->views[r->next_stripe].first) {
                 const auto& views = r->views[r->next_stripe].second;
                 if (views.empty()) {  // nothing selected in this stripe: not even staged
@@ -575,7 +580,6 @@ static std::unique_ptr<Job> reader_start_group(OrcbReader* r) {
 // wrong while starting a group ahead of time is reported when that group's turn comes, after every batch before it,
 // as the reference reports a bad stripe only when it gets there.
 static bool reader_advance(OrcbReader* r) {
-    ensure_planned(r);
     static const bool prefetch = !(getenv("ORCB_NO_PREFETCH") && getenv("ORCB_NO_PREFETCH")[0] == '1');
     // A group of several stripes that fails (while it is planned, or on the device) is started again one stripe at a
     // time: every batch of the stripes before the bad one is yielded first, as the reference does

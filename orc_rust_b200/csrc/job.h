@@ -95,6 +95,21 @@ std::vector<std::pair<bool, std::vector<std::pair<uint32_t, uint32_t>>>> selecti
     std::vector<RowSelector> selectors, const std::vector<uint64_t>& stripe_rows, uint64_t batch_size,
     const std::vector<std::vector<RowSelector>>* predicate = nullptr, bool has_selection = true);
 
+// The same, one stripe at a time: with_predicate evaluates a stripe's row-group statistics only when the reader gets
+// to that stripe (ArrowReader::try_advance_stripe, src/arrow_reader.rs:256-309), so a reader that is dropped early - or a
+// ChunkReader behind slow storage - never touches the index areas of the stripes it does not reach.
+class SelectionCursor {
+public:
+    SelectionCursor() = default;
+    SelectionCursor(std::vector<RowSelector> selectors, bool has_selection);
+    std::pair<bool, std::vector<std::pair<uint32_t, uint32_t>>> next_stripe(uint64_t rows, uint64_t batch_size,
+                                                                            const std::vector<RowSelector>* predicate);
+
+private:
+    std::vector<RowSelector> sel_;
+    bool has_selection_ = false;
+};
+
 // where one column of one stripe lands
 struct ColStripePlan {
     uint32_t row_base = 0;   // stripe row that row 0 of this column's buffers holds (> 0: windowed partial decode)

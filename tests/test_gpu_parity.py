@@ -1271,6 +1271,18 @@ def test_chunk_reader_feed(ob, tmp_path):
     data_reads = [c for c in cr2.calls[1:] if c in whole]
     # (a footer that lies inside the tail already read costs no call of its own)
     assert not data_reads and len(cr2.calls) <= 1 + 2 * n_stripes and sum(c[1] for c in cr2.calls) < 100_000, cr2.calls
+    # the predicate is evaluated stripe by stripe as the reader advances (src/arrow_reader.rs:256-309): after the first
+    # batch of a reader that takes one stripe per launch nothing of the last stripe has been read, not even its index
+    cr3 = ob.FileChunkReader(p)
+    keep_all = ob.Predicate.gte("l_orderkey", ob.PredicateValue("Int64", 0))
+    it = iter(ob.ArrowReaderBuilder.try_new(cr3).with_predicate(keep_all).with_max_stripes_per_launch(1).build())
+    first = next(it)
+    assert first.num_rows > 0
+    last = infos[-1]
+    touched_last = [c for c in cr3.calls[1:] if c[0] >= last["offset"] and c[0] < last["offset"] + last["index_length"] + last["data_length"] + last["footer_length"]]
+    assert not touched_last, cr3.calls
+    rest = [first] + list(it)
+    assert_batches_equal_logically(rest, exp, "chunk reader, predicate that keeps everything")  # (selected ranges are views)
     # a failing callback is an IoError, not a crash
     class Broken(ob.FileChunkReader):
         def get_bytes(self, off, n):
