@@ -703,7 +703,7 @@ def main():
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         "run": {"stripes": n_stripes, "launch_groups_per_gpu": len(groups), "stripe_sharding": shard_note,
                 "input_bytes": in_bytes, "arrow_bytes": out_bytes, "device_bytes": dev_bytes, "dataset_gen_s": round(gen_s, 1),
-                "waves": args.waves, "group_streams": args.group_streams, "index_retries": ob.index_retries()},
+                "waves": args.waves, "group_streams": args.group_streams, "index_retries": ob.index_retries(), "layout_retries": ob.layout_retries()},
     }
     if readers:
         line.update(readers)

@@ -322,6 +322,10 @@ int orcb_host_decompress_section(int compression_kind, const uint8_t* in, size_t
 /* Jobs of this process that were decoded a second time without the row index because a (stream, row group) segment did
  * not end where the index says the next one starts (damaged stream or index).  0 on well-formed files. */
 uint64_t orcb_index_retries(void);
+/* Jobs of this process that were planned and decoded a second time because a Zlib / LZ4 / LZO / unsized Zstandard chunk
+ * in the middle of a stream did not fill its block (the writers of the reference's fixtures do fill them in 32 files out
+ * of 33; the sizes found are remembered per open file, so a file pays at most once per group of stripes). */
+uint64_t orcb_layout_retries(void);
 /* Error detail of the last failing call on this thread. */
 const char* orcb_last_error(void);
 /* Build identification: "sm_100a" etc. */

@@ -111,7 +111,7 @@ EXPORTED_SYMBOLS = [
     "orcb_reader_next_device", "orcb_reader_next_async", "orcb_reader_drain", "orcb_job_new", "orcb_job_free", "orcb_job_plan", "orcb_job_stage",
     "orcb_job_launch", "orcb_job_finish", "orcb_job_stats", "orcb_job_restage", "orcb_job_kernel_stats", "orcb_job_num_batches", "orcb_job_export_batch",
     "orcb_job_export_batch_device", "orcb_decode_int_rle", "orcb_decode_byte_rle", "orcb_decode_bool_rle",
-    "orcb_decode_varint128", "orcb_decompress_stream", "orcb_host_decompress_section", "orcb_last_error", "orcb_index_retries", "orcb_build_info",
+    "orcb_decode_varint128", "orcb_decompress_stream", "orcb_host_decompress_section", "orcb_last_error", "orcb_index_retries", "orcb_layout_retries", "orcb_build_info",
     "orcb_device_available",
 ]
 
@@ -125,6 +125,7 @@ def lib() -> ctypes.CDLL:
         L.orcb_last_error.restype = ctypes.c_char_p
         L.orcb_build_info.restype = ctypes.c_char_p
         L.orcb_index_retries.restype = ctypes.c_uint64
+        L.orcb_layout_retries.restype = ctypes.c_uint64
         L.orcb_file_num_rows.restype = ctypes.c_uint64
         L.orcb_file_compression_block_size.restype = ctypes.c_uint64
         L.orcb_file_row_index_stride.restype = ctypes.c_int64
@@ -194,6 +195,11 @@ def _check(rc: int):
 def index_retries() -> int:
     """Jobs decoded a second time without the row index (positions that did not agree with the streams)."""
     return int(lib().orcb_index_retries())
+
+
+def layout_retries() -> int:
+    """Jobs decoded a second time because a compressed chunk in the middle of a stream did not fill its block."""
+    return int(lib().orcb_layout_retries())
 
 
 def device_available() -> bool:

@@ -89,7 +89,7 @@ struct OrcbReader {
     }
 };
 
-static std::atomic<uint64_t> g_index_retries{0};
+static std::atomic<uint64_t> g_index_retries{0}, g_layout_retries{0};
 
 // finish() with the re-plan a LayoutRetry asks for (at most a few rounds: every round fixes the sizes of all chunks the
 // device could decode)
@@ -109,6 +109,7 @@ static void finish_job(std::unique_ptr<Job>& job) {
             job = std::move(again);
         } catch (const LayoutRetry&) {
             if (round >= 3) fail(ORCB_UNEXPECTED, "compressed chunk sizes keep changing between decode passes");
+            g_layout_retries++;
             std::unique_ptr<Job> again = job->rebuild();
             again->plan();
             again->stage();
@@ -148,6 +149,7 @@ extern "C" {
 
 const char* orcb_last_error(void) { return g_last_error.c_str(); }
 uint64_t orcb_index_retries(void) { return g_index_retries.load(); }
+uint64_t orcb_layout_retries(void) { return g_layout_retries.load(); }
 const char* orcb_build_info(void) { return "orc_b200 " __DATE__ " sm_100a cuda " ORCB_STR(CUDART_VERSION); }
 
 int orcb_device_available(void) {
