@@ -477,7 +477,7 @@ def main():
     ap.add_argument("--rows", type=int, default=SF10_ROWS, help="rows of one tile (default: SF10)")
     ap.add_argument("--files", type=int, default=32, help="ORC files of one tile")
     ap.add_argument("--tiles", type=int, default=7, help="times the tile is repeated (7 x SF10 = 672 stripes)")
-    ap.add_argument("--compression", default="uncompressed", choices=["uncompressed", "snappy", "lz4", "lz4-lib", "snappy-recompressed", "zstd", "lzo"])
+    ap.add_argument("--compression", default="uncompressed", choices=["uncompressed", "snappy", "zlib", "lz4", "lz4-lib", "snappy-recompressed", "zstd", "lzo"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-row-index", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the configs array (1, 2, 3, 4)")

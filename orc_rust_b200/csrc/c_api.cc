@@ -1034,8 +1034,8 @@ int orcb_decompress_stream(int device, int compression_kind, const uint8_t* in, 
         StreamRun sr(device, in, in_len);
         const size_t cap = chunks.size() * block_size + 256;
         if (chunks.size() * block_size > out_cap) fail(ORCB_INVALID_ARGUMENT, "out_cap must be >= chunks * block_size");
-        DevBuf dout(cap), ddesc(chunks.size() * sizeof(ChunkDesc) + 16), dlens(chunks.size() * 4 + 16), dctr(16);
-        CU(cudaMemset(dctr.p, 0, 16));
+        DevBuf dout(cap), ddesc(chunks.size() * sizeof(ChunkDesc) + 16), dlens(chunks.size() * 4 + 16), dctr(32);
+        CU(cudaMemset(dctr.p, 0, 32));
         std::vector<ChunkDesc> descs(chunks.size());
         for (size_t i = 0; i < chunks.size(); i++) {
             ChunkDesc& d = descs[i];
@@ -1058,8 +1058,8 @@ int orcb_decompress_stream(int device, int compression_kind, const uint8_t* in, 
         }
         const bool bits = compression_kind == C_ZLIB || compression_kind == C_ZSTD || compression_kind == C_LZO;
         const uint32_t nc = (uint32_t)chunks.size();
-        int rc = launch_decompress((ChunkDesc*)ddesc.p, nc, bits ? nc : 0u, compression_kind == C_SNAPPY ? nc : 0u, (uint32_t*)sr.err.p, (uint32_t*)dlens.p,
-                                   (uint32_t*)dctr.p, nullptr, 0);
+        int rc = launch_decompress((ChunkDesc*)ddesc.p, nc, bits ? nc : 0u, bits ? 1u << compression_kind : 0u, compression_kind == C_SNAPPY ? nc : 0u,
+                                   (uint32_t*)sr.err.p, (uint32_t*)dlens.p, (uint32_t*)dctr.p, nullptr, 0);
         if (rc) fail(ORCB_CUDA, cudaGetErrorString((cudaError_t)rc));
         if (timing) {
             float ms = 0;

@@ -365,7 +365,7 @@ void Job::launch() {
         launches += nk;
     };
     if (N(chunks_))
-        run("k_decompress", ab_decomp_, N(chunks_), (n_bits_chunks_ ? 1 : 0) + (n_snappy_chunks_ ? 1 : 0) + (N(chunks_) > n_bits_chunks_ + n_snappy_chunks_ ? 1 : 0), [&] { return launch_decompress((ChunkDesc*)(d_desc_ + o_chunk_), N(chunks_), n_bits_chunks_, n_snappy_chunks_, err, (uint32_t*)(d_meta_ + o_clens_), (uint32_t*)(d_state_ + o_nblocks_) + 3, (uint32_t*)(d_meta_ + o_retry_), st); });
+        run("k_decompress", ab_decomp_, N(chunks_), (int)__builtin_popcount(bits_codecs_) + (n_snappy_chunks_ ? 1 : 0) + (N(chunks_) > n_bits_chunks_ + n_snappy_chunks_ ? 1 : 0), [&] { return launch_decompress((ChunkDesc*)(d_desc_ + o_chunk_), N(chunks_), n_bits_chunks_, bits_codecs_, n_snappy_chunks_, err, (uint32_t*)(d_meta_ + o_clens_), (uint32_t*)(d_state_ + o_nblocks_) + 3, (uint32_t*)(d_meta_ + o_retry_), st); });
     if (N(present_byte_segs_)) {
         run("k_byte_rle(present)", ab_present_, N(present_byte_segs_), 1, [&] { return launch_byte_rle((Seg*)(d_desc_ + o_pbyte_), N(present_byte_segs_), cnt, dstart, err, segchk, st); });
         run("k_bits(present)", ab_present_, N(present_bit_segs_), 1, [&] { return launch_bits((BitSeg*)(d_desc_ + o_pbit_), N(present_bit_segs_), cnt, dstart, st); });

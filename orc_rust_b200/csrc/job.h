@@ -236,6 +236,7 @@ class Job {
     uint32_t n_cnt_ = 0, n_colstripes_ = 0;
     uint8_t* d_state_ = nullptr;
     uint32_t n_str_int_segs_ = 0;  // leading int_segs_ that feed the string kernels (string lengths, dictionary keys)
+    uint32_t bits_codecs_ = 0;  // 1 << codec over the serial-chain chunks
     uint32_t n_bits_chunks_ = 0, n_snappy_chunks_ = 0;  // chunks_ is ordered: serial-chain codecs, Snappy, then LZ4 / stored
     uint64_t state_bytes_ = 0, o_cnt_ = 0, o_dstart_ = 0, o_mis_ = 0, o_jobstate_ = 0, o_nblocks_ = 0;
     // meta blob (device, zeroed per launch, copied to host at finish): err[], nulls[], ptr_table[], batch_base[]

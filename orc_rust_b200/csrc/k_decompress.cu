@@ -742,33 +742,37 @@ __device__ __forceinline__ bool inf_build(const uint8_t* lens, int nsym, uint16_
     return true;
 }
 
+// LSB-first bit reader: a read is two aligned word loads and a funnel shift (the words may extend a few bytes beyond the
+// chunk: inside the arena, never part of a value)
 struct InfBits {
-    const uint8_t* s;
-    uint32_t n, pos;   // pos: next input byte
-    uint64_t buf;
-    int cnt;
-    __device__ __forceinline__ void refill() {
-        while (cnt <= 56) {
-            buf |= (uint64_t)(pos < n ? s[pos] : 0u) << cnt;
-            pos++;
-            cnt += 8;
-        }
+    const uint32_t* W;  // chunk start rounded down to a word
+    uint32_t boff;      // bit offset of the chunk in W
+    uint32_t n;         // chunk bytes
+    uint32_t pos;       // next bit
+    __device__ __forceinline__ void init(const uint8_t* s, uint32_t len) {
+        W = (const uint32_t*)((uintptr_t)s & ~(uintptr_t)3);
+        boff = (uint32_t)((uintptr_t)s & 3) * 8;
+        n = len;
+        pos = 0;
     }
-    __device__ __forceinline__ uint32_t take(int k) {
-        const uint32_t v = (uint32_t)buf & ((1u << k) - 1u);
-        buf >>= k;
-        cnt -= k;
+    __device__ __forceinline__ uint32_t peek32() const {
+        const uint32_t a = pos + boff;
+        return __funnelshift_r(W[a >> 5], W[(a >> 5) + 1], a & 31);
+    }
+    __device__ __forceinline__ uint32_t take(int k) {  // k <= 16
+        const uint32_t v = peek32() & ((1u << k) - 1u);
+        pos += k;
         return v;
     }
-    __device__ __forceinline__ bool overrun() const { return (uint64_t)pos * 8 - (uint64_t)cnt > (uint64_t)n * 8; }
+    __device__ __forceinline__ bool overrun() const { return pos > n * 8u; }
 };
 
 // one symbol; -1 = invalid code
 __device__ __forceinline__ int inf_symbol(InfBits& b, const uint16_t* lut, int lut_bits, const uint16_t* sorted, const uint16_t* first,
                                           const uint16_t* offs, const uint16_t* count) {
-    const uint32_t e = lut[(uint32_t)b.buf & ((1u << lut_bits) - 1u)];
+    const uint32_t e = lut[b.peek32() & ((1u << lut_bits) - 1u)];
     if (e) {
-        b.take(e & 15);
+        b.pos += e & 15;
         return (int)(e >> 4);
     }
     // long code: canonical decode, one bit at a time (count[] holds the number of codes per length after the build)
@@ -788,16 +792,18 @@ __device__ uint32_t inflate_chunk(const uint8_t* __restrict__ s, uint32_t n, uin
     static const uint8_t DEXT[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
     static const uint8_t CLORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
     const uint32_t BAD = ORCB_IO_ERROR;
-    InfBits b{s, n, 0, 0, 0};
+    InfBits b;
+    b.init(s, n);
+    if (n > (1u << 28)) return BAD;
     uint32_t o = 0;
     int last = 0;
     while (!last) {
         // ---- block header (lane 0 reads, everyone follows)
         uint32_t type = 0;
         if (lane == 0) {
-            b.refill();
             last = (int)b.take(1);
             type = b.take(2);
+            if (b.overrun()) type = 3;
         }
         last = __shfl_sync(FULL, last, 0);
         type = __shfl_sync(FULL, type, 0);
@@ -806,18 +812,13 @@ __device__ uint32_t inflate_chunk(const uint8_t* __restrict__ s, uint32_t n, uin
             // stored block: to the next byte boundary, LEN, ~LEN, bytes
             uint32_t len = 0, from = 0, bad = 0;
             if (lane == 0) {
-                b.take(b.cnt & 7);
-                b.refill();
+                b.pos = (b.pos + 7u) & ~7u;
                 len = b.take(16);
                 const uint32_t nlen = b.take(16);
                 if ((len ^ nlen) != 0xffffu) bad = 1;
-                from = b.pos - (uint32_t)(b.cnt >> 3);  // first byte not yet consumed
+                from = b.pos >> 3;  // first byte not yet consumed
                 if (from > n || len > n - from || len > cap - o) bad = 1;
-                if (!bad) {
-                    b.pos = from + len;
-                    b.buf = 0;
-                    b.cnt = 0;
-                }
+                if (!bad) b.pos = (from + len) * 8u;
             }
             if (__shfl_sync(FULL, bad, 0)) return BAD;
             len = __shfl_sync(FULL, len, 0);
@@ -836,16 +837,12 @@ __device__ uint32_t inflate_chunk(const uint8_t* __restrict__ s, uint32_t n, uin
             // dynamic code: code-length code, then the literal/length and distance code lengths
             uint32_t bad = 0;
             if (lane == 0) {
-                b.refill();
                 nlen = (int)b.take(5) + 257;
                 ndist = (int)b.take(5) + 1;
                 const int ncode = (int)b.take(4) + 4;
                 if (nlen > 286 || ndist > 30) bad = 1;
                 for (int i = 0; i < 19; i++) w.stage[i] = 0;
-                for (int i = 0; i < ncode && !bad; i++) {
-                    b.refill();
-                    w.stage[CLORDER[i]] = (uint8_t)b.take(3);
-                }
+                for (int i = 0; i < ncode && !bad; i++) w.stage[CLORDER[i]] = (uint8_t)b.take(3);
             }
             if (__shfl_sync(FULL, bad, 0)) return BAD;
             nlen = __shfl_sync(FULL, nlen, 0);
@@ -858,7 +855,7 @@ __device__ uint32_t inflate_chunk(const uint8_t* __restrict__ s, uint32_t n, uin
                 int i = 0, prev = 0;
                 uint8_t* out = w.stage + 32;
                 while (i < nlen + ndist && !bad) {
-                    b.refill();
+                    if (b.overrun()) { bad = 1; break; }
                     const int sym = inf_symbol(b, w.dlut, 7, w.dsorted, w.dfirst, w.doffs, w.dcount);
                     if (sym < 0) { bad = 1; break; }
                     if (sym < 16) {
@@ -899,7 +896,6 @@ __device__ uint32_t inflate_chunk(const uint8_t* __restrict__ s, uint32_t n, uin
             uint32_t nt = 0, bad = 0;
             if (lane == 0) {
                 while (nt < 32) {
-                    b.refill();
                     const int sym = inf_symbol(b, w.llut, INF_LBITS, w.lsorted, w.lfirst, w.loffs, w.lcount);
                     if (sym < 0) { bad = 1; break; }
                     if (sym < 256) {
@@ -1300,26 +1296,33 @@ __global__ void __launch_bounds__(128, ORCB_LZ_CTAS) k_decompress(const ChunkDes
     }
 }
 
-union BitsWarp {
-    InfWarp inf;
-    ZstdWarp zstd;
-    uint32_t tok[32 * 4];
-};
-
+// one kernel per serial-chain codec: each has only its own tables in shared memory, so the small ones (inflate: 4.5 KiB
+// per warp, LZO: 512 bytes) keep more chains in flight per SM than the Zstandard tables would allow
+template <int CODEC> struct BitsSmem;
+template <> struct BitsSmem<1> { InfWarp w; };
+template <> struct BitsSmem<3> { uint32_t tok[32 * 4]; };
+template <> struct BitsSmem<5> { ZstdWarp w; };
 #ifndef ORCB_BITS_CTAS
 #define ORCB_BITS_CTAS 5
 #endif
-__global__ void __launch_bounds__(128, ORCB_BITS_CTAS) k_decompress_bits(const ChunkDesc* __restrict__ chunks, uint32_t nchunks, uint32_t* err,
-                                                            uint32_t* out_lens, uint32_t* counter, uint32_t* retry) {
-    __shared__ BitsWarp warp_sm[4];
+#ifndef ORCB_INF_CTAS
+#define ORCB_INF_CTAS 8
+#endif
+
+template <int CODEC>
+__global__ void __launch_bounds__(128, CODEC == 5 ? ORCB_BITS_CTAS : ORCB_INF_CTAS)
+k_decompress_bits(const ChunkDesc* __restrict__ chunks, uint32_t nchunks, uint32_t* err, uint32_t* out_lens, uint32_t* counter,
+                  uint32_t* retry, int copy_stored) {
+    __shared__ BitsSmem<CODEC> warp_sm[4];
     const int lane = threadIdx.x & 31;
-    BitsWarp& sm = warp_sm[threadIdx.x >> 5];
+    BitsSmem<CODEC>& sm = warp_sm[threadIdx.x >> 5];
     for (;;) {
         uint32_t ci = 0;
         if (lane == 0) ci = atomicAdd(counter, 1u);
         ci = __shfl_sync(FULL, ci, 0);
         if (ci >= nchunks) return;
         const ChunkDesc& c = chunks[ci];
+        if (c.codec != CODEC && !(c.codec == 0 && copy_stored)) continue;  // another launch takes it
         const uint8_t* s = (const uint8_t*)c.src;
         uint8_t* d = (uint8_t*)c.dst;
         const uint32_t n = c.src_len;
@@ -1328,14 +1331,12 @@ __global__ void __launch_bounds__(128, ORCB_BITS_CTAS) k_decompress_bits(const C
             if (n > c.dst_cap) fail = ORCB_UNEXPECTED;
             else warp_copy_fwd(d, s, n, lane);
             o = n;
-        } else if (c.codec == 1) {
-            fail = inflate_chunk(s, n, d, c.dst_cap, o, sm.inf, lane);
-        } else if (c.codec == 5) {
-            fail = zstd_chunk(s, n, d, c.dst_cap, o, sm.zstd, lane);
-        } else if (c.codec == 3) {
-            fail = lzo_chunk(s, n, d, c.dst_cap, o, sm.tok, lane);
+        } else if constexpr (CODEC == 1) {
+            fail = inflate_chunk(s, n, d, c.dst_cap, o, sm.w, lane);
+        } else if constexpr (CODEC == 5) {
+            fail = zstd_chunk(s, n, d, c.dst_cap, o, sm.w, lane);
         } else {
-            fail = ORCB_UNEXPECTED;
+            fail = lzo_chunk(s, n, d, c.dst_cap, o, sm.tok, lane);
         }
         // the size of a stream's last chunk is only known here: what the layout reserved beyond it reads as zeros
         if (c.codec != 0 && c.expect_len < 0 && !fail)
@@ -1360,18 +1361,33 @@ static uint32_t resident_ctas(K kernel, int& cache) {
     return (uint32_t)cache;
 }
 
-// The first n_bits chunks of the list go to k_decompress_bits, the next n_snappy to k_decompress<2>, the rest (LZ4,
-// stored) to k_decompress<4>.  counter: three zeroed words.
-int launch_decompress(const ChunkDesc* c, uint32_t n, uint32_t n_bits, uint32_t n_snappy, uint32_t* err, uint32_t* out_lens, uint32_t* counter,
-                      uint32_t* retry, cudaStream_t st) {
+template <int CODEC>
+static int launch_bits(const ChunkDesc* c, uint32_t n, uint32_t* err, uint32_t* out_lens, uint32_t* counter, uint32_t* retry, int copy_stored,
+                       cudaStream_t st) {
+    static int ctas = 0;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(resident_ctas(k_decompress_bits<CODEC>, ctas), ((uint64_t)n + 3) / 4);
+    k_decompress_bits<CODEC><<<grid, 128, 0, st>>>(c, n, err, out_lens, counter, retry, copy_stored);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+// The first n_bits chunks of the list go to the k_decompress_bits kernels (one launch per codec in `bits_codecs`, a
+// bit mask of 1 << codec; each takes its own chunks of the range), the next n_snappy to k_decompress<2>, the rest
+// (LZ4, stored) to k_decompress<4>.  counter: eight zeroed words.
+int launch_decompress(const ChunkDesc* c, uint32_t n, uint32_t n_bits, uint32_t bits_codecs, uint32_t n_snappy, uint32_t* err, uint32_t* out_lens,
+                      uint32_t* counter, uint32_t* retry, cudaStream_t st) {
     if (!n) return 0;
-    static int ctas_snappy = 0, ctas_lz4 = 0, ctas_bits = 0;
+    static int ctas_snappy = 0, ctas_lz4 = 0;
     if (n_bits > n) n_bits = n;
     if (n_snappy > n - n_bits) n_snappy = n - n_bits;
     if (n_bits) {
-        const uint32_t grid = (uint32_t)std::min<uint64_t>(resident_ctas(k_decompress_bits, ctas_bits), ((uint64_t)n_bits + 3) / 4);
-        k_decompress_bits<<<grid, 128, 0, st>>>(c, n_bits, err, out_lens, counter + 1, retry);
-        LAUNCH_CHECK();
+        int copy_stored = 1, rc = 0;  // stored chunks of the range (stream-level entry point only) go with the first launch
+        if (bits_codecs & (1u << 1)) { rc = launch_bits<1>(c, n_bits, err, out_lens, counter + 1, retry, copy_stored, st); copy_stored = 0; }
+        if (rc) return rc;
+        if (bits_codecs & (1u << 5)) { rc = launch_bits<5>(c, n_bits, err, out_lens, counter + 3, retry, copy_stored, st); copy_stored = 0; }
+        if (rc) return rc;
+        if ((bits_codecs & (1u << 3)) || copy_stored) rc = launch_bits<3>(c, n_bits, err, out_lens, counter + 4, retry, copy_stored, st);
+        if (rc) return rc;
     }
     if (n_snappy) {
         const uint32_t grid = (uint32_t)std::min<uint64_t>(resident_ctas(k_decompress<2>, ctas_snappy), ((uint64_t)n_snappy + 3) / 4);

@@ -40,12 +40,13 @@ int launch_utf8(const StrCol* cols, const uint2* tiles, uint32_t ntiles, cudaStr
 int launch_strings(StrCol* cols, uint32_t ncols, uint32_t ntiles, uint32_t* err, JobState* state, uint64_t heap_base,
                    uint64_t heap_cap, uint64_t* ptr_table, cudaStream_t st);
 int launch_repack(const RepackDesc* d, uint32_t ndesc, uint32_t nwork, uint32_t* nulls, cudaStream_t st);
-// The chunk list is ordered: first n_bits Zlib / Zstandard / LZO chunks (k_decompress_bits), then n_snappy Snappy chunks
-// (k_decompress<2>), then LZ4 and stored chunks (k_decompress<4>).  counter: three zeroed words (the persistent warps
-// of each kernel draw chunk indices from their own).  out_lens[c.id] receives every chunk's decompressed size; *retry is
-// raised when a chunk whose size the planner only assumed turned out different (either may be NULL)
-int launch_decompress(const ChunkDesc* c, uint32_t n, uint32_t n_bits, uint32_t n_snappy, uint32_t* err, uint32_t* out_lens, uint32_t* counter,
-                      uint32_t* retry, cudaStream_t st);
+// The chunk list is ordered: first n_bits Zlib / Zstandard / LZO chunks (k_decompress_bits<codec>, one launch per codec
+// of the bit mask `bits_codecs`), then n_snappy Snappy chunks (k_decompress<2>), then LZ4 and stored chunks
+// (k_decompress<4>).  counter: eight zeroed words (the persistent warps of each kernel draw chunk indices from their own).
+// out_lens[c.id] receives every chunk's decompressed size; *retry is raised when a chunk whose size the planner only
+// assumed turned out different (either may be NULL)
+int launch_decompress(const ChunkDesc* c, uint32_t n, uint32_t n_bits, uint32_t bits_codecs, uint32_t n_snappy, uint32_t* err, uint32_t* out_lens,
+                      uint32_t* counter, uint32_t* retry, cudaStream_t st);
 
 constexpr uint32_t COPY_TILE_BYTES = 16384;
 

@@ -122,8 +122,9 @@ void Job::plan() {
     auto chunk_class = [](const ChunkDesc& c) -> uint64_t { return c.codec == 1 || c.codec == 3 || c.codec == 5 ? 2 : c.codec == 2 ? 1 : 0; };
     auto chunk_key = [&](const ChunkDesc& c) { return (chunk_class(c) << 40) | ((uint64_t)(c.codec != 0) << 32) | c.src_len; };
     std::stable_sort(chunks_.begin(), chunks_.end(), [&](const ChunkDesc& a, const ChunkDesc& b) { return chunk_key(a) > chunk_key(b); });
-    n_bits_chunks_ = n_snappy_chunks_ = 0;
+    n_bits_chunks_ = n_snappy_chunks_ = bits_codecs_ = 0;
     for (auto& c : chunks_) {
+        if (chunk_class(c) == 2) bits_codecs_ |= 1u << c.codec;
         n_bits_chunks_ += chunk_class(c) == 2;
         n_snappy_chunks_ += chunk_class(c) == 1;
     }
