@@ -1306,7 +1306,7 @@ template <> struct BitsSmem<5> { ZstdWarp w; };
 #define ORCB_BITS_CTAS 5
 #endif
 #ifndef ORCB_INF_CTAS
-#define ORCB_INF_CTAS 8
+#define ORCB_INF_CTAS 10
 #endif
 
 template <int CODEC>
