@@ -438,6 +438,7 @@ def other_configs(torch, ob, args, device, peak, sf10_files):
                                       sf10_files, device, peak, steps=10, parity=(sf10_files[0], 1) if check else None))
     for comp, label in (("snappy", "Snappy (pyarrow writer, 256 KiB chunks)"), ("snappy-recompressed", "Snappy (in-repo re-compressor, 256 KiB chunks)"),
                         ("lz4-lib", "LZ4 (liblz4 blocks framed by the in-repo re-compressor, 256 KiB chunks)"),
+                        ("zlib", "Zlib (pyarrow writer, 256 KiB chunks; the ORC default of Hive / Java writers)"),
                         ("zstd", "Zstandard level 3 (in-repo re-compressor, 256 KiB chunks)")):
         def mk(comp=comp, label=label):
             files, _ = _dataset(args.rows, args.files, comp)
