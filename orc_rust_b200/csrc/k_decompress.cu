@@ -1072,7 +1072,7 @@ __device__ uint32_t zstd_block(const uint8_t* __restrict__ b, uint32_t size, uin
         if (lh.streams == 1) {
             if (lane == 0) ok = huf_stream(sp, sn, w.T.huf, fs.huf_log, area, lh.regen);
         } else {
-            if (sn < 6) return 1;
+            if (sn < 10 || lh.regen < 6) return 1;  // libzstd: jump table + one byte per stream; at least 6 literals
             const uint32_t l1 = sp[0] | (sp[1] << 8), l2 = sp[2] | (sp[3] << 8), l3 = sp[4] | (sp[5] << 8);
             if (6u + l1 + l2 + l3 > sn) return 1;
             const uint32_t q = (lh.regen + 3) / 4;

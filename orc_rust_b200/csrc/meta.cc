@@ -282,7 +282,7 @@ static void host_zstd_frames(const uint8_t* s, size_t n, std::vector<uint8_t>& o
                     if (lh.streams == 1) {
                         if (!huf_stream(sp, sn, T->huf, fs.huf_log, lits.data(), lh.regen)) bad();
                     } else {
-                        if (sn < 6) bad();
+                        if (sn < 10 || lh.regen < 6) bad();  // libzstd: jump table + one byte per stream; at least 6 literals
                         const uint32_t l1 = sp[0] | (sp[1] << 8), l2 = sp[2] | (sp[3] << 8), l3 = sp[4] | (sp[5] << 8);
                         if ((uint64_t)6 + l1 + l2 + l3 > sn) bad();
                         const uint32_t l4 = sn - 6 - l1 - l2 - l3, q = (lh.regen + 3) / 4;
