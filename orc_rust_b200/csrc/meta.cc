@@ -632,6 +632,7 @@ std::vector<std::vector<uint64_t>> FileMeta::read_row_index(const StripeInfo& si
     while (c.next(f)) {
         if (f.number != 1) continue;
         std::vector<uint64_t> pos;
+        pos.reserve(8);  // (a row-index entry has 1..7 positions: one allocation instead of four)
         PbCursor ec(f.data, f.len);
         PbField g;
         while (ec.next(g)) {

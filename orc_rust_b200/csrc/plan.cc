@@ -41,11 +41,12 @@ bool is_utc_zone(const std::string& z) {
     return false;
 }
 
-// Scheduling hint only: do the first few RLE v2 runs at `pos` all hold more than 64 values?  (Header walk,
+// Scheduling hint only: do the first few (8; ORCB_PEEK_RUNS) RLE v2 runs at `pos` all hold more than 64 values?  (Header walk,
 // no values decoded.)  Such segments go to the warp-per-segment kernel.
 bool rle2_opens_with_long_runs(const uint8_t* s, uint32_t len, uint32_t pos) {
     static const int W[32] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 26, 28, 30, 32, 40, 48, 56, 64};
-    for (int r = 0; r < 8; r++) {
+    static const int depth = getenv("ORCB_PEEK_RUNS") ? std::max(1, atoi(getenv("ORCB_PEEK_RUNS"))) : 8;
+    for (int r = 0; r < depth; r++) {
         if (pos + 4 > len) return r > 0;
         const uint32_t h = s[pos], kind = h >> 6;
         if (kind == 0) return false;
@@ -622,6 +623,13 @@ void Job::plan_stripe(uint32_t task_idx) {
             const std::vector<Entry>& en = spec_of(&sr);
             const uint32_t ng = indexed ? n_groups : 1;
             uint32_t chk_prev = 0;
+            // the stream's bytes as the host sees them (for the scheduling hint below)
+            const uint8_t* sp = nullptr;
+            if (v2 && sr.present)
+                sp = fm.base_for(data_start) + (sf.find(cid, &sr == &s_data ? S_DATA : (&sr == &s_length ? S_LENGTH : S_SECONDARY))->offset);
+            // (every look is a cache miss in a file of hundreds of MB: have them all in flight before the loop needs them)
+            if (sp && !compressed)
+                for (uint32_t g = 0; g < ng; g++) __builtin_prefetch(sp + std::min(en[g].byte, sr.len));
             for (uint32_t g = 0; g < ng; g++) {
                 Seg sg{};
                 sg.in = sr.ptr;
@@ -648,8 +656,7 @@ void Job::plan_stripe(uint32_t task_idx) {
                 // compressed): segments that open with a long run go to the warp-per-segment kernel,
                 // everything else to the lane-per-segment kernel.  Purely a scheduling hint.
                 bool long_runs = false;
-                if (v2 && sr.present) {
-                    const uint8_t* sp = fm.base_for(data_start) + (sf.find(cid, &sr == &s_data ? S_DATA : (&sr == &s_length ? S_LENGTH : S_SECONDARY))->offset);
+                if (sp) {
                     if (!compressed) {
                         long_runs = rle2_opens_with_long_runs(sp, sr.len, sg.start_byte);
                     } else if (!sr.chunks.empty()) {
