@@ -24,6 +24,8 @@ static void host_snappy_block(const uint8_t* s, size_t n, std::vector<uint8_t>& 
         if (b < 0x80) break;
     }
     size_t base = out.size();
+    // no element makes more than 64 bytes out of 3: a larger preamble cannot be met, and must not size an allocation
+    if (want > 32 * (uint64_t)n + 64) fail(ORCB_BUILD_SNAPPY_DECODER, "snappy length mismatch");
     out.reserve(base + want);
     while (ip < n) {
         const uint8_t tag = s[ip++];
