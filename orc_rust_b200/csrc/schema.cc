@@ -189,64 +189,63 @@ void fill_schema(ArrowSchema* s, const std::string& fmt, const std::string& name
 }
 }  // namespace
 
+// Exception safety: a node's children are linked (zeroed, release == nullptr) before any of them is built, so that
+// releasing the root frees whatever exists when a damaged file makes column_info throw half-way.
+static void link_children(ArrowSchema* s, size_t n) {
+    auto* p = (SchemaPriv*)s->private_data;
+    p->child_store.assign(n, ArrowSchema{});
+    p->child_ptrs.resize(n);
+    for (size_t i = 0; i < n; i++) p->child_ptrs[i] = &p->child_store[i];
+    s->n_children = (int64_t)n;
+    s->children = p->child_ptrs.data();
+}
+
 static void export_column_schema(const FileMeta& fm, const OutColumn& c, const ReadOptions& opt, const std::string& name,
                                  int64_t flags, ArrowSchema* out) {
     fill_schema(out, c.format, name, flags);
     if (c.child_ids.empty()) return;
-    auto* p = (SchemaPriv*)out->private_data;
     const OrcType& t = fm.types[c.col_id];
     const int64_t NULLABLE = 2;
-    auto child = [&](size_t i, uint32_t id, const std::string& nm, int64_t fl) {
-        export_column_schema(fm, column_info(fm, id, nm, opt, -1), opt, nm, fl, &p->child_store[i]);
-    };
     if (c.kind == T_MAP) {
         // Map(entries: Struct(keys non-null, values nullable), non-null), not sorted (src/schema.rs:548-557)
-        p->child_store.resize(1);
-        p->child_ptrs = {&p->child_store[0]};
-        fill_schema(&p->child_store[0], "+s", "entries", 0);
-        auto* ep = (SchemaPriv*)p->child_store[0].private_data;
-        ep->child_store.resize(2);
-        ep->child_ptrs = {&ep->child_store[0], &ep->child_store[1]};
-        export_column_schema(fm, column_info(fm, c.child_ids[0], "keys", opt, -1), opt, "keys", 0, &ep->child_store[0]);
-        export_column_schema(fm, column_info(fm, c.child_ids[1], "values", opt, -1), opt, "values", NULLABLE, &ep->child_store[1]);
-        p->child_store[0].n_children = 2;
-        p->child_store[0].children = ep->child_ptrs.data();
+        link_children(out, 1);
+        ArrowSchema* entries = out->children[0];
+        fill_schema(entries, "+s", "entries", 0);
+        link_children(entries, 2);
+        export_column_schema(fm, column_info(fm, c.child_ids.at(0), "keys", opt, -1), opt, "keys", 0, entries->children[0]);
+        export_column_schema(fm, column_info(fm, c.child_ids.at(1), "values", opt, -1), opt, "values", NULLABLE, entries->children[1]);
     } else {
-        p->child_store.resize(c.child_ids.size());
-        p->child_ptrs.resize(c.child_ids.size());
+        link_children(out, c.child_ids.size());
         for (size_t i = 0; i < c.child_ids.size(); i++) {
-            p->child_ptrs[i] = &p->child_store[i];
-            const std::string nm = c.kind == T_STRUCT ? t.field_names[i] : c.kind == T_LIST ? std::string("item") : "_union_" + std::to_string(i);
-            child(i, c.child_ids[i], nm, NULLABLE);
+            const std::string nm = c.kind == T_STRUCT ? t.field_names.at(i) : c.kind == T_LIST ? std::string("item") : "_union_" + std::to_string(i);
+            export_column_schema(fm, column_info(fm, c.child_ids[i], nm, opt, -1), opt, nm, NULLABLE, out->children[i]);
         }
     }
-    out->n_children = (int64_t)p->child_ptrs.size();
-    out->children = p->child_ptrs.data();
 }
 
 void export_schema(const FileMeta& fm, const std::vector<OutColumn>& cols, const ReadOptions& opt, ArrowSchema* out) {
     fill_schema(out, "+s", "", 0);
-    auto* p = (SchemaPriv*)out->private_data;
-    if (!fm.user_metadata.empty()) {
-        std::string& m = p->metadata;
-        auto put32 = [&](int32_t v) { m.append((const char*)&v, 4); };
-        put32((int32_t)fm.user_metadata.size());
-        for (auto& kv : fm.user_metadata) {
-            put32((int32_t)kv.first.size());
-            m.append(kv.first);
-            put32((int32_t)kv.second.size());
-            m.append(kv.second);
+    try {
+        auto* p = (SchemaPriv*)out->private_data;
+        if (!fm.user_metadata.empty()) {
+            std::string& m = p->metadata;
+            auto put32 = [&](int32_t v) { m.append((const char*)&v, 4); };
+            put32((int32_t)fm.user_metadata.size());
+            for (auto& kv : fm.user_metadata) {
+                put32((int32_t)kv.first.size());
+                m.append(kv.first);
+                put32((int32_t)kv.second.size());
+                m.append(kv.second);
+            }
+            out->metadata = p->metadata.data();
         }
-        out->metadata = p->metadata.data();
+        link_children(out, cols.size());
+        for (size_t i = 0; i < cols.size(); i++)
+            export_column_schema(fm, cols[i], opt, cols[i].name, 2 /* ARROW_FLAG_NULLABLE: src/schema.rs:131 */, out->children[i]);
+    } catch (...) {
+        out->release(out);
+        throw;
     }
-    p->child_store.resize(cols.size());
-    p->child_ptrs.resize(cols.size());
-    for (size_t i = 0; i < cols.size(); i++) {
-        export_column_schema(fm, cols[i], opt, cols[i].name, 2 /* ARROW_FLAG_NULLABLE: src/schema.rs:131 */, &p->child_store[i]);
-        p->child_ptrs[i] = &p->child_store[i];
-    }
-    out->n_children = (int64_t)cols.size();
-    out->children = p->child_ptrs.data();
 }
 
 }  // namespace orcb
