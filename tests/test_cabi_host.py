@@ -31,6 +31,10 @@ def test_library_exports_every_declared_symbol(ob):
     assert not missing, f"library lacks {missing}"
     assert set(declared) == set(ob.EXPORTED_SYMBOLS)
     assert b"sm_100a" in L.orcb_build_info()
+    # the reference-side binding shown in INTEGRATION.md (the Rust `extern "C"` block) covers the whole header
+    integ = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    unbound = [s for s in declared if not re.search(r"\bfn " + s + r"\(", integ)]
+    assert not unbound, f"INTEGRATION.md does not bind {unbound}"
 
 
 def test_no_cpu_decode_fallback(ob):

@@ -58,6 +58,48 @@ static void mutate(std::vector<uint8_t>& b, uint64_t span, int it) {
 
 static long n_ok = 0, n_err = 0;
 
+struct CbCtx {
+    const uint8_t* p;
+    size_t n;
+};
+static int read_at(void* ctx, uint64_t off, uint64_t len, uint8_t* dst) {
+    const CbCtx* c = (const CbCtx*)ctx;
+    if (off > c->n || len > c->n - off) return 5;  // a reader that refuses ranges outside the file
+    memcpy(dst, c->p + off, len);
+    return 0;
+}
+
+// The same bytes behind a read callback (ChunkReader): tail reads at open, one read per stripe at plan time, and a
+// reader with a row selection whose batches are planned on the host.
+static void one_file_callbacks(const uint8_t* heap, size_t n) {
+    CbCtx ctx{heap, n};
+    OrcbFile* f = nullptr;
+    if (orcb_open_callbacks(n, read_at, &ctx, &f) != 0) return;
+    OrcbReadOptions opt;
+    memset(&opt, 0, sizeof opt);
+    opt.use_row_index = 1;
+    opt.batch_size = 1 + (uint32_t)below(5000);
+    OrcbRowSelector sel[6];
+    for (auto& s : sel) s.row_count = below(3000), s.skip = (int32_t)below(2), s.reserved = 0;
+    OrcbReader* r = nullptr;
+    if (orcb_reader_new_with_selection(f, &opt, sel, 6, &r) == 0) {
+        int32_t applies[16];
+        uint64_t triples[3 * 64];
+        size_t ns = 0, nt = 0;
+        orcb_reader_plan(r, applies, 16, &ns, triples, 64, &nt);
+        orcb_reader_free(r);
+    }
+    OrcbJob* j = nullptr;
+    OrcbFile* files[1] = {f};
+    if (orcb_job_new(files, 1, &opt, &j) == 0) {
+        orcb_job_plan(j);
+        orcb_job_free(j);
+    }
+    uint64_t io[2];
+    orcb_file_io_stats(f, io);
+    orcb_file_free(f);
+}
+
 static void one_file(const std::vector<uint8_t>& bytes) {
     // exactly-sized heap copy: ASan's redzones sit right behind the last byte
     uint8_t* heap = (uint8_t*)malloc(bytes.size() ? bytes.size() : 1);
@@ -122,6 +164,7 @@ static void one_file(const std::vector<uint8_t>& bytes) {
         ok = false;
     }
     orcb_file_free(f);
+    if (below(4) == 0) one_file_callbacks(heap, bytes.size());
     free(heap);
     (ok ? n_ok : n_err)++;
 }
