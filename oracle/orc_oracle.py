@@ -15,8 +15,9 @@ oracle/codecs.c; this module restates the planner half:
   decimal / timestamp        src/array_decoder/decimal.rs:36-166, timestamp.rs:51-314
   schema mapping             src/schema.rs:390-577
 
-Parity pinning: tests/test_oracle_kat.py (reference unit-test vectors) and tests/test_oracle_files.py
-(reference expected_arrow feather goldens + pyarrow.orc as an independent reader).
+Parity pinning: tests/test_oracle_kat.py (reference unit-test vectors), tests/test_oracle_files.py
+(reference expected_arrow feather goldens + pyarrow.orc as an independent reader) and
+tests/test_reference_tables.py (the expected tables of the reference's tests/basic/main.rs).
 Nested columns (struct / list / map / union) are restated as a recursive walk (OracleFile._decode_node).
 """
 from __future__ import annotations

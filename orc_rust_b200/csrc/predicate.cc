@@ -296,6 +296,8 @@ std::vector<RowSelector> predicate_selection(const FileMeta& fm, uint32_t stripe
                                              const Predicate& pred, std::vector<uint8_t>* filter, bool* evaluated) {
     const StripeInfo& si = fm.stripes[stripe];
     const uint64_t rows_per_group = fm.row_index_stride >= 0 ? (uint64_t)fm.row_index_stride : 10000;  // src/stripe.rs:300
+    // (the decoder takes stripes of up to 2^32 rows; without this a damaged row count sizes the verdict vector below)
+    if (si.rows > 0xfffffff0ull) fail(ORCB_NOT_IMPLEMENTED, "stripes with more than 2^32 rows");
     std::vector<uint8_t> result;
     bool ok = true;
     // callback files: the index area and the stripe footer, not the data in between (a pruned stripe is never read)

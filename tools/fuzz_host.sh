@@ -18,7 +18,7 @@ done
 for p in "${pids[@]}"; do wait $p; done
 g++ -O1 -g -std=c++17 ${SAN//,/ } -c tools/fuzz_host.cc -o $B/obj/fuzz_host.o
 nvcc -o $B/fuzz_host $B/obj/*.o -gencode arch=compute_100a,code=sm_100a -cudart static -Xlinker -lasan -Xlinker -lubsan
-[ -n "$(ls $B/seeds 2>/dev/null)" ] || python tools/fuzz_host_seeds.py $B/seeds
+[ -n "$(ls $B/seeds/gen_*.orc 2>/dev/null)" ] || python tools/fuzz_host_seeds.py $B/seeds
 FILES=$(find tests/golden -name '*.orc' -size -400k | sort)
 ASAN_OPTIONS=detect_leaks=${LEAKS:-0}:allocator_may_return_null=1:max_allocation_size_mb=4096 UBSAN_OPTIONS=print_stacktrace=1 \
-  $B/fuzz_host $ITERS $SEED $FILES $B/seeds/*.sec
+  $B/fuzz_host $ITERS $SEED $FILES $B/seeds/*.orc $B/seeds/*.sec

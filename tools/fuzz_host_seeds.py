@@ -39,6 +39,18 @@ def main(out: str) -> None:
             open(os.path.join(out, f"1_{name}_l{lvl}.sec"), "wb").write(framed(co.compress(d) + co.flush()))
         co = zlib.compressobj(6, zlib.DEFLATED, -15, 9, zlib.Z_FIXED)
         open(os.path.join(out, f"1_{name}_fixed.sec"), "wb").write(framed(co.compress(d) + co.flush()))
+    # generated ORC files: the BASELINE configs at toy sizes (several stripes, row index every 1000 rows), NONE and every
+    # codec (pyarrow's writers, plus the re-compressor for real LZ4 / LZO chunks)
+    import gen_orc
+    import orc_recompress
+    import pyarrow.orc as orc
+    tables = {"cfg1": gen_orc.config1_table(6000), "lineitem": gen_orc.lineitem_table(1500), "nullheavy": gen_orc.nullheavy_table(5000)}
+    for name, t in tables.items():
+        for comp in ("uncompressed", "snappy", "zlib", "zstd"):
+            orc.write_table(t, os.path.join(out, f"gen_{name}_{comp}.orc"), compression=comp, stripe_size=64 << 10,
+                            row_index_stride=1000, compression_block_size=64 << 10, dictionary_key_size_threshold=0.8)
+        for kind in ("lz4", "lzo"):
+            orc_recompress.recompress(os.path.join(out, f"gen_{name}_uncompressed.orc"), os.path.join(out, f"gen_{name}_{kind}.orc"), kind, 16 << 10)
 
 
 if __name__ == "__main__":
