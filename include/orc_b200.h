@@ -319,6 +319,14 @@ int orcb_decompress_stream(int device, int compression_kind, const uint8_t* in, 
 int orcb_host_decompress_section(int compression_kind, const uint8_t* in, size_t in_len, size_t block_size, uint8_t* out,
                                  size_t out_cap, size_t* out_len);
 
+/* Host-only: the writer-zone table the device searches when a TIMESTAMP column was written in a zone other than UTC
+ * (src/array_decoder/timestamp.rs:128-147, 242-286; the reference asks chrono-tz): `at[i]` = UTC instant of transition i
+ * (ascending), `off[i]` = UTC offset in seconds east in force from at[i] on, *first_off = the offset before at[0].
+ * *n = number of transitions (also when it exceeds cap); *orc_epoch = 2015-01-01 00:00:00 on the zone's wall clock as
+ * seconds since the UNIX epoch (the base of the column's DATA stream).  ORCB_NOT_IMPLEMENTED when the host has no TZif
+ * file for `name`. */
+int orcb_zone_table(const char* name, int64_t* at, int32_t* off, size_t cap, size_t* n, int32_t* first_off, int64_t* orc_epoch);
+
 /* Jobs of this process that were decoded a second time without the row index because a (stream, row group) segment did
  * not end where the index says the next one starts (damaged stream or index).  0 on well-formed files. */
 uint64_t orcb_index_retries(void);

@@ -112,7 +112,7 @@ EXPORTED_SYMBOLS = [
     "orcb_job_launch", "orcb_job_finish", "orcb_job_stats", "orcb_job_restage", "orcb_job_kernel_stats", "orcb_job_num_batches", "orcb_job_export_batch",
     "orcb_job_export_batch_device", "orcb_decode_int_rle", "orcb_decode_byte_rle", "orcb_decode_bool_rle",
     "orcb_decode_varint128", "orcb_decompress_stream", "orcb_host_decompress_section", "orcb_last_error", "orcb_index_retries", "orcb_layout_retries", "orcb_build_info",
-    "orcb_device_available",
+    "orcb_device_available", "orcb_zone_table",
 ]
 
 
@@ -1063,6 +1063,19 @@ def host_decompress_section(kind: int, data: bytes, block_size: int) -> bytes:
             continue
         _check(rc)
         return out[: out_len.value].tobytes()
+
+
+def zone_table(name: str):
+    """Host-only: the writer-zone table the device searches (transition instants, offsets from each on, the offset before
+    the first, the ORC epoch on the zone's wall clock); works without a GPU."""
+    import numpy as np
+    n, first, epoch = ctypes.c_size_t(0), ctypes.c_int32(0), ctypes.c_int64(0)
+    L = lib()
+    _check(L.orcb_zone_table(name.encode(), None, None, ctypes.c_size_t(0), ctypes.byref(n), ctypes.byref(first), ctypes.byref(epoch)))
+    at, off = np.zeros(max(n.value, 1), dtype=np.int64), np.zeros(max(n.value, 1), dtype=np.int32)
+    _check(L.orcb_zone_table(name.encode(), at.ctypes.data_as(ctypes.c_void_p), off.ctypes.data_as(ctypes.c_void_p),
+                             ctypes.c_size_t(n.value), ctypes.byref(n), ctypes.byref(first), ctypes.byref(epoch)))
+    return at[: n.value], off[: n.value], int(first.value), int(epoch.value)
 
 
 def decompress_stream(kind: int, data: bytes, block_size: int, device: int = 0) -> bytes:

@@ -17,6 +17,7 @@
 #include "job.h"
 #include "job_internal.h"
 #include "predicate.h"
+#include "tz.h"
 #include "kernels.h"
 #include "meta.h"
 
@@ -420,6 +421,22 @@ int orcb_predicate_row_groups(OrcbFile* f, uint32_t stripe, const OrcbReadOption
         *evaluated = ok ? 1 : 0;
         *n_groups = filter.size();
         for (size_t i = 0; keep && i < filter.size() && i < cap; i++) keep[i] = filter[i];
+    });
+}
+
+int orcb_zone_table(const char* name, int64_t* at, int32_t* off, size_t cap, size_t* n, int32_t* first_off, int64_t* orc_epoch) {
+    return guarded([&] {
+        if (!name || !n || (cap && (!at || !off))) fail(ORCB_INVALID_ARGUMENT, "NULL argument");
+        ZoneTable z;
+        std::string why;
+        if (!load_zone_table(name, z, why)) fail(ORCB_NOT_IMPLEMENTED, "no table for zone " + std::string(name) + ": " + why);
+        *n = z.at.size();
+        for (size_t i = 0; i < z.at.size() && i < cap; i++) at[i] = z.at[i], off[i] = z.off[i];
+        if (first_off) *first_off = z.first_off;
+        if (orc_epoch) {
+            const int64_t local = ORC_EPOCH_UTC;  // 2015-01-01 00:00:00
+            if (!zone_local_to_utc(z, local, *orc_epoch)) fail(ORCB_UNEXPECTED, "2015-01-01 00:00 is not a unique instant in zone " + std::string(name));
+        }
     });
 }
 

@@ -385,3 +385,43 @@ def test_projection_mask(ob):
     m = ob.ProjectionMask.roots(f, [f.column_ids[0], f.column_ids[3]])
     assert b.with_projection(m).schema().names == [f.column_names[0], f.column_names[3]]
     assert ob.ArrowReaderBuilder.try_new(path).with_projection(ob.ProjectionMask.all()).schema().names == f.column_names
+
+
+def test_writer_zone_tables_match_zoneinfo(ob):
+    """The tables the device searches when a stripe was written in a zone other than UTC (src/array_decoder/timestamp.rs:
+    128-147, 242-286: the reference asks chrono-tz for the offset at each instant) against CPython's zoneinfo, an independent
+    reader of the same IANA data: the offset at thousands of instants from 1850 to 2400 - before the first transition, at
+    both sides of every transition, and past 2037, where the table continues from the TZif footer rule - and the ORC
+    epoch (2015-01-01 00:00 on the zone's wall clock)."""
+    import datetime
+    import zoneinfo
+    import numpy as np
+    zones = ["America/Los_Angeles", "America/New_York", "Europe/London", "Europe/Berlin", "Europe/Moscow", "Asia/Kolkata",
+             "Asia/Shanghai", "Asia/Tokyo", "Asia/Kathmandu", "Australia/Sydney", "Australia/Lord_Howe", "Pacific/Auckland",
+             "Pacific/Apia", "America/Sao_Paulo", "America/St_Johns", "Africa/Cairo", "Africa/Casablanca", "Asia/Tehran",
+             "Europe/Dublin", "CET", "EET", "MST", "US/Pacific", "Asia/Calcutta", "Japan", "GB"]
+    rng = np.random.default_rng(5)
+    utc = datetime.timezone.utc
+    epoch0 = datetime.datetime(1970, 1, 1, tzinfo=utc)
+    lo, hi = -3786825600, 13569465600  # 1850-01-01 .. 2400-01-01
+    checked = 0
+    for name in zones:
+        try:
+            zi = zoneinfo.ZoneInfo(name)
+        except zoneinfo.ZoneInfoNotFoundError:
+            continue
+        at, off, first, orc_epoch = ob.zone_table(name)
+        assert np.all(np.diff(at) >= 0)
+        probes = np.concatenate([rng.integers(lo, hi, 1500), at - 1, at, at + 1, at + 3600])
+        probes = probes[(probes >= lo) & (probes < hi)]
+        k = np.searchsorted(at, probes, side="right")
+        got = np.where(k == 0, first, np.append(off, first)[np.maximum(k - 1, 0)]) if len(at) else np.full(len(probes), first)
+        for t, g in zip(probes.tolist(), got.tolist()):
+            exp = (epoch0 + datetime.timedelta(seconds=t)).astimezone(zi).utcoffset().total_seconds()
+            assert g == exp, f"{name} at {t}: table says {g}, zoneinfo {exp}"
+            checked += 1
+        wall = datetime.datetime(2015, 1, 1, tzinfo=zi)
+        assert orc_epoch == int((wall - epoch0).total_seconds()), name
+    assert checked > 20000
+    with pytest.raises(ob.OrcError):
+        ob.zone_table("Not/AZone")
