@@ -702,6 +702,13 @@ class ArrowReaderBuilder:
         """`source`: path or bytes-like (the two `ChunkReader` impls, src/reader/mod.rs:48-76)."""
         return cls(_File(source))
 
+    @classmethod
+    async def try_new_async(cls, source) -> "ArrowReaderBuilder":
+        """`ArrowReaderBuilder::try_new_async` (src/async_arrow_reader.rs:292-296): the tail is read and parsed off the
+        event loop (an `AsyncChunkReader` maps to a `ChunkReader` whose `get_bytes` blocks on a worker thread)."""
+        import asyncio
+        return await asyncio.get_running_loop().run_in_executor(None, cls.try_new, source)
+
     def file_metadata(self) -> _File:
         return self._file
 

@@ -425,3 +425,16 @@ def test_writer_zone_tables_match_zoneinfo(ob):
     assert checked > 20000
     with pytest.raises(ob.OrcError):
         ob.zone_table("Not/AZone")
+
+
+def test_try_new_async(ob):
+    """`ArrowReaderBuilder::try_new_async` (src/async_arrow_reader.rs:292-296), the entry of the reference's async tests
+    (tests/basic/main.rs:44-63): metadata and schema without a device."""
+    import asyncio
+
+    async def go():
+        b = await ob.ArrowReaderBuilder.try_new_async(os.path.join(GOLDEN, "ref_basic", "test.orc"))
+        return b.file_metadata().number_of_rows, b.schema().names[:3], b.with_file_byte_range(100, 2000).build().total_row_count()
+
+    rows, names, total = asyncio.run(go())
+    assert (rows, names, total) == (5, ["a", "b", "str_direct"], 5)
