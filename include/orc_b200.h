@@ -128,6 +128,13 @@ uint32_t orcb_file_num_root_columns(const OrcbFile* f);
 const char* orcb_file_root_column_name(const OrcbFile* f, uint32_t i);
 /* ORC column index of root column i (what ProjectionMask::roots takes, src/projection.rs:37-50); 0 when out of range */
 uint32_t orcb_file_root_column_id(const OrcbFile* f, uint32_t i);
+/* FileMetadata::file_format_version (src/reader/metadata.rs:119-127, 175-177): "0.12", "" when the postscript has none */
+const char* orcb_file_format_version(const OrcbFile* f);
+/* FileMetadata::user_custom_metadata (src/reader/metadata.rs:112-117, 161-163): entry i of *orcb_file_num_user_metadata*,
+ * in file order (the same pairs travel as the metadata of the Arrow schema).  `key` is NUL-terminated; the value is
+ * `*value_len` bytes and need not be text.  Both stay valid for the life of the handle. */
+uint32_t orcb_file_num_user_metadata(const OrcbFile* f);
+int orcb_file_user_metadata(const OrcbFile* f, uint32_t i, const char** key, const uint8_t** value, size_t* value_len);
 /* StripeMetadata (src/stripe.rs:38-81): out[0..5) = offset, index_length, data_length, footer_length, rows */
 int orcb_file_stripe_info(const OrcbFile* f, uint32_t stripe, uint64_t out[5]);
 

@@ -112,7 +112,7 @@ EXPORTED_SYMBOLS = [
     "orcb_job_launch", "orcb_job_finish", "orcb_job_stats", "orcb_job_restage", "orcb_job_kernel_stats", "orcb_job_num_batches", "orcb_job_export_batch",
     "orcb_job_export_batch_device", "orcb_decode_int_rle", "orcb_decode_byte_rle", "orcb_decode_bool_rle",
     "orcb_decode_varint128", "orcb_decompress_stream", "orcb_host_decompress_section", "orcb_last_error", "orcb_index_retries", "orcb_layout_retries", "orcb_build_info",
-    "orcb_device_available", "orcb_zone_table",
+    "orcb_device_available", "orcb_zone_table", "orcb_file_format_version", "orcb_file_num_user_metadata", "orcb_file_user_metadata",
 ]
 
 
@@ -293,6 +293,24 @@ class _File:
     @property
     def compression_block_size(self) -> int:
         return lib().orcb_file_compression_block_size(self._h)
+
+    @property
+    def file_format_version(self) -> str:
+        L = lib()
+        L.orcb_file_format_version.restype = ctypes.c_char_p
+        L.orcb_file_format_version.argtypes = [ctypes.c_void_p]
+        return L.orcb_file_format_version(self._h).decode()
+
+    @property
+    def user_custom_metadata(self) -> dict:
+        L = lib()
+        L.orcb_file_num_user_metadata.argtypes = [ctypes.c_void_p]
+        out = {}
+        for i in range(L.orcb_file_num_user_metadata(self._h)):
+            k, v, n = ctypes.c_char_p(), ctypes.POINTER(ctypes.c_uint8)(), ctypes.c_size_t(0)
+            _check(L.orcb_file_user_metadata(self._h, ctypes.c_uint32(i), ctypes.byref(k), ctypes.byref(v), ctypes.byref(n)))
+            out[k.value.decode()] = ctypes.string_at(v, n.value) if n.value else b""
+        return out
 
     @property
     def row_index_stride(self) -> Optional[int]:

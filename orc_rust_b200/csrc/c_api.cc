@@ -305,6 +305,17 @@ const char* orcb_file_root_column_name(const OrcbFile* f, uint32_t i) {
     return i < f->meta.root_columns.size() ? f->meta.root_columns[i].first.c_str() : nullptr;
 }
 uint32_t orcb_file_root_column_id(const OrcbFile* f, uint32_t i) { return i < f->meta.root_columns.size() ? f->meta.root_columns[i].second : 0u; }
+const char* orcb_file_format_version(const OrcbFile* f) { return f->meta.format_version.c_str(); }
+uint32_t orcb_file_num_user_metadata(const OrcbFile* f) { return (uint32_t)f->meta.user_metadata.size(); }
+int orcb_file_user_metadata(const OrcbFile* f, uint32_t i, const char** key, const uint8_t** value, size_t* value_len) {
+    return guarded([&] {
+        if (!f || !key || !value || !value_len) fail(ORCB_INVALID_ARGUMENT, "NULL argument");
+        if (i >= f->meta.user_metadata.size()) fail(ORCB_INVALID_ARGUMENT, "metadata index out of range");
+        *key = f->meta.user_metadata[i].first.c_str();
+        *value = (const uint8_t*)f->meta.user_metadata[i].second.data();
+        *value_len = f->meta.user_metadata[i].second.size();
+    });
+}
 int orcb_file_stripe_info(const OrcbFile* f, uint32_t stripe, uint64_t out[5]) {
     return guarded([&] {
         if (stripe >= f->meta.stripes.size()) fail(ORCB_INVALID_ARGUMENT, "stripe index out of range");

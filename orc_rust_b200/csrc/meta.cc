@@ -516,6 +516,12 @@ void parse_file_tail(FileMeta& fm) {
                 case 1: footer_len = f.value; have_footer = true; break;
                 case 2: fm.compression = (int)f.value; break;
                 case 3: fm.block_size = f.value; break;
+                case 4: {  // repeated uint32 version, packed or not
+                    std::vector<uint64_t> v;
+                    PbCursor::packed_u64(f, v);
+                    for (uint64_t x : v) fm.format_version += (fm.format_version.empty() ? "" : ".") + std::to_string((uint32_t)x);
+                    break;
+                }
                 case 5: meta_len = f.value; have_meta = true; break;
                 default: break;
             }

@@ -140,6 +140,7 @@ struct FileMeta {
     std::vector<std::pair<std::string, uint32_t>> root_columns;  // (name, column id)
     uint64_t num_rows = 0;
     int64_t row_index_stride = -1;
+    std::string format_version;  // PostScript.version joined with '.', "" when absent (src/reader/metadata.rs:119-127)
 
     StripeFooter read_stripe_footer(uint32_t stripe) const;
     // positions of every row-index entry of `column` in `stripe` (empty if no ROW_INDEX stream)

@@ -438,3 +438,29 @@ def test_try_new_async(ob):
 
     rows, names, total = asyncio.run(go())
     assert (rows, names, total) == (5, ["a", "b", "str_direct"], 5)
+
+
+def test_file_format_version_and_user_metadata(ob):
+    """FileMetadata::file_format_version / user_custom_metadata (src/reader/metadata.rs:112-127) on every fixture, against
+    the oracle's footer parse and pyarrow (`file_version`, `metadata`)."""
+    import glob
+    import pyarrow.orc as po
+    from oracle import orc_oracle as oo
+    n = with_md = 0
+    for f in sorted(glob.glob(os.path.join(GOLDEN, "ref_*", "*.orc"))):
+        data = open(f, "rb").read()
+        try:
+            of = oo.OracleFile(data)
+        except oo.OracleError:
+            continue
+        fm = ob.ArrowReaderBuilder.try_new(data).file_metadata()
+        assert fm.user_custom_metadata == {k: bytes(v) for k, v in of.user_metadata.items()}, f
+        try:
+            pf = po.ORCFile(f)
+        except Exception:
+            continue
+        assert fm.file_format_version == pf.file_version, f
+        assert {k.encode(): v for k, v in fm.user_custom_metadata.items()} == dict(pf.metadata or {}), f
+        n += 1
+        with_md += bool(fm.user_custom_metadata)
+    assert n > 40 and with_md >= 1
