@@ -464,3 +464,27 @@ def test_file_format_version_and_user_metadata(ob):
         n += 1
         with_md += bool(fm.user_custom_metadata)
     assert n > 40 and with_md >= 1
+
+
+def test_c_program_against_the_header(ob, tmp_path):
+    """include/orc_b200.h is plain C (C99, -pedantic) and the library links from C: tests/c_abi_host.c opens a fixture,
+    reads metadata and schema, plans a job, and sees statuses (not aborts, not a CPU fallback) where a device or a valid
+    file is missing."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    libdir = os.path.dirname(ob.lib()._name)
+    exe = str(tmp_path / "c_abi_host")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c_abi_host.c"), "-o", exe, "-L", libdir, "-l:liborc_b200.so",
+                           "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe, os.path.join(GOLDEN, "ref_basic", "test.orc")], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.splitlines()
+    assert lines[0] == "rows=5 stripes=1 compression=0 version=0.12 columns=20"
+    assert lines[1] == "schema=+s children=20 first=a:f"
+    assert lines[2].startswith("planned stripes=1 rows=5 batches=1 segments=")
+    if not ob.device_available():
+        assert "next_without_device=20" in lines  # ORCB_CUDA
+    assert lines[-1].startswith("open_truncated=3 ")  # ORCB_OUT_OF_SPEC
