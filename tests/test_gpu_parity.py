@@ -1,7 +1,8 @@
 """GPU parity: CUDA decode through the C ABI vs the CPU oracle, byte-identical Arrow buffers per batch.
-Covers the reference's fixture files the device path accepts (NONE / Snappy / LZ4, flat schemas), the
-stream-level known-answer vectors of the reference's unit tests, and seeded synthetic files of the
-BASELINE configs at sizes the oracle finishes in seconds."""
+Covers every fixture file of the reference (all six compression kinds; flat schemas byte for byte, nested ones by
+value, validity and null count), the stream-level known-answer vectors of the reference's unit tests, random and
+damaged streams of every codec, and seeded synthetic files of the BASELINE configs at sizes the oracle finishes in
+seconds."""
 import glob
 import os
 
