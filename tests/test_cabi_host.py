@@ -488,3 +488,35 @@ def test_c_program_against_the_header(ob, tmp_path):
     if not ob.device_available():
         assert "next_without_device=20" in lines  # ORCB_CUDA
     assert lines[-1].startswith("open_truncated=3 ")  # ORCB_OUT_OF_SPEC
+
+
+@pytest.mark.parametrize("kind", ["lz4", "snappy", "zstd", "lzo", "lzo-plain"])
+def test_recompressed_files_are_valid_orc(ob, tmp_path, kind):
+    """tools/orc_recompress.py (the source of the bench's LZ4 / LZO / Zstandard sets and of config 3's identical chunking,
+    SURVEY.md §8(d)) without a GPU: the rewritten file reads back equal to the original through Apache ORC C++ (pyarrow,
+    an independent reader) and through the oracle, a fair share of its chunks is really compressed, and the planner
+    accepts the rewritten row-index positions (as many (stream, row group) segments as for the uncompressed file)."""
+    import sys
+    import pyarrow.orc as po
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_orc
+    import orc_recompress
+    from oracle import orc_oracle as oo
+    from parity_util import assert_batches_identical
+    for name, table in (("li", gen_orc.lineitem_table(20_000, 21)), ("nh", gen_orc.nullheavy_table(40_000, 5))):
+        src = gen_orc.write(table, str(tmp_path / f"{name}.orc"), row_index_stride=2000)
+        dst = str(tmp_path / f"{name}.{kind}.orc")
+        st = orc_recompress.recompress(src, dst, kind, 65536)
+        assert st["compressed"] > 0 and os.path.getsize(dst) < os.path.getsize(src)
+        assert orc_recompress.compressed_chunk_fraction(dst)["fraction"] > 0.15
+        if kind != "lzo":
+            # (LZO: the in-repo compressor emits the M1 instructions of LZO1X - a 2-byte match after 1-3 literals, a 3-byte
+            # match at 2049..3072 after a literal run - on purpose, and Apache ORC C++ 's decoder places those 2048 bytes
+            # further back than minilzo / the published format do: found with this test, see DESIGN.md §6.  The oracle
+            # and the planner checks below still run for LZO; "lzo-plain" is the same compressor without those two
+            # instructions, which Apache reads.)
+            assert po.read_table(dst).equals(po.read_table(src)), f"{name} {kind}: pyarrow reads different data"
+        assert_batches_identical(oo.OracleFile(open(dst, "rb").read()).read(), oo.OracleFile(open(src, "rb").read()).read(), f"{name} {kind}")
+        a, b = ob.DecodeJob([dst]).plan().stats(), ob.DecodeJob([src]).plan().stats()
+        assert a["n_segments"] == b["n_segments"] and a["n_rows"] == b["n_rows"]
+        assert a["input_bytes"] < b["input_bytes"]

@@ -112,6 +112,11 @@ static uint8_t* lzo_run_len(uint8_t* o, size_t t) { /* t >= 1: zero bytes of 255
     return o;
 }
 
+/* lzc_lzo_use_m1(0): leave out the two M1 instructions (what the LZO compressors of ORC writers produce; Apache ORC C++'s
+ * decoder reads M1 distances 2048 bytes too far back, so files for that reader need this). */
+static int lzo_m1 = 1;
+void lzc_lzo_use_m1(int on) { lzo_m1 = on; }
+
 size_t lzc_lzo_compress(const uint8_t* src, size_t n, uint8_t* dst) {
     enum { HB = 15 };
     static int32_t h3[1 << HB], h2[1 << 16];
@@ -132,11 +137,12 @@ size_t lzc_lzo_compress(const uint8_t* src, size_t n, uint8_t* dst) {
             if (c >= 0 && ip - (size_t)c <= 49151) {
                 size_t l = 0, lim = n - ip < 3000 ? n - ip : 3000;
                 while (l < lim && src[c + l] == src[ip + l]) l++;
-                if (l >= 3) { mlen = l; mdist = ip - (size_t)c; }
+                /* (plain mode: no 3- and 4-byte matches beyond 16 KiB either - Apache's decoder rejects an M4 that short) */
+                if (l >= 3 && (lzo_m1 || l >= 5 || ip - (size_t)c <= 16384)) { mlen = l; mdist = ip - (size_t)c; }
             }
         }
         size_t ll = ip - lit_start;
-        if (!mlen && ip + 2 <= n && started && ll >= 1 && ll <= 3) {
+        if (lzo_m1 && !mlen && ip + 2 <= n && started && ll >= 1 && ll <= 3) {
             uint32_t k = src[ip] | (src[ip + 1] << 8);
             int32_t c = h2[k];
             if (c >= 0 && ip - (size_t)c <= 1024) { mlen = 2; mdist = ip - (size_t)c; }
@@ -169,7 +175,7 @@ size_t lzc_lzo_compress(const uint8_t* src, size_t n, uint8_t* dst) {
             sbits = o;
             *o++ = (uint8_t)((d & 3) << 2);
             *o++ = (uint8_t)(d >> 2);
-        } else if (mlen == 3 && state == 4 && mdist >= 2049 && mdist <= 3072) {
+        } else if (lzo_m1 && mlen == 3 && state == 4 && mdist >= 2049 && mdist <= 3072) {
             size_t d = mdist - 2049;
             sbits = o;
             *o++ = (uint8_t)((d & 3) << 2);

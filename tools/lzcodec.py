@@ -33,7 +33,8 @@ def compress_block(kind: str, data: bytes) -> bytes:
         import pyarrow as pa
         codec = pa.Codec("zstd", compression_level=3) if kind == "zstd" else pa.Codec("lz4_raw" if kind == "lz4-lib" else "snappy")
         return codec.compress(bytes(data), asbytes=True) if len(data) else b""
-    fn = {"lz4": L.lzc_lz4_compress, "snappy": L.lzc_snappy_compress, "lzo": L.lzc_lzo_compress}[kind]
+    fn = {"lz4": L.lzc_lz4_compress, "snappy": L.lzc_snappy_compress, "lzo": L.lzc_lzo_compress, "lzo-plain": L.lzc_lzo_compress}[kind]
+    L.lzc_lzo_use_m1(0 if kind == "lzo-plain" else 1)  # "lzo-plain": without the M1 instructions (see lzcodec.c)
     n = fn(bytes(data), len(data), buf)
     return buf.raw[:n]
 

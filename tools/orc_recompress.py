@@ -20,7 +20,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import lzcodec  # noqa: E402
 
-KIND_CODE = {"snappy": 2, "snappy-lib": 2, "lzo": 3, "lz4": 4, "lz4-lib": 4, "zstd": 5}
+KIND_CODE = {"snappy": 2, "snappy-lib": 2, "lzo": 3, "lzo-plain": 3, "lz4": 4, "lz4-lib": 4, "zstd": 5}
 # ORC TypeKind numbers (orc_proto.proto)
 T_BOOLEAN, T_BYTE, T_SHORT, T_INT, T_LONG, T_FLOAT, T_DOUBLE, T_STRING, T_BINARY, T_TIMESTAMP, T_LIST, T_MAP, T_STRUCT, \
     T_UNION, T_DECIMAL, T_DATE, T_VARCHAR, T_CHAR, T_TIMESTAMP_INSTANT = range(19)
@@ -360,7 +360,7 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("src")
     ap.add_argument("dst")
-    ap.add_argument("--kind", default="lz4", choices=["lz4", "lz4-lib", "snappy", "snappy-lib", "zstd", "lzo"])
+    ap.add_argument("--kind", default="lz4", choices=["lz4", "lz4-lib", "snappy", "snappy-lib", "zstd", "lzo", "lzo-plain"])
     ap.add_argument("--block-size", type=int, default=256 << 10)
     a = ap.parse_args()
     st = recompress(a.src, a.dst, a.kind, a.block_size)
