@@ -520,3 +520,34 @@ def test_recompressed_files_are_valid_orc(ob, tmp_path, kind):
         a, b = ob.DecodeJob([dst]).plan().stats(), ob.DecodeJob([src]).plan().stats()
         assert a["n_segments"] == b["n_segments"] and a["n_rows"] == b["n_rows"]
         assert a["input_bytes"] < b["input_bytes"]
+
+
+def test_in_repo_compressors_against_the_libraries(ob):
+    """The block compressors that make the decoders' test inputs (tools/lzcodec.c: every Snappy element form, every LZ4
+    sequence shape) produce streams the libraries themselves decode to the same bytes - snappy and liblz4 through pyarrow's
+    codecs, the C counterparts of the reference's `snap` and `lz4_flex` - and the host decoders of metadata sections
+    agree with the libraries in both directions (library-compressed blocks decode here, blocks compressed here decode
+    there)."""
+    import sys
+    import numpy as np
+    import pyarrow as pa
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import lzcodec
+    rng = np.random.default_rng(9)
+    words = [bytes(rng.integers(97, 123, rng.integers(1, 12), dtype=np.uint8)) for _ in range(300)]
+    cases = {
+        "text": b" ".join(words[i] for i in rng.integers(0, 300, 30_000)),
+        "runs": b"".join(bytes([int(v)]) * int(k) for v, k in zip(rng.integers(0, 256, 400), rng.integers(1, 700, 400))),
+        "noise": bytes(rng.integers(0, 256, 70_000, dtype=np.uint8)),
+        "far": (lambda a: a + bytes(rng.integers(0, 256, 40_000, dtype=np.uint8)) + a)(bytes(rng.integers(0, 256, 5_000, dtype=np.uint8))),
+        "ints": np.cumsum(rng.integers(0, 50, 30_000)).astype("<i4").tobytes(),
+        "tiny": b"abc",
+    }
+    for name, d in cases.items():
+        for kind, codec, code in (("snappy", "snappy", 2), ("lz4", "lz4_raw", 4)):
+            ours = lzcodec.compress_block(kind, d)
+            assert pa.Codec(codec).decompress(ours, decompressed_size=len(d), asbytes=True) == d, f"{kind} {name}: the library rejects our block"
+            theirs = pa.Codec(codec).compress(d, asbytes=True)
+            for blk in (ours, theirs):
+                framed = (len(blk) << 1).to_bytes(3, "little") + blk
+                assert ob.host_decompress_section(code, framed, 1 << 20) == d, f"{kind} {name}"
