@@ -533,6 +533,7 @@ def test_in_repo_compressors_against_the_libraries(ob):
     import pyarrow as pa
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import lzcodec
+    from oracle import orc_oracle as oo
     rng = np.random.default_rng(9)
     words = [bytes(rng.integers(97, 123, rng.integers(1, 12), dtype=np.uint8)) for _ in range(300)]
     cases = {
@@ -551,3 +552,4 @@ def test_in_repo_compressors_against_the_libraries(ob):
             for blk in (ours, theirs):
                 framed = (len(blk) << 1).to_bytes(3, "little") + blk
                 assert ob.host_decompress_section(code, framed, 1 << 20) == d, f"{kind} {name}"
+                assert bytes(oo.decompress_stream(code, framed, 1 << 20)) == d, f"oracle {kind} {name}"
