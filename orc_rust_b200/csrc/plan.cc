@@ -664,10 +664,10 @@ void Job::plan_stripe(uint32_t task_idx) {
                     } else if (!sr.chunks.empty()) {
                         // compressed file: the bytes are readable where the entry point lies in a chunk that was stored
                         // as is (incompressible integer streams usually are)
-                        const size_t ci = (size_t)(std::upper_bound(sr.chunk_dst.begin(), sr.chunk_dst.end(), (uint64_t)sg.start_byte) - sr.chunk_dst.begin()) - 1;
-                        if (ci < sr.chunks.size() && sr.chunks[ci].original)
-                            long_runs = rle2_opens_with_long_runs(sp + sr.chunks[ci].src_off, sr.chunks[ci].src_len,
-                                                                  (uint32_t)(sg.start_byte - sr.chunk_dst[ci]));
+                        const size_t chi = (size_t)(std::upper_bound(sr.chunk_dst.begin(), sr.chunk_dst.end(), (uint64_t)sg.start_byte) - sr.chunk_dst.begin()) - 1;
+                        if (chi < sr.chunks.size() && sr.chunks[chi].original)
+                            long_runs = rle2_opens_with_long_runs(sp + sr.chunks[chi].src_off, sr.chunks[chi].src_len,
+                                                                  (uint32_t)(sg.start_byte - sr.chunk_dst[chi]));
                         else
                             // not readable here: decimal scales are constant runs in practice, and so is any stream that
                             // spends less than a bit per value (sr.len is exact for Snappy and sized Zstandard frames,
