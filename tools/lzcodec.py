@@ -16,6 +16,11 @@ def lib():
         if not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
             subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-o", _SO, src])
         L = ctypes.CDLL(_SO)
+        if not hasattr(L, "lzc_lzo_use_m1"):  # a library from before that entry point (copied trees do not keep mtimes)
+            tmp = _SO + f".{os.getpid()}.tmp"
+            subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-o", tmp, src])
+            os.replace(tmp, _SO)
+            L = ctypes.CDLL(_SO)
         for f in (L.lzc_lz4_compress, L.lzc_snappy_compress, L.lzc_lzo_compress):
             f.restype = ctypes.c_size_t
             f.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p]
