@@ -553,3 +553,35 @@ def test_in_repo_compressors_against_the_libraries(ob):
                 framed = (len(blk) << 1).to_bytes(3, "little") + blk
                 assert ob.host_decompress_section(code, framed, 1 << 20) == d, f"{kind} {name}"
                 assert bytes(oo.decompress_stream(code, framed, 1 << 20)) == d, f"oracle {kind} {name}"
+
+
+def test_async_stream_error_state_without_device(ob):
+    """`ArrowStreamReader` (src/async_arrow_reader.rs:252-290) when a request fails: the error reaches the awaiting task
+    from the library's thread, and the stream stays in the error state (StreamState::Error, :262-277) - here the failure
+    is the missing device, which also shows that the async path has no CPU fallback; an empty stream (a byte range
+    without stripes) simply ends."""
+    import asyncio
+    if ob.device_available():
+        pytest.skip("needs a machine without a CUDA device")
+    path = os.path.join(GOLDEN, "ref_basic", "test.orc")
+
+    async def failing():
+        stream = ob.ArrowReaderBuilder.try_new(path).build_async()
+        assert stream.schema().names[:2] == ["a", "b"]
+        seen = []
+        for _ in range(2):
+            try:
+                await stream.__anext__()
+                seen.append("batch")
+            except ob.OrcError as e:
+                seen.append(e.variant)
+            except StopAsyncIteration:
+                seen.append("end")
+        return seen
+
+    async def empty():
+        return [b async for b in ob.ArrowReaderBuilder.try_new(path).with_file_byte_range(100, 2000).build_async()]
+
+    first, second = asyncio.run(failing())
+    assert first == "Cuda" and second in ("Cuda", "Unexpected")  # the reader stays in the error state
+    assert asyncio.run(empty()) == []
