@@ -106,6 +106,10 @@ static void host_lz4_block(const uint8_t* s, size_t n, size_t max_out, std::vect
 // Raw DEFLATE for metadata sections of Zlib files (footer, stripe footers, row indexes); data streams are inflated on the
 // device (k_decompress.cu).  Bit-by-bit canonical decode: these sections are a few KiB.
 namespace {
+// The input ended inside the stream.  flate2's read decoder (the reference, src/compression.rs:142-149) does not report
+// that: read_to_end returns what was decoded up to there, and so does this decoder (whatever parses the section next
+// usually fails on the short bytes, with its own error).
+struct InflateEof {};
 struct HostBits {
     const uint8_t* s;
     size_t n, pos = 0;
@@ -113,7 +117,7 @@ struct HostBits {
     int cnt = 0;
     uint32_t bits(int k) {
         while (cnt < k) {
-            if (pos >= n) fail(ORCB_IO_ERROR, "corrupt deflate stream");
+            if (pos >= n) throw InflateEof{};
             buf |= (uint32_t)s[pos++] << cnt;
             cnt += 8;
         }
@@ -155,7 +159,15 @@ struct HostHuff {
 };
 }  // namespace
 
+static void host_inflate_blocks(const uint8_t* s, size_t n, std::vector<uint8_t>& out);
 static void host_inflate(const uint8_t* s, size_t n, std::vector<uint8_t>& out) {
+    try {
+        host_inflate_blocks(s, n, out);
+    } catch (const InflateEof&) {
+    }
+}
+
+static void host_inflate_blocks(const uint8_t* s, size_t n, std::vector<uint8_t>& out) {
     static const uint16_t LBASE[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
     static const uint8_t LEXT[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
     static const uint16_t DBASE[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
@@ -170,10 +182,14 @@ static void host_inflate(const uint8_t* s, size_t n, std::vector<uint8_t>& out) 
         if (type == 0) {
             b.buf = 0;
             b.cnt = 0;
-            if (b.pos + 4 > n) fail(ORCB_IO_ERROR, "corrupt deflate stream");
+            if (b.pos + 4 > n) throw InflateEof{};
             const uint32_t len = s[b.pos] | (s[b.pos + 1] << 8), nlen = s[b.pos + 2] | (s[b.pos + 3] << 8);
             b.pos += 4;
-            if ((len ^ nlen) != 0xffffu || b.pos + len > n) fail(ORCB_IO_ERROR, "corrupt deflate stream");
+            if ((len ^ nlen) != 0xffffu) fail(ORCB_IO_ERROR, "corrupt deflate stream");
+            if (len > n - b.pos) {  // a stored block cut short: the bytes that are there, then the end of input
+                out.insert(out.end(), s + b.pos, s + n);
+                throw InflateEof{};
+            }
             out.insert(out.end(), s + b.pos, s + b.pos + len);
             b.pos += len;
             continue;

@@ -585,3 +585,40 @@ def test_async_stream_error_state_without_device(ob):
     first, second = asyncio.run(failing())
     assert first == "Cuda" and second in ("Cuda", "Unexpected")  # the reader stays in the error state
     assert asyncio.run(empty()) == []
+
+
+def test_host_inflate_on_damaged_and_truncated_streams(ob):
+    """The host inflate of metadata sections against zlib used the way flate2's read decoder behaves (the oracle,
+    oracle/codecs.c zlib_block; src/compression.rs:142-149): same verdict and same bytes on damaged streams, and a
+    stream whose input ends early yields what was decoded up to there instead of an error."""
+    import zlib
+    import numpy as np
+    from oracle import orc_oracle as oo
+    rng = np.random.default_rng(3)
+    words = [bytes(rng.integers(97, 123, rng.integers(2, 10), dtype=np.uint8)) for _ in range(300)]
+    cases = {"text": b" ".join(words[i] for i in rng.integers(0, 300, 6000)), "noise": bytes(rng.integers(0, 256, 4000, dtype=np.uint8)),
+             "low": bytes(rng.integers(0, 4, 20_000, dtype=np.uint8))}
+    both_ok = both_err = 0
+    for name, d in cases.items():
+        for lvl, strategy in ((1, zlib.Z_DEFAULT_STRATEGY), (9, zlib.Z_DEFAULT_STRATEGY), (6, zlib.Z_FIXED), (0, zlib.Z_DEFAULT_STRATEGY)):
+            co = zlib.compressobj(lvl, zlib.DEFLATED, -15, 9, strategy)
+            c = co.compress(d) + co.flush()
+            for it in range(150):
+                bad = bytearray(c)
+                for _ in range(int(rng.integers(0, 4))):
+                    bad[int(rng.integers(0, len(bad)))] = int(rng.integers(0, 256))
+                if it % 3 == 0:
+                    bad = bad[: int(rng.integers(1, len(bad)))]
+                f = (len(bad) << 1).to_bytes(3, "little") + bytes(bad)
+                try:
+                    exp = bytes(oo.decompress_stream(1, f, 1 << 20))
+                except oo.OracleError:
+                    exp = None
+                try:
+                    got = ob.host_decompress_section(1, f, 1 << 20)
+                except ob.OrcError:
+                    got = None
+                assert got == exp, f"{name} level {lvl} #{it}: {None if exp is None else len(exp)} vs {None if got is None else len(got)}"
+                both_ok += exp is not None
+                both_err += exp is None
+    assert both_ok > 500 and both_err > 100
