@@ -622,3 +622,48 @@ def test_host_inflate_on_damaged_and_truncated_streams(ob):
                 both_ok += exp is not None
                 both_err += exp is None
     assert both_ok > 500 and both_err > 100
+
+
+@pytest.mark.parametrize("kind,code,codec", [("snappy", 2, "snappy"), ("lz4", 4, "lz4_raw")])
+def test_host_lz_decoders_on_damaged_streams(ob, kind, code, codec):
+    """The host Snappy / LZ4 decoders of metadata sections against the oracle's (two separate restatements of
+    `snap` / `lz4_flex`, src/compression.rs:161-195) on damaged and truncated blocks from the in-repo compressors and
+    from the libraries: same verdict, same bytes.  For Snappy the library's verdict is the same as well."""
+    import sys
+    import numpy as np
+    import pyarrow as pa
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import lzcodec
+    from oracle import orc_oracle as oo
+    rng = np.random.default_rng(8)
+    words = [bytes(rng.integers(97, 123, rng.integers(2, 10), dtype=np.uint8)) for _ in range(300)]
+    cases = {"text": b" ".join(words[i] for i in rng.integers(0, 300, 5000)), "noise": bytes(rng.integers(0, 256, 3000, dtype=np.uint8)),
+             "low": bytes(rng.integers(0, 4, 15_000, dtype=np.uint8))}
+    ok = err = 0
+    for name, d in cases.items():
+        for c in (lzcodec.compress_block(kind, d), pa.Codec(codec).compress(d, asbytes=True)):
+            for it in range(200):
+                bad = bytearray(c)
+                for _ in range(int(rng.integers(0, 4))):
+                    bad[int(rng.integers(0, len(bad)))] = int(rng.integers(0, 256))
+                if it % 3 == 0:
+                    bad = bad[: int(rng.integers(1, len(bad)))]
+                f = (len(bad) << 1).to_bytes(3, "little") + bytes(bad)
+                try:
+                    exp = bytes(oo.decompress_stream(code, f, 1 << 20))
+                except oo.OracleError:
+                    exp = None
+                try:
+                    got = ob.host_decompress_section(code, f, 1 << 20)
+                except ob.OrcError:
+                    got = None
+                assert got == exp, f"{kind} {name} #{it}"
+                if kind == "snappy":
+                    try:
+                        lib = pa.Codec(codec).decompress(bytes(bad), decompressed_size=len(got) if got is not None else len(d), asbytes=True)
+                    except Exception:
+                        lib = None
+                    assert lib == got, f"snappy {name} #{it}: the library disagrees"
+                ok += got is not None
+                err += got is None
+    assert ok > 200 and err > 200
