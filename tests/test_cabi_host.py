@@ -512,7 +512,8 @@ def test_recompressed_files_are_valid_orc(ob, tmp_path, kind):
         if kind != "lzo":
             # (LZO: the in-repo compressor emits the M1 instructions of LZO1X - a 2-byte match after 1-3 literals, a 3-byte
             # match at 2049..3072 after a literal run - on purpose, and Apache ORC C++ 's decoder places those 2048 bytes
-            # further back than minilzo / the published format do: found with this test, see DESIGN.md §6.  The oracle
+            # further back than minilzo / the published format do (and rejects a 3-byte M4 match, opcode 0x11): found with this
+            # test, see DESIGN.md §6.  The oracle
             # and the planner checks below still run for LZO; "lzo-plain" is the same compressor without those two
             # instructions, which Apache reads.)
             assert po.read_table(dst).equals(po.read_table(src)), f"{name} {kind}: pyarrow reads different data"

@@ -137,7 +137,8 @@ size_t lzc_lzo_compress(const uint8_t* src, size_t n, uint8_t* dst) {
             if (c >= 0 && ip - (size_t)c <= 49151) {
                 size_t l = 0, lim = n - ip < 3000 ? n - ip : 3000;
                 while (l < lim && src[c + l] == src[ip + l]) l++;
-                /* (plain mode: no 3- and 4-byte matches beyond 16 KiB either - Apache's decoder rejects an M4 that short) */
+                /* (plain mode: no 3- and 4-byte matches beyond 16 KiB either - Apache's decoder takes the 3-byte M4 opcode, 0x11, for
+                 * the end marker) */
                 if (l >= 3 && (lzo_m1 || l >= 5 || ip - (size_t)c <= 16384)) { mlen = l; mdist = ip - (size_t)c; }
             }
         }
