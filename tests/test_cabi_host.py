@@ -668,3 +668,25 @@ def test_host_lz_decoders_on_damaged_streams(ob, kind, code, codec):
                 ok += got is not None
                 err += got is None
     assert ok > 200 and err > 200
+
+
+def test_snappy_preamble_cannot_size_an_allocation(ob):
+    """Regression (found by tools/fuzz_host.sh): the uncompressed-length preamble of a Snappy block in a metadata section
+    used to reserve that many bytes before anything was decoded - 32 GiB for five bytes of input.  No element makes more
+    than 64 bytes out of 3, so a preamble the input cannot meet is an error at once."""
+    import time
+    for preamble in (b"\xff\xff\xff\xff\x7f", b"\xff\xff\xff\xff\x0f", b"\x80\x80\x80\x80\x08"):
+        blk = preamble + b"\x00a"
+        framed = (len(blk) << 1).to_bytes(3, "little") + blk
+        t0 = time.time()
+        with pytest.raises(ob.OrcError) as e:
+            ob.host_decompress_section(2, framed, 1 << 18)
+        assert e.value.variant == "BuildSnappyDecoder" and time.time() - t0 < 1.0
+    # a preamble the input can meet still decodes
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import lzcodec
+    d = b"ab" * 40_000
+    blk = lzcodec.compress_block("snappy", d)
+    assert len(blk) * 16 < len(d)
+    assert ob.host_decompress_section(2, (len(blk) << 1).to_bytes(3, "little") + blk, 1 << 18) == d
