@@ -690,3 +690,43 @@ def test_snappy_preamble_cannot_size_an_allocation(ob):
     blk = lzcodec.compress_block("snappy", d)
     assert len(blk) * 16 < len(d)
     assert ob.host_decompress_section(2, (len(blk) << 1).to_bytes(3, "little") + blk, 1 << 18) == d
+
+
+def test_damaged_stripe_row_count_with_predicate(ob, tmp_path):
+    """Regression (found by tools/fuzz_host.sh): with_predicate sizes its row-group verdict vector from the stripe's row
+    count; a footer that claims 2^60 rows used to ask for that much memory.  Such a stripe is refused (the decoder takes
+    stripes of up to 2^32 rows), quickly, and so is planning it."""
+    import sys
+    import time
+    import pyarrow as pa
+    import pyarrow.orc as po
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import orc_recompress as rc
+    p = str(tmp_path / "t.orc")
+    po.write_table(pa.table({"x": pa.array(range(5000), pa.int64())}), p, compression="uncompressed", row_index_stride=1000)
+    data = open(p, "rb").read()
+    n = len(data)
+    ps_len = data[-1]
+    ps = rc.pb_parse(data[n - 1 - ps_len:n - 1])
+    fl = rc.pb_get(ps, 1)
+    footer = rc.pb_parse(data[n - 1 - ps_len - fl:n - 1 - ps_len])
+    for fld in footer:
+        if fld[0] == 3:  # StripeInformation: numberOfRows = 5
+            si = rc.pb_parse(fld[2])
+            for g in si:
+                if g[0] == 5:
+                    g[2] = 1 << 60
+            fld[2] = rc.pb_build(si)
+    new_footer = rc.pb_build(footer)
+    for fld in ps:
+        if fld[0] == 1:
+            fld[2] = len(new_footer)
+    new_ps = rc.pb_build(ps)
+    bad = data[:n - 1 - ps_len - fl] + new_footer + new_ps + bytes([len(new_ps)])
+    t0 = time.time()
+    with pytest.raises(ob.OrcError) as e:
+        ob.predicate_row_groups(bad, 0, ob.Predicate.eq("x", ob.PredicateValue.Int64(5)))
+    assert e.value.variant == "NotImplemented"
+    with pytest.raises(ob.OrcError):
+        ob.DecodeJob([bad]).plan()
+    assert time.time() - t0 < 2.0
