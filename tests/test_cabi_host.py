@@ -730,3 +730,50 @@ def test_damaged_stripe_row_count_with_predicate(ob, tmp_path):
     with pytest.raises(ob.OrcError):
         ob.DecodeJob([bad]).plan()
     assert time.time() - t0 < 2.0
+
+
+def test_crafted_type_trees(ob, tmp_path):
+    """A footer whose type list is not a tree - a type that is its own child, a child that is an ancestor or the root, a
+    child id past the list, a struct with fewer children than names - is refused when the file is opened (as
+    RootDataType::from_proto refuses it); it cannot send the schema export or the planner into a loop."""
+    import sys
+    import pyarrow as pa
+    import pyarrow.orc as po
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import orc_recompress as rc
+    p = str(tmp_path / "n.orc")
+    po.write_table(pa.table({"s": pa.array([{"a": 1, "b": [1, 2]}, {"a": 2, "b": []}]), "x": pa.array([1, 2])}), p, compression="uncompressed")
+    data = open(p, "rb").read()
+    n, ps_len = len(data), data[-1]
+
+    def with_subtypes(type_idx, subs):
+        ps = rc.pb_parse(data[n - 1 - ps_len:n - 1])
+        fl = rc.pb_get(ps, 1)
+        footer = rc.pb_parse(data[n - 1 - ps_len - fl:n - 1 - ps_len])
+        k = 0
+        for f in footer:
+            if f[0] == 4:  # Footer.types
+                if k == type_idx:
+                    ty = rc.pb_parse(f[2])
+                    for g in ty:
+                        if g[0] == 2:  # Type.subtypes (packed)
+                            g[2] = bytes(subs)
+                    f[2] = rc.pb_build(ty)
+                k += 1
+        nf = rc.pb_build(footer)
+        for f in ps:
+            if f[0] == 1:
+                f[2] = len(nf)
+        nps = rc.pb_build(ps)
+        return data[:n - 1 - ps_len - fl] + nf + nps + bytes([len(nps)])
+
+    # types of the file: 0 struct<s, x>, 1 struct<a, b>, 2 a, 3 list, 4 item, 5 x
+    assert ob.ArrowReaderBuilder.try_new(with_subtypes(3, [4])).schema().names == ["s", "x"]  # the rewrite itself is sound
+    for what, (ti, subs) in {"a list that is its own child": (3, [3]), "a list whose child is its parent": (3, [1]),
+                             "a struct with the root as a child": (1, [0, 3]), "a root that contains itself": (0, [0, 5]),
+                             "a child id past the type list": (3, [99]), "fewer children than names": (1, [2])}.items():
+        with pytest.raises(ob.OrcError):
+            b = ob.ArrowReaderBuilder.try_new(with_subtypes(ti, subs))
+            b.schema()
+            ob.DecodeJob([with_subtypes(ti, subs)]).plan()
+            pytest.fail(what + " was accepted")
