@@ -290,7 +290,7 @@ class OracleFile:
                     elif g == 2:
                         t.subtypes.extend(_packed_u(w, gw))
                     elif g == 3:
-                        t.field_names.append(w.decode("utf-8"))
+                        t.field_names.append(_pb_str(w, gw))
                     elif g == 4:
                         t.maximum_length = w
                     elif g == 5:
@@ -300,9 +300,9 @@ class OracleFile:
                 self.types.append(t)
             elif f == 5:
                 name, val = "", b""
-                for g, _, w in pb_fields(v):
+                for g, gw, w in pb_fields(v):
                     if g == 1:
-                        name = w.decode("utf-8")
+                        name = _pb_str(w, gw)
                     elif g == 2:
                         val = bytes(w)
                 self.user_metadata[name] = val
@@ -315,7 +315,28 @@ class OracleFile:
         root = self.types[0]
         if root.kind != K_STRUCT:
             raise OracleError(13, "non-struct root")
+        self._check_type_tree(0, 0)
         self.columns: List[Tuple[str, int]] = list(zip(root.field_names, root.subtypes))
+
+    def _check_type_tree(self, cid: int, depth: int):
+        """RootDataType::from_proto / DataType::from_proto (src/schema.rs:154-162, 206-234, 390-487): every type reachable
+        from the root must exist and have the children its kind takes.  (The reference recurses without a visited set: a
+        type that contains itself overflows its stack; here that is an Unexpected error like the other shapes.)"""
+        if depth > 256 or cid >= len(self.types):
+            raise OracleError(13, f"Column index out of bounds: {cid}")
+        t = self.types[cid]
+        n = len(t.subtypes)
+        if t.kind == K_STRUCT and n != len(t.field_names):
+            raise OracleError(13, f"Struct type for column index {cid} must have matching lengths for subtypes and field names lists")
+        if t.kind == K_LIST and n != 1:
+            raise OracleError(13, f"List type for column index {cid} must have 1 sub type, found {n}")
+        if t.kind == K_MAP and n != 2:
+            raise OracleError(13, f"Map type for column index {cid} must have 2 sub types, found {n}")
+        if t.kind == K_UNION and n > 127:
+            raise OracleError(13, f"Union type for column index {cid} cannot exceed 127 variants, found {n}")
+        if t.kind in (K_STRUCT, K_LIST, K_MAP, K_UNION):
+            for c in t.subtypes:
+                self._check_type_tree(c, depth + 1)
 
     # --- schema (src/schema.rs:503-577) ---------------------------------------------------------
     def arrow_type(self, col_id: int, ts_unit: str = "ns"):
@@ -371,7 +392,7 @@ class OracleFile:
         encodings: List[Tuple[int, int]] = []
         tz = None
         pos = s.offset
-        for f, _, v in pb_fields(b):
+        for f, fw, v in pb_fields(b):
             if f == 1:
                 kind = column = length = 0
                 for g, _, w in pb_fields(v):
@@ -392,7 +413,7 @@ class OracleFile:
                         ds = w
                 encodings.append((ek, ds))
             elif f == 3:
-                tz = v.decode("utf-8")
+                tz = _pb_str(v, fw)
         return streams, encodings, tz
 
     def _stream(self, smap, col, kind) -> np.ndarray:

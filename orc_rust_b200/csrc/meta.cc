@@ -472,6 +472,8 @@ const uint8_t* FileMeta::base_for(uint64_t off) const {
 // ---------------------------------------------------------------------------------------------
 // File tail (src/reader/metadata.rs:180-263)
 // ---------------------------------------------------------------------------------------------
+static std::string pb_string(const PbField& f);  // UTF-8 checked, as prost checks `string` fields
+
 static OrcType parse_type(const uint8_t* p, size_t n) {
     OrcType t;
     PbCursor c(p, n);
@@ -485,7 +487,7 @@ static OrcType parse_type(const uint8_t* p, size_t n) {
                 for (auto x : v) t.subtypes.push_back((uint32_t)x);
                 break;
             }
-            case 3: t.field_names.emplace_back((const char*)f.data, f.len); break;
+            case 3: t.field_names.push_back(pb_string(f)); break;
             case 4: t.max_length = (uint32_t)f.value; break;
             case 5: t.precision = (uint32_t)f.value; break;
             case 6: t.scale = (uint32_t)f.value; break;
@@ -574,7 +576,7 @@ void parse_file_tail(FileMeta& fm) {
                 PbCursor mc(f.data, f.len);
                 PbField g;
                 while (mc.next(g)) {
-                    if (g.number == 1) k.assign((const char*)g.data, g.len);
+                    if (g.number == 1) k = pb_string(g);  // string name = 1; bytes value = 2
                     else if (g.number == 2) v.assign((const char*)g.data, g.len);
                 }
                 fm.user_metadata.emplace_back(k, v);
@@ -637,7 +639,7 @@ StripeFooter FileMeta::read_stripe_footer(uint32_t stripe) const {
             sf.encodings.push_back(e);
         } else if (f.number == 3) {
             sf.has_tz = true;
-            sf.tz.assign((const char*)f.data, f.len);
+            sf.tz = pb_string(f);
         }
     }
     return sf;
