@@ -777,3 +777,61 @@ def test_crafted_type_trees(ob, tmp_path):
             b.schema()
             ob.DecodeJob([with_subtypes(ti, subs)]).plan()
             pytest.fail(what + " was accepted")
+
+
+def test_non_utf8_strings_in_the_footer(ob, tmp_path):
+    """prost checks `string` fields while it decodes the footer, so a field name or a user-metadata key that is not UTF-8
+    fails the open with DecodeProto in the reference; so it does here and in the oracle (found by tools/fuzz_struct.py:
+    such a name used to be exported in the Arrow schema as it was)."""
+    import sys
+    import pyarrow as pa
+    import pyarrow.orc as po
+    from oracle import orc_oracle as oo
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import orc_recompress as rc
+    p = str(tmp_path / "u.orc")
+    po.write_table(pa.table({"name": pa.array([1, 2, 3])}).replace_schema_metadata({"key": "v"}), p, compression="uncompressed")
+    data = open(p, "rb").read()
+    n, ps_len = len(data), data[-1]
+
+    def rebuilt(edit):
+        ps = rc.pb_parse(data[n - 1 - ps_len:n - 1])
+        fl = rc.pb_get(ps, 1)
+        footer = rc.pb_parse(data[n - 1 - ps_len - fl:n - 1 - ps_len])
+        assert edit(footer)
+        nf = rc.pb_build(footer)
+        for f in ps:
+            if f[0] == 1:
+                f[2] = len(nf)
+        nps = rc.pb_build(ps)
+        return data[:n - 1 - ps_len - fl] + nf + nps + bytes([len(nps)])
+
+    def bad_field_name(footer):
+        for f in footer:
+            if f[0] == 4:  # types[0]: the root struct
+                ty = rc.pb_parse(f[2])
+                for g in ty:
+                    if g[0] == 3:
+                        g[2] = b"na\xffe"
+                        f[2] = rc.pb_build(ty)
+                        return True
+        return False
+
+    def good_metadata_key(footer):  # UserMetadataItem { name = 1 (string), value = 2 (bytes: anything goes) }
+        footer.append([5, 2, rc.pb_build([[1, 2, "clé".encode()], [2, 2, b"\xff\x00"]])])
+        return True
+
+    def bad_metadata_key(footer):
+        footer.append([5, 2, rc.pb_build([[1, 2, b"\xc3\x28"], [2, 2, b"v"]])])
+        return True
+
+    assert ob.ArrowReaderBuilder.try_new(rebuilt(lambda f: True)).schema().names == ["name"]
+    assert ob.ArrowReaderBuilder.try_new(rebuilt(good_metadata_key)).file_metadata().user_custom_metadata == {"clé": b"\xff\x00"}
+    for edit in (bad_field_name, bad_metadata_key):
+        bad = rebuilt(edit)
+        with pytest.raises(ob.OrcError) as e:
+            ob.ArrowReaderBuilder.try_new(bad)
+        assert e.value.variant == "DecodeProto"
+        with pytest.raises(oo.OracleError) as e2:
+            oo.OracleFile(bad)
+        assert e2.value.variant == "DecodeProto"
