@@ -835,3 +835,33 @@ def test_non_utf8_strings_in_the_footer(ob, tmp_path):
         with pytest.raises(oo.OracleError) as e2:
             oo.OracleFile(bad)
         assert e2.value.variant == "DecodeProto"
+
+
+def test_unparsable_row_index_does_not_fail_the_plan(ob, tmp_path):
+    """The reference never reads ROW_INDEX streams when it decodes, so a row index that does not even parse as protobuf
+    must not fail the decode: the planner falls back to a sequential decode of that column (found by
+    tools/fuzz_struct.py; with_predicate, which does read the index in the reference, keeps every row in that case,
+    src/arrow_reader.rs:281-291)."""
+    import sys
+    import pyarrow as pa
+    import pyarrow.orc as po
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import fuzz_struct as fs
+    p = str(tmp_path / "i.orc")
+    po.write_table(pa.table({"a": pa.array(range(6000), pa.int64()), "b": pa.array([f"s{i % 50}" for i in range(6000)])}), p,
+                   compression="uncompressed", row_index_stride=1000, dictionary_key_size_threshold=0.8)
+    o = fs.Orc(open(p, "rb").read())
+    idx, _ = o.last_stripe_parts()
+    whole = ob.DecodeJob([o.build()]).plan().stats()
+    damaged = 0
+    for at in range(4, len(idx), 7):
+        bad = bytearray(idx)
+        bad[at] = 0x07  # wire type 7 does not exist
+        bad[at + 1] = 0xFF
+        data = o.build(index=bytes(bad))
+        st = ob.DecodeJob([data]).plan().stats()  # does not raise
+        assert st["n_rows"] == whole["n_rows"]
+        damaged += st["n_segments"] < whole["n_segments"]
+        keep = ob.predicate_row_groups(data, 0, ob.Predicate.eq("a", ob.PredicateValue.Int64(5)))
+        assert keep is None or len(keep) == 6
+    assert damaged > 3
