@@ -165,10 +165,14 @@ def pb_fields(b: bytes):
     while p < n:
         key, p = _pb_varint(b, p)
         fno, wt = key >> 3, key & 7
+        if fno == 0 or key >> 32:  # prost: "invalid tag value: 0" / "invalid key value"
+            raise OracleError(7, "invalid protobuf key")
         if wt == 0:
             v, p = _pb_varint(b, p)
         elif wt == 1:
             v = b[p:p + 8]
+            if len(v) != 8:
+                raise OracleError(7, "truncated fixed64 field")
             p += 8
         elif wt == 2:
             ln, p = _pb_varint(b, p)
@@ -178,6 +182,8 @@ def pb_fields(b: bytes):
             p += ln
         elif wt == 5:
             v = b[p:p + 4]
+            if len(v) != 4:
+                raise OracleError(7, "truncated fixed32 field")
             p += 4
         else:
             raise OracleError(7, f"wire type {wt}")
@@ -349,6 +355,9 @@ class OracleFile:
         if k in simple:
             return simple[k]
         if k == K_DECIMAL:
+            # arrow-rs validates the type when the array is built (array_decoder/decimal.rs:99): precision 1..=38, scale <= precision
+            if t.precision == 0 or t.precision > 38 or t.scale > t.precision:
+                raise OracleError(18, f"invalid Decimal128 precision / scale ({t.precision}, {t.scale})")
             return pa.decimal128(t.precision, t.scale)
         if k in (K_TIMESTAMP, K_TIMESTAMP_INSTANT) and ts_unit == "dec":
             return pa.decimal128(38, 9)  # with_schema: Decimal128(38, 9) nanoseconds (array_decoder/timestamp.rs:150-232)

@@ -19,6 +19,7 @@ class PbCursor {
     bool next(PbField& f) {
         if (p_ >= end_) return false;
         uint64_t key = varint();
+        if ((key >> 32) != 0 || (key >> 3) == 0) fail(ORCB_DECODE_PROTO, "invalid protobuf key");  // prost: key > u32, tag 0
         f.number = (uint32_t)(key >> 3);
         f.wire = (uint32_t)(key & 7);
         f.data = nullptr;
