@@ -160,6 +160,8 @@ def _pb_varint(b: bytes, p: int) -> Tuple[int, int]:
 
 
 def pb_fields(b: bytes):
+    if isinstance(b, int):  # a varint where a message is expected (prost: invalid wire type)
+        raise OracleError(7, "wire type of a message field")
     p = 0
     n = len(b)
     while p < n:

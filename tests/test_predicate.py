@@ -327,3 +327,53 @@ def test_reader_plan_with_byte_range_and_projection(ob, generated):
                [None if p is None else [tuple(map(int, v)) for v in p] for p in exp], proj
         if proj == ["s", "t"]:  # "Column 'l' not found in schema": select_all for every stripe
             assert all(p == [(0, r)] for p, r in zip(got, rows))
+
+
+def test_verdicts_on_edited_row_indexes_match_oracle(ob, tmp_path):
+    """Predicate pushdown over row indexes whose protobuf FIELDS were edited (tools/fuzz_struct.py: statistics with extreme
+    or missing values, positions, counts, duplicated / deleted / halved entries): the library and the oracle reach the same
+    verdict - the same row groups kept, or the same fall-back to reading the whole stripe (src/arrow_reader.rs:281-291).
+    Where the reference would panic (bucket statistics without a count, src/statistics.rs) the library reports
+    Unexpected."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tools"))
+    import fuzz_struct as fs
+    rng = random.Random(2)
+    files = []
+    for d in fs.seeds(str(tmp_path)):
+        try:
+            files.append(fs.Orc(d))
+        except AssertionError:
+            pass
+    same = fallbacks = pruned = panics = 0
+    for it in range(4000):
+        o = rng.choice(files)
+        idx, _sf = o.last_stripe_parts()
+        part = fs.as_message(idx)
+        if part is None or not fs.edit(part, rng):
+            continue
+        new = fs.rc.pb_build(part)
+        if it % 8 and len(new) != len(idx):
+            continue  # mostly edits that keep the index streams where the stripe footer says they are
+        data = o.build(index=new)
+        of = oo.OracleFile(data)
+        names = [n for n, _ in of.columns]
+        si = len(of.stripes) - 1
+        for _ in range(3):
+            c = rng.choice(names)
+            val = rng.choice([("Int64", rng.choice([0, 5, 1000, 10**6, -3])), ("Int32", rng.choice([0, 7, 50000])),
+                              ("Utf8", rng.choice(["a", "m", "w3", "zebra", ""])), ("Float64", rng.choice([0.0, 1.5, 1e9])), ("Boolean", True)])
+            pred = rng.choice([("cmp", c, rng.choice(list(OPS)), val), ("is_null", c), ("is_not_null", c),
+                               ("not", ("cmp", c, rng.choice(list(OPS)), val))])
+            try:
+                got = ob.predicate_row_groups(data, si, to_api(ob, pred))
+            except ob.OrcError as e:
+                assert e.variant == "Unexpected" and "index out of bounds" in str(e), (pred, str(e))
+                panics += 1
+                continue
+            exp = of.predicate_selection(si, pred, None)[1]
+            assert got == exp, (pred, got, exp)
+            same += 1
+            fallbacks += exp is None
+            pruned += exp is not None and not all(exp)
+    assert same > 1000 and fallbacks > 20 and pruned > 40, (same, fallbacks, pruned, panics)
