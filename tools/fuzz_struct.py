@@ -162,6 +162,12 @@ def seeds(tmp):
         p = os.path.join(tmp, f"fs_{name}.orc")
         po.write_table(t, p, compression="uncompressed", stripe_size=64 << 10, row_index_stride=1000, dictionary_key_size_threshold=0.8)
         out.append(open(p, "rb").read())
+    # Bloom filters (with_predicate reads them for equality): integer and string columns
+    t = pa.table({"k": pa.array([(i * 7919) % 100_000 for i in range(6000)], pa.int64()), "w": pa.array([f"w{(i * 31) % 977}" for i in range(6000)])})
+    p = os.path.join(tmp, "fs_bloom.orc")
+    po.write_table(t, p, compression="uncompressed", row_index_stride=1000, bloom_filter_columns=[0, 1], bloom_filter_fpp=0.05,
+                   dictionary_key_size_threshold=0.0)
+    out.append(open(p, "rb").read())
     for f in ("tests/golden/ref_basic/test.orc", "tests/golden/ref_basic/alltypes.none.orc"):
         d = open(os.path.join(ROOT, f), "rb").read()
         out.append(d)
