@@ -1,6 +1,6 @@
 """Structure-aware companion of tools/fuzz_host.sh: instead of overwriting bytes it edits protobuf FIELDS of an
-uncompressed ORC file - the file footer, the last stripe's footer and its row-index streams - and rebuilds the file around
-the edit (section lengths in the footer / postscript follow), so every input still frames correctly and the edit reaches
+ORC file - the file footer, the last stripe's footer and its row-index streams - and rebuilds the file around
+the edit (section lengths in the footer / postscript follow; sections of compressed files are stored back as original chunks), so every input still frames correctly and the edit reaches
 the code behind the parser: a stream length of 2^63, a dictionary size of 2^32-1, a row-index position past the stream,
 a stripe of 2^60 rows, a stride of 0, a duplicated or missing stream ...  Each input goes through open, schema, planning
 with and without the row index, predicate evaluation and a reader with a selection.  Run it on the sanitizer build:
@@ -75,17 +75,35 @@ def edit(fields, rng, depth=0):
 
 
 class Orc:
-    """An uncompressed file cut into the pieces this fuzzer rebuilds."""
+    """A file cut into the pieces this fuzzer rebuilds.  Compressed files too: a metadata section is decompressed, edited
+    and stored back as "original" chunks (header bit 0 set), which every compression kind allows; their row-index area is
+    a run of separately framed streams and is left alone."""
+
+    def unframe(self, raw: bytes) -> bytes:
+        if self.kind == 0:
+            return bytes(raw)
+        from oracle import orc_oracle as oo
+        return bytes(oo.decompress_stream(self.kind, bytes(raw), self.block))
+
+    def frame(self, b: bytes) -> bytes:
+        if self.kind == 0:
+            return b
+        out = bytearray()
+        for p in range(0, len(b), self.block):
+            c = b[p:p + self.block]
+            out += ((len(c) << 1) | 1).to_bytes(3, "little") + c
+        return bytes(out)
 
     def __init__(self, data: bytes):
         self.data = data
         n = len(data)
         self.ps_len = data[-1]
         self.ps = rc.pb_parse(data[n - 1 - self.ps_len:n - 1])
-        assert rc.pb_get(self.ps, 2, 0) == 0, "uncompressed files only"
+        self.kind = rc.pb_get(self.ps, 2, 0)
+        self.block = rc.pb_get(self.ps, 3, 256 << 10)
         self.fl = rc.pb_get(self.ps, 1)
         self.ml = rc.pb_get(self.ps, 5, 0)
-        self.footer = rc.pb_parse(data[n - 1 - self.ps_len - self.fl:n - 1 - self.ps_len])
+        self.footer = rc.pb_parse(self.unframe(data[n - 1 - self.ps_len - self.fl:n - 1 - self.ps_len]))
         self.meta = data[n - 1 - self.ps_len - self.fl - self.ml:n - 1 - self.ps_len - self.fl]
         self.stripes = [rc.pb_parse(f[2]) for f in self.footer if f[0] == 3]
         self.body_end = n - 1 - self.ps_len - self.fl - self.ml
@@ -98,7 +116,7 @@ class Orc:
             si = {g[0]: g[2] for g in self.stripes[-1]}
             off, il, dl, sfl = si.get(1, 0), si.get(2, 0), si.get(3, 0), si.get(4, 0)
             idx = index if index is not None else body[off:off + il]
-            sf = stripe_footer if stripe_footer is not None else body[off + il + dl:off + il + dl + sfl]
+            sf = self.frame(stripe_footer) if stripe_footer is not None else body[off + il + dl:off + il + dl + sfl]
             body = body[:off] + idx + body[off + il:off + il + dl] + sf
             k = [i for i, f in enumerate(footer) if f[0] == 3][-1]
             s = rc.pb_parse(footer[k][2])
@@ -108,7 +126,7 @@ class Orc:
                 if g[0] == 4:
                     g[2] = len(sf)
             footer[k][2] = rc.pb_build(s)
-        nf = rc.pb_build(footer)
+        nf = self.frame(rc.pb_build(footer))
         ps = [list(f) for f in self.ps]
         for f in ps:
             if f[0] == 1:
@@ -119,7 +137,7 @@ class Orc:
     def last_stripe_parts(self):
         si = {g[0]: g[2] for g in self.stripes[-1]}
         off, il, dl, sfl = si.get(1, 0), si.get(2, 0), si.get(3, 0), si.get(4, 0)
-        return self.data[off:off + il], self.data[off + il + dl:off + il + dl + sfl]
+        return self.data[off:off + il], self.unframe(self.data[off + il + dl:off + il + dl + sfl])
 
 
 def exercise(ob, data: bytes):
@@ -162,6 +180,16 @@ def seeds(tmp):
         p = os.path.join(tmp, f"fs_{name}.orc")
         po.write_table(t, p, compression="uncompressed", stripe_size=64 << 10, row_index_stride=1000, dictionary_key_size_threshold=0.8)
         out.append(open(p, "rb").read())
+    for comp in ("snappy", "zlib", "zstd"):  # compressed files: chunk tables, (chunk start, offset in chunk) positions
+        p = os.path.join(tmp, f"fs_lineitem_{comp}.orc")
+        po.write_table(tables["lineitem"], p, compression=comp, stripe_size=64 << 10, row_index_stride=1000, compression_block_size=64 << 10,
+                       dictionary_key_size_threshold=0.8)
+        out.append(open(p, "rb").read())
+    import orc_recompress
+    for kind in ("lz4", "lzo"):
+        p = os.path.join(tmp, f"fs_nullheavy_{kind}.orc")
+        orc_recompress.recompress(os.path.join(tmp, "fs_nullheavy.orc"), p, kind, 16 << 10)
+        out.append(open(p, "rb").read())
     # Bloom filters (with_predicate reads them for equality): integer and string columns
     t = pa.table({"k": pa.array([(i * 7919) % 100_000 for i in range(6000)], pa.int64()), "w": pa.array([f"w{(i * 31) % 977}" for i in range(6000)])})
     p = os.path.join(tmp, "fs_bloom.orc")
@@ -195,6 +223,8 @@ def main():
         for it in range(iters):
             o = rng.choice(files)
             target = rng.choice(("footer", "footer", "stripe_footer", "stripe_footer", "index"))
+            if target == "index" and o.kind != 0:
+                target = "stripe_footer"
             if target == "footer":
                 f = [list(x) for x in o.footer]
                 if not edit(f, rng):
