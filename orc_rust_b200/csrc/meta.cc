@@ -462,9 +462,14 @@ const uint8_t* FileMeta::base_for(uint64_t off) const {
     if (!source) return data;
     if (tail && off >= tail->off && off <= tail->off + tail->len) return tail->p - tail->off;
     std::lock_guard<std::mutex> lock(source->mu);
-    for (auto& w : source->live) {
-        std::shared_ptr<RangeBuf> r = w.lock();
-        if (r && r->off <= off && off <= r->off + r->len) return r->p - r->off;
+    // A range that holds the byte at `off` first; one that merely ENDS there only when nothing else matches (an empty
+    // read at the end of a range).  Ranges of consecutive stripes touch: the data area of a stripe without an index area
+    // starts exactly where the range of the stripe before it ends, and must not be looked up in that one.
+    for (int pass = 0; pass < 2; pass++) {
+        for (auto& w : source->live) {
+            std::shared_ptr<RangeBuf> r = w.lock();
+            if (r && r->off <= off && (pass == 0 ? off < r->off + r->len : off <= r->off + r->len)) return r->p - r->off;
+        }
     }
     fail(ORCB_UNEXPECTED, "file bytes at offset " + std::to_string(off) + " are not loaded");
 }

@@ -865,3 +865,33 @@ def test_unparsable_row_index_does_not_fail_the_plan(ob, tmp_path):
         keep = ob.predicate_row_groups(data, 0, ob.Predicate.eq("a", ob.PredicateValue.Int64(5)))
         assert keep is None or len(keep) == 6
     assert damaged > 3
+
+
+def test_callback_feed_on_stripes_without_an_index_area(ob):
+    """Regression (found by tools/fuzz_host.sh under AddressSanitizer): the per-stripe ranges a callback-fed file keeps in
+    memory touch each other, and a stripe without an index area starts its data exactly where the range of the stripe
+    before it ends - the lookup of "the loaded range that holds this offset" took the range that merely ended there, so
+    the stripe footer (and the staged data) of every stripe but the first came from beyond the wrong buffer:
+    TestOrcFile.testWithoutIndex.orc failed to plan through a ChunkReader.  Every multi-stripe fixture plans through
+    callbacks exactly as it does from memory, with one read per stripe outside the tail."""
+    import glob
+    checked = no_index = 0
+    for p in sorted(glob.glob(os.path.join(GOLDEN, "ref_*", "*.orc"))):
+        try:
+            f = ob._File(p)
+        except ob.OrcError:
+            continue
+        if f.num_stripes < 2:
+            continue
+        try:
+            want = ob.DecodeJob([f]).plan().stats()
+        except ob.OrcError:
+            continue
+        cr = ob.FileChunkReader(p)
+        got = ob.DecodeJob([ob._File(cr)]).plan().stats()
+        for k in ("n_stripes", "n_rows", "n_segments", "input_bytes", "staged_bytes", "n_batches"):
+            assert got[k] == want[k], (os.path.basename(p), k)
+        assert len(cr.calls) <= f.num_stripes + 2
+        checked += 1
+        no_index += any(f.stripe_info(i)["index_length"] == 0 for i in range(f.num_stripes))
+    assert checked >= 8 and no_index >= 3
