@@ -76,3 +76,20 @@ def test_gpu_against_reference_basic_tests(name):
             list(reader)
         return
     _check(name, spec, list(reader), reader.schema(), total)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["TestOrcFile.testWithoutIndex.orc", "TestOrcFile.testMemoryManagementV11.orc",
+                                  "TestOrcFile.testMemoryManagementV12.orc"])
+def test_gpu_callback_feed_without_index_area(name):
+    """Multi-stripe files whose stripes have no index area, seen only through a ChunkReader: the data area of stripe k+1
+    starts where the loaded range of stripe k ends (see tests/test_cabi_host.py::
+    test_callback_feed_on_stripes_without_an_index_area); the batches are the oracle's, byte for byte."""
+    import orc_rust_b200 as ob
+    from oracle import orc_oracle as oo
+    from parity_util import assert_batches_identical
+    assert ob.device_available(), "no CUDA device: the product path has no CPU fallback"
+    path = os.path.join(GOLDEN, "ref_integration", name)
+    exp = oo.OracleFile(open(path, "rb").read()).read()
+    got = list(ob.ArrowReaderBuilder.try_new(ob.FileChunkReader(path)).build())
+    assert_batches_identical(got, exp, name)
