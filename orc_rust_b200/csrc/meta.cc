@@ -408,6 +408,7 @@ RangeBuf::~RangeBuf() {
 
 std::shared_ptr<RangeBuf> FileMeta::load_range(uint64_t off, uint64_t n) const {
     if (!source) return nullptr;
+    if (off > len || n > len - off) fail(ORCB_IO_ERROR, "read beyond the end of the file");  // (before off + n is formed)
     {
         std::lock_guard<std::mutex> lock(source->mu);
         auto& v = source->live;
@@ -422,7 +423,6 @@ std::shared_ptr<RangeBuf> FileMeta::load_range(uint64_t off, uint64_t n) const {
             i++;
         }
     }
-    if (off > len || n > len - off) fail(ORCB_IO_ERROR, "read beyond the end of the file");
     auto r = std::make_shared<RangeBuf>();
     r->off = off;
     r->len = n;
