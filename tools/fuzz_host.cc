@@ -164,7 +164,8 @@ static void one_file(const std::vector<uint8_t>& bytes) {
         ok = false;
     }
     orcb_file_free(f);
-    if (below(4) == 0) one_file_callbacks(heap, bytes.size());
+    static const bool always_cb = getenv("ORCB_FUZZ_CALLBACKS") != nullptr;  // every input through the callback feed as well
+    if (always_cb || below(4) == 0) one_file_callbacks(heap, bytes.size());
     free(heap);
     (ok ? n_ok : n_err)++;
 }
