@@ -458,18 +458,17 @@ std::shared_ptr<RangeBuf> FileMeta::load_stripe(uint32_t stripe) const {
     return load_range(si.offset, si.index_length + si.data_length + si.footer_length);
 }
 
-const uint8_t* FileMeta::base_for(uint64_t off) const {
+const uint8_t* FileMeta::base_for(uint64_t off, uint64_t need) const {
     if (!source) return data;
-    if (tail && off >= tail->off && off <= tail->off + tail->len) return tail->p - tail->off;
+    // The loaded range must hold the whole extent.  Ranges of consecutive stripes touch (the data area of a stripe
+    // without an index area starts exactly where the range of the stripe before it ends) and, in a damaged file, stripes
+    // may overlap: a range that merely ends at `off`, or ends inside the extent, is not the one to read from.
+    auto holds = [&](const RangeBuf& r) { return r.off <= off && off - r.off <= r.len && need <= r.len - (off - r.off); };
+    if (tail && holds(*tail)) return tail->p - tail->off;
     std::lock_guard<std::mutex> lock(source->mu);
-    // A range that holds the byte at `off` first; one that merely ENDS there only when nothing else matches (an empty
-    // read at the end of a range).  Ranges of consecutive stripes touch: the data area of a stripe without an index area
-    // starts exactly where the range of the stripe before it ends, and must not be looked up in that one.
-    for (int pass = 0; pass < 2; pass++) {
-        for (auto& w : source->live) {
-            std::shared_ptr<RangeBuf> r = w.lock();
-            if (r && r->off <= off && (pass == 0 ? off < r->off + r->len : off <= r->off + r->len)) return r->p - r->off;
-        }
+    for (auto& w : source->live) {
+        std::shared_ptr<RangeBuf> r = w.lock();
+        if (r && holds(*r)) return r->p - r->off;
     }
     fail(ORCB_UNEXPECTED, "file bytes at offset " + std::to_string(off) + " are not loaded");
 }
@@ -614,7 +613,7 @@ void parse_file_tail(FileMeta& fm) {
 StripeFooter FileMeta::read_stripe_footer(uint32_t stripe) const {
     const StripeInfo& si = stripes.at(stripe);
     uint64_t off = si.offset + si.index_length + si.data_length;
-    std::vector<uint8_t> raw = host_decompress_section(compression, block_size, base_for(off) + off, si.footer_length);
+    std::vector<uint8_t> raw = host_decompress_section(compression, block_size, base_for(off, si.footer_length) + off, si.footer_length);
     StripeFooter sf;
     PbCursor c(raw.data(), raw.size());
     PbField f;
@@ -657,7 +656,7 @@ std::vector<std::vector<uint64_t>> FileMeta::read_row_index(const StripeInfo& si
     std::vector<std::vector<uint64_t>> out;
     const StreamInfo* st = sf.find(column, S_ROW_INDEX);
     if (!st || st->length == 0) return out;
-    std::vector<uint8_t> raw = host_decompress_section(compression, block_size, base_for(st->offset) + st->offset, st->length);
+    std::vector<uint8_t> raw = host_decompress_section(compression, block_size, base_for(st->offset, st->length) + st->offset, st->length);
     PbCursor c(raw.data(), raw.size());
     PbField f;
     while (c.next(f)) {
@@ -805,7 +804,7 @@ std::vector<RowGroupEntry> FileMeta::read_row_group_entries(const StripeFooter& 
     *present = st != nullptr;
     if (!st) return out;
     {
-        std::vector<uint8_t> raw = host_decompress_section(compression, block_size, base_for(st->offset) + st->offset, st->length);
+        std::vector<uint8_t> raw = host_decompress_section(compression, block_size, base_for(st->offset, st->length) + st->offset, st->length);
         PbCursor c(raw.data(), raw.size());
         PbField f, g;
         while (c.next(f)) {
@@ -826,7 +825,7 @@ std::vector<RowGroupEntry> FileMeta::read_row_group_entries(const StripeFooter& 
     const StreamInfo* bs = sf.find(column, S_BLOOM_FILTER);
     if (!bs) bs = sf.find(column, S_BLOOM_FILTER_UTF8);
     if (!bs) return out;
-    std::vector<uint8_t> raw = host_decompress_section(compression, block_size, base_for(bs->offset) + bs->offset, bs->length);
+    std::vector<uint8_t> raw = host_decompress_section(compression, block_size, base_for(bs->offset, bs->length) + bs->offset, bs->length);
     std::vector<BloomBits> filters;
     PbCursor c(raw.data(), raw.size());
     PbField f, g;
@@ -882,7 +881,7 @@ std::vector<RowGroupEntry> FileMeta::read_row_group_entries(const StripeFooter& 
 // src/compression.rs:244-275 — header walk only
 std::vector<ChunkInfo> FileMeta::chunk_table(uint64_t stream_off, uint64_t stream_len) const {
     std::vector<ChunkInfo> out;
-    const uint8_t* s = base_for(stream_off) + stream_off;
+    const uint8_t* s = base_for(stream_off, stream_len) + stream_off;
     uint64_t p = 0;
     while (p < stream_len) {
         if (p + 3 > stream_len) fail(ORCB_OUT_OF_SPEC, "truncated compression chunk header");

@@ -124,7 +124,8 @@ struct FileMeta {
     std::shared_ptr<RangeBuf> tail;   // footer + metadata + postscript
     // Pointer q such that q[off] is the file's byte at offset `off`.  Memory files: `data`.  Callback files: the range
     // that holds `off` must be alive (load_stripe / the tail), else Unexpected.
-    const uint8_t* base_for(uint64_t off) const;
+    // base pointer (indexable by file offset) of loaded bytes that hold [off, off + need)
+    const uint8_t* base_for(uint64_t off, uint64_t need = 1) const;
     // the stripe's bytes (index, data, footer) in one read; null for memory files
     std::shared_ptr<RangeBuf> load_stripe(uint32_t stripe) const;
     std::shared_ptr<RangeBuf> load_range(uint64_t off, uint64_t len) const;

@@ -264,7 +264,7 @@ void Job::plan_stripe(uint32_t task_idx) {
             in_off = it->second;
         } else {
             in_off = alloc(AR_IN, si.data_length);
-            stage_copies_.push_back({fm.base_for(data_start) + data_start, in_off & ((1ull << 60) - 1), si.data_length});
+            stage_copies_.push_back({fm.base_for(data_start, si.data_length) + data_start, in_off & ((1ull << 60) - 1), si.data_length});
             staged_stripes_[key] = in_off;
         }
     }
@@ -636,7 +636,7 @@ void Job::plan_stripe(uint32_t task_idx) {
             // the stream's bytes as the host sees them (for the scheduling hint below)
             const uint8_t* sp = nullptr;
             if (v2 && sr.present)
-                sp = fm.base_for(data_start) + (sf.find(cid, &sr == &s_data ? S_DATA : (&sr == &s_length ? S_LENGTH : S_SECONDARY))->offset);
+                sp = fm.base_for(data_start, si.data_length) + (sf.find(cid, &sr == &s_data ? S_DATA : (&sr == &s_length ? S_LENGTH : S_SECONDARY))->offset);
             // (every look is a cache miss in a file of hundreds of MB: have them all in flight before the loop needs them)
             if (sp && !compressed)
                 for (uint32_t g = 0; g < ng; g++) __builtin_prefetch(sp + std::min(en[g].byte, sr.len));

@@ -89,6 +89,25 @@ static void one_file_callbacks(const uint8_t* heap, size_t n) {
         orcb_reader_plan(r, applies, 16, &ns, triples, 64, &nt);
         orcb_reader_free(r);
     }
+    // with_predicate on the callback-fed file: index areas and stripe footers are read on their own, then whole stripes
+    if (const char* name = orcb_file_root_column_name(f, 0)) {
+        OrcbPredicateNode node;
+        memset(&node, 0, sizeof node);
+        node.kind = ORCB_PRED_COMPARISON, node.op = ORCB_OP_GE, node.value_type = ORCB_VAL_INT64, node.i64 = 0, node.column = name;
+        OrcbReaderBuild rb;
+        memset(&rb, 0, sizeof rb);
+        rb.options = &opt;
+        rb.predicate = &node;
+        rb.n_predicate_nodes = 1;
+        OrcbReader* pr = nullptr;
+        if (orcb_reader_build(f, &rb, &pr) == 0) {
+            int32_t applies[16];
+            uint64_t triples[3 * 64];
+            size_t ns = 0, nt = 0;
+            orcb_reader_plan(pr, applies, 16, &ns, triples, 64, &nt);
+            orcb_reader_free(pr);
+        }
+    }
     OrcbJob* j = nullptr;
     OrcbFile* files[1] = {f};
     if (orcb_job_new(files, 1, &opt, &j) == 0) {
